@@ -1,0 +1,58 @@
+"""Pins the CPU oracle against the reference's own golden vectors: the gold PNGs of
+tests/image-gold-tests.sh.  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from galaxy_b200 import scenes
+from oracle import oracle
+
+# (state, camera index) -> minimum fraction of pixels within 1/255 of the gold, per channel.
+# 9 of 11 reproduce the gold on >= 99.9 % of pixels with the reference's CURRENT source order.
+# nineBalls_0/_1 reach 99.78 / 99.82 %: their golds were produced by a build that integrated the
+# DVR interval before searching it for an iso crossing (proved by test_ninballs_gold_provenance).
+GOLDS = [("infinite", 0, 0.999), ("infinite-shadow", 0, 0.999), ("absolute", 0, 0.999), ("absolute-shadow", 0, 0.999),
+         ("camera", 0, 0.999), ("camera-shadow", 0, 0.999), ("xyz", 0, 0.999), ("oneBall", 0, 0.999),
+         ("nineBalls", 0, 0.997), ("nineBalls", 1, 0.998), ("nineBalls", 2, 0.999)]
+
+
+def render_oracle(golden_dir, provider, name, cam_idx, size=512):
+    st = scenes.parse_state(json.load(open(os.path.join(golden_dir, "states", name + ".state"))))
+    ds = scenes.load_datasets(st, provider)
+    vis, cam = st["visualizations"][0], st["cameras"][cam_idx]
+    parts = scenes.build_partitions(oracle, vis, ds, 1)
+    fb, stats = oracle.render(parts, cam, vis["lighting"], size, size, st["epsilon"])
+    return oracle.fb_to_rgba8(fb), stats
+
+
+def gold_fraction(golden_dir, img, name, cam_idx):
+    gold = np.asarray(Image.open(os.path.join(golden_dir, "golds", "%s_%05d.png" % (name, cam_idx))).convert("RGBA"))
+    assert gold.shape == img.shape
+    diff = np.abs(img[..., :3].astype(int) - gold[..., :3].astype(int)).max(-1)
+    return float((diff <= 1).mean())
+
+
+@pytest.mark.parametrize("name,cam_idx,min_frac", GOLDS)
+def test_oracle_matches_gold(golden_dir, provider, name, cam_idx, min_frac):
+    img, stats = render_oracle(golden_dir, provider, name, cam_idx)
+    frac = gold_fraction(golden_dir, img, name, cam_idx)
+    print(name, cam_idx, "fraction within 1/255:", frac, stats)
+    assert frac >= min_frac
+    assert (img[..., 3] == 255).all()
+    assert stats["orphan_pixels"] == 0
+
+
+def test_nineballs_gold_provenance(golden_dir, provider):
+    """With the DVR interval integrated BEFORE the iso search (diagnostic switch), all three
+    nineBalls golds are reproduced on >= 99.99 % of pixels: evidence that those golds predate the
+    reference's current TraceRays.ispc:483-506 ordering."""
+    oracle.lib().gxo_set_option(b"dvr_before_iso", 1)
+    try:
+        for cam_idx in range(3):
+            img, _ = render_oracle(golden_dir, provider, "nineBalls", cam_idx)
+            assert gold_fraction(golden_dir, img, "nineBalls", cam_idx) >= 0.9999
+    finally:
+        oracle.lib().gxo_set_option(b"dvr_before_iso", 0)
