@@ -1,0 +1,1077 @@
+// gxy_api.cu -- the C ABI of include/gxy_gpu.h: handles, commit, the per-RayList entry points
+// (TraceRays::Trace, Classify, SpawnRays) and the frame-level wave loop that replaces
+// Renderer::local_render / processRays_task / RayQManager / SendRaysMsg / SendPixelsMsg
+// (src/renderer/Renderer.cpp:179-269,504-656,732-836; Rendering.cpp:125-153) on the device.
+#include "gxy_internal.h"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace gxy;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_error[1024] = "";
+void gxy_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof g_error, fmt, ap);
+  va_end(ap);
+}
+#define GXY_CHECK(cond, ...)          \
+  do {                                \
+    if (!(cond)) {                    \
+      gxy_set_error(__VA_ARGS__);     \
+      return 1;                       \
+    }                                 \
+  } while (0)
+
+// ---- NCCL through dlopen (no link-time dependency; the single-GPU path never touches it) ---------
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+  if (g_nccl.lib) return 0;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *nm : names) {
+    g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  GXY_CHECK(g_nccl.lib, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define LOADSYM(field, name)                                        \
+  *(void **)(&g_nccl.field) = dlsym(g_nccl.lib, name);              \
+  GXY_CHECK(g_nccl.field, "libnccl: missing symbol %s", name);
+  LOADSYM(GetUniqueId, "ncclGetUniqueId")
+  LOADSYM(CommInitRank, "ncclCommInitRank")
+  LOADSYM(CommDestroy, "ncclCommDestroy")
+  LOADSYM(Send, "ncclSend")
+  LOADSYM(Recv, "ncclRecv")
+  LOADSYM(AllGather, "ncclAllGather")
+  LOADSYM(Reduce, "ncclReduce")
+  LOADSYM(GroupStart, "ncclGroupStart")
+  LOADSYM(GroupEnd, "ncclGroupEnd")
+  LOADSYM(GetErrorString, "ncclGetErrorString")
+#undef LOADSYM
+  return 0;
+}
+#define GXY_NCCL(call)                                                                              \
+  do {                                                                                              \
+    ncclResult_t r_ = (call);                                                                       \
+    if (r_ != ncclSuccess) {                                                                        \
+      gxy_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_));  \
+      return 1;                                                                                     \
+    }                                                                                               \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+struct gxy_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+};
+
+struct gxy_volume {
+  gxy_context *ctx;
+  DevVolume dv;
+  void *d_vox;
+  int last_tf;
+};
+struct gxy_triangles {
+  gxy_context *ctx;
+  int nv, nt;
+  float *d_verts, *d_normals, *d_data;
+  int *d_idx;
+};
+struct gxy_particles {
+  gxy_context *ctx;
+  int n;
+  float *d_centers, *d_data;
+};
+struct gxy_raylist {
+  float *base;
+  int n, aligned_n;
+};
+
+// growable device ray list
+struct RayBuf {
+  float *base = nullptr;
+  size_t cap = 0;
+  Rays v;
+  int reserve(size_t n, bool keep, cudaStream_t st) {
+    if (n <= cap) return 0;
+    size_t ncap = std::max(n, cap + cap / 2);
+    ncap = (ncap + 63) & ~(size_t)63;
+    float *nb = nullptr;
+    GXY_CUDA(cudaMalloc(&nb, sizeof(float) * GXY_RAYLIST_COLUMNS * ncap));
+    if (keep && base && cap) {
+      GXY_CUDA(cudaMemcpy2DAsync(nb, ncap * 4, base, cap * 4, cap * 4, GXY_RAYLIST_COLUMNS, cudaMemcpyDeviceToDevice, st));
+      GXY_CUDA(cudaStreamSynchronize(st));
+    }
+    if (base) cudaFree(base);
+    base = nb;
+    cap = ncap;
+    v = rays_view(base, cap);
+    return 0;
+  }
+  void release() {
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = 0;
+  }
+};
+
+template <typename T>
+struct Scratch {
+  T *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n) {
+    if (n <= cap) return 0;
+    if (p) cudaFree(p);
+    cap = (n + n / 4 + 255) & ~(size_t)255;
+    GXY_CUDA(cudaMalloc(&p, sizeof(T) * cap));
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct VolOp {
+  gxy_volume *vol;
+  std::vector<float> slices, iso;
+  int volume_render;
+  gxy_transfer_function tf;
+};
+struct GeomOp {
+  int kind;
+  gxy_triangles *tri;
+  gxy_particles *par;
+  float radius0, radius1, value0, value1;
+  gxy_transfer_function tf;
+};
+
+struct gxy_vis {
+  gxy_context *ctx;
+  float gmin[3], gmax[3], lmin[3], lmax[3];
+  int neighbors[6];
+  std::vector<VolOp> vols;
+  std::vector<GeomOp> geoms;
+  bool committed = false;
+  SceneParams P;
+  DevTF *d_tfs = nullptr;
+  DevGeom *d_geoms = nullptr;
+  int *d_error = nullptr;
+  BvhResult bvh;
+  bool has_dvr = false;
+  // work buffers
+  RayBuf cur, next, send, recv;
+  Scratch<int> hit_index, block_sums, small;  // small: nhit, counts, offsets, cursor ...
+  Scratch<unsigned long long> counters;       // [0] terminated [1] samples
+  Scratch<float> fb, fb_tmp;
+  Scratch<unsigned char> rgba8;
+  Scratch<float> io_f;
+  Scratch<int> io_i;
+  int fb_w = 0, fb_h = 0;
+};
+
+static int use_device(gxy_context *c) {
+  GXY_CUDA(cudaSetDevice(c->device));
+  return 0;
+}
+
+template <typename T>
+static int upload(T **dst, const T *src, size_t n) {
+  *dst = nullptr;
+  if (!src || !n) return 0;
+  GXY_CUDA(cudaMalloc(dst, sizeof(T) * n));
+  GXY_CUDA(cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *gxy_last_error(void) { return g_error; }
+const char *gxy_version(void) { return "galaxy_b200 0.1 (sm_100a)"; }
+
+int gxy_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int gxy_context_create(int device, gxy_context **out) {
+  int n = gxy_device_count();
+  GXY_CHECK(n > 0, "no CUDA device available: galaxy_b200 has no CPU fallback");
+  GXY_CHECK(device >= 0 && device < n, "invalid device %d (have %d)", device, n);
+  GXY_CUDA(cudaSetDevice(device));
+  gxy_context *c = new gxy_context();
+  c->device = device;
+  GXY_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = c;
+  return 0;
+}
+void gxy_context_destroy(gxy_context *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+int gxy_context_synchronize(gxy_context *c) {
+  if (use_device(c)) return 1;
+  GXY_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- datasets --------------------------------------------------------------------------------
+int gxy_volume_create(gxy_context *c, const int dims[3], const float origin[3], const float spacing[3], int type, const void *voxels,
+                      gxy_volume **out) {
+  if (use_device(c)) return 1;
+  GXY_CHECK(type == 0 || type == 1, "volume type must be 0 (float) or 1 (uchar)");
+  GXY_CHECK(dims[0] >= 2 && dims[1] >= 2 && dims[2] >= 2, "volume dims must be >= 2");
+  gxy_volume *v = new gxy_volume();
+  v->ctx = c;
+  v->last_tf = -1;
+  DevVolume &d = v->dv;
+  for (int k = 0; k < 3; k++) d.dims[k] = dims[k];
+  d.type = type;
+  d.origin = make_float3(origin[0], origin[1], origin[2]);
+  d.spacing = make_float3(spacing[0], spacing[1], spacing[2]);
+  d.rcp = make_float3(1.0f / spacing[0], 1.0f / spacing[1], 1.0f / spacing[2]);  // rcp(gridSpacing), StructuredVolume.ispc:208-211
+  d.upper = make_float3(nextafterf((float)(dims[0] - 1), 0.f), nextafterf((float)(dims[1] - 1), 0.f),
+                        nextafterf((float)(dims[2] - 1), 0.f));                    // StructuredVolume.ispc:223
+  d.samplingStep = fminf(fminf(spacing[0], spacing[1]), spacing[2]);              // StructuredVolume.ispc:250
+  d.samplingRate = 1.0f;                                                          // OsprayVolume.cpp:45
+  d.nx = (unsigned long long)dims[0];
+  d.nxy = (unsigned long long)dims[0] * dims[1];
+  d.tf = 0;
+  d.pad = 0;
+  const size_t bytes = (size_t)dims[0] * dims[1] * dims[2] * (type == 0 ? 4 : 1);
+  if (cudaMalloc(&v->d_vox, bytes) != cudaSuccess) { delete v; gxy_set_error("cudaMalloc(%zu) failed for volume", bytes); return 1; }
+  GXY_CUDA(cudaMemcpy(v->d_vox, voxels, bytes, cudaMemcpyHostToDevice));
+  d.vox = v->d_vox;
+  *out = v;
+  return 0;
+}
+void gxy_volume_destroy(gxy_volume *v) {
+  if (!v) return;
+  cudaSetDevice(v->ctx->device);
+  cudaFree(v->d_vox);
+  delete v;
+}
+
+int gxy_triangles_create(gxy_context *c, int nv, const float *verts, const float *normals, const float *data, int nt, const int *indices,
+                         gxy_triangles **out) {
+  if (use_device(c)) return 1;
+  GXY_CHECK(nv >= 0 && nt >= 0 && (nt == 0 || (verts && indices)), "triangle mesh needs vertices and indices");
+  gxy_triangles *t = new gxy_triangles();
+  t->ctx = c; t->nv = nv; t->nt = nt;
+  if (upload(&t->d_verts, verts, (size_t)nv * 3) || upload(&t->d_normals, normals, (size_t)nv * 3) || upload(&t->d_data, data, (size_t)nv) ||
+      upload(&t->d_idx, indices, (size_t)nt * 3)) {
+    delete t;
+    return 1;
+  }
+  *out = t;
+  return 0;
+}
+void gxy_triangles_destroy(gxy_triangles *t) {
+  if (!t) return;
+  cudaSetDevice(t->ctx->device);
+  cudaFree(t->d_verts); cudaFree(t->d_normals); cudaFree(t->d_data); cudaFree(t->d_idx);
+  delete t;
+}
+
+int gxy_particles_create(gxy_context *c, int n, const float *centers, const float *data, gxy_particles **out) {
+  if (use_device(c)) return 1;
+  GXY_CHECK(n >= 0 && (n == 0 || centers), "particles need centres");
+  gxy_particles *p = new gxy_particles();
+  p->ctx = c; p->n = n;
+  if (upload(&p->d_centers, centers, (size_t)n * 3) || upload(&p->d_data, data, (size_t)n)) { delete p; return 1; }
+  *out = p;
+  return 0;
+}
+void gxy_particles_destroy(gxy_particles *p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  cudaFree(p->d_centers); cudaFree(p->d_data);
+  delete p;
+}
+
+// ---- Visualization -----------------------------------------------------------------------------
+int gxy_vis_create(gxy_context *c, gxy_vis **out) {
+  if (use_device(c)) return 1;
+  gxy_vis *v = new gxy_vis();
+  v->ctx = c;
+  for (int k = 0; k < 3; k++) v->gmin[k] = v->gmax[k] = v->lmin[k] = v->lmax[k] = 0.f;
+  for (int k = 0; k < 6; k++) v->neighbors[k] = -1;
+  memset(&v->P, 0, sizeof v->P);
+  *out = v;
+  return 0;
+}
+
+static void vis_free_commit(gxy_vis *v) {
+  if (v->d_tfs) cudaFree(v->d_tfs);
+  if (v->d_geoms) cudaFree(v->d_geoms);
+  if (v->d_error) cudaFree(v->d_error);
+  if (v->bvh.nodes) cudaFree(v->bvh.nodes);
+  if (v->bvh.prims) cudaFree(v->bvh.prims);
+  v->d_tfs = nullptr; v->d_geoms = nullptr; v->d_error = nullptr;
+  v->bvh = BvhResult();
+  v->committed = false;
+}
+
+void gxy_vis_destroy(gxy_vis *v) {
+  if (!v) return;
+  cudaSetDevice(v->ctx->device);
+  vis_free_commit(v);
+  v->cur.release(); v->next.release(); v->send.release(); v->recv.release();
+  v->hit_index.release(); v->block_sums.release(); v->small.release(); v->counters.release();
+  v->fb.release(); v->fb_tmp.release(); v->rgba8.release(); v->io_f.release(); v->io_i.release();
+  delete v;
+}
+
+int gxy_vis_set_partition(gxy_vis *v, const float gmin[3], const float gmax[3], const float lmin[3], const float lmax[3],
+                          const int neighbors[6]) {
+  for (int k = 0; k < 3; k++) { v->gmin[k] = gmin[k]; v->gmax[k] = gmax[k]; v->lmin[k] = lmin[k]; v->lmax[k] = lmax[k]; }
+  for (int k = 0; k < 6; k++) v->neighbors[k] = neighbors[k];
+  v->committed = false;
+  return 0;
+}
+
+int gxy_vis_add_volume(gxy_vis *v, gxy_volume *vol, int n_slices, const float *slices4, int n_iso, const float *isovalues, int volume_render,
+                       const gxy_transfer_function *tf) {
+  GXY_CHECK(vol && tf, "gxy_vis_add_volume: NULL argument");
+  GXY_CHECK((int)v->vols.size() < GXY_MAX_VOLUME_VIS, "more than %d volume operators in one Visualization", GXY_MAX_VOLUME_VIS);
+  GXY_CHECK(n_slices <= GXY_MAX_SLICES && n_iso <= GXY_MAX_ISOVALUES, "too many slices (%d > %d) or isovalues (%d > %d)", n_slices,
+            GXY_MAX_SLICES, n_iso, GXY_MAX_ISOVALUES);
+  GXY_CHECK(vol->ctx == v->ctx, "volume belongs to another context");
+  VolOp op;
+  op.vol = vol;
+  op.slices.assign(slices4, slices4 + 4 * (size_t)n_slices);
+  op.iso.assign(isovalues, isovalues + n_iso);
+  op.volume_render = volume_render;
+  op.tf = *tf;
+  v->vols.push_back(op);
+  v->committed = false;
+  return 0;
+}
+
+int gxy_vis_add_triangles(gxy_vis *v, gxy_triangles *t, const gxy_transfer_function *tf) {
+  GXY_CHECK(t && tf, "gxy_vis_add_triangles: NULL argument");
+  GXY_CHECK(t->ctx == v->ctx, "mesh belongs to another context");
+  GeomOp g;
+  memset(&g, 0, sizeof g);
+  g.kind = 0; g.tri = t; g.tf = *tf;
+  v->geoms.push_back(g);
+  v->committed = false;
+  return 0;
+}
+
+int gxy_vis_add_particles(gxy_vis *v, gxy_particles *p, float radius0, float radius1, float value0, float value1,
+                          const gxy_transfer_function *tf) {
+  GXY_CHECK(p && tf, "gxy_vis_add_particles: NULL argument");
+  GXY_CHECK(p->ctx == v->ctx, "particles belong to another context");
+  GeomOp g;
+  memset(&g, 0, sizeof g);
+  g.kind = 1; g.par = p; g.tf = *tf;
+  g.radius0 = radius0; g.radius1 = radius1; g.value0 = value0; g.value1 = value1;
+  v->geoms.push_back(g);
+  v->committed = false;
+  return 0;
+}
+
+static void pack_tf(const gxy_transfer_function &in, DevTF &out) {
+  for (int i = 0; i < 256; i++) out.e[i] = make_float4(in.colors[i][0], in.colors[i][1], in.colors[i][2], in.opacities[i]);
+  out.lo = in.range_lo; out.hi = in.range_hi; out.pad0 = out.pad1 = 0.f;
+}
+
+int gxy_vis_commit(gxy_vis *v) {
+  if (use_device(v->ctx)) return 1;
+  vis_free_commit(v);
+  SceneParams &P = v->P;
+  memset(&P, 0, sizeof P);
+  P.gmin = make_float3(v->gmin[0], v->gmin[1], v->gmin[2]); P.gmax = make_float3(v->gmax[0], v->gmax[1], v->gmax[2]);
+  P.lmin = make_float3(v->lmin[0], v->lmin[1], v->lmin[2]); P.lmax = make_float3(v->lmax[0], v->lmax[1], v->lmax[2]);
+  for (int k = 0; k < 6; k++) P.neighbors[k] = v->neighbors[k];
+  P.n_volvis = (int)v->vols.size();
+  P.n_geoms = (int)v->geoms.size();
+  std::vector<DevTF> tfs(v->vols.size() + v->geoms.size());
+  // TraceRays.ispc:342-361
+  P.integrate = 0;
+  P.step = -1.f;
+  v->has_dvr = false;
+  for (size_t m = 0; m < v->vols.size(); m++) {
+    const VolOp &op = v->vols[m];
+    pack_tf(op.tf, tfs[m]);
+    op.vol->last_tf = (int)m;  // MappedVis.cpp:206-212: last committed Vis owns the volume object's TF
+    if (op.volume_render) { P.integrate = 1; v->has_dvr = true; }
+    if (!op.iso.empty()) P.integrate = 1;
+    const float s = op.vol->dv.samplingStep * op.vol->dv.samplingRate;
+    if (P.step < 0 || P.step > s) P.step = s;
+  }
+  for (size_t m = 0; m < v->vols.size(); m++) {
+    const VolOp &op = v->vols[m];
+    DevVolVis &d = P.vv[m];
+    d.n_slices = (int)op.slices.size() / 4;
+    d.n_iso = (int)op.iso.size();
+    d.volume_render = op.volume_render;
+    d.tf = (int)m;
+    for (int k = 0; k < d.n_slices; k++) d.slices[k] = make_float4(op.slices[4 * k], op.slices[4 * k + 1], op.slices[4 * k + 2], op.slices[4 * k + 3]);
+    for (int k = 0; k < d.n_iso; k++) d.iso[k] = op.iso[k];
+    d.vol = op.vol->dv;
+    d.vol.tf = op.vol->last_tf;
+  }
+  std::vector<DevGeom> dg(v->geoms.size());
+  std::vector<GeomBuildInput> bi(v->geoms.size());
+  for (size_t k = 0; k < v->geoms.size(); k++) {
+    const GeomOp &g = v->geoms[k];
+    pack_tf(g.tf, tfs[v->vols.size() + k]);
+    DevGeom &d = dg[k];
+    memset(&d, 0, sizeof d);
+    GeomBuildInput &b = bi[k];
+    memset(&b, 0, sizeof b);
+    d.kind = g.kind;
+    d.tf = (int)(v->vols.size() + k);
+    b.kind = g.kind;
+    b.geom_id = (int)k;
+    if (g.kind == 0) {
+      d.idx = g.tri->d_idx; d.normals = g.tri->d_normals; d.data = g.tri->d_data;
+      b.n_prims = g.tri->nt; b.verts = g.tri->d_verts; b.idx = g.tri->d_idx;
+    } else {
+      d.centers = g.par->d_centers; d.data = g.par->d_data;
+      d.radius0 = g.radius0; d.radius1 = g.radius1; d.value0 = g.value0; d.value1 = g.value1;
+      // DataDrivenSpheres.ispc:211-220
+      float eps = logf(g.radius0);
+      if (eps < 0.f) eps = -1.f / eps;
+      if (eps > (float)(g.radius0 / 100.0)) eps = (float)(g.radius0 / 100.0);
+      d.epsilon = eps;
+      b.n_prims = g.par->n; b.centers = g.par->d_centers; b.data = g.par->d_data;
+      b.radius0 = g.radius0; b.radius1 = g.radius1; b.value0 = g.value0; b.value1 = g.value1; b.epsilon = eps;
+    }
+  }
+  if (!tfs.empty()) {
+    GXY_CUDA(cudaMalloc(&v->d_tfs, sizeof(DevTF) * tfs.size()));
+    GXY_CUDA(cudaMemcpy(v->d_tfs, tfs.data(), sizeof(DevTF) * tfs.size(), cudaMemcpyHostToDevice));
+  }
+  if (!dg.empty()) {
+    GXY_CUDA(cudaMalloc(&v->d_geoms, sizeof(DevGeom) * dg.size()));
+    GXY_CUDA(cudaMemcpy(v->d_geoms, dg.data(), sizeof(DevGeom) * dg.size(), cudaMemcpyHostToDevice));
+  }
+  GXY_CUDA(cudaMalloc(&v->d_error, sizeof(int)));
+  GXY_CUDA(cudaMemset(v->d_error, 0, sizeof(int)));
+  if (!bi.empty()) {
+    if (build_bvh(bi.data(), (int)bi.size(), &v->bvh, v->ctx->stream)) return 1;
+  }
+  P.tfs = v->d_tfs;
+  P.geoms = v->d_geoms;
+  P.nodes = v->bvh.nodes;
+  P.prims = v->bvh.prims;
+  P.n_prims = v->bvh.n_prims;
+  P.error_flag = v->d_error;
+  v->committed = true;
+  return 0;
+}
+
+int gxy_vis_build_info(gxy_vis *v, long long *n_prims, long long *n_nodes, float *build_ms) {
+  if (n_prims) *n_prims = v->bvh.n_prims;
+  if (n_nodes) *n_nodes = v->bvh.n_nodes;
+  if (build_ms) *build_ms = v->bvh.build_ms;
+  return 0;
+}
+
+// ---- host helpers ------------------------------------------------------------------------------
+struct H3 { float x, y, z; };
+static inline void h_normalize(H3 &a) {  // src/data/dtypes.h normalize(vec3f&)
+  float d = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
+  if (d != 0) { d = (float)(1.0 / d); a.x *= d; a.y *= d; a.z *= d; }
+}
+static inline H3 h_cross(H3 a, H3 b) { return H3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+int gxy_resolve_lights(const gxy_lighting *in, const gxy_camera *cam, gxy_lighting *out) {
+  // Rendering::resolve_lights (Rendering.cpp:157-216)
+  GXY_CHECK(in && cam && out, "gxy_resolve_lights: NULL argument");
+  GXY_CHECK(in->n_lights >= 0 && in->n_lights <= GXY_MAX_LIGHTS, "too many lights");
+  *out = *in;
+  H3 viewpoint{cam->eye[0], cam->eye[1], cam->eye[2]}, viewup{cam->up[0], cam->up[1], cam->up[2]}, viewdir{cam->dir[0], cam->dir[1], cam->dir[2]};
+  h_normalize(viewup);
+  h_normalize(viewdir);
+  H3 right = h_cross(viewdir, viewup);
+  h_normalize(right);
+  H3 up = h_cross(viewdir, right);
+  for (int i = 0; i < in->n_lights; i++)
+    if (in->types[i] == 1) {
+      const float lx = in->lights[i][0], ly = in->lights[i][1], lz = in->lights[i][2];
+      // viewpoint + scale1(x,right) + scale1(y,up) + scale1(z,viewdir), left to right
+      out->lights[i][0] = ((viewpoint.x + lx * right.x) + ly * up.x) + lz * viewdir.x;
+      out->lights[i][1] = ((viewpoint.y + lx * right.y) + ly * up.y) + lz * viewdir.y;
+      out->lights[i][2] = ((viewpoint.z + lx * right.z) + ly * up.z) + lz * viewdir.z;
+      out->types[i] = 2;
+    }
+  return 0;
+}
+
+int gxy_resample_transfer_function(int n, const float *cmap, int m, const float *omap, gxy_transfer_function *out) {
+  // MappedVis::local_commit (MappedVis.cpp:277-338); x is evaluated in double there
+  GXY_CHECK(n >= 2 && m >= 2 && cmap && omap && out, "transfer function needs >= 2 control points");
+  int i0 = 0, i1 = 1;
+  float xmin = cmap[0], xmax = cmap[4 * (n - 1)];
+  for (int i = 0; i < 256; i++) {
+    float x = (float)(xmin + (i / (255.0)) * (xmax - xmin));
+    if (x > xmax) x = xmax;
+    while (cmap[4 * i1] < x) i0++, i1++;
+    const float d = (x - cmap[4 * i0]) / (cmap[4 * i1] - cmap[4 * i0]);
+    for (int c = 0; c < 3; c++) out->colors[i][c] = cmap[4 * i0 + 1 + c] + d * (cmap[4 * i1 + 1 + c] - cmap[4 * i0 + 1 + c]);
+  }
+  i0 = 0, i1 = 1;
+  xmin = omap[0]; xmax = omap[2 * (m - 1)];
+  for (int i = 0; i < 256; i++) {
+    float x = (float)(xmin + (i / (255.0)) * (xmax - xmin));
+    if (x > xmax) x = xmax;
+    while (omap[2 * i1] < x) i0++, i1++;
+    const float d = (x - omap[2 * i0]) / (omap[2 * i1] - omap[2 * i0]);
+    out->opacities[i] = omap[2 * i0 + 1] + d * (omap[2 * i1 + 1] - omap[2 * i0 + 1]);
+  }
+  return 0;
+}
+
+void gxy_factor(int ijk, int factors[3]) {
+  // Volume.cpp:88-122
+  factors[0] = factors[1] = 1; factors[2] = ijk;
+  if (ijk == 1) { factors[2] = 1; return; }
+  int mm = ijk + 3;
+  for (int i = 1; i <= ijk >> 1; i++) {
+    const int jk = ijk / i;
+    if (ijk == (i * jk))
+      for (int j = 1; j <= jk >> 1; j++) {
+        const int k = jk / j;
+        if (jk == (j * k)) {
+          const int m = i + j + k;
+          if (m < mm) { mm = m; factors[0] = i; factors[1] = j; factors[2] = k; }
+        }
+      }
+  }
+}
+
+void gxy_partition(int n, const int factors[3], const int grid[3], int *out) {
+  // Volume.cpp:133-172
+  (void)n;
+  const int ni = grid[0] - 2, nj = grid[1] - 2, nk = grid[2] - 2;
+  const int di = ni / factors[0], dj = nj / factors[1], dk = nk / factors[2];
+  int *p = out;
+  for (int k = 0; k < factors[2]; k++)
+    for (int j = 0; j < factors[1]; j++)
+      for (int i = 0; i < factors[0]; i++, p += 15) {
+        p[0] = i; p[1] = j; p[2] = k;
+        p[3] = 1 + i * di; p[4] = 1 + j * dj; p[5] = 1 + k * dk;
+        p[6] = 1 + ((i == (factors[0] - 1)) ? ni - p[3] : di);
+        p[7] = 1 + ((j == (factors[1] - 1)) ? nj - p[4] : dj);
+        p[8] = 1 + ((k == (factors[2] - 1)) ? nk - p[5] : dk);
+        p[9] = p[3] - 1; p[10] = p[4] - 1; p[11] = p[5] - 1;
+        p[12] = p[6] + 2; p[13] = p[7] + 2; p[14] = p[8] + 2;
+      }
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+static DevLights make_dev_lights(const gxy_lighting &L) {
+  DevLights d;
+  memset(&d, 0, sizeof d);
+  d.n_lights = L.n_lights; d.n_ao = L.n_ao; d.shadows = L.shadows;
+  d.ao_radius = L.ao_radius; d.Ka = L.Ka; d.Kd = L.Kd;
+  for (int i = 0; i < L.n_lights; i++) {
+    for (int k = 0; k < 3; k++) d.lights[i][k] = L.lights[i][k];
+    d.types[i] = L.types[i];
+  }
+  return d;
+}
+
+static DevCamera make_dev_camera(const gxy_camera &c, int width, int height) {
+  // Camera::generate_initial_rays set-up (Camera.cpp:528-582); tan() in double as the reference
+  DevCamera f;
+  H3 veye{c.eye[0], c.eye[1], c.eye[2]}, vu{c.up[0], c.up[1], c.up[2]}, vdir{c.dir[0], c.dir[1], c.dir[2]};
+  H3 center;
+  if (c.aov == 0.0f) {
+    center = H3{veye.x + vdir.x, veye.y + vdir.y, veye.z + vdir.z};
+    h_normalize(vdir);
+  } else {
+    const float d = (float)(1.0 / tan(2 * 3.1415926 * ((double)c.aov / 2.0) / 360.0));
+    h_normalize(vdir);
+    center = H3{veye.x + vdir.x * d, veye.y + vdir.y * d, veye.z + vdir.z * d};
+  }
+  H3 vr = h_cross(vdir, vu);
+  h_normalize(vr);
+  vu = h_cross(vr, vdir);
+  h_normalize(vu);
+  const float pixel_scaling = (float)((((width < height) ? width : height) - 1.0) / 2.0);
+  f.off_x = (float)((width - 1) / 2.0);
+  f.off_y = (float)((height - 1) / 2.0);
+  f.scaling = (float)(1.0 / pixel_scaling);  // Camera.h:66
+  f.veye = make_float3(veye.x, veye.y, veye.z); f.vdir = make_float3(vdir.x, vdir.y, vdir.z);
+  f.vr = make_float3(vr.x, vr.y, vr.z); f.vu = make_float3(vu.x, vu.y, vu.z);
+  f.center = make_float3(center.x, center.y, center.z);
+  f.ortho = (c.aov == 0.0f) ? 1 : 0;
+  return f;
+}
+
+static int check_vis(gxy_vis *v) {
+  GXY_CHECK(v, "NULL visualization");
+  GXY_CHECK(v->committed, "visualization not committed (call gxy_vis_commit)");
+  return use_device(v->ctx);
+}
+
+static int check_error_flag(gxy_vis *v) {
+  int e = 0;
+  GXY_CUDA(cudaMemcpyAsync(&e, v->d_error, sizeof(int), cudaMemcpyDeviceToHost, v->ctx->stream));
+  GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  GXY_CHECK(e == 0, "BVH traversal stack overflow (tree too deep)");
+  return 0;
+}
+
+static int h2d_rays(gxy_vis *v, RayBuf &buf, gxy_raylist_view r) {
+  cudaStream_t st = v->ctx->stream;
+  if (buf.reserve((size_t)std::max(r.n, 1), false, st)) return 1;
+  if (r.n > 0)
+    GXY_CUDA(cudaMemcpy2DAsync(buf.base, buf.cap * 4, r.base, (size_t)r.aligned_n * 4, (size_t)r.n * 4, GXY_RAYLIST_COLUMNS,
+                               cudaMemcpyHostToDevice, st));
+  return 0;
+}
+static int d2h_rays(gxy_vis *v, RayBuf &buf, float *base, int n, int aligned_n, int first_col = 0, int ncols = GXY_RAYLIST_COLUMNS) {
+  if (n > 0)
+    GXY_CUDA(cudaMemcpy2DAsync(base + (size_t)first_col * aligned_n, (size_t)aligned_n * 4, buf.base + (size_t)first_col * buf.cap, buf.cap * 4,
+                               (size_t)n * 4, ncols, cudaMemcpyDeviceToHost, v->ctx->stream));
+  return 0;
+}
+
+extern "C" {
+
+int gxy_trace_raylist(gxy_vis *v, const gxy_lighting *lights, gxy_raylist_view rays, float epsilon, gxy_raylist **out, int *hit_ids) {
+  if (check_vis(v)) return 1;
+  GXY_CHECK(lights && rays.base && rays.n >= 0 && rays.aligned_n >= rays.n, "gxy_trace_raylist: bad arguments");
+  GXY_CHECK(lights->n_lights >= 1 && lights->n_lights <= GXY_MAX_LIGHTS, "lighting needs 1..%d lights", GXY_MAX_LIGHTS);
+  if (out) *out = nullptr;
+  const int n = rays.n;
+  if (n == 0) return 0;
+  cudaStream_t st = v->ctx->stream;
+  if (h2d_rays(v, v->cur, rays)) return 1;
+  int *d_hits = nullptr;
+  if (hit_ids) {
+    if (v->io_i.reserve((size_t)2 * n)) return 1;
+    d_hits = v->io_i.p;
+  }
+  if (launch_trace(v->P, v->cur.v, n, epsilon, d_hits, false, nullptr, st)) return 1;
+  if (v->hit_index.reserve((size_t)2 * n) || v->block_sums.reserve((size_t)n / 1024 + 2) || v->small.reserve(64)) return 1;
+  if (launch_hit_scan(v->cur.v, n, v->hit_index.p, v->block_sums.p, v->small.p, st)) return 1;
+  int nhit = 0;
+  GXY_CUDA(cudaMemcpyAsync(&nhit, v->small.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GXY_CUDA(cudaStreamSynchronize(st));
+  const long long n_out = (long long)nhit * (lights->n_ao + (lights->shadows ? lights->n_lights : 0));
+  GXY_CHECK(n_out < (1ll << 31), "secondary ray list too large (%lld)", n_out);
+  const DevLights L = make_dev_lights(*lights);
+  if (v->next.reserve((size_t)std::max<long long>(n_out, 1), false, st)) return 1;
+  if (launch_shade_spawn(L, v->cur.v, n, v->hit_index.p, v->small.p, v->next.v, epsilon, st)) return 1;
+  if (d2h_rays(v, v->cur, rays.base, n, rays.aligned_n)) return 1;
+  if (hit_ids) GXY_CUDA(cudaMemcpyAsync(hit_ids, d_hits, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, st));
+  if (n_out > 0 && out) {
+    gxy_raylist *o = new gxy_raylist();
+    o->n = (int)n_out;
+    o->aligned_n = std::max(16, (o->n + 15) & ~15);  // Rays.cpp:57-58
+    o->base = (float *)calloc((size_t)GXY_RAYLIST_COLUMNS * o->aligned_n, sizeof(float));
+    if (!o->base) { delete o; gxy_set_error("out of host memory for the secondary list"); return 1; }
+    if (d2h_rays(v, v->next, o->base, o->n, o->aligned_n)) return 1;
+    *out = o;
+  }
+  GXY_CUDA(cudaStreamSynchronize(st));
+  return check_error_flag(v);
+}
+
+int gxy_raylist_get_view(gxy_raylist *l, gxy_raylist_view *view) {
+  GXY_CHECK(l && view, "NULL raylist");
+  view->base = l->base; view->n = l->n; view->aligned_n = l->aligned_n;
+  return 0;
+}
+void gxy_raylist_free(gxy_raylist *l) {
+  if (!l) return;
+  free(l->base);
+  delete l;
+}
+
+int gxy_classify(gxy_vis *v, gxy_raylist_view rays) {
+  if (check_vis(v)) return 1;
+  if (rays.n == 0) return 0;
+  if (h2d_rays(v, v->cur, rays)) return 1;
+  if (launch_classify(v->P, v->cur.v, rays.n, v->ctx->stream)) return 1;
+  if (d2h_rays(v, v->cur, rays.base, rays.n, rays.aligned_n, 24, 1)) return 1;
+  GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  return 0;
+}
+
+int gxy_generate_rays(gxy_vis *v, const gxy_camera *cam, int w, int h, gxy_raylist_view rays, int *n_out) {
+  if (check_vis(v)) return 1;
+  GXY_CHECK(cam && rays.base && w > 0 && h > 0 && rays.aligned_n >= w * h, "gxy_generate_rays: bad arguments");
+  cudaStream_t st = v->ctx->stream;
+  const int npix = w * h;
+  if (v->cur.reserve(npix, false, st) || v->block_sums.reserve((size_t)npix / 1024 + 2) || v->small.reserve(64)) return 1;
+  const DevCamera C = make_dev_camera(*cam, w, h);
+  if (launch_generate(v->P, C, w, h, v->cur.v, nullptr, v->block_sums.p, v->small.p, st)) return 1;
+  int n = 0;
+  GXY_CUDA(cudaMemcpyAsync(&n, v->small.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GXY_CUDA(cudaStreamSynchronize(st));
+  if (d2h_rays(v, v->cur, rays.base, n, rays.aligned_n)) return 1;
+  GXY_CUDA(cudaStreamSynchronize(st));
+  *n_out = n;
+  return 0;
+}
+
+int gxy_intersect(gxy_vis *v, int n, const float *org3, const float *dir3, const float *tnear, const float *tfar, int *geom_prim2,
+                  float *tuv3) {
+  if (check_vis(v)) return 1;
+  if (n <= 0) return 0;
+  cudaStream_t st = v->ctx->stream;
+  if (v->io_f.reserve((size_t)11 * n) || v->io_i.reserve((size_t)2 * n)) return 1;
+  float *d_org = v->io_f.p, *d_dir = d_org + 3 * (size_t)n, *d_tn = d_dir + 3 * (size_t)n, *d_tf = d_tn + n, *d_tuv = d_tf + n;
+  GXY_CUDA(cudaMemcpyAsync(d_org, org3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, st));
+  GXY_CUDA(cudaMemcpyAsync(d_dir, dir3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, st));
+  GXY_CUDA(cudaMemcpyAsync(d_tn, tnear, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+  GXY_CUDA(cudaMemcpyAsync(d_tf, tfar, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+  if (launch_intersect(v->P, n, d_org, d_dir, d_tn, d_tf, v->io_i.p, d_tuv, st)) return 1;
+  GXY_CUDA(cudaMemcpyAsync(geom_prim2, v->io_i.p, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, st));
+  GXY_CUDA(cudaMemcpyAsync(tuv3, d_tuv, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+  GXY_CUDA(cudaStreamSynchronize(st));
+  return check_error_flag(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frame-level wave loop.
+//
+// A wave on one partition: trace the current list (mixed types) -> scan surface hits -> spawn AO /
+// shadow rays into the next list + light the primaries -> classify -> add TERMINATED rays to this
+// partition's partial framebuffer -> counting-sort the BOUNDARY rays by destination rank.  Between
+// waves the sorted segments are handed to their destinations (device copy in-process, NCCL
+// send/recv across processes) and appended to the destination's next list.  The loop ends when no
+// partition has rays left (global sum), which replaces the reference's busy/idle tree +
+// MPI_Allreduce termination protocol (RenderingSet.cpp:289-589).
+int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const gxy_lighting *lights_in, int w, int h, float epsilon,
+               gxy_stats *stats) {
+  GXY_CHECK(nparts >= 1 && parts && cam && lights_in && w > 0 && h > 0, "gxy_render: bad arguments");
+  for (int p = 0; p < nparts; p++)
+    if (check_vis(parts[p])) return 1;
+  gxy_context *ctx0 = parts[0]->ctx;
+  const bool multi_proc = ctx0->comm != nullptr;
+  GXY_CHECK(!multi_proc || nparts == 1, "with a communicator attached each process drives exactly one partition");
+  const int nranks = multi_proc ? ctx0->nranks : nparts;
+  const int rank0 = multi_proc ? ctx0->rank : 0;
+  gxy_lighting lights;
+  if (gxy_resolve_lights(lights_in, cam, &lights)) return 1;
+  GXY_CHECK(lights.n_lights >= 1, "lighting needs at least one light");
+  const DevLights L = make_dev_lights(lights);
+  const DevCamera C = make_dev_camera(*cam, w, h);
+  const int npix = w * h;
+  const int n_sec_per_hit = lights.n_ao + (lights.shadows ? lights.n_lights : 0);
+  gxy_stats S;
+  memset(&S, 0, sizeof S);
+
+  cudaEvent_t ev0, ev1;
+  if (use_device(ctx0)) return 1;
+  GXY_CUDA(cudaEventCreate(&ev0));
+  GXY_CUDA(cudaEventCreate(&ev1));
+  GXY_CUDA(cudaEventRecord(ev0, ctx0->stream));
+
+  std::vector<int> n_cur(nparts, 0);
+  // ---- generation (Camera::generate_initial_rays; every partition scans the full window) ----
+  for (int p = 0; p < nparts; p++) {
+    gxy_vis *v = parts[p];
+    if (use_device(v->ctx)) return 1;
+    cudaStream_t st = v->ctx->stream;
+    if (v->cur.reserve(npix, false, st) || v->block_sums.reserve((size_t)std::max(npix, 1 << 20) / 1024 + 2) || v->small.reserve(64 + 4 * (size_t)nranks) ||
+        v->counters.reserve(4) || v->fb.reserve((size_t)npix * 4))
+      return 1;
+    v->fb_w = w; v->fb_h = h;
+    GXY_CUDA(cudaMemsetAsync(v->fb.p, 0, sizeof(float) * 4 * npix, st));
+    GXY_CUDA(cudaMemsetAsync(v->counters.p, 0, sizeof(unsigned long long) * 4, st));
+    if (launch_generate(v->P, C, w, h, v->cur.v, nullptr, v->block_sums.p, v->small.p, st)) return 1;
+    S.kernel_launches += 3;
+  }
+  for (int p = 0; p < nparts; p++) {
+    gxy_vis *v = parts[p];
+    if (use_device(v->ctx)) return 1;
+    GXY_CUDA(cudaMemcpyAsync(&n_cur[p], v->small.p, sizeof(int), cudaMemcpyDeviceToHost, v->ctx->stream));
+    GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    S.primary_rays += n_cur[p];
+  }
+
+  // small[] layout (ints): [0] nhit/ngen  [8 .. 8+nranks) counts  [8+nranks .. 8+2nranks] offsets  then cursor
+  std::vector<std::vector<int>> send_counts(nparts, std::vector<int>(nranks, 0)), send_offsets(nparts, std::vector<int>(nranks + 1, 0));
+  std::vector<int> n_spawn(nparts, 0);
+  std::vector<int> all_counts;  // multi-process: nranks x (nranks+1)
+  for (int wave = 0; wave < 100000; wave++) {
+    long long pending_local = 0;
+    for (int p = 0; p < nparts; p++) pending_local += n_cur[p];
+    if (!multi_proc && pending_local == 0) break;
+    // ---- trace + scan (async per partition) ----
+    for (int p = 0; p < nparts; p++) {
+      gxy_vis *v = parts[p];
+      const int n = n_cur[p];
+      if (n == 0) continue;
+      if (use_device(v->ctx)) return 1;
+      cudaStream_t st = v->ctx->stream;
+      if (launch_trace(v->P, v->cur.v, n, epsilon, nullptr, !v->has_dvr, nullptr, st)) return 1;
+      if (v->hit_index.reserve((size_t)2 * n) || v->block_sums.reserve((size_t)n / 1024 + 2)) return 1;
+      if (launch_hit_scan(v->cur.v, n, v->hit_index.p, v->block_sums.p, v->small.p, st)) return 1;
+      S.kernel_launches += 4;
+      S.traced_rays += n;
+      S.waves++;
+    }
+    // ---- read hit counts, size the next lists, shade + spawn, classify, accumulate, sort ----
+    std::vector<int> nhit(nparts, 0);
+    for (int p = 0; p < nparts; p++) {
+      if (n_cur[p] == 0) continue;
+      gxy_vis *v = parts[p];
+      if (use_device(v->ctx)) return 1;
+      GXY_CUDA(cudaMemcpyAsync(&nhit[p], v->small.p, sizeof(int), cudaMemcpyDeviceToHost, v->ctx->stream));
+    }
+    for (int p = 0; p < nparts; p++) {
+      gxy_vis *v = parts[p];
+      n_spawn[p] = 0;
+      std::fill(send_counts[p].begin(), send_counts[p].end(), 0);
+      const int n = n_cur[p];
+      if (n == 0) continue;
+      if (use_device(v->ctx)) return 1;
+      cudaStream_t st = v->ctx->stream;
+      GXY_CUDA(cudaStreamSynchronize(st));
+      const long long nsp = (long long)nhit[p] * n_sec_per_hit;
+      GXY_CHECK(nsp < (1ll << 31) - (1ll << 24), "secondary ray list too large (%lld rays)", nsp);
+      n_spawn[p] = (int)nsp;
+      S.ao_rays += (long long)nhit[p] * lights.n_ao;
+      S.shadow_rays += (long long)nhit[p] * (lights.shadows ? lights.n_lights : 0);
+      if (v->next.reserve((size_t)std::max<long long>(nsp, 1), false, st)) return 1;
+      if (launch_shade_spawn(L, v->cur.v, n, v->hit_index.p, v->small.p, v->next.v, epsilon, st)) return 1;
+      if (launch_classify(v->P, v->cur.v, n, st)) return 1;
+      if (launch_accumulate(v->cur.v, n, v->fb.p, w, h, v->counters.p, st)) return 1;
+      S.kernel_launches += 3 + (lights.n_ao > 0 ? 1 : 0);
+      if (nranks > 1) {
+        if (v->send.reserve((size_t)n, false, st)) return 1;
+        int *d_counts = v->small.p + 8, *d_offsets = d_counts + nranks, *d_cursor = d_offsets + nranks + 1;
+        if (launch_partition_by_destination(v->cur.v, n, nranks, multi_proc ? rank0 : p, v->send.v, d_counts, d_offsets, d_cursor, st)) return 1;
+        S.kernel_launches += 3;
+        GXY_CUDA(cudaMemcpyAsync(send_counts[p].data(), d_counts, sizeof(int) * nranks, cudaMemcpyDeviceToHost, st));
+        GXY_CUDA(cudaMemcpyAsync(send_offsets[p].data(), d_offsets, sizeof(int) * (nranks + 1), cudaMemcpyDeviceToHost, st));
+      }
+    }
+    for (int p = 0; p < nparts; p++) {
+      if (n_cur[p] == 0) continue;
+      if (use_device(parts[p]->ctx)) return 1;
+      GXY_CUDA(cudaStreamSynchronize(parts[p]->ctx->stream));
+    }
+    // ---- exchange ----
+    std::vector<int> n_next(nparts, 0);
+    for (int p = 0; p < nparts; p++) n_next[p] = n_spawn[p];
+    if (!multi_proc) {
+      for (int src = 0; src < nparts; src++)
+        for (int dst = 0; dst < nparts; dst++) {
+          const int cnt = send_counts[src][dst];
+          if (!cnt) continue;
+          gxy_vis *vs = parts[src], *vd = parts[dst];
+          S.forwarded_rays += cnt;
+          if (use_device(vd->ctx)) return 1;
+          cudaStream_t st = vd->ctx->stream;
+          if (vd->next.reserve((size_t)n_next[dst] + cnt, true, st)) return 1;
+          if (vs->ctx->device == vd->ctx->device) {
+            if (launch_copy_rays(vd->next.v, (size_t)n_next[dst], vs->send.v, (size_t)send_offsets[src][dst], cnt, st)) return 1;
+          } else {
+            // stage through the destination's recv list with peer copies, column by column
+            if (vd->recv.reserve((size_t)cnt, false, st)) return 1;
+            for (int c = 0; c < 24; c++)
+              GXY_CUDA(cudaMemcpyPeerAsync(vd->recv.base + (size_t)c * vd->recv.cap, vd->ctx->device,
+                                           vs->send.base + (size_t)c * vs->send.cap + send_offsets[src][dst], vs->ctx->device,
+                                           sizeof(float) * cnt, st));
+            if (launch_copy_rays(vd->next.v, (size_t)n_next[dst], vd->recv.v, 0, cnt, st)) return 1;
+          }
+          S.kernel_launches += 1;
+          n_next[dst] += cnt;
+        }
+      if (nparts > 1)  // the send lists are rewritten by the next wave: wait for every consumer
+        for (int p = 0; p < nparts; p++) {
+          if (use_device(parts[p]->ctx)) return 1;
+          GXY_CUDA(cudaStreamSynchronize(parts[p]->ctx->stream));
+        }
+    } else {
+      // one process per GPU: exchange counts, then the ray columns, with NCCL over NVLink
+      gxy_vis *v = parts[0];
+      cudaStream_t st = v->ctx->stream;
+      const int me = rank0;
+      std::vector<int> mine(nranks + 1, 0);
+      for (int d = 0; d < nranks; d++) mine[d] = send_counts[0][d];
+      mine[nranks] = n_spawn[0];
+      if (v->io_i.reserve((size_t)(nranks + 1) * (nranks + 1))) return 1;
+      int *d_mine = v->io_i.p, *d_all = v->io_i.p + (nranks + 1);
+      GXY_CUDA(cudaMemcpyAsync(d_mine, mine.data(), sizeof(int) * (nranks + 1), cudaMemcpyHostToDevice, st));
+      GXY_NCCL(g_nccl.AllGather(d_mine, d_all, nranks + 1, ncclInt32, v->ctx->comm, st));
+      all_counts.resize((size_t)nranks * (nranks + 1));
+      GXY_CUDA(cudaMemcpyAsync(all_counts.data(), d_all, sizeof(int) * nranks * (nranks + 1), cudaMemcpyDeviceToHost, st));
+      GXY_CUDA(cudaStreamSynchronize(st));
+      long long global_pending = 0;
+      int n_recv_total = 0;
+      std::vector<int> recv_from(nranks, 0);
+      for (int r = 0; r < nranks; r++) {
+        for (int d = 0; d < nranks; d++) global_pending += all_counts[(size_t)r * (nranks + 1) + d];
+        global_pending += all_counts[(size_t)r * (nranks + 1) + nranks];
+        recv_from[r] = all_counts[(size_t)r * (nranks + 1) + me];
+        n_recv_total += recv_from[r];
+      }
+      for (int d = 0; d < nranks; d++) S.forwarded_rays += send_counts[0][d];
+      if (n_recv_total) {
+        if (v->recv.reserve((size_t)n_recv_total, false, st)) return 1;
+      }
+      bool any = false;
+      for (int r = 0; r < nranks; r++) any = any || recv_from[r] || send_counts[0][r];
+      if (any) {
+        GXY_NCCL(g_nccl.GroupStart());
+        int roff = 0;
+        for (int r = 0; r < nranks; r++) {
+          if (r != me && send_counts[0][r])
+            for (int c = 0; c < 24; c++)
+              GXY_NCCL(g_nccl.Send(v->send.base + (size_t)c * v->send.cap + send_offsets[0][r], send_counts[0][r], ncclFloat32, r, v->ctx->comm, st));
+          if (r != me && recv_from[r])
+            for (int c = 0; c < 24; c++)
+              GXY_NCCL(g_nccl.Recv(v->recv.base + (size_t)c * v->recv.cap + roff, recv_from[r], ncclFloat32, r, v->ctx->comm, st));
+          roff += recv_from[r];
+        }
+        GXY_NCCL(g_nccl.GroupEnd());
+        if (v->next.reserve((size_t)n_next[0] + n_recv_total, true, st)) return 1;
+        roff = 0;
+        for (int r = 0; r < nranks; r++) {
+          if (!recv_from[r]) continue;
+          if (r == me) {
+            if (launch_copy_rays(v->next.v, (size_t)n_next[0], v->send.v, (size_t)send_offsets[0][me], recv_from[r], st)) return 1;
+          } else {
+            if (launch_copy_rays(v->next.v, (size_t)n_next[0], v->recv.v, (size_t)roff, recv_from[r], st)) return 1;
+          }
+          S.kernel_launches += 1;
+          n_next[0] += recv_from[r];
+          roff += recv_from[r];
+        }
+      }
+      if (global_pending == 0) { n_cur[0] = 0; break; }
+    }
+    for (int p = 0; p < nparts; p++) {
+      std::swap(parts[p]->cur, parts[p]->next);
+      n_cur[p] = n_next[p];
+    }
+  }
+
+  // ---- framebuffer: partial sums -> owner (SendPixelsMsg / AddLocalPixels) ----
+  if (!multi_proc) {
+    gxy_vis *v0 = parts[0];
+    for (int p = 1; p < nparts; p++) {
+      gxy_vis *v = parts[p];
+      if (use_device(v->ctx)) return 1;
+      GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+      if (use_device(v0->ctx)) return 1;
+      const float *src = v->fb.p;
+      if (v->ctx->device != v0->ctx->device) {
+        if (v0->fb_tmp.reserve((size_t)npix * 4)) return 1;
+        GXY_CUDA(cudaMemcpyPeerAsync(v0->fb_tmp.p, v0->ctx->device, v->fb.p, v->ctx->device, sizeof(float) * 4 * npix, v0->ctx->stream));
+        src = v0->fb_tmp.p;
+      }
+      if (launch_fb_add(v0->fb.p, src, (size_t)npix * 4, v0->ctx->stream)) return 1;
+      S.kernel_launches += 1;
+    }
+  } else {
+    gxy_vis *v = parts[0];
+    GXY_NCCL(g_nccl.Reduce(v->fb.p, v->fb.p, (size_t)npix * 4, ncclFloat32, ncclSum, 0, v->ctx->comm, v->ctx->stream));
+  }
+  if (use_device(ctx0)) return 1;
+  GXY_CUDA(cudaEventRecord(ev1, ctx0->stream));
+  GXY_CUDA(cudaEventSynchronize(ev1));
+  cudaEventElapsedTime(&S.device_ms, ev0, ev1);
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  for (int p = 0; p < nparts; p++) {
+    gxy_vis *v = parts[p];
+    if (use_device(v->ctx)) return 1;
+    unsigned long long c[4];
+    GXY_CUDA(cudaMemcpy(c, v->counters.p, sizeof c, cudaMemcpyDeviceToHost));
+    S.terminated_rays += (long long)c[0];
+    if (check_error_flag(v)) return 1;
+  }
+  if (stats) *stats = S;
+  return 0;
+}
+
+int gxy_frame_download_rgba32f(gxy_vis *v, float *fb) {
+  if (check_vis(v)) return 1;
+  GXY_CHECK(v->fb_w > 0 && fb, "no frame rendered yet");
+  GXY_CUDA(cudaMemcpyAsync(fb, v->fb.p, sizeof(float) * 4 * (size_t)v->fb_w * v->fb_h, cudaMemcpyDeviceToHost, v->ctx->stream));
+  GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  return 0;
+}
+
+int gxy_frame_download_rgba8(gxy_vis *v, unsigned char *rgba) {
+  if (check_vis(v)) return 1;
+  GXY_CHECK(v->fb_w > 0 && rgba, "no frame rendered yet");
+  const size_t n = (size_t)v->fb_w * v->fb_h * 4;
+  if (v->rgba8.reserve(n)) return 1;
+  if (launch_tonemap(v->fb.p, v->fb_w, v->fb_h, v->rgba8.p, v->ctx->stream)) return 1;
+  GXY_CUDA(cudaMemcpyAsync(rgba, v->rgba8.p, n, cudaMemcpyDeviceToHost, v->ctx->stream));
+  GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  return 0;
+}
+
+// ---- multi-process -------------------------------------------------------------------------------
+int gxy_comm_unique_id(unsigned char id[128]) {
+  if (load_nccl()) return 1;
+  ncclUniqueId u;
+  GXY_NCCL(g_nccl.GetUniqueId(&u));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id, &u, 128);
+  return 0;
+}
+
+int gxy_comm_init(gxy_context *c, int rank, int nranks, const unsigned char id[128]) {
+  if (load_nccl()) return 1;
+  if (use_device(c)) return 1;
+  GXY_CHECK(!c->comm, "communicator already initialised");
+  ncclUniqueId u;
+  memcpy(&u, id, 128);
+  GXY_NCCL(g_nccl.CommInitRank(&c->comm, nranks, u, rank));
+  c->rank = rank;
+  c->nranks = nranks;
+  return 0;
+}
+
+int gxy_comm_destroy(gxy_context *c) {
+  if (c->comm) {
+    if (use_device(c)) return 1;
+    GXY_NCCL(g_nccl.CommDestroy(c->comm));
+    c->comm = nullptr;
+    c->rank = 0;
+    c->nranks = 1;
+  }
+  return 0;
+}
+
+}  // extern "C"

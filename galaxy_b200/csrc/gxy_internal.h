@@ -1,0 +1,57 @@
+// gxy_internal.h -- host-side declarations shared by the translation units of libgxy_b200.so
+#pragma once
+#include "gxy_common.cuh"
+
+namespace gxy {
+
+// ---- kernels (gxy_kernels.cu) ---------------------------------------------------------------
+// K1 TraceRays_TraceRays on n rays (TraceRays.ispc:326-623).  hit_ids may be NULL.
+// anyhit_secondary: occlusion-only traversal for non-PRIMARY rays (valid when no DVR integrates).
+int launch_trace(const SceneParams &P, Rays R, int n, float global_epsilon, int *hit_ids, bool anyhit_secondary,
+                 unsigned long long *sample_counter, cudaStream_t st);
+// offsets for the secondary list (TraceRays.cpp:89-117): per ray "1 if PRIMARY&&SURFACE" flags are
+// scanned; returns device pointers inside `scratch`.  n_hit is written to *d_nhit (device).
+int launch_hit_scan(Rays R, int n, int *d_hit_index /*n*/, int *d_block_sums, int *d_nhit, cudaStream_t st);
+// ambientLighting + generateAORays + diffuseLighting + generateShadowRays (TraceRays.ispc:625-923)
+int launch_shade_spawn(const DevLights &L, Rays R, int n, const int *d_hit_index, const int *d_nhit, Rays out, float epsilon,
+                       cudaStream_t st);
+// Renderer::Classify + AssignDestinations (Renderer.cpp:304-454)
+int launch_classify(const SceneParams &P, Rays R, int n, cudaStream_t st);
+// HandleTerminatedRays + AddLocalPixels (Renderer.cpp:456-502, Rendering.cpp:125-153): fb += rgba
+int launch_accumulate(Rays R, int n, float *fb, int w, int h, unsigned long long *d_terminated, cudaStream_t st);
+// counting-sort of rays with classification >= 0 into per-destination segments of `out`
+// (Renderer.cpp:561-618).  d_counts: nranks ints (device, zeroed by the call), d_offsets nranks+1.
+int launch_partition_by_destination(Rays R, int n, int nranks, int keep_rank, Rays out, int *d_counts, int *d_offsets, int *d_cursor,
+                                    cudaStream_t st);
+// Camera::SpawnRays (Camera.cpp:379-493): ordered compaction of the kept pixels
+int launch_generate(const SceneParams &P, const DevCamera &C, int w, int h, Rays out, int *d_flags_scan, int *d_block_sums,
+                    int *d_count, cudaStream_t st);
+// ColorImageWriter::Write (ImageWriter.cpp:30-48)
+int launch_tonemap(const float *fb, int w, int h, unsigned char *rgba, cudaStream_t st);
+int launch_fb_add(float *dst, const float *src, size_t n, cudaStream_t st);
+// copy n rays (25 columns) between lists: dst[dst_off + i] = src[src_off + i]
+int launch_copy_rays(Rays dst, size_t dst_off, Rays src, size_t src_off, int n, cudaStream_t st);
+int launch_intersect(const SceneParams &P, int n, const float *org3, const float *dir3, const float *tnear, const float *tfar,
+                     int *geom_prim2, float *tuv3, cudaStream_t st);
+
+// ---- BVH build (gxy_bvh.cu) -----------------------------------------------------------------
+struct GeomBuildInput {
+  int kind;  // 0 triangles, 1 spheres
+  int geom_id;
+  long long n_prims;
+  const float *verts;  // device
+  const int *idx;      // device
+  const float *centers;
+  const float *data;
+  float radius0, radius1, value0, value1, epsilon;
+};
+struct BvhResult {
+  WideNode *nodes = nullptr;
+  PrimRec *prims = nullptr;
+  long long n_nodes = 0, n_prims = 0;
+  int max_depth = 0;
+  float build_ms = 0.f;
+};
+int build_bvh(const GeomBuildInput *geoms, int n_geoms, BvhResult *out, cudaStream_t st);
+
+}  // namespace gxy

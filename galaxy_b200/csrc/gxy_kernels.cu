@@ -1,0 +1,820 @@
+// gxy_kernels.cu -- the per-ray kernels of the hot path (sm_100a).
+//
+//  trace_kernel        K1  TraceRays_TraceRays             src/renderer/TraceRays.ispc:326-623
+//                      K2/K4/K5 traversal + prim tests + postIntersect (gxy_traverse.cuh)
+//                      K6/K7 volume sample / gradient / TF  (gxy_common.cuh)
+//  ao_spawn_kernel     K9  TraceRays_generateAORays        TraceRays.ispc:625-733
+//  light_shadow_kernel K10/K8 ambient+diffuse lighting, generateShadowRays  :735-923
+//  classify_kernel     K11 Renderer::Classify/AssignDestinations  src/renderer/Renderer.cpp:304-454
+//  accumulate_kernel   K13 Rendering::AddLocalPixels       src/renderer/Rendering.cpp:125-153
+//  generate_*          K12 Camera::SpawnRays               src/renderer/Camera.cpp:379-493
+//  tonemap_kernel      K14 ColorImageWriter::Write         src/renderer/ImageWriter.cpp:30-48
+#include "gxy_internal.h"
+#include "gxy_traverse.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+namespace gxy {
+
+// ------------------------------------------------------------------------------------------------
+struct SurfHit {  // TraceRays.ispc:79-88
+  float t, opacity;
+  float3 normal, color;
+};
+
+template <int NV>
+__device__ __forceinline__ void sample_volumes(const SceneParams &P, int nvv, float3 coord, float *s) {
+#pragma unroll
+  for (int m = 0; m < NV; m++)
+    if (m < nvv) s[m] = vol_sample(P.vv[m].vol, coord);
+}
+
+template <int NV, bool HAS_GEOM>
+__global__ void __launch_bounds__(GXY_TRACE_THREADS)
+    trace_kernel(const __grid_constant__ SceneParams P, Rays R, int n, float global_epsilon, int *__restrict__ hit_ids,
+                 int anyhit_secondary, unsigned long long *__restrict__ sample_counter) {
+  __shared__ uint2 stack[HAS_GEOM ? GXY_STACK_SMEM * GXY_TRACE_THREADS : 1];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int nvv = NV < P.n_volvis ? NV : P.n_volvis;
+  const float step = P.step;
+  const float epsilon = global_epsilon * step;  // TraceRays.ispc:359
+  unsigned nsamples = 0;
+
+  const bool shadeFlag = R.type[i] == RAY_PRIMARY;
+  const float3 org = f3(R.ox[i], R.oy[i], R.oz[i]);
+  float3 dir = f3(R.dx[i], R.dy[i], R.dz[i]);
+  if (dir.x == 0.f) dir.x = 1e-6f;  // :377-379
+  if (dir.y == 0.f) dir.y = 1e-6f;
+  if (dir.z == 0.f) dir.z = 1e-6f;
+  float ray_t0 = R.t[i], ray_t = R.tMax[i];
+  const float tTimeout = ray_t;
+  float cr = R.r[i], cg = R.g[i], cb = R.b[i], co = R.o[i];
+
+  // MyIntersectBox :90-106, rcp(dir) := 1.0f/dir
+  float tEntry, tExitVolume;
+  {
+    const float rx = 1.0f / dir.x, ry = 1.0f / dir.y, rz = 1.0f / dir.z;
+    const float mnx = (P.lmin.x - org.x) * rx, mny = (P.lmin.y - org.y) * ry, mnz = (P.lmin.z - org.z) * rz;
+    const float mxx = (P.lmax.x - org.x) * rx, mxy = (P.lmax.y - org.y) * ry, mxz = (P.lmax.z - org.z) * rz;
+    tEntry = fmaxf(fminf(mnx, mxx), fmaxf(fminf(mny, mxy), fminf(mnz, mxz)));
+    tExitVolume = fminf(fmaxf(mnx, mxx), fminf(fmaxf(mny, mxy), fmaxf(mnz, mxz)));
+  }
+  if (tEntry < ray_t0) tEntry = ray_t0;  // :412-413
+  else if (tEntry > ray_t0) ray_t0 = tEntry;
+  ray_t = fminf(ray_t, tExitVolume);  // :418
+
+  SurfHit hit;
+  hit.t = 0.f; hit.opacity = 0.f; hit.normal = f3(0.f, 0.f, 0.f); hit.color = f3(0.f, 0.f, 0.f);
+  bool surface_hit = false;
+
+  // LookForSliceHit :143-250
+  if (NV > 0) {
+    int vid = -1;
+    for (int major = 0; major < nvv; major++) {
+      const int ns = P.vv[major].n_slices;
+      for (int minor = 0; minor < ns; minor++) {
+        const float4 pl = P.vv[major].slices[minor];
+        const float3 pnorm = f3(pl.x, pl.y, pl.z);
+        const float denom = dot3(dir, pnorm);
+        if (fabsf(denom) > 0.0001f) {
+          const float t = (pl.w - dot3(org, pnorm)) / denom;
+          if (t >= ray_t0 && t <= ray_t) {
+            hit.normal = denom > 0 ? neg3(pnorm) : pnorm;
+            hit.opacity = 1.0f; hit.t = t; vid = major; ray_t = t; surface_hit = true;
+          }
+        }
+      }
+    }
+    if (surface_hit && shadeFlag) {
+      const float3 point = org + hit.t * dir;
+      const float s = vol_sample(P.vv[vid].vol, point);
+      nsamples++;
+      hit.color = tf_color(P.tfs + P.vv[vid].tf, s);
+      hit.opacity = 1.0f;
+    }
+  }
+
+  // LookForGeometryHit :108-141 + postIntersect (Model.ih:97-187)
+  if (HAS_GEOM) {
+    Hit1 h1;
+    bool found;
+    if (!shadeFlag && anyhit_secondary) found = traverse<true>(P, org, dir, ray_t0, ray_t, h1, stack);
+    else found = traverse<false>(P, org, dir, ray_t0, ray_t, h1, stack);
+    if (hit_ids) { hit_ids[2 * i] = found ? h1.geom : -1; hit_ids[2 * i + 1] = found ? h1.prim : -1; }
+    if (found) {
+      ray_t = h1.t;
+      if (shadeFlag) {
+        const DevGeom g = P.geoms[h1.geom];
+        float3 Ng = h1.Ng, Ns = h1.Ng;
+        float3 col = f3(1.f, 1.f, 1.f);
+        float ca = 1.f;
+        if (g.kind == 0) {  // DataDrivenTriangleMesh.ispc:34-121
+          const int i0 = __ldg(g.idx + 3 * (size_t)h1.prim), i1 = __ldg(g.idx + 3 * (size_t)h1.prim + 1),
+                    i2 = __ldg(g.idx + 3 * (size_t)h1.prim + 2);
+          const float3 bary = f3(1.0f - h1.u - h1.v, h1.u, h1.v);
+          if (g.normals) {
+            const float3 a = f3(__ldg(g.normals + 3 * (size_t)i0), __ldg(g.normals + 3 * (size_t)i0 + 1), __ldg(g.normals + 3 * (size_t)i0 + 2));
+            const float3 b = f3(__ldg(g.normals + 3 * (size_t)i1), __ldg(g.normals + 3 * (size_t)i1 + 1), __ldg(g.normals + 3 * (size_t)i1 + 2));
+            const float3 c = f3(__ldg(g.normals + 3 * (size_t)i2), __ldg(g.normals + 3 * (size_t)i2 + 1), __ldg(g.normals + 3 * (size_t)i2 + 2));
+            Ns = bary.x * a + bary.y * b + bary.z * c;  // interpolate(), vec.ih:723-726
+          }
+          if (g.data) {
+            const float d = bary.x * __ldg(g.data + i0) + bary.y * __ldg(g.data + i1) + bary.z * __ldg(g.data + i2);
+            col = tf_color(P.tfs + g.tf, d);
+            ca = 1.0f;
+          }
+        } else {  // DataDrivenSpheres.ispc:46-63
+          col = tf_color(P.tfs + g.tf, g.data ? __ldg(g.data + h1.prim) : 0.f);
+          ca = 1.0f;
+        }
+        Ng = normalize_isp(Ng);
+        Ns = normalize_isp(Ns);
+        if (dot3(dir, Ng) >= 0.f) Ng = neg3(Ng);
+        if (dot3(Ng, Ns) < 0.f) Ns = neg3(Ns);
+        hit.color = col; hit.opacity = ca; hit.normal = Ns; hit.t = ray_t;
+      }
+      surface_hit = true;
+    }
+  } else if (hit_ids) {
+    hit_ids[2 * i] = -1; hit_ids[2 * i + 1] = -1;
+  }
+
+  float tTermination = ray_t;
+
+  if (NV > 0 && P.integrate) {  // :446-570
+    float tLast, tThis;
+    float sLast[NV > 0 ? NV : 1], sThis[NV > 0 ? NV : 1];
+    bool hit_isosurface = false;
+    tLast = tEntry + epsilon;
+    bool opaque = (min3f(cr, cg, cb) >= 1.0f || co > 0.999f);
+    for (tThis = tEntry; tThis <= tTermination && !opaque && !hit_isosurface;
+         tThis = (tThis == tEntry) ? (tEntry + epsilon)
+                                   : (((tThis + step) > tTermination) && (tThis < tTermination)) ? tTermination : tThis + step) {
+      sample_volumes<NV>(P, nvv, org + tThis * dir, sThis);
+      nsamples += nvv;
+      if (tThis > tEntry && tLast >= epsilon) {
+        // LookForIsoHit :252-310
+        bool h = false;
+        int vid = -1;
+        float hsample = 0.f;
+#pragma unroll
+        for (int major = 0; major < NV; major++)
+          if (major < nvv) {
+            const float sl = sLast[major], st = sThis[major];
+            const int ni = P.vv[major].n_iso;
+            for (int minor = 0; minor < ni; minor++) {
+              const float isoval = P.vv[major].iso[minor];
+              if (((isoval >= sl) && (isoval < st)) || ((isoval <= sl) && (isoval > st))) {
+                h = true; vid = major;
+                hit.t = tLast + ((isoval - sl) / (st - sl)) * (tThis - tLast);
+                hsample = isoval;
+              }
+            }
+          }
+        if (h) {
+          const float3 point = org + hit.t * dir;
+          if (shadeFlag) {
+            hit.normal = safe_normalize(vol_gradient(P.vv[vid].vol, point));
+            nsamples += 4;
+            if (dot3(dir, hit.normal) > 0) hit.normal = neg3(hit.normal);
+            hit.color = tf_color(P.tfs + P.vv[vid].tf, hsample);
+            hit.opacity = 1.0f;
+          }
+          tTermination = hit.t; tThis = hit.t;
+          surface_hit = true; hit_isosurface = true;
+          sample_volumes<NV>(P, nvv, org + tThis * dir, sThis);
+          nsamples += nvv;
+        }
+        // DVR :512-542
+#pragma unroll
+        for (int major = 0; major < NV; major++)
+          if (major < nvv) {
+            if (P.vv[major].volume_render) {
+              const DevTF *tf = P.tfs + P.vv[major].vol.tf;
+              const float sVolume = (sLast[major] + sThis[major]) / 2;
+              const float rate = P.vv[major].vol.samplingRate;
+              if (shadeFlag) {
+                const float4 ca = tf_both(tf, sVolume);
+                if (ca.w > 0) {
+                  const float wo = fmaxf(0.0f, fminf(ca.w / rate, 1.0f));
+                  const float om = 1.0f - co;
+                  cr = cr + om * (wo * ca.x); cg = cg + om * (wo * ca.y); cb = cb + om * (wo * ca.z); co = co + om * (wo * 1.0f);
+                }
+              } else {
+                const float sampleOpacity = tf_opacity(tf, sVolume);
+                if (sampleOpacity > 0) {
+                  const float weightedOpacity = ((tThis - tLast) / step) * fmaxf(0.0f, fminf(sampleOpacity / rate, 1.0f));
+                  const float f = 1 - weightedOpacity;
+                  cr = cr * f; cg = cg * f; cb = cb * f; co = co * f;
+                }
+              }
+            }
+          }
+      }
+#pragma unroll
+      for (int m = 0; m < NV; m++) sLast[m] = sThis[m];
+      opaque = (min3f(cr, cg, cb) >= 1.0f || co > 0.999f);
+      if (opaque) tTermination = tThis;
+      tLast = tThis;
+    }
+    ray_t = tTermination;
+  }
+
+  R.r[i] = cr; R.g[i] = cg; R.b[i] = cb; R.o[i] = co;
+  int term = (min3f(cr, cg, cb) >= 1.0f || co > 0.999f) ? RAY_OPAQUE : 0;
+  R.t[i] = ray_t;
+  if (surface_hit) {
+    term |= RAY_SURFACE;
+    // non-shaded rays: the reference reads an uninitialised hit.opacity (:591); every surface kind
+    // sets opacity 1 when shaded, and Classify treats SURFACE like OPAQUE for SHADOW/AO rays.
+    if (!shadeFlag || hit.opacity > 0.999f) term |= RAY_OPAQUE;
+    if (shadeFlag) {
+      R.sr[i] = hit.color.x; R.sg[i] = hit.color.y; R.sb[i] = hit.color.z; R.so[i] = 1.0f;
+      R.nx[i] = hit.normal.x; R.ny[i] = hit.normal.y; R.nz[i] = hit.normal.z;
+    }
+  } else if (tTermination == tExitVolume) term |= RAY_BOUNDARY;
+  else if (tTermination == tTimeout) term |= RAY_TIMEOUT;
+  R.term[i] = term;
+
+  if (sample_counter) {
+    unsigned tot = nsamples;
+    const unsigned mask = __activemask();
+    for (int off = 16; off > 0; off >>= 1) tot += __shfl_down_sync(mask, tot, off);
+    // lanes that exited early make this an over/under count only if the leader is inactive
+    if ((threadIdx.x & 31) == (__ffs(mask) - 1)) atomicAdd(sample_counter, (unsigned long long)tot);
+  }
+}
+
+template <int NV>
+static int launch_trace_nv(const SceneParams &P, Rays R, int n, float eps, int *hit_ids, bool anyhit, unsigned long long *sc,
+                           cudaStream_t st) {
+  const int blocks = (n + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
+  if (P.n_prims > 0) trace_kernel<NV, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, anyhit ? 1 : 0, sc);
+  else trace_kernel<NV, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, 0, sc);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_trace(const SceneParams &P, Rays R, int n, float global_epsilon, int *hit_ids, bool anyhit_secondary,
+                 unsigned long long *sample_counter, cudaStream_t st) {
+  if (n <= 0) return 0;
+  switch (P.n_volvis) {
+    case 0: return launch_trace_nv<0>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st);
+    case 1: return launch_trace_nv<1>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st);
+    case 2: return launch_trace_nv<2>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st);
+    case 3: return launch_trace_nv<3>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st);
+    default: return launch_trace_nv<GXY_MAX_VOLUME_VIS>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// nearest-hit only (gxy_intersect)
+__global__ void __launch_bounds__(GXY_TRACE_THREADS)
+    intersect_kernel(const __grid_constant__ SceneParams P, int n, const float *__restrict__ org3, const float *__restrict__ dir3,
+                     const float *__restrict__ tnear, const float *__restrict__ tfar, int *__restrict__ gp, float *__restrict__ tuv) {
+  __shared__ uint2 stack[GXY_STACK_SMEM * GXY_TRACE_THREADS];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Hit1 h;
+  const float3 o = f3(org3[3 * i], org3[3 * i + 1], org3[3 * i + 2]), d = f3(dir3[3 * i], dir3[3 * i + 1], dir3[3 * i + 2]);
+  const bool f = traverse<false>(P, o, d, tnear[i], tfar[i], h, stack);
+  gp[2 * i] = f ? h.geom : -1;
+  gp[2 * i + 1] = f ? h.prim : -1;
+  tuv[3 * i] = f ? h.t : tfar[i];
+  tuv[3 * i + 1] = f ? h.u : 0.f;
+  tuv[3 * i + 2] = f ? h.v : 0.f;
+}
+
+int launch_intersect(const SceneParams &P, int n, const float *org3, const float *dir3, const float *tnear, const float *tfar,
+                     int *geom_prim2, float *tuv3, cudaStream_t st) {
+  if (n <= 0) return 0;
+  intersect_kernel<<<(n + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS, GXY_TRACE_THREADS, 0, st>>>(P, n, org3, dir3, tnear, tfar,
+                                                                                                 geom_prim2, tuv3);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ordered compaction helpers: 3 passes (block counts, scan of block counts, ranked write)
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 4
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
+  // v: this thread's count; returns exclusive prefix within the block
+  __shared__ int warp_sums[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = v;
+  for (int off = 1; off < 32; off <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= off) inc += t;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+    for (int off = 1; off < 32; off <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, w, off);
+      if (lane >= off) w += t;
+    }
+    if (lane < SCAN_THREADS / 32) warp_sums[lane] = w;
+  }
+  __syncthreads();
+  const int base = wid ? warp_sums[wid - 1] : 0;
+  if (total) *total = warp_sums[SCAN_THREADS / 32 - 1];
+  __syncthreads();
+  return base + inc - v;
+}
+
+__global__ void scan_block_sums_kernel(int *__restrict__ sums, int nblocks, int *__restrict__ total_out) {
+  // single block: exclusive scan of sums[0..nblocks) in place, total to *total_out
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += SCAN_THREADS) {
+    const int idx = base + threadIdx.x;
+    const int v = idx < nblocks ? sums[idx] : 0;
+    int tot;
+    const int ex = block_exclusive_scan(v, &tot);
+    const int c = carry;
+    if (idx < nblocks) sums[idx] = c + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = carry;
+}
+
+// ---- hit scan (TraceRays.cpp:89-117): flag = PRIMARY && SURFACE
+__device__ __forceinline__ int hit_flag(const Rays &R, int i, int n) {
+  return (i < n && R.type[i] == RAY_PRIMARY && (R.term[i] & RAY_SURFACE)) ? 1 : 0;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) hit_count_kernel(Rays R, int n, int *__restrict__ block_sums) {
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) c += hit_flag(R, base + k, n);
+  int tot;
+  block_exclusive_scan(c, &tot);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(SCAN_THREADS)
+    hit_index_kernel(Rays R, int n, const int *__restrict__ block_sums, int *__restrict__ hit_index, int *__restrict__ hit_list) {
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int f[SCAN_ITEMS], c = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { f[k] = hit_flag(R, base + k, n); c += f[k]; }
+  int pos = block_sums[blockIdx.x] + block_exclusive_scan(c, nullptr);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++)
+    if (base + k < n) {
+      hit_index[base + k] = f[k] ? pos : -1;
+      if (f[k]) { hit_list[pos] = base + k; pos++; }
+    }
+}
+
+int launch_hit_scan(Rays R, int n, int *d_hit_index, int *d_block_sums, int *d_nhit, cudaStream_t st) {
+  // d_hit_index holds 2*n ints: [0,n) hit_index, [n,2n) hit_list
+  const int nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
+  hit_count_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(R, n, d_block_sums);
+  scan_block_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(d_block_sums, nblocks, d_nhit);
+  hit_index_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(R, n, d_block_sums, d_hit_index, d_hit_index + n);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// AO direction tables (src/renderer/UV.ih:21-58 + TraceRays.ispc:692-701), filled by the host:
+// x = cos(2*pi*r0)*sqrt(1-r1), y = sin(2*pi*r0)*sqrt(1-r1), z = sqrt(r1)  for the 256 (r0,r1) pairs
+__constant__ float c_ao_x[256], c_ao_y[256], c_ao_z[256];
+
+static void halton_tables(float U[256], float V[256]) {
+  // UV.ih holds base-2 / base-3 radical inverses accumulated in fp32 and printed with "%g"
+  for (int pass = 0; pass < 2; pass++) {
+    const int b = pass ? 3 : 2;
+    for (int i = 0; i < 256; i++) {
+      float inv = 1.f / (float)b, f = inv, r = 0.f;
+      for (int k = i; k > 0; k /= b) { r = r + f * (float)(k % b); f = f * inv; }
+      char buf[64];
+      snprintf(buf, sizeof buf, "%g", (double)r);
+      (pass ? V : U)[i] = strtof(buf, nullptr);
+    }
+  }
+}
+
+static int ensure_ao_tables() {
+  static bool done = false;
+  if (done) return 0;
+  float U[256], V[256], x[256], y[256], z[256];
+  halton_tables(U, V);
+  for (int r = 0; r < 256; r++) {
+    const float r0 = U[r], r1 = V[r];
+    const float w = sqrtf(1.f - r1);
+    x[r] = cosf((2.f * (float)M_PI) * r0) * w;
+    y[r] = sinf((2.f * (float)M_PI) * r0) * w;
+    z[r] = sqrtf(r1);
+  }
+  GXY_CUDA(cudaMemcpyToSymbol(c_ao_x, x, sizeof x));
+  GXY_CUDA(cudaMemcpyToSymbol(c_ao_y, y, sizeof y));
+  GXY_CUDA(cudaMemcpyToSymbol(c_ao_z, z, sizeof z));
+  done = true;
+  return 0;
+}
+
+// one thread per AO ray (TraceRays.ispc:645-731); runs BEFORE light_shadow_kernel (uses o before
+// diffuseLighting updates it, as the reference's call order does, TraceRays.cpp:124-131)
+__global__ void __launch_bounds__(256)
+    ao_spawn_kernel(const __grid_constant__ DevLights L, Rays R, const int *__restrict__ hit_list, const int *__restrict__ d_nhit, Rays O,
+                    float epsilon) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nAO = L.n_ao;
+  const long long total = (long long)(*d_nhit) * nAO;
+  if (k >= total) return;
+  const int h = (int)(k / nAO), j = (int)(k - (long long)h * nAO);
+  const int i = hit_list[h];
+  const float Ka = -L.Ka / nAO;  // GXY_REVERSE_LIGHTING
+  const float3 sn = f3(R.nx[i], R.ny[i], R.nz[i]);
+  const float ambient_scale = Ka * (1.0f - R.o[i]);
+  float3 b0 = f3(1.0f, 0.0f, 0.0f);
+  if (fabsf(dot3(b0, sn)) > 0.95f) b0 = f3(0.0f, 1.0f, 0.0f);
+  const float3 b1 = normalize_isp(cross3(b0, sn));
+  b0 = normalize_isp(cross3(b1, sn));
+  const float t = R.t[i];
+  float ox = R.ox[i] + t * R.dx[i], oy = R.oy[i] + t * R.dy[i], oz = R.oz[i] + t * R.dz[i];
+  ox = ox + epsilon * sn.x; oy = oy + epsilon * sn.y; oz = oz + epsilon * sn.z;
+  const int px = R.x[i], py = R.y[i];
+  const int r = ((px * 9949 + py * 9613 + j * 9151) >> 8) & 0xff;
+  const float x = c_ao_x[r], y = c_ao_y[r], z = c_ao_z[r] + epsilon;
+  const float3 rd = x * b0 + y * b1 + z * sn;
+  O.ox[k] = ox; O.oy[k] = oy; O.oz[k] = oz;
+  O.dx[k] = rd.x; O.dy[k] = rd.y; O.dz[k] = rd.z;
+  O.r[k] = ambient_scale * R.sr[i]; O.g[k] = ambient_scale * R.sg[i]; O.b[k] = ambient_scale * R.sb[i]; O.o[k] = 0.0f;
+  O.t[k] = 0.0f; O.tMax[k] = L.ao_radius;
+  O.x[k] = px; O.y[k] = py; O.type[k] = RAY_AO; O.term[k] = 0;
+}
+
+// one thread per surface-hit primary: ambient (:735-761), diffuse (:859-923), shadow rays (:763-857)
+__global__ void __launch_bounds__(256)
+    light_shadow_kernel(const __grid_constant__ DevLights L, Rays R, const int *__restrict__ hit_list, const int *__restrict__ d_nhit,
+                        Rays O, float epsilon) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nhit = *d_nhit;
+  if (h >= nhit) return;
+  const int i = hit_list[h];
+  const int nL = L.n_lights;
+  const float3 sn = f3(R.nx[i], R.ny[i], R.nz[i]);
+  const float sr = R.sr[i], sg = R.sg[i], sb = R.sb[i];
+  float r = R.r[i], g = R.g[i], b = R.b[i], o = R.o[i];
+  const float t = R.t[i];
+  const float ox = R.ox[i], oy = R.oy[i], oz = R.oz[i], dx = R.dx[i], dy = R.dy[i], dz = R.dz[i];
+  // ambientLighting
+  {
+    const float ambient_scale = L.Ka * (1.0f - o);
+    r += ambient_scale * sr; g += ambient_scale * sg; b += ambient_scale * sb;
+  }
+  // diffuseLighting
+  {
+    const float Kd = L.Kd / nL;
+    float tr = 0, tg = 0, tb = 0;
+    for (int k = 0; k < nL; k++) {
+      const float3 lt = f3(L.lights[k][0], L.lights[k][1], L.lights[k][2]);
+      float3 lvec;
+      if (L.types[k]) {
+        const float3 sp = f3(ox + t * dx, oy + t * dy, oz + t * dz);
+        lvec = safe_normalize(lt - sp);
+      } else lvec = neg3(lt);
+      const float d = dot3(sn, lvec);
+      if (d > 0) {
+        const float dff = (1.0f - o) * d;
+        tr += dff * sr; tg += dff * sg; tb += dff * sb;
+      }
+    }
+    r = r + Kd * (1 - o) * tr;
+    g = g + Kd * (1 - o) * tg;
+    b = b + Kd * (1 - o) * tb;
+    o = o + Kd * (1 - o) * o;
+  }
+  R.r[i] = r; R.g[i] = g; R.b[i] = b; R.o[i] = o;
+  // generateShadowRays (uses the o updated by diffuseLighting, as the reference does)
+  if (L.shadows) {
+    const float Kd = -L.Kd / nL;  // GXY_REVERSE_LIGHTING
+    long long offset = (long long)nhit * L.n_ao + (long long)h * nL;
+    const int px = R.x[i], py = R.y[i];
+    for (int k = 0; k < nL; k++) {
+      const float3 sp = f3(ox + t * dx + epsilon * sn.x, oy + t * dy + epsilon * sn.y, oz + t * dz + epsilon * sn.z);
+      const float3 lt = f3(L.lights[k][0], L.lights[k][1], L.lights[k][2]);
+      float3 lvec;
+      if (L.types[k]) lvec = safe_normalize(lt - sp);
+      else lvec = neg3(lt);
+      lvec = safe_normalize(lvec);
+      float d = dot3(sn, lvec);
+      if (d < 0) d = 0;
+      const float dff = (1.0f - o) * Kd * d;
+      O.ox[offset] = sp.x; O.oy[offset] = sp.y; O.oz[offset] = sp.z;
+      O.dx[offset] = lvec.x; O.dy[offset] = lvec.y; O.dz[offset] = lvec.z;
+      O.r[offset] = dff * sr; O.g[offset] = dff * sg; O.b[offset] = dff * sb; O.o[offset] = 0.0f;
+      O.t[offset] = 0.0f; O.tMax[offset] = __int_as_float(0x7f800000);
+      O.x[offset] = px; O.y[offset] = py; O.type[offset] = RAY_SHADOW; O.term[offset] = 0;
+      offset++;
+    }
+  }
+}
+
+int launch_shade_spawn(const DevLights &L, Rays R, int n, const int *d_hit_index, const int *d_nhit, Rays out, float epsilon,
+                       cudaStream_t st) {
+  // upper bounds for the grids (the exact hit count stays on the device)
+  if (n <= 0) return 0;
+  if (ensure_ao_tables()) return 1;
+  const int *hit_list = d_hit_index + n;
+  if (L.n_ao > 0) {
+    const long long total = (long long)n * L.n_ao;
+    const long long blocks = (total + 255) / 256;
+    ao_spawn_kernel<<<(unsigned)blocks, 256, 0, st>>>(L, R, hit_list, d_nhit, out, epsilon);
+  }
+  light_shadow_kernel<<<(n + 255) / 256, 256, 0, st>>>(L, R, hit_list, d_nhit, out, epsilon);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Box::exit_face (src/data/Box.cpp:84-97)
+__device__ __forceinline__ int exit_face(float3 mn, float3 mx, float x, float y, float z, float dx, float dy, float dz) {
+  float tx = (dx > 0.0001f) ? ((mx.x - x) / dx) : (dx < -0.0001f) ? ((mn.x - x) / dx) : FLT_MAX;
+  float ty = (dy > 0.0001f) ? ((mx.y - y) / dy) : (dy < -0.0001f) ? ((mn.y - y) / dy) : FLT_MAX;
+  float tz = (dz > 0.0001f) ? ((mx.z - z) / dz) : (dz < -0.0001f) ? ((mn.z - z) / dz) : FLT_MAX;
+  if (tx < 0) tx = FLT_MAX;
+  if (ty < 0) ty = FLT_MAX;
+  if (tz < 0) tz = FLT_MAX;
+  if (tx < ty && tx < tz) return (dx < 0) ? 0 : 1;
+  else if (ty < tz) return (dy < 0) ? 2 : 3;
+  else return (dz < 0) ? 4 : 5;
+}
+
+__device__ __forceinline__ int classify_ray(const SceneParams &P, const Rays &R, int i) {
+  const int typ = R.type[i], term = R.term[i];
+  int c = CLS_UNDETERMINED;
+  if (typ == RAY_PRIMARY) {
+    if (term & RAY_BOUNDARY) c = RAY_BOUNDARY;
+    else if ((term & RAY_OPAQUE) | (term & RAY_TIMEOUT)) c = CLS_TERMINATED;
+    else c = CLS_KEEP_HERE;
+  } else if (typ == RAY_SHADOW) {
+    if ((term & RAY_OPAQUE) | (term & RAY_SURFACE)) c = CLS_TERMINATED;
+    else if (term & RAY_BOUNDARY) c = RAY_BOUNDARY;
+    else c = CLS_DROP_ON_FLOOR;
+  } else if (typ == RAY_AO) {
+    if ((term & RAY_OPAQUE) | (term & RAY_SURFACE)) c = CLS_TERMINATED;
+    else if (term & RAY_BOUNDARY) c = RAY_BOUNDARY;
+    else c = CLS_DROP_ON_FLOOR;  // TIMEOUT or unknown
+  }
+  if (c == RAY_BOUNDARY) {
+    const int f = exit_face(P.lmin, P.lmax, R.ox[i], R.oy[i], R.oz[i], R.dx[i], R.dy[i], R.dz[i]);
+    const int nb = P.neighbors[f];
+    if (nb >= 0) c = nb;
+    else c = (typ == RAY_SHADOW || typ == RAY_AO) ? CLS_DROP_ON_FLOOR : CLS_TERMINATED;
+  }
+  return c;
+}
+
+__global__ void __launch_bounds__(256) classify_kernel(const __grid_constant__ SceneParams P, Rays R, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  R.classification[i] = classify_ray(P, R, i);
+}
+
+int launch_classify(const SceneParams &P, Rays R, int n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(P, R, n);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void __launch_bounds__(256)
+    accumulate_kernel(Rays R, int n, float *__restrict__ fb, int w, int h, unsigned long long *__restrict__ d_terminated) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool term = i < n && R.classification[i] == CLS_TERMINATED;
+  if (term) {
+    const int x = R.x[i], y = R.y[i];
+    if (x >= 0 && x < w && y >= 0 && y < h) {
+      float4 *p = reinterpret_cast<float4 *>(fb) + ((size_t)y * w + x);
+      atomicAdd(p, make_float4(R.r[i], R.g[i], R.b[i], R.o[i]));  // red.global.add.v4.f32 (sm_90+)
+    }
+  }
+  if (d_terminated) {
+    const unsigned b = __ballot_sync(0xffffffffu, term);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(d_terminated, (unsigned long long)__popc(b));
+  }
+}
+
+int launch_accumulate(Rays R, int n, float *fb, int w, int h, unsigned long long *d_terminated, cudaStream_t st) {
+  if (n <= 0) return 0;
+  accumulate_kernel<<<(n + 255) / 256, 256, 0, st>>>(R, n, fb, w, h, d_terminated);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// counting sort by destination (Renderer.cpp:561-618).  KEEP_HERE rays are re-queued locally by
+// the caller mapping them to its own rank before this runs (keep_rank).
+__global__ void __launch_bounds__(256) dest_count_kernel(Rays R, int n, int nranks, int keep_rank, int *__restrict__ counts) {
+  extern __shared__ int s_counts[];
+  for (int k = threadIdx.x; k < nranks; k += blockDim.x) s_counts[k] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int c = R.classification[i];
+    if (c == CLS_KEEP_HERE) c = keep_rank;
+    if (c >= 0 && c < nranks) atomicAdd(&s_counts[c], 1);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nranks; k += blockDim.x)
+    if (s_counts[k]) atomicAdd(&counts[k], s_counts[k]);
+}
+__global__ void dest_offsets_kernel(const int *__restrict__ counts, int nranks, int *__restrict__ offsets, int *__restrict__ cursor) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int acc = 0;
+    for (int k = 0; k < nranks; k++) { offsets[k] = acc; cursor[k] = acc; acc += counts[k]; }
+    offsets[nranks] = acc;
+  }
+}
+__global__ void __launch_bounds__(256) dest_scatter_kernel(Rays R, int n, int nranks, int keep_rank, Rays O, int *__restrict__ cursor) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = R.classification[i];
+  if (c == CLS_KEEP_HERE) c = keep_rank;
+  if (c < 0 || c >= nranks) return;
+  const int j = atomicAdd(&cursor[c], 1);
+  // live columns only: surface/normal/sample/classification are dead across a hop
+  O.ox[j] = R.ox[i]; O.oy[j] = R.oy[i]; O.oz[j] = R.oz[i];
+  O.dx[j] = R.dx[i]; O.dy[j] = R.dy[i]; O.dz[j] = R.dz[i];
+  O.r[j] = R.r[i]; O.g[j] = R.g[i]; O.b[j] = R.b[i]; O.o[j] = R.o[i];
+  O.t[j] = R.t[i]; O.tMax[j] = R.tMax[i];
+  O.x[j] = R.x[i]; O.y[j] = R.y[i]; O.type[j] = R.type[i]; O.term[j] = R.term[i];
+}
+
+int launch_partition_by_destination(Rays R, int n, int nranks, int keep_rank, Rays out, int *d_counts, int *d_offsets, int *d_cursor,
+                                    cudaStream_t st) {
+  GXY_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int) * nranks, st));
+  if (n > 0) dest_count_kernel<<<(n + 255) / 256, 256, sizeof(int) * nranks, st>>>(R, n, nranks, keep_rank, d_counts);
+  dest_offsets_kernel<<<1, 32, 0, st>>>(d_counts, nranks, d_offsets, d_cursor);
+  if (n > 0) dest_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(R, n, nranks, keep_rank, out, d_cursor);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Box::intersect (src/data/Box.cpp:107-150)
+__device__ __forceinline__ bool box_intersect(float3 mn, float3 mx, float3 org, float3 dir, float &tmin, float &tmax) {
+  tmin = (mn.x - org.x) / dir.x;
+  tmax = (mx.x - org.x) / dir.x;
+  if (tmin > tmax) { float s = tmax; tmax = tmin; tmin = s; }
+  if (tmax < 0) return false;
+  float tymin = (mn.y - org.y) / dir.y, tymax = (mx.y - org.y) / dir.y;
+  if (tymin > tymax) { float s = tymax; tymax = tymin; tymin = s; }
+  if (tymax < 0) return false;
+  if ((tmin > tymax) || (tymin > tmax)) return false;
+  if (tymin > tmin) tmin = tymin;
+  if (tymax < tmax) tmax = tymax;
+  float tzmin = (mn.z - org.z) / dir.z, tzmax = (mx.z - org.z) / dir.z;
+  if (tzmin > tzmax) { float s = tzmax; tzmax = tzmin; tzmin = s; }
+  if (tzmax < 0) return false;
+  if ((tmin > tzmax) || (tzmin > tmax)) return false;
+  if (tzmin > tmin) tmin = tzmin;
+  if (tzmax < tmax) tmax = tzmax;
+  if (tmin < 0) tmin = 0;
+  return true;
+}
+
+// Camera::SpawnRays per pixel (Camera.cpp:403-441)
+__device__ __forceinline__ bool spawn_pixel(const SceneParams &P, const DevCamera &a, int x, int y, float3 &vorigin, float3 &vray) {
+  const float fx = ((float)x - a.off_x) * a.scaling;
+  const float fy = ((float)y - a.off_y) * a.scaling;
+  float3 xy;
+  xy.x = a.center.x + fx * a.vr.x + fy * a.vu.x;
+  xy.y = a.center.y + fx * a.vr.y + fy * a.vu.y;
+  xy.z = a.center.z + fx * a.vr.z + fy * a.vu.z;
+  if (a.ortho) { vorigin = xy - a.vdir; vray = a.vdir; }
+  else { vorigin = a.veye; vray = xy - a.veye; normalize_gxy(vray); }
+  float gmin, gmax, lmin = 0, lmax = 0;
+  bool hit = box_intersect(P.gmin, P.gmax, vorigin, vray, gmin, gmax);
+  if (hit) hit = box_intersect(P.lmin, P.lmax, vorigin, vray, lmin, lmax);
+  const float d = fabsf(lmin) - fabsf(gmin);
+  return hit && (lmax >= 0) && (d < 0.000001f) && (d > -0.000001f);
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+    generate_count_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevCamera C, int w, int npix,
+                          int *__restrict__ block_sums) {
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    const int p = base + k;
+    float3 o, d;
+    if (p < npix && spawn_pixel(P, C, p % w, p / w, o, d)) c++;
+  }
+  int tot;
+  block_exclusive_scan(c, &tot);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(SCAN_THREADS)
+    generate_write_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevCamera C, int w, int npix,
+                          const int *__restrict__ block_sums, Rays O) {
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  float3 o[SCAN_ITEMS], d[SCAN_ITEMS];
+  bool f[SCAN_ITEMS];
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    const int p = base + k;
+    f[k] = p < npix && spawn_pixel(P, C, p % w, p / w, o[k], d[k]);
+    c += f[k] ? 1 : 0;
+  }
+  int dst = block_sums[blockIdx.x] + block_exclusive_scan(c, nullptr);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++)
+    if (f[k]) {
+      const int p = base + k;
+      O.x[dst] = p % w; O.y[dst] = p / w;
+      O.ox[dst] = o[k].x; O.oy[dst] = o[k].y; O.oz[dst] = o[k].z;
+      O.dx[dst] = d[k].x; O.dy[dst] = d[k].y; O.dz[dst] = d[k].z;
+      O.r[dst] = 0; O.g[dst] = 0; O.b[dst] = 0; O.o[dst] = 0; O.t[dst] = 0; O.tMax[dst] = FLT_MAX;
+      O.type[dst] = RAY_PRIMARY; O.term[dst] = 0;
+      dst++;
+    }
+}
+
+int launch_generate(const SceneParams &P, const DevCamera &C, int w, int h, Rays out, int *d_flags_scan, int *d_block_sums,
+                    int *d_count, cudaStream_t st) {
+  (void)d_flags_scan;
+  const int npix = w * h;
+  const int nblocks = (npix + SCAN_TILE - 1) / SCAN_TILE;
+  generate_count_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(P, C, w, npix, d_block_sums);
+  scan_block_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(d_block_sums, nblocks, d_count);
+  generate_write_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(P, C, w, npix, d_block_sums, out);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tonemap_kernel(const float4 *__restrict__ fb, int w, int h, uchar4 *__restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= w * h) return;
+  const int x = p % w, y = p / w;
+  const float4 c = fb[p];
+  // (unsigned char)(255*f): x86 cvttss2si (0x80000000 when out of range / NaN) then low byte
+  auto cvt = [](float f) -> unsigned char {
+    const float v = 255 * f;
+    int iv;
+    if (!(v > -2147483904.0f && v < 2147483648.0f)) iv = (int)0x80000000;
+    else iv = (int)v;  // cvt.rzi
+    return (unsigned char)(iv & 0xff);
+  };
+  out[(size_t)((h - 1) - y) * w + x] = make_uchar4(cvt(c.x), cvt(c.y), cvt(c.z), 0xff);
+}
+int launch_tonemap(const float *fb, int w, int h, unsigned char *rgba, cudaStream_t st) {
+  tonemap_kernel<<<(w * h + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4 *>(fb), w, h, reinterpret_cast<uchar4 *>(rgba));
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) fb_add_kernel(float4 *__restrict__ dst, const float4 *__restrict__ src, size_t n4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = dst[i];
+  const float4 b = src[i];
+  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  dst[i] = a;
+}
+int launch_fb_add(float *dst, const float *src, size_t n, cudaStream_t st) {
+  const size_t n4 = n / 4;
+  fb_add_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4 *>(dst), reinterpret_cast<const float4 *>(src), n4);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) copy_rays_kernel(Rays D, size_t doff, Rays S, size_t soff, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = blockIdx.y;  // column
+  float *const *df = &D.ox;
+  float *const *sf = &S.ox;
+  // the 5 int columns follow the 20 float columns in the struct; copy them as raw 32-bit words
+  if (c < 20) df[c][doff + i] = sf[c][soff + i];
+  else {
+    int *const *di = &D.x;
+    int *const *si = &S.x;
+    di[c - 20][doff + i] = si[c - 20][soff + i];
+  }
+}
+int launch_copy_rays(Rays dst, size_t dst_off, Rays src, size_t src_off, int n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  dim3 grid((n + 255) / 256, 24);  // classification (column 24) is dead across a hop
+  copy_rays_kernel<<<grid, 256, 0, st>>>(dst, dst_off, src, src_off, n);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gxy

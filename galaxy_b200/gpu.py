@@ -1,0 +1,345 @@
+"""ctypes binding of the product library libgxy_b200.so (include/gxy_gpu.h).
+
+Mirrors the reference's host-side objects for the hot path (Visualization / Lighting / Camera /
+RayList / Renderer::render) one to one on top of the C ABI.  There is NO fallback: if the
+library is not built or no CUDA device is usable every compute call raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+MAX_LIGHTS = 16
+
+
+class GxyError(RuntimeError):
+    pass
+
+
+class Lighting(C.Structure):
+    _fields_ = [("n_lights", C.c_int), ("lights", (C.c_float * 3) * MAX_LIGHTS), ("types", C.c_int * MAX_LIGHTS),
+                ("n_ao", C.c_int), ("ao_radius", C.c_float), ("shadows", C.c_int), ("Ka", C.c_float), ("Kd", C.c_float)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("eye", C.c_float * 3), ("dir", C.c_float * 3), ("up", C.c_float * 3), ("aov", C.c_float)]
+
+
+class TransferFunction(C.Structure):
+    _fields_ = [("colors", (C.c_float * 3) * 256), ("opacities", C.c_float * 256), ("range_lo", C.c_float), ("range_hi", C.c_float)]
+
+
+class RayListView(C.Structure):
+    _fields_ = [("base", C.POINTER(C.c_float)), ("n", C.c_int), ("aligned_n", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_longlong) for n in ("primary_rays", "shadow_rays", "ao_rays", "forwarded_rays", "terminated_rays", "traced_rays",
+                                            "waves", "kernel_launches")] + [("device_ms", C.c_float)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def library_path():
+    return os.path.join(_HERE, "libgxy_b200.so")
+
+
+def build(force=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    src_dir = os.path.join(_HERE, "csrc")
+    so = library_path()
+    srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cu", ".cuh", ".h"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "gxy_gpu.h"))
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        if not os.path.exists("/usr/local/cuda/bin/nvcc") and os.path.exists(so):
+            return so
+        subprocess.check_call(["make", "-C", src_dir, "-j4"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = library_path()
+        if not os.path.exists(so):
+            raise GxyError("libgxy_b200.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(so)
+        fp, ip, vp = C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_void_p
+        L.gxy_last_error.restype = C.c_char_p
+        L.gxy_version.restype = C.c_char_p
+        L.gxy_context_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.gxy_context_destroy.argtypes = [vp]
+        L.gxy_context_synchronize.argtypes = [vp]
+        L.gxy_volume_create.argtypes = [vp, ip, fp, fp, C.c_int, vp, C.POINTER(vp)]
+        L.gxy_volume_destroy.argtypes = [vp]
+        L.gxy_triangles_create.argtypes = [vp, C.c_int, fp, fp, fp, C.c_int, ip, C.POINTER(vp)]
+        L.gxy_triangles_destroy.argtypes = [vp]
+        L.gxy_particles_create.argtypes = [vp, C.c_int, fp, fp, C.POINTER(vp)]
+        L.gxy_particles_destroy.argtypes = [vp]
+        L.gxy_vis_create.argtypes = [vp, C.POINTER(vp)]
+        L.gxy_vis_destroy.argtypes = [vp]
+        L.gxy_vis_set_partition.argtypes = [vp, fp, fp, fp, fp, ip]
+        L.gxy_vis_add_volume.argtypes = [vp, vp, C.c_int, fp, C.c_int, fp, C.c_int, C.POINTER(TransferFunction)]
+        L.gxy_vis_add_triangles.argtypes = [vp, vp, C.POINTER(TransferFunction)]
+        L.gxy_vis_add_particles.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(TransferFunction)]
+        L.gxy_vis_commit.argtypes = [vp]
+        L.gxy_vis_build_info.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), fp]
+        L.gxy_resolve_lights.argtypes = [C.POINTER(Lighting), C.POINTER(Camera), C.POINTER(Lighting)]
+        L.gxy_resample_transfer_function.argtypes = [C.c_int, fp, C.c_int, fp, C.POINTER(TransferFunction)]
+        L.gxy_factor.argtypes = [C.c_int, ip]
+        L.gxy_partition.argtypes = [C.c_int, ip, ip, ip]
+        L.gxy_trace_raylist.argtypes = [vp, C.POINTER(Lighting), RayListView, C.c_float, C.POINTER(vp), ip]
+        L.gxy_raylist_get_view.argtypes = [vp, C.POINTER(RayListView)]
+        L.gxy_raylist_free.argtypes = [vp]
+        L.gxy_classify.argtypes = [vp, RayListView]
+        L.gxy_generate_rays.argtypes = [vp, C.POINTER(Camera), C.c_int, C.c_int, RayListView, ip]
+        L.gxy_intersect.argtypes = [vp, C.c_int, fp, fp, fp, fp, ip, fp]
+        L.gxy_render.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(Camera), C.POINTER(Lighting), C.c_int, C.c_int, C.c_float, C.POINTER(Stats)]
+        L.gxy_frame_download_rgba32f.argtypes = [vp, fp]
+        L.gxy_frame_download_rgba8.argtypes = [vp, C.POINTER(C.c_ubyte)]
+        L.gxy_comm_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
+        L.gxy_comm_init.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]
+        L.gxy_comm_destroy.argtypes = [vp]
+        _LIB = L
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        raise GxyError(lib().gxy_last_error().decode())
+
+
+def device_count():
+    return lib().gxy_device_count()
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def make_lighting(d):
+    L = Lighting()
+    L.n_lights = len(d["lights"])
+    for i, (l, t) in enumerate(zip(d["lights"], d["types"])):
+        for k in range(3):
+            L.lights[i][k] = l[k]
+        L.types[i] = t
+    L.n_ao, L.ao_radius, L.shadows, L.Ka, L.Kd = d["n_ao"], d["ao_radius"], int(d["shadows"]), d["Ka"], d["Kd"]
+    return L
+
+
+def lighting_to_dict(L):
+    return dict(lights=[[L.lights[i][k] for k in range(3)] for i in range(L.n_lights)], types=[L.types[i] for i in range(L.n_lights)],
+                n_ao=L.n_ao, ao_radius=L.ao_radius, shadows=bool(L.shadows), Ka=L.Ka, Kd=L.Kd)
+
+
+def make_camera(d):
+    c = Camera()
+    for k in range(3):
+        c.eye[k], c.dir[k], c.up[k] = d["eye"][k], d["dir"][k], d["up"][k]
+    c.aov = d["aov"]
+    return c
+
+
+def make_tf(colors, opacities, lo, hi):
+    tf = TransferFunction()
+    col, op = _f32(colors).reshape(256, 3), _f32(opacities).reshape(256)
+    C.memmove(tf.colors, col.ctypes.data, 256 * 3 * 4)
+    C.memmove(tf.opacities, op.ctypes.data, 256 * 4)
+    tf.range_lo, tf.range_hi = lo, hi
+    return tf
+
+
+class Context:
+    _default = {}
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        check(lib().gxy_context_create(device, C.byref(self.h)))
+        self.device = device
+
+    @classmethod
+    def default(cls, device=0):
+        if device not in cls._default:
+            cls._default[device] = Context(device)
+        return cls._default[device]
+
+    def synchronize(self):
+        check(lib().gxy_context_synchronize(self.h))
+
+    def comm_init(self, rank, nranks, uid):
+        buf = (C.c_ubyte * 128)(*uid)
+        check(lib().gxy_comm_init(self.h, rank, nranks, buf))
+
+
+def comm_unique_id():
+    buf = (C.c_ubyte * 128)()
+    check(lib().gxy_comm_unique_id(buf))
+    return bytes(buf)
+
+
+class Scene:
+    """One partition's Visualization on one GPU (gxy_vis + the datasets it owns)."""
+
+    def __init__(self, ctx=None, device=0):
+        self.ctx = ctx or Context.default(device)
+        self.h = C.c_void_p()
+        check(lib().gxy_vis_create(self.ctx.h, C.byref(self.h)))
+        self._volumes = {}
+        self._owned = []
+
+    def __del__(self):
+        try:
+            L = lib()
+            if getattr(self, "h", None):
+                L.gxy_vis_destroy(self.h)
+                self.h = None
+            for kind, h in getattr(self, "_owned", []):
+                getattr(L, "gxy_%s_destroy" % kind)(h)
+            self._owned = []
+        except Exception:
+            pass
+
+    def set_partition(self, gmin, gmax, lmin, lmax, neighbors):
+        a = [_f32(x) for x in (gmin, gmax, lmin, lmax)]
+        n = np.ascontiguousarray(neighbors, dtype=np.int32)
+        check(lib().gxy_vis_set_partition(self.h, _f(a[0]), _f(a[1]), _f(a[2]), _f(a[3]), _i(n)))
+
+    def add_volume_vis(self, dataset_id, dims, origin, spacing, voxels, slices, isovalues, volume_render, colors, opacities, lo, hi):
+        if dataset_id not in self._volumes:
+            voxels = np.ascontiguousarray(voxels)
+            assert voxels.dtype in (np.float32, np.uint8)
+            d = np.ascontiguousarray(dims, dtype=np.int32)
+            o, s = _f32(origin), _f32(spacing)
+            h = C.c_void_p()
+            check(lib().gxy_volume_create(self.ctx.h, _i(d), _f(o), _f(s), 0 if voxels.dtype == np.float32 else 1,
+                                          voxels.ctypes.data_as(C.c_void_p), C.byref(h)))
+            self._volumes[dataset_id] = h
+            self._owned.append(("volume", h))
+        sl = _f32(np.asarray(slices, dtype=np.float32).reshape(-1, 4)) if len(slices) else np.zeros((0, 4), np.float32)
+        iso = _f32(isovalues) if len(isovalues) else np.zeros((0,), np.float32)
+        tf = make_tf(colors, opacities, lo, hi)
+        check(lib().gxy_vis_add_volume(self.h, self._volumes[dataset_id], len(sl), _f(sl), len(iso), _f(iso), int(volume_render), C.byref(tf)))
+
+    def add_triangles_vis(self, verts, normals, data, indices, colors, opacities, lo, hi):
+        verts, normals, data = _f32(verts), _f32(normals), _f32(data)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        h = C.c_void_p()
+        check(lib().gxy_triangles_create(self.ctx.h, len(verts), _f(verts), _f(normals), _f(data), len(indices), _i(indices), C.byref(h)))
+        self._owned.append(("triangles", h))
+        tf = make_tf(colors, opacities, lo, hi)
+        check(lib().gxy_vis_add_triangles(self.h, h, C.byref(tf)))
+
+    def add_particles_vis(self, centers, data, radius0, radius1, value0, value1, colors, opacities, lo, hi):
+        centers, data = _f32(centers), _f32(data)
+        h = C.c_void_p()
+        check(lib().gxy_particles_create(self.ctx.h, len(centers), _f(centers), _f(data), C.byref(h)))
+        self._owned.append(("particles", h))
+        tf = make_tf(colors, opacities, lo, hi)
+        check(lib().gxy_vis_add_particles(self.h, h, radius0, radius1, value0, value1, C.byref(tf)))
+
+    def commit(self):
+        check(lib().gxy_vis_commit(self.h))
+
+    def build_info(self):
+        a, b, ms = C.c_longlong(), C.c_longlong(), C.c_float()
+        check(lib().gxy_vis_build_info(self.h, C.byref(a), C.byref(b), C.byref(ms)))
+        return dict(n_prims=a.value, n_nodes=b.value, build_ms=ms.value)
+
+    # -- per-list entry points (TraceRays::Trace etc.) ------------------------------------------
+    def trace_raylist(self, lighting, rays, n, epsilon=0.001, want_hits=False):
+        assert rays.dtype == np.float32 and rays.flags.c_contiguous and rays.shape[0] == 25
+        hits = np.empty((n, 2), np.int32) if want_hits else None
+        L = make_lighting(lighting)
+        view = RayListView(_f(rays), n, rays.shape[1])
+        out_h = C.c_void_p()
+        check(lib().gxy_trace_raylist(self.h, C.byref(L), view, epsilon, C.byref(out_h), _i(hits)))
+        out, nout = None, 0
+        if out_h:
+            ov = RayListView()
+            check(lib().gxy_raylist_get_view(out_h, C.byref(ov)))
+            nout = ov.n
+            out = np.ctypeslib.as_array(ov.base, shape=(25, ov.aligned_n)).copy()
+            lib().gxy_raylist_free(out_h)
+        return out, nout, hits
+
+    def classify(self, rays, n):
+        check(lib().gxy_classify(self.h, RayListView(_f(rays), n, rays.shape[1])))
+
+    def generate_rays(self, camera, w, h):
+        al = max(16, (w * h + 15) & ~15)
+        rays = np.zeros((25, al), np.float32)
+        cam = make_camera(camera)
+        n = C.c_int()
+        check(lib().gxy_generate_rays(self.h, C.byref(cam), w, h, RayListView(_f(rays), 0, al), C.byref(n)))
+        return rays, n.value
+
+    def intersect(self, org, dir, tnear, tfar):
+        org, dir, tnear, tfar = _f32(org), _f32(dir), _f32(tnear), _f32(tfar)
+        n = len(org)
+        ids = np.empty((n, 2), np.int32)
+        tuv = np.empty((n, 3), np.float32)
+        check(lib().gxy_intersect(self.h, n, _f(org), _f(dir), _f(tnear), _f(tfar), _i(ids), _f(tuv)))
+        return ids, tuv
+
+    def download_rgba32f(self, w, h):
+        fb = np.empty((h, w, 4), np.float32)
+        check(lib().gxy_frame_download_rgba32f(self.h, _f(fb)))
+        return fb
+
+    def download_rgba8(self, w, h):
+        out = np.empty((h, w, 4), np.uint8)
+        check(lib().gxy_frame_download_rgba8(self.h, out.ctypes.data_as(C.POINTER(C.c_ubyte))))
+        return out
+
+
+def render_device(parts, camera, lighting, w, h, epsilon=0.001):
+    """Renderer::render for one frame; the framebuffer stays on the device of parts[0]."""
+    arr = (C.c_void_p * len(parts))(*[p.h for p in parts])
+    cam, L, st = make_camera(camera), make_lighting(lighting), Stats()
+    check(lib().gxy_render(len(parts), arr, C.byref(cam), C.byref(L), w, h, epsilon, C.byref(st)))
+    return st.as_dict()
+
+
+def render(parts, camera, lighting, w, h, epsilon=0.001, **_ignored):
+    """Same interface as oracle.render: (fb float32 (h,w,4) y-up, stats)."""
+    st = render_device(parts, camera, lighting, w, h, epsilon)
+    return parts[0].download_rgba32f(w, h), st
+
+
+def resolve_lights(lighting, camera):
+    L, cam, out = make_lighting(lighting), make_camera(camera), Lighting()
+    check(lib().gxy_resolve_lights(C.byref(L), C.byref(cam), C.byref(out)))
+    return lighting_to_dict(out)
+
+
+def resample_tf(cmap, omap):
+    cmap, omap = _f32(np.asarray(cmap).reshape(-1, 4)), _f32(np.asarray(omap).reshape(-1, 2))
+    tf = TransferFunction()
+    check(lib().gxy_resample_transfer_function(len(cmap), _f(cmap), len(omap), _f(omap), C.byref(tf)))
+    return np.ctypeslib.as_array(tf.colors).reshape(256, 3).copy(), np.ctypeslib.as_array(tf.opacities).copy()
+
+
+def factor(n):
+    f = np.zeros(3, np.int32)
+    lib().gxy_factor(n, _i(f))
+    return tuple(int(x) for x in f)
+
+
+def partition(n, factors, grid):
+    out = np.zeros((n, 15), np.int32)
+    f, g = np.asarray(factors, np.int32), np.asarray(grid, np.int32)
+    lib().gxy_partition(n, _i(f), _i(g), _i(out))
+    return out

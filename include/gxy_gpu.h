@@ -1,0 +1,198 @@
+/*
+ * gxy_gpu.h -- C ABI of the B200-native (sm_100a) implementation of Galaxy's ray-rendering
+ * hot path: "trace a RayList against a Visualization" (BVH traversal + ray/triangle +
+ * ray/sphere, volume march with isosurface/slice detection, lighting + secondary rays,
+ * classify/forward between spatial partitions, additive framebuffer).
+ *
+ * This is the drop-in boundary.  In the reference the C++ host reaches native code for this path
+ * only through the ISPC `export` functions (extern "C", void* handles) and the OSPRay C API;
+ * every entry point below names the reference interface it replaces (file:line relative to the
+ * TACC/Galaxy tree).  Plain pointers and sizes only; no torch / CUDA types in the signatures.
+ * INTEGRATION.md shows the reference-side bindings a Galaxy maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; gxy_last_error() gives the text.
+ *    Nothing ever calls exit() (the reference prints and exit(1)s, e.g. Renderer.cpp:377).
+ *  - host buffers passed in are copied to the device at create/commit time (the reference shares
+ *    them, OSP_DATA_SHARED_BUFFER, OsprayVolume.cpp:36-37); the device owns its copy.
+ *  - there is NO CPU fallback: if no CUDA device is usable every compute entry fails loudly.
+ */
+#ifndef GXY_GPU_H
+#define GXY_GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GXY_MAX_LIGHTS     16
+#define GXY_MAX_VOLUME_VIS 8    /* reference: 100 (TraceRays.ispc:455) */
+#define GXY_MAX_SLICES     16
+#define GXY_MAX_ISOVALUES  16
+#define GXY_RAYLIST_COLUMNS 25
+
+typedef struct gxy_context   gxy_context;    /* one CUDA device + stream + memory pools          */
+typedef struct gxy_volume    gxy_volume;     /* src/data/Volume + src/ospray/OsprayVolume         */
+typedef struct gxy_triangles gxy_triangles;  /* src/data/Triangles + OsprayTriangles              */
+typedef struct gxy_particles gxy_particles;  /* src/data/Particles + OsprayParticles              */
+typedef struct gxy_vis       gxy_vis;        /* src/renderer/Visualization (one partition)        */
+typedef struct gxy_raylist   gxy_raylist;    /* src/renderer/Rays.h RayList, library-owned        */
+
+/* Lighting_ispc (src/renderer/Lighting.ih:23-32; Lighting_Set{Lights,K,AO,ShadowFlag},
+ * Lighting.ispc:54-134). */
+typedef struct {
+  int   n_lights;
+  float lights[GXY_MAX_LIGHTS][3];
+  int   types[GXY_MAX_LIGHTS];      /* 0 directional, 1 camera-relative, 2 point (Lighting.cpp:59-115) */
+  int   n_ao;
+  float ao_radius;
+  int   shadows;
+  float Ka, Kd;
+} gxy_lighting;
+
+/* Camera (src/renderer/Camera.h:199-204). */
+typedef struct {
+  float eye[3];
+  float dir[3];
+  float up[3];
+  float aov;                         /* degrees; 0 => orthographic (Camera.cpp:548-556) */
+} gxy_camera;
+
+/* transfer function as handed to OSPRay by MappedVis::local_commit (MappedVis.cpp:277-338):
+ * 256 colours, 256 opacities, valueRange. */
+typedef struct {
+  float colors[256][3];
+  float opacities[256];
+  float range_lo, range_hi;
+} gxy_transfer_function;
+
+/* RayList_ispc (src/renderer/Rays.ih:20-47; layout Rays.cpp:42-204): 25 columns of aligned_n
+ * 4-byte entries, order ox oy oz dx dy dz nx ny nz sample r g b o sr sg sb so t tMax (float),
+ * x y type term classification (int).  base points at column 0 (host memory). */
+typedef struct {
+  float *base;
+  int    n;
+  int    aligned_n;
+} gxy_raylist_view;
+
+typedef struct {
+  long long primary_rays;     /* originated (Camera.cpp:475)                                  */
+  long long shadow_rays;      /* spawned (TraceRays.cpp:98-122)                               */
+  long long ao_rays;
+  long long forwarded_rays;   /* sent to a neighbour partition (Renderer.cpp:620-634)         */
+  long long terminated_rays;  /* contributions added to the framebuffer (Rendering.cpp:125-153) */
+  long long traced_rays;      /* rays passed through the trace kernel, incl. re-traces        */
+  long long waves;            /* trace launches                                               */
+  long long kernel_launches;  /* kernels of this library launched for the frame               */
+  float     device_ms;        /* CUDA-event time, generation -> last framebuffer add          */
+} gxy_stats;
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char *gxy_last_error(void);
+const char *gxy_version(void);
+/* number of usable CUDA devices (0 => every compute entry point will fail) */
+int gxy_device_count(void);
+
+/* ---- context ---------------------------------------------------------------------------- */
+int  gxy_context_create(int device, gxy_context **out);
+void gxy_context_destroy(gxy_context *);
+int  gxy_context_synchronize(gxy_context *);
+
+/* ---- datasets (partition-local data, copied H2D once) -------------------------------------- */
+/* replaces ospNewVolume("shared_structured_volume") + ospSet* in OsprayVolume::OsprayVolume
+ * (src/ospray/OsprayVolume.cpp:25-52).  dims/origin are those of the GHOSTED brick
+ * (Volume.h:124-129), voxels x-fastest, type 0 = float32, 1 = uint8. */
+int  gxy_volume_create(gxy_context *, const int dims[3], const float origin[3], const float spacing[3],
+                       int type, const void *voxels, gxy_volume **out);
+void gxy_volume_destroy(gxy_volume *);
+
+/* replaces ospNewGeometry("ddtriangles") + ospSetData (src/ospray/OsprayTriangles.cpp:25-57):
+ * float3 vertices / normals (normals may be NULL), per-vertex data (may be NULL), int3 indices. */
+int  gxy_triangles_create(gxy_context *, int n_verts, const float *verts, const float *normals,
+                          const float *data, int n_tris, const int *indices, gxy_triangles **out);
+void gxy_triangles_destroy(gxy_triangles *);
+
+/* replaces ospNewGeometry("ddspheres") (src/ospray/OsprayParticles.cpp:34-40): float3 centres,
+ * per-particle data (may be NULL). */
+int  gxy_particles_create(gxy_context *, int n, const float *centers, const float *data, gxy_particles **out);
+void gxy_particles_destroy(gxy_particles *);
+
+/* ---- Visualization ------------------------------------------------------------------------ */
+int  gxy_vis_create(gxy_context *, gxy_vis **out);
+void gxy_vis_destroy(gxy_vis *);
+/* Visualization_commit boxes (src/renderer/Visualization.ispc:48-93) + neighbours
+ * (Visualization.cpp:139-160; Volume.cpp:358-377; -1 = no neighbour on that face). */
+int  gxy_vis_set_partition(gxy_vis *, const float gmin[3], const float gmax[3], const float lmin[3],
+                           const float lmax[3], const int neighbors[6]);
+/* VolumeVis operator: VolumeVis_SetSlices/SetIsovalues/SetVolumeRenderFlag (VolumeVis.ispc:57-91)
+ * + MappedVis_set_transferFunction.  Operators on the same gxy_volume share the volume object's
+ * transfer function for DVR (last added wins, MappedVis.cpp:206-212). */
+int  gxy_vis_add_volume(gxy_vis *, gxy_volume *, int n_slices, const float *slices4, int n_isovalues,
+                        const float *isovalues, int volume_render, const gxy_transfer_function *);
+/* TrianglesVis operator (geomID = order among geometry operators, Visualization.cpp:270-273) */
+int  gxy_vis_add_triangles(gxy_vis *, gxy_triangles *, const gxy_transfer_function *);
+/* ParticlesVis operator; radius0/1 value0/1 per ParticlesVis.cpp:136-144 */
+int  gxy_vis_add_particles(gxy_vis *, gxy_particles *, float radius0, float radius1, float value0,
+                           float value1, const gxy_transfer_function *);
+/* Visualization::SetOsprayObjects -> ospCommit(model) (Visualization.cpp:207-285): builds the
+ * BVH over all geometry operators on the device. */
+int  gxy_vis_commit(gxy_vis *);
+/* build statistics of the last commit: primitives, wide nodes, build milliseconds */
+int  gxy_vis_build_info(gxy_vis *, long long *n_prims, long long *n_nodes, float *build_ms);
+
+/* ---- host-side helpers that the reference keeps in C++ ------------------------------------ */
+/* Rendering::resolve_lights (src/renderer/Rendering.cpp:157-216) */
+int  gxy_resolve_lights(const gxy_lighting *in, const gxy_camera *, gxy_lighting *out);
+/* MappedVis::local_commit resampling (src/renderer/MappedVis.cpp:277-338); cmap n x (x,r,g,b),
+ * omap m x (x,o); range is NOT touched. */
+int  gxy_resample_transfer_function(int n, const float *cmap4, int m, const float *omap2,
+                                    gxy_transfer_function *out);
+/* Volume partitioning (src/data/Volume.cpp:88-172) */
+void gxy_factor(int n, int factors[3]);
+/* out: per part 15 ints ijk[3] offsets[3] counts[3] goffsets[3] gcounts[3], rank order */
+void gxy_partition(int n, const int factors[3], const int grid[3], int *out);
+
+/* ---- per-RayList entry points (the reference's hot call) ------------------------------------ */
+/* TraceRays::Trace (src/renderer/TraceRays.cpp:68-146), i.e. ispc::TraceRays_TraceRays +
+ * _ambientLighting + _generateAORays + _diffuseLighting + _generateShadowRays
+ * (TraceRays.ispc:326,625,735,763,859).  rays (host) are traced in place; *out receives the
+ * SECONDARY list (NULL if no ray was spawned), library-owned.  lights must be resolved.
+ * hit_ids (may be NULL): 2 ints per ray, nearest-hit (geomID, primID) or (-1,-1). */
+int  gxy_trace_raylist(gxy_vis *, const gxy_lighting *lights, gxy_raylist_view rays, float epsilon,
+                       gxy_raylist **out, int *hit_ids);
+int  gxy_raylist_get_view(gxy_raylist *, gxy_raylist_view *view);
+void gxy_raylist_free(gxy_raylist *);
+/* Renderer::Classify + AssignDestinations (src/renderer/Renderer.cpp:304-454) */
+int  gxy_classify(gxy_vis *, gxy_raylist_view rays);
+/* Camera::generate_initial_rays + SpawnRays (src/renderer/Camera.cpp:379-493,528-829) for this
+ * partition; rays.aligned_n >= w*h; *n_out = number of rays kept, in pixel order. */
+int  gxy_generate_rays(gxy_vis *, const gxy_camera *, int w, int h, gxy_raylist_view rays, int *n_out);
+/* nearest-hit only (rtcIntersect through Model.ih:54-70): org/dir 3 floats per ray */
+int  gxy_intersect(gxy_vis *, int n, const float *org3, const float *dir3, const float *tnear,
+                   const float *tfar, int *geom_prim2, float *tuv3);
+
+/* ---- frame level ------------------------------------------------------------------------- */
+/* Renderer::local_render + the processRays loop + Rendering::AddLocalPixels, all on device
+ * (src/renderer/Renderer.cpp:179-269,504-656; Rendering.cpp:125-153).  parts[0..nparts) are the
+ * partitions driven by THIS process (normally 1; several partitions on one device are allowed
+ * and exchange rays by device copies).  If a communicator is attached (gxy_comm_init) the
+ * partitions of all ranks take part and rays are exchanged with NCCL send/recv.
+ * lights are unresolved (resolve_lights is applied).  The float framebuffer (w*h*4, y up) stays
+ * on the device of parts[0] (image owner = rank 0); fetch it with gxy_frame_download_*. */
+int  gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *, const gxy_lighting *, int w, int h,
+                float epsilon, gxy_stats *stats);
+/* D2H of the last frame: float RGBA (y up) ... */
+int  gxy_frame_download_rgba32f(gxy_vis *owner, float *fb);
+/* ... or RGBA8 rows top-down exactly as ColorImageWriter::Write does (ImageWriter.cpp:30-48) */
+int  gxy_frame_download_rgba8(gxy_vis *owner, unsigned char *rgba);
+
+/* ---- multi-process (one process per GPU) --------------------------------------------------- */
+/* replaces MessageManager's MPI transport for SendRaysMsg / SendPixelsMsg
+ * (src/framework/MessageManager.cpp:321-434; Renderer.cpp:732-836) inside one NVLink box. */
+int  gxy_comm_unique_id(unsigned char id[128]);
+int  gxy_comm_init(gxy_context *, int rank, int nranks, const unsigned char id[128]);
+int  gxy_comm_destroy(gxy_context *);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
