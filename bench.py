@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path: Mrays/s at 1080p, primary + shadow + AO rays,
+on the synthetic 100 M-triangle scene (BASELINE.json configs[4], SURVEY 8d "C5"), N GPUs of one
+node, one process per GPU.
+
+  python bench.py --gpus 1 --steps K --warmup W                (our arm, CUDA through the C ABI)
+  python bench.py --impl reference ...                         (CPU arm: the oracle port of the
+                                                                reference's algorithm on host cores)
+  torchrun ... bench.py --gpus N ...                           (N>1: spatial partitions + NCCL)
+
+A step is one frame: generation -> trace waves -> shading/secondary rays -> classify -> ray
+forwarding -> additive framebuffer.  value = (primary + shadow + AO rays of the frame) / frame time
+(re-traces of forwarded rays are not counted twice).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from galaxy_b200 import scenes  # noqa: E402
+
+W, H = 1920, 1080
+EPS = 0.001
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def c5_alg_bytes_per_ray(n_prims_in_partition, hit_fraction):
+    """B_alg = 52 + 24 + 28 h (ray I/O) + L*80 (L = ceil(log8(N/4)) 8-wide nodes) + 144 (one 4-triangle leaf)."""
+    import math
+    L = max(1, math.ceil(math.log(max(n_prims_in_partition, 8) / 4.0, 8)))
+    return 76.0 + 28.0 * hit_fraction + 80.0 * L + 144.0, L
+
+
+def cpu_sample_scene(oracle_mod, n_lat, n_lon):
+    ds, _ = scenes.c5_partition_mesh(n_lat, n_lon, 1, 0)
+    vis = scenes.c5_vis()
+    parts = scenes.build_partitions(oracle_mod, vis, {"mesh": ds}, 1)
+    return parts, vis, len(ds.indices)
+
+
+def run_cpu_baseline(steps, warmup, sample_div=1, tess_div=4):
+    """The oracle (CPU restatement of the reference's algorithm) on a bounded sample of the workload."""
+    from oracle import oracle
+    n_lat, n_lon = scenes.C5_FULL[0] // tess_div, scenes.C5_FULL[1] // tess_div
+    parts, vis, ntri = cpu_sample_scene(oracle, n_lat, n_lon)
+    cam = scenes.c5_camera()
+    w, h = W // sample_div, H // sample_div
+    cores = os.cpu_count() or 1
+    times, rays = [], 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        fb, st = oracle.render(parts, cam, vis["lighting"], w, h, EPS, nthreads=cores)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+            rays = st["primary_rays"] + st["shadow_rays"] + st["ao_rays"]
+    t = float(np.mean(times))
+    sample = "oracle port; same camera/lighting, %dx%d window (1/%d of the 1080p pixels), %d triangles (1/%d tessellation of the 100M scene); %d rays/frame" % (
+        w, h, sample_div * sample_div, ntri, tess_div * tess_div, rays)
+    return {"value": rays / t / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample}, t * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
+    ap.add_argument("--tess-div", type=int, default=1, help="divide the C5 tessellation (debug only; 1 = the 100M-triangle workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = args.gpus
+    workload = "C5 eightBalls-100M: %d triangles, 1920x1080, primary + shadow (1 light) + 8 AO rays, Triangles vis, spatial partitions=%d" % (
+        8 * 2 * (scenes.C5_FULL[0] // args.tess_div) * (scenes.C5_FULL[1] // args.tess_div), n_gpus)
+    config = {"workload": workload, "width": W, "height": H, "partitions": n_gpus, "timing": "inputs larger than L2 (scene >> 126 MB) + 256 MB L2 flush between frames"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, ms = run_cpu_baseline(max(1, args.steps), max(0, min(args.warmup, 1)))
+        line = {"metric": "Mrays/s, 1080p primary+shadow+AO", "value": cb["value"], "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config, "impl": "reference", "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from galaxy_b200 import gpu
+    if not torch.cuda.is_available() or gpu.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device; galaxy_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == n_gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    nparts = world
+
+    # ---- scene: this rank's spatial partition -------------------------------------------------
+    ctx = gpu.Context(local_rank)
+    if world > 1:
+        uid = [gpu.comm_unique_id()] if rank == 0 else [None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+    n_lat, n_lon = scenes.C5_FULL[0] // args.tess_div, scenes.C5_FULL[1] // args.tess_div
+    t0 = time.perf_counter()
+    ds, _ = scenes.c5_partition_mesh(n_lat, n_lon, nparts, rank)
+    t_gen = time.perf_counter() - t0
+    vis, cam = scenes.c5_vis(), scenes.c5_camera()
+    t0 = time.perf_counter()
+    part = scenes.build_partitions(gpu, vis, {"mesh": ds}, nparts, only_rank=rank, ctx=ctx)[0]
+    t_commit = time.perf_counter() - t0
+    info = part.build_info()
+    n_tris_local = len(ds.indices)
+    del ds
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def frame():
+        return gpu.render_device([part], cam, vis["lighting"], W, H, EPS)
+
+    for _ in range(max(3, args.warmup)):
+        flush.zero_()
+        st = frame()
+    # ---- timed region: K frames, device-timed (CUDA events on the library's stream) ------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    dev_ms, trace_ms, launches, traced = [], 0.0, 0, 0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        st = frame()
+        dev_ms.append(st["device_ms"])
+        trace_ms += st["trace_ms"]
+        launches += st["kernel_launches"]
+        traced += st["traced_rays"]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    ms_local = float(np.sum(dev_ms))
+    rays_local = st["primary_rays"] + st["shadow_rays"] + st["ao_rays"]
+    hit_local = st["shadow_rays"]  # one shadow ray per surface-hit primary (1 light)
+
+    # ---- e2e: through the public call with host buffers: camera/lights H2D, RGBA8 image D2H ------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        frame()
+        img = part.download_rgba8(W, H) if rank == 0 else None
+    barrier()
+    t_e2e = time.perf_counter() - t0
+
+    if world > 1:
+        t = torch.tensor([ms_local, t_e2e, trace_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max, t_e2e, trace_ms_max = t.tolist()
+        c = torch.tensor([rays_local, launches, traced, hit_local, st["primary_rays"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        rays_total, launches_total, traced_total, hits_total, prim_total = c.tolist()
+    else:
+        ms_max, trace_ms_max = ms_local, trace_ms
+        rays_total, launches_total, traced_total, hits_total, prim_total = rays_local, launches, traced, hit_local, st["primary_rays"]
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_per_step = ms_max / args.steps
+    value = rays_total / (ms_per_step * 1e-3) / 1e6
+    e2e_value = rays_total / (t_e2e / args.steps) / 1e6
+    peaks, peak_kind = measured_peaks()
+    hbm = float(peaks["hbm_gbs"])
+    hfrac = hits_total / max(1.0, prim_total)
+    b_alg, levels = c5_alg_bytes_per_ray(n_tris_local, hfrac)
+    # dominant kernel = trace_kernel: algorithmic bytes of the rays it traced / its summed CUDA-event time (this rank)
+    achieved = (traced / max(1, 1)) * b_alg / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                "kernel": "gxy::trace_kernel", "peak_kind": peak_kind + " (burst copy figure)", "alg_bytes_per_ray": b_alg, "bvh_levels_model": levels,
+                "trace_share_of_step": trace_ms_max / max(1e-9, ms_max)}
+    line = {"metric": "Mrays/s, 1080p primary+shadow+AO", "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 40 + 276, "d2h_bytes_per_step": W * H * 4},
+            "gpu_launches": int(launches_total), "roofline": roofline, "clocks": clocks,
+            "rays_per_frame": int(rays_total), "traced_rays_per_frame": int(traced_total / args.steps), "wall_ms_per_step": t_wall / args.steps * 1e3,
+            "scene": {"triangles_this_rank": n_tris_local, "bvh_nodes": info["n_nodes"], "bvh_build_ms": info["build_ms"], "mesh_gen_s": t_gen,
+                      "commit_s": t_commit}}
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        cb, _ = run_cpu_baseline(3, 0)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

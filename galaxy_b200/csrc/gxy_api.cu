@@ -827,6 +827,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
   std::vector<std::vector<int>> send_counts(nparts, std::vector<int>(nranks, 0)), send_offsets(nparts, std::vector<int>(nranks + 1, 0));
   std::vector<int> n_spawn(nparts, 0);
   std::vector<int> all_counts;  // multi-process: nranks x (nranks+1)
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_events;
   for (int wave = 0; wave < 100000; wave++) {
     long long pending_local = 0;
     for (int p = 0; p < nparts; p++) pending_local += n_cur[p];
@@ -838,7 +839,13 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       if (n == 0) continue;
       if (use_device(v->ctx)) return 1;
       cudaStream_t st = v->ctx->stream;
+      cudaEvent_t ta, tb;
+      GXY_CUDA(cudaEventCreate(&ta));
+      GXY_CUDA(cudaEventCreate(&tb));
+      GXY_CUDA(cudaEventRecord(ta, st));
       if (launch_trace(v->P, v->cur.v, n, epsilon, nullptr, !v->has_dvr, nullptr, st)) return 1;
+      GXY_CUDA(cudaEventRecord(tb, st));
+      trace_events.push_back(std::make_pair(ta, tb));
       if (v->hit_index.reserve((size_t)2 * n) || v->block_sums.reserve((size_t)n / 1024 + 2)) return 1;
       if (launch_hit_scan(v->cur.v, n, v->hit_index.p, v->block_sums.p, v->small.p, st)) return 1;
       S.kernel_launches += 4;
@@ -1010,6 +1017,14 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
   cudaEventElapsedTime(&S.device_ms, ev0, ev1);
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
+  for (auto &e : trace_events) {
+    float ms = 0.f;
+    cudaEventSynchronize(e.second);
+    cudaEventElapsedTime(&ms, e.first, e.second);
+    S.trace_ms += ms;
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
   for (int p = 0; p < nparts; p++) {
     gxy_vis *v = parts[p];
     if (use_device(v->ctx)) return 1;

@@ -481,3 +481,66 @@ def noise_volume(n, seed=7):
         out[k] = (eb + 0.15 * fbm3(8.0 * np.stack([X, Y, Z], -1) + 31.0, seed)).astype(f32)
     sp = 2.0 / (n - 1)
     return VolumeDataset([-1.0, -1.0, -1.0], (n, n, n), [sp, sp, sp], out)
+
+
+# ------------------------------------------------------------------------------------------------
+# C5: "eightBalls-100M" triangle scene, its Visualization, lighting and camera
+C5_FULL = (1768, 3536)  # n_lat x n_lon -> 8 x 12,503,296 = 100,026,368 triangles
+C5_CENTERS = [(x, y, z) for z in (-.5, .5) for y in (-.5, .5) for x in (-.5, .5)]
+
+
+def c5_vis():
+    return dict(annotation="", lighting=parse_lighting({"Sources": [[1, 2, -3, 0]], "shadows": True, "Ka": 0.3, "Kd": 0.7, "ao count": 8,
+                                                        "ao radius": 0.3}),
+                operators=[dict(type="TrianglesVis", dataset="mesh", colormap=[[0.3, 0.0, 0.0, 1.0], [1.0, 1.0, 1.0, 0.0]],
+                                opacitymap=[[0.0, 1.0], [1.0, 1.0]], data_range=None)])
+
+
+def c5_camera():
+    return parse_camera({"viewpoint": [3, 2, -4], "viewcenter": [0, 0, 0], "viewup": [0, 1, 0], "aov": 30})
+
+
+def eightballs_mesh_single(n_lat, n_lon, seed=11, bump=0.05):
+    th = np.linspace(0.0, math.pi, n_lat + 1)
+    ph = np.linspace(0.0, 2 * math.pi, n_lon + 1)
+    T, P = np.meshgrid(th, ph, indexing="ij")
+    d = np.stack([np.sin(T) * np.cos(P), np.sin(T) * np.sin(P), np.cos(T)], -1)
+    d[:, -1] = d[:, 0]
+    r = 0.3 * (1.0 + bump * (2.0 * fbm3(6.0 * d + 17.0, seed) - 1.0))
+    r[0, :] = r[0, 0]
+    r[-1, :] = r[-1, 0]
+    pts = (d * r[..., None]).reshape(-1, 3)
+    nrm = d.reshape(-1, 3).astype(f32)
+    i, j = np.meshgrid(np.arange(n_lat, dtype=np.int32), np.arange(n_lon, dtype=np.int32), indexing="ij")
+    a = (i * np.int32(n_lon + 1) + j).ravel()
+    b = a + np.int32(1)
+    c = a + np.int32(n_lon + 1)
+    e = c + np.int32(1)
+    tris = np.concatenate([np.stack([a, c, b], 1), np.stack([b, c, e], 1)], 0).astype(np.int32)
+    return dict(pts=pts, nrm=nrm, tris=tris)
+
+
+def c5_partition_mesh(n_lat, n_lon, nparts, rank, seed=11, ghost=0.1):
+    """The triangles of partition `rank`: every bumpy sphere whose box touches the ghost-extended
+    extent (no sphere straddles a partition plane for nparts in 1,2,4,8, so this equals the
+    reference's cell-level clipping, scripts/partitionVTUs.vpy:35,66-67).  Returns (dataset, extents)."""
+    one = eightballs_mesh_single(n_lat, n_lon, seed)
+    ext, _ = geometry_extents(nparts)
+    e = ext[rank]
+    lo = np.array([e[0], e[2], e[4]]) - ghost
+    hi = np.array([e[1], e[3], e[5]]) + ghost
+    V, N, I, D = [], [], [], []
+    nv = 0
+    for c in C5_CENTERS:
+        c = np.asarray(c)
+        if nparts > 1 and (np.any(c + 0.34 < lo) or np.any(c - 0.34 > hi)):
+            continue
+        v = (one["pts"] + c).astype(f32)
+        V.append(v)
+        N.append(one["nrm"])
+        I.append(one["tris"] + np.int32(nv))
+        D.append(np.sqrt((v.astype(np.float64) ** 2).sum(1)).astype(f32))
+        nv += len(v)
+    if not V:
+        return TrianglesDataset(np.zeros((0, 3), f32), np.zeros((0, 3), f32), np.zeros((0,), f32), np.zeros((0, 3), np.int32)), ext
+    return TrianglesDataset(np.concatenate(V), np.concatenate(N), np.concatenate(D), np.concatenate(I)), ext

@@ -84,6 +84,7 @@ typedef struct {
   long long waves;            /* trace launches                                               */
   long long kernel_launches;  /* kernels of this library launched for the frame               */
   float     device_ms;        /* CUDA-event time, generation -> last framebuffer add          */
+  float     trace_ms;         /* sum of the trace-kernel launch durations (CUDA events)       */
 } gxy_stats;
 
 /* ---- library ---------------------------------------------------------------------------- */
