@@ -39,16 +39,18 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (samples are time-stamped
+    on arrival; only those inside [mark_begin, mark_end] are used)."""
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.samples = index, None, []
+        self.t0 = self.t1 = None
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -57,7 +59,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -67,9 +75,15 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             pass
+        inside = [l for (t, l) in self.samples if self.t0 is not None and self.t0 <= t <= self.t1]
+        note = None
+        if not inside and self.samples:  # region shorter than the sampling period: nearest samples
+            mid = 0.5 * (self.t0 + self.t1)
+            inside = [l for (t, l) in sorted(self.samples, key=lambda s: abs(s[0] - mid))[:3]]
+            note = "timed region shorter than the sampling period; nearest samples used"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        for l in inside:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 7:
                 continue
@@ -81,8 +95,11 @@ class ClockSampler:
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+               "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def c5_alg_bytes_per_ray(n_prims_in_partition, hit_fraction):
@@ -124,7 +141,7 @@ def run_cpu_baseline(steps, warmup, sample_div=1, tess_div=4):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
     ap.add_argument("--tess-div", type=int, default=1, help="divide the C5 tessellation (debug only; 1 = the 100M-triangle workload)")
@@ -189,13 +206,14 @@ def main():
     def frame():
         return gpu.render_device([part], cam, vis["lighting"], W, H, EPS)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(3, args.warmup)):
         flush.zero_()
         st = frame()
     # ---- timed region: K frames, device-timed (CUDA events on the library's stream) ------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    sampler.mark_begin()
     t_wall0 = time.perf_counter()
     dev_ms, trace_ms, launches, traced = [], 0.0, 0, 0
     for _ in range(args.steps):
@@ -208,6 +226,7 @@ def main():
         traced += st["traced_rays"]
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    sampler.mark_end()
     clocks = sampler.stop()
     ms_local = float(np.sum(dev_ms))
     rays_local = st["primary_rays"] + st["shadow_rays"] + st["ao_rays"]
