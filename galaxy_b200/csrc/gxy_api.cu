@@ -480,8 +480,9 @@ int gxy_vis_commit(gxy_vis *v) {
     GXY_CUDA(cudaMalloc(&v->d_geoms, sizeof(DevGeom) * dg.size()));
     GXY_CUDA(cudaMemcpy(v->d_geoms, dg.data(), sizeof(DevGeom) * dg.size(), cudaMemcpyHostToDevice));
   }
-  GXY_CUDA(cudaMalloc(&v->d_error, sizeof(int)));
-  GXY_CUDA(cudaMemset(v->d_error, 0, sizeof(int)));
+  // [0] error flag (int) [1] ray-queue head (unsigned) [2..5] traversal counters (2 x u64)
+  GXY_CUDA(cudaMalloc(&v->d_error, 32));
+  GXY_CUDA(cudaMemset(v->d_error, 0, 32));
   if (!bi.empty()) {
     if (build_bvh(bi.data(), (int)bi.size(), &v->bvh, v->ctx->stream)) return 1;
   }
@@ -491,6 +492,8 @@ int gxy_vis_commit(gxy_vis *v) {
   P.prims = v->bvh.prims;
   P.n_prims = v->bvh.n_prims;
   P.error_flag = v->d_error;
+  P.work_counter = reinterpret_cast<unsigned *>(v->d_error) + 1;
+  P.trav_counters = reinterpret_cast<unsigned long long *>(v->d_error + 2);
   v->committed = true;
   return 0;
 }
@@ -1031,6 +1034,11 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
     unsigned long long c[4];
     GXY_CUDA(cudaMemcpy(c, v->counters.p, sizeof c, cudaMemcpyDeviceToHost));
     S.terminated_rays += (long long)c[0];
+    unsigned long long tc[2];
+    GXY_CUDA(cudaMemcpy(tc, v->P.trav_counters, sizeof tc, cudaMemcpyDeviceToHost));
+    GXY_CUDA(cudaMemset(v->P.trav_counters, 0, sizeof tc));
+    S.nodes_visited += (long long)tc[0];
+    S.prims_tested += (long long)tc[1];
     if (check_error_flag(v)) return 1;
   }
   if (stats) *stats = S;

@@ -8,10 +8,11 @@
 //   2. 63-bit Morton keys, radix sort (cub::DeviceRadixSort; build-time only, not on the frame path)
 //   3. Karras 2012 binary radix tree + bottom-up refit with atomic flags
 //   4. top-down collapse, level by level, into 8-wide nodes: repeatedly open the child with the
-//      largest surface area; subtrees of <= LEAF_MAX primitives become leaves (contiguous ranges
-//      of the sorted primitive records); child boxes quantised to 8 bits in a per-node
-//      power-of-two frame (conservative), children placed in octant order
-//   5. primitive records (48 B: v0,e1,e2 | centre,radius + ids) written in leaf order
+//      largest surface area; subtrees of <= LEAF_MAX primitives become leaves; child boxes
+//      quantised to 8 bits in a per-node power-of-two frame (conservative), children placed in
+//      octant order; the internal children of a node get consecutive node ids (in slot order)
+//      and its leaf primitives consecutive record positions (compressed-wide-BVH addressing)
+//   5. primitive records (48 B: v0,e1,e2 | centre,radius + ids) written in node order
 #include "gxy_internal.h"
 
 #include <cub/cub.cuh>
@@ -20,7 +21,7 @@
 
 namespace gxy {
 
-#define LEAF_MAX 4
+#define LEAF_MAX 3  // 8 slots x 3 primitives = the 24 primitive bits of a hit mask
 #define MAX_BUILD_GEOMS 16
 
 struct BuildGeoms {
@@ -218,7 +219,8 @@ __device__ __forceinline__ int quant_exp(float ext) {
 
 __global__ void __launch_bounds__(128)
     collapse_kernel(const __grid_constant__ BinView B, int begin, int end, int *__restrict__ wide_bin, WideNode *__restrict__ nodes,
-                    int *__restrict__ counter, int capacity, int *__restrict__ err) {
+                    int *__restrict__ counter, int capacity, unsigned *__restrict__ prim_counter, unsigned *__restrict__ dest_of,
+                    int *__restrict__ err) {
   const int wid = begin + blockIdx.x * blockDim.x + threadIdx.x;
   if (wid >= end) return;
   const int root = wide_bin[wid];
@@ -269,22 +271,32 @@ __global__ void __launch_bounds__(128)
     slot_of[m] = bests;
     used |= 1u << bests;
   }
-  // allocate ids for the internal children
-  int n_int = 0;
-  for (int m = 0; m < k; m++)
-    if (!(ch[m] < 0 || bin_count(B, ch[m]) <= LEAF_MAX)) n_int++;
+  // slot -> child
+  int child_in_slot[8];
+  for (int sl = 0; sl < 8; sl++) child_in_slot[sl] = -1;
+  for (int m = 0; m < k; m++) child_in_slot[slot_of[m]] = m;
+  // consecutive node ids for the internal children, consecutive record positions for the leaf primitives
+  int n_int = 0, n_leaf_prims = 0;
+  for (int m = 0; m < k; m++) {
+    if (ch[m] < 0 || bin_count(B, ch[m]) <= LEAF_MAX) n_leaf_prims += bin_count(B, ch[m]);
+    else n_int++;
+  }
   int base = 0;
   if (n_int) {
     base = atomicAdd(counter, n_int);
     if (base + n_int > capacity) { *err = 2; return; }
   }
+  unsigned pbase = 0;
+  if (n_leaf_prims) pbase = atomicAdd(prim_counter, (unsigned)n_leaf_prims);
   WideNode nd;
   nd.ox = ulo[0]; nd.oy = ulo[1]; nd.oz = ulo[2];
-  nd.nchild = (unsigned char)k;
-  for (int s = 0; s < 8; s++) {
-    nd.child[s] = 0;
-    nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255;  // empty slot: inverted box
-    nd.qhix[s] = nd.qhiy[s] = nd.qhiz[s] = 0;
+  nd.imask = 0;
+  nd.child_base = (unsigned)base;
+  nd.prim_base = pbase;
+  for (int sl = 0; sl < 8; sl++) {
+    nd.meta[sl] = 0;
+    nd.qlox[sl] = nd.qloy[sl] = nd.qloz[sl] = 255;  // empty slot: inverted box
+    nd.qhix[sl] = nd.qhiy[sl] = nd.qhiz[sl] = 0;
   }
   // quantisation frame per axis; verified against the exact expression the traversal uses
   int eb[3];
@@ -294,19 +306,18 @@ __global__ void __launch_bounds__(128)
       const float scale = __uint_as_float((unsigned)eb[a] << 23);
       bool ok = true;
       for (int m = 0; m < k && ok; m++) {
-        const float cl = a == 0 ? lo[m].x : a == 1 ? lo[m].y : lo[m].z;
         const float chh = a == 0 ? hi[m].x : a == 1 ? hi[m].y : hi[m].z;
         if (ceilf((chh - ulo[a]) / scale) > 255.0f) ok = false;
-        (void)cl;
       }
       if (ok) break;
       eb[a] = min(eb[a] + 1, 254);
     }
   }
   nd.ex = (unsigned char)eb[0]; nd.ey = (unsigned char)eb[1]; nd.ez = (unsigned char)eb[2];
-  int next_int = 0;
-  for (int m = 0; m < k; m++) {
-    const int s = slot_of[m];
+  int next_int = 0, poff = 0;
+  for (int sl = 0; sl < 8; sl++) {
+    const int m = child_in_slot[sl];
+    if (m < 0) continue;
     unsigned char *ql[3] = {nd.qlox, nd.qloy, nd.qloz}, *qh[3] = {nd.qhix, nd.qhiy, nd.qhiz};
     for (int a = 0; a < 3; a++) {
       const float scale = __uint_as_float((unsigned)eb[a] << 23);
@@ -317,14 +328,18 @@ __global__ void __launch_bounds__(128)
       q1 = fminf(fmaxf(q1, 0.f), 255.f);
       while (q0 > 0.f && __fmaf_rn(q0, scale, ulo[a]) > cl) q0 -= 1.f;
       while (q1 < 255.f && __fmaf_rn(q1, scale, ulo[a]) < chh) q1 += 1.f;
-      ql[a][s] = (unsigned char)q0;
-      qh[a][s] = (unsigned char)q1;
+      ql[a][sl] = (unsigned char)q0;
+      qh[a][sl] = (unsigned char)q1;
     }
     if (ch[m] < 0 || bin_count(B, ch[m]) <= LEAF_MAX) {
-      nd.child[s] = 0x80000000u | ((unsigned)bin_first(B, ch[m]) << 3) | (unsigned)(bin_count(B, ch[m]) - 1);
+      const int cnt = bin_count(B, ch[m]), first = bin_first(B, ch[m]);
+      nd.meta[sl] = (unsigned char)((((1u << cnt) - 1u) << 5) | (unsigned)poff);  // count in unary | record offset
+      for (int j = 0; j < cnt; j++) dest_of[first + j] = pbase + (unsigned)(poff + j);
+      poff += cnt;
     } else {
       const int id = base + next_int++;
-      nd.child[s] = (unsigned)id;
+      nd.meta[sl] = (unsigned char)(0x20u | (24u + (unsigned)sl));
+      nd.imask |= (unsigned char)(1u << sl);
       wide_bin[id] = ch[m];
     }
   }
@@ -340,7 +355,8 @@ __global__ void __launch_bounds__(256)
 }
 
 __global__ void __launch_bounds__(256)
-    emit_prims_kernel(const __grid_constant__ BuildGeoms B, long long N, const unsigned *__restrict__ vals, PrimRec *__restrict__ out) {
+    emit_prims_kernel(const __grid_constant__ BuildGeoms B, long long N, const unsigned *__restrict__ vals,
+                      const unsigned *__restrict__ dest_of, PrimRec *__restrict__ out) {
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= N) return;
   const long long p = vals[s];
@@ -359,7 +375,7 @@ __global__ void __launch_bounds__(256)
     r.b = make_float4(g.epsilon, 0.f, 0.f, 0.f);
     r.c = make_float4(0.f, __uint_as_float((unsigned)g.geom_id | (1u << 24)), __uint_as_float((unsigned)i), 0.f);
   }
-  out[s] = r;
+  out[dest_of[s]] = r;
 }
 
 template <typename T>
@@ -421,8 +437,9 @@ int build_bvh(const GeomBuildInput *geoms, int n_geoms, BvhResult *out, cudaStre
 
   PrimRec *prims = nullptr;
   GXY_CUDA(cudaMalloc(&prims, sizeof(PrimRec) * N));
-  emit_prims_kernel<<<gridN, 256, 0, st>>>(B, N, vals.p, prims);
-  GXY_CUDA(cudaGetLastError());
+  DevBuf<unsigned> dest_of, prim_counter;  // sorted position -> record position (node order)
+  if (dest_of.alloc(N) || prim_counter.alloc(1)) { cudaFree(prims); gxy_set_error("BVH build: out of device memory"); return 1; }
+  GXY_CUDA(cudaMemsetAsync(prim_counter.p, 0, sizeof(unsigned), st));
 
   WideNode *nodes = nullptr;
   long long n_nodes = 0;
@@ -447,11 +464,14 @@ int build_bvh(const GeomBuildInput *geoms, int n_geoms, BvhResult *out, cudaStre
       if (ext > 0.f) frexpf(ext / 255.0f, &e); else e = -126;
       *ex[a] = (unsigned char)std::max(1, std::min(e + 1 + 127, 254));  // one extra octave of slack
     }
-    nd.nchild = 1;
-    for (int s = 0; s < 8; s++) { nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255; nd.qhix[s] = nd.qhiy[s] = nd.qhiz[s] = 0; }
+    nd.imask = 0; nd.child_base = 0; nd.prim_base = 0;
+    for (int s = 0; s < 8; s++) { nd.meta[s] = 0; nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255; nd.qhix[s] = nd.qhiy[s] = nd.qhiz[s] = 0; }
     nd.qlox[0] = nd.qloy[0] = nd.qloz[0] = 0;
     nd.qhix[0] = nd.qhiy[0] = nd.qhiz[0] = 255;
-    nd.child[0] = 0x80000000u | (0u << 3) | (unsigned)(n - 1);
+    nd.meta[0] = (unsigned char)((((1u << n) - 1u) << 5) | 0u);
+    const unsigned ident[LEAF_MAX] = {0u, 1u, 2u};
+    GXY_CUDA(cudaMemcpyAsync(dest_of.p, ident, sizeof(unsigned) * n, cudaMemcpyHostToDevice, st));
+    GXY_CUDA(cudaStreamSynchronize(st));
     GXY_CUDA(cudaMalloc(&nodes, sizeof(WideNode)));
     GXY_CUDA(cudaMemcpy(nodes, &nd, sizeof nd, cudaMemcpyHostToDevice));
     n_nodes = 1;
@@ -485,7 +505,8 @@ int build_bvh(const GeomBuildInput *geoms, int n_geoms, BvhResult *out, cudaStre
     bv.n = n; bv.child = child.p; bv.range = range.p; bv.slo = slo.p; bv.shi = shi.p; bv.nlo = nlo.p; bv.nhi = nhi.p;
     int begin = 0, end = 1;
     while (begin < end) {
-      collapse_kernel<<<(end - begin + 127) / 128, 128, 0, st>>>(bv, begin, end, wide_bin.p, tmp_nodes, counter.p, capacity, err.p);
+      collapse_kernel<<<(end - begin + 127) / 128, 128, 0, st>>>(bv, begin, end, wide_bin.p, tmp_nodes, counter.p, capacity, prim_counter.p,
+                                                                 dest_of.p, err.p);
       int h_counter = 0;
       GXY_CUDA(cudaMemcpyAsync(&h_counter, counter.p, sizeof(int), cudaMemcpyDeviceToHost, st));
       GXY_CUDA(cudaStreamSynchronize(st));
@@ -503,6 +524,8 @@ int build_bvh(const GeomBuildInput *geoms, int n_geoms, BvhResult *out, cudaStre
     GXY_CUDA(cudaStreamSynchronize(st));
     cudaFree(tmp_nodes);
   }
+  emit_prims_kernel<<<gridN, 256, 0, st>>>(B, N, vals.p, dest_of.p, prims);
+  GXY_CUDA(cudaGetLastError());
   GXY_CUDA(cudaEventRecord(e1, st));
   GXY_CUDA(cudaEventSynchronize(e1));
   float ms = 0.f;

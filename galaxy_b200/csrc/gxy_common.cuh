@@ -79,17 +79,23 @@ struct DevGeom {
   int pad;
 };
 
-// 8-wide quantised BVH node, 96 bytes (6 x 16 B loads):
-//   origin (3 f32) | ex ey ez imask (4 u8) | child refs (8 u32) | qlo/qhi per axis (6 x 8 u8)
-// child ref: 0 = empty; bit31 set = leaf: bits[30:3] first primitive record, bits[2:0] count-1;
-// else index of the child node.
+// 8-wide quantised BVH node, 80 bytes (5 x 16 B loads), after Ylitie/Karras/Laine 2017 ("compressed
+// wide BVH"): children of a node are stored contiguously (internal children from child_base in slot
+// order, primitive records of its leaf children from prim_base), so a child is addressed by a
+// bit position instead of a 32-bit reference and the traversal stack holds one entry per NODE.
+//   origin (3 f32) | ex ey ez imask (4 u8) | child_base prim_base (2 u32) | meta (8 u8) | qlo/qhi per axis (6 x 8 u8)
+// imask: bit s set = slot s holds an internal node.  meta[s]: 0 = empty slot;
+//   internal: 0b001_11sss (low 5 bits = 24 + s); leaf: high 3 bits = primitive count in unary
+//   (001, 011, 111), low 5 bits = offset of its first record from prim_base (<= 21).
+// Slots are filled in octant order (bit0 = x-high, bit1 = y-high, bit2 = z-high half).
 struct __align__(16) WideNode {
   float ox, oy, oz;
-  unsigned char ex, ey, ez, nchild;
-  unsigned int child[8];
+  unsigned char ex, ey, ez, imask;
+  unsigned int child_base, prim_base;
+  unsigned char meta[8];
   unsigned char qlox[8], qloy[8], qloz[8], qhix[8], qhiy[8], qhiz[8];
 };
-static_assert(sizeof(WideNode) == 96, "WideNode must be 96 bytes");
+static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
 
 // primitive record in leaf order, 48 bytes (3 x 16 B loads)
 //   triangle: a=(v0.xyz, e1.x) b=(e1.yz, e2.xy) c=(e2.z, bits(geom|kind<<24), bits(prim), 0)
@@ -111,6 +117,8 @@ struct SceneParams {
   const PrimRec *prims;
   long long n_prims;
   int *error_flag;  // set to 1 by a kernel on traversal-stack overflow
+  unsigned *work_counter;  // ray queue head of the persistent trace kernel (zeroed before each launch)
+  unsigned long long *trav_counters;  // [0] nodes visited [1] primitives tested (only with -DGXY_TRAV_COUNTERS)
 };
 
 struct DevLights {

@@ -15,6 +15,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace gxy {
 
@@ -23,6 +24,39 @@ struct SurfHit {  // TraceRays.ispc:79-88
   float t, opacity;
   float3 normal, color;
 };
+
+// postIntersect of a geometry hit (Model.ih:97-187 + DataDrivenTriangleMesh.ispc:34-121 /
+// DataDrivenSpheres.ispc:46-63): colour from the transfer function, shading normal normalised and
+// faced towards the ray
+__device__ __forceinline__ void shade_geometry_hit(const SceneParams &P, const Hit1 &h1, float3 dir, float3 &col, float &ca, float3 &Ns) {
+  const DevGeom g = P.geoms[h1.geom];
+  float3 Ng = h1.Ng;
+  Ns = h1.Ng;
+  col = f3(1.f, 1.f, 1.f);
+  ca = 1.f;
+  if (g.kind == 0) {  // DataDrivenTriangleMesh.ispc:34-121
+    const int i0 = __ldg(g.idx + 3 * (size_t)h1.prim), i1 = __ldg(g.idx + 3 * (size_t)h1.prim + 1), i2 = __ldg(g.idx + 3 * (size_t)h1.prim + 2);
+    const float3 bary = f3(1.0f - h1.u - h1.v, h1.u, h1.v);
+    if (g.normals) {
+      const float3 a = f3(__ldg(g.normals + 3 * (size_t)i0), __ldg(g.normals + 3 * (size_t)i0 + 1), __ldg(g.normals + 3 * (size_t)i0 + 2));
+      const float3 b = f3(__ldg(g.normals + 3 * (size_t)i1), __ldg(g.normals + 3 * (size_t)i1 + 1), __ldg(g.normals + 3 * (size_t)i1 + 2));
+      const float3 c = f3(__ldg(g.normals + 3 * (size_t)i2), __ldg(g.normals + 3 * (size_t)i2 + 1), __ldg(g.normals + 3 * (size_t)i2 + 2));
+      Ns = bary.x * a + bary.y * b + bary.z * c;  // interpolate(), vec.ih:723-726
+    }
+    if (g.data) {
+      const float d = bary.x * __ldg(g.data + i0) + bary.y * __ldg(g.data + i1) + bary.z * __ldg(g.data + i2);
+      col = tf_color(P.tfs + g.tf, d);
+      ca = 1.0f;
+    }
+  } else {  // DataDrivenSpheres.ispc:46-63
+    col = tf_color(P.tfs + g.tf, g.data ? __ldg(g.data + h1.prim) : 0.f);
+    ca = 1.0f;
+  }
+  Ng = normalize_isp(Ng);
+  Ns = normalize_isp(Ns);
+  if (dot3(dir, Ng) >= 0.f) Ng = neg3(Ng);
+  if (dot3(Ng, Ns) < 0.f) Ns = neg3(Ns);
+}
 
 template <int NV>
 __device__ __forceinline__ void sample_volumes(const SceneParams &P, int nvv, float3 coord, float *s) {
@@ -107,33 +141,9 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS)
     if (found) {
       ray_t = h1.t;
       if (shadeFlag) {
-        const DevGeom g = P.geoms[h1.geom];
-        float3 Ng = h1.Ng, Ns = h1.Ng;
-        float3 col = f3(1.f, 1.f, 1.f);
-        float ca = 1.f;
-        if (g.kind == 0) {  // DataDrivenTriangleMesh.ispc:34-121
-          const int i0 = __ldg(g.idx + 3 * (size_t)h1.prim), i1 = __ldg(g.idx + 3 * (size_t)h1.prim + 1),
-                    i2 = __ldg(g.idx + 3 * (size_t)h1.prim + 2);
-          const float3 bary = f3(1.0f - h1.u - h1.v, h1.u, h1.v);
-          if (g.normals) {
-            const float3 a = f3(__ldg(g.normals + 3 * (size_t)i0), __ldg(g.normals + 3 * (size_t)i0 + 1), __ldg(g.normals + 3 * (size_t)i0 + 2));
-            const float3 b = f3(__ldg(g.normals + 3 * (size_t)i1), __ldg(g.normals + 3 * (size_t)i1 + 1), __ldg(g.normals + 3 * (size_t)i1 + 2));
-            const float3 c = f3(__ldg(g.normals + 3 * (size_t)i2), __ldg(g.normals + 3 * (size_t)i2 + 1), __ldg(g.normals + 3 * (size_t)i2 + 2));
-            Ns = bary.x * a + bary.y * b + bary.z * c;  // interpolate(), vec.ih:723-726
-          }
-          if (g.data) {
-            const float d = bary.x * __ldg(g.data + i0) + bary.y * __ldg(g.data + i1) + bary.z * __ldg(g.data + i2);
-            col = tf_color(P.tfs + g.tf, d);
-            ca = 1.0f;
-          }
-        } else {  // DataDrivenSpheres.ispc:46-63
-          col = tf_color(P.tfs + g.tf, g.data ? __ldg(g.data + h1.prim) : 0.f);
-          ca = 1.0f;
-        }
-        Ng = normalize_isp(Ng);
-        Ns = normalize_isp(Ns);
-        if (dot3(dir, Ng) >= 0.f) Ng = neg3(Ng);
-        if (dot3(Ng, Ns) < 0.f) Ns = neg3(Ns);
+        float3 col, Ns;
+        float ca;
+        shade_geometry_hit(P, h1, dir, col, ca, Ns);
         hit.color = col; hit.opacity = ca; hit.normal = Ns; hit.t = ray_t;
       }
       surface_hit = true;
@@ -248,6 +258,287 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent-warp variant of K1 for Visualizations with geometry only (no volume operators): the
+// same per-ray arithmetic as trace_kernel<0, true>, but each lane fetches a new ray from a global
+// queue as soon as FETCH_T lanes of its warp have finished theirs (Aila/Laine-style dynamic fetch),
+// so that a warp is not held by its longest ray.  Per lane: setup (clip to the local box,
+// TraceRays.ispc:377-418) -> trav_step()* -> finish (postIntersect + term, :563-610).
+struct PendingRay {
+  int ray;        // index in the list, -1 = none
+  float tExit;    // tExitVolume of MyIntersectBox
+  bool anyhit;
+};
+
+__device__ __forceinline__ bool setup_geom_ray(const SceneParams &P, const Rays &R, int i, int anyhit_secondary, RayCtx &rc, TravState &st,
+                                               PendingRay &pr) {
+  const bool shadeFlag = R.type[i] == RAY_PRIMARY;
+  const float3 org = f3(R.ox[i], R.oy[i], R.oz[i]);
+  float3 dir = f3(R.dx[i], R.dy[i], R.dz[i]);
+  if (dir.x == 0.f) dir.x = 1e-6f;  // :377-379
+  if (dir.y == 0.f) dir.y = 1e-6f;
+  if (dir.z == 0.f) dir.z = 1e-6f;
+  float ray_t0 = R.t[i], ray_t = R.tMax[i];
+  float tEntry, tExitVolume;
+  {
+    const float rx = 1.0f / dir.x, ry = 1.0f / dir.y, rz = 1.0f / dir.z;
+    const float mnx = (P.lmin.x - org.x) * rx, mny = (P.lmin.y - org.y) * ry, mnz = (P.lmin.z - org.z) * rz;
+    const float mxx = (P.lmax.x - org.x) * rx, mxy = (P.lmax.y - org.y) * ry, mxz = (P.lmax.z - org.z) * rz;
+    tEntry = fmaxf(fminf(mnx, mxx), fmaxf(fminf(mny, mxy), fminf(mnz, mxz)));
+    tExitVolume = fminf(fmaxf(mnx, mxx), fminf(fmaxf(mny, mxy), fmaxf(mnz, mxz)));
+  }
+  if (tEntry < ray_t0) tEntry = ray_t0;  // :412-413
+  else if (tEntry > ray_t0) ray_t0 = tEntry;
+  ray_t = fminf(ray_t, tExitVolume);  // :418
+  ray_ctx_init(rc, org, dir, ray_t0, ray_t);
+  trav_init(st, rc);
+  pr.ray = i;
+  pr.tExit = tExitVolume;
+  pr.anyhit = !shadeFlag && anyhit_secondary;
+  // an empty interval cannot accept any candidate (both primitive tests need tnear < t <= tfar)
+  return ray_t0 <= ray_t;
+}
+
+__device__ __forceinline__ void finish_geom_ray(const SceneParams &P, const Rays &R, const RayCtx &rc, const TravState &st,
+                                                const PendingRay &pr, int *__restrict__ hit_ids) {
+  const int i = pr.ray;
+  const bool shadeFlag = R.type[i] == RAY_PRIMARY;
+  const bool found = st.best_key != GXY_NO_HIT;
+  const float cr = R.r[i], cg = R.g[i], cb = R.b[i], co = R.o[i];  // unchanged without volumes
+  const float tTimeout = R.tMax[i];
+  float ray_t = rc.tfar;
+  int term = (min3f(cr, cg, cb) >= 1.0f || co > 0.999f) ? RAY_OPAQUE : 0;
+  if (found) {
+    ray_t = st.best_t;
+    term |= RAY_SURFACE;
+    float opacity = 1.0f;
+    if (shadeFlag) {
+      Hit1 h1;
+      trav_fetch_hit(P, rc, st, h1);
+      float3 col, Ns;
+      shade_geometry_hit(P, h1, rc.dir, col, opacity, Ns);
+      R.sr[i] = col.x; R.sg[i] = col.y; R.sb[i] = col.z; R.so[i] = 1.0f;
+      R.nx[i] = Ns.x; R.ny[i] = Ns.y; R.nz[i] = Ns.z;
+    }
+    if (!shadeFlag || opacity > 0.999f) term |= RAY_OPAQUE;  // see trace_kernel
+  } else if (ray_t == pr.tExit) term |= RAY_BOUNDARY;
+  else if (ray_t == tTimeout) term |= RAY_TIMEOUT;
+  R.t[i] = ray_t;
+  R.term[i] = term;
+  if (hit_ids) {
+    hit_ids[2 * i] = found ? (int)(st.best_key >> 28) : -1;
+    hit_ids[2 * i + 1] = found ? (int)(st.best_key & 0x0fffffffu) : -1;
+  }
+#ifdef GXY_TRAV_COUNTERS
+  atomicAdd(P.trav_counters, (unsigned long long)st.n_nodes);
+  atomicAdd(P.trav_counters + 1, (unsigned long long)st.n_prims);
+#endif
+}
+
+template <int FETCH_T, int PRIM_T, int MIN_BLOCKS, int PREFETCH>
+__global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
+    trace_geom_kernel(const __grid_constant__ SceneParams P, Rays R, int n, int *__restrict__ hit_ids, int anyhit_secondary) {
+  __shared__ uint2 stack[GXY_STACK_SMEM * GXY_TRACE_THREADS];
+  uint2 lstack[GXY_STACK_LOCAL];
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  RayCtx rc;
+  TravState st;
+  PendingRay pr;
+  pr.ray = -1; pr.tExit = 0.f; pr.anyhit = false;
+  st.tg.y = 0u; st.ng.y = 0u;
+  bool trav = false, exhausted = false;
+  while (true) {
+    // ---- refill: finished lanes write their result and fetch the next ray of the queue
+    const unsigned m_idle = __ballot_sync(FULL, !trav);
+    if (m_idle == FULL || (!exhausted && __popc(m_idle) >= FETCH_T)) {
+      bool ex_local = false;
+      if (!trav) {
+        if (pr.ray >= 0) {
+          finish_geom_ray(P, R, rc, st, pr, hit_ids);
+          pr.ray = -1;
+        }
+        if (!exhausted) {
+          const int leader = __ffs((int)m_idle) - 1;
+          const unsigned cnt = (unsigned)__popc(m_idle);
+          unsigned base = 0;
+          if ((int)lane == leader) base = atomicAdd(P.work_counter, cnt);
+          base = __shfl_sync(m_idle, base, leader);
+          const unsigned my = base + (unsigned)__popc(m_idle & ((1u << lane) - 1u));
+          ex_local = base + cnt >= (unsigned)n;
+          if (my < (unsigned)n) trav = setup_geom_ray(P, R, (int)my, anyhit_secondary, rc, st, pr);
+        }
+      }
+      exhausted = exhausted || __any_sync(FULL, ex_local);
+      if (__ballot_sync(FULL, pr.ray >= 0) == 0u) break;
+    }
+    // ---- one warp-synchronous phase: primitives when enough lanes hold a group (or nobody can do
+    //      node work), else one node step for every lane that has a node to visit
+    const bool has_prims = trav && st.tg.y != 0u;
+    const bool can_node = trav && !has_prims;  // invariant: then st.ng.y > 0x00ffffff
+    const unsigned mp = __ballot_sync(FULL, has_prims), mn = __ballot_sync(FULL, can_node);
+    if (mp != 0u && (__popc(mp) >= PRIM_T || mn == 0u)) {
+      if (has_prims) {
+        if (prim_step(P, rc, st, pr.anyhit)) trav = false;
+        else trav = trav_advance(st, stack, lstack);
+      }
+    } else if (can_node) {
+      node_step<PREFETCH>(P, rc, st, stack, lstack);
+      trav = trav_advance(st, stack, lstack);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cooperative variant: the node phase is per lane, but the primitive tests of a warp are spread over
+// ALL its lanes.  After a node step ~4 lanes of a warp hold a primitive group of 1..8 records; tested
+// by their owners alone that is a loop of up to 8 dependent DRAM round trips at 2 lanes of 32.  Here
+// lane 4g+k tests the k-th pending primitive of the g-th owning lane (ray fetched with shuffles), so
+// one pass tests up to 4 primitives of each of 8 owners with independent loads, and the owner picks
+// the (t, geomID, primID)-smallest candidate of its 4 helpers with shuffles.
+template <int FETCH_T, int MIN_BLOCKS, int PREFETCH>
+__global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
+    trace_geom_coop_kernel(const __grid_constant__ SceneParams P, Rays R, int n, int *__restrict__ hit_ids, int anyhit_secondary) {
+  __shared__ uint2 stack[GXY_STACK_SMEM * GXY_TRACE_THREADS];
+  __shared__ unsigned char owner_of[GXY_TRACE_THREADS / 32][8];
+  uint2 lstack[GXY_STACK_LOCAL];
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  RayCtx rc;
+  TravState st;
+  PendingRay pr;
+  pr.ray = -1; pr.tExit = 0.f; pr.anyhit = false;
+  st.tg.y = 0u; st.ng.y = 0u;
+  rc.org = f3(0.f, 0.f, 0.f); rc.dir = f3(1.f, 1.f, 1.f); rc.tnear = 0.f; rc.tfar = 0.f;
+  st.best_t = 0.f; st.best_key = GXY_NO_HIT;
+  bool trav = false, exhausted = false;
+  while (true) {
+    // ---- refill: finished lanes write their result and fetch the next ray of the queue
+    const unsigned m_idle = __ballot_sync(FULL, !trav);
+    if (m_idle == FULL || (!exhausted && __popc(m_idle) >= FETCH_T)) {
+      bool ex_local = false;
+      if (!trav) {
+        if (pr.ray >= 0) {
+          finish_geom_ray(P, R, rc, st, pr, hit_ids);
+          pr.ray = -1;
+        }
+        if (!exhausted) {
+          const int leader = __ffs((int)m_idle) - 1;
+          const unsigned cnt = (unsigned)__popc(m_idle);
+          unsigned base = 0;
+          if ((int)lane == leader) base = atomicAdd(P.work_counter, cnt);
+          base = __shfl_sync(m_idle, base, leader);
+          const unsigned my = base + (unsigned)__popc(m_idle & lt_mask);
+          ex_local = base + cnt >= (unsigned)n;
+          if (my < (unsigned)n) trav = setup_geom_ray(P, R, (int)my, anyhit_secondary, rc, st, pr);
+        }
+      }
+      exhausted = exhausted || __any_sync(FULL, ex_local);
+      if (__ballot_sync(FULL, pr.ray >= 0) == 0u) break;
+    }
+    // ---- node phase (invariant: a traversing lane has st.ng.y > 0x00ffffff and no pending primitives here)
+    if (trav) node_step<PREFETCH>(P, rc, st, stack, lstack);
+    // ---- cooperative primitive passes
+    unsigned owners = __ballot_sync(FULL, trav && st.tg.y != 0u);
+    while (owners != 0u) {
+      const bool own = trav && st.tg.y != 0u;
+      const unsigned r = (unsigned)__popc(owners & lt_mask);  // rank among the owning lanes
+      if (own && r < 8u) owner_of[warp][r] = (unsigned char)lane;
+      __syncwarp();
+      const unsigned g = lane >> 2, k = lane & 3u;
+      const bool gvalid = g < (unsigned)__popc(owners);
+      const unsigned o = gvalid ? (unsigned)owner_of[warp][g] : lane;
+      const unsigned obits = __shfl_sync(FULL, st.tg.y, o), obase = __shfl_sync(FULL, st.tg.x, o);
+      unsigned b = obits;  // drop the k lowest set bits: the k-th pending primitive of the owner
+      if (k >= 1u) b &= b - 1u;
+      if (k >= 2u) b &= b - 1u;
+      if (k >= 3u) b &= b - 1u;
+      const bool tvalid = gvalid && b != 0u;
+      const float3 oorg = f3(__shfl_sync(FULL, rc.org.x, o), __shfl_sync(FULL, rc.org.y, o), __shfl_sync(FULL, rc.org.z, o));
+      const float3 odir = f3(__shfl_sync(FULL, rc.dir.x, o), __shfl_sync(FULL, rc.dir.y, o), __shfl_sync(FULL, rc.dir.z, o));
+      const float otn = __shfl_sync(FULL, rc.tnear, o), otf = __shfl_sync(FULL, rc.tfar, o);
+      float ct = __int_as_float(0x7f800000), cu = 0.f, cv = 0.f;
+      unsigned ckey = GXY_NO_HIT, crec = 0u;
+      if (tvalid) {
+        crec = obase + (unsigned)(__ffs((int)b) - 1);
+        const float4 *rec = reinterpret_cast<const float4 *>(P.prims + crec);
+        const float4 ra = __ldg(rec), rb = __ldg(rec + 1), rcq = __ldg(rec + 2);
+#ifdef GXY_TRAV_COUNTERS
+        atomicAdd(P.trav_counters + 1, 1ull);
+#endif
+        const unsigned gk = __float_as_uint(rcq.y);
+        float t, u = 0.f, v = 0.f;
+        bool h;
+        if ((gk >> 24) == 0) h = tri_test(ra, rb, rcq, oorg, odir, otn, otf, t, u, v);
+        else h = sphere_test(ra, rb, oorg, odir, otn, otf, t);
+        if (h) { ct = t; cu = u; cv = v; ckey = ((gk & 0xffffffu) << 28) | __float_as_uint(rcq.z); }
+      }
+      // the owner (rank r < 8) picks the best of its helpers, lanes 4r .. 4r+3
+      const unsigned h0 = (4u * r) & 31u;
+      int hb = -1;
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        const float ht = __shfl_sync(FULL, ct, h0 + kk);
+        const unsigned hk = __shfl_sync(FULL, ckey, h0 + kk);
+        if (own && r < 8u && hk != GXY_NO_HIT && (ht < st.best_t || (ht == st.best_t && hk < st.best_key))) {
+          st.best_t = ht; st.best_key = hk; hb = kk;
+        }
+      }
+      const unsigned hsrc = h0 + (unsigned)(hb < 0 ? 0 : hb);
+      const float hu = __shfl_sync(FULL, cu, hsrc), hv = __shfl_sync(FULL, cv, hsrc);
+      const unsigned hrec = __shfl_sync(FULL, crec, hsrc);
+      if (own && r < 8u) {
+        if (hb >= 0) { st.best_u = hu; st.best_v = hv; st.best_rec = hrec; }
+        unsigned nb = st.tg.y;  // the 4 lowest pending primitives have been tested
+        nb &= nb - 1u; nb &= nb - 1u; nb &= nb - 1u; nb &= nb - 1u;
+        st.tg.y = nb;
+        if (hb >= 0 && pr.anyhit) { trav = false; st.tg.y = 0u; }
+      }
+      __syncwarp();
+      owners = __ballot_sync(FULL, trav && st.tg.y != 0u);
+    }
+    // ---- next node group (stack pop) or end of traversal
+    if (trav) trav = trav_advance(st, stack, lstack);
+  }
+}
+
+typedef void (*trace_geom_fn)(const SceneParams, Rays, int, int *, int);
+struct TraceVariant {
+  const char *name;
+  trace_geom_fn fn;
+  int min_blocks;
+};
+// tuning variants (GXY_TRACE_VARIANT=<name>): f = fetch threshold, p = primitive-phase threshold,
+// b = resident blocks per SM the kernel is compiled for, n = no prefetch; the first one is the default
+static const TraceVariant g_trace_variants[] = {
+    {"c8b8", trace_geom_coop_kernel<8, 8, 0>, 8},      {"c8b8L2", trace_geom_coop_kernel<8, 8, 1>, 8},  {"c4b8", trace_geom_coop_kernel<4, 8, 0>, 8},
+    {"c12b8", trace_geom_coop_kernel<12, 8, 0>, 8},    {"c8b6", trace_geom_coop_kernel<8, 6, 0>, 6},    {"c8b10", trace_geom_coop_kernel<8, 10, 0>, 10},
+    {"f8p1b8", trace_geom_kernel<8, 1, 8, 0>, 8},      {"f8p1b8L2", trace_geom_kernel<8, 1, 8, 1>, 8},  {"f8p8b8", trace_geom_kernel<8, 8, 8, 0>, 8},
+};
+
+static int launch_trace_geom(const SceneParams &P, Rays R, int n, int *hit_ids, bool anyhit, cudaStream_t st) {
+  // the environment is consulted on every launch so that a tuning script can sweep variants in one process
+  const TraceVariant *variant = &g_trace_variants[0];
+  if (const char *e = getenv("GXY_TRACE_VARIANT"))
+    for (const TraceVariant &v : g_trace_variants)
+      if (!strcmp(v.name, e)) variant = &v;
+  int blocks_per_sm = variant->min_blocks;
+  if (const char *e = getenv("GXY_TRACE_BLOCKS_PER_SM")) blocks_per_sm = atoi(e) > 0 ? atoi(e) : blocks_per_sm;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = GXY_SM_COUNT;
+  }
+  const int needed = (n + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
+  const int blocks = needed < sms * blocks_per_sm ? needed : sms * blocks_per_sm;
+  GXY_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned), st));
+  variant->fn<<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, hit_ids, anyhit ? 1 : 0);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int NV>
 static int launch_trace_nv(const SceneParams &P, Rays R, int n, float eps, int *hit_ids, bool anyhit, unsigned long long *sc,
                            cudaStream_t st) {
@@ -261,6 +552,9 @@ static int launch_trace_nv(const SceneParams &P, Rays R, int n, float eps, int *
 int launch_trace(const SceneParams &P, Rays R, int n, float global_epsilon, int *hit_ids, bool anyhit_secondary,
                  unsigned long long *sample_counter, cudaStream_t st) {
   if (n <= 0) return 0;
+  const char *pe = getenv("GXY_TRACE_PERSISTENT");
+  const bool persistent = !(pe && atoi(pe) == 0);
+  if (P.n_volvis == 0 && P.n_prims > 0 && persistent) return launch_trace_geom(P, R, n, hit_ids, anyhit_secondary, st);
   switch (P.n_volvis) {
     case 0: return launch_trace_nv<0>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st);
     case 1: return launch_trace_nv<1>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st);

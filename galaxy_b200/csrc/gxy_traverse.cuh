@@ -1,7 +1,22 @@
-// gxy_traverse.cuh -- nearest-hit traversal of the 8-wide quantised BVH + the two primitive tests.
+// gxy_traverse.cuh -- nearest-hit traversal of the compressed 8-wide BVH + the two primitive tests.
 // Replaces rtcIntersectV (ospray/common/Model.ih:54-70) i.e. Embree's BVH8 traversal with
 // MoellerTrumboreIntersectorK (embree/kernels/geometry/triangle_intersector_moeller.h:210-266)
 // and the DataDrivenSpheres user-geometry callback (src/ospray/DataDrivenSpheres.ispc:90-155).
+//
+// Traversal scheme (after Ylitie, Karras, Laine 2017): the per-ray state is a NODE GROUP
+// (child_base, hit bits of the still-unvisited internal children | imask) and a PRIMITIVE GROUP
+// (prim_base, hit bits of up to 24 leaf primitives).  One step = pop the nearest child of the node
+// group in octant order (highest set bit), test its 8 quantised child boxes branch-free into a new
+// hit mask, then test the primitive group.  The stack holds one 8-byte entry per node whose
+// children are only partly visited; the first GXY_STACK_SMEM entries live in shared memory.
+// The persistent kernel runs the two phases warp-synchronously: lanes holding a primitive group
+// wait until PRIM_T lanes of the warp have one (or nobody can do node work), so that the
+// primitive tests run with many lanes instead of one or two (gxy_kernels.cu).
+//
+// Exactness: child boxes are conservative (quantised outwards at build time, rounding of the slab
+// arithmetic bounded per node and added to the interval), every primitive is tested against the
+// ORIGINAL (tnear, tfar] with the reference's arithmetic, and the winner is the smallest t with
+// ties broken on the lowest (geomID, primID) -- independent of traversal order.
 #pragma once
 #include "gxy_common.cuh"
 
@@ -13,9 +28,10 @@ struct Hit1 {
   float3 Ng;
 };
 
-#define GXY_STACK_SMEM 24   // entries per thread kept in shared memory
-#define GXY_STACK_LOCAL 40  // overflow entries in local memory
+#define GXY_STACK_SMEM 10   // entries per thread kept in shared memory
+#define GXY_STACK_LOCAL 54  // overflow entries in local memory
 #define GXY_TRACE_THREADS 128
+#define GXY_NO_HIT 0xffffffffu
 
 // Embree AVX2 op order (common/math/vec3.h:216,221): dot = madd(x,x, madd(y,y, z*z)),
 // cross.x = msub(a.y,b.z, a.z*b.y)
@@ -27,9 +43,9 @@ __device__ __forceinline__ float3 ecross(float3 a, float3 b) {
 
 // one triangle record against the ray; candidate interval is the ORIGINAL (tnear, tfar]
 __device__ __forceinline__ bool tri_test(const float4 ra, const float4 rb, const float4 rc, float3 org, float3 dir, float tnear,
-                                         float tfar, float &t, float &u, float &v, float3 &Ng) {
+                                         float tfar, float &t, float &u, float &v) {
   const float3 v0 = f3(ra.x, ra.y, ra.z), e1 = f3(ra.w, rb.x, rb.y), e2 = f3(rb.z, rb.w, rc.x);
-  Ng = ecross(e2, e1);
+  const float3 Ng = ecross(e2, e1);
   const float3 C = v0 - org;
   const float3 R = ecross(C, dir);
   const float den = edot(Ng, dir);
@@ -51,8 +67,7 @@ __device__ __forceinline__ bool tri_test(const float4 ra, const float4 rb, const
 }
 
 // DataDrivenSpheres.ispc:114-141 with (t0, tfar) the ORIGINAL interval
-__device__ __forceinline__ bool sphere_test(const float4 ra, const float4 rb, float3 org, float3 dir, float t0, float tfar, float &t,
-                                            float3 &Ng) {
+__device__ __forceinline__ bool sphere_test(const float4 ra, const float4 rb, float3 org, float3 dir, float t0, float tfar, float &t) {
   const float3 center = f3(ra.x, ra.y, ra.z);
   const float radius = ra.w, geps = rb.x;
   const float approxDist = dot3(center - org, dir);
@@ -69,128 +84,217 @@ __device__ __forceinline__ bool sphere_test(const float4 ra, const float4 rb, fl
   bool hit = false;
   if (t_in > t0 && t_in < tfar) { hit = true; t = t_in; }
   else if (t_out > (t0 + geps) && t_out < tfar) { hit = true; t = t_out; }
-  if (hit) Ng = org + t * dir - center;
   return hit;
+}
+
+// ---- per-ray constants and traversal state ------------------------------------------------------
+struct RayCtx {
+  float3 org, dir;
+  float idx, idy, idz;  // guarded reciprocals (box tests only; they never decide a result)
+  float tnear, tfar;    // the ORIGINAL interval
+  unsigned octinv4;     // (7 ^ negative-direction mask) replicated in 4 bytes
+};
+
+struct TravState {
+  uint2 ng, tg;       // node group (child_base, hits<<24 | imask), primitive group (prim_base, 24 hit bits)
+  int sp;
+  float best_t, best_u, best_v;
+  unsigned best_key;  // geomID << 28 | primID; GXY_NO_HIT = none (the builder guarantees primID < 2^28, geomID < 16)
+  unsigned best_rec;  // index of the winning primitive record
+#ifdef GXY_TRAV_COUNTERS
+  unsigned n_nodes, n_prims;
+#endif
+};
+
+__device__ __forceinline__ void ray_ctx_init(RayCtx &rc, float3 org, float3 dir, float tnear, float tfar) {
+  rc.org = org; rc.dir = dir; rc.tnear = tnear; rc.tfar = tfar;
+  const float gx = fabsf(dir.x) > 1e-30f ? dir.x : copysignf(1e-30f, dir.x);
+  const float gy = fabsf(dir.y) > 1e-30f ? dir.y : copysignf(1e-30f, dir.y);
+  const float gz = fabsf(dir.z) > 1e-30f ? dir.z : copysignf(1e-30f, dir.z);
+  rc.idx = 1.0f / gx; rc.idy = 1.0f / gy; rc.idz = 1.0f / gz;
+  // octant from the sign of the reciprocal actually used, so that near/far plane selection and
+  // child order always agree with the slab arithmetic (also for -0.0 components)
+  const unsigned rs = (rc.idx < 0.f ? 1u : 0u) | (rc.idy < 0.f ? 2u : 0u) | (rc.idz < 0.f ? 4u : 0u);
+  rc.octinv4 = (7u ^ rs) * 0x01010101u;
+}
+
+__device__ __forceinline__ void trav_init(TravState &s, const RayCtx &rc) {
+  s.ng = make_uint2(0u, 0x80000000u);  // root = "child 0 of a virtual group": bit 31, imask 0
+  s.tg = make_uint2(0u, 0u);
+  s.sp = 0;
+  s.best_t = rc.tfar; s.best_u = 0.f; s.best_v = 0.f;
+  s.best_key = GXY_NO_HIT; s.best_rec = 0u;
+#ifdef GXY_TRAV_COUNTERS
+  s.n_nodes = 0; s.n_prims = 0;
+#endif
 }
 
 __device__ __forceinline__ float byte_f(unsigned w, int k) { return (float)((w >> (8 * k)) & 0xffu); }
 
-// Nearest hit in (tnear, tfar]: smallest t wins; equal t -> lowest (geomID, primID)  [deterministic,
-// independent of traversal order; Embree's own tie rule is BVH-order dependent, SURVEY A.7].
-// ANYHIT: stop at the first accepted candidate (occlusion rays when nothing integrates along t).
-// stack: shared-memory array [GXY_STACK_SMEM][blockDim.x] of uint2, this thread uses column threadIdx.x.
+// the 4 children of one half of a node: returns their contribution to the hit mask
+__device__ __forceinline__ unsigned test_half(unsigned meta4, unsigned octinv4, unsigned nx4, unsigned ny4, unsigned nz4, unsigned fx4,
+                                              unsigned fy4, unsigned fz4, float ax, float ay, float az, float bnx, float bny, float bnz,
+                                              float bfx, float bfy, float bfz, float tnear, float tbest) {
+  const unsigned is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+  const unsigned inner_mask4 = (is_inner4 >> 4) * 0xffu;
+  const unsigned bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+  const unsigned child_bits4 = (meta4 >> 5) & 0x07070707u;
+  unsigned hitmask = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float tnx = __fmaf_rn(byte_f(nx4, k), ax, bnx), tfx = __fmaf_rn(byte_f(fx4, k), ax, bfx);
+    const float tny = __fmaf_rn(byte_f(ny4, k), ay, bny), tfy = __fmaf_rn(byte_f(fy4, k), ay, bfy);
+    const float tnz = __fmaf_rn(byte_f(nz4, k), az, bnz), tfz = __fmaf_rn(byte_f(fz4, k), az, bfz);
+    const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tnear));
+    const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, tbest));
+    if (tmin <= tmax) hitmask |= ((child_bits4 >> (8 * k)) & 0xffu) << ((bit_index4 >> (8 * k)) & 0xffu);
+  }
+  return hitmask;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ void stack_push(const SceneParams &P, TravState &s, uint2 e, uint2 *__restrict__ stack, uint2 *__restrict__ lstack) {
+  if (s.sp < GXY_STACK_SMEM) stack[s.sp * blockDim.x + threadIdx.x] = e;
+  else if (s.sp < GXY_STACK_SMEM + GXY_STACK_LOCAL) lstack[s.sp - GXY_STACK_SMEM] = e;
+  if (s.sp < GXY_STACK_SMEM + GXY_STACK_LOCAL) s.sp++;
+  else *P.error_flag = 1;
+}
+
+// Node phase: pop the nearest unvisited internal child of the node group (requires s.ng.y > 0x00ffffff)
+// and test its 8 children -> new node group + primitive group.
+// PREFETCH: 0 none; 1 = L2 prefetch of the primitive records of the new group and of the node that
+// will be visited next (overlaps their DRAM latency with the primitive phase); 2 = same into L1
+template <int PREFETCH>
+__device__ __forceinline__ void node_step(const SceneParams &P, const RayCtx &rc, TravState &s, uint2 *__restrict__ stack,
+                                          uint2 *__restrict__ lstack) {
+  const unsigned hits_imask = s.ng.y;
+  const int bit = 31 - __clz((int)hits_imask);
+  s.ng.y &= ~(1u << bit);
+  if (s.ng.y > 0x00ffffffu) stack_push(P, s, s.ng, stack, lstack);  // siblings left: the group goes to the stack
+  const unsigned slot = (unsigned)(bit - 24) ^ (rc.octinv4 & 7u);
+  const unsigned rel = __popc(hits_imask & ~(0xffffffffu << slot));
+  const uint4 *np = reinterpret_cast<const uint4 *>(P.nodes + (s.ng.x + rel));
+  const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+#ifdef GXY_TRAV_COUNTERS
+  s.n_nodes++;
+#endif
+  // slab coefficients in the node's quantisation frame: t = q * a + b
+  const float ax = __uint_as_float((n0.w & 0xffu) << 23) * rc.idx, ay = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * rc.idy,
+              az = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * rc.idz;
+  const float bx = (__uint_as_float(n0.x) - rc.org.x) * rc.idx, by = (__uint_as_float(n0.y) - rc.org.y) * rc.idy,
+              bz = (__uint_as_float(n0.z) - rc.org.z) * rc.idz;
+  // rounding of (q*a + b) against the exact plane distance is below 2^-24 * (4|b| + 510|a|)
+  // (reciprocal, difference, product, fma): widen the interval by 4e-7 * (|b| + 255|a|) per axis
+  const float Ex = 4e-7f * __fmaf_rn(255.f, fabsf(ax), fabsf(bx)), Ey = 4e-7f * __fmaf_rn(255.f, fabsf(ay), fabsf(by)),
+              Ez = 4e-7f * __fmaf_rn(255.f, fabsf(az), fabsf(bz));
+  const float bnx = bx - Ex, bny = by - Ey, bnz = bz - Ez, bfx = bx + Ex, bfy = by + Ey, bfz = bz + Ez;
+  const bool negx = rc.idx < 0.f, negy = rc.idy < 0.f, negz = rc.idz < 0.f;
+  // n2 = qlox[8] qloy[8]   n3 = qloz[8] qhix[8]   n4 = qhiy[8] qhiz[8]
+  const unsigned nx0 = negx ? n3.z : n2.x, nx1 = negx ? n3.w : n2.y, fx0 = negx ? n2.x : n3.z, fx1 = negx ? n2.y : n3.w;
+  const unsigned ny0 = negy ? n4.x : n2.z, ny1 = negy ? n4.y : n2.w, fy0 = negy ? n2.z : n4.x, fy1 = negy ? n2.w : n4.y;
+  const unsigned nz0 = negz ? n4.z : n3.x, nz1 = negz ? n4.w : n3.y, fz0 = negz ? n3.x : n4.z, fz1 = negz ? n3.y : n4.w;
+  const float tb = s.best_t;
+  unsigned hitmask = test_half(n1.z, rc.octinv4, nx0, ny0, nz0, fx0, fy0, fz0, ax, ay, az, bnx, bny, bnz, bfx, bfy, bfz, rc.tnear, tb);
+  hitmask |= test_half(n1.w, rc.octinv4, nx1, ny1, nz1, fx1, fy1, fz1, ax, ay, az, bnx, bny, bnz, bfx, bfy, bfz, rc.tnear, tb);
+  s.ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
+  s.tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
+  if (PREFETCH) {
+    if (s.tg.y) {
+      const char *first = reinterpret_cast<const char *>(P.prims + (s.tg.x + (unsigned)(__ffs((int)s.tg.y) - 1)));
+      const char *last = reinterpret_cast<const char *>(P.prims + (s.tg.x + (unsigned)(31 - __clz((int)s.tg.y))));
+      if (PREFETCH == 1) { prefetch_l2(first); prefetch_l2(first + 32); prefetch_l2(last + 16); prefetch_l2(last + 32); }
+      else { prefetch_l1(first); prefetch_l1(first + 32); prefetch_l1(last + 16); prefetch_l1(last + 32); }
+    }
+    if (s.ng.y > 0x00ffffffu) {
+      const int nbit = 31 - __clz((int)s.ng.y);
+      const unsigned nslot = (unsigned)(nbit - 24) ^ (rc.octinv4 & 7u);
+      const char *nn = reinterpret_cast<const char *>(P.nodes + (s.ng.x + __popc(s.ng.y & ~(0xffffffffu << nslot))));
+      if (PREFETCH == 1) { prefetch_l2(nn); prefetch_l2(nn + 32); prefetch_l2(nn + 64); }
+      else { prefetch_l1(nn); prefetch_l1(nn + 32); prefetch_l1(nn + 64); }
+    }
+  }
+}
+
+// Primitive phase: test every primitive of the group.  Returns true if the traversal is over
+// (anyhit and a candidate was accepted).
+__device__ __forceinline__ bool prim_step(const SceneParams &P, const RayCtx &rc, TravState &s, const bool anyhit) {
+  while (s.tg.y != 0u) {
+    const int b = __ffs((int)s.tg.y) - 1;
+    s.tg.y &= s.tg.y - 1u;
+    const unsigned ri = s.tg.x + (unsigned)b;
+    const float4 *rec = reinterpret_cast<const float4 *>(P.prims + ri);
+    const float4 ra = __ldg(rec), rb = __ldg(rec + 1), rcq = __ldg(rec + 2);
+#ifdef GXY_TRAV_COUNTERS
+    s.n_prims++;
+#endif
+    const unsigned gk = __float_as_uint(rcq.y);
+    const unsigned key = ((gk & 0xffffffu) << 28) | __float_as_uint(rcq.z);
+    float t, u = 0.f, v = 0.f;
+    bool h;
+    if ((gk >> 24) == 0) h = tri_test(ra, rb, rcq, rc.org, rc.dir, rc.tnear, rc.tfar, t, u, v);
+    else h = sphere_test(ra, rb, rc.org, rc.dir, rc.tnear, rc.tfar, t);
+    if (h && (t < s.best_t || (t == s.best_t && key < s.best_key))) {
+      s.best_t = t; s.best_u = u; s.best_v = v; s.best_key = key; s.best_rec = ri;
+      if (anyhit) return true;
+    }
+  }
+  return false;
+}
+
+// After a phase: make sure the lane has a node group with unvisited children (or pending primitives);
+// returns false when the traversal is complete.
+__device__ __forceinline__ bool trav_advance(TravState &s, const uint2 *__restrict__ stack, const uint2 *__restrict__ lstack) {
+  if (s.tg.y == 0u && s.ng.y <= 0x00ffffffu) {
+    if (s.sp == 0) return false;
+    --s.sp;
+    s.ng = s.sp < GXY_STACK_SMEM ? stack[s.sp * blockDim.x + threadIdx.x] : lstack[s.sp - GXY_STACK_SMEM];
+  }
+  return true;
+}
+
+// One per-lane traversal step (node, then its primitives).  Returns false when the traversal is complete.
+__device__ __forceinline__ bool trav_step(const SceneParams &P, const RayCtx &rc, TravState &s, const bool anyhit,
+                                          uint2 *__restrict__ stack, uint2 *__restrict__ lstack) {
+  if (s.ng.y > 0x00ffffffu) node_step<0>(P, rc, s, stack, lstack);
+  if (prim_step(P, rc, s, anyhit)) return false;
+  return trav_advance(s, stack, lstack);
+}
+
+// geomID / primID / Ng of the winner, recomputed from its record (saves registers in the loop)
+__device__ __forceinline__ void trav_fetch_hit(const SceneParams &P, const RayCtx &rc, const TravState &s, Hit1 &best) {
+  best.t = s.best_t; best.u = s.best_u; best.v = s.best_v;
+  best.geom = (int)(s.best_key >> 28);
+  best.prim = (int)(s.best_key & 0x0fffffffu);
+  const float4 *rec = reinterpret_cast<const float4 *>(P.prims + s.best_rec);
+  const float4 ra = __ldg(rec), rb = __ldg(rec + 1), rcq = __ldg(rec + 2);
+  if ((__float_as_uint(rcq.y) >> 24) == 0) {
+    const float3 e1 = f3(ra.w, rb.x, rb.y), e2 = f3(rb.z, rb.w, rcq.x);
+    best.Ng = ecross(e2, e1);  // embree triangle.h:133-136
+  } else {
+    best.Ng = rc.org + s.best_t * rc.dir - f3(ra.x, ra.y, ra.z);  // DataDrivenSpheres.ispc:143-150
+  }
+}
+
+// Nearest hit in (tnear, tfar], run to completion.  ANYHIT: stop at the first accepted candidate
+// (occlusion rays when nothing integrates along t).  stack: shared-memory array
+// [GXY_STACK_SMEM][blockDim.x] of uint2, this thread uses column threadIdx.x.
 template <bool ANYHIT>
 __device__ __forceinline__ bool traverse(const SceneParams &P, float3 org, float3 dir, float tnear, float tfar, Hit1 &best,
                                          uint2 *__restrict__ stack) {
-  best.geom = -1;
-  best.prim = -1;
-  best.t = tfar;
-  best.u = best.v = 0.f;
+  best.geom = -1; best.prim = -1; best.t = tfar; best.u = best.v = 0.f;
   best.Ng = f3(0.f, 0.f, 0.f);
   if (P.n_prims == 0) return false;
-  bool found = false;
-  const WideNode *__restrict__ nodes = P.nodes;
-  const PrimRec *__restrict__ prims = P.prims;
-  // box tests never decide a result: guarded reciprocal, FMA allowed
-  const float gx = fabsf(dir.x) > 1e-30f ? dir.x : copysignf(1e-30f, dir.x);
-  const float gy = fabsf(dir.y) > 1e-30f ? dir.y : copysignf(1e-30f, dir.y);
-  const float gz = fabsf(dir.z) > 1e-30f ? dir.z : copysignf(1e-30f, dir.z);
-  const float idx = 1.0f / gx, idy = 1.0f / gy, idz = 1.0f / gz;
-  const bool o1 = dir.x < 0.f, o2 = dir.y < 0.f, o4 = dir.z < 0.f;
-  const unsigned sel = o1 ? (o2 ? 0x0123u : 0x2301u) : (o2 ? 0x1032u : 0x3210u);
-  uint2 local_stack[GXY_STACK_LOCAL];
-  int sp = 0;
-  const int tid = threadIdx.x, stride = blockDim.x;
-  unsigned cur = 0;  // root node ref
-  float cur_t = tnear;
-  bool have = true;
-  while (true) {
-    if (!have) {
-      if (sp == 0) break;
-      --sp;
-      uint2 e = sp < GXY_STACK_SMEM ? stack[sp * stride + tid] : local_stack[sp - GXY_STACK_SMEM];
-      cur = e.x;
-      cur_t = __uint_as_float(e.y);
-      if (cur_t > best.t) continue;  // strict: equal-t candidates are still examined (tie rule)
-    }
-    have = false;
-    if (cur & 0x80000000u) {
-      // ---- leaf: up to 8 primitive records
-      unsigned first = (cur & 0x7fffffffu) >> 3;
-      int count = (int)(cur & 7u) + 1;
-      for (int k = 0; k < count; k++) {
-        const float4 *rec = reinterpret_cast<const float4 *>(prims + first + k);
-        const float4 ra = __ldg(rec), rb = __ldg(rec + 1), rc = __ldg(rec + 2);
-        const unsigned gk = __float_as_uint(rc.y);
-        const int geom = (int)(gk & 0xffffffu), prim = (int)__float_as_uint(rc.z);
-        float t, u = 0.f, v = 0.f;
-        float3 Ng;
-        bool h;
-        if ((gk >> 24) == 0) h = tri_test(ra, rb, rc, org, dir, tnear, tfar, t, u, v, Ng);
-        else h = sphere_test(ra, rb, org, dir, tnear, tfar, t, Ng);
-        if (h && (!found || t < best.t || (t == best.t && (geom < best.geom || (geom == best.geom && prim < best.prim))))) {
-          found = true;
-          best.t = t; best.u = u; best.v = v; best.geom = geom; best.prim = prim; best.Ng = Ng;
-          if (ANYHIT) return true;
-        }
-      }
-      continue;
-    }
-    // ---- inner node: test the 8 quantised child boxes
-    const uint4 *np = reinterpret_cast<const uint4 *>(nodes + cur);
-    const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4), n5 = __ldg(np + 5);
-    const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
-                sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
-    const float ax = sx * idx, ay = sy * idy, az = sz * idz;
-    const float bx = (__uint_as_float(n0.x) - org.x) * idx, by = (__uint_as_float(n0.y) - org.y) * idy,
-                bz = (__uint_as_float(n0.z) - org.z) * idz;
-    // permute slots so that position p holds slot p^oct (no dynamic register indexing):
-    // bytes inside a word by PRMT with a per-ray selector, words and refs by conditional swaps
-    unsigned r0 = n1.x, r1 = n1.y, r2 = n1.z, r3 = n1.w, r4 = n2.x, r5 = n2.y, r6 = n2.z, r7 = n2.w;
-#define GXY_CSWAP(c, a_, b_) { unsigned ta = (c) ? b_ : a_; b_ = (c) ? a_ : b_; a_ = ta; }
-    GXY_CSWAP(o1, r0, r1) GXY_CSWAP(o1, r2, r3) GXY_CSWAP(o1, r4, r5) GXY_CSWAP(o1, r6, r7)
-    GXY_CSWAP(o2, r0, r2) GXY_CSWAP(o2, r1, r3) GXY_CSWAP(o2, r4, r6) GXY_CSWAP(o2, r5, r7)
-    GXY_CSWAP(o4, r0, r4) GXY_CSWAP(o4, r1, r5) GXY_CSWAP(o4, r2, r6) GXY_CSWAP(o4, r3, r7)
-    const unsigned refs[8] = {r0, r1, r2, r3, r4, r5, r6, r7};
-    // qlox qloy | qloz qhix | qhiy qhiz   (8 bytes each)
-    unsigned qlox[2] = {__byte_perm(n3.x, 0, sel), __byte_perm(n3.y, 0, sel)}, qloy[2] = {__byte_perm(n3.z, 0, sel), __byte_perm(n3.w, 0, sel)};
-    unsigned qloz[2] = {__byte_perm(n4.x, 0, sel), __byte_perm(n4.y, 0, sel)}, qhix[2] = {__byte_perm(n4.z, 0, sel), __byte_perm(n4.w, 0, sel)};
-    unsigned qhiy[2] = {__byte_perm(n5.x, 0, sel), __byte_perm(n5.y, 0, sel)}, qhiz[2] = {__byte_perm(n5.z, 0, sel), __byte_perm(n5.w, 0, sel)};
-    GXY_CSWAP(o4, qlox[0], qlox[1]) GXY_CSWAP(o4, qloy[0], qloy[1]) GXY_CSWAP(o4, qloz[0], qloz[1])
-    GXY_CSWAP(o4, qhix[0], qhix[1]) GXY_CSWAP(o4, qhiy[0], qhiy[1]) GXY_CSWAP(o4, qhiz[0], qhiz[1])
-#undef GXY_CSWAP
-    const float tb = best.t;
-    // push far-to-near in octant order so the nearest octant is popped first
-#pragma unroll
-    for (int p = 7; p >= 0; p--) {
-      const unsigned ref = refs[p];
-      if (ref == 0) continue;
-      const int w = p >> 2, k = p & 3;
-      float x0 = byte_f(qlox[w], k), x1 = byte_f(qhix[w], k);
-      float y0 = byte_f(qloy[w], k), y1 = byte_f(qhiy[w], k);
-      float z0 = byte_f(qloz[w], k), z1 = byte_f(qhiz[w], k);
-      float tx0 = __fmaf_rn(x0, ax, bx), tx1 = __fmaf_rn(x1, ax, bx);
-      float ty0 = __fmaf_rn(y0, ay, by), ty1 = __fmaf_rn(y1, ay, by);
-      float tz0 = __fmaf_rn(z0, az, bz), tz1 = __fmaf_rn(z1, az, bz);
-      float tmin = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tnear));
-      float tmax = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tb));
-      // conservative slack: a few ulps of the magnitudes involved
-      float slack = 4e-6f * fmaxf(fabsf(tmin), fabsf(tmax)) + 1e-30f;
-      if (tmin - tmax <= slack) {
-        if (have) {  // previously selected (farther) child goes to the stack
-          uint2 e = make_uint2(cur, __float_as_uint(cur_t));
-          if (sp < GXY_STACK_SMEM) stack[sp * stride + tid] = e;
-          else if (sp < GXY_STACK_SMEM + GXY_STACK_LOCAL) local_stack[sp - GXY_STACK_SMEM] = e;
-          if (sp < GXY_STACK_SMEM + GXY_STACK_LOCAL) sp++;
-          else *P.error_flag = 1;
-        }
-        cur = ref;
-        cur_t = fminf(tmin, tmax) - slack;
-        have = true;
-      }
-    }
-  }
-  return found;
+  RayCtx rc;
+  ray_ctx_init(rc, org, dir, tnear, tfar);
+  TravState s;
+  trav_init(s, rc);
+  uint2 lstack[GXY_STACK_LOCAL];
+  while (trav_step(P, rc, s, ANYHIT, stack, lstack)) {}
+  if (s.best_key == GXY_NO_HIT) return false;
+  trav_fetch_hit(P, rc, s, best);
+  return true;
 }
 
 }  // namespace gxy

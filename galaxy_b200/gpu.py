@@ -38,14 +38,16 @@ class RayListView(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in ("primary_rays", "shadow_rays", "ao_rays", "forwarded_rays", "terminated_rays", "traced_rays",
-                                            "waves", "kernel_launches")] + [("device_ms", C.c_float), ("trace_ms", C.c_float)]
+                                            "waves", "kernel_launches")] + [("device_ms", C.c_float), ("trace_ms", C.c_float),
+                                                                                ("nodes_visited", C.c_longlong), ("prims_tested", C.c_longlong)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 def library_path():
-    return os.path.join(_HERE, "libgxy_b200.so")
+    # GXY_LIB selects a diagnostic build (e.g. libgxy_b200_counters.so, `make counters`)
+    return os.environ.get("GXY_LIB") or os.path.join(_HERE, "libgxy_b200.so")
 
 
 def build(force=False):

@@ -85,6 +85,8 @@ typedef struct {
   long long kernel_launches;  /* kernels of this library launched for the frame               */
   float     device_ms;        /* CUDA-event time, generation -> last framebuffer add          */
   float     trace_ms;         /* sum of the trace-kernel launch durations (CUDA events)       */
+  long long nodes_visited;    /* BVH nodes / primitives tested by the trace kernel; 0 unless  */
+  long long prims_tested;     /* the library was compiled with -DGXY_TRAV_COUNTERS            */
 } gxy_stats;
 
 /* ---- library ---------------------------------------------------------------------------- */
