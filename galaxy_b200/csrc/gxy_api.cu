@@ -186,7 +186,9 @@ struct gxy_vis {
   BvhResult bvh;
   bool has_dvr = false;
   // work buffers
-  RayBuf cur, next, send, recv;
+  RayBuf cur, next, send, recv, hits;
+  Scratch<unsigned long long> fq;  // FusedQueues of the fused frame path
+  Scratch<unsigned> rawhits;
   Scratch<int> hit_index, block_sums, small;  // small: nhit, counts, offsets, cursor ...
   Scratch<unsigned long long> counters;       // [0] terminated [1] samples
   Scratch<float> fb, fb_tmp;
@@ -347,7 +349,7 @@ void gxy_vis_destroy(gxy_vis *v) {
   if (!v) return;
   cudaSetDevice(v->ctx->device);
   vis_free_commit(v);
-  v->cur.release(); v->next.release(); v->send.release(); v->recv.release();
+  v->cur.release(); v->next.release(); v->send.release(); v->recv.release(); v->hits.release(); v->fq.release(); v->rawhits.release();
   v->hit_index.release(); v->block_sums.release(); v->small.release(); v->counters.release();
   v->fb.release(); v->fb_tmp.release(); v->rgba8.release(); v->io_f.release(); v->io_i.release();
   delete v;
@@ -804,39 +806,123 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
   GXY_CUDA(cudaEventRecord(ev0, ctx0->stream));
 
   std::vector<int> n_cur(nparts, 0);
-  // ---- generation (Camera::generate_initial_rays; every partition scans the full window) ----
+  // Geometry-only Visualizations take the fused path for the rays born in this frame (gxy_fused.cu);
+  // only rays that cross into a neighbour partition come back as lists ("spill") for the wave loop.
+  bool fused = true;
+  for (int p = 0; p < nparts; p++) fused = fused && parts[p]->P.n_volvis == 0 && parts[p]->P.n_prims > 0;
+  if (const char *e = getenv("GXY_FUSED")) fused = fused && atoi(e) != 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_events;
   for (int p = 0; p < nparts; p++) {
     gxy_vis *v = parts[p];
     if (use_device(v->ctx)) return 1;
     cudaStream_t st = v->ctx->stream;
-    if (v->cur.reserve(npix, false, st) || v->block_sums.reserve((size_t)std::max(npix, 1 << 20) / 1024 + 2) || v->small.reserve(64 + 4 * (size_t)nranks) ||
-        v->counters.reserve(4) || v->fb.reserve((size_t)npix * 4))
+    if (v->block_sums.reserve((size_t)std::max(npix, 1 << 20) / 1024 + 2) || v->small.reserve(64 + 4 * (size_t)nranks) || v->counters.reserve(4) ||
+        v->fb.reserve((size_t)npix * 4))
       return 1;
     v->fb_w = w; v->fb_h = h;
     GXY_CUDA(cudaMemsetAsync(v->fb.p, 0, sizeof(float) * 4 * npix, st));
     GXY_CUDA(cudaMemsetAsync(v->counters.p, 0, sizeof(unsigned long long) * 4, st));
-    if (launch_generate(v->P, C, w, h, v->cur.v, nullptr, v->block_sums.p, v->small.p, st)) return 1;
-    S.kernel_launches += 3;
   }
-  for (int p = 0; p < nparts; p++) {
-    gxy_vis *v = parts[p];
-    if (use_device(v->ctx)) return 1;
-    GXY_CUDA(cudaMemcpyAsync(&n_cur[p], v->small.p, sizeof(int), cudaMemcpyDeviceToHost, v->ctx->stream));
-    GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
-    S.primary_rays += n_cur[p];
+  if (fused) {
+    static_assert(sizeof(FusedQueues) == 48, "FusedQueues layout");
+    std::vector<FusedQueues> fq(nparts);
+    std::vector<bool> can_spill(nparts, false);
+    // ---- primary rays: generate -> trace -> light -> framebuffer, hit records for the secondaries
+    for (int p = 0; p < nparts; p++) {
+      gxy_vis *v = parts[p];
+      if (use_device(v->ctx)) return 1;
+      cudaStream_t st = v->ctx->stream;
+      for (int f = 0; f < 6; f++) can_spill[p] = can_spill[p] || v->neighbors[f] >= 0;
+      if (v->hits.reserve(npix, false, st) || v->fq.reserve(sizeof(FusedQueues) / 8) || v->rawhits.reserve((size_t)6 * npix)) return 1;
+      if (v->next.reserve(npix, false, st)) return 1;  // the generated primaries
+      if (v->cur.reserve(can_spill[p] ? (size_t)npix : 64, false, st)) return 1;
+      GXY_CUDA(cudaMemsetAsync(v->fq.p, 0, sizeof(FusedQueues), st));
+      cudaEvent_t ta, tb;
+      GXY_CUDA(cudaEventCreate(&ta));
+      GXY_CUDA(cudaEventCreate(&tb));
+      GXY_CUDA(cudaEventRecord(ta, st));
+      if (launch_fused_primary(v->P, C, L, w, h, v->fb.p, v->next.v, v->rawhits.p, v->hits.v, v->cur.v,
+                               can_spill[p] ? (unsigned)v->cur.cap : 0u, reinterpret_cast<FusedQueues *>(v->fq.p), epsilon, st))
+        return 1;
+      GXY_CUDA(cudaEventRecord(tb, st));
+      trace_events.push_back(std::make_pair(ta, tb));
+      S.kernel_launches += 3;
+      S.waves++;
+    }
+    // ---- secondary rays.  A partition without neighbours cannot spill: no host round trip at all.
+    for (int p = 0; p < nparts; p++) {
+      gxy_vis *v = parts[p];
+      if (n_sec_per_hit == 0) continue;
+      if (use_device(v->ctx)) return 1;
+      cudaStream_t st = v->ctx->stream;
+      long long max_rays = (long long)npix * n_sec_per_hit;
+      if (can_spill[p]) {  // size the spill list for the worst case: every secondary ray leaves
+        GXY_CUDA(cudaMemcpyAsync(&fq[p], v->fq.p, sizeof(FusedQueues), cudaMemcpyDeviceToHost, st));
+        GXY_CUDA(cudaStreamSynchronize(st));
+        max_rays = (long long)fq[p].n_hits * n_sec_per_hit;
+        GXY_CHECK(max_rays + fq[p].n_spill < (1ll << 31) - (1ll << 24), "secondary ray list too large (%lld rays)", max_rays);
+        if (v->cur.reserve((size_t)(max_rays + fq[p].n_spill), true, st)) return 1;
+      }
+      cudaEvent_t ta, tb;
+      GXY_CUDA(cudaEventCreate(&ta));
+      GXY_CUDA(cudaEventCreate(&tb));
+      GXY_CUDA(cudaEventRecord(ta, st));
+      if (launch_fused_secondary(v->P, L, w, h, n_sec_per_hit, max_rays, v->fb.p, v->hits.v, v->cur.v, can_spill[p] ? (unsigned)v->cur.cap : 0u,
+                                 reinterpret_cast<FusedQueues *>(v->fq.p), epsilon, !v->has_dvr, st))
+        return 1;
+      GXY_CUDA(cudaEventRecord(tb, st));
+      trace_events.push_back(std::make_pair(ta, tb));
+      S.kernel_launches += 1;
+      S.waves++;
+    }
+    for (int p = 0; p < nparts; p++) {
+      gxy_vis *v = parts[p];
+      if (use_device(v->ctx)) return 1;
+      GXY_CUDA(cudaMemcpyAsync(&fq[p], v->fq.p, sizeof(FusedQueues), cudaMemcpyDeviceToHost, v->ctx->stream));
+    }
+    for (int p = 0; p < nparts; p++) {
+      gxy_vis *v = parts[p];
+      if (use_device(v->ctx)) return 1;
+      GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+      S.primary_rays += (long long)fq[p].n_primary32;
+      S.ao_rays += (long long)fq[p].n_hits * lights.n_ao;
+      S.shadow_rays += (long long)fq[p].n_hits * (lights.shadows ? lights.n_lights : 0);
+      S.traced_rays += (long long)fq[p].n_primary32 + (long long)fq[p].n_hits * n_sec_per_hit;
+      S.terminated_rays += (long long)fq[p].n_terminated;
+      S.nodes_visited += (long long)fq[p].nodes;
+      S.prims_tested += (long long)fq[p].prims;
+      n_cur[p] = (int)fq[p].n_spill;  // rays bound for a neighbour partition, classification already set
+    }
+  } else {
+    // ---- generation (Camera::generate_initial_rays; every partition scans the full window) ----
+    for (int p = 0; p < nparts; p++) {
+      gxy_vis *v = parts[p];
+      if (use_device(v->ctx)) return 1;
+      if (v->cur.reserve(npix, false, v->ctx->stream)) return 1;
+      if (launch_generate(v->P, C, w, h, v->cur.v, nullptr, v->block_sums.p, v->small.p, v->ctx->stream)) return 1;
+      S.kernel_launches += 3;
+    }
+    for (int p = 0; p < nparts; p++) {
+      gxy_vis *v = parts[p];
+      if (use_device(v->ctx)) return 1;
+      GXY_CUDA(cudaMemcpyAsync(&n_cur[p], v->small.p, sizeof(int), cudaMemcpyDeviceToHost, v->ctx->stream));
+      GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+      S.primary_rays += n_cur[p];
+    }
   }
 
   // small[] layout (ints): [0] nhit/ngen  [8 .. 8+nranks) counts  [8+nranks .. 8+2nranks] offsets  then cursor
   std::vector<std::vector<int>> send_counts(nparts, std::vector<int>(nranks, 0)), send_offsets(nparts, std::vector<int>(nranks + 1, 0));
   std::vector<int> n_spawn(nparts, 0);
   std::vector<int> all_counts;  // multi-process: nranks x (nranks+1)
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_events;
   for (int wave = 0; wave < 100000; wave++) {
+    // the spill lists of the fused kernels enter the loop at its exchange step
+    const bool lists_classified = fused && wave == 0;
     long long pending_local = 0;
     for (int p = 0; p < nparts; p++) pending_local += n_cur[p];
     if (!multi_proc && pending_local == 0) break;
     // ---- trace + scan (async per partition) ----
-    for (int p = 0; p < nparts; p++) {
+    for (int p = 0; p < nparts && !lists_classified; p++) {
       gxy_vis *v = parts[p];
       const int n = n_cur[p];
       if (n == 0) continue;
@@ -857,7 +943,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
     }
     // ---- read hit counts, size the next lists, shade + spawn, classify, accumulate, sort ----
     std::vector<int> nhit(nparts, 0);
-    for (int p = 0; p < nparts; p++) {
+    for (int p = 0; p < nparts && !lists_classified; p++) {
       if (n_cur[p] == 0) continue;
       gxy_vis *v = parts[p];
       if (use_device(v->ctx)) return 1;
@@ -872,16 +958,18 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       if (use_device(v->ctx)) return 1;
       cudaStream_t st = v->ctx->stream;
       GXY_CUDA(cudaStreamSynchronize(st));
-      const long long nsp = (long long)nhit[p] * n_sec_per_hit;
-      GXY_CHECK(nsp < (1ll << 31) - (1ll << 24), "secondary ray list too large (%lld rays)", nsp);
-      n_spawn[p] = (int)nsp;
-      S.ao_rays += (long long)nhit[p] * lights.n_ao;
-      S.shadow_rays += (long long)nhit[p] * (lights.shadows ? lights.n_lights : 0);
-      if (v->next.reserve((size_t)std::max<long long>(nsp, 1), false, st)) return 1;
-      if (launch_shade_spawn(L, v->cur.v, n, v->hit_index.p, v->small.p, v->next.v, epsilon, st)) return 1;
-      if (launch_classify(v->P, v->cur.v, n, st)) return 1;
-      if (launch_accumulate(v->cur.v, n, v->fb.p, w, h, v->counters.p, st)) return 1;
-      S.kernel_launches += 3 + (lights.n_ao > 0 ? 1 : 0);
+      if (!lists_classified) {
+        const long long nsp = (long long)nhit[p] * n_sec_per_hit;
+        GXY_CHECK(nsp < (1ll << 31) - (1ll << 24), "secondary ray list too large (%lld rays)", nsp);
+        n_spawn[p] = (int)nsp;
+        S.ao_rays += (long long)nhit[p] * lights.n_ao;
+        S.shadow_rays += (long long)nhit[p] * (lights.shadows ? lights.n_lights : 0);
+        if (v->next.reserve((size_t)std::max<long long>(nsp, 1), false, st)) return 1;
+        if (launch_shade_spawn(L, v->cur.v, n, v->hit_index.p, v->small.p, v->next.v, epsilon, st)) return 1;
+        if (launch_classify(v->P, v->cur.v, n, st)) return 1;
+        if (launch_accumulate(v->cur.v, n, v->fb.p, w, h, v->counters.p, st)) return 1;
+        S.kernel_launches += 3 + (lights.n_ao > 0 ? 1 : 0);
+      }
       if (nranks > 1) {
         if (v->send.reserve((size_t)n, false, st)) return 1;
         int *d_counts = v->small.p + 8, *d_offsets = d_counts + nranks, *d_cursor = d_offsets + nranks + 1;

@@ -1,0 +1,387 @@
+// gxy_fused.cu -- the frame path for geometry-only Visualizations: two persistent kernels that keep
+// a ray in registers from its creation to its framebuffer contribution.
+//
+//   fused_primary_kernel    Camera::SpawnRays (Camera.cpp:379-493) -> TraceRays_TraceRays
+//                           (TraceRays.ispc:326-623) -> ambient/diffuseLighting (:735-761, :859-923) ->
+//                           Renderer::Classify/AssignDestinations (Renderer.cpp:304-454) ->
+//                           Rendering::AddLocalPixels (Rendering.cpp:125-153) + a compact record per
+//                           surface hit
+//   fused_secondary_kernel  TraceRays_generateAORays/_generateShadowRays (:625-733, :763-857) from
+//                           those records -> TraceRays_TraceRays -> Classify -> AddLocalPixels
+//
+// The list-based kernels (gxy_kernels.cu) materialise every ray of a wave in a 100-B/ray RayList and
+// run generate / trace / hit-scan / spawn / classify / accumulate as separate launches with host
+// round trips between them.  On one partition no ray ever needs to exist in memory: only rays that
+// leave through an internal face are written out ("spilled") as ordinary RayList entries and then
+// take the list path (exchange, re-trace on the neighbour).  Arithmetic per ray is the same device
+// code as the list path (gxy_shade.cuh, gxy_traverse.cuh); only the order of the framebuffer
+// additions differs, which is unordered in the reference too (Rendering.cpp:91-153).
+#include "gxy_internal.h"
+#include "gxy_shade.cuh"
+
+#include <string.h>
+
+#include <algorithm>
+
+namespace gxy {
+
+#define FULLMASK 0xffffffffu
+
+// pixel order of the primary queue: 8x4 tiles, so that the 32 lanes of a warp start as a compact beam
+__device__ __forceinline__ void tile_pixel(unsigned idx, int tiles_x, int &x, int &y) {
+  const unsigned tile = idx >> 5, in = idx & 31u;
+  x = (int)(tile % (unsigned)tiles_x) * 8 + (int)(in & 7u);
+  y = (int)(tile / (unsigned)tiles_x) * 4 + (int)(in >> 3);
+}
+
+__device__ __forceinline__ void write_spill(const Rays &S, unsigned j, float3 org, float3 dir, float r, float g, float b, float o, float t,
+                                            float tMax, int x, int y, int type, int term, int cls) {
+  S.ox[j] = org.x; S.oy[j] = org.y; S.oz[j] = org.z;
+  S.dx[j] = dir.x; S.dy[j] = dir.y; S.dz[j] = dir.z;
+  S.r[j] = r; S.g[j] = g; S.b[j] = b; S.o[j] = o;
+  S.t[j] = t; S.tMax[j] = tMax;
+  S.x[j] = x; S.y[j] = y; S.type[j] = type; S.term[j] = term; S.classification[j] = cls;
+}
+
+// position of each flagged lane in a global append list; all lanes of `group` must call (converged)
+__device__ __forceinline__ unsigned group_append(unsigned group, unsigned lane, bool flag, unsigned *counter) {
+  const unsigned m = __ballot_sync(group, flag);
+  if (m == 0u) return 0u;
+  const int leader = __ffs((int)m) - 1;
+  unsigned base = 0u;
+  if ((int)lane == leader) base = atomicAdd(counter, (unsigned)__popc(m));
+  base = __shfl_sync(group, base, leader);
+  return base + (unsigned)__popc(m & ((1u << lane) - 1u));
+}
+
+// Camera::SpawnRays for the whole window (Camera.cpp:379-493): one thread per pixel in tile order,
+// kept rays appended (unordered) to `out` (columns ox..dz x y; t = 0, tMax = FLT_MAX, type PRIMARY implied)
+__global__ void __launch_bounds__(256)
+    gen_primary_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevCamera C, int w, int h, int tiles_x,
+                       unsigned n_queue, Rays out, FusedQueues *__restrict__ q) {
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31u;
+  bool kept = false;
+  int x = 0, y = 0;
+  float3 o3 = f3(0.f, 0.f, 0.f), d3 = f3(0.f, 0.f, 0.f);
+  if (idx < n_queue) {
+    tile_pixel(idx, tiles_x, x, y);
+    kept = x < w && y < h && spawn_pixel(P, C, x, y, o3, d3);
+  }
+  const unsigned pos = group_append(FULLMASK, lane, kept, &q->n_primary32);
+  if (kept) {
+    out.ox[pos] = o3.x; out.oy[pos] = o3.y; out.oz[pos] = o3.z;
+    out.dx[pos] = d3.x; out.dy[pos] = d3.y; out.dz[pos] = d3.z;
+    out.x[pos] = x; out.y[pos] = y;
+  }
+}
+
+// Trace of the generated primaries (persistent warps, dynamic fetch, cooperative primitive tests).
+// A surface hit leaves a 6-word raw record (ray, t, u, v, ids, record) for shade_hits_kernel; a miss is
+// classified here: TERMINATED (adds nothing: its colour is 0) or spilled towards a neighbour.
+template <int FETCH_T, int MIN_BLOCKS>
+__global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
+    primary_trace_kernel(const __grid_constant__ SceneParams P, Rays R, unsigned *__restrict__ raw, unsigned raw_stride, Rays spill,
+                         unsigned spill_cap, FusedQueues *__restrict__ q) {
+  __shared__ uint2 stack[GXY_STACK_SMEM * GXY_TRACE_THREADS];
+  __shared__ unsigned char owner_of[GXY_TRACE_THREADS / 32][8];
+  uint2 lstack[GXY_STACK_LOCAL];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned n_queue = q->n_primary32;
+  RayCtx rc;
+  TravState st;
+  PendingRay pr;
+  pr.ray = -1; pr.tExit = 0.f; pr.anyhit = false; pr.opaque = false;
+  st.tg.y = 0u; st.ng.y = 0u;
+  rc.org = f3(0.f, 0.f, 0.f); rc.dir = f3(1.f, 1.f, 1.f); rc.tnear = 0.f; rc.tfar = 0.f;
+  st.best_t = 0.f; st.best_u = 0.f; st.best_v = 0.f; st.best_key = GXY_NO_HIT; st.best_rec = 0u;
+  bool trav = false, exhausted = false;
+  while (true) {
+    const unsigned m_idle = __ballot_sync(FULLMASK, !trav);
+    if (m_idle == FULLMASK || (!exhausted && __popc(m_idle) >= FETCH_T)) {
+      bool ex_local = false;
+      if (!trav) {
+        const bool fin = pr.ray >= 0;
+        const bool has_hit = fin && st.best_key != GXY_NO_HIT;
+        bool do_spill = false, terminated = false;
+        int term = 0, cls = CLS_UNDETERMINED;
+        if (fin && !has_hit) {
+          const float ray_t = rc.tfar;
+          if (ray_t == pr.tExit) term |= RAY_BOUNDARY;
+          else if (ray_t == FLT_MAX) term |= RAY_TIMEOUT;
+          cls = classify_values(P, RAY_PRIMARY, term, rc.org.x, rc.org.y, rc.org.z, R.dx[pr.ray], R.dy[pr.ray], R.dz[pr.ray]);
+          terminated = cls == CLS_TERMINATED;  // carries (0,0,0,0): nothing to add
+          do_spill = cls >= 0;
+        }
+#ifdef GXY_TRAV_COUNTERS
+        if (fin) atomicAdd(&q->nodes, (unsigned long long)st.n_nodes);
+#endif
+        // all appends and the fetch of this refill are issued back to back by one lane
+        const unsigned hm = __ballot_sync(m_idle, has_hit), sm = __ballot_sync(m_idle, do_spill), tm = __ballot_sync(m_idle, terminated);
+        const int leader = __ffs((int)m_idle) - 1;
+        const unsigned cnt = (unsigned)__popc(m_idle);
+        unsigned hbase = 0u, sbase = 0u, fbase = 0u;
+        if ((int)lane == leader) {
+          if (hm) hbase = atomicAdd(&q->n_hits, (unsigned)__popc(hm));
+          if (sm) sbase = atomicAdd(&q->n_spill, (unsigned)__popc(sm));
+          if (tm) atomicAdd(&q->n_terminated, (unsigned long long)__popc(tm));
+          if (!exhausted) fbase = atomicAdd(&q->pixel_head, cnt);
+        }
+        hbase = __shfl_sync(m_idle, hbase, leader);
+        sbase = __shfl_sync(m_idle, sbase, leader);
+        fbase = __shfl_sync(m_idle, fbase, leader);
+        if (has_hit) {
+          const unsigned hp = hbase + (unsigned)__popc(hm & lt_mask);
+          raw[hp] = (unsigned)pr.ray;
+          raw[hp + raw_stride] = __float_as_uint(st.best_t);
+          raw[hp + 2u * raw_stride] = __float_as_uint(st.best_u);
+          raw[hp + 3u * raw_stride] = __float_as_uint(st.best_v);
+          raw[hp + 4u * raw_stride] = st.best_key;
+          raw[hp + 5u * raw_stride] = st.best_rec;
+        }
+        if (do_spill) {
+          const unsigned sp = sbase + (unsigned)__popc(sm & lt_mask);
+          if (sp < spill_cap)
+            write_spill(spill, sp, rc.org, f3(R.dx[pr.ray], R.dy[pr.ray], R.dz[pr.ray]), 0.f, 0.f, 0.f, 0.f, rc.tfar, FLT_MAX, R.x[pr.ray],
+                        R.y[pr.ray], RAY_PRIMARY, term, cls);
+          else *P.error_flag = 3;
+        }
+        pr.ray = -1;
+        if (!exhausted) {
+          const unsigned my = fbase + (unsigned)__popc(m_idle & lt_mask);
+          ex_local = fbase + cnt >= n_queue;
+          if (my < n_queue)
+            trav = setup_ray_values(P, (int)my, true, f3(R.ox[my], R.oy[my], R.oz[my]), f3(R.dx[my], R.dy[my], R.dz[my]), 0.f, FLT_MAX, 0, rc,
+                                    st, pr);
+        }
+      }
+      exhausted = exhausted || __any_sync(FULLMASK, ex_local);
+      if (exhausted && __ballot_sync(FULLMASK, pr.ray >= 0) == 0u) break;
+    }
+    if (trav) node_step<0>(P, rc, st, stack, lstack);
+    coop_prim_passes(P, rc, st, trav, false, owner_of[warp], lane, lt_mask);
+    if (trav) trav = trav_advance(st, stack, lstack);
+  }
+}
+
+// postIntersect + ambient/diffuse lighting + framebuffer add for every surface hit, one thread per hit
+// (full SIMD efficiency, unlike a finish inside the persistent kernel), and the record the secondary
+// kernel generates AO/shadow rays from
+__global__ void __launch_bounds__(256)
+    shade_hits_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevLights L, Rays R, const unsigned *__restrict__ raw,
+                      unsigned raw_stride, int w, float4 *__restrict__ fb, Rays hits, FusedQueues *__restrict__ q, float epsilon) {
+  const unsigned hidx = blockIdx.x * blockDim.x + threadIdx.x;
+  bool terminated = false;
+  if (hidx < q->n_hits) {
+    const unsigned i = raw[hidx];
+    RayCtx rc;
+    rc.org = f3(R.ox[i], R.oy[i], R.oz[i]);
+    const float3 dir0 = f3(R.dx[i], R.dy[i], R.dz[i]);
+    rc.dir = dir0;
+    if (rc.dir.x == 0.f) rc.dir.x = 1e-6f;  // TraceRays.ispc:377-379
+    if (rc.dir.y == 0.f) rc.dir.y = 1e-6f;
+    if (rc.dir.z == 0.f) rc.dir.z = 1e-6f;
+    TravState st;
+    st.best_t = __uint_as_float(raw[hidx + raw_stride]);
+    st.best_u = __uint_as_float(raw[hidx + 2u * raw_stride]);
+    st.best_v = __uint_as_float(raw[hidx + 3u * raw_stride]);
+    st.best_key = raw[hidx + 4u * raw_stride];
+    st.best_rec = raw[hidx + 5u * raw_stride];
+    Hit1 h1;
+    trav_fetch_hit(P, rc, st, h1);
+    float3 col, Ns;
+    float opacity;
+    shade_geometry_hit(P, h1, rc.dir, col, opacity, Ns);
+    int term = RAY_SURFACE;
+    if (opacity > 0.999f) term |= RAY_OPAQUE;
+    HitPoint hp;
+    hp.ox = rc.org.x; hp.oy = rc.org.y; hp.oz = rc.org.z; hp.dx = dir0.x; hp.dy = dir0.y; hp.dz = dir0.z; hp.t = st.best_t;
+    hp.sn = Ns; hp.sr = col.x; hp.sg = col.y; hp.sb = col.z; hp.o = 0.f; hp.px = R.x[i]; hp.py = R.y[i];
+    float r = 0.f, g = 0.f, b = 0.f, o = 0.f;
+    light_primary(L, hp, r, g, b, o);
+    const int cls = classify_values(P, RAY_PRIMARY, term, hp.ox, hp.oy, hp.oz, hp.dx, hp.dy, hp.dz);
+    if (cls == CLS_TERMINATED) {
+      terminated = true;
+      atomicAdd(fb + ((size_t)hp.py * w + hp.px), make_float4(r, g, b, o));
+    }
+    hits.ox[hidx] = hp.ox; hits.oy[hidx] = hp.oy; hits.oz[hidx] = hp.oz;
+    hits.dx[hidx] = hp.dx; hits.dy[hidx] = hp.dy; hits.dz[hidx] = hp.dz;
+    hits.t[hidx] = hp.t;
+    hits.nx[hidx] = Ns.x; hits.ny[hidx] = Ns.y; hits.nz[hidx] = Ns.z;
+    hits.sr[hidx] = col.x; hits.sg[hidx] = col.y; hits.sb[hidx] = col.z;
+    hits.o[hidx] = 0.f;  // opacity before diffuseLighting (no volumes on this path)
+    hits.x[hidx] = hp.px; hits.y[hidx] = hp.py;
+    // the j-independent part of generateAORays, once per hit: origin -> r g b, b0 -> sample so tMax,
+    // b1 -> type term classification (spare columns of the record)
+    float3 aorg, b0, b1;
+    ao_basis(hp, epsilon, aorg, b0, b1);
+    hits.r[hidx] = aorg.x; hits.g[hidx] = aorg.y; hits.b[hidx] = aorg.z;
+    hits.sample[hidx] = b0.x; hits.so[hidx] = b0.y; hits.tMax[hidx] = b0.z;
+    hits.type[hidx] = __float_as_int(b1.x); hits.term[hidx] = __float_as_int(b1.y); hits.classification[hidx] = __float_as_int(b1.z);
+  }
+  const unsigned tm = __ballot_sync(FULLMASK, terminated);
+  if (tm != 0u && (threadIdx.x & 31u) == 0u) atomicAdd(&q->n_terminated, (unsigned long long)__popc(tm));
+}
+
+// queue order of the secondary rays: all AO rays (hit-major), then all shadow rays (hit-major), as the
+// reference lays out its SECONDARY list (TraceRays.cpp:89-122): keeps the long, parallel shadow rays of
+// neighbouring hits together in a warp instead of mixing them with the short AO rays
+__device__ __forceinline__ void secondary_index(unsigned k, unsigned n_hits, int n_ao, int n_sh, int &hi, int &j) {
+  const unsigned n_ao_rays = n_hits * (unsigned)n_ao;
+  if (k < n_ao_rays) { hi = (int)(k / (unsigned)n_ao); j = (int)(k - (unsigned)hi * (unsigned)n_ao); }
+  else { const unsigned k2 = k - n_ao_rays; hi = (int)(k2 / (unsigned)n_sh); j = n_ao + (int)(k2 - (unsigned)hi * (unsigned)n_sh); }
+}
+
+// secondary ray j of hit record hi: AO rays first (from the prepared basis), then one shadow ray per light
+__device__ __forceinline__ SecRay make_secondary(const DevLights &L, const Rays &hits, int hi, int j, float epsilon, const float *tx,
+                                                 const float *ty, const float *tz) {
+  if (j < L.n_ao) {
+    const float3 sn = f3(hits.nx[hi], hits.ny[hi], hits.nz[hi]);
+    const float3 org = f3(hits.r[hi], hits.g[hi], hits.b[hi]);
+    const float3 b0 = f3(hits.sample[hi], hits.so[hi], hits.tMax[hi]);
+    const float3 b1 = f3(__int_as_float(hits.type[hi]), __int_as_float(hits.term[hi]), __int_as_float(hits.classification[hi]));
+    return ao_ray_from_basis(L, sn, org, b0, b1, hits.sr[hi], hits.sg[hi], hits.sb[hi], hits.o[hi], hits.x[hi], hits.y[hi], j, epsilon, tx, ty,
+                             tz);
+  }
+  const HitPoint hp = load_hit_point(hits, hi);
+  const float Kd = L.Kd / L.n_lights;
+  const float o_lit = hp.o + Kd * (1 - hp.o) * hp.o;  // the o diffuseLighting leaves behind (:918-920)
+  return make_shadow_ray(L, hp, j - L.n_ao, epsilon, o_lit);
+}
+
+template <int FETCH_T, int MIN_BLOCKS>
+__global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
+    fused_secondary_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevLights L, int w, int h, int nsec,
+                           float4 *__restrict__ fb, Rays hits, Rays spill, unsigned spill_cap, FusedQueues *__restrict__ q, float epsilon,
+                           int anyhit_secondary) {
+  __shared__ uint2 stack[GXY_STACK_SMEM * GXY_TRACE_THREADS];
+  __shared__ unsigned char owner_of[GXY_TRACE_THREADS / 32][8];
+  __shared__ float ao_tab[3][256];  // divergent indices: shared memory, not the constant cache
+  uint2 lstack[GXY_STACK_LOCAL];
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) { ao_tab[0][k] = c_ao_x[k]; ao_tab[1][k] = c_ao_y[k]; ao_tab[2][k] = c_ao_z[k]; }
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned n_hits = q->n_hits;
+  const unsigned long long total64 = (unsigned long long)n_hits * (unsigned)nsec;
+  const unsigned n_queue = total64 > 0xfffffff0ull ? 0xfffffff0u : (unsigned)total64;
+  RayCtx rc;
+  TravState st;
+  PendingRay pr;
+  pr.ray = -1; pr.tExit = 0.f; pr.anyhit = false; pr.opaque = false;
+  st.tg.y = 0u; st.ng.y = 0u;
+  rc.org = f3(0.f, 0.f, 0.f); rc.dir = f3(1.f, 1.f, 1.f); rc.tnear = 0.f; rc.tfar = 0.f;
+  st.best_t = 0.f; st.best_key = GXY_NO_HIT;
+  bool trav = false, exhausted = false;
+  while (true) {
+    const unsigned m_idle = __ballot_sync(FULLMASK, !trav);
+    if (m_idle == FULLMASK || (!exhausted && __popc(m_idle) >= FETCH_T)) {
+      bool ex_local = false;
+      if (!trav) {
+        bool do_spill = false, terminated = false;
+        SecRay s;
+        s.org = f3(0.f, 0.f, 0.f); s.dir = f3(0.f, 0.f, 0.f); s.r = s.g = s.b = 0.f; s.tMax = 0.f; s.type = 0;
+        float ray_t = 0.f;
+        int px = 0, py = 0, term = 0, cls = CLS_UNDETERMINED;
+        if (pr.ray >= 0) {
+          const bool found = st.best_key != GXY_NO_HIT;
+          ray_t = found ? st.best_t : rc.tfar;
+          // only rays that were occluded or reached the box need their colour / exact direction again
+          if (found || ray_t == pr.tExit || pr.opaque) {
+            int hi, j;
+            secondary_index((unsigned)pr.ray, n_hits, L.n_ao, nsec - L.n_ao, hi, j);
+            s = make_secondary(L, hits, hi, j, epsilon, ao_tab[0], ao_tab[1], ao_tab[2]);
+            px = hits.x[hi]; py = hits.y[hi];
+            term = (min3f(s.r, s.g, s.b) >= 1.0f) ? RAY_OPAQUE : 0;
+            if (found) term |= RAY_SURFACE | RAY_OPAQUE;  // non-shaded ray on a surface, see trace_kernel
+            else if (ray_t == pr.tExit) term |= RAY_BOUNDARY;
+            else if (ray_t == s.tMax) term |= RAY_TIMEOUT;
+            cls = classify_values(P, s.type, term, s.org.x, s.org.y, s.org.z, s.dir.x, s.dir.y, s.dir.z);
+            if (cls == CLS_TERMINATED) {
+              terminated = true;
+              atomicAdd(fb + ((size_t)py * w + px), make_float4(s.r, s.g, s.b, 0.f));
+            } else if (cls >= 0) do_spill = true;
+          }
+          // else: TIMEOUT (AO ray that reached ao_radius) or nothing: DROP_ON_FLOOR (Renderer.cpp:394-419)
+#ifdef GXY_TRAV_COUNTERS
+          atomicAdd(&q->nodes, (unsigned long long)st.n_nodes);
+#endif
+        }
+        // the spill append, the statistics and the fetch of this refill are issued back to back by one lane
+        const unsigned sm = __ballot_sync(m_idle, do_spill), tm = __ballot_sync(m_idle, terminated);
+        const int leader = __ffs((int)m_idle) - 1;
+        const unsigned cnt = (unsigned)__popc(m_idle);
+        unsigned sbase = 0u, fbase = 0u;
+        if ((int)lane == leader) {
+          if (sm) sbase = atomicAdd(&q->n_spill, (unsigned)__popc(sm));
+          if (tm) atomicAdd(&q->n_terminated, (unsigned long long)__popc(tm));
+          if (!exhausted) fbase = atomicAdd(&q->sec_head, cnt);
+        }
+        sbase = __shfl_sync(m_idle, sbase, leader);
+        fbase = __shfl_sync(m_idle, fbase, leader);
+        if (do_spill) {
+          const unsigned sp = sbase + (unsigned)__popc(sm & lt_mask);
+          if (sp < spill_cap) write_spill(spill, sp, s.org, s.dir, s.r, s.g, s.b, 0.f, ray_t, s.tMax, px, py, s.type, term, cls);
+          else *P.error_flag = 3;
+        }
+        pr.ray = -1;
+        if (!exhausted) {
+          const unsigned my = fbase + (unsigned)__popc(m_idle & lt_mask);
+          ex_local = fbase + cnt >= n_queue;
+          if (my < n_queue) {
+            int hi, j;
+            secondary_index(my, n_hits, L.n_ao, nsec - L.n_ao, hi, j);
+            const SecRay sr = make_secondary(L, hits, hi, j, epsilon, ao_tab[0], ao_tab[1], ao_tab[2]);
+            trav = setup_ray_values(P, (int)my, false, sr.org, sr.dir, 0.f, sr.tMax, anyhit_secondary, rc, st, pr);
+            pr.opaque = min3f(sr.r, sr.g, sr.b) >= 1.0f;
+          }
+        }
+      }
+      exhausted = exhausted || __any_sync(FULLMASK, ex_local);
+      if (exhausted && __ballot_sync(FULLMASK, pr.ray >= 0) == 0u) break;
+    }
+    if (trav) node_step<0>(P, rc, st, stack, lstack);
+    coop_prim_passes(P, rc, st, trav, pr.anyhit, owner_of[warp], lane, lt_mask);
+    if (trav) trav = trav_advance(st, stack, lstack);
+  }
+}
+
+static int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = GXY_SM_COUNT;
+  }
+  return sms;
+}
+
+int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLights &L, int w, int h, float *fb, Rays prim, unsigned *raw,
+                         Rays hits, Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, cudaStream_t st) {
+  if (ensure_ao_tables()) return 1;
+  const int tiles_x = (w + 7) / 8, tiles_y = (h + 3) / 4;
+  const unsigned n_queue = (unsigned)tiles_x * (unsigned)tiles_y * 32u;
+  const unsigned npix = (unsigned)w * (unsigned)h;
+  gen_primary_kernel<<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, n_queue, prim, q);
+  const unsigned needed = (npix + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
+  const unsigned blocks = std::min<unsigned>(needed, (unsigned)sm_count() * 8u);
+  primary_trace_kernel<8, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q);
+  shade_hits_kernel<<<(npix + 255) / 256, 256, 0, st>>>(P, L, prim, raw, npix, w, reinterpret_cast<float4 *>(fb), hits, q, epsilon);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_fused_secondary(const SceneParams &P, const DevLights &L, int w, int h, int nsec, long long max_rays, float *fb, Rays hits,
+                           Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, bool anyhit, cudaStream_t st) {
+  if (nsec <= 0 || max_rays <= 0) return 0;
+  if (ensure_ao_tables()) return 1;
+  const long long needed = (max_rays + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
+  const unsigned blocks = (unsigned)std::min<long long>(needed, (long long)sm_count() * 8);
+  fused_secondary_kernel<8, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, L, w, h, nsec, reinterpret_cast<float4 *>(fb), hits, spill,
+                                                                     spill_cap, q, epsilon, anyhit ? 1 : 0);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gxy

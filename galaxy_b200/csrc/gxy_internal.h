@@ -34,6 +34,22 @@ int launch_copy_rays(Rays dst, size_t dst_off, Rays src, size_t src_off, int n, 
 int launch_intersect(const SceneParams &P, int n, const float *org3, const float *dir3, const float *tnear, const float *tfar,
                      int *geom_prim2, float *tuv3, cudaStream_t st);
 
+// ---- fused frame kernels for geometry-only Visualizations (gxy_fused.cu) ---------------------------
+struct FusedQueues {  // device memory, zeroed at the start of a frame
+  unsigned pixel_head, n_hits, n_spill, sec_head;
+  unsigned n_primary32, pad;
+  unsigned long long n_terminated, nodes, prims;
+};
+// generation (1 kernel) -> trace + classify of the misses (persistent kernel) -> shade/light/framebuffer of
+// the hits (1 kernel); hit records go to `hits` (columns ox..dz t nx..nz sr..sb o x y), rays bound for
+// a neighbour to `spill`
+// prim: list for the generated rays (>= w*h), raw: 6*w*h words of scratch, hits: >= w*h records
+int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLights &L, int w, int h, float *fb, Rays prim, unsigned *raw,
+                         Rays hits, Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, cudaStream_t st);
+// AO + shadow rays of every hit record: generate -> trace -> classify -> framebuffer
+int launch_fused_secondary(const SceneParams &P, const DevLights &L, int w, int h, int nsec, long long max_rays, float *fb, Rays hits,
+                           Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, bool anyhit, cudaStream_t st);
+
 // ---- BVH build (gxy_bvh.cu) -----------------------------------------------------------------
 struct GeomBuildInput {
   int kind;  // 0 triangles, 1 spheres

@@ -10,7 +10,7 @@
 //  generate_*          K12 Camera::SpawnRays               src/renderer/Camera.cpp:379-493
 //  tonemap_kernel      K14 ColorImageWriter::Write         src/renderer/ImageWriter.cpp:30-48
 #include "gxy_internal.h"
-#include "gxy_traverse.cuh"
+#include "gxy_shade.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -24,39 +24,6 @@ struct SurfHit {  // TraceRays.ispc:79-88
   float t, opacity;
   float3 normal, color;
 };
-
-// postIntersect of a geometry hit (Model.ih:97-187 + DataDrivenTriangleMesh.ispc:34-121 /
-// DataDrivenSpheres.ispc:46-63): colour from the transfer function, shading normal normalised and
-// faced towards the ray
-__device__ __forceinline__ void shade_geometry_hit(const SceneParams &P, const Hit1 &h1, float3 dir, float3 &col, float &ca, float3 &Ns) {
-  const DevGeom g = P.geoms[h1.geom];
-  float3 Ng = h1.Ng;
-  Ns = h1.Ng;
-  col = f3(1.f, 1.f, 1.f);
-  ca = 1.f;
-  if (g.kind == 0) {  // DataDrivenTriangleMesh.ispc:34-121
-    const int i0 = __ldg(g.idx + 3 * (size_t)h1.prim), i1 = __ldg(g.idx + 3 * (size_t)h1.prim + 1), i2 = __ldg(g.idx + 3 * (size_t)h1.prim + 2);
-    const float3 bary = f3(1.0f - h1.u - h1.v, h1.u, h1.v);
-    if (g.normals) {
-      const float3 a = f3(__ldg(g.normals + 3 * (size_t)i0), __ldg(g.normals + 3 * (size_t)i0 + 1), __ldg(g.normals + 3 * (size_t)i0 + 2));
-      const float3 b = f3(__ldg(g.normals + 3 * (size_t)i1), __ldg(g.normals + 3 * (size_t)i1 + 1), __ldg(g.normals + 3 * (size_t)i1 + 2));
-      const float3 c = f3(__ldg(g.normals + 3 * (size_t)i2), __ldg(g.normals + 3 * (size_t)i2 + 1), __ldg(g.normals + 3 * (size_t)i2 + 2));
-      Ns = bary.x * a + bary.y * b + bary.z * c;  // interpolate(), vec.ih:723-726
-    }
-    if (g.data) {
-      const float d = bary.x * __ldg(g.data + i0) + bary.y * __ldg(g.data + i1) + bary.z * __ldg(g.data + i2);
-      col = tf_color(P.tfs + g.tf, d);
-      ca = 1.0f;
-    }
-  } else {  // DataDrivenSpheres.ispc:46-63
-    col = tf_color(P.tfs + g.tf, g.data ? __ldg(g.data + h1.prim) : 0.f);
-    ca = 1.0f;
-  }
-  Ng = normalize_isp(Ng);
-  Ns = normalize_isp(Ns);
-  if (dot3(dir, Ng) >= 0.f) Ng = neg3(Ng);
-  if (dot3(Ng, Ns) < 0.f) Ns = neg3(Ns);
-}
 
 template <int NV>
 __device__ __forceinline__ void sample_volumes(const SceneParams &P, int nvv, float3 coord, float *s) {
@@ -264,41 +231,6 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS)
 // queue as soon as FETCH_T lanes of its warp have finished theirs (Aila/Laine-style dynamic fetch),
 // so that a warp is not held by its longest ray.  Per lane: setup (clip to the local box,
 // TraceRays.ispc:377-418) -> trav_step()* -> finish (postIntersect + term, :563-610).
-struct PendingRay {
-  int ray;        // index in the list, -1 = none
-  float tExit;    // tExitVolume of MyIntersectBox
-  bool anyhit;
-};
-
-__device__ __forceinline__ bool setup_geom_ray(const SceneParams &P, const Rays &R, int i, int anyhit_secondary, RayCtx &rc, TravState &st,
-                                               PendingRay &pr) {
-  const bool shadeFlag = R.type[i] == RAY_PRIMARY;
-  const float3 org = f3(R.ox[i], R.oy[i], R.oz[i]);
-  float3 dir = f3(R.dx[i], R.dy[i], R.dz[i]);
-  if (dir.x == 0.f) dir.x = 1e-6f;  // :377-379
-  if (dir.y == 0.f) dir.y = 1e-6f;
-  if (dir.z == 0.f) dir.z = 1e-6f;
-  float ray_t0 = R.t[i], ray_t = R.tMax[i];
-  float tEntry, tExitVolume;
-  {
-    const float rx = 1.0f / dir.x, ry = 1.0f / dir.y, rz = 1.0f / dir.z;
-    const float mnx = (P.lmin.x - org.x) * rx, mny = (P.lmin.y - org.y) * ry, mnz = (P.lmin.z - org.z) * rz;
-    const float mxx = (P.lmax.x - org.x) * rx, mxy = (P.lmax.y - org.y) * ry, mxz = (P.lmax.z - org.z) * rz;
-    tEntry = fmaxf(fminf(mnx, mxx), fmaxf(fminf(mny, mxy), fminf(mnz, mxz)));
-    tExitVolume = fminf(fmaxf(mnx, mxx), fminf(fmaxf(mny, mxy), fmaxf(mnz, mxz)));
-  }
-  if (tEntry < ray_t0) tEntry = ray_t0;  // :412-413
-  else if (tEntry > ray_t0) ray_t0 = tEntry;
-  ray_t = fminf(ray_t, tExitVolume);  // :418
-  ray_ctx_init(rc, org, dir, ray_t0, ray_t);
-  trav_init(st, rc);
-  pr.ray = i;
-  pr.tExit = tExitVolume;
-  pr.anyhit = !shadeFlag && anyhit_secondary;
-  // an empty interval cannot accept any candidate (both primitive tests need tnear < t <= tfar)
-  return ray_t0 <= ray_t;
-}
-
 __device__ __forceinline__ void finish_geom_ray(const SceneParams &P, const Rays &R, const RayCtx &rc, const TravState &st,
                                                 const PendingRay &pr, int *__restrict__ hit_ids) {
   const int i = pr.ray;
@@ -440,64 +372,7 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
     // ---- node phase (invariant: a traversing lane has st.ng.y > 0x00ffffff and no pending primitives here)
     if (trav) node_step<PREFETCH>(P, rc, st, stack, lstack);
     // ---- cooperative primitive passes
-    unsigned owners = __ballot_sync(FULL, trav && st.tg.y != 0u);
-    while (owners != 0u) {
-      const bool own = trav && st.tg.y != 0u;
-      const unsigned r = (unsigned)__popc(owners & lt_mask);  // rank among the owning lanes
-      if (own && r < 8u) owner_of[warp][r] = (unsigned char)lane;
-      __syncwarp();
-      const unsigned g = lane >> 2, k = lane & 3u;
-      const bool gvalid = g < (unsigned)__popc(owners);
-      const unsigned o = gvalid ? (unsigned)owner_of[warp][g] : lane;
-      const unsigned obits = __shfl_sync(FULL, st.tg.y, o), obase = __shfl_sync(FULL, st.tg.x, o);
-      unsigned b = obits;  // drop the k lowest set bits: the k-th pending primitive of the owner
-      if (k >= 1u) b &= b - 1u;
-      if (k >= 2u) b &= b - 1u;
-      if (k >= 3u) b &= b - 1u;
-      const bool tvalid = gvalid && b != 0u;
-      const float3 oorg = f3(__shfl_sync(FULL, rc.org.x, o), __shfl_sync(FULL, rc.org.y, o), __shfl_sync(FULL, rc.org.z, o));
-      const float3 odir = f3(__shfl_sync(FULL, rc.dir.x, o), __shfl_sync(FULL, rc.dir.y, o), __shfl_sync(FULL, rc.dir.z, o));
-      const float otn = __shfl_sync(FULL, rc.tnear, o), otf = __shfl_sync(FULL, rc.tfar, o);
-      float ct = __int_as_float(0x7f800000), cu = 0.f, cv = 0.f;
-      unsigned ckey = GXY_NO_HIT, crec = 0u;
-      if (tvalid) {
-        crec = obase + (unsigned)(__ffs((int)b) - 1);
-        const float4 *rec = reinterpret_cast<const float4 *>(P.prims + crec);
-        const float4 ra = __ldg(rec), rb = __ldg(rec + 1), rcq = __ldg(rec + 2);
-#ifdef GXY_TRAV_COUNTERS
-        atomicAdd(P.trav_counters + 1, 1ull);
-#endif
-        const unsigned gk = __float_as_uint(rcq.y);
-        float t, u = 0.f, v = 0.f;
-        bool h;
-        if ((gk >> 24) == 0) h = tri_test(ra, rb, rcq, oorg, odir, otn, otf, t, u, v);
-        else h = sphere_test(ra, rb, oorg, odir, otn, otf, t);
-        if (h) { ct = t; cu = u; cv = v; ckey = ((gk & 0xffffffu) << 28) | __float_as_uint(rcq.z); }
-      }
-      // the owner (rank r < 8) picks the best of its helpers, lanes 4r .. 4r+3
-      const unsigned h0 = (4u * r) & 31u;
-      int hb = -1;
-#pragma unroll
-      for (int kk = 0; kk < 4; kk++) {
-        const float ht = __shfl_sync(FULL, ct, h0 + kk);
-        const unsigned hk = __shfl_sync(FULL, ckey, h0 + kk);
-        if (own && r < 8u && hk != GXY_NO_HIT && (ht < st.best_t || (ht == st.best_t && hk < st.best_key))) {
-          st.best_t = ht; st.best_key = hk; hb = kk;
-        }
-      }
-      const unsigned hsrc = h0 + (unsigned)(hb < 0 ? 0 : hb);
-      const float hu = __shfl_sync(FULL, cu, hsrc), hv = __shfl_sync(FULL, cv, hsrc);
-      const unsigned hrec = __shfl_sync(FULL, crec, hsrc);
-      if (own && r < 8u) {
-        if (hb >= 0) { st.best_u = hu; st.best_v = hv; st.best_rec = hrec; }
-        unsigned nb = st.tg.y;  // the 4 lowest pending primitives have been tested
-        nb &= nb - 1u; nb &= nb - 1u; nb &= nb - 1u; nb &= nb - 1u;
-        st.tg.y = nb;
-        if (hb >= 0 && pr.anyhit) { trav = false; st.tg.y = 0u; }
-      }
-      __syncwarp();
-      owners = __ballot_sync(FULL, trav && st.tg.y != 0u);
-    }
+    coop_prim_passes(P, rc, st, trav, pr.anyhit, owner_of[warp], lane, lt_mask);
     // ---- next node group (stack pop) or end of traversal
     if (trav) trav = trav_advance(st, stack, lstack);
   }
@@ -680,44 +555,6 @@ int launch_hit_scan(Rays R, int n, int *d_hit_index, int *d_block_sums, int *d_n
   return 0;
 }
 
-// ------------------------------------------------------------------------------------------------
-// AO direction tables (src/renderer/UV.ih:21-58 + TraceRays.ispc:692-701), filled by the host:
-// x = cos(2*pi*r0)*sqrt(1-r1), y = sin(2*pi*r0)*sqrt(1-r1), z = sqrt(r1)  for the 256 (r0,r1) pairs
-__constant__ float c_ao_x[256], c_ao_y[256], c_ao_z[256];
-
-static void halton_tables(float U[256], float V[256]) {
-  // UV.ih holds base-2 / base-3 radical inverses accumulated in fp32 and printed with "%g"
-  for (int pass = 0; pass < 2; pass++) {
-    const int b = pass ? 3 : 2;
-    for (int i = 0; i < 256; i++) {
-      float inv = 1.f / (float)b, f = inv, r = 0.f;
-      for (int k = i; k > 0; k /= b) { r = r + f * (float)(k % b); f = f * inv; }
-      char buf[64];
-      snprintf(buf, sizeof buf, "%g", (double)r);
-      (pass ? V : U)[i] = strtof(buf, nullptr);
-    }
-  }
-}
-
-static int ensure_ao_tables() {
-  static bool done = false;
-  if (done) return 0;
-  float U[256], V[256], x[256], y[256], z[256];
-  halton_tables(U, V);
-  for (int r = 0; r < 256; r++) {
-    const float r0 = U[r], r1 = V[r];
-    const float w = sqrtf(1.f - r1);
-    x[r] = cosf((2.f * (float)M_PI) * r0) * w;
-    y[r] = sinf((2.f * (float)M_PI) * r0) * w;
-    z[r] = sqrtf(r1);
-  }
-  GXY_CUDA(cudaMemcpyToSymbol(c_ao_x, x, sizeof x));
-  GXY_CUDA(cudaMemcpyToSymbol(c_ao_y, y, sizeof y));
-  GXY_CUDA(cudaMemcpyToSymbol(c_ao_z, z, sizeof z));
-  done = true;
-  return 0;
-}
-
 // one thread per AO ray (TraceRays.ispc:645-731); runs BEFORE light_shadow_kernel (uses o before
 // diffuseLighting updates it, as the reference's call order does, TraceRays.cpp:124-131)
 __global__ void __launch_bounds__(256)
@@ -728,26 +565,13 @@ __global__ void __launch_bounds__(256)
   const long long total = (long long)(*d_nhit) * nAO;
   if (k >= total) return;
   const int h = (int)(k / nAO), j = (int)(k - (long long)h * nAO);
-  const int i = hit_list[h];
-  const float Ka = -L.Ka / nAO;  // GXY_REVERSE_LIGHTING
-  const float3 sn = f3(R.nx[i], R.ny[i], R.nz[i]);
-  const float ambient_scale = Ka * (1.0f - R.o[i]);
-  float3 b0 = f3(1.0f, 0.0f, 0.0f);
-  if (fabsf(dot3(b0, sn)) > 0.95f) b0 = f3(0.0f, 1.0f, 0.0f);
-  const float3 b1 = normalize_isp(cross3(b0, sn));
-  b0 = normalize_isp(cross3(b1, sn));
-  const float t = R.t[i];
-  float ox = R.ox[i] + t * R.dx[i], oy = R.oy[i] + t * R.dy[i], oz = R.oz[i] + t * R.dz[i];
-  ox = ox + epsilon * sn.x; oy = oy + epsilon * sn.y; oz = oz + epsilon * sn.z;
-  const int px = R.x[i], py = R.y[i];
-  const int r = ((px * 9949 + py * 9613 + j * 9151) >> 8) & 0xff;
-  const float x = c_ao_x[r], y = c_ao_y[r], z = c_ao_z[r] + epsilon;
-  const float3 rd = x * b0 + y * b1 + z * sn;
-  O.ox[k] = ox; O.oy[k] = oy; O.oz[k] = oz;
-  O.dx[k] = rd.x; O.dy[k] = rd.y; O.dz[k] = rd.z;
-  O.r[k] = ambient_scale * R.sr[i]; O.g[k] = ambient_scale * R.sg[i]; O.b[k] = ambient_scale * R.sb[i]; O.o[k] = 0.0f;
-  O.t[k] = 0.0f; O.tMax[k] = L.ao_radius;
-  O.x[k] = px; O.y[k] = py; O.type[k] = RAY_AO; O.term[k] = 0;
+  const HitPoint hp = load_hit_point(R, hit_list[h]);
+  const SecRay s = make_ao_ray(L, hp, j, epsilon);
+  O.ox[k] = s.org.x; O.oy[k] = s.org.y; O.oz[k] = s.org.z;
+  O.dx[k] = s.dir.x; O.dy[k] = s.dir.y; O.dz[k] = s.dir.z;
+  O.r[k] = s.r; O.g[k] = s.g; O.b[k] = s.b; O.o[k] = 0.0f;
+  O.t[k] = 0.0f; O.tMax[k] = s.tMax;
+  O.x[k] = hp.px; O.y[k] = hp.py; O.type[k] = RAY_AO; O.term[k] = 0;
 }
 
 // one thread per surface-hit primary: ambient (:735-761), diffuse (:859-923), shadow rays (:763-857)
@@ -759,59 +583,20 @@ __global__ void __launch_bounds__(256)
   if (h >= nhit) return;
   const int i = hit_list[h];
   const int nL = L.n_lights;
-  const float3 sn = f3(R.nx[i], R.ny[i], R.nz[i]);
-  const float sr = R.sr[i], sg = R.sg[i], sb = R.sb[i];
-  float r = R.r[i], g = R.g[i], b = R.b[i], o = R.o[i];
-  const float t = R.t[i];
-  const float ox = R.ox[i], oy = R.oy[i], oz = R.oz[i], dx = R.dx[i], dy = R.dy[i], dz = R.dz[i];
-  // ambientLighting
-  {
-    const float ambient_scale = L.Ka * (1.0f - o);
-    r += ambient_scale * sr; g += ambient_scale * sg; b += ambient_scale * sb;
-  }
-  // diffuseLighting
-  {
-    const float Kd = L.Kd / nL;
-    float tr = 0, tg = 0, tb = 0;
-    for (int k = 0; k < nL; k++) {
-      const float3 lt = f3(L.lights[k][0], L.lights[k][1], L.lights[k][2]);
-      float3 lvec;
-      if (L.types[k]) {
-        const float3 sp = f3(ox + t * dx, oy + t * dy, oz + t * dz);
-        lvec = safe_normalize(lt - sp);
-      } else lvec = neg3(lt);
-      const float d = dot3(sn, lvec);
-      if (d > 0) {
-        const float dff = (1.0f - o) * d;
-        tr += dff * sr; tg += dff * sg; tb += dff * sb;
-      }
-    }
-    r = r + Kd * (1 - o) * tr;
-    g = g + Kd * (1 - o) * tg;
-    b = b + Kd * (1 - o) * tb;
-    o = o + Kd * (1 - o) * o;
-  }
+  const HitPoint hp = load_hit_point(R, i);
+  float r = R.r[i], g = R.g[i], b = R.b[i], o = hp.o;
+  light_primary(L, hp, r, g, b, o);
   R.r[i] = r; R.g[i] = g; R.b[i] = b; R.o[i] = o;
   // generateShadowRays (uses the o updated by diffuseLighting, as the reference does)
   if (L.shadows) {
-    const float Kd = -L.Kd / nL;  // GXY_REVERSE_LIGHTING
     long long offset = (long long)nhit * L.n_ao + (long long)h * nL;
-    const int px = R.x[i], py = R.y[i];
     for (int k = 0; k < nL; k++) {
-      const float3 sp = f3(ox + t * dx + epsilon * sn.x, oy + t * dy + epsilon * sn.y, oz + t * dz + epsilon * sn.z);
-      const float3 lt = f3(L.lights[k][0], L.lights[k][1], L.lights[k][2]);
-      float3 lvec;
-      if (L.types[k]) lvec = safe_normalize(lt - sp);
-      else lvec = neg3(lt);
-      lvec = safe_normalize(lvec);
-      float d = dot3(sn, lvec);
-      if (d < 0) d = 0;
-      const float dff = (1.0f - o) * Kd * d;
-      O.ox[offset] = sp.x; O.oy[offset] = sp.y; O.oz[offset] = sp.z;
-      O.dx[offset] = lvec.x; O.dy[offset] = lvec.y; O.dz[offset] = lvec.z;
-      O.r[offset] = dff * sr; O.g[offset] = dff * sg; O.b[offset] = dff * sb; O.o[offset] = 0.0f;
-      O.t[offset] = 0.0f; O.tMax[offset] = __int_as_float(0x7f800000);
-      O.x[offset] = px; O.y[offset] = py; O.type[offset] = RAY_SHADOW; O.term[offset] = 0;
+      const SecRay s = make_shadow_ray(L, hp, k, epsilon, o);
+      O.ox[offset] = s.org.x; O.oy[offset] = s.org.y; O.oz[offset] = s.org.z;
+      O.dx[offset] = s.dir.x; O.dy[offset] = s.dir.y; O.dz[offset] = s.dir.z;
+      O.r[offset] = s.r; O.g[offset] = s.g; O.b[offset] = s.b; O.o[offset] = 0.0f;
+      O.t[offset] = 0.0f; O.tMax[offset] = s.tMax;
+      O.x[offset] = hp.px; O.y[offset] = hp.py; O.type[offset] = RAY_SHADOW; O.term[offset] = 0;
       offset++;
     }
   }
@@ -831,45 +616,6 @@ int launch_shade_spawn(const DevLights &L, Rays R, int n, const int *d_hit_index
   light_shadow_kernel<<<(n + 255) / 256, 256, 0, st>>>(L, R, hit_list, d_nhit, out, epsilon);
   GXY_CUDA(cudaGetLastError());
   return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Box::exit_face (src/data/Box.cpp:84-97)
-__device__ __forceinline__ int exit_face(float3 mn, float3 mx, float x, float y, float z, float dx, float dy, float dz) {
-  float tx = (dx > 0.0001f) ? ((mx.x - x) / dx) : (dx < -0.0001f) ? ((mn.x - x) / dx) : FLT_MAX;
-  float ty = (dy > 0.0001f) ? ((mx.y - y) / dy) : (dy < -0.0001f) ? ((mn.y - y) / dy) : FLT_MAX;
-  float tz = (dz > 0.0001f) ? ((mx.z - z) / dz) : (dz < -0.0001f) ? ((mn.z - z) / dz) : FLT_MAX;
-  if (tx < 0) tx = FLT_MAX;
-  if (ty < 0) ty = FLT_MAX;
-  if (tz < 0) tz = FLT_MAX;
-  if (tx < ty && tx < tz) return (dx < 0) ? 0 : 1;
-  else if (ty < tz) return (dy < 0) ? 2 : 3;
-  else return (dz < 0) ? 4 : 5;
-}
-
-__device__ __forceinline__ int classify_ray(const SceneParams &P, const Rays &R, int i) {
-  const int typ = R.type[i], term = R.term[i];
-  int c = CLS_UNDETERMINED;
-  if (typ == RAY_PRIMARY) {
-    if (term & RAY_BOUNDARY) c = RAY_BOUNDARY;
-    else if ((term & RAY_OPAQUE) | (term & RAY_TIMEOUT)) c = CLS_TERMINATED;
-    else c = CLS_KEEP_HERE;
-  } else if (typ == RAY_SHADOW) {
-    if ((term & RAY_OPAQUE) | (term & RAY_SURFACE)) c = CLS_TERMINATED;
-    else if (term & RAY_BOUNDARY) c = RAY_BOUNDARY;
-    else c = CLS_DROP_ON_FLOOR;
-  } else if (typ == RAY_AO) {
-    if ((term & RAY_OPAQUE) | (term & RAY_SURFACE)) c = CLS_TERMINATED;
-    else if (term & RAY_BOUNDARY) c = RAY_BOUNDARY;
-    else c = CLS_DROP_ON_FLOOR;  // TIMEOUT or unknown
-  }
-  if (c == RAY_BOUNDARY) {
-    const int f = exit_face(P.lmin, P.lmax, R.ox[i], R.oy[i], R.oz[i], R.dx[i], R.dy[i], R.dz[i]);
-    const int nb = P.neighbors[f];
-    if (nb >= 0) c = nb;
-    else c = (typ == RAY_SHADOW || typ == RAY_AO) ? CLS_DROP_ON_FLOOR : CLS_TERMINATED;
-  }
-  return c;
 }
 
 __global__ void __launch_bounds__(256) classify_kernel(const __grid_constant__ SceneParams P, Rays R, int n) {
@@ -956,46 +702,6 @@ int launch_partition_by_destination(Rays R, int n, int nranks, int keep_rank, Ra
   if (n > 0) dest_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(R, n, nranks, keep_rank, out, d_cursor);
   GXY_CUDA(cudaGetLastError());
   return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Box::intersect (src/data/Box.cpp:107-150)
-__device__ __forceinline__ bool box_intersect(float3 mn, float3 mx, float3 org, float3 dir, float &tmin, float &tmax) {
-  tmin = (mn.x - org.x) / dir.x;
-  tmax = (mx.x - org.x) / dir.x;
-  if (tmin > tmax) { float s = tmax; tmax = tmin; tmin = s; }
-  if (tmax < 0) return false;
-  float tymin = (mn.y - org.y) / dir.y, tymax = (mx.y - org.y) / dir.y;
-  if (tymin > tymax) { float s = tymax; tymax = tymin; tymin = s; }
-  if (tymax < 0) return false;
-  if ((tmin > tymax) || (tymin > tmax)) return false;
-  if (tymin > tmin) tmin = tymin;
-  if (tymax < tmax) tmax = tymax;
-  float tzmin = (mn.z - org.z) / dir.z, tzmax = (mx.z - org.z) / dir.z;
-  if (tzmin > tzmax) { float s = tzmax; tzmax = tzmin; tzmin = s; }
-  if (tzmax < 0) return false;
-  if ((tmin > tzmax) || (tzmin > tmax)) return false;
-  if (tzmin > tmin) tmin = tzmin;
-  if (tzmax < tmax) tmax = tzmax;
-  if (tmin < 0) tmin = 0;
-  return true;
-}
-
-// Camera::SpawnRays per pixel (Camera.cpp:403-441)
-__device__ __forceinline__ bool spawn_pixel(const SceneParams &P, const DevCamera &a, int x, int y, float3 &vorigin, float3 &vray) {
-  const float fx = ((float)x - a.off_x) * a.scaling;
-  const float fy = ((float)y - a.off_y) * a.scaling;
-  float3 xy;
-  xy.x = a.center.x + fx * a.vr.x + fy * a.vu.x;
-  xy.y = a.center.y + fx * a.vr.y + fy * a.vu.y;
-  xy.z = a.center.z + fx * a.vr.z + fy * a.vu.z;
-  if (a.ortho) { vorigin = xy - a.vdir; vray = a.vdir; }
-  else { vorigin = a.veye; vray = xy - a.veye; normalize_gxy(vray); }
-  float gmin, gmax, lmin = 0, lmax = 0;
-  bool hit = box_intersect(P.gmin, P.gmax, vorigin, vray, gmin, gmax);
-  if (hit) hit = box_intersect(P.lmin, P.lmax, vorigin, vray, lmin, lmax);
-  const float d = fabsf(lmin) - fabsf(gmin);
-  return hit && (lmax >= 0) && (d < 0.000001f) && (d > -0.000001f);
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)

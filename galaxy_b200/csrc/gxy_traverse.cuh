@@ -243,6 +243,73 @@ __device__ __forceinline__ bool prim_step(const SceneParams &P, const RayCtx &rc
   return false;
 }
 
+// Cooperative primitive passes of one warp (all 32 lanes must call this, converged): lane 4g+k tests
+// the k-th pending primitive of the g-th lane that holds a primitive group, the owner then takes the
+// (t, geomID, primID)-smallest candidate of its helpers.  On return no lane has pending primitives.
+// owner_slot: 8 bytes of shared memory private to the warp.
+__device__ __forceinline__ void coop_prim_passes(const SceneParams &P, const RayCtx &rc, TravState &st, bool &trav, const bool anyhit,
+                                                 unsigned char *owner_slot, const unsigned lane, const unsigned lt_mask) {
+  const unsigned FULL = 0xffffffffu;
+  unsigned owners = __ballot_sync(FULL, trav && st.tg.y != 0u);
+  while (owners != 0u) {
+    const bool own = trav && st.tg.y != 0u;
+    const unsigned r = (unsigned)__popc(owners & lt_mask);  // rank among the owning lanes
+    if (own && r < 8u) owner_slot[r] = (unsigned char)lane;
+    __syncwarp();
+    const unsigned g = lane >> 2, k = lane & 3u;
+    const bool gvalid = g < (unsigned)__popc(owners);
+    const unsigned o = gvalid ? (unsigned)owner_slot[g] : lane;
+    const unsigned obits = __shfl_sync(FULL, st.tg.y, o), obase = __shfl_sync(FULL, st.tg.x, o);
+    unsigned b = obits;  // drop the k lowest set bits: the k-th pending primitive of the owner
+    if (k >= 1u) b &= b - 1u;
+    if (k >= 2u) b &= b - 1u;
+    if (k >= 3u) b &= b - 1u;
+    const bool tvalid = gvalid && b != 0u;
+    const float3 oorg = f3(__shfl_sync(FULL, rc.org.x, o), __shfl_sync(FULL, rc.org.y, o), __shfl_sync(FULL, rc.org.z, o));
+    const float3 odir = f3(__shfl_sync(FULL, rc.dir.x, o), __shfl_sync(FULL, rc.dir.y, o), __shfl_sync(FULL, rc.dir.z, o));
+    const float otn = __shfl_sync(FULL, rc.tnear, o), otf = __shfl_sync(FULL, rc.tfar, o);
+    float ct = __int_as_float(0x7f800000), cu = 0.f, cv = 0.f;
+    unsigned ckey = GXY_NO_HIT, crec = 0u;
+    if (tvalid) {
+      crec = obase + (unsigned)(__ffs((int)b) - 1);
+      const float4 *rec = reinterpret_cast<const float4 *>(P.prims + crec);
+      const float4 ra = __ldg(rec), rb = __ldg(rec + 1), rcq = __ldg(rec + 2);
+#ifdef GXY_TRAV_COUNTERS
+      atomicAdd(P.trav_counters + 1, 1ull);
+#endif
+      const unsigned gk = __float_as_uint(rcq.y);
+      float t, u = 0.f, v = 0.f;
+      bool h;
+      if ((gk >> 24) == 0) h = tri_test(ra, rb, rcq, oorg, odir, otn, otf, t, u, v);
+      else h = sphere_test(ra, rb, oorg, odir, otn, otf, t);
+      if (h) { ct = t; cu = u; cv = v; ckey = ((gk & 0xffffffu) << 28) | __float_as_uint(rcq.z); }
+    }
+    // the owner (rank r < 8) picks the best of its helpers, lanes 4r .. 4r+3
+    const unsigned h0 = (4u * r) & 31u;
+    int hb = -1;
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      const float ht = __shfl_sync(FULL, ct, h0 + kk);
+      const unsigned hk = __shfl_sync(FULL, ckey, h0 + kk);
+      if (own && r < 8u && hk != GXY_NO_HIT && (ht < st.best_t || (ht == st.best_t && hk < st.best_key))) {
+        st.best_t = ht; st.best_key = hk; hb = kk;
+      }
+    }
+    const unsigned hsrc = h0 + (unsigned)(hb < 0 ? 0 : hb);
+    const float hu = __shfl_sync(FULL, cu, hsrc), hv = __shfl_sync(FULL, cv, hsrc);
+    const unsigned hrec = __shfl_sync(FULL, crec, hsrc);
+    if (own && r < 8u) {
+      if (hb >= 0) { st.best_u = hu; st.best_v = hv; st.best_rec = hrec; }
+      unsigned nb = st.tg.y;  // the 4 lowest pending primitives have been tested
+      nb &= nb - 1u; nb &= nb - 1u; nb &= nb - 1u; nb &= nb - 1u;
+      st.tg.y = nb;
+      if (hb >= 0 && anyhit) { trav = false; st.tg.y = 0u; }
+    }
+    __syncwarp();
+    owners = __ballot_sync(FULL, trav && st.tg.y != 0u);
+  }
+}
+
 // After a phase: make sure the lane has a node group with unvisited children (or pending primitives);
 // returns false when the traversal is complete.
 __device__ __forceinline__ bool trav_advance(TravState &s, const uint2 *__restrict__ stack, const uint2 *__restrict__ lstack) {
