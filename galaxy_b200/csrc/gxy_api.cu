@@ -1152,6 +1152,16 @@ int gxy_frame_download_rgba8(gxy_vis *v, unsigned char *rgba) {
   return 0;
 }
 
+int gxy_host_alloc(size_t bytes, void **out) {
+  GXY_CHECK(out, "gxy_host_alloc: NULL argument");
+  GXY_CHECK(gxy_device_count() > 0, "no CUDA device available: galaxy_b200 has no CPU fallback");
+  GXY_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  return 0;
+}
+void gxy_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
 // ---- multi-process -------------------------------------------------------------------------------
 int gxy_comm_unique_id(unsigned char id[128]) {
   if (load_nccl()) return 1;

@@ -103,6 +103,8 @@ def lib():
         L.gxy_render.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(Camera), C.POINTER(Lighting), C.c_int, C.c_int, C.c_float, C.POINTER(Stats)]
         L.gxy_frame_download_rgba32f.argtypes = [vp, fp]
         L.gxy_frame_download_rgba8.argtypes = [vp, C.POINTER(C.c_ubyte)]
+        L.gxy_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+        L.gxy_host_free.argtypes = [vp]
         L.gxy_comm_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
         L.gxy_comm_init.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]
         L.gxy_comm_destroy.argtypes = [vp]
@@ -301,10 +303,37 @@ class Scene:
         check(lib().gxy_frame_download_rgba32f(self.h, _f(fb)))
         return fb
 
-    def download_rgba8(self, w, h):
-        out = np.empty((h, w, 4), np.uint8)
+    def download_rgba8(self, w, h, out=None):
+        """RGBA8 image of the last frame; `out` may be a reusable (pinned) buffer from pinned_array()."""
+        if out is None:
+            out = np.empty((h, w, 4), np.uint8)
         check(lib().gxy_frame_download_rgba8(self.h, out.ctypes.data_as(C.POINTER(C.c_ubyte))))
         return out
+
+
+class _Pinned:
+    def __init__(self, nbytes):
+        self.p = C.c_void_p()
+        check(lib().gxy_host_alloc(nbytes, C.byref(self.p)))
+
+    def __del__(self):
+        try:
+            lib().gxy_host_free(self.p)
+        except Exception:
+            pass
+
+
+def pinned_array(shape, dtype):
+    """numpy array over page-locked host memory (gxy_host_alloc); freed with the array."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    owner = _Pinned(n)
+    buf = (C.c_ubyte * n).from_address(owner.p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _PINNED_OWNERS[id(buf)] = owner  # keep the allocation alive as long as the module is
+    return arr
+
+
+_PINNED_OWNERS = {}
 
 
 def render_device(parts, camera, lighting, w, h, epsilon=0.001):

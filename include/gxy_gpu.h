@@ -20,6 +20,8 @@
 #ifndef GXY_GPU_H
 #define GXY_GPU_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -187,6 +189,13 @@ int  gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *, const gxy
 int  gxy_frame_download_rgba32f(gxy_vis *owner, float *fb);
 /* ... or RGBA8 rows top-down exactly as ColorImageWriter::Write does (ImageWriter.cpp:30-48) */
 int  gxy_frame_download_rgba8(gxy_vis *owner, unsigned char *rgba);
+
+/* Page-locked host memory for the buffers handed to gxy_frame_download_* / gxy_trace_raylist: with it
+ * the D2H/H2D copies run at PCIe speed without a staging copy (any host pointer is accepted; pageable
+ * ones go through the driver's staging path).  The reference allocates RayLists and framebuffers with
+ * malloc (framework/smem.cpp:54-79); this is the CUDA equivalent of that allocator. */
+int  gxy_host_alloc(size_t bytes, void **out);
+void gxy_host_free(void *p);
 
 /* ---- multi-process (one process per GPU) --------------------------------------------------- */
 /* replaces MessageManager's MPI transport for SendRaysMsg / SendPixelsMsg
