@@ -18,6 +18,30 @@
 
 using namespace gxy;
 
+#include <chrono>
+struct PhaseTimer {  // GXY_PROFILE=1: host wall-clock per phase of gxy_render (each mark synchronises nothing)
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  std::vector<std::pair<std::string, double>> marks;
+  PhaseTimer() : on(getenv("GXY_PROFILE") && atoi(getenv("GXY_PROFILE"))), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char *name) {
+    if (!on) return;
+    auto t = std::chrono::steady_clock::now();
+    marks.push_back(std::make_pair(std::string(name), std::chrono::duration<double, std::milli>(t - t0).count()));
+    t0 = t;
+  }
+  void report(int rank) {
+    if (!on) return;
+    std::map<std::string, double> agg;
+    std::vector<std::string> order;
+    for (auto &m : marks) { if (!agg.count(m.first)) order.push_back(m.first); agg[m.first] += m.second; }
+    std::string line = "[gxy_render rank " + std::to_string(rank) + "]";
+    char buf[64];
+    for (auto &k : order) { snprintf(buf, sizeof buf, " %s=%.3f", k.c_str(), agg[k]); line += buf; }
+    fprintf(stderr, "%s\n", line.c_str());
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_error[1024] = "";
 void gxy_set_error(const char *fmt, ...) {
@@ -798,6 +822,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
   const int n_sec_per_hit = lights.n_ao + (lights.shadows ? lights.n_lights : 0);
   gxy_stats S;
   memset(&S, 0, sizeof S);
+  PhaseTimer PT;
 
   cudaEvent_t ev0, ev1;
   if (use_device(ctx0)) return 1;
@@ -849,6 +874,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       S.kernel_launches += 3;
       S.waves++;
     }
+    PT.mark("launchP");
     // ---- secondary rays.  A partition without neighbours cannot spill: no host round trip at all.
     for (int p = 0; p < nparts; p++) {
       gxy_vis *v = parts[p];
@@ -893,6 +919,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       S.prims_tested += (long long)fq[p].prims;
       n_cur[p] = (int)fq[p].n_spill;  // rays bound for a neighbour partition, classification already set
     }
+    PT.mark("fusedPS");
   } else {
     // ---- generation (Camera::generate_initial_rays; every partition scans the full window) ----
     for (int p = 0; p < nparts; p++) {
@@ -984,6 +1011,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       if (use_device(parts[p]->ctx)) return 1;
       GXY_CUDA(cudaStreamSynchronize(parts[p]->ctx->stream));
     }
+    PT.mark("wave_compute");
     // ---- exchange ----
     std::vector<int> n_next(nparts, 0);
     for (int p = 0; p < nparts; p++) n_next[p] = n_spawn[p];
@@ -1075,12 +1103,14 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       }
       if (global_pending == 0) { n_cur[0] = 0; break; }
     }
+    PT.mark("exchange");
     for (int p = 0; p < nparts; p++) {
       std::swap(parts[p]->cur, parts[p]->next);
       n_cur[p] = n_next[p];
     }
   }
 
+  PT.mark("exchange_tail");
   // ---- framebuffer: partial sums -> owner (SendPixelsMsg / AddLocalPixels) ----
   if (!multi_proc) {
     gxy_vis *v0 = parts[0];
@@ -1105,6 +1135,9 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
   if (use_device(ctx0)) return 1;
   GXY_CUDA(cudaEventRecord(ev1, ctx0->stream));
   GXY_CUDA(cudaEventSynchronize(ev1));
+  PT.mark("fb_reduce");
+  PT.report(rank0);
+  if (PT.on) fprintf(stderr, "[gxy_render rank %d] waves=%lld traced=%lld forwarded=%lld\n", rank0, S.waves, S.traced_rays, S.forwarded_rays);
   cudaEventElapsedTime(&S.device_ms, ev0, ev1);
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);

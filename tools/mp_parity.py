@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Multi-process parity check of the spatially partitioned frame path (one process per GPU, NCCL ray
+exchange + framebuffer reduce): run under torchrun, rank r owns partition r; rank 0 compares the image
+and the ray statistics with the CPU oracle rendering the same partitions in one process.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/mp_parity.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from galaxy_b200 import gpu, scenes  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = gpu.Context(local)
+    uid = [gpu.comm_unique_id()] if rank == 0 else [None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init(rank, world, uid[0])
+    n_lat, n_lon, w, h = 60, 120, 320, 240
+    vis, cam = scenes.c5_vis(), scenes.c5_camera()
+    ds, _ = scenes.c5_partition_mesh(n_lat, n_lon, world, rank)
+    part = scenes.build_partitions(gpu, vis, {"mesh": ds}, world, only_rank=rank, ctx=ctx)[0]
+    results = {}
+    for mode in ("fused", "lists"):
+        os.environ["GXY_FUSED"] = "1" if mode == "fused" else "0"
+        st = gpu.render_device([part], cam, vis["lighting"], w, h, 0.001)
+        keys = ["primary_rays", "shadow_rays", "ao_rays", "forwarded_rays", "terminated_rays"]
+        t = torch.tensor([st[k] for k in keys], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        results[mode] = (dict(zip(keys, t.tolist())), part.download_rgba32f(w, h) if rank == 0 else None)
+    ok = True
+    if rank == 0:
+        from oracle import oracle
+        full, _ = scenes.c5_partition_mesh(n_lat, n_lon, 1, 0)
+        o_parts = scenes.build_partitions(oracle, vis, {"mesh": full}, world)
+        fb_o, st_o = oracle.render(o_parts, cam, vis["lighting"], w, h, 0.001)
+        for mode, (st, fb) in results.items():
+            frac = float((np.abs(fb[..., :3] - fb_o[..., :3]).max(-1) <= 1.0 / 255).mean())
+            same = all(st[k] == st_o[k] for k in st)
+            print(json.dumps({"mode": mode, "world": world, "fraction_within_1_255": frac, "stats_equal": same, "gpu": st,
+                              "oracle": {k: st_o[k] for k in st}}), flush=True)
+            ok = ok and same and frac >= 0.999
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
