@@ -959,7 +959,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       GXY_CUDA(cudaEventCreate(&ta));
       GXY_CUDA(cudaEventCreate(&tb));
       GXY_CUDA(cudaEventRecord(ta, st));
-      if (launch_trace(v->P, v->cur.v, n, epsilon, nullptr, !v->has_dvr, nullptr, st)) return 1;
+      if (launch_trace(v->P, v->cur.v, n, epsilon, nullptr, !v->has_dvr, v->counters.p + 1, st)) return 1;
       GXY_CUDA(cudaEventRecord(tb, st));
       trace_events.push_back(std::make_pair(ta, tb));
       if (v->hit_index.reserve((size_t)2 * n) || v->block_sums.reserve((size_t)n / 1024 + 2)) return 1;
@@ -1155,6 +1155,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
     unsigned long long c[4];
     GXY_CUDA(cudaMemcpy(c, v->counters.p, sizeof c, cudaMemcpyDeviceToHost));
     S.terminated_rays += (long long)c[0];
+    S.volume_samples += (long long)c[1];
     unsigned long long tc[2];
     GXY_CUDA(cudaMemcpy(tc, v->P.trav_counters, sizeof tc, cudaMemcpyDeviceToHost));
     GXY_CUDA(cudaMemset(v->P.trav_counters, 0, sizeof tc));

@@ -19,6 +19,7 @@
 #include "gxy_internal.h"
 #include "gxy_shade.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -366,7 +367,15 @@ int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLigh
   gen_primary_kernel<<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, n_queue, prim, q);
   const unsigned needed = (npix + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
   const unsigned blocks = std::min<unsigned>(needed, (unsigned)sm_count() * 8u);
-  primary_trace_kernel<8, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q);
+  int ft = 12;  // measured optimum on the 100M-triangle scene (tools/trace_sweep.py, GXY_FETCH_SWEEP)
+  if (const char *e = getenv("GXY_FETCH_P")) ft = atoi(e);
+  switch (ft) {
+    case 4: primary_trace_kernel<4, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q); break;
+    case 8: primary_trace_kernel<8, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q); break;
+    case 16: primary_trace_kernel<16, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q); break;
+    case 24: primary_trace_kernel<24, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q); break;
+    default: primary_trace_kernel<12, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q); break;
+  }
   shade_hits_kernel<<<(npix + 255) / 256, 256, 0, st>>>(P, L, prim, raw, npix, w, reinterpret_cast<float4 *>(fb), hits, q, epsilon);
   GXY_CUDA(cudaGetLastError());
   return 0;
@@ -378,8 +387,17 @@ int launch_fused_secondary(const SceneParams &P, const DevLights &L, int w, int 
   if (ensure_ao_tables()) return 1;
   const long long needed = (max_rays + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
   const unsigned blocks = (unsigned)std::min<long long>(needed, (long long)sm_count() * 8);
-  fused_secondary_kernel<8, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, L, w, h, nsec, reinterpret_cast<float4 *>(fb), hits, spill,
-                                                                     spill_cap, q, epsilon, anyhit ? 1 : 0);
+  int ft = 12;
+  if (const char *e = getenv("GXY_FETCH_S")) ft = atoi(e);
+#define GXY_LAUNCH_S(T) fused_secondary_kernel<T, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, L, w, h, nsec, reinterpret_cast<float4 *>(fb), hits, spill, spill_cap, q, epsilon, anyhit ? 1 : 0)
+  switch (ft) {
+    case 4: GXY_LAUNCH_S(4); break;
+    case 8: GXY_LAUNCH_S(8); break;
+    case 16: GXY_LAUNCH_S(16); break;
+    case 24: GXY_LAUNCH_S(24); break;
+    default: GXY_LAUNCH_S(12); break;
+  }
+#undef GXY_LAUNCH_S
   GXY_CUDA(cudaGetLastError());
   return 0;
 }

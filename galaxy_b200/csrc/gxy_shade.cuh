@@ -60,8 +60,10 @@ __device__ __forceinline__ bool setup_ray_values(const SceneParams &P, int i, bo
   if (dir.y == 0.f) dir.y = 1e-6f;
   if (dir.z == 0.f) dir.z = 1e-6f;
   float tEntry, tExitVolume;
+  float3 rcp;
   {
     const float rx = 1.0f / dir.x, ry = 1.0f / dir.y, rz = 1.0f / dir.z;
+    rcp = f3(rx, ry, rz);
     const float mnx = (P.lmin.x - org.x) * rx, mny = (P.lmin.y - org.y) * ry, mnz = (P.lmin.z - org.z) * rz;
     const float mxx = (P.lmax.x - org.x) * rx, mxy = (P.lmax.y - org.y) * ry, mxz = (P.lmax.z - org.z) * rz;
     tEntry = fmaxf(fminf(mnx, mxx), fmaxf(fminf(mny, mxy), fminf(mnz, mxz)));
@@ -70,7 +72,7 @@ __device__ __forceinline__ bool setup_ray_values(const SceneParams &P, int i, bo
   if (tEntry < ray_t0) tEntry = ray_t0;  // :412-413
   else if (tEntry > ray_t0) ray_t0 = tEntry;
   ray_t = fminf(ray_t, tExitVolume);  // :418
-  ray_ctx_init(rc, org, dir, ray_t0, ray_t);
+  ray_ctx_init(rc, org, dir, ray_t0, ray_t, &rcp);
   trav_init(st, rc);
   pr.ray = i;
   pr.tExit = tExitVolume;

@@ -106,12 +106,18 @@ struct TravState {
 #endif
 };
 
-__device__ __forceinline__ void ray_ctx_init(RayCtx &rc, float3 org, float3 dir, float tnear, float tfar) {
+// rcp: 1.0f/dir per component if the caller has it already (the box clip of TraceRays computes it), else NULL
+__device__ __forceinline__ void ray_ctx_init(RayCtx &rc, float3 org, float3 dir, float tnear, float tfar, const float3 *rcp = nullptr) {
   rc.org = org; rc.dir = dir; rc.tnear = tnear; rc.tfar = tfar;
-  const float gx = fabsf(dir.x) > 1e-30f ? dir.x : copysignf(1e-30f, dir.x);
-  const float gy = fabsf(dir.y) > 1e-30f ? dir.y : copysignf(1e-30f, dir.y);
-  const float gz = fabsf(dir.z) > 1e-30f ? dir.z : copysignf(1e-30f, dir.z);
-  rc.idx = 1.0f / gx; rc.idy = 1.0f / gy; rc.idz = 1.0f / gz;
+  const bool sx = fabsf(dir.x) > 1e-30f, sy = fabsf(dir.y) > 1e-30f, sz = fabsf(dir.z) > 1e-30f;
+  if (rcp && sx && sy && sz) {
+    rc.idx = rcp->x; rc.idy = rcp->y; rc.idz = rcp->z;
+  } else {
+    const float gx = sx ? dir.x : copysignf(1e-30f, dir.x);
+    const float gy = sy ? dir.y : copysignf(1e-30f, dir.y);
+    const float gz = sz ? dir.z : copysignf(1e-30f, dir.z);
+    rc.idx = 1.0f / gx; rc.idy = 1.0f / gy; rc.idz = 1.0f / gz;
+  }
   // octant from the sign of the reciprocal actually used, so that near/far plane selection and
   // child order always agree with the slab arithmetic (also for -0.0 components)
   const unsigned rs = (rc.idx < 0.f ? 1u : 0u) | (rc.idy < 0.f ? 2u : 0u) | (rc.idz < 0.f ? 4u : 0u);

@@ -89,6 +89,7 @@ typedef struct {
   float     trace_ms;         /* sum of the trace-kernel launch durations (CUDA events)       */
   long long nodes_visited;    /* BVH nodes / primitives tested by the trace kernel; 0 unless  */
   long long prims_tested;     /* the library was compiled with -DGXY_TRAV_COUNTERS            */
+  long long volume_samples;   /* trilinear volume samples taken by the march (SampleVolumes x volumes) */
 } gxy_stats;
 
 /* ---- library ---------------------------------------------------------------------------- */

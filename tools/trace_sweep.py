@@ -24,7 +24,11 @@ part = scenes.build_partitions(gpu, vis, {"mesh": ds}, 1, only_rank=0, ctx=ctx)[
 print("scene", len(ds.indices), "tris", part.build_info(), "setup %.1fs" % (time.time() - t0), flush=True)
 del ds
 ref_img = None
-for v in variants:
+fetch = [(int(a), int(b)) for a, b in (x.split(",") for x in os.environ.get("GXY_FETCH_SWEEP", "").split(";") if x)] or [None]
+for v in [(v, f) for v in variants for f in fetch]:
+    v, f = v
+    if f:
+        os.environ["GXY_FETCH_P"], os.environ["GXY_FETCH_S"] = str(f[0]), str(f[1])
     if v == "old":
         os.environ["GXY_TRACE_PERSISTENT"] = "0"
     else:
@@ -40,7 +44,7 @@ for v in variants:
     if ref_img is None:
         ref_img = img
     rays = st["primary_rays"] + st["shadow_rays"] + st["ao_rays"]
-    print(json.dumps({"variant": v, "ms": round(float(np.median(ms)), 4), "trace_ms": round(float(np.median(tr)), 4), "min_ms": round(float(np.min(ms)), 4),
+    print(json.dumps({"variant": v, "fetch": f, "ms": round(float(np.median(ms)), 4), "trace_ms": round(float(np.median(tr)), 4), "min_ms": round(float(np.min(ms)), 4),
                       "Mrays/s": round(rays / np.median(ms) / 1e3, 1), "rays": rays, "nodes/ray": round(st["nodes_visited"] / max(1, st["traced_rays"]), 2),
                       "prims/ray": round(st["prims_tested"] / max(1, st["traced_rays"]), 2), "img_equal_first": bool(np.array_equal(img, ref_img)),
                       "img_maxdiff": int(np.abs(img.astype(int) - ref_img.astype(int)).max())}), flush=True)
