@@ -107,11 +107,23 @@ static int load_nccl() {
   } while (0)
 
 // ------------------------------------------------------------------------------------------------
+// one rank's peer arena and the arenas of all other ranks mapped through CUDA IPC (PeerTable, gxy_internal.h)
+struct PeerArena {
+  char *base = nullptr;
+  size_t bytes = 0;
+  PeerTable T;
+  void *opened[GXY_MAX_RANKS];
+  unsigned epoch = 0;
+  bool disabled = false;  // IPC mapping failed on some rank (or GXY_PEER=0): the NCCL exchange is used instead
+  PeerArena() { memset(&T, 0, sizeof T); memset(opened, 0, sizeof opened); }
+};
+
 struct gxy_context {
   int device = 0;
   cudaStream_t stream = nullptr;
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  PeerArena arena;
 };
 
 struct gxy_volume {
@@ -216,6 +228,7 @@ struct gxy_vis {
   Scratch<int> hit_index, block_sums, small;  // small: nhit, counts, offsets, cursor ...
   Scratch<unsigned long long> counters;       // [0] terminated [1] samples
   Scratch<float> fb, fb_tmp;
+  float *fb_result = nullptr;  // where the last frame's image is (fb.p, or a buffer inside the peer arena)
   Scratch<unsigned char> rgba8;
   Scratch<float> io_f;
   Scratch<int> io_i;
@@ -794,6 +807,206 @@ int gxy_intersect(gxy_vis *v, int n, const float *org3, const float *dir3, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// Peer arenas (one process per GPU).  Collective over the communicator: every rank must call with the same
+// sizes (they follow from w, h and the lighting, which are the same everywhere).  NCCL is only the bootstrap
+// here: it carries the 64-byte IPC handles and the "did it work everywhere" vote.
+static void peer_arena_unmap(PeerArena &A, int rank) {
+  for (int r = 0; r < GXY_MAX_RANKS; r++)
+    if (A.opened[r] && r != rank) { cudaIpcCloseMemHandle(A.opened[r]); A.opened[r] = nullptr; }
+}
+
+static int peer_allgather_bytes(gxy_context *c, const void *mine, void *all, size_t bytes_each, Scratch<unsigned char> &dev) {
+  const size_t n = (size_t)c->nranks;
+  if (dev.reserve(bytes_each * (n + 1))) return 1;
+  GXY_CUDA(cudaMemcpyAsync(dev.p, mine, bytes_each, cudaMemcpyHostToDevice, c->stream));
+  GXY_NCCL(g_nccl.AllGather(dev.p, dev.p + bytes_each, bytes_each, ncclChar, c->comm, c->stream));
+  GXY_CUDA(cudaMemcpyAsync(all, dev.p + bytes_each, bytes_each * n, cudaMemcpyDeviceToHost, c->stream));
+  GXY_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static int ensure_peer_arena(gxy_context *c, unsigned npix, unsigned inbox_cap) {
+  PeerArena &A = c->arena;
+  if (A.disabled) return 0;
+  if (A.base && A.T.npix >= npix && A.T.inbox_cap >= inbox_cap) return 0;
+  GXY_CHECK(c->nranks <= GXY_MAX_RANKS, "peer arenas support up to %d ranks", GXY_MAX_RANKS);
+  Scratch<unsigned char> dev;
+  // 1. nobody may still have the old arenas mapped when they are freed
+  peer_arena_unmap(A, c->rank);
+  char token = 1, tokens[GXY_MAX_RANKS];
+  if (peer_allgather_bytes(c, &token, tokens, 1, dev)) return 1;
+  if (A.base) { cudaFree(A.base); A.base = nullptr; }
+  // 2. allocate and clear the new arena
+  PeerTable T;
+  memset(&T, 0, sizeof T);
+  T.rank = c->rank; T.nranks = c->nranks; T.inbox_cap = inbox_cap; T.npix = npix;
+  auto align = [](unsigned long long x) { return (x + 255ull) & ~255ull; };
+  T.off_fb = sizeof(PeerCtrl);
+  T.off_final = align(T.off_fb + (unsigned long long)npix * 16ull);
+  T.off_inbox[0] = align(T.off_final + (unsigned long long)npix * 16ull);
+  T.off_inbox[1] = align(T.off_inbox[0] + (unsigned long long)inbox_cap * 64ull);
+  const size_t bytes = (size_t)align(T.off_inbox[1] + (unsigned long long)inbox_cap * 64ull);
+  int ok = 1;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof mine);
+  if (cudaMalloc(&A.base, bytes) != cudaSuccess) { cudaGetLastError(); A.base = nullptr; ok = 0; }
+  if (ok && cudaMemsetAsync(A.base, 0, sizeof(PeerCtrl), c->stream) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine, A.base) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  // 3. exchange handles (the all-gather also orders every rank's memset before any peer access) and map
+  struct Msg { cudaIpcMemHandle_t h; int ok; int pad[15]; } msg, all[GXY_MAX_RANKS];
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memset(&msg, 0, sizeof msg);
+  msg.h = mine; msg.ok = ok;
+  if (peer_allgather_bytes(c, &msg, all, sizeof(Msg), dev)) return 1;
+  for (int r = 0; r < c->nranks; r++) ok = ok && all[r].ok;
+  if (ok) {
+    for (int r = 0; r < c->nranks && ok; r++) {
+      if (r == c->rank) { T.base[r] = A.base; continue; }
+      void *ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        fprintf(stderr, "[galaxy_b200 rank %d] cudaIpcOpenMemHandle(rank %d) failed: %s\n", c->rank, r, cudaGetErrorString(cudaGetLastError()));
+        ok = 0;
+        break;
+      }
+      A.opened[r] = ptr;
+      T.base[r] = (char *)ptr;
+    }
+  }
+  // 4. all or nothing
+  int vote = ok, votes[GXY_MAX_RANKS];
+  if (peer_allgather_bytes(c, &vote, votes, sizeof(int), dev)) return 1;
+  for (int r = 0; r < c->nranks; r++) ok = ok && votes[r];
+  dev.release();
+  if (!ok) {
+    peer_arena_unmap(A, c->rank);
+    if (A.base) cudaFree(A.base);
+    A.base = nullptr;
+    A.disabled = true;
+    if (c->rank == 0) fprintf(stderr, "[galaxy_b200] peer arenas unavailable (CUDA IPC); using the NCCL ray exchange\n");
+    return 0;
+  }
+  A.T = T;
+  A.bytes = bytes;
+  A.epoch = 0;
+  return 0;
+}
+
+// The frame on one rank of a multi-process run, geometry-only Visualization: a fixed schedule of kernel
+// launches with no host round trip until the end of the frame.
+//   wave 0     generate -> trace primaries -> shade hits -> AO/shadow rays; rays that leave go to peer inboxes[0]
+//   wave k>=1  trace inbox[(k-1)&1] -> shade the new hits -> their AO/shadow rays; leavers go to inboxes[k&1]
+// each wave ends with the flag barrier.  A ray crosses at most H = sum(grid_i - 1) partition faces and so does
+// each of its secondaries: 2H waves after wave 0 suffice for a regular grid; the global in-flight count the last
+// barrier leaves behind is checked anyway and further waves run until it is zero.
+static int render_peer(gxy_vis *v, const DevCamera &C, const DevLights &L, const gxy_lighting &lights, int w, int h, float epsilon,
+                       int n_sec_per_hit, gxy_stats *stats) {
+  gxy_context *c = v->ctx;
+  PeerArena &A = c->arena;
+  const PeerTable &T = A.T;
+  cudaStream_t st = c->stream;
+  const int npix = w * h;
+  gxy_stats S;
+  memset(&S, 0, sizeof S);
+  if (v->hits.reserve(npix, false, st) || v->fq.reserve(sizeof(FusedQueues) / 8) || v->rawhits.reserve((size_t)6 * npix) ||
+      v->next.reserve(npix, false, st) || v->cur.reserve(64, false, st) || v->counters.reserve(4))
+    return 1;
+  float *fb = reinterpret_cast<float *>(A.base + T.off_fb);
+  FusedQueues *q = reinterpret_cast<FusedQueues *>(v->fq.p);
+  v->fb_w = w; v->fb_h = h;
+  v->fb_result = c->rank == 0 ? reinterpret_cast<float *>(A.base + T.off_final) : fb;
+  cudaEvent_t ev0, ev1;
+  GXY_CUDA(cudaEventCreate(&ev0));
+  GXY_CUDA(cudaEventCreate(&ev1));
+  GXY_CUDA(cudaEventRecord(ev0, st));
+  GXY_CUDA(cudaMemsetAsync(fb, 0, sizeof(float) * 4 * npix, st));
+  GXY_CUDA(cudaMemsetAsync(q, 0, sizeof(FusedQueues), st));
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_events;
+  auto ev_begin = [&]() -> int {
+    cudaEvent_t ta, tb;
+    GXY_CUDA(cudaEventCreate(&ta));
+    GXY_CUDA(cudaEventCreate(&tb));
+    GXY_CUDA(cudaEventRecord(ta, st));
+    trace_events.push_back(std::make_pair(ta, tb));
+    return 0;
+  };
+  auto ev_end = [&]() -> int {
+    GXY_CUDA(cudaEventRecord(trace_events.back().second, st));
+    return 0;
+  };
+  // ---- wave 0
+  if (ev_begin()) return 1;
+  if (launch_fused_primary(v->P, C, L, w, h, fb, v->next.v, v->rawhits.p, v->hits.v, v->cur.v, 0u, q, epsilon, &T, st)) return 1;
+  if (ev_end()) return 1;
+  S.kernel_launches += 3;
+  if (n_sec_per_hit > 0) {
+    if (ev_begin()) return 1;
+    if (launch_fused_secondary(v->P, L, w, h, n_sec_per_hit, (long long)npix * n_sec_per_hit, fb, v->hits.v, v->cur.v, 0u, q, epsilon,
+                               !v->has_dvr, &T, 0, st))
+      return 1;
+    if (ev_end()) return 1;
+    S.kernel_launches += 1;
+  }
+  if (launch_wave_epilogue(T, q, ++A.epoch, -1, v->d_error, st)) return 1;
+  S.kernel_launches += 1;
+  S.waves = 1;
+  // ---- waves 1..: the bound first, then as long as anything is in flight anywhere
+  int f[3];
+  gxy_factor(c->nranks, f);
+  const int bound = 2 * ((f[0] - 1) + (f[1] - 1) + (f[2] - 1));
+  int k = 0;
+  FusedQueues hq;
+  while (true) {
+    const int batch = k == 0 ? bound : 1;
+    for (int b = 0; b < batch; b++) {
+      k++;
+      const int parity_in = (k - 1) & 1;
+      if (ev_begin()) return 1;
+      if (launch_inbox_wave(v->P, L, T, parity_in, w, h, fb, v->rawhits.p, (unsigned)npix, v->hits.v, q, epsilon, !v->has_dvr, st)) return 1;
+      if (n_sec_per_hit > 0 &&
+          launch_fused_secondary(v->P, L, w, h, n_sec_per_hit, (long long)npix * n_sec_per_hit, fb, v->hits.v, v->cur.v, 0u, q, epsilon,
+                                 !v->has_dvr, &T, k & 1, st))
+        return 1;
+      if (ev_end()) return 1;
+      if (launch_wave_epilogue(T, q, ++A.epoch, parity_in, v->d_error, st)) return 1;
+      S.kernel_launches += 3 + (n_sec_per_hit > 0 ? 1 : 0);
+      S.waves++;
+    }
+    GXY_CUDA(cudaMemcpyAsync(&hq, q, sizeof hq, cudaMemcpyDeviceToHost, st));
+    GXY_CUDA(cudaStreamSynchronize(st));
+    if (check_error_flag(v)) return 1;
+    if (hq.global_pending == 0u) break;
+    GXY_CHECK(k < 4096, "peer wave loop does not terminate (%u rays in flight)", hq.global_pending);
+  }
+  // ---- framebuffer: every rank sums its slice of all partial images into the owner's final image
+  if (launch_fb_gather(T, st)) return 1;
+  if (launch_wave_epilogue(T, q, ++A.epoch, -1, v->d_error, st)) return 1;
+  S.kernel_launches += 2;
+  GXY_CUDA(cudaEventRecord(ev1, st));
+  GXY_CUDA(cudaEventSynchronize(ev1));
+  cudaEventElapsedTime(&S.device_ms, ev0, ev1);
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  for (auto &e : trace_events) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.first, e.second);
+    S.trace_ms += ms;
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  if (check_error_flag(v)) return 1;
+  S.primary_rays = (long long)hq.n_primary32;
+  S.ao_rays = (long long)hq.n_hits * lights.n_ao;
+  S.shadow_rays = (long long)hq.n_hits * (lights.shadows ? lights.n_lights : 0);
+  S.forwarded_rays = (long long)hq.n_spill;
+  S.terminated_rays = (long long)hq.n_terminated;
+  S.traced_rays = (long long)hq.n_primary32 + (long long)hq.n_hits * n_sec_per_hit + (long long)hq.n_inbox;
+  S.nodes_visited = (long long)hq.nodes;
+  S.prims_tested = (long long)hq.prims;
+  if (stats) *stats = S;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Frame-level wave loop.
 //
 // A wave on one partition: trace the current list (mixed types) -> scan surface hits -> spawn AO /
@@ -834,8 +1047,22 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
   // Geometry-only Visualizations take the fused path for the rays born in this frame (gxy_fused.cu);
   // only rays that cross into a neighbour partition come back as lists ("spill") for the wave loop.
   bool fused = true;
-  for (int p = 0; p < nparts; p++) fused = fused && parts[p]->P.n_volvis == 0 && parts[p]->P.n_prims > 0;
+  // (decided from the operator list, which is the same on every rank, not from the clipped primitive count)
+  for (int p = 0; p < nparts; p++) fused = fused && parts[p]->P.n_volvis == 0 && !parts[p]->geoms.empty();
   if (const char *e = getenv("GXY_FUSED")) fused = fused && atoi(e) != 0;
+  if (multi_proc && fused) {
+    // one process per GPU, geometry only: rays and pixels move through peer arenas, not through NCCL
+    if (const char *e = getenv("GXY_PEER"))
+      if (atoi(e) == 0) ctx0->arena.disabled = true;
+    const unsigned long long cap = (unsigned long long)npix * (unsigned long long)(1 + n_sec_per_hit);
+    GXY_CHECK(cap < (1ull << 31), "peer inbox too large (%llu records)", cap);
+    if (ensure_peer_arena(ctx0, (unsigned)npix, (unsigned)cap)) return 1;
+    if (!ctx0->arena.disabled) {
+      cudaEventDestroy(ev0);
+      cudaEventDestroy(ev1);
+      return render_peer(parts[0], C, L, lights, w, h, epsilon, n_sec_per_hit, stats);
+    }
+  }
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_events;
   for (int p = 0; p < nparts; p++) {
     gxy_vis *v = parts[p];
@@ -845,11 +1072,12 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
         v->fb.reserve((size_t)npix * 4))
       return 1;
     v->fb_w = w; v->fb_h = h;
+    v->fb_result = v->fb.p;
     GXY_CUDA(cudaMemsetAsync(v->fb.p, 0, sizeof(float) * 4 * npix, st));
     GXY_CUDA(cudaMemsetAsync(v->counters.p, 0, sizeof(unsigned long long) * 4, st));
   }
   if (fused) {
-    static_assert(sizeof(FusedQueues) == 48, "FusedQueues layout");
+    static_assert(sizeof(FusedQueues) == 80, "FusedQueues layout");
     std::vector<FusedQueues> fq(nparts);
     std::vector<bool> can_spill(nparts, false);
     // ---- primary rays: generate -> trace -> light -> framebuffer, hit records for the secondaries
@@ -867,7 +1095,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       GXY_CUDA(cudaEventCreate(&tb));
       GXY_CUDA(cudaEventRecord(ta, st));
       if (launch_fused_primary(v->P, C, L, w, h, v->fb.p, v->next.v, v->rawhits.p, v->hits.v, v->cur.v,
-                               can_spill[p] ? (unsigned)v->cur.cap : 0u, reinterpret_cast<FusedQueues *>(v->fq.p), epsilon, st))
+                               can_spill[p] ? (unsigned)v->cur.cap : 0u, reinterpret_cast<FusedQueues *>(v->fq.p), epsilon, nullptr, st))
         return 1;
       GXY_CUDA(cudaEventRecord(tb, st));
       trace_events.push_back(std::make_pair(ta, tb));
@@ -894,7 +1122,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       GXY_CUDA(cudaEventCreate(&tb));
       GXY_CUDA(cudaEventRecord(ta, st));
       if (launch_fused_secondary(v->P, L, w, h, n_sec_per_hit, max_rays, v->fb.p, v->hits.v, v->cur.v, can_spill[p] ? (unsigned)v->cur.cap : 0u,
-                                 reinterpret_cast<FusedQueues *>(v->fq.p), epsilon, !v->has_dvr, st))
+                                 reinterpret_cast<FusedQueues *>(v->fq.p), epsilon, !v->has_dvr, nullptr, 0, st))
         return 1;
       GXY_CUDA(cudaEventRecord(tb, st));
       trace_events.push_back(std::make_pair(ta, tb));
@@ -1169,18 +1397,18 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
 
 int gxy_frame_download_rgba32f(gxy_vis *v, float *fb) {
   if (check_vis(v)) return 1;
-  GXY_CHECK(v->fb_w > 0 && fb, "no frame rendered yet");
-  GXY_CUDA(cudaMemcpyAsync(fb, v->fb.p, sizeof(float) * 4 * (size_t)v->fb_w * v->fb_h, cudaMemcpyDeviceToHost, v->ctx->stream));
+  GXY_CHECK(v->fb_w > 0 && v->fb_result && fb, "no frame rendered yet");
+  GXY_CUDA(cudaMemcpyAsync(fb, v->fb_result, sizeof(float) * 4 * (size_t)v->fb_w * v->fb_h, cudaMemcpyDeviceToHost, v->ctx->stream));
   GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
   return 0;
 }
 
 int gxy_frame_download_rgba8(gxy_vis *v, unsigned char *rgba) {
   if (check_vis(v)) return 1;
-  GXY_CHECK(v->fb_w > 0 && rgba, "no frame rendered yet");
+  GXY_CHECK(v->fb_w > 0 && v->fb_result && rgba, "no frame rendered yet");
   const size_t n = (size_t)v->fb_w * v->fb_h * 4;
   if (v->rgba8.reserve(n)) return 1;
-  if (launch_tonemap(v->fb.p, v->fb_w, v->fb_h, v->rgba8.p, v->ctx->stream)) return 1;
+  if (launch_tonemap(v->fb_result, v->fb_w, v->fb_h, v->rgba8.p, v->ctx->stream)) return 1;
   GXY_CUDA(cudaMemcpyAsync(rgba, v->rgba8.p, n, cudaMemcpyDeviceToHost, v->ctx->stream));
   GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
   return 0;
@@ -1221,6 +1449,10 @@ int gxy_comm_init(gxy_context *c, int rank, int nranks, const unsigned char id[1
 int gxy_comm_destroy(gxy_context *c) {
   if (c->comm) {
     if (use_device(c)) return 1;
+    cudaStreamSynchronize(c->stream);
+    peer_arena_unmap(c->arena, c->rank);
+    if (c->arena.base) cudaFree(c->arena.base);
+    c->arena = PeerArena();
     GXY_NCCL(g_nccl.CommDestroy(c->comm));
     c->comm = nullptr;
     c->rank = 0;

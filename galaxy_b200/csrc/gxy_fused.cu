@@ -55,6 +55,41 @@ __device__ __forceinline__ unsigned group_append(unsigned group, unsigned lane, 
   return base + (unsigned)__popc(m & ((1u << lane) - 1u));
 }
 
+// ---- peer inboxes (PeerTable, gxy_internal.h) -----------------------------------------------------
+__device__ __forceinline__ PeerCtrl *peer_ctrl(const PeerTable &T, int r) { return reinterpret_cast<PeerCtrl *>(T.base[r]); }
+__device__ __forceinline__ float4 *peer_inbox(const PeerTable &T, int r, int parity) {
+  return reinterpret_cast<float4 *>(T.base[r] + T.off_inbox[parity]);
+}
+// Append one 64-byte record per flagged lane to the inbox[parity] of its destination rank.  All lanes of
+// `group` must call (converged).  Lanes bound for the same rank share one system-scope atomicAdd on that
+// rank's counter (an NVLink round trip) and write neighbouring records.
+__device__ __forceinline__ void peer_push(const PeerTable &T, int parity, unsigned group, unsigned lane, bool flag, int dest, float3 org,
+                                          float3 dir, float r, float g, float b, float o, float t, float tMax, int x, int y, int type, int term,
+                                          int *error_flag) {
+  if (dest < 0 || dest >= T.nranks) flag = false;
+  unsigned todo = __ballot_sync(group, flag);
+  const unsigned lt = (1u << lane) - 1u;
+  while (todo != 0u) {
+    const int leader = __ffs((int)todo) - 1;
+    const int d = __shfl_sync(group, dest, leader);
+    const unsigned same = __ballot_sync(group, flag && dest == d);
+    unsigned base = 0u;
+    if ((int)lane == leader) base = atomicAdd_system(&peer_ctrl(T, d)->inbox_count[parity], (unsigned)__popc(same));
+    base = __shfl_sync(group, base, leader);
+    if (flag && dest == d) {
+      const unsigned pos = base + (unsigned)__popc(same & lt);
+      if (pos < T.inbox_cap) {
+        float4 *rec = peer_inbox(T, d, parity) + 4 * (size_t)pos;
+        rec[0] = make_float4(org.x, org.y, org.z, dir.x);
+        rec[1] = make_float4(dir.y, dir.z, t, tMax);
+        rec[2] = make_float4(r, g, b, o);
+        rec[3] = make_float4(__int_as_float(x), __int_as_float(y), __int_as_float(type), __int_as_float(term));
+      } else *error_flag = 3;
+    }
+    todo &= ~same;
+  }
+}
+
 // Camera::SpawnRays for the whole window (Camera.cpp:379-493): one thread per pixel in tile order,
 // kept rays appended (unordered) to `out` (columns ox..dz x y; t = 0, tMax = FLT_MAX, type PRIMARY implied)
 __global__ void __launch_bounds__(256)
@@ -80,10 +115,10 @@ __global__ void __launch_bounds__(256)
 // Trace of the generated primaries (persistent warps, dynamic fetch, cooperative primitive tests).
 // A surface hit leaves a 6-word raw record (ray, t, u, v, ids, record) for shade_hits_kernel; a miss is
 // classified here: TERMINATED (adds nothing: its colour is 0) or spilled towards a neighbour.
-template <int FETCH_T, int MIN_BLOCKS>
+template <int FETCH_T, int MIN_BLOCKS, bool PEER>
 __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
     primary_trace_kernel(const __grid_constant__ SceneParams P, Rays R, unsigned *__restrict__ raw, unsigned raw_stride, Rays spill,
-                         unsigned spill_cap, FusedQueues *__restrict__ q) {
+                         unsigned spill_cap, FusedQueues *__restrict__ q, const __grid_constant__ PeerTable T) {
   __shared__ uint2 stack[GXY_STACK_SMEM * GXY_TRACE_THREADS];
   __shared__ unsigned char owner_of[GXY_TRACE_THREADS / 32][8];
   uint2 lstack[GXY_STACK_LOCAL];
@@ -141,7 +176,12 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
           raw[hp + 4u * raw_stride] = st.best_key;
           raw[hp + 5u * raw_stride] = st.best_rec;
         }
-        if (do_spill) {
+        if (PEER) {
+          float3 d0 = f3(0.f, 0.f, 0.f);
+          int px = 0, py = 0;
+          if (do_spill) { d0 = f3(R.dx[pr.ray], R.dy[pr.ray], R.dz[pr.ray]); px = R.x[pr.ray]; py = R.y[pr.ray]; }
+          peer_push(T, 0, m_idle, lane, do_spill, cls, rc.org, d0, 0.f, 0.f, 0.f, 0.f, rc.tfar, FLT_MAX, px, py, RAY_PRIMARY, term, P.error_flag);
+        } else if (do_spill) {
           const unsigned sp = sbase + (unsigned)__popc(sm & lt_mask);
           if (sp < spill_cap)
             write_spill(spill, sp, rc.org, f3(R.dx[pr.ray], R.dy[pr.ray], R.dz[pr.ray]), 0.f, 0.f, 0.f, 0.f, rc.tfar, FLT_MAX, R.x[pr.ray],
@@ -166,19 +206,32 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
   }
 }
 
-// postIntersect + ambient/diffuse lighting + framebuffer add for every surface hit, one thread per hit
-// (full SIMD efficiency, unlike a finish inside the persistent kernel), and the record the secondary
-// kernel generates AO/shadow rays from
+// postIntersect + ambient/diffuse lighting + framebuffer add for the surface hits [q->hits_done, q->n_hits), one
+// thread per hit (full SIMD efficiency, unlike a finish inside the persistent kernel), and the record the
+// secondary kernel generates AO/shadow rays from.  The traced ray is read from the primary list (AOS = false)
+// or from the 64-byte records of an inbox (AOS = true; the ray's own colour is 0 on this path).
+template <bool AOS>
 __global__ void __launch_bounds__(256)
-    shade_hits_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevLights L, Rays R, const unsigned *__restrict__ raw,
-                      unsigned raw_stride, int w, float4 *__restrict__ fb, Rays hits, FusedQueues *__restrict__ q, float epsilon) {
-  const unsigned hidx = blockIdx.x * blockDim.x + threadIdx.x;
-  bool terminated = false;
-  if (hidx < q->n_hits) {
+    shade_hits_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevLights L, Rays R, const float4 *__restrict__ inbox,
+                      const unsigned *__restrict__ raw, unsigned raw_stride, int w, float4 *__restrict__ fb, Rays hits,
+                      FusedQueues *__restrict__ q, float epsilon) {
+  const unsigned n_hits = q->n_hits;
+  unsigned n_term = 0u;
+  for (unsigned hidx = q->hits_done + blockIdx.x * blockDim.x + threadIdx.x; hidx < n_hits; hidx += gridDim.x * blockDim.x) {
     const unsigned i = raw[hidx];
     RayCtx rc;
-    rc.org = f3(R.ox[i], R.oy[i], R.oz[i]);
-    const float3 dir0 = f3(R.dx[i], R.dy[i], R.dz[i]);
+    float3 dir0;
+    int px, py;
+    if (AOS) {
+      const float4 a = inbox[4 * (size_t)i], b = inbox[4 * (size_t)i + 1], d = inbox[4 * (size_t)i + 3];
+      rc.org = f3(a.x, a.y, a.z);
+      dir0 = f3(a.w, b.x, b.y);
+      px = __float_as_int(d.x); py = __float_as_int(d.y);
+    } else {
+      rc.org = f3(R.ox[i], R.oy[i], R.oz[i]);
+      dir0 = f3(R.dx[i], R.dy[i], R.dz[i]);
+      px = R.x[i]; py = R.y[i];
+    }
     rc.dir = dir0;
     if (rc.dir.x == 0.f) rc.dir.x = 1e-6f;  // TraceRays.ispc:377-379
     if (rc.dir.y == 0.f) rc.dir.y = 1e-6f;
@@ -198,12 +251,12 @@ __global__ void __launch_bounds__(256)
     if (opacity > 0.999f) term |= RAY_OPAQUE;
     HitPoint hp;
     hp.ox = rc.org.x; hp.oy = rc.org.y; hp.oz = rc.org.z; hp.dx = dir0.x; hp.dy = dir0.y; hp.dz = dir0.z; hp.t = st.best_t;
-    hp.sn = Ns; hp.sr = col.x; hp.sg = col.y; hp.sb = col.z; hp.o = 0.f; hp.px = R.x[i]; hp.py = R.y[i];
+    hp.sn = Ns; hp.sr = col.x; hp.sg = col.y; hp.sb = col.z; hp.o = 0.f; hp.px = px; hp.py = py;
     float r = 0.f, g = 0.f, b = 0.f, o = 0.f;
     light_primary(L, hp, r, g, b, o);
     const int cls = classify_values(P, RAY_PRIMARY, term, hp.ox, hp.oy, hp.oz, hp.dx, hp.dy, hp.dz);
     if (cls == CLS_TERMINATED) {
-      terminated = true;
+      n_term++;
       atomicAdd(fb + ((size_t)hp.py * w + hp.px), make_float4(r, g, b, o));
     }
     hits.ox[hidx] = hp.ox; hits.oy[hidx] = hp.oy; hits.oz[hidx] = hp.oz;
@@ -221,8 +274,8 @@ __global__ void __launch_bounds__(256)
     hits.sample[hidx] = b0.x; hits.so[hidx] = b0.y; hits.tMax[hidx] = b0.z;
     hits.type[hidx] = __float_as_int(b1.x); hits.term[hidx] = __float_as_int(b1.y); hits.classification[hidx] = __float_as_int(b1.z);
   }
-  const unsigned tm = __ballot_sync(FULLMASK, terminated);
-  if (tm != 0u && (threadIdx.x & 31u) == 0u) atomicAdd(&q->n_terminated, (unsigned long long)__popc(tm));
+  for (int off = 16; off > 0; off >>= 1) n_term += __shfl_down_sync(FULLMASK, n_term, off);
+  if (n_term != 0u && (threadIdx.x & 31u) == 0u) atomicAdd(&q->n_terminated, (unsigned long long)n_term);
 }
 
 // queue order of the secondary rays: all AO rays (hit-major), then all shadow rays (hit-major), as the
@@ -251,11 +304,11 @@ __device__ __forceinline__ SecRay make_secondary(const DevLights &L, const Rays 
   return make_shadow_ray(L, hp, j - L.n_ao, epsilon, o_lit);
 }
 
-template <int FETCH_T, int MIN_BLOCKS>
+template <int FETCH_T, int MIN_BLOCKS, bool PEER>
 __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
     fused_secondary_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevLights L, int w, int h, int nsec,
                            float4 *__restrict__ fb, Rays hits, Rays spill, unsigned spill_cap, FusedQueues *__restrict__ q, float epsilon,
-                           int anyhit_secondary) {
+                           int anyhit_secondary, const __grid_constant__ PeerTable T, int parity_out) {
   __shared__ uint2 stack[GXY_STACK_SMEM * GXY_TRACE_THREADS];
   __shared__ unsigned char owner_of[GXY_TRACE_THREADS / 32][8];
   __shared__ float ao_tab[3][256];  // divergent indices: shared memory, not the constant cache
@@ -264,7 +317,9 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
   __syncthreads();
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const unsigned n_hits = q->n_hits;
+  const unsigned h0 = q->hits_done;  // hit records [h0, q->n_hits) are this wave's
+  const unsigned n_hits = q->n_hits - h0;
+  if (n_hits == 0u) return;
   const unsigned long long total64 = (unsigned long long)n_hits * (unsigned)nsec;
   const unsigned n_queue = total64 > 0xfffffff0ull ? 0xfffffff0u : (unsigned)total64;
   RayCtx rc;
@@ -292,6 +347,7 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
           if (found || ray_t == pr.tExit || pr.opaque) {
             int hi, j;
             secondary_index((unsigned)pr.ray, n_hits, L.n_ao, nsec - L.n_ao, hi, j);
+            hi += (int)h0;
             s = make_secondary(L, hits, hi, j, epsilon, ao_tab[0], ao_tab[1], ao_tab[2]);
             px = hits.x[hi]; py = hits.y[hi];
             term = (min3f(s.r, s.g, s.b) >= 1.0f) ? RAY_OPAQUE : 0;
@@ -321,7 +377,10 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
         }
         sbase = __shfl_sync(m_idle, sbase, leader);
         fbase = __shfl_sync(m_idle, fbase, leader);
-        if (do_spill) {
+        if (PEER) {
+          peer_push(T, parity_out, m_idle, lane, do_spill, cls, s.org, s.dir, s.r, s.g, s.b, 0.f, ray_t, s.tMax, px, py, s.type, term,
+                    P.error_flag);
+        } else if (do_spill) {
           const unsigned sp = sbase + (unsigned)__popc(sm & lt_mask);
           if (sp < spill_cap) write_spill(spill, sp, s.org, s.dir, s.r, s.g, s.b, 0.f, ray_t, s.tMax, px, py, s.type, term, cls);
           else *P.error_flag = 3;
@@ -333,6 +392,7 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
           if (my < n_queue) {
             int hi, j;
             secondary_index(my, n_hits, L.n_ao, nsec - L.n_ao, hi, j);
+            hi += (int)h0;
             const SecRay sr = make_secondary(L, hits, hi, j, epsilon, ao_tab[0], ao_tab[1], ao_tab[2]);
             trav = setup_ray_values(P, (int)my, false, sr.org, sr.dir, 0.f, sr.tMax, anyhit_secondary, rc, st, pr);
             pr.opaque = min3f(sr.r, sr.g, sr.b) >= 1.0f;
@@ -348,6 +408,189 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Wave >= 1 of the peer path: the rays other ranks wrote into this rank's inbox[parity_in] (PRIMARY rays
+// that found nothing in their first partition, SHADOW/AO rays on their way to the light / out of the AO
+// sphere).  Same persistent-warp traversal; per ray TraceRays_TraceRays restricted to geometry
+// (TraceRays.ispc:377-441, 563-610), then Renderer::Classify (Renderer.cpp:304-454): a PRIMARY hit leaves a
+// raw record for shade_hits_kernel<true>; everything else adds to the framebuffer, is dropped, or is
+// written on into the next partition's inbox[parity_in ^ 1].
+template <int FETCH_T, int MIN_BLOCKS>
+__global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
+    inbox_trace_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ PeerTable T, int parity_in, int w,
+                       float4 *__restrict__ fb, unsigned *__restrict__ raw, unsigned raw_stride, FusedQueues *__restrict__ q,
+                       int anyhit_secondary) {
+  __shared__ uint2 stack[GXY_STACK_SMEM * GXY_TRACE_THREADS];
+  __shared__ unsigned char owner_of[GXY_TRACE_THREADS / 32][8];
+  uint2 lstack[GXY_STACK_LOCAL];
+  const float4 *__restrict__ inbox = peer_inbox(T, T.rank, parity_in);
+  const unsigned n_in = peer_ctrl(T, T.rank)->inbox_count[parity_in];
+  const unsigned n_queue = n_in < T.inbox_cap ? n_in : T.inbox_cap;
+  if (n_queue == 0u) return;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  RayCtx rc;
+  TravState st;
+  PendingRay pr;
+  pr.ray = -1; pr.tExit = 0.f; pr.anyhit = false; pr.opaque = false;
+  st.tg.y = 0u; st.ng.y = 0u;
+  rc.org = f3(0.f, 0.f, 0.f); rc.dir = f3(1.f, 1.f, 1.f); rc.tnear = 0.f; rc.tfar = 0.f;
+  st.best_t = 0.f; st.best_u = 0.f; st.best_v = 0.f; st.best_key = GXY_NO_HIT; st.best_rec = 0u;
+  bool trav = false, exhausted = false;
+  while (true) {
+    const unsigned m_idle = __ballot_sync(FULLMASK, !trav);
+    if (m_idle == FULLMASK || (!exhausted && __popc(m_idle) >= FETCH_T)) {
+      bool ex_local = false;
+      if (!trav) {
+        bool has_hit = false, do_spill = false, terminated = false;
+        float3 d0 = f3(0.f, 0.f, 0.f);
+        float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ray_t = 0.f, tMax = 0.f;
+        int px = 0, py = 0, type = 0, term = 0, cls = CLS_UNDETERMINED;
+        if (pr.ray >= 0) {
+          const float4 a = inbox[4 * (size_t)pr.ray], b = inbox[4 * (size_t)pr.ray + 1], d = inbox[4 * (size_t)pr.ray + 3];
+          col = inbox[4 * (size_t)pr.ray + 2];
+          d0 = f3(a.w, b.x, b.y);
+          tMax = b.w;
+          px = __float_as_int(d.x); py = __float_as_int(d.y); type = __float_as_int(d.z);
+          const bool found = st.best_key != GXY_NO_HIT;
+          ray_t = found ? st.best_t : rc.tfar;
+          term = (min3f(col.x, col.y, col.z) >= 1.0f || col.w > 0.999f) ? RAY_OPAQUE : 0;  // TraceRays.ispc:573
+          if (type == RAY_PRIMARY && found) has_hit = true;  // shaded, lit and classified by shade_hits_kernel
+          else {
+            if (found) term |= RAY_SURFACE | RAY_OPAQUE;  // non-shaded ray on a surface, see trace_kernel
+            else if (ray_t == pr.tExit) term |= RAY_BOUNDARY;
+            else if (ray_t == tMax) term |= RAY_TIMEOUT;
+            cls = classify_values(P, type, term, rc.org.x, rc.org.y, rc.org.z, d0.x, d0.y, d0.z);
+            if (cls == CLS_TERMINATED) {
+              terminated = true;
+              if (col.x != 0.f || col.y != 0.f || col.z != 0.f || col.w != 0.f) atomicAdd(fb + ((size_t)py * w + px), col);
+            } else if (cls >= 0) do_spill = true;
+          }
+#ifdef GXY_TRAV_COUNTERS
+          atomicAdd(&q->nodes, (unsigned long long)st.n_nodes);
+#endif
+        }
+        const unsigned hm = __ballot_sync(m_idle, has_hit), sm = __ballot_sync(m_idle, do_spill), tm = __ballot_sync(m_idle, terminated);
+        const int leader = __ffs((int)m_idle) - 1;
+        const unsigned cnt = (unsigned)__popc(m_idle);
+        unsigned hbase = 0u, fbase = 0u;
+        if ((int)lane == leader) {
+          if (hm) hbase = atomicAdd(&q->n_hits, (unsigned)__popc(hm));
+          if (sm) atomicAdd(&q->n_spill, (unsigned)__popc(sm));
+          if (tm) atomicAdd(&q->n_terminated, (unsigned long long)__popc(tm));
+          if (!exhausted) fbase = atomicAdd(&q->inbox_head, cnt);
+        }
+        hbase = __shfl_sync(m_idle, hbase, leader);
+        fbase = __shfl_sync(m_idle, fbase, leader);
+        if (has_hit) {
+          const unsigned hp = hbase + (unsigned)__popc(hm & lt_mask);
+          if (hp < raw_stride) {
+            raw[hp] = (unsigned)pr.ray;
+            raw[hp + raw_stride] = __float_as_uint(st.best_t);
+            raw[hp + 2u * raw_stride] = __float_as_uint(st.best_u);
+            raw[hp + 3u * raw_stride] = __float_as_uint(st.best_v);
+            raw[hp + 4u * raw_stride] = st.best_key;
+            raw[hp + 5u * raw_stride] = st.best_rec;
+          } else *P.error_flag = 3;
+        }
+        peer_push(T, parity_in ^ 1, m_idle, lane, do_spill, cls, rc.org, d0, col.x, col.y, col.z, col.w, ray_t, tMax, px, py, type, term,
+                  P.error_flag);
+        pr.ray = -1;
+        if (!exhausted) {
+          const unsigned my = fbase + (unsigned)__popc(m_idle & lt_mask);
+          ex_local = fbase + cnt >= n_queue;
+          if (my < n_queue) {
+            const float4 a = inbox[4 * (size_t)my], b = inbox[4 * (size_t)my + 1], d = inbox[4 * (size_t)my + 3];
+            trav = setup_ray_values(P, (int)my, __float_as_int(d.z) == RAY_PRIMARY, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), b.z, b.w,
+                                    anyhit_secondary, rc, st, pr);
+          }
+        }
+      }
+      exhausted = exhausted || __any_sync(FULLMASK, ex_local);
+      if (exhausted && __ballot_sync(FULLMASK, pr.ray >= 0) == 0u) break;
+    }
+    if (trav) node_step<0>(P, rc, st, stack, lstack);
+    coop_prim_passes(P, rc, st, trav, pr.anyhit, owner_of[warp], lane, lt_mask);
+    if (trav) trav = trav_advance(st, stack, lstack);
+  }
+}
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// End of a wave on this rank (one warp): advance the queue bookkeeping, hand the consumed inbox back, then a
+// flag barrier over all ranks -- lane r publishes (rays sent this wave, epoch) in rank r's arena and waits for
+// rank r's flag in its own.  Everything the kernels before this one wrote into peer arenas is complete (stream
+// order) before the flags go out.  After the barrier every rank holds the same global count of rays in flight.
+// Replaces the per-wave count all-gather + host synchronisation of the NCCL path and, over a frame, the
+// reference's busy/idle termination tree (RenderingSet.cpp:289-589).
+__global__ void __launch_bounds__(32)
+    wave_epilogue_kernel(const __grid_constant__ PeerTable T, FusedQueues *__restrict__ q, unsigned epoch, int parity_consumed,
+                         unsigned long long timeout_ns, int *__restrict__ error_flag) {
+  const unsigned lane = threadIdx.x;
+  PeerCtrl *mine = peer_ctrl(T, T.rank);
+  unsigned sent = 0u;
+  if (lane == 0u) {
+    sent = q->n_spill - q->spill_done;
+    q->spill_done = q->n_spill;
+    q->hits_done = q->n_hits;
+    q->sec_head = 0u;
+    q->inbox_head = 0u;
+    if (parity_consumed >= 0) {
+      q->n_inbox += (unsigned long long)mine->inbox_count[parity_consumed];
+      mine->inbox_count[parity_consumed] = 0u;
+    }
+  }
+  sent = __shfl_sync(FULLMASK, sent, 0);
+  __threadfence_system();
+  __syncwarp();
+  unsigned theirs = 0u;
+  if ((int)lane < T.nranks) {
+    PeerCtrl *pc = peer_ctrl(T, (int)lane);
+    *reinterpret_cast<volatile unsigned *>(&pc->pending[epoch & 1u][T.rank]) = sent;
+    __threadfence_system();
+    st_release_sys(&pc->flags[T.rank], epoch);
+    const unsigned long long t0 = global_timer_ns();
+    bool ok = true;
+    while ((int)(ld_acquire_sys(&mine->flags[lane]) - epoch) < 0) {
+      if (global_timer_ns() - t0 > timeout_ns) { ok = false; break; }
+      __nanosleep(200);
+    }
+    if (!ok) *error_flag = 4;
+    theirs = *reinterpret_cast<volatile unsigned *>(&mine->pending[epoch & 1u][lane]);
+  }
+  for (int off = 16; off > 0; off >>= 1) theirs += __shfl_down_sync(FULLMASK, theirs, off);
+  if (lane == 0u) q->global_pending = theirs;
+}
+
+// Rendering::AddLocalPixels over all ranks (Rendering.cpp:125-153) for this rank's slice of the image: the sum of
+// every rank's partial framebuffer (peer loads over NVLink, rank order) goes to the image owner's final buffer.
+__global__ void __launch_bounds__(256) fb_gather_kernel(const __grid_constant__ PeerTable T) {
+  const unsigned per = (T.npix + (unsigned)T.nranks - 1u) / (unsigned)T.nranks;
+  const unsigned lo = per * (unsigned)T.rank, hi = min(T.npix, lo + per);
+  float4 *__restrict__ dst = reinterpret_cast<float4 *>(T.base[0] + T.off_final);
+  for (unsigned i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+    float4 acc = reinterpret_cast<const float4 *>(T.base[0] + T.off_fb)[i];
+    for (int r = 1; r < T.nranks; r++) {
+      const float4 v = reinterpret_cast<const float4 *>(T.base[r] + T.off_fb)[i];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    dst[i] = acc;
+  }
+}
+
 static int sm_count() {
   static int sms = 0;
   if (!sms) {
@@ -358,8 +601,20 @@ static int sm_count() {
   return sms;
 }
 
+static PeerTable no_peers() {
+  PeerTable T;
+  memset(&T, 0, sizeof T);
+  return T;
+}
+
+static int fetch_threshold(const char *env) {
+  int ft = 12;  // measured optimum on the 100M-triangle scene (tools/trace_sweep.py, GXY_FETCH_SWEEP)
+  if (const char *e = getenv(env)) ft = atoi(e);
+  return ft;
+}
+
 int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLights &L, int w, int h, float *fb, Rays prim, unsigned *raw,
-                         Rays hits, Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, cudaStream_t st) {
+                         Rays hits, Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, const PeerTable *peer, cudaStream_t st) {
   if (ensure_ao_tables()) return 1;
   const int tiles_x = (w + 7) / 8, tiles_y = (h + 3) / 4;
   const unsigned n_queue = (unsigned)tiles_x * (unsigned)tiles_y * 32u;
@@ -367,30 +622,43 @@ int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLigh
   gen_primary_kernel<<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, n_queue, prim, q);
   const unsigned needed = (npix + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
   const unsigned blocks = std::min<unsigned>(needed, (unsigned)sm_count() * 8u);
-  int ft = 12;  // measured optimum on the 100M-triangle scene (tools/trace_sweep.py, GXY_FETCH_SWEEP)
-  if (const char *e = getenv("GXY_FETCH_P")) ft = atoi(e);
-  switch (ft) {
-    case 4: primary_trace_kernel<4, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q); break;
-    case 8: primary_trace_kernel<8, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q); break;
-    case 16: primary_trace_kernel<16, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q); break;
-    case 24: primary_trace_kernel<24, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q); break;
-    default: primary_trace_kernel<12, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q); break;
+  const PeerTable T = peer ? *peer : no_peers();
+#define GXY_LAUNCH_P(FT)                                                                                                              \
+  do {                                                                                                                                \
+    if (peer) primary_trace_kernel<FT, 8, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q, T);    \
+    else primary_trace_kernel<FT, 8, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q, T);         \
+  } while (0)
+  switch (fetch_threshold("GXY_FETCH_P")) {
+    case 4: GXY_LAUNCH_P(4); break;
+    case 8: GXY_LAUNCH_P(8); break;
+    case 16: GXY_LAUNCH_P(16); break;
+    case 24: GXY_LAUNCH_P(24); break;
+    default: GXY_LAUNCH_P(12); break;
   }
-  shade_hits_kernel<<<(npix + 255) / 256, 256, 0, st>>>(P, L, prim, raw, npix, w, reinterpret_cast<float4 *>(fb), hits, q, epsilon);
+#undef GXY_LAUNCH_P
+  shade_hits_kernel<false><<<(npix + 255) / 256, 256, 0, st>>>(P, L, prim, nullptr, raw, npix, w, reinterpret_cast<float4 *>(fb), hits, q, epsilon);
   GXY_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_fused_secondary(const SceneParams &P, const DevLights &L, int w, int h, int nsec, long long max_rays, float *fb, Rays hits,
-                           Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, bool anyhit, cudaStream_t st) {
+                           Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, bool anyhit, const PeerTable *peer, int parity_out,
+                           cudaStream_t st) {
   if (nsec <= 0 || max_rays <= 0) return 0;
   if (ensure_ao_tables()) return 1;
   const long long needed = (max_rays + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
   const unsigned blocks = (unsigned)std::min<long long>(needed, (long long)sm_count() * 8);
-  int ft = 12;
-  if (const char *e = getenv("GXY_FETCH_S")) ft = atoi(e);
-#define GXY_LAUNCH_S(T) fused_secondary_kernel<T, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, L, w, h, nsec, reinterpret_cast<float4 *>(fb), hits, spill, spill_cap, q, epsilon, anyhit ? 1 : 0)
-  switch (ft) {
+  const PeerTable T = peer ? *peer : no_peers();
+#define GXY_LAUNCH_S(FT)                                                                                                              \
+  do {                                                                                                                                \
+    if (peer)                                                                                                                         \
+      fused_secondary_kernel<FT, 8, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, L, w, h, nsec, reinterpret_cast<float4 *>(fb), hits, spill, \
+                                                                                spill_cap, q, epsilon, anyhit ? 1 : 0, T, parity_out);     \
+    else                                                                                                                              \
+      fused_secondary_kernel<FT, 8, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, L, w, h, nsec, reinterpret_cast<float4 *>(fb), hits, spill, \
+                                                                                 spill_cap, q, epsilon, anyhit ? 1 : 0, T, parity_out);    \
+  } while (0)
+  switch (fetch_threshold("GXY_FETCH_S")) {
     case 4: GXY_LAUNCH_S(4); break;
     case 8: GXY_LAUNCH_S(8); break;
     case 16: GXY_LAUNCH_S(16); break;
@@ -398,6 +666,33 @@ int launch_fused_secondary(const SceneParams &P, const DevLights &L, int w, int 
     default: GXY_LAUNCH_S(12); break;
   }
 #undef GXY_LAUNCH_S
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_inbox_wave(const SceneParams &P, const DevLights &L, const PeerTable &T, int parity_in, int w, int h, float *fb, unsigned *raw,
+                      unsigned raw_stride, Rays hits, FusedQueues *q, float epsilon, bool anyhit, cudaStream_t st) {
+  (void)h;
+  const unsigned blocks = (unsigned)sm_count() * 8u;
+  inbox_trace_kernel<12, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, T, parity_in, w, reinterpret_cast<float4 *>(fb), raw, raw_stride, q,
+                                                                   anyhit ? 1 : 0);
+  const float4 *inbox = reinterpret_cast<const float4 *>(T.base[T.rank] + T.off_inbox[parity_in]);
+  shade_hits_kernel<true><<<(unsigned)sm_count() * 4u, 256, 0, st>>>(P, L, hits, inbox, raw, raw_stride, w, reinterpret_cast<float4 *>(fb), hits, q,
+                                                                    epsilon);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_wave_epilogue(const PeerTable &T, FusedQueues *q, unsigned epoch, int parity_consumed, int *error_flag, cudaStream_t st) {
+  unsigned long long timeout_ns = 30ull * 1000000000ull;
+  if (const char *e = getenv("GXY_PEER_TIMEOUT_MS")) timeout_ns = (unsigned long long)atoll(e) * 1000000ull;
+  wave_epilogue_kernel<<<1, 32, 0, st>>>(T, q, epoch, parity_consumed, timeout_ns, error_flag);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_fb_gather(const PeerTable &T, cudaStream_t st) {
+  fb_gather_kernel<<<(unsigned)sm_count() * 4u, 256, 0, st>>>(T);
   GXY_CUDA(cudaGetLastError());
   return 0;
 }

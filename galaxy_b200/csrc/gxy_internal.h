@@ -37,18 +37,53 @@ int launch_intersect(const SceneParams &P, int n, const float *org3, const float
 // ---- fused frame kernels for geometry-only Visualizations (gxy_fused.cu) ---------------------------
 struct FusedQueues {  // device memory, zeroed at the start of a frame
   unsigned pixel_head, n_hits, n_spill, sec_head;
-  unsigned n_primary32, pad;
-  unsigned long long n_terminated, nodes, prims;
+  unsigned n_primary32, hits_done, inbox_head, spill_done;
+  unsigned long long n_terminated, nodes, prims, n_inbox;
+  unsigned global_pending, pad[3];
 };
+
+// ---- peer arenas: the one-process-per-GPU exchange without NCCL on the data path -------------------
+// Every rank owns one device allocation ("arena") that all other ranks map with CUDA IPC.  A ray that
+// leaves a partition is written by the trace kernel itself, as one 64-byte record, straight into the
+// destination rank's inbox over NVLink (slot from a system-scope atomicAdd on the destination's
+// counter); waves are separated by a device-side flag barrier; the partial framebuffers are summed tile
+// by tile with peer loads.  Replaces SendRaysMsg / SendPixelsMsg over MPI (Renderer.cpp:732-836,
+// Renderer.h:246-340) and the busy/idle termination protocol (RenderingSet.cpp:289-589).
+#define GXY_MAX_RANKS 16
+struct PeerCtrl {  // first 256 bytes of every arena
+  unsigned flags[GXY_MAX_RANKS];       // flags[r]: last epoch rank r has signalled to this rank
+  unsigned pending[2][GXY_MAX_RANKS];  // pending[epoch & 1][r]: rays rank r sent anywhere in that epoch's wave
+  unsigned inbox_count[2];             // records appended to this rank's inbox[parity]
+  unsigned pad[14];
+};
+static_assert(sizeof(PeerCtrl) == 256, "PeerCtrl layout");
+struct PeerTable {  // kernel parameter: every rank's arena as mapped in THIS process (base[rank] = own)
+  int rank, nranks;
+  unsigned inbox_cap;  // 64-byte records per inbox
+  unsigned npix;
+  unsigned long long off_fb, off_final, off_inbox[2];  // byte offsets inside an arena, the same on every rank
+  char *base[GXY_MAX_RANKS];
+};
+// inbox record: 4 x float4 = (ox oy oz dx) (dy dz t tMax) (r g b o) (x y type term)
+
 // generation (1 kernel) -> trace + classify of the misses (persistent kernel) -> shade/light/framebuffer of
 // the hits (1 kernel); hit records go to `hits` (columns ox..dz t nx..nz sr..sb o x y), rays bound for
-// a neighbour to `spill`
+// a neighbour to `spill` (peer == NULL) or to the neighbour's inbox[0] (peer != NULL)
 // prim: list for the generated rays (>= w*h), raw: 6*w*h words of scratch, hits: >= w*h records
 int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLights &L, int w, int h, float *fb, Rays prim, unsigned *raw,
-                         Rays hits, Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, cudaStream_t st);
-// AO + shadow rays of every hit record: generate -> trace -> classify -> framebuffer
+                         Rays hits, Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, const PeerTable *peer, cudaStream_t st);
+// AO + shadow rays of the hit records [q->hits_done, q->n_hits): generate -> trace -> classify -> framebuffer
 int launch_fused_secondary(const SceneParams &P, const DevLights &L, int w, int h, int nsec, long long max_rays, float *fb, Rays hits,
-                           Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, bool anyhit, cudaStream_t st);
+                           Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, bool anyhit, const PeerTable *peer, int parity_out,
+                           cudaStream_t st);
+// one wave >= 1 of the peer path: trace the records of inbox[parity_in]; PRIMARY hits -> raw records -> shading
+// (hit records appended to `hits`); everything else is classified: framebuffer, dropped, or the next inbox
+int launch_inbox_wave(const SceneParams &P, const DevLights &L, const PeerTable &T, int parity_in, int w, int h, float *fb, unsigned *raw,
+                      unsigned raw_stride, Rays hits, FusedQueues *q, float epsilon, bool anyhit, cudaStream_t st);
+// end of a wave: queue bookkeeping, reset of the consumed inbox, flag barrier across ranks, global pending count
+int launch_wave_epilogue(const PeerTable &T, FusedQueues *q, unsigned epoch, int parity_consumed, int *error_flag, cudaStream_t st);
+// sum of all partial framebuffers for this rank's slice of the image, written to the image owner (rank 0)
+int launch_fb_gather(const PeerTable &T, cudaStream_t st);
 
 // ---- BVH build (gxy_bvh.cu) -----------------------------------------------------------------
 struct GeomBuildInput {

@@ -78,8 +78,9 @@ __device__ __forceinline__ bool setup_ray_values(const SceneParams &P, int i, bo
   pr.tExit = tExitVolume;
   pr.anyhit = !shadeFlag && anyhit_secondary;
   pr.opaque = false;
-  // an empty interval cannot accept any candidate (both primitive tests need tnear < t <= tfar)
-  return ray_t0 <= ray_t;
+  // an empty interval cannot accept any candidate (both primitive tests need tnear < t <= tfar); a partition
+  // whose clipped geometry is empty has no tree to walk
+  return ray_t0 <= ray_t && P.n_prims > 0;
 }
 
 
