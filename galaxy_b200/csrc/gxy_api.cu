@@ -994,12 +994,12 @@ static int render_peer(gxy_vis *v, const DevCamera &C, const DevLights &L, const
     cudaEventDestroy(e.second);
   }
   if (check_error_flag(v)) return 1;
-  S.primary_rays = (long long)hq.n_primary32;
+  S.primary_rays = (long long)hq.n_generated;
   S.ao_rays = (long long)hq.n_hits * lights.n_ao;
   S.shadow_rays = (long long)hq.n_hits * (lights.shadows ? lights.n_lights : 0);
   S.forwarded_rays = (long long)hq.n_spill;
   S.terminated_rays = (long long)hq.n_terminated;
-  S.traced_rays = (long long)hq.n_primary32 + (long long)hq.n_hits * n_sec_per_hit + (long long)hq.n_inbox;
+  S.traced_rays = (long long)hq.n_generated + (long long)hq.n_hits * n_sec_per_hit + (long long)hq.n_inbox;
   S.nodes_visited = (long long)hq.nodes;
   S.prims_tested = (long long)hq.prims;
   if (stats) *stats = S;
@@ -1138,10 +1138,10 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       gxy_vis *v = parts[p];
       if (use_device(v->ctx)) return 1;
       GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
-      S.primary_rays += (long long)fq[p].n_primary32;
+      S.primary_rays += (long long)fq[p].n_generated;
       S.ao_rays += (long long)fq[p].n_hits * lights.n_ao;
       S.shadow_rays += (long long)fq[p].n_hits * (lights.shadows ? lights.n_lights : 0);
-      S.traced_rays += (long long)fq[p].n_primary32 + (long long)fq[p].n_hits * n_sec_per_hit;
+      S.traced_rays += (long long)fq[p].n_generated + (long long)fq[p].n_hits * n_sec_per_hit;
       S.terminated_rays += (long long)fq[p].n_terminated;
       S.nodes_visited += (long long)fq[p].nodes;
       S.prims_tested += (long long)fq[p].prims;

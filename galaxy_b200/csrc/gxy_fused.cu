@@ -90,25 +90,63 @@ __device__ __forceinline__ void peer_push(const PeerTable &T, int parity, unsign
   }
 }
 
-// Camera::SpawnRays for the whole window (Camera.cpp:379-493): one thread per pixel in tile order,
-// kept rays appended (unordered) to `out` (columns ox..dz x y; t = 0, tMax = FLT_MAX, type PRIMARY implied)
+// Camera::SpawnRays for the whole window (Camera.cpp:379-493): one thread per pixel in tile order.  A kept ray is
+// clipped to the local box and tested against the top two levels of the BVH (may_hit_anything): rays that can
+// reach no primitive are finished here at full SIMD width exactly as the trace kernel finishes a ray without a
+// hit (term BOUNDARY/TIMEOUT -> Classify: TERMINATED with colour 0, or on to the neighbour partition); the
+// others are appended (unordered) to `out` (columns ox..dz x y; t = 0, tMax = FLT_MAX, type PRIMARY implied).
+template <bool PEER>
 __global__ void __launch_bounds__(256)
     gen_primary_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevCamera C, int w, int h, int tiles_x,
-                       unsigned n_queue, Rays out, FusedQueues *__restrict__ q) {
+                       unsigned n_queue, Rays out, Rays spill, unsigned spill_cap, FusedQueues *__restrict__ q,
+                       const __grid_constant__ PeerTable T) {
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
-  bool kept = false;
+  bool kept = false, queued = false;
   int x = 0, y = 0;
   float3 o3 = f3(0.f, 0.f, 0.f), d3 = f3(0.f, 0.f, 0.f);
   if (idx < n_queue) {
     tile_pixel(idx, tiles_x, x, y);
     kept = x < w && y < h && spawn_pixel(P, C, x, y, o3, d3);
   }
-  const unsigned pos = group_append(FULLMASK, lane, kept, &q->n_primary32);
+  bool do_spill = false, terminated = false;
+  int term = 0, cls = CLS_UNDETERMINED;
+  float ray_t = 0.f;
   if (kept) {
+    RayCtx rc;
+    TravState st;
+    PendingRay pr;
+    queued = setup_ray_values(P, 0, true, o3, d3, 0.f, FLT_MAX, 0, rc, st, pr) && may_hit_anything(P, rc);
+    if (!queued) {
+      ray_t = rc.tfar;
+      if (ray_t == pr.tExit) term |= RAY_BOUNDARY;
+      else if (ray_t == FLT_MAX) term |= RAY_TIMEOUT;
+      cls = classify_values(P, RAY_PRIMARY, term, o3.x, o3.y, o3.z, d3.x, d3.y, d3.z);
+      terminated = cls == CLS_TERMINATED;  // carries (0,0,0,0): nothing to add
+      do_spill = cls >= 0;
+    }
+  }
+  const unsigned km = __ballot_sync(FULLMASK, kept), tm = __ballot_sync(FULLMASK, terminated);
+  if (lane == 0u) {
+    if (km) atomicAdd(&q->n_generated, (unsigned)__popc(km));
+    if (tm) atomicAdd(&q->n_terminated, (unsigned long long)__popc(tm));
+  }
+  const unsigned pos = group_append(FULLMASK, lane, queued, &q->n_primary32);
+  if (queued) {
     out.ox[pos] = o3.x; out.oy[pos] = o3.y; out.oz[pos] = o3.z;
     out.dx[pos] = d3.x; out.dy[pos] = d3.y; out.dz[pos] = d3.z;
     out.x[pos] = x; out.y[pos] = y;
+  }
+  if (PEER) {
+    const unsigned sm = __ballot_sync(FULLMASK, do_spill);
+    if (sm && lane == 0u) atomicAdd(&q->n_spill, (unsigned)__popc(sm));
+    peer_push(T, 0, FULLMASK, lane, do_spill, cls, o3, d3, 0.f, 0.f, 0.f, 0.f, ray_t, FLT_MAX, x, y, RAY_PRIMARY, term, P.error_flag);
+  } else {
+    const unsigned sp = group_append(FULLMASK, lane, do_spill, &q->n_spill);
+    if (do_spill) {
+      if (sp < spill_cap) write_spill(spill, sp, o3, d3, 0.f, 0.f, 0.f, 0.f, ray_t, FLT_MAX, x, y, RAY_PRIMARY, term, cls);
+      else *P.error_flag = 3;
+    }
   }
 }
 
@@ -619,10 +657,11 @@ int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLigh
   const int tiles_x = (w + 7) / 8, tiles_y = (h + 3) / 4;
   const unsigned n_queue = (unsigned)tiles_x * (unsigned)tiles_y * 32u;
   const unsigned npix = (unsigned)w * (unsigned)h;
-  gen_primary_kernel<<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, n_queue, prim, q);
+  const PeerTable T = peer ? *peer : no_peers();
+  if (peer) gen_primary_kernel<true><<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, n_queue, prim, spill, spill_cap, q, T);
+  else gen_primary_kernel<false><<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, n_queue, prim, spill, spill_cap, q, T);
   const unsigned needed = (npix + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
   const unsigned blocks = std::min<unsigned>(needed, (unsigned)sm_count() * 8u);
-  const PeerTable T = peer ? *peer : no_peers();
 #define GXY_LAUNCH_P(FT)                                                                                                              \
   do {                                                                                                                                \
     if (peer) primary_trace_kernel<FT, 8, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q, T);    \

@@ -39,7 +39,7 @@ struct FusedQueues {  // device memory, zeroed at the start of a frame
   unsigned pixel_head, n_hits, n_spill, sec_head;
   unsigned n_primary32, hits_done, inbox_head, spill_done;
   unsigned long long n_terminated, nodes, prims, n_inbox;
-  unsigned global_pending, pad[3];
+  unsigned global_pending, n_generated, pad[2];  // n_generated: kept primaries (n_primary32 = those queued for the trace kernel)
 };
 
 // ---- peer arenas: the one-process-per-GPU exchange without NCCL on the data path -------------------

@@ -25,15 +25,107 @@ struct SurfHit {  // TraceRays.ispc:79-88
   float3 normal, color;
 };
 
-template <int NV>
-__device__ __forceinline__ void sample_volumes(const SceneParams &P, int nvv, float3 coord, float *s) {
-#pragma unroll
-  for (int m = 0; m < NV; m++)
-    if (m < nvv) s[m] = vol_sample(P.vv[m].vol, coord);
+// Per-volume constants of the march loop, held in registers for the whole ray (the loop is issue bound: every
+// constant-bank reload and every 64-bit address operation inside it costs an issue slot per sample).
+struct VolK {
+  float ox, oy, oz, rx, ry, rz, ux, uy, uz;
+  unsigned nx, nxy;      // IDX32 only: row / slice pitch in elements
+  const char *vox;
+  int type;
+};
+__device__ __forceinline__ void pin(float &x) { asm volatile("" : "+f"(x)); }
+__device__ __forceinline__ void pin(unsigned &x) { asm volatile("" : "+r"(x)); }
+__device__ __forceinline__ void volk_load(VolK &k, const DevVolume &v) {
+  k.ox = v.origin.x; k.oy = v.origin.y; k.oz = v.origin.z;
+  k.rx = v.rcp.x; k.ry = v.rcp.y; k.rz = v.rcp.z;
+  k.ux = v.upper.x; k.uy = v.upper.y; k.uz = v.upper.z;
+  k.nx = (unsigned)v.nx; k.nxy = (unsigned)v.nxy;
+  k.vox = (const char *)v.vox; k.type = v.type;
+  pin(k.ox); pin(k.oy); pin(k.oz); pin(k.rx); pin(k.ry); pin(k.rz); pin(k.ux); pin(k.uy); pin(k.uz); pin(k.nx); pin(k.nxy);
 }
 
-template <int NV, bool HAS_GEOM>
-__global__ void __launch_bounds__(GXY_TRACE_THREADS)
+// SSV_sample_float_32 (SharedStructuredVolume.ispc:131-191): the arithmetic of vol_sample() (gxy_common.cuh), split
+// into its three stages so that the march loop can run them one sample apart (software pipeline):
+//   tap    cell index + interpolation weights; 32-bit element indices (volumes below 2^31 voxels): 2 IMAD instead
+//          of 64-bit index math
+//   fetch  the 8 voxel loads (or 4 L1 prefetches of the rows that hold them)
+//   lerp   x -> y -> z as a + f*(b - a)
+struct VolTap {
+  unsigned o0;
+  float fx, fy, fz;
+};
+struct Vox8 {
+  float v000, v001, v010, v011, v100, v101, v110, v111;
+};
+__device__ __forceinline__ void vol_tap_k32(const VolK &v, float3 p, VolTap &t) {
+  const float lx = v.rx * (p.x - v.ox), ly = v.ry * (p.y - v.oy), lz = v.rz * (p.z - v.oz);
+  const float cx = fmaxf(0.0f, fminf(lx, v.ux)), cy = fmaxf(0.0f, fminf(ly, v.uy)), cz = fmaxf(0.0f, fminf(lz, v.uz));
+  const int ix = (int)cx, iy = (int)cy, iz = (int)cz;
+  t.fx = cx - (float)ix; t.fy = cy - (float)iy; t.fz = cz - (float)iz;
+  t.o0 = (unsigned)ix + (unsigned)iy * v.nx + (unsigned)iz * v.nxy;
+}
+__device__ __forceinline__ void vol_fetch_k32(const VolK &v, const VolTap &t, Vox8 &x) {
+  const unsigned o0 = t.o0, o1 = o0 + v.nx, o2 = o0 + v.nxy, o3 = o2 + v.nx;
+  if (v.type == 0) {
+    const float *__restrict__ b = (const float *)v.vox;
+    const float *q0 = b + o0, *q1 = b + o1, *q2 = b + o2, *q3 = b + o3;
+    x.v000 = __ldg(q0); x.v001 = __ldg(q0 + 1);
+    x.v010 = __ldg(q1); x.v011 = __ldg(q1 + 1);
+    x.v100 = __ldg(q2); x.v101 = __ldg(q2 + 1);
+    x.v110 = __ldg(q3); x.v111 = __ldg(q3 + 1);
+  } else {
+    const unsigned char *__restrict__ b = (const unsigned char *)v.vox;
+    const unsigned char *q0 = b + o0, *q1 = b + o1, *q2 = b + o2, *q3 = b + o3;
+    x.v000 = (float)__ldg(q0); x.v001 = (float)__ldg(q0 + 1);
+    x.v010 = (float)__ldg(q1); x.v011 = (float)__ldg(q1 + 1);
+    x.v100 = (float)__ldg(q2); x.v101 = (float)__ldg(q2 + 1);
+    x.v110 = (float)__ldg(q3); x.v111 = (float)__ldg(q3 + 1);
+  }
+}
+__device__ __forceinline__ void vol_prefetch_k32(const VolK &v, const VolTap &t) {
+  const unsigned o0 = t.o0, o1 = o0 + v.nx, o2 = o0 + v.nxy, o3 = o2 + v.nx;
+  const unsigned sh = v.type == 0 ? 2u : 0u;
+  const char *b = v.vox;
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(b + ((size_t)o0 << sh)));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(b + ((size_t)o1 << sh)));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(b + ((size_t)o2 << sh)));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(b + ((size_t)o3 << sh)));
+}
+__device__ __forceinline__ float vol_lerp8(const Vox8 &x, const VolTap &t) {
+  const float v00 = x.v000 + t.fx * (x.v001 - x.v000);
+  const float v01 = x.v010 + t.fx * (x.v011 - x.v010);
+  const float v10 = x.v100 + t.fx * (x.v101 - x.v100);
+  const float v11 = x.v110 + t.fx * (x.v111 - x.v110);
+  const float v0 = v00 + t.fy * (v01 - v00);
+  const float v1 = v10 + t.fy * (v11 - v10);
+  return v0 + t.fz * (v1 - v0);
+}
+__device__ __forceinline__ float vol_sample_k32(const VolK &v, float3 p) {
+  VolTap t;
+  Vox8 x;
+  vol_tap_k32(v, p, t);
+  vol_fetch_k32(v, t, x);
+  return vol_lerp8(x, t);
+}
+
+template <int NV, bool IDX32>
+__device__ __forceinline__ void sample_volumes(const SceneParams &P, const VolK *vk, int nvv, float3 coord, float *s) {
+#pragma unroll
+  for (int m = 0; m < NV; m++)
+    if (m < nvv) s[m] = IDX32 ? vol_sample_k32(vk[m], coord) : vol_sample(P.vv[m].vol, coord);
+}
+
+// march-loop software pipeline (IDX32 volumes): 0 = none, 1 = L1 prefetch of the next sample's rows,
+// 2 = the next sample's 8 voxels are loaded into registers while the current sample is processed
+#ifndef GXY_MARCH_PIPE
+#define GXY_MARCH_PIPE 0
+#endif
+#ifndef GXY_MARCH_BLOCKS
+#define GXY_MARCH_BLOCKS 8
+#endif
+
+template <int NV, bool HAS_GEOM, bool IDX32>
+__global__ void __launch_bounds__(GXY_TRACE_THREADS, (NV <= 2 && !HAS_GEOM) ? GXY_MARCH_BLOCKS : 1)
     trace_kernel(const __grid_constant__ SceneParams P, Rays R, int n, float global_epsilon, int *__restrict__ hit_ids,
                  int anyhit_secondary, unsigned long long *__restrict__ sample_counter) {
   __shared__ uint2 stack[HAS_GEOM ? GXY_STACK_SMEM * GXY_TRACE_THREADS : 1];
@@ -122,68 +214,128 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS)
   float tTermination = ray_t;
 
   if (NV > 0 && P.integrate) {  // :446-570
+    constexpr int NVA = NV > 0 ? NV : 1;
     float tLast, tThis;
-    float sLast[NV > 0 ? NV : 1], sThis[NV > 0 ? NV : 1];
+    float sLast[NVA], sThis[NVA];
+    // loop invariants, fetched once per ray
+    VolK vk[NVA];
+    const DevTF *tf_vol[NVA];
+    float rate[NVA];
+    bool dvr[NVA];
+    bool any_iso = false;
+#pragma unroll
+    for (int m = 0; m < NV; m++)
+      if (m < nvv) {
+        if (IDX32) volk_load(vk[m], P.vv[m].vol);
+        tf_vol[m] = P.tfs + P.vv[m].vol.tf;
+        rate[m] = P.vv[m].vol.samplingRate;
+        dvr[m] = P.vv[m].volume_render != 0;
+        any_iso = any_iso || P.vv[m].n_iso > 0;
+      }
+    unsigned iters = 0;
     bool hit_isosurface = false;
     tLast = tEntry + epsilon;
     bool opaque = (min3f(cr, cg, cb) >= 1.0f || co > 0.999f);
+    constexpr int PIPE = IDX32 ? GXY_MARCH_PIPE : 0;
+    // pipeline state: taps (and voxels) of the sample at tSpec, the position the loop will visit next unless it ends
+    VolTap tap[NVA];
+    Vox8 vox[NVA];
+    float tSpec = tEntry;
+    if (PIPE) {
+#pragma unroll
+      for (int m = 0; m < NV; m++)
+        if (m < nvv) {
+          vol_tap_k32(vk[m], org + tSpec * dir, tap[m]);
+          if (PIPE == 2) vol_fetch_k32(vk[m], tap[m], vox[m]);
+        }
+    }
     for (tThis = tEntry; tThis <= tTermination && !opaque && !hit_isosurface;
          tThis = (tThis == tEntry) ? (tEntry + epsilon)
                                    : (((tThis + step) > tTermination) && (tThis < tTermination)) ? tTermination : tThis + step) {
-      sample_volumes<NV>(P, nvv, org + tThis * dir, sThis);
-      nsamples += nvv;
-      if (tThis > tEntry && tLast >= epsilon) {
-        // LookForIsoHit :252-310
-        bool h = false;
-        int vid = -1;
-        float hsample = 0.f;
+      if (PIPE) {
+        // the loop update only depends on tThis and tTermination; when neither an isosurface hit nor opacity ends
+        // the loop, the next position is the one predicted here (clamped addresses: any position is safe to load)
+        const float tNext = (tThis == tEntry) ? (tEntry + epsilon)
+                                              : (((tThis + step) > tTermination) && (tThis < tTermination)) ? tTermination : tThis + step;
+        VolTap ntap[NVA];
+        Vox8 nvox[NVA];
 #pragma unroll
-        for (int major = 0; major < NV; major++)
-          if (major < nvv) {
-            const float sl = sLast[major], st = sThis[major];
-            const int ni = P.vv[major].n_iso;
-            for (int minor = 0; minor < ni; minor++) {
-              const float isoval = P.vv[major].iso[minor];
-              if (((isoval >= sl) && (isoval < st)) || ((isoval <= sl) && (isoval > st))) {
-                h = true; vid = major;
-                hit.t = tLast + ((isoval - sl) / (st - sl)) * (tThis - tLast);
-                hsample = isoval;
+        for (int m = 0; m < NV; m++)
+          if (m < nvv) {
+            if (tThis != tSpec) {  // never taken by construction; keeps the pipeline honest
+              vol_tap_k32(vk[m], org + tThis * dir, tap[m]);
+              if (PIPE == 2) vol_fetch_k32(vk[m], tap[m], vox[m]);
+            }
+            vol_tap_k32(vk[m], org + tNext * dir, ntap[m]);
+            if (PIPE == 2) vol_fetch_k32(vk[m], ntap[m], nvox[m]);
+            else {
+              vol_prefetch_k32(vk[m], ntap[m]);
+              vol_fetch_k32(vk[m], tap[m], vox[m]);
+            }
+            sThis[m] = vol_lerp8(vox[m], tap[m]);
+            tap[m] = ntap[m];
+            if (PIPE == 2) vox[m] = nvox[m];
+          }
+        tSpec = tNext;
+      } else {
+        sample_volumes<NV, IDX32>(P, vk, nvv, org + tThis * dir, sThis);
+      }
+      iters++;
+      if (tThis > tEntry && tLast >= epsilon) {
+        if (any_iso) {
+          // LookForIsoHit :252-310
+          bool h = false;
+          int vid = -1;
+          float hsample = 0.f;
+#pragma unroll
+          for (int major = 0; major < NV; major++)
+            if (major < nvv) {
+              const float sl = sLast[major], st = sThis[major];
+              const int ni = P.vv[major].n_iso;
+              for (int minor = 0; minor < ni; minor++) {
+                const float isoval = P.vv[major].iso[minor];
+                if (((isoval >= sl) && (isoval < st)) || ((isoval <= sl) && (isoval > st))) {
+                  h = true; vid = major;
+                  hit.t = tLast + ((isoval - sl) / (st - sl)) * (tThis - tLast);
+                  hsample = isoval;
+                }
               }
             }
+          if (h) {
+            const float3 point = org + hit.t * dir;
+            if (shadeFlag) {
+              hit.normal = safe_normalize(vol_gradient(P.vv[vid].vol, point));
+              nsamples += 4;
+              if (dot3(dir, hit.normal) > 0) hit.normal = neg3(hit.normal);
+              hit.color = tf_color(P.tfs + P.vv[vid].tf, hsample);
+              hit.opacity = 1.0f;
+            }
+            tTermination = hit.t; tThis = hit.t;
+            surface_hit = true; hit_isosurface = true;
+            sample_volumes<NV, IDX32>(P, vk, nvv, org + tThis * dir, sThis);
+            iters++;
           }
-        if (h) {
-          const float3 point = org + hit.t * dir;
-          if (shadeFlag) {
-            hit.normal = safe_normalize(vol_gradient(P.vv[vid].vol, point));
-            nsamples += 4;
-            if (dot3(dir, hit.normal) > 0) hit.normal = neg3(hit.normal);
-            hit.color = tf_color(P.tfs + P.vv[vid].tf, hsample);
-            hit.opacity = 1.0f;
-          }
-          tTermination = hit.t; tThis = hit.t;
-          surface_hit = true; hit_isosurface = true;
-          sample_volumes<NV>(P, nvv, org + tThis * dir, sThis);
-          nsamples += nvv;
         }
         // DVR :512-542
 #pragma unroll
         for (int major = 0; major < NV; major++)
           if (major < nvv) {
-            if (P.vv[major].volume_render) {
-              const DevTF *tf = P.tfs + P.vv[major].vol.tf;
+            if (dvr[major]) {
+              const DevTF *tf = tf_vol[major];
               const float sVolume = (sLast[major] + sThis[major]) / 2;
-              const float rate = P.vv[major].vol.samplingRate;
               if (shadeFlag) {
                 const float4 ca = tf_both(tf, sVolume);
                 if (ca.w > 0) {
-                  const float wo = fmaxf(0.0f, fminf(ca.w / rate, 1.0f));
+                  // x / 1.0f == x for every x: the division is only executed for a sampling rate other than 1
+                  const float wo = fmaxf(0.0f, fminf(rate[major] == 1.0f ? ca.w : ca.w / rate[major], 1.0f));
                   const float om = 1.0f - co;
                   cr = cr + om * (wo * ca.x); cg = cg + om * (wo * ca.y); cb = cb + om * (wo * ca.z); co = co + om * (wo * 1.0f);
                 }
               } else {
                 const float sampleOpacity = tf_opacity(tf, sVolume);
                 if (sampleOpacity > 0) {
-                  const float weightedOpacity = ((tThis - tLast) / step) * fmaxf(0.0f, fminf(sampleOpacity / rate, 1.0f));
+                  const float so1 = rate[major] == 1.0f ? sampleOpacity : sampleOpacity / rate[major];
+                  const float weightedOpacity = ((tThis - tLast) / step) * fmaxf(0.0f, fminf(so1, 1.0f));
                   const float f = 1 - weightedOpacity;
                   cr = cr * f; cg = cg * f; cb = cb * f; co = co * f;
                 }
@@ -197,6 +349,7 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS)
       if (opaque) tTermination = tThis;
       tLast = tThis;
     }
+    nsamples += iters * (unsigned)nvv;
     ray_t = tTermination;
   }
 
@@ -418,8 +571,19 @@ template <int NV>
 static int launch_trace_nv(const SceneParams &P, Rays R, int n, float eps, int *hit_ids, bool anyhit, unsigned long long *sc,
                            cudaStream_t st) {
   const int blocks = (n + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
-  if (P.n_prims > 0) trace_kernel<NV, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, anyhit ? 1 : 0, sc);
-  else trace_kernel<NV, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, 0, sc);
+  // 32-bit element indices in the sampler when every volume of the Visualization has fewer than 2^31 voxels
+  bool idx32 = NV > 0;
+  for (int m = 0; m < P.n_volvis && m < NV; m++) {
+    const DevVolume &v = P.vv[m].vol;
+    idx32 = idx32 && (unsigned long long)v.dims[0] * (unsigned long long)v.dims[1] * (unsigned long long)v.dims[2] < (1ull << 31);
+  }
+  if (P.n_prims > 0) {
+    if (idx32) trace_kernel<NV, true, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, anyhit ? 1 : 0, sc);
+    else trace_kernel<NV, true, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, anyhit ? 1 : 0, sc);
+  } else {
+    if (idx32) trace_kernel<NV, false, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, 0, sc);
+    else trace_kernel<NV, false, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, 0, sc);
+  }
   GXY_CUDA(cudaGetLastError());
   return 0;
 }

@@ -135,7 +135,22 @@ __device__ __forceinline__ void trav_init(TravState &s, const RayCtx &rc) {
 #endif
 }
 
-__device__ __forceinline__ float byte_f(unsigned w, int k) { return (float)((w >> (8 * k)) & 0xffu); }
+// Quantised plane byte -> float without the conversion unit.  I2F.U8 runs on the quarter-rate XU pipe (measured on
+// B200: 16 conversions/clk/SM, tools/ubench/f32x2.cu) and a node test needs 48 of them; instead one PRMT drops the
+// byte into mantissa bits 8..15 of 128.0f: f = 128 + q/256 exactly, and the slab equation t = q*a + b becomes
+// t = f*(256a) + (b - 32768a), one FFMA per plane (the constant folding costs 3 FFMA per node; its rounding,
+// <= ulp(32768|a|)/2 = |a|/512, goes into the conservative widening E).
+//   GXY_BOX_CONV 0: I2F + FFMA   1: PRMT + FFMA   2: PRMT + FFMA2 (near/far plane of an axis as one packed f32x2 op)
+#ifndef GXY_BOX_CONV
+#define GXY_BOX_CONV 0
+#endif
+__device__ __forceinline__ float byte_f(unsigned w, int k) {
+#if GXY_BOX_CONV == 0
+  return (float)((w >> (8 * k)) & 0xffu);
+#else
+  return __uint_as_float(__byte_perm(w, 0x43000000u, 0x7404u + 0x10u * (unsigned)k));
+#endif
+}
 
 // the 4 children of one half of a node: returns their contribution to the hit mask
 __device__ __forceinline__ unsigned test_half(unsigned meta4, unsigned octinv4, unsigned nx4, unsigned ny4, unsigned nz4, unsigned fx4,
@@ -148,9 +163,16 @@ __device__ __forceinline__ unsigned test_half(unsigned meta4, unsigned octinv4, 
   unsigned hitmask = 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
+#if GXY_BOX_CONV == 2
+    const float2 tx = __ffma2_rn(make_float2(byte_f(nx4, k), byte_f(fx4, k)), make_float2(ax, ax), make_float2(bnx, bfx));
+    const float2 ty = __ffma2_rn(make_float2(byte_f(ny4, k), byte_f(fy4, k)), make_float2(ay, ay), make_float2(bny, bfy));
+    const float2 tz = __ffma2_rn(make_float2(byte_f(nz4, k), byte_f(fz4, k)), make_float2(az, az), make_float2(bnz, bfz));
+    const float tnx = tx.x, tfx = tx.y, tny = ty.x, tfy = ty.y, tnz = tz.x, tfz = tz.y;
+#else
     const float tnx = __fmaf_rn(byte_f(nx4, k), ax, bnx), tfx = __fmaf_rn(byte_f(fx4, k), ax, bfx);
     const float tny = __fmaf_rn(byte_f(ny4, k), ay, bny), tfy = __fmaf_rn(byte_f(fy4, k), ay, bfy);
     const float tnz = __fmaf_rn(byte_f(nz4, k), az, bnz), tfz = __fmaf_rn(byte_f(fz4, k), az, bfz);
+#endif
     const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tnear));
     const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, tbest));
     if (tmin <= tmax) hitmask |= ((child_bits4 >> (8 * k)) & 0xffu) << ((bit_index4 >> (8 * k)) & 0xffu);
@@ -168,6 +190,67 @@ __device__ __forceinline__ void stack_push(const SceneParams &P, TravState &s, u
   else *P.error_flag = 1;
 }
 
+// Test the 8 quantised child boxes of one node against the ray: `bit` (24..31) selects a hit child of the node
+// group (child_base, hits_imask); tbest = current upper end of the interval.  Returns the node group and the
+// primitive group of that node.  No traversal state is touched (also used by the generation kernel's cull).
+__device__ __forceinline__ void node_eval(const SceneParams &P, const RayCtx &rc, unsigned child_base, unsigned hits_imask, int bit, float tb,
+                                          uint2 &ng_out, uint2 &tg_out) {
+  const unsigned slot = (unsigned)(bit - 24) ^ (rc.octinv4 & 7u);
+  const unsigned rel = __popc(hits_imask & ~(0xffffffffu << slot));
+  const uint4 *np = reinterpret_cast<const uint4 *>(P.nodes + (child_base + rel));
+  const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+  // slab coefficients in the node's quantisation frame: t = q * a + b
+  const float ax0 = __uint_as_float((n0.w & 0xffu) << 23) * rc.idx, ay0 = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * rc.idy,
+              az0 = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * rc.idz;
+  const float bx0 = (__uint_as_float(n0.x) - rc.org.x) * rc.idx, by0 = (__uint_as_float(n0.y) - rc.org.y) * rc.idy,
+              bz0 = (__uint_as_float(n0.z) - rc.org.z) * rc.idz;
+#if GXY_BOX_CONV == 0
+  const float ax = ax0, ay = ay0, az = az0, bx = bx0, by = by0, bz = bz0;
+  // rounding of (q*a + b) against the exact plane distance is below 2^-24 * (4|b| + 510|a|)
+  // (reciprocal, difference, product, fma): widen the interval by 4e-7 * (|b| + 255|a|) per axis
+  const float Ex = 4e-7f * __fmaf_rn(255.f, fabsf(ax), fabsf(bx)), Ey = 4e-7f * __fmaf_rn(255.f, fabsf(ay), fabsf(by)),
+              Ez = 4e-7f * __fmaf_rn(255.f, fabsf(az), fabsf(bz));
+  const float bnx = bx - Ex, bny = by - Ey, bnz = bz - Ez, bfx = bx + Ex, bfy = by + Ey, bfz = bz + Ez;
+#else
+  // byte_f() yields f = 128 + q/256: t = f*(256 a) + (b - 32768 a).  256a is exact; the folded constant rounds once more,
+  // by at most ulp(|b| + 32768|a|)/2 <= 6e-8|b| + |a|/512.  Total: (2.4e-7 + 6e-8)|b| + (3.1e-5 + 1/512)|a| < 5e-7|b| + 0.0021|a|,
+  // applied with directed rounding because it is of the order of one ulp of the folded constant.
+  const float ax = 256.f * ax0, ay = 256.f * ay0, az = 256.f * az0;
+  const float bx = __fmaf_rn(-32768.f, ax0, bx0), by = __fmaf_rn(-32768.f, ay0, by0), bz = __fmaf_rn(-32768.f, az0, bz0);
+  const float Ex = __fmaf_rn(0.0021f, fabsf(ax0), 5e-7f * fabsf(bx0)), Ey = __fmaf_rn(0.0021f, fabsf(ay0), 5e-7f * fabsf(by0)),
+              Ez = __fmaf_rn(0.0021f, fabsf(az0), 5e-7f * fabsf(bz0));
+  const float bnx = __fadd_rd(bx, -Ex), bny = __fadd_rd(by, -Ey), bnz = __fadd_rd(bz, -Ez);
+  const float bfx = __fadd_ru(bx, Ex), bfy = __fadd_ru(by, Ey), bfz = __fadd_ru(bz, Ez);
+#endif
+  const bool negx = rc.idx < 0.f, negy = rc.idy < 0.f, negz = rc.idz < 0.f;
+  // n2 = qlox[8] qloy[8]   n3 = qloz[8] qhix[8]   n4 = qhiy[8] qhiz[8]
+  const unsigned nx0 = negx ? n3.z : n2.x, nx1 = negx ? n3.w : n2.y, fx0 = negx ? n2.x : n3.z, fx1 = negx ? n2.y : n3.w;
+  const unsigned ny0 = negy ? n4.x : n2.z, ny1 = negy ? n4.y : n2.w, fy0 = negy ? n2.z : n4.x, fy1 = negy ? n2.w : n4.y;
+  const unsigned nz0 = negz ? n4.z : n3.x, nz1 = negz ? n4.w : n3.y, fz0 = negz ? n3.x : n4.z, fz1 = negz ? n3.y : n4.w;
+  unsigned hitmask = test_half(n1.z, rc.octinv4, nx0, ny0, nz0, fx0, fy0, fz0, ax, ay, az, bnx, bny, bnz, bfx, bfy, bfz, rc.tnear, tb);
+  hitmask |= test_half(n1.w, rc.octinv4, nx1, ny1, nz1, fx1, fy1, fz1, ax, ay, az, bnx, bny, bnz, bfx, bfy, bfz, rc.tnear, tb);
+  ng_out = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
+  tg_out = make_uint2(n1.y, hitmask & 0x00ffffffu);
+}
+
+// Conservative cull (generation kernel): false only if the ray (interval of rc) cannot reach any primitive --
+// no child box of the root is hit, or none of the boxes one level below those.  Box tests are conservative
+// (see above), so a culled ray has no candidate and the full traversal would return "no hit".
+__device__ __forceinline__ bool may_hit_anything(const SceneParams &P, const RayCtx &rc) {
+  uint2 ng, tg;
+  node_eval(P, rc, 0u, 0x80000000u, 31, rc.tfar, ng, tg);
+  if (tg.y != 0u) return true;
+  unsigned pending = ng.y;
+  while (pending > 0x00ffffffu) {
+    const int bit = 31 - __clz((int)pending);
+    pending &= ~(1u << bit);
+    uint2 ng2, tg2;
+    node_eval(P, rc, ng.x, ng.y, bit, rc.tfar, ng2, tg2);
+    if (tg2.y != 0u || ng2.y > 0x00ffffffu) return true;
+  }
+  return false;
+}
+
 // Node phase: pop the nearest unvisited internal child of the node group (requires s.ng.y > 0x00ffffff)
 // and test its 8 children -> new node group + primitive group.
 // PREFETCH: 0 none; 1 = L2 prefetch of the primitive records of the new group and of the node that
@@ -179,33 +262,10 @@ __device__ __forceinline__ void node_step(const SceneParams &P, const RayCtx &rc
   const int bit = 31 - __clz((int)hits_imask);
   s.ng.y &= ~(1u << bit);
   if (s.ng.y > 0x00ffffffu) stack_push(P, s, s.ng, stack, lstack);  // siblings left: the group goes to the stack
-  const unsigned slot = (unsigned)(bit - 24) ^ (rc.octinv4 & 7u);
-  const unsigned rel = __popc(hits_imask & ~(0xffffffffu << slot));
-  const uint4 *np = reinterpret_cast<const uint4 *>(P.nodes + (s.ng.x + rel));
-  const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
 #ifdef GXY_TRAV_COUNTERS
   s.n_nodes++;
 #endif
-  // slab coefficients in the node's quantisation frame: t = q * a + b
-  const float ax = __uint_as_float((n0.w & 0xffu) << 23) * rc.idx, ay = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * rc.idy,
-              az = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * rc.idz;
-  const float bx = (__uint_as_float(n0.x) - rc.org.x) * rc.idx, by = (__uint_as_float(n0.y) - rc.org.y) * rc.idy,
-              bz = (__uint_as_float(n0.z) - rc.org.z) * rc.idz;
-  // rounding of (q*a + b) against the exact plane distance is below 2^-24 * (4|b| + 510|a|)
-  // (reciprocal, difference, product, fma): widen the interval by 4e-7 * (|b| + 255|a|) per axis
-  const float Ex = 4e-7f * __fmaf_rn(255.f, fabsf(ax), fabsf(bx)), Ey = 4e-7f * __fmaf_rn(255.f, fabsf(ay), fabsf(by)),
-              Ez = 4e-7f * __fmaf_rn(255.f, fabsf(az), fabsf(bz));
-  const float bnx = bx - Ex, bny = by - Ey, bnz = bz - Ez, bfx = bx + Ex, bfy = by + Ey, bfz = bz + Ez;
-  const bool negx = rc.idx < 0.f, negy = rc.idy < 0.f, negz = rc.idz < 0.f;
-  // n2 = qlox[8] qloy[8]   n3 = qloz[8] qhix[8]   n4 = qhiy[8] qhiz[8]
-  const unsigned nx0 = negx ? n3.z : n2.x, nx1 = negx ? n3.w : n2.y, fx0 = negx ? n2.x : n3.z, fx1 = negx ? n2.y : n3.w;
-  const unsigned ny0 = negy ? n4.x : n2.z, ny1 = negy ? n4.y : n2.w, fy0 = negy ? n2.z : n4.x, fy1 = negy ? n2.w : n4.y;
-  const unsigned nz0 = negz ? n4.z : n3.x, nz1 = negz ? n4.w : n3.y, fz0 = negz ? n3.x : n4.z, fz1 = negz ? n3.y : n4.w;
-  const float tb = s.best_t;
-  unsigned hitmask = test_half(n1.z, rc.octinv4, nx0, ny0, nz0, fx0, fy0, fz0, ax, ay, az, bnx, bny, bnz, bfx, bfy, bfz, rc.tnear, tb);
-  hitmask |= test_half(n1.w, rc.octinv4, nx1, ny1, nz1, fx1, fy1, fz1, ax, ay, az, bnx, bny, bnz, bfx, bfy, bfz, rc.tnear, tb);
-  s.ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
-  s.tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
+  node_eval(P, rc, s.ng.x, hits_imask, bit, s.best_t, s.ng, s.tg);
   if (PREFETCH) {
     if (s.tg.y) {
       const char *first = reinterpret_cast<const char *>(P.prims + (s.tg.x + (unsigned)(__ffs((int)s.tg.y) - 1)));
