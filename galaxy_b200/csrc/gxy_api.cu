@@ -19,6 +19,35 @@
 using namespace gxy;
 
 #include <chrono>
+// GXY_PROFILE=1: named CUDA events after the launches of a frame (device timeline, printed per rank at the end of the frame)
+static std::vector<std::pair<const char *, cudaEvent_t>> g_timeline;
+static bool timeline_on() { const char *e = getenv("GXY_PROFILE"); return e && atoi(e); }
+namespace gxy {
+void gxy_timeline_mark(const char *name, cudaStream_t st) {
+  if (!timeline_on()) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_timeline.push_back(std::make_pair(name, e));
+}
+}  // namespace gxy
+static void timeline_print(int rank) {
+  if (g_timeline.empty()) return;
+  std::string line = "[timeline rank " + std::to_string(rank) + "]";
+  float prev = 0.f;
+  for (size_t i = 1; i < g_timeline.size(); i++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_timeline[0].second, g_timeline[i].second);
+    char buf[96];
+    snprintf(buf, sizeof buf, " %s %.3f(+%.3f)", g_timeline[i].first, ms, ms - prev);
+    line += buf;
+    prev = ms;
+  }
+  fprintf(stderr, "%s\n", line.c_str());
+  for (auto &e : g_timeline) cudaEventDestroy(e.second);
+  g_timeline.clear();
+}
+
 struct PhaseTimer {  // GXY_PROFILE=1: host wall-clock per phase of gxy_render (each mark synchronises nothing)
   bool on;
   std::chrono::steady_clock::time_point t0;
@@ -225,6 +254,7 @@ struct gxy_vis {
   RayBuf cur, next, send, recv, hits;
   Scratch<unsigned long long> fq;  // FusedQueues of the fused frame path
   Scratch<unsigned> rawhits;
+  Scratch<unsigned char> proxies;  // peer path: the PartProxy of every rank (launch_proxy_gather)
   Scratch<int> hit_index, block_sums, small;  // small: nhit, counts, offsets, cursor ...
   Scratch<unsigned long long> counters;       // [0] terminated [1] samples
   Scratch<float> fb, fb_tmp;
@@ -841,7 +871,8 @@ static int ensure_peer_arena(gxy_context *c, unsigned npix, unsigned inbox_cap) 
   memset(&T, 0, sizeof T);
   T.rank = c->rank; T.nranks = c->nranks; T.inbox_cap = inbox_cap; T.npix = npix;
   auto align = [](unsigned long long x) { return (x + 255ull) & ~255ull; };
-  T.off_fb = sizeof(PeerCtrl);
+  T.off_proxy = sizeof(PeerCtrl);
+  T.off_fb = align(T.off_proxy + sizeof(PartProxy));
   T.off_final = align(T.off_fb + (unsigned long long)npix * 16ull);
   T.off_inbox[0] = align(T.off_final + (unsigned long long)npix * 16ull);
   T.off_inbox[1] = align(T.off_inbox[0] + (unsigned long long)inbox_cap * 64ull);
@@ -893,11 +924,14 @@ static int ensure_peer_arena(gxy_context *c, unsigned npix, unsigned inbox_cap) 
 
 // The frame on one rank of a multi-process run, geometry-only Visualization: a fixed schedule of kernel
 // launches with no host round trip until the end of the frame.
-//   wave 0     generate -> trace primaries -> shade hits -> AO/shadow rays; rays that leave go to peer inboxes[0]
-//   wave k>=1  trace inbox[(k-1)&1] -> shade the new hits -> their AO/shadow rays; leavers go to inboxes[k&1]
-// each wave ends with the flag barrier.  A ray crosses at most H = sum(grid_i - 1) partition faces and so does
-// each of its secondaries: 2H waves after wave 0 suffice for a regular grid; the global in-flight count the last
-// barrier leaves behind is checked anyway and further waves run until it is zero.
+//   wave 0     generate -> trace primaries -> shade hits; rays that leave go to peer inboxes[0]
+//   wave k>=1  AO/shadow rays of the hits of wave k-1 -> trace inbox[(k-1)&1] -> shade the new hits; leavers go to inboxes[k&1]
+// each wave ends with the flag barrier.  The secondaries of a wave's hits run one wave later on purpose: the rays a rank
+// forwards while tracing reach its neighbours one barrier earlier, so a back partition traces the forwarded primaries
+// while the front partition is busy with its AO/shadow rays (measured on 2 GPUs: the two phases used to run back to
+// back).  A ray crosses at most H = sum(grid_i - 1) partition faces and so does each of its secondaries: 2H + 1 waves
+// after wave 0 suffice for a regular grid; the global count of outstanding work (rays in flight + hits without
+// secondaries) the last barrier leaves behind is checked anyway and further waves run until it is zero.
 static int render_peer(gxy_vis *v, const DevCamera &C, const DevLights &L, const gxy_lighting &lights, int w, int h, float epsilon,
                        int n_sec_per_hit, gxy_stats *stats) {
   gxy_context *c = v->ctx;
@@ -908,7 +942,8 @@ static int render_peer(gxy_vis *v, const DevCamera &C, const DevLights &L, const
   gxy_stats S;
   memset(&S, 0, sizeof S);
   if (v->hits.reserve(npix, false, st) || v->fq.reserve(sizeof(FusedQueues) / 8) || v->rawhits.reserve((size_t)6 * npix) ||
-      v->next.reserve(npix, false, st) || v->cur.reserve(64, false, st) || v->counters.reserve(4))
+      v->next.reserve(npix, false, st) || v->cur.reserve(64, false, st) || v->counters.reserve(4) ||
+      v->proxies.reserve(sizeof(PartProxy) * (size_t)c->nranks))
     return 1;
   float *fb = reinterpret_cast<float *>(A.base + T.off_fb);
   FusedQueues *q = reinterpret_cast<FusedQueues *>(v->fq.p);
@@ -918,8 +953,10 @@ static int render_peer(gxy_vis *v, const DevCamera &C, const DevLights &L, const
   GXY_CUDA(cudaEventCreate(&ev0));
   GXY_CUDA(cudaEventCreate(&ev1));
   GXY_CUDA(cudaEventRecord(ev0, st));
+  gxy_timeline_mark("start", st);
   GXY_CUDA(cudaMemsetAsync(fb, 0, sizeof(float) * 4 * npix, st));
   GXY_CUDA(cudaMemsetAsync(q, 0, sizeof(FusedQueues), st));
+  gxy_timeline_mark("memset", st);
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_events;
   auto ev_begin = [&]() -> int {
     cudaEvent_t ta, tb;
@@ -933,26 +970,27 @@ static int render_peer(gxy_vis *v, const DevCamera &C, const DevLights &L, const
     GXY_CUDA(cudaEventRecord(trace_events.back().second, st));
     return 0;
   };
-  // ---- wave 0
+  // ---- every rank publishes its partition proxy (box, neighbours, top of the BVH) and collects everybody's
+  const bool spawn = n_sec_per_hit > 0;
+  PartProxy *proxies = reinterpret_cast<PartProxy *>(v->proxies.p);
+  if (launch_proxy_publish(v->P, T, st)) return 1;
+  if (launch_wave_epilogue(T, q, ++A.epoch, -1, false, v->d_error, st)) return 1;
+  if (launch_proxy_gather(T, proxies, st)) return 1;
+  gxy_timeline_mark("proxies", st);
+  S.kernel_launches += 3;
+  // ---- wave 0: generation, trace of the primaries, shading of the hits (their AO/shadow rays follow in wave 1)
   if (ev_begin()) return 1;
-  if (launch_fused_primary(v->P, C, L, w, h, fb, v->next.v, v->rawhits.p, v->hits.v, v->cur.v, 0u, q, epsilon, &T, st)) return 1;
+  if (launch_fused_primary(v->P, C, L, w, h, fb, v->next.v, v->rawhits.p, v->hits.v, v->cur.v, 0u, q, epsilon, &T, proxies, st)) return 1;
   if (ev_end()) return 1;
   S.kernel_launches += 3;
-  if (n_sec_per_hit > 0) {
-    if (ev_begin()) return 1;
-    if (launch_fused_secondary(v->P, L, w, h, n_sec_per_hit, (long long)npix * n_sec_per_hit, fb, v->hits.v, v->cur.v, 0u, q, epsilon,
-                               !v->has_dvr, &T, 0, st))
-      return 1;
-    if (ev_end()) return 1;
-    S.kernel_launches += 1;
-  }
-  if (launch_wave_epilogue(T, q, ++A.epoch, -1, v->d_error, st)) return 1;
+  if (launch_wave_epilogue(T, q, ++A.epoch, -1, spawn, v->d_error, st)) return 1;
+  gxy_timeline_mark("barrier0", st);
   S.kernel_launches += 1;
   S.waves = 1;
   // ---- waves 1..: the bound first, then as long as anything is in flight anywhere
   int f[3];
   gxy_factor(c->nranks, f);
-  const int bound = 2 * ((f[0] - 1) + (f[1] - 1) + (f[2] - 1));
+  const int bound = 2 * ((f[0] - 1) + (f[1] - 1) + (f[2] - 1)) + (spawn ? 1 : 0);
   int k = 0;
   FusedQueues hq;
   while (true) {
@@ -961,31 +999,39 @@ static int render_peer(gxy_vis *v, const DevCamera &C, const DevLights &L, const
       k++;
       const int parity_in = (k - 1) & 1;
       if (ev_begin()) return 1;
-      if (launch_inbox_wave(v->P, L, T, parity_in, w, h, fb, v->rawhits.p, (unsigned)npix, v->hits.v, q, epsilon, !v->has_dvr, st)) return 1;
-      if (n_sec_per_hit > 0 &&
-          launch_fused_secondary(v->P, L, w, h, n_sec_per_hit, (long long)npix * n_sec_per_hit, fb, v->hits.v, v->cur.v, 0u, q, epsilon,
-                                 !v->has_dvr, &T, k & 1, st))
+      // AO/shadow rays of the hits the previous wave found (leavers go to inboxes[k&1]) ...
+      if (spawn && launch_fused_secondary(v->P, L, w, h, n_sec_per_hit, (long long)npix * n_sec_per_hit, fb, v->hits.v, v->cur.v, 0u, q, epsilon,
+                                          !v->has_dvr, &T, k & 1, st))
         return 1;
+      gxy_timeline_mark("secondary", st);
+      // ... and the rays the neighbours sent during the previous wave
+      if (launch_inbox_wave(v->P, L, T, parity_in, w, h, fb, v->rawhits.p, (unsigned)npix, v->hits.v, q, epsilon, !v->has_dvr, st)) return 1;
       if (ev_end()) return 1;
-      if (launch_wave_epilogue(T, q, ++A.epoch, parity_in, v->d_error, st)) return 1;
-      S.kernel_launches += 3 + (n_sec_per_hit > 0 ? 1 : 0);
+      gxy_timeline_mark("inbox+shade", st);
+      if (launch_wave_epilogue(T, q, ++A.epoch, parity_in, spawn, v->d_error, st)) return 1;
+      gxy_timeline_mark("barrier", st);
+      S.kernel_launches += 3 + (spawn ? 1 : 0);
       S.waves++;
     }
     GXY_CUDA(cudaMemcpyAsync(&hq, q, sizeof hq, cudaMemcpyDeviceToHost, st));
     GXY_CUDA(cudaStreamSynchronize(st));
     if (check_error_flag(v)) return 1;
     if (hq.global_pending == 0u) break;
-    GXY_CHECK(k < 4096, "peer wave loop does not terminate (%u rays in flight)", hq.global_pending);
+    GXY_CHECK(k < 4096, "peer wave loop does not terminate (%u units of work in flight)", hq.global_pending);
   }
   // ---- framebuffer: every rank sums its slice of all partial images into the owner's final image
+  gxy_timeline_mark("hostsync", st);
   if (launch_fb_gather(T, st)) return 1;
-  if (launch_wave_epilogue(T, q, ++A.epoch, -1, v->d_error, st)) return 1;
+  gxy_timeline_mark("fb_gather", st);
+  if (launch_wave_epilogue(T, q, ++A.epoch, -1, false, v->d_error, st)) return 1;
+  gxy_timeline_mark("barrier_end", st);
   S.kernel_launches += 2;
   GXY_CUDA(cudaEventRecord(ev1, st));
   GXY_CUDA(cudaEventSynchronize(ev1));
   cudaEventElapsedTime(&S.device_ms, ev0, ev1);
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
+  timeline_print(c->rank);
   for (auto &e : trace_events) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e.first, e.second);
@@ -997,7 +1043,7 @@ static int render_peer(gxy_vis *v, const DevCamera &C, const DevLights &L, const
   S.primary_rays = (long long)hq.n_generated;
   S.ao_rays = (long long)hq.n_hits * lights.n_ao;
   S.shadow_rays = (long long)hq.n_hits * (lights.shadows ? lights.n_lights : 0);
-  S.forwarded_rays = (long long)hq.n_spill;
+  S.forwarded_rays = (long long)hq.n_spill + (long long)hq.n_virtual;
   S.terminated_rays = (long long)hq.n_terminated;
   S.traced_rays = (long long)hq.n_generated + (long long)hq.n_hits * n_sec_per_hit + (long long)hq.n_inbox;
   S.nodes_visited = (long long)hq.nodes;
@@ -1077,7 +1123,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
     GXY_CUDA(cudaMemsetAsync(v->counters.p, 0, sizeof(unsigned long long) * 4, st));
   }
   if (fused) {
-    static_assert(sizeof(FusedQueues) == 80, "FusedQueues layout");
+    static_assert(sizeof(FusedQueues) == 96, "FusedQueues layout");
     std::vector<FusedQueues> fq(nparts);
     std::vector<bool> can_spill(nparts, false);
     // ---- primary rays: generate -> trace -> light -> framebuffer, hit records for the secondaries
@@ -1095,7 +1141,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       GXY_CUDA(cudaEventCreate(&tb));
       GXY_CUDA(cudaEventRecord(ta, st));
       if (launch_fused_primary(v->P, C, L, w, h, v->fb.p, v->next.v, v->rawhits.p, v->hits.v, v->cur.v,
-                               can_spill[p] ? (unsigned)v->cur.cap : 0u, reinterpret_cast<FusedQueues *>(v->fq.p), epsilon, nullptr, st))
+                               can_spill[p] ? (unsigned)v->cur.cap : 0u, reinterpret_cast<FusedQueues *>(v->fq.p), epsilon, nullptr, nullptr, st))
         return 1;
       GXY_CUDA(cudaEventRecord(tb, st));
       trace_events.push_back(std::make_pair(ta, tb));

@@ -94,12 +94,10 @@ __device__ __forceinline__ void peer_push(const PeerTable &T, int parity, unsign
 // clipped to the local box and tested against the top two levels of the BVH (may_hit_anything): rays that can
 // reach no primitive are finished here at full SIMD width exactly as the trace kernel finishes a ray without a
 // hit (term BOUNDARY/TIMEOUT -> Classify: TERMINATED with colour 0, or on to the neighbour partition); the
-// others are appended (unordered) to `out` (columns ox..dz x y; t = 0, tMax = FLT_MAX, type PRIMARY implied).
-template <bool PEER>
+// others are appended (unordered) to `out` (columns ox..dz t x y; tMax = FLT_MAX, type PRIMARY implied).
 __global__ void __launch_bounds__(256)
     gen_primary_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevCamera C, int w, int h, int tiles_x,
-                       unsigned n_queue, Rays out, Rays spill, unsigned spill_cap, FusedQueues *__restrict__ q,
-                       const __grid_constant__ PeerTable T) {
+                       unsigned n_queue, Rays out, Rays spill, unsigned spill_cap, FusedQueues *__restrict__ q) {
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
   bool kept = false, queued = false;
@@ -116,7 +114,7 @@ __global__ void __launch_bounds__(256)
     RayCtx rc;
     TravState st;
     PendingRay pr;
-    queued = setup_ray_values(P, 0, true, o3, d3, 0.f, FLT_MAX, 0, rc, st, pr) && may_hit_anything(P, rc);
+    queued = setup_ray_values(P, 0, true, o3, d3, 0.f, FLT_MAX, 0, rc, st, pr) && may_hit_anything(P.nodes, rc);
     if (!queued) {
       ray_t = rc.tfar;
       if (ray_t == pr.tExit) term |= RAY_BOUNDARY;
@@ -135,18 +133,126 @@ __global__ void __launch_bounds__(256)
   if (queued) {
     out.ox[pos] = o3.x; out.oy[pos] = o3.y; out.oz[pos] = o3.z;
     out.dx[pos] = d3.x; out.dy[pos] = d3.y; out.dz[pos] = d3.z;
+    out.t[pos] = 0.f;
     out.x[pos] = x; out.y[pos] = y;
   }
-  if (PEER) {
-    const unsigned sm = __ballot_sync(FULLMASK, do_spill);
-    if (sm && lane == 0u) atomicAdd(&q->n_spill, (unsigned)__popc(sm));
-    peer_push(T, 0, FULLMASK, lane, do_spill, cls, o3, d3, 0.f, 0.f, 0.f, 0.f, ray_t, FLT_MAX, x, y, RAY_PRIMARY, term, P.error_flag);
-  } else {
-    const unsigned sp = group_append(FULLMASK, lane, do_spill, &q->n_spill);
-    if (do_spill) {
-      if (sp < spill_cap) write_spill(spill, sp, o3, d3, 0.f, 0.f, 0.f, 0.f, ray_t, FLT_MAX, x, y, RAY_PRIMARY, term, cls);
-      else *P.error_flag = 3;
+  const unsigned sp = group_append(FULLMASK, lane, do_spill, &q->n_spill);
+  if (do_spill) {
+    if (sp < spill_cap) write_spill(spill, sp, o3, d3, 0.f, 0.f, 0.f, 0.f, ray_t, FLT_MAX, x, y, RAY_PRIMARY, term, cls);
+    else *P.error_flag = 3;
+  }
+}
+
+// The same for one rank of a multi-process frame.  Every rank holds the PartProxy of every partition (box, neighbours,
+// top two BVH levels), so it can follow a pixel's ray through the partitions exactly as generation -> trace -> Classify
+// -> forward would (Camera.cpp:431-441, TraceRays.ispc:377-418, Renderer.cpp:304-454), for as long as the ray cannot hit
+// anything: the partition that the ray enters first originates it (statistics), every partition it leaves without a
+// possible hit forwards it (statistics), and the first partition whose proxy it MAY hit takes it into its trace queue
+// with t = the exit distance of the partition before, which is what the forwarded record would have carried.  All ranks
+// evaluate the same arithmetic on the same proxies, so exactly one rank queues (or terminates) each ray and nothing
+// crosses NVLink for the ~80 % of the primaries that only pass through.  Rays that may hit a partition but do not are
+// forwarded for real by the trace kernel.
+__global__ void __launch_bounds__(256)
+    gen_primary_peer_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevCamera C, int w, int h, int tiles_x,
+                            unsigned n_queue, Rays out, unsigned queue_cap, FusedQueues *__restrict__ q, int me, int nranks,
+                            const PartProxy *__restrict__ prox) {
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31u;
+  int x = 0, y = 0;
+  float3 o3 = f3(0.f, 0.f, 0.f), d3 = f3(0.f, 0.f, 0.f);
+  float gmin = 0.f;
+  bool in_data = false;
+  if (idx < n_queue) {
+    tile_pixel(idx, tiles_x, x, y);
+    in_data = x < w && y < h && camera_ray(P, C, x, y, o3, d3, gmin);
+  }
+  unsigned n_gen = 0u, n_fwd = 0u, n_term = 0u;
+  bool queued = false;
+  float t_queued = 0.f;
+  if (in_data) {
+    for (int s = 0; s < nranks; s++) {
+      if (!first_brick(prox[s].lmin, prox[s].lmax, o3, d3, gmin)) continue;
+      if (s == me) n_gen++;
+      int cur = s;
+      float t0 = 0.f;
+      for (int hops = 0;; hops++) {
+        const PartProxy &pp = prox[cur];
+        RayCtx rc;
+        TravState st;
+        PendingRay pr;
+        const bool may = setup_ray_box(pp.lmin, pp.lmax, pp.has_prims != 0, 0, true, o3, d3, t0, FLT_MAX, 0, rc, st, pr) &&
+                         may_hit_anything(pp.nodes, rc);
+        if (may || hops >= 2 * nranks) {  // (the hop bound only guards against a cyclic neighbour table)
+          if (cur == me && !queued) { queued = true; t_queued = t0; }
+          else if (cur == me) {  // a pixel that two partitions both originate (boundary tie) and both rays end up here
+            const unsigned pos2 = atomicAdd(&q->n_primary32, 1u);
+            if (pos2 >= queue_cap) { *P.error_flag = 3; break; }
+            out.ox[pos2] = o3.x; out.oy[pos2] = o3.y; out.oz[pos2] = o3.z;
+            out.dx[pos2] = d3.x; out.dy[pos2] = d3.y; out.dz[pos2] = d3.z;
+            out.t[pos2] = t0;
+            out.x[pos2] = x; out.y[pos2] = y;
+          }
+          break;
+        }
+        const float ray_t = rc.tfar;
+        int term = 0;
+        if (ray_t == pr.tExit) term |= RAY_BOUNDARY;
+        else if (ray_t == FLT_MAX) term |= RAY_TIMEOUT;
+        const int cls = classify_box(pp.lmin, pp.lmax, pp.neighbors, RAY_PRIMARY, term, o3.x, o3.y, o3.z, d3.x, d3.y, d3.z);
+        if (cls == CLS_TERMINATED) { if (cur == me) n_term++; break; }
+        if (cls < 0 || cls >= nranks) break;  // KEEP_HERE without a hit: the reference drops it too
+        if (cur == me) n_fwd++;
+        t0 = ray_t;
+        cur = cls;
+      }
     }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    n_gen += __shfl_down_sync(FULLMASK, n_gen, off);
+    n_fwd += __shfl_down_sync(FULLMASK, n_fwd, off);
+    n_term += __shfl_down_sync(FULLMASK, n_term, off);
+  }
+  if (lane == 0u) {
+    if (n_gen) atomicAdd(&q->n_generated, n_gen);
+    if (n_fwd) atomicAdd(&q->n_virtual, n_fwd);
+    if (n_term) atomicAdd(&q->n_terminated, (unsigned long long)n_term);
+  }
+  const unsigned pos = group_append(FULLMASK, lane, queued, &q->n_primary32);
+  if (queued && pos >= queue_cap) { *P.error_flag = 3; queued = false; }
+  if (queued) {
+    out.ox[pos] = o3.x; out.oy[pos] = o3.y; out.oz[pos] = o3.z;
+    out.dx[pos] = d3.x; out.dy[pos] = d3.y; out.dz[pos] = d3.z;
+    out.t[pos] = t_queued;
+    out.x[pos] = x; out.y[pos] = y;
+  }
+}
+
+// this rank's PartProxy, written into its own arena (read by every rank after the next flag barrier)
+__global__ void __launch_bounds__(32) proxy_publish_kernel(const __grid_constant__ SceneParams P, PartProxy *__restrict__ dst) {
+  const unsigned lane = threadIdx.x;
+  if (lane == 0u) {
+    dst->lmin = P.lmin; dst->lmax = P.lmax;
+    for (int f = 0; f < 6; f++) dst->neighbors[f] = P.neighbors[f];
+    dst->has_prims = P.n_prims > 0 ? 1 : 0;
+    dst->pad[0] = dst->pad[1] = dst->pad[2] = 0;
+  }
+  if (P.n_prims <= 0) return;
+  const WideNode root = P.nodes[0];
+  const unsigned n_inner = (unsigned)__popc((unsigned)root.imask);
+  if (lane == 0u) {
+    WideNode r = root;
+    r.child_base = 1u;
+    dst->nodes[0] = r;
+  } else if (lane <= 8u && lane - 1u < n_inner) {
+    dst->nodes[lane] = P.nodes[root.child_base + (lane - 1u)];
+  }
+}
+
+__global__ void __launch_bounds__(256) proxy_gather_kernel(const __grid_constant__ PeerTable T, PartProxy *__restrict__ out) {
+  constexpr unsigned W = sizeof(PartProxy) / 16u;
+  for (unsigned i = threadIdx.x; i < W * (unsigned)T.nranks; i += blockDim.x) {
+    const unsigned r = i / W, k = i - r * W;
+    reinterpret_cast<uint4 *>(out + r)[k] = reinterpret_cast<const uint4 *>(T.base[r] + T.off_proxy)[k];
   }
 }
 
@@ -231,8 +337,8 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
           const unsigned my = fbase + (unsigned)__popc(m_idle & lt_mask);
           ex_local = fbase + cnt >= n_queue;
           if (my < n_queue)
-            trav = setup_ray_values(P, (int)my, true, f3(R.ox[my], R.oy[my], R.oz[my]), f3(R.dx[my], R.dy[my], R.dz[my]), 0.f, FLT_MAX, 0, rc,
-                                    st, pr);
+            trav = setup_ray_values(P, (int)my, true, f3(R.ox[my], R.oy[my], R.oz[my]), f3(R.dx[my], R.dy[my], R.dz[my]), R.t[my], FLT_MAX, 0,
+                                    rc, st, pr);
         }
       }
       exhausted = exhausted || __any_sync(FULLMASK, ex_local);
@@ -355,8 +461,11 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
   __syncthreads();
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const unsigned h0 = q->hits_done;  // hit records [h0, q->n_hits) are this wave's
-  const unsigned n_hits = q->n_hits - h0;
+  // hit records of this launch: the wave's own [hits_done, n_hits) on the single-process path; on the peer path the
+  // records of the PREVIOUS wave [sec_lo, sec_hi) (wave_epilogue_kernel), so that the rays a rank forwards while
+  // tracing become visible to its neighbours one barrier before the rank starts on its own secondaries
+  const unsigned h0 = PEER ? q->sec_lo : q->hits_done;
+  const unsigned n_hits = (PEER ? q->sec_hi : q->n_hits) - h0;
   if (n_hits == 0u) return;
   const unsigned long long total64 = (unsigned long long)n_hits * (unsigned)nsec;
   const unsigned n_queue = total64 > 0xfffffff0ull ? 0xfffffff0u : (unsigned)total64;
@@ -576,13 +685,18 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // reference's busy/idle termination tree (RenderingSet.cpp:289-589).
 __global__ void __launch_bounds__(32)
     wave_epilogue_kernel(const __grid_constant__ PeerTable T, FusedQueues *__restrict__ q, unsigned epoch, int parity_consumed,
-                         unsigned long long timeout_ns, int *__restrict__ error_flag) {
+                         int hits_spawn, unsigned long long timeout_ns, int *__restrict__ error_flag) {
   const unsigned lane = threadIdx.x;
   PeerCtrl *mine = peer_ctrl(T, T.rank);
   unsigned sent = 0u;
   if (lane == 0u) {
+    // work this wave leaves behind for a later one: rays sent to other ranks, and surface hits whose AO/shadow rays
+    // are generated in the next wave
     sent = q->n_spill - q->spill_done;
+    if (hits_spawn) sent += q->n_hits - q->hits_done;
     q->spill_done = q->n_spill;
+    q->sec_lo = q->sec_hi;
+    q->sec_hi = q->n_hits;
     q->hits_done = q->n_hits;
     q->sec_head = 0u;
     q->inbox_head = 0u;
@@ -652,14 +766,16 @@ static int fetch_threshold(const char *env) {
 }
 
 int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLights &L, int w, int h, float *fb, Rays prim, unsigned *raw,
-                         Rays hits, Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, const PeerTable *peer, cudaStream_t st) {
+                         Rays hits, Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, const PeerTable *peer,
+                         const PartProxy *proxies, cudaStream_t st) {
   if (ensure_ao_tables()) return 1;
   const int tiles_x = (w + 7) / 8, tiles_y = (h + 3) / 4;
   const unsigned n_queue = (unsigned)tiles_x * (unsigned)tiles_y * 32u;
   const unsigned npix = (unsigned)w * (unsigned)h;
   const PeerTable T = peer ? *peer : no_peers();
-  if (peer) gen_primary_kernel<true><<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, n_queue, prim, spill, spill_cap, q, T);
-  else gen_primary_kernel<false><<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, n_queue, prim, spill, spill_cap, q, T);
+  if (peer) gen_primary_peer_kernel<<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, n_queue, prim, npix, q, T.rank, T.nranks, proxies);
+  else gen_primary_kernel<<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, n_queue, prim, spill, spill_cap, q);
+  gxy_timeline_mark("gen", st);
   const unsigned needed = (npix + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
   const unsigned blocks = std::min<unsigned>(needed, (unsigned)sm_count() * 8u);
 #define GXY_LAUNCH_P(FT)                                                                                                              \
@@ -675,6 +791,7 @@ int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLigh
     default: GXY_LAUNCH_P(12); break;
   }
 #undef GXY_LAUNCH_P
+  gxy_timeline_mark("primary", st);
   shade_hits_kernel<false><<<(npix + 255) / 256, 256, 0, st>>>(P, L, prim, nullptr, raw, npix, w, reinterpret_cast<float4 *>(fb), hits, q, epsilon);
   GXY_CUDA(cudaGetLastError());
   return 0;
@@ -715,6 +832,7 @@ int launch_inbox_wave(const SceneParams &P, const DevLights &L, const PeerTable 
   const unsigned blocks = (unsigned)sm_count() * 8u;
   inbox_trace_kernel<12, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, T, parity_in, w, reinterpret_cast<float4 *>(fb), raw, raw_stride, q,
                                                                    anyhit ? 1 : 0);
+  gxy_timeline_mark("inbox", st);
   const float4 *inbox = reinterpret_cast<const float4 *>(T.base[T.rank] + T.off_inbox[parity_in]);
   shade_hits_kernel<true><<<(unsigned)sm_count() * 4u, 256, 0, st>>>(P, L, hits, inbox, raw, raw_stride, w, reinterpret_cast<float4 *>(fb), hits, q,
                                                                     epsilon);
@@ -722,10 +840,23 @@ int launch_inbox_wave(const SceneParams &P, const DevLights &L, const PeerTable 
   return 0;
 }
 
-int launch_wave_epilogue(const PeerTable &T, FusedQueues *q, unsigned epoch, int parity_consumed, int *error_flag, cudaStream_t st) {
+int launch_wave_epilogue(const PeerTable &T, FusedQueues *q, unsigned epoch, int parity_consumed, bool hits_spawn, int *error_flag,
+                         cudaStream_t st) {
   unsigned long long timeout_ns = 30ull * 1000000000ull;
   if (const char *e = getenv("GXY_PEER_TIMEOUT_MS")) timeout_ns = (unsigned long long)atoll(e) * 1000000ull;
-  wave_epilogue_kernel<<<1, 32, 0, st>>>(T, q, epoch, parity_consumed, timeout_ns, error_flag);
+  wave_epilogue_kernel<<<1, 32, 0, st>>>(T, q, epoch, parity_consumed, hits_spawn ? 1 : 0, timeout_ns, error_flag);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_proxy_publish(const SceneParams &P, const PeerTable &T, cudaStream_t st) {
+  proxy_publish_kernel<<<1, 32, 0, st>>>(P, reinterpret_cast<PartProxy *>(T.base[T.rank] + T.off_proxy));
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_proxy_gather(const PeerTable &T, PartProxy *out, cudaStream_t st) {
+  proxy_gather_kernel<<<1, 256, 0, st>>>(T, out);
   GXY_CUDA(cudaGetLastError());
   return 0;
 }

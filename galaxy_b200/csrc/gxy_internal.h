@@ -39,7 +39,9 @@ struct FusedQueues {  // device memory, zeroed at the start of a frame
   unsigned pixel_head, n_hits, n_spill, sec_head;
   unsigned n_primary32, hits_done, inbox_head, spill_done;
   unsigned long long n_terminated, nodes, prims, n_inbox;
-  unsigned global_pending, n_generated, pad[2];  // n_generated: kept primaries (n_primary32 = those queued for the trace kernel)
+  unsigned global_pending, n_generated;  // n_generated: kept primaries (n_primary32 = those queued for the trace kernel)
+  unsigned sec_lo, sec_hi;               // peer path: hit records [sec_lo, sec_hi) get their AO/shadow rays in the current wave
+  unsigned n_virtual, pad[3];            // peer path: forwards decided at generation from the partition proxies (no record sent)
 };
 
 // ---- peer arenas: the one-process-per-GPU exchange without NCCL on the data path -------------------
@@ -57,11 +59,23 @@ struct PeerCtrl {  // first 256 bytes of every arena
   unsigned pad[14];
 };
 static_assert(sizeof(PeerCtrl) == 256, "PeerCtrl layout");
+// What a rank publishes about its partition so that every other rank can tell, without communication, that a primary
+// ray cannot hit anything there: the partition box, its neighbour table and the top two levels of its BVH (root, patched
+// to child_base = 1, followed by its internal children in slot order).  See gen_primary_peer_kernel (gxy_fused.cu).
+struct PartProxy {
+  float3 lmin, lmax;
+  int neighbors[6];
+  int has_prims;
+  int pad[3];
+  WideNode nodes[9];
+};
+static_assert(sizeof(PartProxy) == 64 + 9 * 80, "PartProxy layout");
 struct PeerTable {  // kernel parameter: every rank's arena as mapped in THIS process (base[rank] = own)
   int rank, nranks;
   unsigned inbox_cap;  // 64-byte records per inbox
   unsigned npix;
   unsigned long long off_fb, off_final, off_inbox[2];  // byte offsets inside an arena, the same on every rank
+  unsigned long long off_proxy;                        // this rank's PartProxy
   char *base[GXY_MAX_RANKS];
 };
 // inbox record: 4 x float4 = (ox oy oz dx) (dy dz t tMax) (r g b o) (x y type term)
@@ -70,8 +84,15 @@ struct PeerTable {  // kernel parameter: every rank's arena as mapped in THIS pr
 // the hits (1 kernel); hit records go to `hits` (columns ox..dz t nx..nz sr..sb o x y), rays bound for
 // a neighbour to `spill` (peer == NULL) or to the neighbour's inbox[0] (peer != NULL)
 // prim: list for the generated rays (>= w*h), raw: 6*w*h words of scratch, hits: >= w*h records
+// peer != NULL: proxies = the PartProxy of every rank in local memory (launch_proxy_gather); rays are then originated by the
+// first partition on their path whose proxy they may hit instead of being forwarded through the ones they cannot
 int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLights &L, int w, int h, float *fb, Rays prim, unsigned *raw,
-                         Rays hits, Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, const PeerTable *peer, cudaStream_t st);
+                         Rays hits, Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, const PeerTable *peer,
+                         const PartProxy *proxies, cudaStream_t st);
+// write this rank's PartProxy into its arena; after the next flag barrier ...
+int launch_proxy_publish(const SceneParams &P, const PeerTable &T, cudaStream_t st);
+// ... copy every rank's published PartProxy (peer loads) into the local table `out` (nranks entries)
+int launch_proxy_gather(const PeerTable &T, PartProxy *out, cudaStream_t st);
 // AO + shadow rays of the hit records [q->hits_done, q->n_hits): generate -> trace -> classify -> framebuffer
 int launch_fused_secondary(const SceneParams &P, const DevLights &L, int w, int h, int nsec, long long max_rays, float *fb, Rays hits,
                            Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, bool anyhit, const PeerTable *peer, int parity_out,
@@ -81,9 +102,13 @@ int launch_fused_secondary(const SceneParams &P, const DevLights &L, int w, int 
 int launch_inbox_wave(const SceneParams &P, const DevLights &L, const PeerTable &T, int parity_in, int w, int h, float *fb, unsigned *raw,
                       unsigned raw_stride, Rays hits, FusedQueues *q, float epsilon, bool anyhit, cudaStream_t st);
 // end of a wave: queue bookkeeping, reset of the consumed inbox, flag barrier across ranks, global pending count
-int launch_wave_epilogue(const PeerTable &T, FusedQueues *q, unsigned epoch, int parity_consumed, int *error_flag, cudaStream_t st);
+int launch_wave_epilogue(const PeerTable &T, FusedQueues *q, unsigned epoch, int parity_consumed, bool hits_spawn, int *error_flag,
+                         cudaStream_t st);
 // sum of all partial framebuffers for this rank's slice of the image, written to the image owner (rank 0)
 int launch_fb_gather(const PeerTable &T, cudaStream_t st);
+
+// GXY_PROFILE=1: device timeline of a frame -- a named CUDA event after a launch; printed by the frame function
+void gxy_timeline_mark(const char *name, cudaStream_t st);
 
 // ---- BVH build (gxy_bvh.cu) -----------------------------------------------------------------
 struct GeomBuildInput {

@@ -54,8 +54,8 @@ struct PendingRay {
 };
 
 // clip to the local box (TraceRays.ispc:377-418) and start a traversal; returns false if the interval is empty
-__device__ __forceinline__ bool setup_ray_values(const SceneParams &P, int i, bool shadeFlag, float3 org, float3 dir, float ray_t0, float ray_t,
-                                                 int anyhit_secondary, RayCtx &rc, TravState &st, PendingRay &pr) {
+__device__ __forceinline__ bool setup_ray_box(float3 bmin, float3 bmax, bool has_prims, int i, bool shadeFlag, float3 org, float3 dir,
+                                              float ray_t0, float ray_t, int anyhit_secondary, RayCtx &rc, TravState &st, PendingRay &pr) {
   if (dir.x == 0.f) dir.x = 1e-6f;  // :377-379
   if (dir.y == 0.f) dir.y = 1e-6f;
   if (dir.z == 0.f) dir.z = 1e-6f;
@@ -64,8 +64,8 @@ __device__ __forceinline__ bool setup_ray_values(const SceneParams &P, int i, bo
   {
     const float rx = 1.0f / dir.x, ry = 1.0f / dir.y, rz = 1.0f / dir.z;
     rcp = f3(rx, ry, rz);
-    const float mnx = (P.lmin.x - org.x) * rx, mny = (P.lmin.y - org.y) * ry, mnz = (P.lmin.z - org.z) * rz;
-    const float mxx = (P.lmax.x - org.x) * rx, mxy = (P.lmax.y - org.y) * ry, mxz = (P.lmax.z - org.z) * rz;
+    const float mnx = (bmin.x - org.x) * rx, mny = (bmin.y - org.y) * ry, mnz = (bmin.z - org.z) * rz;
+    const float mxx = (bmax.x - org.x) * rx, mxy = (bmax.y - org.y) * ry, mxz = (bmax.z - org.z) * rz;
     tEntry = fmaxf(fminf(mnx, mxx), fmaxf(fminf(mny, mxy), fminf(mnz, mxz)));
     tExitVolume = fminf(fmaxf(mnx, mxx), fminf(fmaxf(mny, mxy), fmaxf(mnz, mxz)));
   }
@@ -80,7 +80,11 @@ __device__ __forceinline__ bool setup_ray_values(const SceneParams &P, int i, bo
   pr.opaque = false;
   // an empty interval cannot accept any candidate (both primitive tests need tnear < t <= tfar); a partition
   // whose clipped geometry is empty has no tree to walk
-  return ray_t0 <= ray_t && P.n_prims > 0;
+  return ray_t0 <= ray_t && has_prims;
+}
+__device__ __forceinline__ bool setup_ray_values(const SceneParams &P, int i, bool shadeFlag, float3 org, float3 dir, float ray_t0, float ray_t,
+                                                 int anyhit_secondary, RayCtx &rc, TravState &st, PendingRay &pr) {
+  return setup_ray_box(P.lmin, P.lmax, P.n_prims > 0, i, shadeFlag, org, dir, ray_t0, ray_t, anyhit_secondary, rc, st, pr);
 }
 
 
@@ -252,8 +256,8 @@ __device__ __forceinline__ int exit_face(float3 mn, float3 mx, float x, float y,
   else return (dz < 0) ? 4 : 5;
 }
 
-__device__ __forceinline__ int classify_values(const SceneParams &P, int typ, int term, float ox, float oy, float oz, float dx, float dy,
-                                               float dz) {
+__device__ __forceinline__ int classify_box(float3 bmin, float3 bmax, const int *__restrict__ neighbors, int typ, int term, float ox, float oy,
+                                            float oz, float dx, float dy, float dz) {
   int c = CLS_UNDETERMINED;
   if (typ == RAY_PRIMARY) {
     if (term & RAY_BOUNDARY) c = RAY_BOUNDARY;
@@ -269,12 +273,16 @@ __device__ __forceinline__ int classify_values(const SceneParams &P, int typ, in
     else c = CLS_DROP_ON_FLOOR;  // TIMEOUT or unknown
   }
   if (c == RAY_BOUNDARY) {
-    const int f = exit_face(P.lmin, P.lmax, ox, oy, oz, dx, dy, dz);
-    const int nb = P.neighbors[f];
+    const int f = exit_face(bmin, bmax, ox, oy, oz, dx, dy, dz);
+    const int nb = neighbors[f];
     if (nb >= 0) c = nb;
     else c = (typ == RAY_SHADOW || typ == RAY_AO) ? CLS_DROP_ON_FLOOR : CLS_TERMINATED;
   }
   return c;
+}
+__device__ __forceinline__ int classify_values(const SceneParams &P, int typ, int term, float ox, float oy, float oz, float dx, float dy,
+                                               float dz) {
+  return classify_box(P.lmin, P.lmax, P.neighbors, typ, term, ox, oy, oz, dx, dy, dz);
 }
 
 __device__ __forceinline__ int classify_ray(const SceneParams &P, const Rays &R, int i) {
@@ -317,6 +325,27 @@ __device__ __forceinline__ bool spawn_pixel(const SceneParams &P, const DevCamer
   float gmin, gmax, lmin = 0, lmax = 0;
   bool hit = box_intersect(P.gmin, P.gmax, vorigin, vray, gmin, gmax);
   if (hit) hit = box_intersect(P.lmin, P.lmax, vorigin, vray, lmin, lmax);
+  const float d = fabsf(lmin) - fabsf(gmin);
+  return hit && (lmax >= 0) && (d < 0.000001f) && (d > -0.000001f);
+}
+// the two halves of spawn_pixel for callers that test one ray against several partition boxes: the pixel's ray and its
+// entry into the global box (false: the ray misses the data altogether) ...
+__device__ __forceinline__ bool camera_ray(const SceneParams &P, const DevCamera &a, int x, int y, float3 &vorigin, float3 &vray, float &gmin) {
+  const float fx = ((float)x - a.off_x) * a.scaling;
+  const float fy = ((float)y - a.off_y) * a.scaling;
+  float3 xy;
+  xy.x = a.center.x + fx * a.vr.x + fy * a.vu.x;
+  xy.y = a.center.y + fx * a.vr.y + fy * a.vu.y;
+  xy.z = a.center.z + fx * a.vr.z + fy * a.vu.z;
+  if (a.ortho) { vorigin = xy - a.vdir; vray = a.vdir; }
+  else { vorigin = a.veye; vray = xy - a.veye; normalize_gxy(vray); }
+  float gmax;
+  return box_intersect(P.gmin, P.gmax, vorigin, vray, gmin, gmax);
+}
+// ... and "is this partition the one the ray enters first" (Camera.cpp:431-441)
+__device__ __forceinline__ bool first_brick(float3 bmin, float3 bmax, float3 vorigin, float3 vray, float gmin) {
+  float lmin = 0, lmax = 0;
+  const bool hit = box_intersect(bmin, bmax, vorigin, vray, lmin, lmax);
   const float d = fabsf(lmin) - fabsf(gmin);
   return hit && (lmax >= 0) && (d < 0.000001f) && (d > -0.000001f);
 }

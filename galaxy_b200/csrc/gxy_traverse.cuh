@@ -193,11 +193,11 @@ __device__ __forceinline__ void stack_push(const SceneParams &P, TravState &s, u
 // Test the 8 quantised child boxes of one node against the ray: `bit` (24..31) selects a hit child of the node
 // group (child_base, hits_imask); tbest = current upper end of the interval.  Returns the node group and the
 // primitive group of that node.  No traversal state is touched (also used by the generation kernel's cull).
-__device__ __forceinline__ void node_eval(const SceneParams &P, const RayCtx &rc, unsigned child_base, unsigned hits_imask, int bit, float tb,
-                                          uint2 &ng_out, uint2 &tg_out) {
+__device__ __forceinline__ void node_eval(const WideNode *__restrict__ nodes, const RayCtx &rc, unsigned child_base, unsigned hits_imask, int bit,
+                                          float tb, uint2 &ng_out, uint2 &tg_out) {
   const unsigned slot = (unsigned)(bit - 24) ^ (rc.octinv4 & 7u);
   const unsigned rel = __popc(hits_imask & ~(0xffffffffu << slot));
-  const uint4 *np = reinterpret_cast<const uint4 *>(P.nodes + (child_base + rel));
+  const uint4 *np = reinterpret_cast<const uint4 *>(nodes + (child_base + rel));
   const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
   // slab coefficients in the node's quantisation frame: t = q * a + b
   const float ax0 = __uint_as_float((n0.w & 0xffu) << 23) * rc.idx, ay0 = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * rc.idy,
@@ -236,16 +236,17 @@ __device__ __forceinline__ void node_eval(const SceneParams &P, const RayCtx &rc
 // Conservative cull (generation kernel): false only if the ray (interval of rc) cannot reach any primitive --
 // no child box of the root is hit, or none of the boxes one level below those.  Box tests are conservative
 // (see above), so a culled ray has no candidate and the full traversal would return "no hit".
-__device__ __forceinline__ bool may_hit_anything(const SceneParams &P, const RayCtx &rc) {
+// nodes: the tree itself, or a 9-node excerpt of it (root with child_base = 1, followed by its internal children).
+__device__ __forceinline__ bool may_hit_anything(const WideNode *__restrict__ nodes, const RayCtx &rc) {
   uint2 ng, tg;
-  node_eval(P, rc, 0u, 0x80000000u, 31, rc.tfar, ng, tg);
+  node_eval(nodes, rc, 0u, 0x80000000u, 31, rc.tfar, ng, tg);
   if (tg.y != 0u) return true;
   unsigned pending = ng.y;
   while (pending > 0x00ffffffu) {
     const int bit = 31 - __clz((int)pending);
     pending &= ~(1u << bit);
     uint2 ng2, tg2;
-    node_eval(P, rc, ng.x, ng.y, bit, rc.tfar, ng2, tg2);
+    node_eval(nodes, rc, ng.x, ng.y, bit, rc.tfar, ng2, tg2);
     if (tg2.y != 0u || ng2.y > 0x00ffffffu) return true;
   }
   return false;
@@ -265,7 +266,7 @@ __device__ __forceinline__ void node_step(const SceneParams &P, const RayCtx &rc
 #ifdef GXY_TRAV_COUNTERS
   s.n_nodes++;
 #endif
-  node_eval(P, rc, s.ng.x, hits_imask, bit, s.best_t, s.ng, s.tg);
+  node_eval(P.nodes, rc, s.ng.x, hits_imask, bit, s.best_t, s.ng, s.tg);
   if (PREFETCH) {
     if (s.tg.y) {
       const char *first = reinterpret_cast<const char *>(P.prims + (s.tg.x + (unsigned)(__ffs((int)s.tg.y) - 1)));
