@@ -48,6 +48,9 @@ static void timeline_print(int rank) {
   g_timeline.clear();
 }
 
+// GXY_TILED=0 restores the reference's row-major primary-ray order on the frame path (tuning / A-B runs)
+static bool tiled_order() { const char *e = getenv("GXY_TILED"); return !(e && atoi(e) == 0); }
+
 struct PhaseTimer {  // GXY_PROFILE=1: host wall-clock per phase of gxy_render (each mark synchronises nothing)
   bool on;
   std::chrono::steady_clock::time_point t0;
@@ -808,7 +811,7 @@ int gxy_generate_rays(gxy_vis *v, const gxy_camera *cam, int w, int h, gxy_rayli
   const int npix = w * h;
   if (v->cur.reserve(npix, false, st) || v->block_sums.reserve((size_t)npix / 1024 + 2) || v->small.reserve(64)) return 1;
   const DevCamera C = make_dev_camera(*cam, w, h);
-  if (launch_generate(v->P, C, w, h, v->cur.v, nullptr, v->block_sums.p, v->small.p, st)) return 1;
+  if (launch_generate(v->P, C, w, h, false, v->cur.v, nullptr, v->block_sums.p, v->small.p, st)) return 1;
   int n = 0;
   GXY_CUDA(cudaMemcpyAsync(&n, v->small.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   GXY_CUDA(cudaStreamSynchronize(st));
@@ -1114,7 +1117,8 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
     gxy_vis *v = parts[p];
     if (use_device(v->ctx)) return 1;
     cudaStream_t st = v->ctx->stream;
-    if (v->block_sums.reserve((size_t)std::max(npix, 1 << 20) / 1024 + 2) || v->small.reserve(64 + 4 * (size_t)nranks) || v->counters.reserve(4) ||
+    const int npix_pad = ((w + 15) / 16) * ((h + 7) / 8) * 128;  // slots of the tiled generation order
+    if (v->block_sums.reserve((size_t)std::max(npix_pad, 1 << 20) / 1024 + 2) || v->small.reserve(64 + 4 * (size_t)nranks) || v->counters.reserve(4) ||
         v->fb.reserve((size_t)npix * 4))
       return 1;
     v->fb_w = w; v->fb_h = h;
@@ -1200,7 +1204,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       gxy_vis *v = parts[p];
       if (use_device(v->ctx)) return 1;
       if (v->cur.reserve(npix, false, v->ctx->stream)) return 1;
-      if (launch_generate(v->P, C, w, h, v->cur.v, nullptr, v->block_sums.p, v->small.p, v->ctx->stream)) return 1;
+      if (launch_generate(v->P, C, w, h, tiled_order(), v->cur.v, nullptr, v->block_sums.p, v->small.p, v->ctx->stream)) return 1;
       S.kernel_launches += 3;
     }
     for (int p = 0; p < nparts; p++) {

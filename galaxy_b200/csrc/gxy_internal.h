@@ -23,8 +23,9 @@ int launch_accumulate(Rays R, int n, float *fb, int w, int h, unsigned long long
 // (Renderer.cpp:561-618).  d_counts: nranks ints (device, zeroed by the call), d_offsets nranks+1.
 int launch_partition_by_destination(Rays R, int n, int nranks, int keep_rank, Rays out, int *d_counts, int *d_offsets, int *d_cursor,
                                     cudaStream_t st);
-// Camera::SpawnRays (Camera.cpp:379-493): ordered compaction of the kept pixels
-int launch_generate(const SceneParams &P, const DevCamera &C, int w, int h, Rays out, int *d_flags_scan, int *d_block_sums,
+// Camera::SpawnRays (Camera.cpp:379-493): ordered compaction of the kept pixels; tiled = false: the reference's pixel order,
+// true: 16x8-pixel CTA tiles of 8x4 warp tiles (frame path: compact beams for the march kernel)
+int launch_generate(const SceneParams &P, const DevCamera &C, int w, int h, bool tiled, Rays out, int *d_flags_scan, int *d_block_sums,
                     int *d_count, cudaStream_t st);
 // ColorImageWriter::Write (ImageWriter.cpp:30-48)
 int launch_tonemap(const float *fb, int w, int h, unsigned char *rgba, cudaStream_t st);

@@ -33,8 +33,20 @@ struct VolK {
   const char *vox;
   int type;
 };
-__device__ __forceinline__ void pin(float &x) { asm volatile("" : "+f"(x)); }
-__device__ __forceinline__ void pin(unsigned &x) { asm volatile("" : "+r"(x)); }
+#ifndef GXY_MARCH_PIN
+#define GXY_MARCH_PIN 0
+#endif
+// keep a loop invariant in a register: ptxas re-materialises kernel parameters from the constant bank inside the loop
+// (one LDC/LDCU issue slot each per sample) unless it cannot see where the value comes from -- a shuffle from the own lane
+__device__ __forceinline__ void pin_rt(float &x) { x = __shfl_sync(0xffffffffu, x, threadIdx.x & 31u); }
+__device__ __forceinline__ void pin_rt(unsigned &x) { x = __shfl_sync(0xffffffffu, x, threadIdx.x & 31u); }
+#if GXY_MARCH_PIN
+__device__ __forceinline__ void pin(float &x) { pin_rt(x); }
+__device__ __forceinline__ void pin(unsigned &x) { pin_rt(x); }
+#else
+__device__ __forceinline__ void pin(float &x) {}
+__device__ __forceinline__ void pin(unsigned &x) {}
+#endif
 __device__ __forceinline__ void volk_load(VolK &k, const DevVolume &v) {
   k.ox = v.origin.x; k.oy = v.origin.y; k.oz = v.origin.z;
   k.rx = v.rcp.x; k.ry = v.rcp.y; k.rz = v.rcp.z;
@@ -108,6 +120,30 @@ __device__ __forceinline__ float vol_sample_k32(const VolK &v, float3 p) {
   return vol_lerp8(x, t);
 }
 
+// tf_both / tf_opacity (gxy_common.cuh; LinearTransferFunction.ispc:19-97) with the value range held in registers
+__device__ __forceinline__ float4 tf_both_k(const DevTF *__restrict__ tf, float lo, float hi, float d, float value) {
+  if (isnan(value)) return make_float4(0.f, 0.f, 0.f, 0.f);
+  if (value <= lo) return __ldg(&tf->e[0]);
+  if (value >= hi) return __ldg(&tf->e[255]);
+  const float remapped = (value - lo) / d * 255.0f;
+  const float fl = floorf(remapped);
+  const int index = (int)fl;
+  const float rem = remapped - fl;  // == remapped - (float)index
+  const float4 a = __ldg(&tf->e[index]), b = __ldg(&tf->e[min(index + 1, 255)]);
+  const float om = 1.0f - rem;
+  return make_float4(om * a.x + rem * b.x, om * a.y + rem * b.y, om * a.z + rem * b.z, om * a.w + rem * b.w);
+}
+__device__ __forceinline__ float tf_opacity_k(const DevTF *__restrict__ tf, float lo, float hi, float d, float value) {
+  if (isnan(value)) return 0.0f;
+  if (value <= lo) return __ldg(&tf->e[0]).w;
+  if (value >= hi) return __ldg(&tf->e[255]).w;
+  const float remapped = (value - lo) / d * 255.0f;
+  const float fl = floorf(remapped);
+  const int index = (int)fl;
+  const float rem = remapped - fl;
+  return (1.0f - rem) * __ldg(&tf->e[index]).w + rem * __ldg(&tf->e[min(index + 1, 255)]).w;
+}
+
 template <int NV, bool IDX32>
 __device__ __forceinline__ void sample_volumes(const SceneParams &P, const VolK *vk, int nvv, float3 coord, float *s) {
 #pragma unroll
@@ -131,9 +167,13 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, (NV <= 2 && !HAS_GEOM) ? GX
   __shared__ uint2 stack[HAS_GEOM ? GXY_STACK_SMEM * GXY_TRACE_THREADS : 1];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int nvv = NV < P.n_volvis ? NV : P.n_volvis;
-  const float step = P.step;
-  const float epsilon = global_epsilon * step;  // TraceRays.ispc:359
+  // launch_trace instantiates NV = n_volvis for up to 3 volume operators; only the catch-all has fewer than NV
+  const int nvv = (NV <= 3) ? NV : (NV < P.n_volvis ? NV : P.n_volvis);
+  float step = P.step;
+  float epsilon = global_epsilon * step;  // TraceRays.ispc:359
+#if GXY_MARCH_PIN
+  pin_rt(step); pin_rt(epsilon);
+#endif
   unsigned nsamples = 0;
 
   const bool shadeFlag = R.type[i] == RAY_PRIMARY;
@@ -220,6 +260,7 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, (NV <= 2 && !HAS_GEOM) ? GX
     // loop invariants, fetched once per ray
     VolK vk[NVA];
     const DevTF *tf_vol[NVA];
+    float tf_lo[NVA], tf_hi[NVA], tf_d[NVA];  // valueRange of the DVR transfer function and hi - lo
     float rate[NVA];
     bool dvr[NVA];
     bool any_iso = false;
@@ -228,6 +269,8 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, (NV <= 2 && !HAS_GEOM) ? GX
       if (m < nvv) {
         if (IDX32) volk_load(vk[m], P.vv[m].vol);
         tf_vol[m] = P.tfs + P.vv[m].vol.tf;
+        tf_lo[m] = __ldg(&tf_vol[m]->lo); tf_hi[m] = __ldg(&tf_vol[m]->hi);
+        tf_d[m] = tf_hi[m] - tf_lo[m];
         rate[m] = P.vv[m].vol.samplingRate;
         dvr[m] = P.vv[m].volume_render != 0;
         any_iso = any_iso || P.vv[m].n_iso > 0;
@@ -324,7 +367,7 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, (NV <= 2 && !HAS_GEOM) ? GX
               const DevTF *tf = tf_vol[major];
               const float sVolume = (sLast[major] + sThis[major]) / 2;
               if (shadeFlag) {
-                const float4 ca = tf_both(tf, sVolume);
+                const float4 ca = tf_both_k(tf, tf_lo[major], tf_hi[major], tf_d[major], sVolume);
                 if (ca.w > 0) {
                   // x / 1.0f == x for every x: the division is only executed for a sampling rate other than 1
                   const float wo = fmaxf(0.0f, fminf(rate[major] == 1.0f ? ca.w : ca.w / rate[major], 1.0f));
@@ -332,7 +375,7 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, (NV <= 2 && !HAS_GEOM) ? GX
                   cr = cr + om * (wo * ca.x); cg = cg + om * (wo * ca.y); cb = cb + om * (wo * ca.z); co = co + om * (wo * 1.0f);
                 }
               } else {
-                const float sampleOpacity = tf_opacity(tf, sVolume);
+                const float sampleOpacity = tf_opacity_k(tf, tf_lo[major], tf_hi[major], tf_d[major], sVolume);
                 if (sampleOpacity > 0) {
                   const float so1 = rate[major] == 1.0f ? sampleOpacity : sampleOpacity / rate[major];
                   const float weightedOpacity = ((tThis - tLast) / step) * fmaxf(0.0f, fminf(so1, 1.0f));
@@ -868,8 +911,20 @@ int launch_partition_by_destination(Rays R, int n, int nranks, int keep_rank, Ra
   return 0;
 }
 
+// Pixel of queue slot p.  tiles_x == 0: the reference's order (row-major, Camera.cpp:403-441).  tiles_x > 0: 16x8-pixel
+// tiles of 128 slots (one trace CTA), each made of four 8x4 warp tiles: the rays of a warp / CTA stay a compact beam, so
+// the voxels they sample at each march step share cache lines and the CTA re-uses them from L1 on the following steps
+// (an oblique view in row-major order re-read the volume 3.7x from DRAM: ncu, profiles/).
+__device__ __forceinline__ bool slot_pixel(int p, int w, int h, int tiles_x, int &x, int &y) {
+  if (tiles_x == 0) { x = p % w; y = p / w; return true; }
+  const int tile = p >> 7, i = p & 127, wq = i >> 5, lane = i & 31;
+  x = (tile % tiles_x) * 16 + (wq & 1) * 8 + (lane & 7);
+  y = (tile / tiles_x) * 8 + (wq >> 1) * 4 + (lane >> 3);
+  return x < w && y < h;
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS)
-    generate_count_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevCamera C, int w, int npix,
+    generate_count_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevCamera C, int w, int h, int tiles_x, int npix,
                           int *__restrict__ block_sums) {
   const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   int c = 0;
@@ -877,31 +932,32 @@ __global__ void __launch_bounds__(SCAN_THREADS)
   for (int k = 0; k < SCAN_ITEMS; k++) {
     const int p = base + k;
     float3 o, d;
-    if (p < npix && spawn_pixel(P, C, p % w, p / w, o, d)) c++;
+    int x, y;
+    if (p < npix && slot_pixel(p, w, h, tiles_x, x, y) && spawn_pixel(P, C, x, y, o, d)) c++;
   }
   int tot;
   block_exclusive_scan(c, &tot);
   if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
 }
 __global__ void __launch_bounds__(SCAN_THREADS)
-    generate_write_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevCamera C, int w, int npix,
+    generate_write_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevCamera C, int w, int h, int tiles_x, int npix,
                           const int *__restrict__ block_sums, Rays O) {
   const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   float3 o[SCAN_ITEMS], d[SCAN_ITEMS];
+  int px[SCAN_ITEMS], py[SCAN_ITEMS];
   bool f[SCAN_ITEMS];
   int c = 0;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) {
     const int p = base + k;
-    f[k] = p < npix && spawn_pixel(P, C, p % w, p / w, o[k], d[k]);
+    f[k] = p < npix && slot_pixel(p, w, h, tiles_x, px[k], py[k]) && spawn_pixel(P, C, px[k], py[k], o[k], d[k]);
     c += f[k] ? 1 : 0;
   }
   int dst = block_sums[blockIdx.x] + block_exclusive_scan(c, nullptr);
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++)
     if (f[k]) {
-      const int p = base + k;
-      O.x[dst] = p % w; O.y[dst] = p / w;
+      O.x[dst] = px[k]; O.y[dst] = py[k];
       O.ox[dst] = o[k].x; O.oy[dst] = o[k].y; O.oz[dst] = o[k].z;
       O.dx[dst] = d[k].x; O.dy[dst] = d[k].y; O.dz[dst] = d[k].z;
       O.r[dst] = 0; O.g[dst] = 0; O.b[dst] = 0; O.o[dst] = 0; O.t[dst] = 0; O.tMax[dst] = FLT_MAX;
@@ -910,14 +966,15 @@ __global__ void __launch_bounds__(SCAN_THREADS)
     }
 }
 
-int launch_generate(const SceneParams &P, const DevCamera &C, int w, int h, Rays out, int *d_flags_scan, int *d_block_sums,
+int launch_generate(const SceneParams &P, const DevCamera &C, int w, int h, bool tiled, Rays out, int *d_flags_scan, int *d_block_sums,
                     int *d_count, cudaStream_t st) {
   (void)d_flags_scan;
-  const int npix = w * h;
+  const int tiles_x = tiled ? (w + 15) / 16 : 0;
+  const int npix = tiled ? tiles_x * ((h + 7) / 8) * 128 : w * h;
   const int nblocks = (npix + SCAN_TILE - 1) / SCAN_TILE;
-  generate_count_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(P, C, w, npix, d_block_sums);
+  generate_count_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(P, C, w, h, tiles_x, npix, d_block_sums);
   scan_block_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(d_block_sums, nblocks, d_count);
-  generate_write_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(P, C, w, npix, d_block_sums, out);
+  generate_write_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(P, C, w, h, tiles_x, npix, d_block_sums, out);
   GXY_CUDA(cudaGetLastError());
   return 0;
 }
