@@ -1,0 +1,134 @@
+"""The C++ host side above the C ABI (galaxy_b200/host: Datasets / Volume / Camera / Lighting / Visualization /
+Rendering + the gxywriter driver): an existing reference .state file, with its .vol datasets on disk, renders
+unchanged.  CPU part: `gxywriter --describe` (no GPU) parses every reference test state to exactly what the Python
+front end (galaxy_b200.scenes, itself pinned by the gold images through the oracle) parses.  GPU part: the PNGs
+gxywriter writes match the reference's gold images."""
+import json
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from galaxy_b200 import scenes
+from tests import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "galaxy_b200", "gxywriter")
+STATES = ["oneBall", "nineBalls", "xyz", "camera", "camera-shadow", "absolute", "absolute-shadow", "infinite", "infinite-shadow"]
+
+
+def write_vol(path, vol):
+    """scripts/vti2vol:70-80: text header (type / origin / counts / deltas / raw file name, %f) + raw file."""
+    raw = os.path.basename(path)[:-4] + ".raw"
+    with open(path, "w") as f:
+        f.write("float\n%f %f %f\n%d %d %d\n%f %f %f\n%s\n" % (*[float(x) for x in vol.origin], *vol.counts, *[float(x) for x in vol.deltas], raw))
+    vol.data.astype(np.float32).tofile(os.path.join(os.path.dirname(path), raw))
+
+
+def stage(tmp, name, n):
+    """state file + the radial .vol files it names, in one directory (what tests/image-gold-tests.sh sets up)."""
+    src = os.path.join(ROOT, "tests", "golden", "states", name + ".state")
+    shutil.copy(src, os.path.join(tmp, name + ".state"))
+    doc = json.load(open(src))
+    for ds in doc["Datasets"]:
+        fn = ds["filename"]
+        p = os.path.join(tmp, fn)
+        if not os.path.exists(p):
+            write_vol(p, scenes.radial_volume(fn[len("radial-"):-len(".vol")], n))
+    return os.path.join(tmp, name + ".state"), doc
+
+
+def f32list(x):
+    return [float(np.float32(v)) for v in np.asarray(x, np.float64).ravel()]
+
+
+@pytest.mark.parametrize("name", STATES)
+@pytest.mark.parametrize("nparts", [1, 8])
+def test_describe_matches_python_front_end(tmp_path, name, nparts):
+    assert os.path.exists(EXE), "galaxy_b200/gxywriter is not built (run __graft_entry__.build())"
+    state, doc = stage(str(tmp_path), name, 20)
+    out = subprocess.run([EXE, "--describe", "-P", str(nparts), state], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    got = json.loads(out.stdout, parse_float=lambda t: float(np.float32(t)))  # %.9g text -> the float32 it denotes
+    st = scenes.parse_state(doc)
+    assert got["epsilon"] == float(np.float32(st["epsilon"]))
+    assert len(got["cameras"]) == len(st["cameras"])
+    for g, c in zip(got["cameras"], st["cameras"]):
+        assert g["eye"] == f32list(c["eye"]) and g["dir"] == f32list(c["dir"]) and g["up"] == f32list(c["up"])
+        assert g["aov"] == float(np.float32(c["aov"])) and g["annotation"] == c["annotation"]
+    assert len(got["visualizations"]) == len(st["visualizations"])
+    for g, v in zip(got["visualizations"], st["visualizations"]):
+        L = v["lighting"]
+        assert g["annotation"] == v["annotation"]
+        assert [f32list(x) for x in L["lights"]] == g["lighting"]["lights"] and L["types"] == g["lighting"]["types"]
+        assert g["lighting"]["n_ao"] == L["n_ao"] and g["lighting"]["shadows"] == L["shadows"]
+        assert g["lighting"]["ao_radius"] == f32list([L["ao_radius"]]) and g["lighting"]["Ka"] == f32list([L["Ka"]])
+        assert g["lighting"]["Kd"] == f32list([L["Kd"]])
+        assert len(g["operators"]) == len(v["operators"])
+        for go, op in zip(g["operators"], v["operators"]):
+            assert go["type"] == op["type"] and go["dataset"] == op["dataset"]
+            assert go["isovalues"] == f32list(op["isovalues"]) and go["slices"] == f32list(op["slices"])
+            assert go["volume_render"] == op["volume_render"]
+            lo, hi = op["data_range"] if op["data_range"] is not None else (op["colormap"][0][0], op["colormap"][-1][0])
+            assert go["range"] == f32list([lo, hi])
+            col, opac = scenes.resample_tf(op["colormap"], op["opacitymap"])
+            assert np.array_equal(np.asarray(go["tf_colors"], np.float32), col.ravel())
+            assert np.array_equal(np.asarray(go["tf_opacities"], np.float32), opac.ravel())
+    # datasets: header values as the reference reads them, partition boxes / neighbours as Volume.cpp computes them
+    fac = scenes.factor(nparts)
+    for g in got["datasets"]:
+        fn = [d["filename"] for d in doc["Datasets"] if d.get("name", d["filename"]) == g["name"]][0]
+        vol = scenes.load_vol_file(os.path.join(str(tmp_path), fn))
+        assert g["counts"] == list(vol.counts) and g["origin"] == f32list(vol.origin) and g["deltas"] == f32list(vol.deltas)
+        parts = scenes.partition(fac, vol.counts)
+        for gp, p in zip(g["partitions"], parts):
+            gmin, gmax, lmin, lmax = scenes.volume_boxes(vol, p)
+            assert gp["gmin"] == f32list(gmin) and gp["gmax"] == f32list(gmax) and gp["lmin"] == f32list(lmin) and gp["lmax"] == f32list(lmax)
+            assert gp["neighbors"] == scenes.neighbors_of(p["ijk"], fac)
+            assert gp["goffsets"] == p["goffsets"] and gp["gcounts"] == p["gcounts"]
+
+
+def test_errors_are_reported_not_fatal(tmp_path):
+    """The reference's loaders print and return false; the driver turns that into exit status 1."""
+    bad = tmp_path / "bad.state"
+    bad.write_text('{"Datasets": [{"name": "x", "type": "Volume", "filename": "missing.vol"}], "Cameras": [], "Visualizations": []}')
+    r = subprocess.run([EXE, "--describe", str(bad)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "unable to open volfile" in r.stderr
+    bad.write_text("{ not json")
+    r = subprocess.run([EXE, "--describe", str(bad)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "Bad state file" in r.stderr
+    geo = tmp_path / "geo.state"
+    geo.write_text('{"Datasets": [{"name": "m", "type": "Triangles", "filename": "m.part"}], "Cameras": [], "Visualizations": []}')
+    r = subprocess.run([EXE, "--describe", str(geo)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "VTK" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n_images,min_gold", [("oneBall", 1, 0.999), ("nineBalls", 3, 0.997), ("xyz", 1, 0.999), ("camera-shadow", 1, 0.999)])
+def test_gxywriter_renders_reference_states_to_gold(tmp_path, golden_dir, name, n_images, min_gold):
+    state, _ = stage(str(tmp_path), name, 256)
+    r = subprocess.run([EXE, "-s", "512", "512", state], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "TIMING total" in r.stdout
+    for k in range(n_images):
+        img = np.asarray(Image.open(os.path.join(str(tmp_path), "image_%05d.png" % k)).convert("RGBA"))
+        gold = np.asarray(Image.open(os.path.join(golden_dir, "golds", "%s_%05d.png" % (name, k))).convert("RGBA"))
+        frac = util.image_fraction(img, gold)
+        print(name, k, "fraction within 1/255 of the gold:", frac)
+        assert img.shape == gold.shape and frac >= min_gold
+
+
+@pytest.mark.gpu
+def test_gxywriter_partitions_match_single(tmp_path):
+    """-P 8: same state rendered on 8 spatial partitions equals the 1-partition image to within the tolerance."""
+    state, _ = stage(str(tmp_path), "nineBalls", 256)
+    for P in (1, 8):
+        r = subprocess.run([EXE, "-s", "384", "384", "-P", str(P), "-o", "p%d" % P, state], capture_output=True, text=True, timeout=300,
+                           cwd=str(tmp_path))
+        assert r.returncode == 0, r.stderr + r.stdout
+    a = np.asarray(Image.open(os.path.join(str(tmp_path), "p1_00001.png")).convert("RGBA"))
+    b = np.asarray(Image.open(os.path.join(str(tmp_path), "p8_00001.png")).convert("RGBA"))
+    assert util.image_fraction(a, b) >= 0.995
