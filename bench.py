@@ -29,9 +29,11 @@ from galaxy_b200 import scenes  # noqa: E402
 
 W, H = 1920, 1080
 EPS = 0.001
-# ncu --set full, one frame of this workload on one B200 (profiles/r01_c_trace_kernels_full.txt):
-# primary_trace_kernel 488.3 MB read + 9.4 MB written, fused_secondary_kernel 508.7 MB read + 9.8 MB written
-NCU_TRAFFIC_BYTES_PER_FRAME = 1.0162e9
+# ncu --set full, one frame of this workload on one B200 (profiles/r01_e_trace_kernels_full.txt):
+# primary_trace_kernel 480.3 MB read + 10.6 MB written, fused_secondary_kernel 501.2 MB read + 10.9 MB written
+NCU_TRAFFIC_BYTES_PER_FRAME = 1.0030e9
+# volume workloads at 1024^3 (profiles/r01_e_volume_full.txt): dram bytes of the march launches of one frame
+NCU_VOLUME_TRAFFIC = {"c3": 4.296e9, "c4": 6.868e9}
 
 
 def measured_peaks():
@@ -119,6 +121,62 @@ def cpu_sample_scene(oracle_mod, n_lat, n_lon):
     return parts, vis, len(ds.indices)
 
 
+CMAP = [[0.0, 1.0, 0.5, 0.5], [0.25, 0.5, 1.0, 0.5], [0.5, 0.5, 0.5, 1.0], [0.75, 1.0, 1.0, 0.5], [1.0, 1.0, 0.5, 1.0]]
+
+
+def synth_volume(n, device="cuda"):
+    """C3/C4 throughput volume: eightBalls distance field + 0.15 * a sine lattice, n^3 float32 on [-1,1]^3,
+    synthesised slab-wise with torch (closed form: no seed, no files)."""
+    import torch
+    dev = device if torch.cuda.is_available() else "cpu"
+    c = torch.linspace(-1.0, 1.0, n, device=dev, dtype=torch.float32)
+    data = np.empty((n, n, n), np.float32)
+    Y, X = torch.meshgrid(c, c, indexing="ij")
+    for k0 in range(0, n, 64):
+        Z = c[k0:k0 + 64].view(-1, 1, 1)
+        eb = torch.sqrt((X.abs() - .5) ** 2 + (Y.abs() - .5) ** 2 + (Z.abs() - .5) ** 2)
+        v = eb + 0.15 * (torch.sin(37.0 * X) * torch.sin(41.0 * Y) * torch.sin(43.0 * Z) * 0.5 + 0.5)
+        data[k0:k0 + 64] = v.cpu().numpy()
+    sp = 2.0 / (n - 1)
+    return scenes.VolumeDataset([-1.0, -1.0, -1.0], (n, n, n), [sp, sp, sp], data)
+
+
+def volume_case(which):
+    """(visualization, camera) of C3 = DVR only (examples/noise.state) and C4 = isosurface + shadow rays
+    (examples/noise_isovalue.state), SURVEY 8d."""
+    if which == "c3":
+        op = dict(type="VolumeVis", dataset="v", colormap=CMAP, opacitymap=[[0.0, 0.05], [0.2, 0.02], [0.21, 0.0], [1.0, 0.0]], data_range=None,
+                  slices=[], isovalues=[], volume_render=True)
+        return (dict(annotation="", lighting=scenes.parse_lighting({}), operators=[op]),
+                scenes.parse_camera({"viewpoint": [0, 0, -4], "viewcenter": [0, 0, 0], "viewup": [0, 1, 0], "aov": 30}))
+    op = dict(type="VolumeVis", dataset="v", colormap=CMAP, opacitymap=[[0, 1], [1, 1]], data_range=None, slices=[], isovalues=[0.35],
+              volume_render=False)
+    return (dict(annotation="", lighting=scenes.parse_lighting({"Sources": [[1, 1, -2, 0]], "shadows": True, "Ka": 0.4, "Kd": 0.6, "ao count": 0}),
+                 operators=[op]),
+            scenes.parse_camera({"viewpoint": [3, 2, -4], "viewcenter": [0, 0, 0], "viewup": [0, 1, 0], "aov": 30}))
+
+
+def run_cpu_baseline_volume(which, steps, warmup, n=192, sample_div=4):
+    """The oracle on a bounded sample of the volume workload: n^3 volume, (1080p / sample_div^2) window."""
+    from oracle import oracle
+    vis, cam = volume_case(which)
+    vol = synth_volume(n, device="cpu")
+    parts = scenes.build_partitions(oracle, vis, {"v": vol}, 1)
+    w, h = W // sample_div, H // sample_div
+    cores = os.cpu_count() or 1
+    times, rays = [], 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        fb, st = oracle.render(parts, cam, vis["lighting"], w, h, EPS, nthreads=cores)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+            rays = st["primary_rays"] + st["shadow_rays"] + st["ao_rays"]
+    t = float(np.mean(times))
+    sample = "oracle port; same camera/lighting/transfer function, %dx%d window, %d^3 volume; %d rays/frame" % (w, h, n, rays)
+    return {"value": rays / t / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample}, t * 1e3
+
+
 def run_cpu_baseline(steps, warmup, sample_div=1, tess_div=4):
     """The oracle (CPU restatement of the reference's algorithm) on a bounded sample of the workload."""
     from oracle import oracle
@@ -149,20 +207,33 @@ def main():
     ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
     ap.add_argument("--tess-div", type=int, default=1, help="divide the C5 tessellation (debug only; 1 = the 100M-triangle workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "c4"],
+                    help="c5 (default, the headline): 100M-triangle mesh; c3: volume DVR; c4: volume isosurface + shadow rays")
+    ap.add_argument("--volume-n", type=int, default=1024, help="c3/c4: voxels per axis of the synthetic volume")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = args.gpus
-    workload = "C5 eightBalls-100M: %d triangles, 1920x1080, primary + shadow (1 light) + 8 AO rays, Triangles vis, spatial partitions=%d" % (
-        8 * 2 * (scenes.C5_FULL[0] // args.tess_div) * (scenes.C5_FULL[1] // args.tess_div), n_gpus)
+    volume = args.workload in ("c3", "c4")
+    if volume:
+        workload = ("C3 noise volume %d^3 float32, 1920x1080, DVR only (no secondary rays), spatial partitions=%d" if args.workload == "c3" else
+                    "C4 noise volume %d^3 float32, 1920x1080, isosurface 0.35 + shadow rays (1 light), spatial partitions=%d") % (args.volume_n, n_gpus)
+        metric = "Mrays/s, 1080p volume march (%s)" % ("DVR" if args.workload == "c3" else "isosurface + shadow")
+    else:
+        workload = "C5 eightBalls-100M: %d triangles, 1920x1080, primary + shadow (1 light) + 8 AO rays, Triangles vis, spatial partitions=%d" % (
+            8 * 2 * (scenes.C5_FULL[0] // args.tess_div) * (scenes.C5_FULL[1] // args.tess_div), n_gpus)
+        metric = "Mrays/s, 1080p primary+shadow+AO"
     config = {"workload": workload, "width": W, "height": H, "partitions": n_gpus, "timing": "inputs larger than L2 (scene >> 126 MB) + 256 MB L2 flush between frames"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        cb, ms = run_cpu_baseline(max(1, args.steps), max(0, min(args.warmup, 1)))
-        line = {"metric": "Mrays/s, 1080p primary+shadow+AO", "value": cb["value"], "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps,
+        if volume:
+            cb, ms = run_cpu_baseline_volume(args.workload, max(1, args.steps), max(0, min(args.warmup, 1)))
+        else:
+            cb, ms = run_cpu_baseline(max(1, args.steps), max(0, min(args.warmup, 1)))
+        line = {"metric": metric, "value": cb["value"], "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config, "impl": "reference", "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -186,17 +257,22 @@ def main():
         uid = [gpu.comm_unique_id()] if rank == 0 else [None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0])
-    n_lat, n_lon = scenes.C5_FULL[0] // args.tess_div, scenes.C5_FULL[1] // args.tess_div
     t0 = time.perf_counter()
-    ds, _ = scenes.c5_partition_mesh(n_lat, n_lon, nparts, rank)
+    if volume:
+        ds = synth_volume(args.volume_n)
+        vis, cam = volume_case(args.workload)
+        dsets, n_tris_local = {"v": ds}, 0
+    else:
+        n_lat, n_lon = scenes.C5_FULL[0] // args.tess_div, scenes.C5_FULL[1] // args.tess_div
+        ds, _ = scenes.c5_partition_mesh(n_lat, n_lon, nparts, rank)
+        vis, cam = scenes.c5_vis(), scenes.c5_camera()
+        dsets, n_tris_local = {"mesh": ds}, len(ds.indices)
     t_gen = time.perf_counter() - t0
-    vis, cam = scenes.c5_vis(), scenes.c5_camera()
     t0 = time.perf_counter()
-    part = scenes.build_partitions(gpu, vis, {"mesh": ds}, nparts, only_rank=rank, ctx=ctx)[0]
+    part = scenes.build_partitions(gpu, vis, dsets, nparts, only_rank=rank, ctx=ctx)[0]
     t_commit = time.perf_counter() - t0
     info = part.build_info()
-    n_tris_local = len(ds.indices)
-    del ds
+    del ds, dsets
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -218,7 +294,7 @@ def main():
     barrier()
     sampler.mark_begin()
     t_wall0 = time.perf_counter()
-    dev_ms, trace_ms, launches, traced = [], 0.0, 0, 0
+    dev_ms, trace_ms, launches, traced, samples = [], 0.0, 0, 0, 0
     for _ in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
@@ -227,6 +303,7 @@ def main():
         trace_ms += st["trace_ms"]
         launches += st["kernel_launches"]
         traced += st["traced_rays"]
+        samples += st["volume_samples"]
     barrier()
     t_wall = time.perf_counter() - t_wall0
     sampler.mark_end()
@@ -277,9 +354,19 @@ def main():
     achieved = (traced / max(1, 1)) * b_alg / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": NCU_TRAFFIC_BYTES_PER_FRAME,
                 "kernel": "gxy::primary_trace_kernel + gxy::fused_secondary_kernel (the two persistent trace launches of a frame)",
-                "traffic_note": "dram__bytes_read+write of the two trace launches of one frame, ncu --set full, profiles/r01_c_trace_kernels_full.txt", "peak_kind": peak_kind + " (burst copy figure)", "alg_bytes_per_ray": b_alg, "bvh_levels_model": levels,
+                "traffic_note": "dram__bytes_read+write of the two trace launches of one frame, ncu --set full, profiles/r01_e_trace_kernels_full.txt", "peak_kind": peak_kind + " (burst copy figure)", "alg_bytes_per_ray": b_alg, "bvh_levels_model": levels,
                 "trace_share_of_step": trace_ms_max / max(1e-9, ms_max)}
-    line = {"metric": "Mrays/s, 1080p primary+shadow+AO", "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps,
+    if volume:
+        # 16 algorithmic bytes per trilinear sample (4 new float voxels per step when rays are >= 1 voxel apart)
+        achieved = samples * 16.0 / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                    "traffic": NCU_VOLUME_TRAFFIC.get(args.workload) if args.volume_n == 1024 else None,
+                    "kernel": "gxy::trace_kernel<1,false,true> (volume march: trilinear sample + transfer function + compositing / isosurface search)",
+                    "traffic_note": "dram__bytes_read+write per frame at 1024^3, ncu --set full, profiles/r01_e_volume_full.txt",
+                    "peak_kind": peak_kind + " (burst copy figure)", "alg_bytes_per_sample": 16.0, "samples_per_frame": samples / args.steps,
+                    "gsamples_per_s": samples / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0,
+                    "trace_share_of_step": trace_ms_max / max(1e-9, ms_max)}
+    line = {"metric": metric, "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 40 + 276, "d2h_bytes_per_step": W * H * 4},
@@ -288,7 +375,7 @@ def main():
             "scene": {"triangles_this_rank": n_tris_local, "bvh_nodes": info["n_nodes"], "bvh_build_ms": info["build_ms"], "mesh_gen_s": t_gen,
                       "commit_s": t_commit}}
     if n_gpus == 1 and not args.no_cpu_baseline:
-        cb, _ = run_cpu_baseline(3, 0)
+        cb, _ = run_cpu_baseline_volume(args.workload, 2, 0) if volume else run_cpu_baseline(3, 0)
         line["cpu_baseline"] = cb
     print(json.dumps(line))
     if world > 1:
