@@ -374,6 +374,8 @@ def build_partitions(backend, vis, datasets, nparts, geom_extents=None, only_ran
                 sc.add_volume_vis(ds_ids[op["dataset"]], gc, origin, ds.deltas, brick, op["slices"], op["isovalues"], op["volume_render"],
                                   colors, opac, lo, hi)
             else:
+                if geom_extents is None:  # geometry after a volume operator: its own partition document
+                    geom_extents, _ = geometry_extents(nparts)
                 ext = geom_extents[r]
                 if not boxes_set:
                     g = geom_extents
