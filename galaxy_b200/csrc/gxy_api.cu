@@ -153,6 +153,9 @@ struct PeerArena {
 struct gxy_context {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // D2H of finished images while the next frame renders
+  cudaStream_t lanes[16] = {};  // extra lanes of the band pipeline of the fused frame path ([0] unused: the main stream)
+  cudaEvent_t ev_fork = nullptr, ev_join[16] = {};
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
   PeerArena arena;
@@ -263,6 +266,9 @@ struct gxy_vis {
   Scratch<float> fb, fb_tmp;
   float *fb_result = nullptr;  // where the last frame's image is (fb.p, or a buffer inside the peer arena)
   Scratch<unsigned char> rgba8;
+  Scratch<unsigned char> rgba8_async[2];  // staging images of gxy_frame_download_rgba8_async
+  cudaEvent_t async_ready[2] = {nullptr, nullptr}, async_done[2] = {nullptr, nullptr};
+  int async_slot = 0;
   Scratch<float> io_f;
   Scratch<int> io_i;
   int fb_w = 0, fb_h = 0;
@@ -309,6 +315,12 @@ void gxy_context_destroy(gxy_context *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (int k = 0; k < 16; k++) {
+    if (c->lanes[k]) cudaStreamDestroy(c->lanes[k]);
+    if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -422,6 +434,13 @@ void gxy_vis_destroy(gxy_vis *v) {
   v->cur.release(); v->next.release(); v->send.release(); v->recv.release(); v->hits.release(); v->fq.release(); v->rawhits.release();
   v->hit_index.release(); v->block_sums.release(); v->small.release(); v->counters.release();
   v->fb.release(); v->fb_tmp.release(); v->rgba8.release(); v->io_f.release(); v->io_i.release();
+  if (v->ctx->copy_stream) cudaStreamSynchronize(v->ctx->copy_stream);
+  for (int s = 0; s < 2; s++) {
+    v->rgba8_async[s].release();
+    if (v->async_ready[s]) cudaEventDestroy(v->async_ready[s]);
+    if (v->async_done[s]) cudaEventDestroy(v->async_done[s]);
+  }
+  v->proxies.release();
   delete v;
 }
 
@@ -983,7 +1002,8 @@ static int render_peer(gxy_vis *v, const DevCamera &C, const DevLights &L, const
   S.kernel_launches += 3;
   // ---- wave 0: generation, trace of the primaries, shading of the hits (their AO/shadow rays follow in wave 1)
   if (ev_begin()) return 1;
-  if (launch_fused_primary(v->P, C, L, w, h, fb, v->next.v, v->rawhits.p, v->hits.v, v->cur.v, 0u, q, epsilon, &T, proxies, st)) return 1;
+  if (launch_fused_primary(v->P, C, L, w, h, fb, v->next.v, v->rawhits.p, (unsigned)npix, v->hits.v, v->cur.v, 0u, q, epsilon, &T, proxies, 0, 1, st))
+    return 1;
   if (ev_end()) return 1;
   S.kernel_launches += 3;
   if (launch_wave_epilogue(T, q, ++A.epoch, -1, spawn, v->d_error, st)) return 1;
@@ -1130,33 +1150,100 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
     static_assert(sizeof(FusedQueues) == 96, "FusedQueues layout");
     std::vector<FusedQueues> fq(nparts);
     std::vector<bool> can_spill(nparts, false);
+    // Band pipeline (one partition without neighbours, i.e. the single-GPU frame): the window is split into interleaved
+    // bands of tile rows, each band runs gen -> primary trace -> shade -> secondary trace with its own queues on its own
+    // stream.  A persistent trace kernel ends with a drain phase -- the last rays fetched still need their ~30 dependent
+    // node visits while most warps have nothing left (ncu: the primary kernel issues on 60 % of its active cycles but
+    // only 31 % of all cycles) -- and a frame has two of them; with bands the CTAs of another band's kernel move into
+    // the SMs a draining kernel vacates, and primary and secondary phases of different bands overlap.
+    int n_bands = 1;
+    {
+      bool alone = nparts == 1;
+      for (int f = 0; f < 6 && alone; f++) alone = parts[0]->neighbors[f] < 0;
+      if (alone) {
+        // measured on C5 (tools/band_sweep.py; bands on as many streams): 1: 1.69 ms, 2: 1.61, 3: 1.53, 4: 1.43, 6: 1.44-1.51, 8: 1.43-1.53,
+        // 16: 1.81; fewer streams than bands is worse than no bands at all (4 bands on 2 streams: 1.99 ms)
+        n_bands = 4;
+        if (const char *e = getenv("GXY_BANDS")) n_bands = std::max(1, std::min(16, atoi(e)));
+      }
+    }
+    const int tiles_x8 = (w + 7) / 8, tiles_y4 = (h + 3) / 4;
+    const size_t qcap = (size_t)tiles_x8 * tiles_y4 * 32;  // queue slots of all bands together (>= npix)
+    auto rays_offset = [](Rays r, size_t off) {
+      float **fcol = &r.ox;
+      for (int k = 0; k < 20; k++) fcol[k] += off;
+      int **icol = &r.x;
+      for (int k = 0; k < 5; k++) icol[k] += off;
+      return r;
+    };
     // ---- primary rays: generate -> trace -> light -> framebuffer, hit records for the secondaries
     for (int p = 0; p < nparts; p++) {
       gxy_vis *v = parts[p];
       if (use_device(v->ctx)) return 1;
       cudaStream_t st = v->ctx->stream;
       for (int f = 0; f < 6; f++) can_spill[p] = can_spill[p] || v->neighbors[f] >= 0;
-      if (v->hits.reserve(npix, false, st) || v->fq.reserve(sizeof(FusedQueues) / 8) || v->rawhits.reserve((size_t)6 * npix)) return 1;
-      if (v->next.reserve(npix, false, st)) return 1;  // the generated primaries
+      if (v->hits.reserve(qcap, false, st) || v->fq.reserve((size_t)n_bands * sizeof(FusedQueues) / 8) || v->rawhits.reserve((size_t)6 * qcap)) return 1;
+      if (v->next.reserve(qcap, false, st)) return 1;  // the generated primaries
       if (v->cur.reserve(can_spill[p] ? (size_t)npix : 64, false, st)) return 1;
-      GXY_CUDA(cudaMemsetAsync(v->fq.p, 0, sizeof(FusedQueues), st));
+      GXY_CUDA(cudaMemsetAsync(v->fq.p, 0, (size_t)n_bands * sizeof(FusedQueues), st));
       cudaEvent_t ta, tb;
       GXY_CUDA(cudaEventCreate(&ta));
       GXY_CUDA(cudaEventCreate(&tb));
       GXY_CUDA(cudaEventRecord(ta, st));
-      if (launch_fused_primary(v->P, C, L, w, h, v->fb.p, v->next.v, v->rawhits.p, v->hits.v, v->cur.v,
-                               can_spill[p] ? (unsigned)v->cur.cap : 0u, reinterpret_cast<FusedQueues *>(v->fq.p), epsilon, nullptr, nullptr, st))
-        return 1;
+      if (n_bands > 1) {
+        gxy_context *c = v->ctx;
+        int n_lanes = n_bands;
+        if (const char *e = getenv("GXY_BAND_STREAMS")) n_lanes = std::max(1, std::min(16, atoi(e)));
+        n_lanes = std::min(n_lanes, n_bands);
+        if (!c->ev_fork) GXY_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        GXY_CUDA(cudaEventRecord(c->ev_fork, st));
+        for (int k = 1; k < n_lanes; k++) {
+          if (!c->lanes[k]) {
+            GXY_CUDA(cudaStreamCreateWithFlags(&c->lanes[k], cudaStreamNonBlocking));
+            GXY_CUDA(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+          }
+          GXY_CUDA(cudaStreamWaitEvent(c->lanes[k], c->ev_fork, 0));
+        }
+        size_t off = 0;
+        for (int b = 0; b < n_bands; b++) {
+          cudaStream_t sb = (b % n_lanes) ? c->lanes[b % n_lanes] : st;
+          const int rows = (tiles_y4 - b + n_bands - 1) / n_bands;
+          if (rows <= 0) continue;
+          const size_t nq = (size_t)tiles_x8 * rows * 32;
+          FusedQueues *qb = reinterpret_cast<FusedQueues *>(v->fq.p) + b;
+          if (launch_fused_primary(v->P, C, L, w, h, v->fb.p, rays_offset(v->next.v, off), v->rawhits.p + off, (unsigned)qcap,
+                                   rays_offset(v->hits.v, off), v->cur.v, 0u, qb, epsilon, nullptr, nullptr, b, n_bands, sb))
+            return 1;
+          S.kernel_launches += 3;
+          if (n_sec_per_hit > 0) {
+            if (launch_fused_secondary(v->P, L, w, h, n_sec_per_hit, (long long)nq * n_sec_per_hit, v->fb.p, rays_offset(v->hits.v, off), v->cur.v, 0u,
+                                       qb, epsilon, !v->has_dvr, nullptr, 0, sb))
+              return 1;
+            S.kernel_launches += 1;
+          }
+          off += nq;
+        }
+        for (int k = 1; k < n_lanes; k++) {
+          GXY_CUDA(cudaEventRecord(c->ev_join[k], c->lanes[k]));
+          GXY_CUDA(cudaStreamWaitEvent(st, c->ev_join[k], 0));
+        }
+        S.waves += n_sec_per_hit > 0 ? 2 : 1;
+      } else {
+        if (launch_fused_primary(v->P, C, L, w, h, v->fb.p, v->next.v, v->rawhits.p, (unsigned)qcap, v->hits.v, v->cur.v,
+                                 can_spill[p] ? (unsigned)v->cur.cap : 0u, reinterpret_cast<FusedQueues *>(v->fq.p), epsilon, nullptr, nullptr, 0, 1,
+                                 st))
+          return 1;
+        S.kernel_launches += 3;
+        S.waves++;
+      }
       GXY_CUDA(cudaEventRecord(tb, st));
       trace_events.push_back(std::make_pair(ta, tb));
-      S.kernel_launches += 3;
-      S.waves++;
     }
     PT.mark("launchP");
     // ---- secondary rays.  A partition without neighbours cannot spill: no host round trip at all.
     for (int p = 0; p < nparts; p++) {
       gxy_vis *v = parts[p];
-      if (n_sec_per_hit == 0) continue;
+      if (n_sec_per_hit == 0 || n_bands > 1) continue;
       if (use_device(v->ctx)) return 1;
       cudaStream_t st = v->ctx->stream;
       long long max_rays = (long long)npix * n_sec_per_hit;
@@ -1179,15 +1266,24 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       S.kernel_launches += 1;
       S.waves++;
     }
+    std::vector<FusedQueues> bq((size_t)n_bands);
     for (int p = 0; p < nparts; p++) {
       gxy_vis *v = parts[p];
       if (use_device(v->ctx)) return 1;
-      GXY_CUDA(cudaMemcpyAsync(&fq[p], v->fq.p, sizeof(FusedQueues), cudaMemcpyDeviceToHost, v->ctx->stream));
+      GXY_CUDA(cudaMemcpyAsync(n_bands > 1 ? bq.data() : &fq[p], v->fq.p, (size_t)n_bands * sizeof(FusedQueues), cudaMemcpyDeviceToHost,
+                               v->ctx->stream));
     }
     for (int p = 0; p < nparts; p++) {
       gxy_vis *v = parts[p];
       if (use_device(v->ctx)) return 1;
       GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+      if (n_bands > 1) {  // the sum over the bands is the partition's frame
+        fq[p] = bq[0];
+        for (int b = 1; b < n_bands; b++) {
+          fq[p].n_generated += bq[b].n_generated; fq[p].n_hits += bq[b].n_hits; fq[p].n_terminated += bq[b].n_terminated;
+          fq[p].nodes += bq[b].nodes; fq[p].prims += bq[b].prims; fq[p].n_spill += bq[b].n_spill;
+        }
+      }
       S.primary_rays += (long long)fq[p].n_generated;
       S.ao_rays += (long long)fq[p].n_hits * lights.n_ao;
       S.shadow_rays += (long long)fq[p].n_hits * (lights.shadows ? lights.n_lights : 0);
@@ -1461,6 +1557,35 @@ int gxy_frame_download_rgba8(gxy_vis *v, unsigned char *rgba) {
   if (launch_tonemap(v->fb_result, v->fb_w, v->fb_h, v->rgba8.p, v->ctx->stream)) return 1;
   GXY_CUDA(cudaMemcpyAsync(rgba, v->rgba8.p, n, cudaMemcpyDeviceToHost, v->ctx->stream));
   GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  return 0;
+}
+
+int gxy_frame_download_rgba8_async(gxy_vis *v, unsigned char *rgba) {
+  if (check_vis(v)) return 1;
+  GXY_CHECK(v->fb_w > 0 && v->fb_result && rgba, "no frame rendered yet");
+  gxy_context *c = v->ctx;
+  if (!c->copy_stream) GXY_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  const int s = v->async_slot;
+  v->async_slot ^= 1;
+  if (!v->async_ready[s]) {
+    GXY_CUDA(cudaEventCreateWithFlags(&v->async_ready[s], cudaEventDisableTiming));
+    GXY_CUDA(cudaEventCreateWithFlags(&v->async_done[s], cudaEventDisableTiming));
+  } else {
+    GXY_CUDA(cudaStreamWaitEvent(c->stream, v->async_done[s], 0));  // the copy that last used this staging image
+  }
+  const size_t n = (size_t)v->fb_w * v->fb_h * 4;
+  if (v->rgba8_async[s].reserve(n)) return 1;
+  if (launch_tonemap(v->fb_result, v->fb_w, v->fb_h, v->rgba8_async[s].p, c->stream)) return 1;
+  GXY_CUDA(cudaEventRecord(v->async_ready[s], c->stream));
+  GXY_CUDA(cudaStreamWaitEvent(c->copy_stream, v->async_ready[s], 0));
+  GXY_CUDA(cudaMemcpyAsync(rgba, v->rgba8_async[s].p, n, cudaMemcpyDeviceToHost, c->copy_stream));
+  GXY_CUDA(cudaEventRecord(v->async_done[s], c->copy_stream));
+  return 0;
+}
+
+int gxy_frame_download_wait(gxy_vis *v) {
+  if (check_vis(v)) return 1;
+  if (v->ctx->copy_stream) GXY_CUDA(cudaStreamSynchronize(v->ctx->copy_stream));
   return 0;
 }
 

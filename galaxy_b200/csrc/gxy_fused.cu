@@ -29,10 +29,12 @@ namespace gxy {
 #define FULLMASK 0xffffffffu
 
 // pixel order of the primary queue: 8x4 tiles, so that the 32 lanes of a warp start as a compact beam
-__device__ __forceinline__ void tile_pixel(unsigned idx, int tiles_x, int &x, int &y) {
+// band / n_bands: the queue covers the tile rows band, band + n_bands, ... (frame split into interleaved bands that are
+// pipelined on two streams, gxy_render)
+__device__ __forceinline__ void tile_pixel(unsigned idx, int tiles_x, int band, int n_bands, int &x, int &y) {
   const unsigned tile = idx >> 5, in = idx & 31u;
   x = (int)(tile % (unsigned)tiles_x) * 8 + (int)(in & 7u);
-  y = (int)(tile / (unsigned)tiles_x) * 4 + (int)(in >> 3);
+  y = ((int)(tile / (unsigned)tiles_x) * n_bands + band) * 4 + (int)(in >> 3);
 }
 
 __device__ __forceinline__ void write_spill(const Rays &S, unsigned j, float3 org, float3 dir, float r, float g, float b, float o, float t,
@@ -96,15 +98,15 @@ __device__ __forceinline__ void peer_push(const PeerTable &T, int parity, unsign
 // hit (term BOUNDARY/TIMEOUT -> Classify: TERMINATED with colour 0, or on to the neighbour partition); the
 // others are appended (unordered) to `out` (columns ox..dz t x y; tMax = FLT_MAX, type PRIMARY implied).
 __global__ void __launch_bounds__(256)
-    gen_primary_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevCamera C, int w, int h, int tiles_x,
-                       unsigned n_queue, Rays out, Rays spill, unsigned spill_cap, FusedQueues *__restrict__ q) {
+    gen_primary_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevCamera C, int w, int h, int tiles_x, int band,
+                       int n_bands, unsigned n_queue, Rays out, Rays spill, unsigned spill_cap, FusedQueues *__restrict__ q) {
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
   bool kept = false, queued = false;
   int x = 0, y = 0;
   float3 o3 = f3(0.f, 0.f, 0.f), d3 = f3(0.f, 0.f, 0.f);
   if (idx < n_queue) {
-    tile_pixel(idx, tiles_x, x, y);
+    tile_pixel(idx, tiles_x, band, n_bands, x, y);
     kept = x < w && y < h && spawn_pixel(P, C, x, y, o3, d3);
   }
   bool do_spill = false, terminated = false;
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(256)
   float gmin = 0.f;
   bool in_data = false;
   if (idx < n_queue) {
-    tile_pixel(idx, tiles_x, x, y);
+    tile_pixel(idx, tiles_x, 0, 1, x, y);
     in_data = x < w && y < h && camera_ray(P, C, x, y, o3, d3, gmin);
   }
   unsigned n_gen = 0u, n_fwd = 0u, n_term = 0u;
@@ -759,6 +761,14 @@ static PeerTable no_peers() {
   return T;
 }
 
+// resident CTAs per SM a persistent trace launch asks for (8 = all the kernel is compiled for; the band pipeline of
+// gxy_render may ask for fewer so that the kernels of several bands share the SMs from the start)
+static unsigned fused_blocks_per_sm() {
+  unsigned b = 8u;
+  if (const char *e = getenv("GXY_FUSED_BLOCKS_PER_SM")) b = (unsigned)std::max(1, std::min(8, atoi(e)));
+  return b;
+}
+
 static int fetch_threshold(const char *env) {
   int ft = 12;  // measured optimum on the 100M-triangle scene (tools/trace_sweep.py, GXY_FETCH_SWEEP)
   if (const char *e = getenv(env)) ft = atoi(e);
@@ -766,22 +776,23 @@ static int fetch_threshold(const char *env) {
 }
 
 int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLights &L, int w, int h, float *fb, Rays prim, unsigned *raw,
-                         Rays hits, Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, const PeerTable *peer,
-                         const PartProxy *proxies, cudaStream_t st) {
+                         unsigned raw_stride, Rays hits, Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, const PeerTable *peer,
+                         const PartProxy *proxies, int band, int n_bands, cudaStream_t st) {
   if (ensure_ao_tables()) return 1;
   const int tiles_x = (w + 7) / 8, tiles_y = (h + 3) / 4;
-  const unsigned n_queue = (unsigned)tiles_x * (unsigned)tiles_y * 32u;
-  const unsigned npix = (unsigned)w * (unsigned)h;
+  const int rows = (tiles_y - band + n_bands - 1) / n_bands;  // tile rows band, band + n_bands, ...
+  if (rows <= 0) return 0;
+  const unsigned n_queue = (unsigned)tiles_x * (unsigned)rows * 32u;
   const PeerTable T = peer ? *peer : no_peers();
-  if (peer) gen_primary_peer_kernel<<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, n_queue, prim, npix, q, T.rank, T.nranks, proxies);
-  else gen_primary_kernel<<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, n_queue, prim, spill, spill_cap, q);
+  if (peer) gen_primary_peer_kernel<<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, n_queue, prim, raw_stride, q, T.rank, T.nranks, proxies);
+  else gen_primary_kernel<<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, band, n_bands, n_queue, prim, spill, spill_cap, q);
   gxy_timeline_mark("gen", st);
-  const unsigned needed = (npix + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
-  const unsigned blocks = std::min<unsigned>(needed, (unsigned)sm_count() * 8u);
-#define GXY_LAUNCH_P(FT)                                                                                                              \
-  do {                                                                                                                                \
-    if (peer) primary_trace_kernel<FT, 8, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q, T);    \
-    else primary_trace_kernel<FT, 8, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, npix, spill, spill_cap, q, T);         \
+  const unsigned needed = (n_queue + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
+  const unsigned blocks = std::min<unsigned>(needed, (unsigned)sm_count() * fused_blocks_per_sm());
+#define GXY_LAUNCH_P(FT)                                                                                                                 \
+  do {                                                                                                                                   \
+    if (peer) primary_trace_kernel<FT, 8, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T); \
+    else primary_trace_kernel<FT, 8, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T);      \
   } while (0)
   switch (fetch_threshold("GXY_FETCH_P")) {
     case 4: GXY_LAUNCH_P(4); break;
@@ -792,7 +803,8 @@ int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLigh
   }
 #undef GXY_LAUNCH_P
   gxy_timeline_mark("primary", st);
-  shade_hits_kernel<false><<<(npix + 255) / 256, 256, 0, st>>>(P, L, prim, nullptr, raw, npix, w, reinterpret_cast<float4 *>(fb), hits, q, epsilon);
+  shade_hits_kernel<false><<<(n_queue + 255) / 256, 256, 0, st>>>(P, L, prim, nullptr, raw, raw_stride, w, reinterpret_cast<float4 *>(fb), hits, q,
+                                                                  epsilon);
   GXY_CUDA(cudaGetLastError());
   return 0;
 }
@@ -803,7 +815,7 @@ int launch_fused_secondary(const SceneParams &P, const DevLights &L, int w, int 
   if (nsec <= 0 || max_rays <= 0) return 0;
   if (ensure_ao_tables()) return 1;
   const long long needed = (max_rays + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
-  const unsigned blocks = (unsigned)std::min<long long>(needed, (long long)sm_count() * 8);
+  const unsigned blocks = (unsigned)std::min<long long>(needed, (long long)sm_count() * fused_blocks_per_sm());
   const PeerTable T = peer ? *peer : no_peers();
 #define GXY_LAUNCH_S(FT)                                                                                                              \
   do {                                                                                                                                \

@@ -87,9 +87,11 @@ struct PeerTable {  // kernel parameter: every rank's arena as mapped in THIS pr
 // prim: list for the generated rays (>= w*h), raw: 6*w*h words of scratch, hits: >= w*h records
 // peer != NULL: proxies = the PartProxy of every rank in local memory (launch_proxy_gather); rays are then originated by the
 // first partition on their path whose proxy they may hit instead of being forwarded through the ones they cannot
+// band / n_bands: only the tile rows band, band + n_bands, ... of the window (gxy_render pipelines bands on two streams);
+// raw_stride: words per plane of `raw` (>= the number of rays this launch can queue)
 int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLights &L, int w, int h, float *fb, Rays prim, unsigned *raw,
-                         Rays hits, Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, const PeerTable *peer,
-                         const PartProxy *proxies, cudaStream_t st);
+                         unsigned raw_stride, Rays hits, Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, const PeerTable *peer,
+                         const PartProxy *proxies, int band, int n_bands, cudaStream_t st);
 // write this rank's PartProxy into its arena; after the next flag barrier ...
 int launch_proxy_publish(const SceneParams &P, const PeerTable &T, cudaStream_t st);
 // ... copy every rank's published PartProxy (peer loads) into the local table `out` (nranks entries)

@@ -103,6 +103,8 @@ def lib():
         L.gxy_render.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(Camera), C.POINTER(Lighting), C.c_int, C.c_int, C.c_float, C.POINTER(Stats)]
         L.gxy_frame_download_rgba32f.argtypes = [vp, fp]
         L.gxy_frame_download_rgba8.argtypes = [vp, C.POINTER(C.c_ubyte)]
+        L.gxy_frame_download_rgba8_async.argtypes = [vp, C.POINTER(C.c_ubyte)]
+        L.gxy_frame_download_wait.argtypes = [vp]
         L.gxy_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
         L.gxy_host_free.argtypes = [vp]
         L.gxy_comm_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
@@ -309,6 +311,13 @@ class Scene:
             out = np.empty((h, w, 4), np.uint8)
         check(lib().gxy_frame_download_rgba8(self.h, out.ctypes.data_as(C.POINTER(C.c_ubyte))))
         return out
+
+    def download_rgba8_async(self, out):
+        """Start the D2H of the last frame into `out` (a pinned_array); the next render overlaps it.  download_wait() before reading."""
+        check(lib().gxy_frame_download_rgba8_async(self.h, out.ctypes.data_as(C.POINTER(C.c_ubyte))))
+
+    def download_wait(self):
+        check(lib().gxy_frame_download_wait(self.h))
 
 
 class _Pinned:

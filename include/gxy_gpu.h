@@ -190,6 +190,14 @@ int  gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *, const gxy
 int  gxy_frame_download_rgba32f(gxy_vis *owner, float *fb);
 /* ... or RGBA8 rows top-down exactly as ColorImageWriter::Write does (ImageWriter.cpp:30-48) */
 int  gxy_frame_download_rgba8(gxy_vis *owner, unsigned char *rgba);
+/* The same without blocking: the image of the last frame is converted on the device and copied to `rgba` (page-locked
+ * memory from gxy_host_alloc, else the copy is not asynchronous) on a separate copy stream, so that the next gxy_render of
+ * this owner overlaps the transfer.  `rgba` is valid after gxy_frame_download_wait, which blocks until every pending
+ * asynchronous download of this owner has landed.  Two downloads may be in flight (two device-side staging images);
+ * a third one waits for the first.  The reference has no counterpart: its image writer runs after WaitForDone
+ * (src/apps/gxywriter.cpp:262-264). */
+int  gxy_frame_download_rgba8_async(gxy_vis *owner, unsigned char *rgba);
+int  gxy_frame_download_wait(gxy_vis *owner);
 
 /* Page-locked host memory for the buffers handed to gxy_frame_download_* / gxy_trace_raylist: with it
  * the D2H/H2D copies run at PCIe speed without a staging copy (any host pointer is accepted; pageable

@@ -128,3 +128,25 @@ def test_primary_ray_order_does_not_change_the_image(gpu, oracle, tiled, golden_
             del os.environ["GXY_TILED"]
         else:
             os.environ["GXY_TILED"] = old
+
+
+def test_async_download_equals_blocking_download(gpu, oracle, golden_dir, provider):
+    """gxy_frame_download_rgba8_async + _wait: two images in flight while later frames render, each equal to the blocking
+    download of the same frame."""
+    st, ds = util.load_state(golden_dir, "xyz", provider)
+    vis = st["visualizations"][0]
+    g = scenes.build_partitions(gpu, vis, ds, 1)[0]
+    cams = [dict(st["cameras"][0]), dict(st["cameras"][0], eye=[1.5, 2.0, -3.0], dir=[-1.5, -2.0, 3.0]), dict(st["cameras"][0], eye=[-2.0, 1.0, -3.0], dir=[2.0, -1.0, 3.0])]
+    w, h = 200, 120
+    want = []
+    for c in cams:
+        gpu.render_device([g], c, vis["lighting"], w, h, st["epsilon"])
+        want.append(g.download_rgba8(w, h).copy())
+    bufs = [gpu.pinned_array((h, w, 4), np.uint8) for _ in cams]
+    for c, b in zip(cams, bufs):
+        gpu.render_device([g], c, vis["lighting"], w, h, st["epsilon"])
+        g.download_rgba8_async(b)  # not waited for: the next render overlaps the copy
+    g.download_wait()
+    for a, b in zip(want, bufs):
+        assert np.array_equal(a, b)
+    assert not np.array_equal(want[0], want[1])
