@@ -994,6 +994,7 @@ static int render_peer(gxy_vis *v, const DevCamera &C, const DevLights &L, const
   };
   // ---- every rank publishes its partition proxy (box, neighbours, top of the BVH) and collects everybody's
   const bool spawn = n_sec_per_hit > 0;
+  const bool peer_overlap = !(getenv("GXY_PEER_OVERLAP") && atoi(getenv("GXY_PEER_OVERLAP")) == 0);
   PartProxy *proxies = reinterpret_cast<PartProxy *>(v->proxies.p);
   if (launch_proxy_publish(v->P, T, st)) return 1;
   if (launch_wave_epilogue(T, q, ++A.epoch, -1, false, v->d_error, st)) return 1;
@@ -1022,13 +1023,28 @@ static int render_peer(gxy_vis *v, const DevCamera &C, const DevLights &L, const
       k++;
       const int parity_in = (k - 1) & 1;
       if (ev_begin()) return 1;
-      // AO/shadow rays of the hits the previous wave found (leavers go to inboxes[k&1]) ...
+      // AO/shadow rays of the hits the previous wave found (leavers go to inboxes[k&1]) on a second stream ...
+      cudaStream_t s2 = st;
+      if (spawn && peer_overlap) {
+        if (!c->ev_fork) GXY_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        if (!c->lanes[1]) {
+          GXY_CUDA(cudaStreamCreateWithFlags(&c->lanes[1], cudaStreamNonBlocking));
+          GXY_CUDA(cudaEventCreateWithFlags(&c->ev_join[1], cudaEventDisableTiming));
+        }
+        s2 = c->lanes[1];
+        GXY_CUDA(cudaEventRecord(c->ev_fork, st));
+        GXY_CUDA(cudaStreamWaitEvent(s2, c->ev_fork, 0));
+      }
       if (spawn && launch_fused_secondary(v->P, L, w, h, n_sec_per_hit, (long long)npix * n_sec_per_hit, fb, v->hits.v, v->cur.v, 0u, q, epsilon,
-                                          !v->has_dvr, &T, k & 1, st))
+                                          !v->has_dvr, &T, k & 1, s2))
         return 1;
-      gxy_timeline_mark("secondary", st);
-      // ... and the rays the neighbours sent during the previous wave
+      gxy_timeline_mark("secondary", s2);
+      // ... while this stream traces the rays the neighbours sent during the previous wave (the two only share atomic counters)
       if (launch_inbox_wave(v->P, L, T, parity_in, w, h, fb, v->rawhits.p, (unsigned)npix, v->hits.v, q, epsilon, !v->has_dvr, st)) return 1;
+      if (s2 != st) {
+        GXY_CUDA(cudaEventRecord(c->ev_join[1], s2));
+        GXY_CUDA(cudaStreamWaitEvent(st, c->ev_join[1], 0));
+      }
       if (ev_end()) return 1;
       gxy_timeline_mark("inbox+shade", st);
       if (launch_wave_epilogue(T, q, ++A.epoch, parity_in, spawn, v->d_error, st)) return 1;
