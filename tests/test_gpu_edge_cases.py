@@ -150,3 +150,24 @@ def test_async_download_equals_blocking_download(gpu, oracle, golden_dir, provid
     for a, b in zip(want, bufs):
         assert np.array_equal(a, b)
     assert not np.array_equal(want[0], want[1])
+
+
+@pytest.mark.parametrize("bands,streams", [("1", "1"), ("3", "3"), ("4", "2"), ("7", "7")])
+def test_band_pipeline_renders_the_same_frame(gpu, oracle, bands, streams):
+    """GXY_BANDS / GXY_BAND_STREAMS: the single-GPU fused frame split into interleaved bands of tile rows on several streams
+    (gxy_render) against the oracle, at a window whose tile rows do not divide evenly among the bands."""
+    tri = scenes.eightballs_mesh(40, 80)
+    ds = {"tris": tri}
+    vis = util.soup_vis(False)
+    cam = dict(eye=[3.0, 2.0, -4.0], dir=[-3.0, -2.0, 4.0], up=[0.0, 1.0, 0.0], aov=30.0, annotation="")
+    old = {k: os.environ.get(k) for k in ("GXY_BANDS", "GXY_BAND_STREAMS")}
+    os.environ["GXY_BANDS"], os.environ["GXY_BAND_STREAMS"] = bands, streams
+    try:
+        fb, st = both(gpu, oracle, vis, ds, cam, 333, 217)
+        assert st["ao_rays"] > 0 and st["shadow_rays"] > 0
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
