@@ -233,23 +233,32 @@ __device__ __forceinline__ void node_eval(const WideNode *__restrict__ nodes, co
   tg_out = make_uint2(n1.y, hitmask & 0x00ffffffu);
 }
 
-// Conservative cull (generation kernel): false only if the ray (interval of rc) cannot reach any primitive --
-// no child box of the root is hit, or none of the boxes one level below those.  Box tests are conservative
-// (see above), so a culled ray has no candidate and the full traversal would return "no hit".
-// nodes: the tree itself, or a 9-node excerpt of it (root with child_base = 1, followed by its internal children).
+// Conservative cull (generation kernel): false only if the ray (interval of rc) cannot reach any primitive -- no child
+// box of the root is hit, or none of the boxes LEVELS levels below those.  Box tests are conservative (see above), so a
+// culled ray has no candidate and the full traversal would return "no hit".
+// nodes: the tree itself, or (LEVELS = 1) a 9-node excerpt of it (root with child_base = 1, followed by its internal children).
+template <int D>
+__device__ __forceinline__ bool cull_group(const WideNode *__restrict__ nodes, const RayCtx &rc, uint2 g) {
+  unsigned pending = g.y;
+  while (pending > 0x00ffffffu) {
+    const int bit = 31 - __clz((int)pending);
+    pending &= ~(1u << bit);
+    uint2 ng, tg;
+    node_eval(nodes, rc, g.x, g.y, bit, rc.tfar, ng, tg);
+    if (tg.y != 0u) return true;
+    if (ng.y > 0x00ffffffu) {
+      if constexpr (D <= 1) return true;
+      else if (cull_group<D - 1>(nodes, rc, ng)) return true;
+    }
+  }
+  return false;
+}
+template <int LEVELS = 1>
 __device__ __forceinline__ bool may_hit_anything(const WideNode *__restrict__ nodes, const RayCtx &rc) {
   uint2 ng, tg;
   node_eval(nodes, rc, 0u, 0x80000000u, 31, rc.tfar, ng, tg);
   if (tg.y != 0u) return true;
-  unsigned pending = ng.y;
-  while (pending > 0x00ffffffu) {
-    const int bit = 31 - __clz((int)pending);
-    pending &= ~(1u << bit);
-    uint2 ng2, tg2;
-    node_eval(nodes, rc, ng.x, ng.y, bit, rc.tfar, ng2, tg2);
-    if (tg2.y != 0u || ng2.y > 0x00ffffffu) return true;
-  }
-  return false;
+  return cull_group<LEVELS>(nodes, rc, ng);
 }
 
 // Node phase: pop the nearest unvisited internal child of the node group (requires s.ng.y > 0x00ffffff)
