@@ -1,6 +1,7 @@
 // gxy_host.cpp -- see gxy_host.h.  Compiled with -ffp-contract=off: the few float expressions here (light
 // normalisation, partition boxes) decide planes and directions that must be bit-identical to the oracle's.
 #include "gxy_host.h"
+#include "gxy_vtu.h"
 
 #include <zlib.h>
 
@@ -153,9 +154,19 @@ static bool load_typed(const json::Value &v, const std::string &state_dir, Datas
     out.volumes.push_back(vol);
     return true;
   }
-  if (type == "Particles" || type == "Triangles" || type == "PathLines") {
-    std::cerr << "Dataset type " << type << ": the reference reads these through VTK (Geometry.cpp:176-257); "
-              << "no VTK-free reader is built into this driver yet\n";
+  if (type == "Particles" || type == "Triangles") {
+    Geometry g;
+    g.type = type;
+    std::string fn = v["filename"].GetString();
+    if (!fn.empty() && fn[0] != '/') fn = state_dir + fn;
+    if (!g.Import(fn)) return false;
+    if (v.HasMember("name")) name = v["name"].GetString();
+    g.name = name;
+    out.geometries.push_back(g);
+    return true;
+  }
+  if (type == "PathLines") {
+    std::cerr << "Dataset type PathLines is not supported by this driver (no curve primitive behind the C ABI yet)\n";
     return false;
   }
   std::cerr << "invalid Dataset type: " << type << "\n";
@@ -174,6 +185,109 @@ bool Datasets::LoadFromJSON(const json::Value &doc, const std::string &state_dir
     return true;
   }
   return load_typed(ds, state_dir, *this);
+}
+
+const Geometry *Datasets::FindGeometry(const std::string &name) const {
+  for (const Geometry &g : geometries)
+    if (g.name == name) return &g;
+  return nullptr;
+}
+
+// ---- Geometry ------------------------------------------------------------------------------------
+bool Geometry::Import(const std::string &fname) {
+  filename = fname;
+  json::Value doc;
+  try {
+    doc = json::ParseFile(fname);
+  } catch (const std::exception &e) {
+    std::cerr << "parse error in partition document: " << fname << " (" << e.what() << ")\n";
+    return false;
+  }
+  if (!doc.HasMember("parts")) {
+    std::cerr << "partition document does not have parts\n";  // Geometry.cpp:283-288
+    return false;
+  }
+  const json::Value &parts = doc["parts"];
+  if (!parts.IsArray() || parts.Size() == 0) {
+    std::cerr << "invalid partition document\n";
+    return false;
+  }
+  const std::string dir = dir_of(fname);
+  try {
+    for (size_t i = 0; i < parts.Size(); i++) {
+      if (!parts[i].HasMember("filename")) {
+        std::cerr << "partition document: only file parts are supported (part " << i << " has no filename)\n";
+        return false;
+      }
+      std::string f = parts[i]["filename"].GetString();
+      if (!f.empty() && f[0] != '/') f = dir + f;
+      part_files.push_back(f);
+      for (int j = 0; j < 6; j++) extents.push_back((float)parts[i]["extent"][j].GetDouble());
+    }
+  } catch (const std::exception &e) {
+    std::cerr << "invalid partition document: " << e.what() << "\n";
+    return false;
+  }
+  return true;
+}
+
+void Geometry::Boxes(int rank, float gmin[3], float gmax[3], float lmin[3], float lmax[3], int neighbors[6]) const {
+  float g[6] = {3.402823466e+38f, -3.402823466e+38f, 3.402823466e+38f, -3.402823466e+38f, 3.402823466e+38f, -3.402823466e+38f};
+  const float *l = &extents[(size_t)rank * 6];
+  for (int i = 0; i < 6; i++) neighbors[i] = -1;
+  for (int i = 0; i < NumberOfParts(); i++) {
+    const float *e = &extents[(size_t)i * 6];
+    for (int a = 0; a < 3; a++) {
+      if (e[2 * a] < g[2 * a]) g[2 * a] = e[2 * a];
+      if (e[2 * a + 1] > g[2 * a + 1]) g[2 * a + 1] = e[2 * a + 1];
+    }
+    auto LAST = [&](int a) { return e[2 * a + 1] == l[2 * a]; };
+    auto NEXT = [&](int a) { return e[2 * a] == l[2 * a + 1]; };
+    auto EQ = [&](int a) { return e[2 * a] == l[2 * a]; };
+    if (LAST(0) && EQ(1) && EQ(2)) neighbors[0] = i;
+    if (NEXT(0) && EQ(1) && EQ(2)) neighbors[1] = i;
+    if (EQ(0) && LAST(1) && EQ(2)) neighbors[2] = i;
+    if (EQ(0) && NEXT(1) && EQ(2)) neighbors[3] = i;
+    if (EQ(0) && EQ(1) && LAST(2)) neighbors[4] = i;
+    if (EQ(0) && EQ(1) && NEXT(2)) neighbors[5] = i;
+  }
+  for (int a = 0; a < 3; a++) { gmin[a] = g[2 * a]; gmax[a] = g[2 * a + 1]; lmin[a] = l[2 * a]; lmax[a] = l[2 * a + 1]; }
+}
+
+bool Geometry::LoadPiece(int rank, GeometryPiece &out) const {
+  VtuData d;
+  std::string err;
+  if (!read_vtu(part_files[(size_t)rank], d, err)) {
+    std::cerr << "error reading " << part_files[(size_t)rank] << ": " << err << "\n";
+    return false;
+  }
+  const size_t nv = (size_t)d.n_points;
+  out.vertices = d.points;
+  if (type == "Triangles") {
+    if (d.normals.empty()) {  // Triangles.cpp:107-118
+      if (nv) std::cerr << "triangle set has no normals\n";
+      out.normals.resize(3 * nv);
+      for (size_t i = 0; i < nv; i++) { out.normals[3 * i] = 1.0f; out.normals[3 * i + 1] = 0.0f; out.normals[3 * i + 2] = 0.0f; }
+    } else {
+      out.normals = d.normals;
+    }
+    long long prev = 0;
+    for (long long o : d.offsets) {
+      if (o - prev != 3) {
+        std::cerr << part_files[(size_t)rank] << ": a Triangles dataset may only hold triangle cells\n";
+        return false;
+      }
+      prev = o;
+    }
+    if (d.connectivity.size() % 3) {
+      std::cerr << part_files[(size_t)rank] << ": connectivity is not a list of triangles\n";
+      return false;
+    }
+    out.connectivity = d.connectivity;
+  }
+  out.data = d.scalars;
+  if (out.data.empty()) out.data.assign(nv, 0.0f);  // Triangles.cpp:127-132 / Particles.cpp:124
+  return true;
 }
 
 const Volume *Datasets::FindVolume(const std::string &name) const {
@@ -335,6 +449,12 @@ bool Vis::LoadFromJSON(const json::Value &v) {
         for (int k = 0; k < 4; k++) slices.push_back((float)v["plane"][k].GetDouble());
       }
       volume_render = v.HasMember("volume rendering") ? v["volume rendering"].GetBool() : false;
+    } else if (type == "ParticlesVis") {  // ParticlesVis.cpp:104-118
+      if (v.HasMember("radius0")) radius0 = (float)v["radius0"].GetDouble();
+      if (v.HasMember("radius1")) radius1 = (float)v["radius1"].GetDouble();
+      if (v.HasMember("value0")) value0 = (float)v["value0"].GetDouble();
+      if (v.HasMember("value1")) value1 = (float)v["value1"].GetDouble();
+      if (v.HasMember("radius")) { radius0 = (float)v["radius"].GetDouble(); radius1 = 0.f; value0 = 0.f; value1 = 0.f; }
     }
   } catch (const std::exception &e) {
     std::cerr << "error loading a Vis: " << e.what() << "\n";
@@ -351,6 +471,10 @@ void Visualization::Release() {
   parts.clear();
   for (gxy_volume *v : owned_volumes) gxy_volume_destroy(v);
   owned_volumes.clear();
+  for (gxy_triangles *t : owned_triangles) gxy_triangles_destroy(t);
+  owned_triangles.clear();
+  for (gxy_particles *p : owned_particles) gxy_particles_destroy(p);
+  owned_particles.clear();
 }
 
 bool Visualization::LoadFromJSON(const json::Value &v) {
@@ -406,8 +530,56 @@ bool Visualization::Commit(gxy_context *ctx, const Datasets &datasets, int npart
     bool boxes_set = false;
     std::vector<std::pair<std::string, gxy_volume *>> vols;  // one device volume per dataset and partition
     for (const Vis &op : operators) {
+      if (op.type == "TrianglesVis" || op.type == "ParticlesVis") {
+        const Geometry *geo = datasets.FindGeometry(op.dataset);
+        if (!geo) {
+          std::cerr << "Unable to find data using name: " << op.dataset << "\n";
+          return false;
+        }
+        if ((geo->type == "Triangles") != (op.type == "TrianglesVis")) {
+          std::cerr << op.type << " on a " << geo->type << " dataset (" << op.dataset << ")\n";
+          return false;
+        }
+        if (geo->NumberOfParts() != nparts) {
+          std::cerr << "invalid partition document: " << geo->filename << " has " << geo->NumberOfParts() << " parts for " << nparts
+                    << " partitions\n";  // Geometry.cpp:291-296
+          return false;
+        }
+        if (!boxes_set) {
+          float gmin[3], gmax[3], lmin[3], lmax[3];
+          int nb[6];
+          geo->Boxes(r, gmin, gmax, lmin, lmax, nb);
+          if (!check_abi(gxy_vis_set_partition(vis, gmin, gmax, lmin, lmax, nb), "gxy_vis_set_partition")) return false;
+          boxes_set = true;
+        }
+        GeometryPiece piece;
+        if (!geo->LoadPiece(r, piece)) return false;
+        gxy_transfer_function gtf;
+        if (!check_abi(gxy_resample_transfer_function((int)op.colormap.size() / 4, op.colormap.data(), (int)op.opacitymap.size() / 2,
+                                                      op.opacitymap.data(), &gtf),
+                       "gxy_resample_transfer_function"))
+          return false;
+        gtf.range_lo = op.has_range ? op.range[0] : op.colormap[0];
+        gtf.range_hi = op.has_range ? op.range[1] : op.colormap[op.colormap.size() - 4];
+        const int nv = (int)(piece.vertices.size() / 3);
+        if (op.type == "TrianglesVis") {
+          gxy_triangles *gt = nullptr;
+          if (!check_abi(gxy_triangles_create(ctx, nv, piece.vertices.data(), piece.normals.data(), piece.data.data(),
+                                              (int)(piece.connectivity.size() / 3), piece.connectivity.data(), &gt),
+                         "gxy_triangles_create"))
+            return false;
+          owned_triangles.push_back(gt);
+          if (!check_abi(gxy_vis_add_triangles(vis, gt, &gtf), "gxy_vis_add_triangles")) return false;
+        } else {
+          gxy_particles *gp = nullptr;
+          if (!check_abi(gxy_particles_create(ctx, nv, piece.vertices.data(), piece.data.data(), &gp), "gxy_particles_create")) return false;
+          owned_particles.push_back(gp);
+          if (!check_abi(gxy_vis_add_particles(vis, gp, op.radius0, op.radius1, op.value0, op.value1, &gtf), "gxy_vis_add_particles")) return false;
+        }
+        continue;
+      }
       if (op.type != "VolumeVis") {
-        std::cerr << op.type << ": geometry datasets cannot be loaded by this driver yet\n";
+        std::cerr << op.type << " is not supported by this driver\n";
         return false;
       }
       const Volume *vol = datasets.FindVolume(op.dataset);
@@ -655,6 +827,40 @@ std::string describe_state(const Renderer &r, const std::vector<Camera> &cams, c
       o << ", \"gcounts\": ";
       put_ints(o, p.gcounts, 3);
       o << "}";
+    }
+    o << "]}";
+  }
+  o << "], \"geometries\": [";
+  auto fnv = [](const void *data, size_t n) {
+    unsigned long long h = 1469598103934665603ull;
+    const unsigned char *b = static_cast<const unsigned char *>(data);
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+  };
+  for (size_t i = 0; i < ds.geometries.size(); i++) {
+    const Geometry &g = ds.geometries[i];
+    o << (i ? ", " : "") << "{\"name\": " << quoted(g.name) << ", \"type\": " << quoted(g.type) << ", \"parts\": [";
+    for (int r2 = 0; r2 < g.NumberOfParts(); r2++) {
+      float gmin[3], gmax[3], lmin[3], lmax[3];
+      int nb[6];
+      g.Boxes(r2, gmin, gmax, lmin, lmax, nb);
+      GeometryPiece piece;
+      const bool ok = g.LoadPiece(r2, piece);
+      o << (r2 ? ", " : "") << "{\"loaded\": " << (ok ? "true" : "false") << ", \"gmin\": ";
+      put_floats(o, gmin, 3);
+      o << ", \"gmax\": ";
+      put_floats(o, gmax, 3);
+      o << ", \"lmin\": ";
+      put_floats(o, lmin, 3);
+      o << ", \"lmax\": ";
+      put_floats(o, lmax, 3);
+      o << ", \"neighbors\": ";
+      put_ints(o, nb, 6);
+      o << ", \"n_vertices\": " << piece.vertices.size() / 3 << ", \"n_connectivity\": " << piece.connectivity.size();
+      o << ", \"hash_vertices\": \"" << fnv(piece.vertices.data(), piece.vertices.size() * 4) << "\"";
+      o << ", \"hash_normals\": \"" << fnv(piece.normals.data(), piece.normals.size() * 4) << "\"";
+      o << ", \"hash_data\": \"" << fnv(piece.data.data(), piece.data.size() * 4) << "\"";
+      o << ", \"hash_connectivity\": \"" << fnv(piece.connectivity.data(), piece.connectivity.size() * 4) << "\"}";
     }
     o << "]}";
   }

@@ -15,9 +15,9 @@
 //   Renderer (src/renderer/Renderer.cpp:125,289-296)         gxy::Renderer       (epsilon)
 //   ColorImageWriter / write_png (ImageWriter.cpp:30-67)     gxy::write_png      (zlib; libpng is not needed)
 //
-// Geometry datasets (Triangles / Particles / PathLines) are read by the reference through VTK
-// (src/data/Geometry.cpp:176-257); a VTK-free .vtu/.vtp reader is not part of this file yet: LoadFromJSON
-// reports them as unsupported instead of guessing.
+//   Geometry / Triangles / Particles (src/data/Geometry.cpp:176-344,  gxy::Geometry  (partition document + .vtu/.vtp pieces through
+//     Triangles.cpp:79-146, Particles.cpp:90-129)                          the VTK-free reader of gxy_vtu.h)
+// PathLines datasets are not supported (their Bezier-curve primitive is not part of the C ABI yet): LoadFromJSON says so.
 #pragma once
 #include <string>
 #include <vector>
@@ -50,11 +50,32 @@ class Volume {
   int number_of_components = 1;
 };
 
+// One partition of a geometry dataset as the reference holds it after load_from_vtkPointSet
+struct GeometryPiece {
+  std::vector<float> vertices, normals, data;  // 3, 3, 1 per vertex
+  std::vector<int> connectivity;               // Triangles: 3 per triangle
+};
+
+// Geometry::local_import / get_partitioning (src/data/Geometry.cpp:176-344): the dataset file is a partition document
+// {"parts": [{"filename": "piece.vtu", "extent": [x0,x1,y0,y1,z0,z1]}, ...]} with one part per rank
+class Geometry {
+ public:
+  bool Import(const std::string &filename);
+  int NumberOfParts() const { return (int)part_files.size(); }
+  bool LoadPiece(int rank, GeometryPiece &out) const;  // Triangles / Particles ::load_from_vtkPointSet
+  void Boxes(int rank, float gmin[3], float gmax[3], float lmin[3], float lmax[3], int neighbors[6]) const;
+  std::string name, type, filename;                    // type: "Triangles" | "Particles"
+  std::vector<std::string> part_files;
+  std::vector<float> extents;                          // 6 per part, stored as float like the reference
+};
+
 class Datasets {
  public:
   bool LoadFromJSON(const json::Value &doc, const std::string &state_dir);
   const Volume *FindVolume(const std::string &name) const;
+  const Geometry *FindGeometry(const std::string &name) const;
   std::vector<Volume> volumes;
+  std::vector<Geometry> geometries;
 };
 
 class Camera {
@@ -83,6 +104,7 @@ struct Vis {
   float range[2] = {0, 1};
   std::vector<float> isovalues, slices;  // slices: k x (a,b,c,d)
   bool volume_render = false;
+  float radius0 = 0.025f, radius1 = 0.f, value0 = 0.f, value1 = 0.f;  // ParticlesVis (ParticlesVis.cpp:46-55,104-118)
   bool LoadFromJSON(const json::Value &v);
 };
 
@@ -99,6 +121,8 @@ class Visualization {
   std::vector<Vis> operators;
   std::vector<gxy_vis *> parts;
   std::vector<gxy_volume *> owned_volumes;
+  std::vector<gxy_triangles *> owned_triangles;
+  std::vector<gxy_particles *> owned_particles;
 };
 
 class Renderer {
