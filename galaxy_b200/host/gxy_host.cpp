@@ -297,10 +297,46 @@ const Volume *Datasets::FindVolume(const std::string &name) const {
 }
 
 // ---- Camera --------------------------------------------------------------------------------------
-bool Camera::LoadFromJSON(const json::Value &v) {
-  if (v.IsString()) {
-    std::cerr << "camera files (.pvcc / ParaView JSON) are not read by this driver: " << v.GetString() << "\n";
-    return false;
+static std::string resolve_path(const std::string &name, const std::string &base_dir) {
+  if (name.empty() || name[0] == '/' || base_dir.empty()) return name;
+  std::ifstream probe((base_dir + name).c_str());
+  return probe ? base_dir + name : name;  // the reference resolves against the working directory
+}
+
+bool Camera::LoadFromJSON(const json::Value &v, const std::string &base_dir) {
+  if (v.IsString()) {  // Camera.cpp:168-232: a ParaView camera configuration converted to JSON
+    const std::string fname = resolve_path(v.GetString(), base_dir);
+    json::Value doc;
+    try {
+      doc = json::ParseFile(fname);
+    } catch (const std::exception &e) {
+      std::cerr << "error loading camera from " << v.GetString() << " (" << e.what() << "; XML .pvcc files are not read by this driver)\n";
+      return false;
+    }
+    try {
+      if (!doc.HasMember("PVCameraConfiguration") || !doc["PVCameraConfiguration"].HasMember("Proxy") ||
+          !doc["PVCameraConfiguration"]["Proxy"].HasMember("Property")) {
+        std::cerr << "invalid Paraview camera file: " << v.GetString() << "\n";
+        return false;
+      }
+      const json::Value &props = doc["PVCameraConfiguration"]["Proxy"]["Property"];
+      float center[3] = {0, 0, 0};
+      for (size_t i = 0; i < props.Size(); i++) {
+        const json::Value &p = props[i];
+        if (!p.HasMember("@name")) continue;
+        const std::string name = p["@name"].GetString();
+        auto elem = [&](int k) { return (float)atof(p["Element"][(size_t)k]["@value"].GetString().c_str()); };
+        if (name == "CameraPosition") for (int k = 0; k < 3; k++) eye[k] = elem(k);
+        else if (name == "CameraFocalPoint") for (int k = 0; k < 3; k++) center[k] = elem(k);
+        else if (name == "CameraViewUp") for (int k = 0; k < 3; k++) up[k] = elem(k);
+        else if (name == "CameraViewAngle") aov = (float)atof(p["Element"]["@value"].GetString().c_str());
+      }
+      for (int k = 0; k < 3; k++) dir[k] = center[k] - eye[k];
+    } catch (const std::exception &e) {
+      std::cerr << "invalid Paraview camera file: " << v.GetString() << " (" << e.what() << ")\n";
+      return false;
+    }
+    return true;
   }
   try {
     if (v.HasMember("annotation")) annotation = v["annotation"].GetString();
@@ -326,7 +362,7 @@ bool Camera::LoadFromJSON(const json::Value &v) {
   return true;
 }
 
-bool Camera::LoadCamerasFromJSON(const json::Value &doc, std::vector<Camera> &out) {
+bool Camera::LoadCamerasFromJSON(const json::Value &doc, std::vector<Camera> &out, const std::string &base_dir) {
   const json::Value *c = doc.Find("Cameras");
   if (!c) c = doc.Find("Camera");
   if (!c) {
@@ -336,12 +372,12 @@ bool Camera::LoadCamerasFromJSON(const json::Value &doc, std::vector<Camera> &ou
   if (c->IsArray()) {
     for (size_t i = 0; i < c->Size(); i++) {
       Camera cam;
-      if (!cam.LoadFromJSON((*c)[i])) return false;
+      if (!cam.LoadFromJSON((*c)[i], base_dir)) return false;
       out.push_back(cam);
     }
   } else {
     Camera cam;
-    if (!cam.LoadFromJSON(*c)) return false;
+    if (!cam.LoadFromJSON(*c, base_dir)) return false;
     out.push_back(cam);
   }
   return true;
@@ -405,7 +441,7 @@ bool Lighting::LoadStateFromValue(const json::Value &v) {
 }
 
 // ---- Vis -----------------------------------------------------------------------------------------
-bool Vis::LoadFromJSON(const json::Value &v) {
+bool Vis::LoadFromJSON(const json::Value &v, const std::string &base_dir) {
   try {
     type = v["type"].GetString();
     if (type.size() < 3 || type.compare(type.size() - 3, 3, "Vis")) type += "Vis";  // Visualization.cpp:318-320
@@ -419,11 +455,33 @@ bool Vis::LoadFromJSON(const json::Value &v) {
     opacitymap = {0.0f, 1.0f, 1.0f, 1.0f};
     const json::Value *m = v.Find("transfer function");
     if (!m) m = v.Find("colormap");
-    if (m && m->IsString()) {
-      std::cerr << "colormap files (ParaView JSON) are not read by this driver: " << m->GetString() << "\n";
-      return false;
-    }
-    if (m) {
+    if (m && m->IsString()) {  // MappedVis.cpp:104-166: a ParaView colormap export ("RGBPoints", optional "Points")
+      const std::string fname = m->GetString();
+      if (!fname.empty() && fname != "default") {
+        json::Value doc;
+        try {
+          doc = json::ParseFile(resolve_path(fname, base_dir));
+        } catch (const std::exception &e) {
+          std::cerr << "unable to open transfer function file: " << fname << " (" << e.what() << ")\n";
+          return false;
+        }
+        const json::Value &cmap = doc.IsArray() ? doc[0] : doc;
+        opacitymap.clear();
+        if (cmap.HasMember("Points")) {
+          const json::Value &oa = cmap["Points"];
+          for (size_t i = 0; i + 1 < oa.Size(); i += 4) {
+            opacitymap.push_back((float)oa[i].GetDouble());
+            opacitymap.push_back((float)oa[i + 1].GetDouble());
+          }
+        } else {
+          opacitymap = {0.0f, 1.0f, 1.0f, 1.0f};
+        }
+        colormap.clear();
+        const json::Value &rgba = cmap["RGBPoints"];
+        for (size_t i = 0; i + 3 < rgba.Size(); i += 4)
+          for (int k = 0; k < 4; k++) colormap.push_back((float)rgba[i + k].GetDouble());
+      }
+    } else if (m) {
       colormap.clear();
       for (size_t i = 0; i < m->Size(); i++)
         for (int k = 0; k < 4; k++) colormap.push_back((float)(*m)[i][k].GetDouble());
@@ -477,7 +535,7 @@ void Visualization::Release() {
   owned_particles.clear();
 }
 
-bool Visualization::LoadFromJSON(const json::Value &v) {
+bool Visualization::LoadFromJSON(const json::Value &v, const std::string &base_dir) {
   try {
     if (v.HasMember("annotation")) annotation = v["annotation"].GetString();
     const json::Value *l = v.Find("Lighting");
@@ -490,7 +548,7 @@ bool Visualization::LoadFromJSON(const json::Value &v) {
     const json::Value &ops = v["operators"];
     for (size_t i = 0; i < ops.Size(); i++) {
       Vis op;
-      if (!op.LoadFromJSON(ops[i])) return false;
+      if (!op.LoadFromJSON(ops[i], base_dir)) return false;
       operators.push_back(op);
     }
   } catch (const std::exception &e) {
@@ -500,7 +558,7 @@ bool Visualization::LoadFromJSON(const json::Value &v) {
   return true;
 }
 
-bool Visualization::LoadVisualizationsFromJSON(const json::Value &doc, std::vector<Visualization> &out) {
+bool Visualization::LoadVisualizationsFromJSON(const json::Value &doc, std::vector<Visualization> &out, const std::string &base_dir) {
   const json::Value *v = doc.Find("Visualization");
   if (!v) v = doc.Find("Visualizations");
   if (!v) {
@@ -510,7 +568,7 @@ bool Visualization::LoadVisualizationsFromJSON(const json::Value &doc, std::vect
   const size_t n = v->IsArray() ? v->Size() : 1;
   out.resize(n);  // in place: a Visualization owns device handles and is not copyable in spirit
   for (size_t i = 0; i < n; i++)
-    if (!out[i].LoadFromJSON(v->IsArray() ? (*v)[i] : *v)) return false;
+    if (!out[i].LoadFromJSON(v->IsArray() ? (*v)[i] : *v, base_dir)) return false;
   return true;
 }
 

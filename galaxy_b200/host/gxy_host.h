@@ -80,8 +80,9 @@ class Datasets {
 
 class Camera {
  public:
-  bool LoadFromJSON(const json::Value &v);
-  static bool LoadCamerasFromJSON(const json::Value &doc, std::vector<Camera> &out);
+  // v: a camera object, or the name of a ParaView camera file in JSON form (Camera.cpp:168-232; XML .pvcc files are refused)
+  bool LoadFromJSON(const json::Value &v, const std::string &base_dir = "");
+  static bool LoadCamerasFromJSON(const json::Value &doc, std::vector<Camera> &out, const std::string &base_dir = "");
   gxy_camera AsABI() const;
   float eye[3] = {0, 0, 0}, dir[3] = {0, 0, 1}, up[3] = {0, 1, 0}, aov = 30.f;
   int width = 512, height = 512;  // Camera.h:203-204
@@ -105,14 +106,15 @@ struct Vis {
   std::vector<float> isovalues, slices;  // slices: k x (a,b,c,d)
   bool volume_render = false;
   float radius0 = 0.025f, radius1 = 0.f, value0 = 0.f, value1 = 0.f;  // ParticlesVis (ParticlesVis.cpp:46-55,104-118)
-  bool LoadFromJSON(const json::Value &v);
+  // base_dir: where a "colormap" / "transfer function" given as a file name (ParaView JSON, MappedVis.cpp:104-166) is looked up
+  bool LoadFromJSON(const json::Value &v, const std::string &base_dir = "");
 };
 
 class Visualization {
  public:
   ~Visualization();
-  bool LoadFromJSON(const json::Value &v);
-  static bool LoadVisualizationsFromJSON(const json::Value &doc, std::vector<Visualization> &out);
+  bool LoadFromJSON(const json::Value &v, const std::string &base_dir = "");
+  static bool LoadVisualizationsFromJSON(const json::Value &doc, std::vector<Visualization> &out, const std::string &base_dir = "");
   // builds one gxy_vis per partition (all on `ctx`'s device) from the datasets
   bool Commit(gxy_context *ctx, const Datasets &datasets, int nparts);
   void Release();

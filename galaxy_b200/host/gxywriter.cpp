@@ -61,11 +61,11 @@ int main(int argc, char *argv[]) {
   gxy::Renderer theRenderer;
   theRenderer.LoadStateFromDocument(doc);
   std::vector<gxy::Camera> theCameras;
-  if (!gxy::Camera::LoadCamerasFromJSON(doc, theCameras)) { std::cerr << "error loading cameras\n"; return 1; }
+  if (!gxy::Camera::LoadCamerasFromJSON(doc, theCameras, state_dir)) { std::cerr << "error loading cameras\n"; return 1; }
   gxy::Datasets theDatasets;
   if (!theDatasets.LoadFromJSON(doc, state_dir)) { std::cerr << "error loading theDatasets\n"; return 1; }
   std::vector<gxy::Visualization> theVisualizations;
-  if (!gxy::Visualization::LoadVisualizationsFromJSON(doc, theVisualizations)) { std::cerr << "error loading visualizations\n"; return 1; }
+  if (!gxy::Visualization::LoadVisualizationsFromJSON(doc, theVisualizations, state_dir)) { std::cerr << "error loading visualizations\n"; return 1; }
 
   if (describe) {
     std::cout << gxy::describe_state(theRenderer, theCameras, theVisualizations, theDatasets, nparts) << std::endl;

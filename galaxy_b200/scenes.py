@@ -145,8 +145,32 @@ def parse_lighting(v):
     return L
 
 
-def parse_camera(v):
-    """Camera::LoadFromJSON (src/renderer/Camera.cpp:238-281)."""
+def _resolve(name, base_dir):
+    if name.startswith("/") or not base_dir:
+        return name
+    p = os.path.join(base_dir, name)
+    return p if os.path.exists(p) else name
+
+
+def parse_camera(v, base_dir=""):
+    """Camera::LoadFromJSON (src/renderer/Camera.cpp:165-281): an object, or the name of a ParaView camera file in JSON form."""
+    if isinstance(v, str):
+        doc = json.load(open(_resolve(v, base_dir)))
+        cam = dict(eye=[0.0] * 3, up=[0.0, 1.0, 0.0], aov=30.0, annotation="")
+        center = [f32(0)] * 3
+        for p in doc["PVCameraConfiguration"]["Proxy"]["Property"]:
+            name = p.get("@name")
+            el = p.get("Element")
+            if name == "CameraPosition":
+                cam["eye"] = [float(f32(float(el[k]["@value"]))) for k in range(3)]
+            elif name == "CameraFocalPoint":
+                center = [f32(float(el[k]["@value"])) for k in range(3)]
+            elif name == "CameraViewUp":
+                cam["up"] = [float(f32(float(el[k]["@value"]))) for k in range(3)]
+            elif name == "CameraViewAngle":
+                cam["aov"] = float(f32(float(el["@value"])))
+        cam["dir"] = [float(f32(center[k] - f32(cam["eye"][k]))) for k in range(3)]
+        return cam
     eye = np.asarray(v["viewpoint"], f32)
     if "viewdirection" in v:
         d = np.asarray(v["viewdirection"], f32)
@@ -179,7 +203,7 @@ def resample_tf(cmap, omap):
     return table(cmap[:, 0], cmap[:, 1:4]), table(omap[:, 0], omap[:, 1])
 
 
-def parse_operator(v):
+def parse_operator(v, base_dir=""):
     """Vis/MappedVis/VolumeVis/ParticlesVis::LoadFromJSON (Vis.cpp:126-146, MappedVis.cpp:86-203,
     VolumeVis.cpp:119-163, ParticlesVis.cpp:104-118)."""
     t = v["type"]
@@ -189,7 +213,14 @@ def parse_operator(v):
     cmap = [[0.0, 0.4, 0.4, 0.4], [1.0, 1.0, 1.0, 1.0]]  # MappedVis.cpp:58-62
     omap = [[0.0, 1.0], [1.0, 1.0]]
     m = v.get("transfer function", v.get("colormap"))
-    if m is not None and not isinstance(m, str):
+    if isinstance(m, str) and m not in ("", "default"):  # MappedVis.cpp:104-166: ParaView colormap export
+        doc = json.load(open(_resolve(m, base_dir)))
+        cm = doc[0] if isinstance(doc, list) else doc
+        pts = cm.get("Points")
+        omap = [[float(pts[i]), float(pts[i + 1])] for i in range(0, len(pts) - 1, 4)] if pts is not None else [[0.0, 1.0], [1.0, 1.0]]
+        rgb = cm["RGBPoints"]
+        cmap = [[float(x) for x in rgb[i:i + 4]] for i in range(0, len(rgb) - 3, 4)]
+    elif m is not None and not isinstance(m, str):
         cmap = [[float(x) for x in row[:4]] for row in m]
         if "opacitymap" in v:
             omap = [[float(x) for x in row[:2]] for row in v["opacitymap"]]
@@ -215,7 +246,7 @@ def parse_operator(v):
     return op
 
 
-def parse_state(doc):
+def parse_state(doc, base_dir=""):
     if isinstance(doc, str):
         doc = json.loads(doc)
     st = dict(datasets=doc.get("Datasets", []), epsilon=float(doc.get("Renderer", {}).get("epsilon", 0.001)))
@@ -223,11 +254,11 @@ def parse_state(doc):
     if not isinstance(vs, list):
         vs = [vs]
     st["visualizations"] = [dict(annotation=v.get("annotation", ""), lighting=parse_lighting(v.get("Lighting", v.get("lighting"))),
-                                 operators=[parse_operator(o) for o in v["operators"]]) for v in vs]
+                                 operators=[parse_operator(o, base_dir) for o in v["operators"]]) for v in vs]
     cs = doc.get("Cameras", doc.get("Camera"))
     if not isinstance(cs, list):
         cs = [cs]
-    st["cameras"] = [parse_camera(c) for c in cs]
+    st["cameras"] = [parse_camera(c, base_dir) for c in cs]
     return st
 
 

@@ -103,7 +103,7 @@ def test_errors_are_reported_not_fatal(tmp_path):
     geo = tmp_path / "geo.state"
     geo.write_text('{"Datasets": [{"name": "m", "type": "Triangles", "filename": "m.part"}], "Cameras": [], "Visualizations": []}')
     r = subprocess.run([EXE, "--describe", str(geo)], capture_output=True, text=True, timeout=60)
-    assert r.returncode == 1 and "VTK" in r.stderr
+    assert r.returncode == 1 and "partition document" in r.stderr  # the .part file does not exist
 
 
 @pytest.mark.gpu
@@ -132,3 +132,48 @@ def test_gxywriter_partitions_match_single(tmp_path):
     a = np.asarray(Image.open(os.path.join(str(tmp_path), "p1_00001.png")).convert("RGBA"))
     b = np.asarray(Image.open(os.path.join(str(tmp_path), "p8_00001.png")).convert("RGBA"))
     assert util.image_fraction(a, b) >= 0.995
+
+
+def test_camera_and_colormap_files(tmp_path):
+    """"Cameras": ["cam.json"] (a ParaView camera configuration in JSON form, Camera.cpp:168-232) and "colormap": "cmap.json"
+    (a ParaView colormap export, MappedVis.cpp:104-166): same values from the C++ host and the Python front end."""
+    tmp = str(tmp_path)
+    write_vol(os.path.join(tmp, "radial-oneBall.vol"), scenes.radial_volume("oneBall", 12))
+    cam = {"PVCameraConfiguration": {"Proxy": {"Property": [
+        {"@name": "CameraPosition", "Element": [{"@value": "1.25"}, {"@value": "-2.5"}, {"@value": "3.1"}]},
+        {"@name": "CameraFocalPoint", "Element": [{"@value": "0.1"}, {"@value": "0.2"}, {"@value": "0.3"}]},
+        {"@name": "CameraViewUp", "Element": [{"@value": "0"}, {"@value": "0"}, {"@value": "1"}]},
+        {"@name": "CameraViewAngle", "Element": {"@value": "27.5"}},
+        {"@name": "Ignored", "Element": {"@value": "1"}}]}}}
+    json.dump(cam, open(os.path.join(tmp, "cam.json"), "w"))
+    cmap = [{"Name": "test", "RGBPoints": [0.0, 0.1, 0.2, 0.3, 0.5, 0.9, 0.8, 0.7, 1.5, 1.0, 1.0, 0.0],
+             "Points": [0.0, 0.0, 0.5, 0.0, 0.7, 0.25, 0.5, 0.0, 1.5, 1.0, 0.5, 0.0]}]
+    json.dump(cmap, open(os.path.join(tmp, "cmap.json"), "w"))
+    json.dump({"RGBPoints": [0.0, 1.0, 0.0, 0.0, 2.0, 0.0, 0.0, 1.0]}, open(os.path.join(tmp, "cmap2.json"), "w"))
+    doc = {"Datasets": [{"name": "oneBall", "type": "Volume", "filename": "radial-oneBall.vol"}],
+           "Visualizations": [{"operators": [{"type": "Volume", "dataset": "oneBall", "volume rendering": True, "colormap": "cmap.json",
+                                              "opacitymap": [[0, 0.5], [1, 0.5]]},
+                                             {"type": "Volume", "dataset": "oneBall", "isovalues": [0.4], "transfer function": "cmap2.json"}]}],
+           "Cameras": ["cam.json"]}
+    state = os.path.join(tmp, "files.state")
+    json.dump(doc, open(state, "w"))
+    out = subprocess.run([EXE, "--describe", state], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    got = json.loads(out.stdout, parse_float=lambda t: float(np.float32(t)))
+    st = scenes.parse_state(doc, base_dir=tmp)
+    c, g = st["cameras"][0], got["cameras"][0]
+    assert g["eye"] == f32list(c["eye"]) and g["dir"] == f32list(c["dir"]) and g["up"] == f32list(c["up"]) and g["aov"] == float(np.float32(c["aov"]))
+    assert g["eye"] == f32list([1.25, -2.5, 3.1]) and g["aov"] == 27.5
+    for go, op in zip(got["visualizations"][0]["operators"], st["visualizations"][0]["operators"]):
+        col, opac = scenes.resample_tf(op["colormap"], op["opacitymap"])
+        assert np.array_equal(np.asarray(go["tf_colors"], np.float32), col.ravel())
+        assert np.array_equal(np.asarray(go["tf_opacities"], np.float32), opac.ravel())
+        assert go["range"] == f32list([op["colormap"][0][0], op["colormap"][-1][0]])
+    # the file's own opacity points win over an "opacitymap" next to a colormap file; no "Points" -> opacity 1
+    assert st["visualizations"][0]["operators"][0]["opacitymap"] == [[0.0, 0.0], [0.7, 0.25], [1.5, 1.0]]
+    assert st["visualizations"][0]["operators"][1]["opacitymap"] == [[0.0, 1.0], [1.0, 1.0]]
+    # a missing file is reported
+    doc["Cameras"] = ["nope.json"]
+    json.dump(doc, open(state, "w"))
+    r = subprocess.run([EXE, "--describe", state], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "error loading camera" in r.stderr
