@@ -51,6 +51,8 @@ static void timeline_print(int rank) {
 // GXY_TILED=0 restores the reference's row-major primary-ray order on the frame path (tuning / A-B runs)
 static bool tiled_order() { const char *e = getenv("GXY_TILED"); return !(e && atoi(e) == 0); }
 
+static bool march_tma_on() { const char *e = getenv("GXY_MARCH_TMA"); return e && atoi(e) != 0; }
+
 struct PhaseTimer {  // GXY_PROFILE=1: host wall-clock per phase of gxy_render (each mark synchronises nothing)
   bool on;
   std::chrono::steady_clock::time_point t0;
@@ -741,7 +743,7 @@ static int check_error_flag(gxy_vis *v) {
   int e = 0;
   GXY_CUDA(cudaMemcpyAsync(&e, v->d_error, sizeof(int), cudaMemcpyDeviceToHost, v->ctx->stream));
   GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
-  GXY_CHECK(e == 0, "BVH traversal stack overflow (tree too deep)");
+  GXY_CHECK(e == 0, "device error flag %d (1: BVH traversal stack overflow, 3: ray list / inbox capacity, 4: peer barrier timeout, 6: TMA copy did not complete)", e);
   return 0;
 }
 
@@ -1349,7 +1351,13 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       GXY_CUDA(cudaEventCreate(&ta));
       GXY_CUDA(cudaEventCreate(&tb));
       GXY_CUDA(cudaEventRecord(ta, st));
-      if (launch_trace(v->P, v->cur.v, n, epsilon, nullptr, !v->has_dvr, v->counters.p + 1, st)) return 1;
+      // GXY_MARCH_TMA=1: the primaries (compact 16x8-pixel beams) of a one-volume scene go through the TMA-staged march
+      const bool tma = wave == 0 && march_tma_on() && march_tma_eligible(v->P);
+      if (tma) {
+        const float ax = fabsf(C.vdir.x), ay = fabsf(C.vdir.y), az = fabsf(C.vdir.z);
+        const int axis = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+        if (launch_march_tma(v->P, v->cur.v, n, epsilon, axis, v->counters.p + 1, v->counters.p + 2, st)) return 1;
+      } else if (launch_trace(v->P, v->cur.v, n, epsilon, nullptr, !v->has_dvr, v->counters.p + 1, st)) return 1;
       GXY_CUDA(cudaEventRecord(tb, st));
       trace_events.push_back(std::make_pair(ta, tb));
       if (v->hit_index.reserve((size_t)2 * n) || v->block_sums.reserve((size_t)n / 1024 + 2)) return 1;
@@ -1546,6 +1554,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
     GXY_CUDA(cudaMemcpy(c, v->counters.p, sizeof c, cudaMemcpyDeviceToHost));
     S.terminated_rays += (long long)c[0];
     S.volume_samples += (long long)c[1];
+    S.staged_samples += (long long)c[2];
     unsigned long long tc[2];
     GXY_CUDA(cudaMemcpy(tc, v->P.trav_counters, sizeof tc, cudaMemcpyDeviceToHost));
     GXY_CUDA(cudaMemset(v->P.trav_counters, 0, sizeof tc));

@@ -35,6 +35,14 @@ int launch_copy_rays(Rays dst, size_t dst_off, Rays src, size_t src_off, int n, 
 int launch_intersect(const SceneParams &P, int n, const float *org3, const float *dir3, const float *tnear, const float *tfar,
                      int *geom_prim2, float *tuv3, cudaStream_t st);
 
+// ---- TMA-staged volume march (gxy_march_tma.cu) ---------------------------------------------------------
+// one float volume operator, no geometry, < 2^31 voxels, x dimension a multiple of 4 (TMA strides are multiples of 16 bytes)
+bool march_tma_eligible(const SceneParams &P);
+// same contract as launch_trace for such a Visualization; axis = volume axis the beams mostly run along (0 x, 1 y, 2 z);
+// staged_counter (may be NULL) receives the number of samples served from the staged boxes
+int launch_march_tma(const SceneParams &P, Rays R, int n, float global_epsilon, int axis, unsigned long long *sample_counter,
+                     unsigned long long *staged_counter, cudaStream_t st);
+
 // ---- fused frame kernels for geometry-only Visualizations (gxy_fused.cu) ---------------------------
 struct FusedQueues {  // device memory, zeroed at the start of a frame
   unsigned pixel_head, n_hits, n_spill, sec_head;

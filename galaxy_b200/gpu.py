@@ -39,7 +39,7 @@ class RayListView(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in ("primary_rays", "shadow_rays", "ao_rays", "forwarded_rays", "terminated_rays", "traced_rays",
                                             "waves", "kernel_launches")] + [("device_ms", C.c_float), ("trace_ms", C.c_float),
-                                                                                ("nodes_visited", C.c_longlong), ("prims_tested", C.c_longlong), ("volume_samples", C.c_longlong)]
+                                                                                ("nodes_visited", C.c_longlong), ("prims_tested", C.c_longlong), ("volume_samples", C.c_longlong), ("staged_samples", C.c_longlong)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

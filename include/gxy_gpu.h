@@ -90,6 +90,7 @@ typedef struct {
   long long nodes_visited;    /* BVH nodes / primitives tested by the trace kernel; 0 unless  */
   long long prims_tested;     /* the library was compiled with -DGXY_TRAV_COUNTERS            */
   long long volume_samples;   /* trilinear volume samples taken by the march (SampleVolumes x volumes) */
+  long long staged_samples;   /* ... of which served from TMA-staged shared-memory boxes (GXY_MARCH_TMA=1)      */
 } gxy_stats;
 
 /* ---- library ---------------------------------------------------------------------------- */

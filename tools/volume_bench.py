@@ -54,6 +54,6 @@ for name, (op, lighting, cam) in cases.items():
     rays = st["primary_rays"] + st["shadow_rays"] + st["ao_rays"]
     m = float(np.median(ms))
     print(json.dumps({"case": name, "N": N, "ms": round(m, 3), "trace_ms": round(st["trace_ms"], 3), "rays": rays, "Mrays/s": round(rays / m / 1e3, 1),
-                      "samples": st["volume_samples"], "Gsamples/s": round(st["volume_samples"] / m / 1e6, 2),
+                      "samples": st["volume_samples"], "staged": round(st["staged_samples"] / max(1, st["volume_samples"]), 3), "Gsamples/s": round(st["volume_samples"] / m / 1e6, 2),
                       "alg_GB/s_16B_per_sample": round(st["volume_samples"] * 16 / m / 1e6, 1), "waves": st["waves"]}), flush=True)
     del part
