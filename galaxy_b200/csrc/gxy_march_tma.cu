@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(128)
     lo[1] = (int)fminf(ay, by); hi[1] = (int)fmaxf(ay, by) + 1;
     lo[2] = (int)fminf(az, bz); hi[2] = (int)fmaxf(az, bz) + 1;
   };
-  // CTA-wide union; every thread returns the same result.  Two barriers inside.
+  // CTA-wide union; every thread returns the same result.  One barrier inside; the caller's next barrier frees red_* again.
   auto cta_box = [&](bool mine, const int lo[3], const int hi[3]) {
     BoxRed r;
 #pragma unroll
@@ -186,8 +186,7 @@ __global__ void __launch_bounds__(128)
       r.lo[a] = min(min(red_lo[0][a], red_lo[1][a]), min(red_lo[2][a], red_lo[3][a]));
       r.hi[a] = max(max(red_hi[0][a], red_hi[1][a]), max(red_hi[2][a], red_hi[3][a]));
     }
-    __syncthreads();
-    return r;
+    return r;  // red_* are written again only after the caller's next CTA barrier (end of the stage / after the first issue)
   };
   constexpr unsigned STAGE_BYTES = (unsigned)(BX * BY * BZ * sizeof(float));
   // thread 0: box origin = low corner of the union (a beam larger than the box is cut off).  The innermost coordinate of a
