@@ -1252,4 +1252,21 @@ int gxo_intersect(gxo_scene *s, int n, const float *org3, const float *dir3, con
   return 0;
 }
 
+/* the box helpers on their own, so that they can be pinned against the reference's compiled Box.cpp (oracle/box_ref.cpp,
+ * tests/test_oracle_box.py): boxes6 = n x (minx miny minz maxx maxy maxz), rays6 = n x (x y z dx dy dz) */
+void gxo_exit_face(int n, const float *boxes6, const float *rays6, int *faces) {
+  for (int i = 0; i < n; i++) {
+    const float *b = boxes6 + 6 * i, *r = rays6 + 6 * i;
+    faces[i] = exit_face(mk(b[0], b[1], b[2]), mk(b[3], b[4], b[5]), r[0], r[1], r[2], r[3], r[4], r[5]);
+  }
+}
+void gxo_box_intersect(int n, const float *boxes6, const float *rays6, int *hit, float *t2) {
+  for (int i = 0; i < n; i++) {
+    const float *b = boxes6 + 6 * i, *r = rays6 + 6 * i;
+    float tmin = 0.f, tmax = 0.f;
+    hit[i] = box_intersect(mk(b[0], b[1], b[2]), mk(b[3], b[4], b[5]), mk(r[0], r[1], r[2]), mk(r[3], r[4], r[5]), tmin, tmax) ? 1 : 0;
+    t2[2 * i] = tmin; t2[2 * i + 1] = tmax;
+  }
+}
+
 }  // extern "C"

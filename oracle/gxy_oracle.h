@@ -139,6 +139,9 @@ void gxo_partition(int n, const int factors[3], const int grid[3], int *out);
 
 /* Diagnostic switches for tests ("dvr_before_iso": see gxy_oracle.cpp). */
 void gxo_set_option(const char *name, int value);
+/* Box::exit_face / Box::intersect restatements on arrays (pinned against the reference's compiled Box.cpp) */
+void gxo_exit_face(int n, const float *boxes6, const float *rays6, int *faces);
+void gxo_box_intersect(int n, const float *boxes6, const float *rays6, int *hit, float *t2);
 
 /* Nearest-hit query only (K2/K4): for n rays (org,dir,tnear,tfar) report geomID, primID, t, u, v.
  * Used for primID parity tests. */
