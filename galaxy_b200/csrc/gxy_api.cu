@@ -268,6 +268,7 @@ struct gxy_vis {
   Scratch<float> fb, fb_tmp;
   float *fb_result = nullptr;  // where the last frame's image is (fb.p, or a buffer inside the peer arena)
   Scratch<unsigned char> rgba8;
+  struct FrameTailT { unsigned long long counters[4], trav[2]; int error, pad; } *h_tail = nullptr;  // page-locked: end-of-frame counters
   Scratch<unsigned char> rgba8_async[2];  // staging images of gxy_frame_download_rgba8_async
   cudaEvent_t async_ready[2] = {nullptr, nullptr}, async_done[2] = {nullptr, nullptr};
   int async_slot = 0;
@@ -443,6 +444,7 @@ void gxy_vis_destroy(gxy_vis *v) {
     if (v->async_done[s]) cudaEventDestroy(v->async_done[s]);
   }
   v->proxies.release();
+  if (v->h_tail) cudaFreeHost(v->h_tail);
   delete v;
 }
 
@@ -1532,6 +1534,19 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
   }
   if (use_device(ctx0)) return 1;
   GXY_CUDA(cudaEventRecord(ev1, ctx0->stream));
+  // the frame's counters and error flags travel to page-locked memory behind the end-of-frame event: one host wait per
+  // partition instead of four blocking copies
+  for (int p = 0; p < nparts; p++) {
+    gxy_vis *v = parts[p];
+    if (use_device(v->ctx)) return 1;
+    if (!v->h_tail) GXY_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&v->h_tail), sizeof(gxy_vis::FrameTailT), cudaHostAllocPortable));
+    cudaStream_t st = v->ctx->stream;
+    GXY_CUDA(cudaMemcpyAsync(v->h_tail->counters, v->counters.p, sizeof v->h_tail->counters, cudaMemcpyDeviceToHost, st));
+    GXY_CUDA(cudaMemcpyAsync(v->h_tail->trav, v->P.trav_counters, sizeof v->h_tail->trav, cudaMemcpyDeviceToHost, st));
+    GXY_CUDA(cudaMemsetAsync(v->P.trav_counters, 0, sizeof v->h_tail->trav, st));
+    GXY_CUDA(cudaMemcpyAsync(&v->h_tail->error, v->d_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
+  if (use_device(ctx0)) return 1;
   GXY_CUDA(cudaEventSynchronize(ev1));
   PT.mark("fb_reduce");
   PT.report(rank0);
@@ -1550,17 +1565,14 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
   for (int p = 0; p < nparts; p++) {
     gxy_vis *v = parts[p];
     if (use_device(v->ctx)) return 1;
-    unsigned long long c[4];
-    GXY_CUDA(cudaMemcpy(c, v->counters.p, sizeof c, cudaMemcpyDeviceToHost));
-    S.terminated_rays += (long long)c[0];
-    S.volume_samples += (long long)c[1];
-    S.staged_samples += (long long)c[2];
-    unsigned long long tc[2];
-    GXY_CUDA(cudaMemcpy(tc, v->P.trav_counters, sizeof tc, cudaMemcpyDeviceToHost));
-    GXY_CUDA(cudaMemset(v->P.trav_counters, 0, sizeof tc));
-    S.nodes_visited += (long long)tc[0];
-    S.prims_tested += (long long)tc[1];
-    if (check_error_flag(v)) return 1;
+    GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    const gxy_vis::FrameTailT &t = *v->h_tail;
+    S.terminated_rays += (long long)t.counters[0];
+    S.volume_samples += (long long)t.counters[1];
+    S.staged_samples += (long long)t.counters[2];
+    S.nodes_visited += (long long)t.trav[0];
+    S.prims_tested += (long long)t.trav[1];
+    GXY_CHECK(t.error == 0, "device error flag %d (1: BVH traversal stack overflow, 3: ray list / inbox capacity, 4: peer barrier timeout, 6: TMA copy did not complete)", t.error);
   }
   if (stats) *stats = S;
   return 0;
