@@ -151,7 +151,7 @@ struct VolumeVisOp {          // src/renderer/VolumeVis.ih:25-37
 // ---------------------------------------------------------------------------------------------
 // Geometry
 struct GeomOp {
-  int kind;                   // 0 triangles, 1 spheres
+  int kind;                   // 0 triangles, 1 spheres, 2 round Bezier curves (PathLines)
   TF tf;
   // triangles (src/ospray/OsprayTriangles.cpp:25-57)
   int nv, nt;
@@ -161,6 +161,9 @@ struct GeomOp {
   int n;
   const float *centers;
   float radius0, radius1, value0, value1, epsilon;
+  // curves: 4 control points (x,y,z,r) per segment, built by build_curves (owned by the scene)
+  int ncurves;
+  const float *cp;
 };
 
 struct Prim { int geom, prim; };
@@ -235,11 +238,303 @@ static inline bool sphere_test(const GeomOp &g, int prim, V3 org, V3 dir, float 
   return hit;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// PathLines: round cubic Bezier segments.  Galaxy turns every poly-line segment into 4 control points (x,y,z,r)
+// (src/ospray/DataDrivenPathLines.cpp:103-156) and hands them to Embree as RTC_GEOMETRY_TYPE_ROUND_BEZIER_CURVE
+// (DataDrivenPathLines.ispc:319-324), which intersects them with SweepCurve1Intersector{1,K}<BezierCurve3fa>
+// (embree/kernels/geometry/curve_intersector_virtual.cpp:256-266; curve_intersector_sweep.h:55-241).  The restatement
+// below follows that file for the AVX/AVX2 build (VSIZEX = 8 lanes = 7 sub-segments per level, numBezierSubdivisions = 2)
+// lane by lane; madd/msub are fmaf as in the AVX2 build, rcp/rsqrt (rcpss/rsqrtss + Newton in Embree) are IEEE.
+struct V4 { float x, y, z, w; };
+static inline V4 mk4(float x, float y, float z, float w) { V4 v = {x, y, z, w}; return v; }
+static inline V3 xyz(V4 a) { return mk(a.x, a.y, a.z); }
+static inline V4 operator+(V4 a, V4 b) { return mk4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+static inline V4 operator-(V4 a, V4 b) { return mk4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+static inline V4 operator*(float s, V4 a) { return mk4(s * a.x, s * a.y, s * a.z, s * a.w); }
+static inline float e_rcp(float x) { return 1.0f / x; }
+static inline float e_rsqrt(float x) { return 1.0f / sqrtf(x); }
+static inline float dot_fa(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }   // Vec3fa dot = _mm_dp_ps(a,b,0x7F), vec3fa.h:289
+static inline V4 lerp4(V4 a, V4 b, float t) {   // vec4.h:191 / vec3fa.h:341: madd(1-t, v0, t*v1)
+  const float s = 1.0f - t;
+  return mk4(fmaf(s, a.x, t * b.x), fmaf(s, a.y, t * b.y), fmaf(s, a.z, t * b.z), fmaf(s, a.w, t * b.w));
+}
+// CubicBezierCurve::eval(t,p,dp) / veval(t,p,dp) (bezier_curve.h:322-339, 476-492): de Casteljau
+static inline void bezier_eval(const V4 cp[4], float t, V4 &p, V4 &dp) {
+  const V4 p10 = lerp4(cp[0], cp[1], t), p11 = lerp4(cp[1], cp[2], t), p12 = lerp4(cp[2], cp[3], t);
+  const V4 p20 = lerp4(p10, p11, t), p21 = lerp4(p11, p12, t);
+  p = lerp4(p20, p21, t);
+  dp = 3.0f * (p21 - p20);
+}
+// eval_dudu (bezier_curve.h:382-386) with BezierBasis::derivative2 (:52-61)
+static inline V4 bezier_dudu(const V4 cp[4], float t1) {
+  const float t0 = 1.0f - t1;
+  const float b0 = 6.0f * t0, b1 = 6.0f * fmaf(-2.0f, t0, t1), b2 = 6.0f * fmaf(-2.0f, t1, t0), b3 = 6.0f * t1;
+  V4 r;
+  r.x = fmaf(b0, cp[0].x, fmaf(b1, cp[1].x, fmaf(b2, cp[2].x, b3 * cp[3].x)));
+  r.y = fmaf(b0, cp[0].y, fmaf(b1, cp[1].y, fmaf(b2, cp[2].y, b3 * cp[3].y)));
+  r.z = fmaf(b0, cp[0].z, fmaf(b1, cp[1].z, fmaf(b2, cp[2].z, b3 * cp[3].z)));
+  r.w = fmaf(b0, cp[0].w, fmaf(b1, cp[1].w, fmaf(b2, cp[2].w, b3 * cp[3].w)));
+  return r;
+}
+
+struct CurveRay { V3 dir; float tnear, tfar; float u; V3 Ng; };   // org is 0 after the shift by dt (:236-238)
+static const float E_ULP = 1.1920929e-07f;   // embree ulp = numeric_limits<float>::epsilon()
+
+// intersect_bezier_iterative_jacobian (curve_intersector_sweep.h:69-120); the epilog (Intersect1Epilog1 without filter,
+// intersector_epilog.h:72-80) shortens the ray
+static bool curve_jacobian(CurveRay &ray, float dt, const V4 cp[4], float u, float t) {
+  const V3 dir = ray.dir;
+  const float length_ray_dir = sqrtf(dot_fa(dir, dir));
+  for (int i = 0; i < 5; i++) {
+    const V3 Q = mk(fmaf(t, dir.x, 0.0f), fmaf(t, dir.y, 0.0f), fmaf(t, dir.z, 0.0f));
+    V4 P4, dP4; bezier_eval(cp, u, P4, dP4);
+    const V4 ddP4 = bezier_dudu(cp, u);
+    const V3 P = xyz(P4), dPdu = xyz(dP4), ddPdu = xyz(ddP4);
+    const V3 R = Q - P;
+    const V3 dRdu = neg(dPdu);
+    const V3 dRdt = dir;
+    const V3 T = dPdu * e_rsqrt(dot_fa(dPdu, dPdu));
+    const float pp = dot_fa(dPdu, dPdu), pdp = dot_fa(dPdu, ddPdu);   // dnormalize, vec3fa.h:321-326
+    const V3 dTdu = ((pp * ddPdu - pdp * dPdu) * e_rcp(pp)) * e_rsqrt(pp);
+    const float f = dot_fa(R, T);
+    const float dfdu = dot_fa(dRdu, T) + dot_fa(R, dTdu);
+    const float dfdt = dot_fa(dRdt, T);
+    const float K = dot_fa(R, R) - f * f;
+    const float dKdu = dot_fa(R, dRdu) - f * dfdu;
+    const float dKdt = dot_fa(R, dRdt) - f * dfdt;
+    const float rsqrt_K = e_rsqrt(K);
+    const float g = sqrtf(K) - P4.w;
+    const float dgdu = dKdu * rsqrt_K - dP4.w;
+    const float dgdt = dKdt * rsqrt_K;
+    // rcp(J)*Vec2f(f,g), J = LinearSpace2f(dfdu,dfdt,dgdu,dgdt): adjoint()/det() (linearspace2.h:49-55), then b.x*vx + b.y*vy
+    const float det = dfdu * dgdt - dgdu * dfdt;
+    const float ixx = dgdt / det, ixy = -dgdu / det, iyx = -dfdt / det, iyy = dfdu / det;   // vx = (ixx,ixy), vy = (iyx,iyy)
+    const float du = f * ixx + g * iyx, dtt = f * ixy + g * iyy;
+    u = u - du; t = t - dtt;
+    const bool converged_u = fabsf(f) < 16.0f * E_ULP * std::max(std::max(fabsf(dPdu.x), fabsf(dPdu.y)), fabsf(dPdu.z));
+    const bool converged_t = fabsf(g) < 16.0f * E_ULP * length_ray_dir;
+    if (converged_u && converged_t) {
+      t += dt;
+      if (!(t > ray.tnear && t < ray.tfar)) return false;
+      if (!(u >= 0.0f && u <= 1.0f)) return false;
+      const V3 QP = Q - P;
+      const V3 Rn = QP * e_rsqrt(dot_fa(QP, QP));
+      const V3 U = mk(fmaf(dP4.w, Rn.x, dPdu.x), fmaf(dP4.w, Rn.y, dPdu.y), fmaf(dP4.w, Rn.z, dPdu.z));
+      const V3 V = ecross(dPdu, Rn);
+      ray.tfar = t; ray.u = u; ray.Ng = ecross(V, U);
+      return true;
+    }
+  }
+  return false;
+}
+
+static inline float vdot(V3 a, V3 b) { return edot(a, b); }   // Vec3<vfloat> dot, vec3.h:216
+
+// CylinderN<8>::intersect, one lane (cylinder.h:162-225).  Returns the lane's valid bit; t0/t1 = +inf/-inf when invalid.
+static inline bool cylinder_lane(V3 p0, V3 p1, float r, V3 dir, float &t_lo, float &t_up, float &u0, V3 &Ng0, float &u1, V3 &Ng1) {
+  const float rr = r * r;
+  const V3 d01 = p1 - p0;
+  const float rl = e_rsqrt(vdot(d01, d01));
+  const V3 dP = d01 * rl;
+  const V3 O = mk(0.f, 0.f, 0.f) - p0, dO = dir;
+  const float dOdO = vdot(dO, dO), OdO = vdot(dO, O), OO = vdot(O, O), dOz = vdot(dP, dO), Oz = vdot(dP, O);
+  const float A = dOdO - dOz * dOz;
+  const float B = 2.0f * (OdO - dOz * Oz);
+  const float C = OO - Oz * Oz - rr;
+  const float D = B * B - 4.0f * A * C;
+  bool valid = D >= 0.0f;
+  const float Q = sqrtf(D);
+  const float rcp_2A = e_rcp(2.0f * A);
+  const float t0 = (-B - Q) * rcp_2A, t1 = (-B + Q) * rcp_2A;
+  u0 = fmaf(t0, dOz, Oz) * rl;
+  { const V3 Pr = t0 * dir; const V3 Pl = mk(fmaf(u0, d01.x, p0.x), fmaf(u0, d01.y, p0.y), fmaf(u0, d01.z, p0.z)); Ng0 = Pr - Pl; }
+  u1 = fmaf(t1, dOz, Oz) * rl;
+  { const V3 Pr = t1 * dir; const V3 Pl = mk(fmaf(u1, d01.x, p0.x), fmaf(u1, d01.y, p0.y), fmaf(u1, d01.z, p0.z)); Ng1 = Pr - Pl; }
+  t_lo = valid ? t0 : INFINITY;
+  t_up = valid ? t1 : -INFINITY;
+  const float eps = 16.0f * E_ULP * std::max(fabsf(dOdO), fabsf(dOz * dOz));
+  if (valid && fabsf(A) < eps) {   // ray parallel to the cylinder
+    const bool inside = C <= 0.0f;
+    t_lo = inside ? -INFINITY : INFINITY;
+    t_up = inside ? INFINITY : -INFINITY;
+    valid = inside;
+  }
+  return valid;
+}
+// HalfPlaneN::intersect, one lane, ray origin 0 (plane.h:60-72)
+static inline void halfplane_lane(V3 P, V3 N, V3 dir, float &lower, float &upper) {
+  const V3 O = mk(0.f, 0.f, 0.f) - P;
+  const float ON = vdot(O, N), DN = vdot(dir, N);
+  const bool eps = fabsf(DN) < 1E-18f;
+  const float t = -ON * e_rcp(DN);
+  lower = (eps || DN < 0.0f) ? -INFINITY : t;
+  upper = (eps || DN > 0.0f) ? INFINITY : t;
+}
+static inline float e_min(float a, float b) { return a < b ? a : b; }   // _mm_min_ps(a,b): a < b ? a : b (NaN -> b)
+static inline float e_max(float a, float b) { return a > b ? a : b; }
+// select_min (vfloat8_avx.h:669-674): lowest lane holding the minimum, else lowest valid lane
+static inline int select_min_lane(unsigned valid, const float *v) {
+  float m = INFINITY;
+  for (int i = 0; i < 8; i++) if (valid >> i & 1) m = e_min(v[i], m);
+  unsigned vm = 0;
+  for (int i = 0; i < 8; i++) if ((valid >> i & 1) && v[i] == m) vm |= 1u << i;
+  if (!vm) vm = valid;
+  return __builtin_ctz(vm);
+}
+
+// intersect_bezier_recursive_jacobian (curve_intersector_sweep.h:122-221)
+static bool curve_recursive(CurveRay &ray, float dt, const V4 cp[4], float u0, float u1, int depth) {
+  const int maxDepth = 2;   // numBezierSubdivisions with __AVX__
+  const V3 dir = ray.dir;
+  const float dscale = (u1 - u0) * (1.0f / (3.0f * 7));
+  float vu0[8]; V4 P0[8], dP0du[8];
+  for (int i = 0; i < 8; i++) {
+    vu0[i] = fmaf((float)i * (1.0f / 7), u1 - u0, u0);   // lerp(u0,u1,step*(1/7)) = madd(t,b-a,a), vfloat8_avx.h:477
+    bezier_eval(cp, vu0[i], P0[i], dP0du[i]);
+    dP0du[i] = mk4(dP0du[i].x * dscale, dP0du[i].y * dscale, dP0du[i].z * dscale, dP0du[i].w * dscale);
+  }
+  unsigned valid = 0, valid0 = 0, valid1 = 0, unstable0 = 0, unstable1 = 0;
+  float tp0_lo[8], tp1_lo[8], tp1_up[8], uo0[8], uo1[8];
+  for (int i = 0; i < 7; i++) {
+    const V4 P3 = P0[i + 1], dP3du = dP0du[i + 1];
+    const V4 P1 = P0[i] + dP0du[i], P2 = P3 - dP3du;
+    const V3 p0 = xyz(P0[i]), p3 = xyz(P3), d0 = xyz(dP0du[i]), d3 = xyz(dP3du), chord = p3 - p0;
+    // bounding cylinders (:147-157); sqr_point_to_line_distance(PmQ0,Q1mQ0), vec3.h:253-258
+    const V3 n1 = ecross(d0, chord), n2 = ecross(d3, chord);
+    const float rcd = e_rcp(vdot(chord, chord));
+    const float rr1 = vdot(n1, n1) * rcd, rr2 = vdot(n2, n2) * rcd;
+    const float maxr12 = sqrtf(e_max(rr1, rr2));
+    const float one_plus_ulp = 1.0f + 2.0f * E_ULP, one_minus_ulp = 1.0f - 2.0f * E_ULP;
+    float r_outer = e_max(e_max(P0[i].w, P1.w), e_max(P2.w, P3.w)) + maxr12;
+    float r_inner = e_min(e_min(P0[i].w, P1.w), e_min(P2.w, P3.w)) - maxr12;
+    r_outer = one_plus_ulp * r_outer;
+    r_inner = e_max(0.0f, one_minus_ulp * r_inner);
+    float to_lo, to_up, u_outer0, u_outer1; V3 Ngo0, Ngo1;
+    bool v = cylinder_lane(p0, p3, r_outer, dir, to_lo, to_up, u_outer0, Ngo0, u_outer1, Ngo1);
+    // cap planes (:165-172); intersect(BBox,BBox) = (max(lower), min(upper))
+    float tp_lo = e_max(ray.tnear - dt, to_lo), tp_up = e_min(ray.tfar - dt, to_up);
+    float hl, hu;
+    halfplane_lane(p0, d0, dir, hl, hu);       tp_lo = e_max(tp_lo, hl); tp_up = e_min(tp_up, hu);
+    halfplane_lane(p3, neg(d3), dir, hl, hu);  tp_lo = e_max(tp_lo, hl); tp_up = e_min(tp_up, hu);
+    v = v && (tp_lo <= tp_up);
+    // u of the outer hits (:176-179)
+    u_outer0 = e_min(e_max(u_outer0, 0.0f), 1.0f);   // clamp(x,lo,hi) = min(max(x,lo),hi)
+    u_outer1 = e_min(e_max(u_outer1, 0.0f), 1.0f);
+    uo0[i] = fmaf(((float)i + u_outer0) * (1.0f / 8.0f), u1 - u0, u0);   // (step+u)*(1/float(VSIZEX)): Embree's own 1/8
+    uo1[i] = fmaf(((float)i + u_outer1) * (1.0f / 8.0f), u1 - u0, u0);
+    // inner cylinder (:181-188)
+    float ti_lo, ti_up, ui0, ui1; V3 Ngi0, Ngi1;
+    const bool valid_inner = cylinder_lane(p0, p3, r_inner, dir, ti_lo, ti_up, ui0, Ngi0, ui1, Ngi1);
+    const V3 nd = dir * e_rsqrt(dot_fa(dir, dir));   // normalize(ray.dir) on Vec3fa, then broadcast
+    const V3 nn0 = Ngi0 * e_rsqrt(vdot(Ngi0, Ngi0)), nn1 = Ngi1 * e_rsqrt(vdot(Ngi1, Ngi1));
+    const bool un0 = !valid_inner || (fabsf(vdot(nd, nn0)) < 0.3f);
+    const bool un1 = !valid_inner || (fabsf(vdot(nd, nn1)) < 0.3f);
+    // subtract the inner interval (:190-195; bbox.h:166-172)
+    tp0_lo[i] = tp_lo; const float tp0_up = e_min(tp_up, ti_lo);
+    tp1_lo[i] = e_max(tp_lo, ti_up); tp1_up[i] = tp_up;
+    if (v) valid |= 1u << i;
+    if (v && tp0_lo[i] <= tp0_up) valid0 |= 1u << i;
+    if (v && tp1_lo[i] <= tp1_up[i]) valid1 |= 1u << i;
+    if (un0) unstable0 |= 1u << i;
+    if (un1) unstable1 |= 1u << i;
+  }
+  if (!valid) return false;
+  if (!(valid0 | valid1)) return false;
+  bool found = false;
+  while (valid0) {   // first hits front to back (:198-208)
+    const int i = select_min_lane(valid0, tp0_lo); valid0 &= ~(1u << i);
+    const int termDepth = (unstable0 >> i & 1) ? maxDepth + 1 : maxDepth;
+    if (depth >= termDepth) found = curve_jacobian(ray, dt, cp, uo0[i], tp0_lo[i]) | found;
+    else                    found = curve_recursive(ray, dt, cp, vu0[i], vu0[i + 1], depth + 1) | found;
+    for (int k = 0; k < 7; k++) if (!(tp0_lo[k] + dt <= ray.tfar)) valid0 &= ~(1u << k);
+  }
+  for (int k = 0; k < 7; k++) if (!(tp1_lo[k] + dt <= ray.tfar)) valid1 &= ~(1u << k);
+  while (valid1) {   // second hits front to back (:211-219)
+    const int i = select_min_lane(valid1, tp1_lo); valid1 &= ~(1u << i);
+    const int termDepth = (unstable1 >> i & 1) ? maxDepth + 1 : maxDepth;
+    if (depth >= termDepth) found = curve_jacobian(ray, dt, cp, uo1[i], tp1_up[i]) | found;
+    else                    found = curve_recursive(ray, dt, cp, vu0[i], vu0[i + 1], depth + 1) | found;
+    for (int k = 0; k < 7; k++) if (!(tp1_lo[k] + dt <= ray.tfar)) valid1 &= ~(1u << k);
+  }
+  return found;
+}
+
+// SweepCurve1Intersector1::intersect (curve_intersector_sweep.h:224-241).  Nearest hit of ONE segment in (tnear, tfar).
+static bool curve_test(const float *cp16, V3 org, V3 dir, float tnear, float tfar, float &t, float &u, V3 &Ng) {
+  V4 cp[4];
+  for (int k = 0; k < 4; k++) cp[k] = mk4(cp16[4 * k], cp16[4 * k + 1], cp16[4 * k + 2], cp16[4 * k + 3]);
+  const V4 c4 = 0.25f * (((cp[0] + cp[1]) + cp[2]) + cp[3]);   // center()
+  const float dt = dot_fa(xyz(c4) - org, dir) * e_rcp(dot_fa(dir, dir));
+  const V3 ref = mk(fmaf(dt, dir.x, org.x), fmaf(dt, dir.y, org.y), fmaf(dt, dir.z, org.z));
+  for (int k = 0; k < 4; k++) { cp[k].x -= ref.x; cp[k].y -= ref.y; cp[k].z -= ref.z; }   // curve0 - ref, ref.w = 0
+  CurveRay ray; ray.dir = dir; ray.tnear = tnear; ray.tfar = tfar; ray.u = 0.f; ray.Ng = mk(0.f, 0.f, 0.f);
+  if (!curve_recursive(ray, dt, cp, 0.0f, 1.0f, 1)) return false;
+  t = ray.tfar; u = ray.u; Ng = ray.Ng;
+  return true;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
+namespace {
+// DataDrivenPathLines::finalize (src/ospray/DataDrivenPathLines.cpp:28-37 MAP_RADIUS, :103-156): one cubic Bezier
+// segment per poly-line segment; `connectivity[i]` is the index of the segment's first vertex (PathLines.cpp:110-122),
+// consecutive segments of one line are joined with Catmull-Rom-like tangents, line ends repeat their end point.
+static inline float map_radius(float d, float radius0, float radius1, float value0, float value1) {
+  if (value0 == value1) return radius0;
+  const float R = (d - value0) / (value1 - value0);
+  // `R <= 0.0` / `R >= 1.0` compare in double, which is exact for a float
+  return (R <= 0.0f) ? radius0 : (R >= 1.0f) ? radius1 : radius0 + R * (radius1 - radius0);
+}
+static inline float lerp_os(float factor, float a, float b) { return (1.f - factor) * a + factor * b; }   // ospcommon lerp(factor,a,b), math.h
+static void build_curves(int nseg, const int *indices, const float *verts, const float *data, float radius0, float radius1,
+                         float value0, float value1, std::vector<float> &out) {
+  std::vector<float> vc;          // vertexCurve: a middle segment pushes 3 points, its 4th is the next segment's first
+  std::vector<size_t> ic(nseg);   // indexCurve
+  bool middleSegment = false;
+  V3 tangent = mk(0.f, 0.f, 0.f);
+  auto push = [&](V3 p, float r) { vc.push_back(p.x); vc.push_back(p.y); vc.push_back(p.z); vc.push_back(r); };
+  auto vert = [&](int i) { return mk(verts[3 * (size_t)i], verts[3 * (size_t)i + 1], verts[3 * (size_t)i + 2]); };
+  for (int i = 0; i < nseg; i++) {
+    const int idx = indices[i];
+    const V3 start = vert(idx), end = vert(idx + 1);
+    const V3 se = start - end;
+    const float lengthSegment = sqrtf(dot(se, se));
+    const float startRadius = map_radius(data ? data[idx] : 0.f, radius0, radius1, value0, value1);
+    const float endRadius = map_radius(data ? data[idx + 1] : 0.f, radius0, radius1, value0, value1);
+    ic[i] = vc.size() / 4;
+    if (middleSegment) {
+      push(start, startRadius);
+      push(start + tangent, lerp_os(1.f / 3, startRadius, endRadius));
+    } else {
+      push(start, startRadius);
+      push(start, startRadius);
+    }
+    middleSegment = i + 1 < nseg && indices[i + 1] == idx + 1;
+    if (middleSegment) {
+      const V3 next = vert(idx + 2);
+      const V3 delta = (1.f / 3) * (next - start);
+      const V3 ne = next - end;
+      const float b = sqrtf(dot(ne, ne));
+      const float r = lengthSegment / (lengthSegment + b);
+      push(end - r * delta, lerp_os(2.f / 3, startRadius, endRadius));
+      tangent = (1.f - r) * delta;
+    } else {
+      push(end, endRadius);
+      push(end, endRadius);
+    }
+  }
+  // what Embree gathers per primitive: the 4 consecutive vertices from indexCurve[i] (rtcSetSharedGeometryBuffer,
+  // DataDrivenPathLines.ispc:319-322), expanded here to 16 floats per segment
+  out.resize((size_t)16 * nseg);
+  for (int i = 0; i < nseg; i++) memcpy(&out[16 * (size_t)i], &vc[4 * ic[i]], 16 * sizeof(float));
+}
+}  // namespace
+
 struct gxo_scene {
   V3 gmin, gmax, lmin, lmax;
+  std::vector<std::unique_ptr<std::vector<float>>> curve_store;
   int neighbors[6];
   std::vector<VolumeVisOp> vvis;
   std::map<int, std::unique_ptr<VolumeData>> volumes;
@@ -266,9 +561,17 @@ static void prim_box(const gxo_scene &s, const Prim &p, float lo[3], float hi[3]
       const float *v = g.verts + 3 * (size_t)g.idx[3 * (size_t)p.prim + j];
       for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], v[k]); hi[k] = std::max(hi[k], v[k]); }
     }
-  } else {
+  } else if (g.kind == 1) {
     float r = sphere_radius(g, p.prim);
     for (int k = 0; k < 3; k++) { lo[k] = g.centers[3 * (size_t)p.prim + k] - r; hi[k] = g.centers[3 * (size_t)p.prim + k] + r; }
+  } else {
+    // the swept surface lies in the convex hull of the control points grown by the largest control radius
+    const float *c = g.cp + 16 * (size_t)p.prim;
+    const float r = std::max(std::max(fabsf(c[3]), fabsf(c[7])), std::max(fabsf(c[11]), fabsf(c[15])));
+    for (int k = 0; k < 3; k++) {
+      lo[k] = std::min(std::min(c[k], c[4 + k]), std::min(c[8 + k], c[12 + k])) - r;
+      hi[k] = std::max(std::max(c[k], c[4 + k]), std::max(c[8 + k], c[12 + k])) + r;
+    }
   }
 }
 
@@ -308,7 +611,7 @@ static void build_accel(gxo_scene &s) {
   s.prims.clear(); s.nodes.clear();
   std::vector<Prim> all;
   for (int g = 0; g < (int)s.geoms.size(); g++) {
-    int np = s.geoms[g].kind == 0 ? s.geoms[g].nt : s.geoms[g].n;
+    int np = s.geoms[g].kind == 0 ? s.geoms[g].nt : s.geoms[g].kind == 1 ? s.geoms[g].n : s.geoms[g].ncurves;
     for (int i = 0; i < np; i++) all.push_back(Prim{g, i});
   }
   if (all.empty()) return;
@@ -360,9 +663,12 @@ static bool nearest_hit(const gxo_scene &s, V3 org, V3 dir, float tnear, float t
         V3 v2 = mk(g.verts[3 * (size_t)ix[2]], g.verts[3 * (size_t)ix[2] + 1], g.verts[3 * (size_t)ix[2] + 2]);
         // candidates are accepted against the ORIGINAL interval, the nearest is picked after
         h = tri_test(v0, v1, v2, org, dir, tnear, tfar, t, u, v, Ng);
-      } else {
+      } else if (g.kind == 1) {
         // spheres: strict t < tfar (DataDrivenSpheres.ispc:135-141)
         h = sphere_test(g, p.prim, org, dir, tnear, tfar, t, Ng);
+      } else {
+        // curves: tnear < t < tfar, u in [0,1] (curve_intersector_sweep.h:108-109); u is the curve parameter
+        h = curve_test(g.cp + 16 * (size_t)p.prim, org, dir, tnear, tfar, t, u, Ng);
       }
       if (!h) continue;
       bool better = !found || t < best.t ||
@@ -524,8 +830,21 @@ static void trace_one(gxo_scene &S, RL &R, int i, bool integrate, float step, fl
             V3 c = tf_color(g.tf, d);
             cr = c.x; cg = c.y; cb = c.z; ca = 1.0f;
           }
-        } else {            // DataDrivenSpheres.ispc:46-63
+        } else if (g.kind == 1) {   // DataDrivenSpheres.ispc:46-63
           V3 c = tf_color(g.tf, g.data ? g.data[h1.primID] : 0.f);
+          cr = c.x; cg = c.y; cb = c.z; ca = 1.0f;
+        } else {            // DataDrivenPathLines_postIntersect, DataDrivenPathLines.ispc:213-277: Ng = Ns = ray.Ng; the
+          // radius between the segment's FIRST TWO control points (vertices[indices[primID]], [+1]) is mapped back to a data value
+          const float *c4 = g.cp + 16 * (size_t)h1.primID;
+          const float radius = ((1.f - h1.u) * c4[3]) + (h1.u * c4[7]);
+          float dataval;
+          if (g.radius0 == g.radius1) dataval = g.value0;
+          else if (g.radius0 < g.radius1 && radius < g.radius0) dataval = g.value0;
+          else if (g.radius0 < g.radius1 && radius > g.radius1) dataval = g.value1;
+          else if (g.radius0 > g.radius1 && radius < g.radius1) dataval = g.value1;
+          else if (g.radius0 > g.radius1 && radius > g.radius0) dataval = g.value0;
+          else dataval = g.value0 + ((radius - g.radius0) / (g.radius1 - g.radius0)) * (g.value1 - g.value0);
+          V3 c = tf_color(g.tf, dataval);
           cr = c.x; cg = c.y; cb = c.z; ca = 1.0f;
         }
         V3 ffnng = normalize_isp(Ng);
@@ -991,6 +1310,55 @@ int gxo_scene_add_particles_vis(gxo_scene *s, int n, const float *centers, const
   set_tf(g.tf, colors, opacities, lo, hi);
   s->geoms.push_back(g);
   return (int)s->geoms.size() - 1;
+}
+
+int gxo_scene_add_pathlines_vis(gxo_scene *s, int n_verts, const float *verts, const float *data, int n_segments,
+                                const int *connectivity, float radius0, float radius1, float value0, float value1,
+                                const float *colors, const float *opacities, float lo, float hi) {
+  for (int i = 0; i < n_segments; i++)
+    if (connectivity[i] < 0 || connectivity[i] + 1 >= n_verts) return -1;
+  GeomOp g; memset(&g, 0, sizeof g);
+  g.kind = 2; g.data = data;
+  g.radius0 = radius0; g.radius1 = radius1; g.value0 = value0; g.value1 = value1;
+  s->curve_store.emplace_back(new std::vector<float>());
+  build_curves(n_segments, connectivity, verts, data, radius0, radius1, value0, value1, *s->curve_store.back());
+  g.ncurves = n_segments; g.cp = s->curve_store.back()->data();
+  set_tf(g.tf, colors, opacities, lo, hi);
+  s->geoms.push_back(g);
+  return (int)s->geoms.size() - 1;
+}
+
+int gxo_build_curves(int n_verts, const float *verts, const float *data, int n_segments, const int *connectivity,
+                     float radius0, float radius1, float value0, float value1, float *cp_out) {
+  for (int i = 0; i < n_segments; i++)
+    if (connectivity[i] < 0 || connectivity[i] + 1 >= n_verts) return -1;
+  std::vector<float> cp;
+  build_curves(n_segments, connectivity, verts, data, radius0, radius1, value0, value1, cp);
+  memcpy(cp_out, cp.data(), cp.size() * sizeof(float));
+  return 0;
+}
+
+int gxo_curve_intersect(int n_curves, const float *cp, int n_rays, const float *org3, const float *dir3, const float *tnear,
+                        const float *tfar, int *prim_out, float *tu_out, float *ng_out, int per_curve) {
+  for (int r = 0; r < n_rays; r++) {
+    const V3 org = mk(org3[3 * r], org3[3 * r + 1], org3[3 * r + 2]), dir = mk(dir3[3 * r], dir3[3 * r + 1], dir3[3 * r + 2]);
+    int best = -1; float bt = tfar[r], bu = 0.f; V3 bn = mk(0.f, 0.f, 0.f);
+    for (int p = 0; p < n_curves; p++) {
+      float t, u; V3 Ng;
+      const bool h = curve_test(cp + 16 * (size_t)p, org, dir, tnear[r], tfar[r], t, u, Ng);
+      if (per_curve) {
+        const size_t o = (size_t)r * n_curves + p;
+        prim_out[o] = h ? 1 : 0;
+        tu_out[2 * o] = h ? t : tfar[r]; tu_out[2 * o + 1] = h ? u : 0.f;
+        if (ng_out) { ng_out[3 * o] = h ? Ng.x : 0.f; ng_out[3 * o + 1] = h ? Ng.y : 0.f; ng_out[3 * o + 2] = h ? Ng.z : 0.f; }
+      } else if (h && (best < 0 || t < bt)) { best = p; bt = t; bu = u; bn = Ng; }
+    }
+    if (!per_curve) {
+      prim_out[r] = best; tu_out[2 * r] = bt; tu_out[2 * r + 1] = bu;
+      if (ng_out) { ng_out[3 * r] = bn.x; ng_out[3 * r + 1] = bn.y; ng_out[3 * r + 2] = bn.z; }
+    }
+  }
+  return 0;
 }
 
 int gxo_scene_commit(gxo_scene *s) {

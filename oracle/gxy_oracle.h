@@ -89,6 +89,20 @@ int gxo_scene_add_particles_vis(gxo_scene *, int n, const float *centers, const 
                                 const float *colors, const float *opacities,
                                 float range_lo, float range_hi);
 
+/* A PathLinesVis operator: poly-line vertices + per-vertex data, connectivity[i] = index of the first vertex of
+ * segment i (PathLines.cpp:110-122).  Built into round cubic Bezier segments as DataDrivenPathLines::finalize does
+ * (src/ospray/DataDrivenPathLines.cpp:103-156); the control points are owned by the scene.  <0: bad connectivity. */
+int gxo_scene_add_pathlines_vis(gxo_scene *, int n_verts, const float *verts, const float *data, int n_segments,
+                                const int *connectivity, float radius0, float radius1, float value0, float value1,
+                                const float *colors, const float *opacities, float range_lo, float range_hi);
+/* the control points alone: cp_out = n_segments x 4 x (x,y,z,r) */
+int gxo_build_curves(int n_verts, const float *verts, const float *data, int n_segments, const int *connectivity,
+                     float radius0, float radius1, float value0, float value1, float *cp_out);
+/* Embree's round-Bezier sweep intersector restated (curve_intersector_sweep.h:55-241), brute force over n_curves
+ * segments; same signature as oracle/embree_curve_ref.cpp's gxr_curve_intersect, against which it is pinned. */
+int gxo_curve_intersect(int n_curves, const float *cp, int n_rays, const float *org3, const float *dir3, const float *tnear,
+                        const float *tfar, int *prim_out, float *tu_out, float *ng_out, int per_curve);
+
 /* Builds the acceleration structure (the oracle's own simple BVH). */
 int gxo_scene_commit(gxo_scene *);
 
