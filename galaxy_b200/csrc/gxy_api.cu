@@ -180,6 +180,12 @@ struct gxy_particles {
   int n;
   float *d_centers, *d_data;
 };
+struct gxy_pathlines {
+  gxy_context *ctx;
+  std::vector<float> verts, data;   // host copies: the curves depend on the Vis (radius mapping), built at commit
+  std::vector<int> conn;
+  bool has_data;
+};
 struct gxy_raylist {
   float *base;
   int n, aligned_n;
@@ -241,6 +247,7 @@ struct GeomOp {
   int kind;
   gxy_triangles *tri;
   gxy_particles *par;
+  gxy_pathlines *pl;
   float radius0, radius1, value0, value1;
   gxy_transfer_function tf;
 };
@@ -257,6 +264,7 @@ struct gxy_vis {
   DevGeom *d_geoms = nullptr;
   int *d_error = nullptr;
   BvhResult bvh;
+  std::vector<float *> d_curves;   // control points of the PathLines operators (device), one buffer per operator
   bool has_dvr = false;
   // work buffers
   RayBuf cur, next, send, recv, hits;
@@ -407,6 +415,75 @@ void gxy_particles_destroy(gxy_particles *p) {
   delete p;
 }
 
+int gxy_pathlines_create(gxy_context *c, int n_verts, const float *verts, const float *data, int n_segments, const int *connectivity,
+                         gxy_pathlines **out) {
+  if (use_device(c)) return 1;
+  GXY_CHECK(n_verts >= 0 && n_segments >= 0 && (n_verts == 0 || verts) && (n_segments == 0 || connectivity), "pathlines need vertices and connectivity");
+  for (int i = 0; i < n_segments; i++)
+    GXY_CHECK(connectivity[i] >= 0 && connectivity[i] + 1 < n_verts, "pathlines: segment %d starts at vertex %d of %d", i, connectivity[i], n_verts);
+  gxy_pathlines *p = new gxy_pathlines();
+  p->ctx = c;
+  p->verts.assign(verts, verts + 3 * (size_t)n_verts);
+  p->has_data = data != nullptr;
+  if (data) p->data.assign(data, data + n_verts);
+  else p->data.assign((size_t)n_verts, 0.f);
+  p->conn.assign(connectivity, connectivity + n_segments);
+  *out = p;
+  return 0;
+}
+void gxy_pathlines_destroy(gxy_pathlines *p) { delete p; }
+
+// DataDrivenPathLines.cpp:28-37 (MAP_RADIUS; its `R <= 0.0` / `R >= 1.0` compare in double, exact for a float)
+static inline float map_radius(float d, float radius0, float radius1, float value0, float value1) {
+  if (value0 == value1) return radius0;
+  const float R = (d - value0) / (value1 - value0);
+  return (R <= 0.0f) ? radius0 : (R >= 1.0f) ? radius1 : radius0 + R * (radius1 - radius0);
+}
+// ospcommon lerp(factor, a, b) (ospmath.h:196-200)
+static inline float os_lerp(float factor, float a, float b) { return (1.f - factor) * a + factor * b; }
+
+int gxy_build_curves(int n_verts, const float *verts, const float *data, int n_segments, const int *connectivity, float radius0,
+                     float radius1, float value0, float value1, float *cp_out) {
+  GXY_CHECK(n_segments == 0 || (verts && connectivity && cp_out), "gxy_build_curves: NULL argument");
+  for (int i = 0; i < n_segments; i++)
+    GXY_CHECK(connectivity[i] >= 0 && connectivity[i] + 1 < n_verts, "pathlines: segment %d starts at vertex %d of %d", i, connectivity[i], n_verts);
+  // DataDrivenPathLines.cpp:103-156.  vertexCurve/indexCurve: a segment that continues pushes 3 control points, its 4th is
+  // the first of the next segment (Embree reads 4 consecutive vertices from indexCurve[i]); a line end repeats its end point.
+  struct P4 { float x, y, z, r; };
+  std::vector<P4> vc;
+  std::vector<size_t> ic((size_t)n_segments);
+  vc.reserve(3 * (size_t)n_segments + 4);
+  bool middle = false;
+  float tx = 0.f, ty = 0.f, tz = 0.f;   // tangent
+  for (int i = 0; i < n_segments; i++) {
+    const int idx = connectivity[i];
+    const float *s = verts + 3 * (size_t)idx, *e = s + 3;
+    const float sx = s[0] - e[0], sy = s[1] - e[1], sz = s[2] - e[2];
+    const float lengthSegment = sqrtf(sx * sx + sy * sy + sz * sz);
+    const float startRadius = map_radius(data ? data[idx] : 0.f, radius0, radius1, value0, value1);
+    const float endRadius = map_radius(data ? data[idx + 1] : 0.f, radius0, radius1, value0, value1);
+    ic[i] = vc.size();
+    vc.push_back(P4{s[0], s[1], s[2], startRadius});
+    if (middle) vc.push_back(P4{s[0] + tx, s[1] + ty, s[2] + tz, os_lerp(1.f / 3, startRadius, endRadius)});
+    else vc.push_back(P4{s[0], s[1], s[2], startRadius});
+    middle = i + 1 < n_segments && connectivity[i + 1] == idx + 1;
+    if (middle) {
+      const float *n = e + 3;
+      const float dx = (1.f / 3) * (n[0] - s[0]), dy = (1.f / 3) * (n[1] - s[1]), dz = (1.f / 3) * (n[2] - s[2]);
+      const float nx = n[0] - e[0], ny = n[1] - e[1], nz = n[2] - e[2];
+      const float b = sqrtf(nx * nx + ny * ny + nz * nz);
+      const float r = lengthSegment / (lengthSegment + b);
+      vc.push_back(P4{e[0] - r * dx, e[1] - r * dy, e[2] - r * dz, os_lerp(2.f / 3, startRadius, endRadius)});
+      tx = (1.f - r) * dx; ty = (1.f - r) * dy; tz = (1.f - r) * dz;
+    } else {
+      vc.push_back(P4{e[0], e[1], e[2], endRadius});
+      vc.push_back(P4{e[0], e[1], e[2], endRadius});
+    }
+  }
+  for (int i = 0; i < n_segments; i++) memcpy(cp_out + 16 * (size_t)i, &vc[ic[i]], 16 * sizeof(float));
+  return 0;
+}
+
 // ---- Visualization -----------------------------------------------------------------------------
 int gxy_vis_create(gxy_context *c, gxy_vis **out) {
   if (use_device(c)) return 1;
@@ -425,6 +502,8 @@ static void vis_free_commit(gxy_vis *v) {
   if (v->d_error) cudaFree(v->d_error);
   if (v->bvh.nodes) cudaFree(v->bvh.nodes);
   if (v->bvh.prims) cudaFree(v->bvh.prims);
+  for (float *p : v->d_curves) cudaFree(p);
+  v->d_curves.clear();
   v->d_tfs = nullptr; v->d_geoms = nullptr; v->d_error = nullptr;
   v->bvh = BvhResult();
   v->committed = false;
@@ -498,6 +577,19 @@ int gxy_vis_add_particles(gxy_vis *v, gxy_particles *p, float radius0, float rad
   return 0;
 }
 
+int gxy_vis_add_pathlines(gxy_vis *v, gxy_pathlines *p, float radius0, float radius1, float value0, float value1,
+                          const gxy_transfer_function *tf) {
+  GXY_CHECK(p && tf, "gxy_vis_add_pathlines: NULL argument");
+  GXY_CHECK(p->ctx == v->ctx, "pathlines belong to another context");
+  GeomOp g;
+  memset(&g, 0, sizeof g);
+  g.kind = 2; g.pl = p; g.tf = *tf;
+  g.radius0 = radius0; g.radius1 = radius1; g.value0 = value0; g.value1 = value1;
+  v->geoms.push_back(g);
+  v->committed = false;
+  return 0;
+}
+
 static void pack_tf(const gxy_transfer_function &in, DevTF &out) {
   for (int i = 0; i < 256; i++) out.e[i] = make_float4(in.colors[i][0], in.colors[i][1], in.colors[i][2], in.opacities[i]);
   out.lo = in.range_lo; out.hi = in.range_hi; out.pad0 = out.pad1 = 0.f;
@@ -555,6 +647,21 @@ int gxy_vis_commit(gxy_vis *v) {
     if (g.kind == 0) {
       d.idx = g.tri->d_idx; d.normals = g.tri->d_normals; d.data = g.tri->d_data;
       b.n_prims = g.tri->nt; b.verts = g.tri->d_verts; b.idx = g.tri->d_idx;
+    } else if (g.kind == 2) {
+      // DataDrivenPathLines::finalize runs at commit in the reference too (the radii depend on this Vis)
+      const int nseg = (int)g.pl->conn.size();
+      std::vector<float> cp(16 * (size_t)nseg);
+      if (gxy_build_curves((int)(g.pl->verts.size() / 3), g.pl->verts.data(), g.pl->has_data ? g.pl->data.data() : nullptr, nseg,
+                           g.pl->conn.data(), g.radius0, g.radius1, g.value0, g.value1, cp.data()))
+        return 1;
+      float *d_cp = nullptr;
+      GXY_CUDA(cudaMalloc(&d_cp, sizeof(float) * (cp.empty() ? 16 : cp.size())));
+      v->d_curves.push_back(d_cp);
+      if (!cp.empty()) GXY_CUDA(cudaMemcpy(d_cp, cp.data(), sizeof(float) * cp.size(), cudaMemcpyHostToDevice));
+      d.centers = d_cp;
+      d.radius0 = g.radius0; d.radius1 = g.radius1; d.value0 = g.value0; d.value1 = g.value1;
+      b.n_prims = nseg; b.centers = d_cp;
+      P.n_curves += nseg;
     } else {
       d.centers = g.par->d_centers; d.data = g.par->d_data;
       d.radius0 = g.radius0; d.radius1 = g.radius1; d.value0 = g.value0; d.value1 = g.value1;
@@ -1138,6 +1245,9 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
   bool fused = true;
   // (decided from the operator list, which is the same on every rank, not from the clipped primitive count)
   for (int p = 0; p < nparts; p++) fused = fused && parts[p]->P.n_volvis == 0 && !parts[p]->geoms.empty();
+  // PathLines operators: the curve test lives in the list-path kernels only (trace_kernel<.., CURVES>)
+  for (int p = 0; p < nparts; p++)
+    for (const GeomOp &g : parts[p]->geoms) fused = fused && g.kind != 2;
   if (const char *e = getenv("GXY_FUSED")) fused = fused && atoi(e) != 0;
   if (multi_proc && fused) {
     // one process per GPU, geometry only: rays and pixels move through peer arenas, not through NCCL

@@ -69,9 +69,18 @@ __global__ void __launch_bounds__(256)
         const float *v = g.verts + 3 * (size_t)g.idx[3 * i + j];
         for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], v[k]); mx[k] = fmaxf(mx[k], v[k]); }
       }
-    } else {
+    } else if (g.kind == 1) {
       const float r = sphere_radius(g, i);
       for (int k = 0; k < 3; k++) { mn[k] = g.centers[3 * i + k] - r; mx[k] = g.centers[3 * i + k] + r; }
+    } else {
+      // round Bezier segment: the swept surface lies in the convex hull of the control points grown by the largest
+      // control radius (position and radius are Bernstein combinations of the control values)
+      const float *c = g.centers + 16 * (size_t)i;
+      const float r = fmaxf(fmaxf(fabsf(c[3]), fabsf(c[7])), fmaxf(fabsf(c[11]), fabsf(c[15])));
+      for (int k = 0; k < 3; k++) {
+        mn[k] = fminf(fminf(c[k], c[4 + k]), fminf(c[8 + k], c[12 + k])) - r;
+        mx[k] = fmaxf(fmaxf(c[k], c[4 + k]), fmaxf(c[8 + k], c[12 + k])) + r;
+      }
     }
     lo[p] = make_float4(mn[0], mn[1], mn[2], 0.f);
     hi[p] = make_float4(mx[0], mx[1], mx[2], 0.f);
@@ -370,10 +379,15 @@ __global__ void __launch_bounds__(256)
     r.a = make_float4(a[0], a[1], a[2], a[0] - b[0]);
     r.b = make_float4(a[1] - b[1], a[2] - b[2], c[0] - a[0], c[1] - a[1]);
     r.c = make_float4(c[2] - a[2], __uint_as_float((unsigned)g.geom_id), __uint_as_float((unsigned)i), 0.f);
-  } else {
+  } else if (g.kind == 1) {
     r.a = make_float4(g.centers[3 * i], g.centers[3 * i + 1], g.centers[3 * i + 2], sphere_radius(g, i));
     r.b = make_float4(g.epsilon, 0.f, 0.f, 0.f);
     r.c = make_float4(0.f, __uint_as_float((unsigned)g.geom_id | (1u << 24)), __uint_as_float((unsigned)i), 0.f);
+  } else {
+    const unsigned long long cp = (unsigned long long)(g.centers + 16 * (size_t)i);   // 64-byte aligned (cudaMalloc + 64 i)
+    r.a = make_float4(__uint_as_float((unsigned)cp), __uint_as_float((unsigned)(cp >> 32)), 0.f, 0.f);
+    r.b = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.c = make_float4(0.f, __uint_as_float((unsigned)g.geom_id | (2u << 24)), __uint_as_float((unsigned)i), 0.f);
   }
   out[dest_of[s]] = r;
 }

@@ -69,12 +69,12 @@ struct DevVolVis {
 
 // geometry operator table entry (post-intersect data)
 struct DevGeom {
-  int kind;  // 0 triangles, 1 spheres
+  int kind;  // 0 triangles, 1 spheres, 2 round Bezier curves (PathLines)
   int tf;
   const int *idx;        // triangles: int3 per prim
   const float *normals;  // float3 per vertex or NULL
   const float *data;     // per vertex (triangles) / per particle (spheres) or NULL
-  const float *centers;
+  const float *centers;  // spheres: float3 per particle; curves: 4 control points (x,y,z,r) = 16 floats per segment
   float radius0, radius1, value0, value1, epsilon;
   int pad;
 };
@@ -100,6 +100,7 @@ static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
 // primitive record in leaf order, 48 bytes (3 x 16 B loads)
 //   triangle: a=(v0.xyz, e1.x) b=(e1.yz, e2.xy) c=(e2.z, bits(geom|kind<<24), bits(prim), 0)
 //   sphere:   a=(c.xyz, radius) b=(epsilon,0,0,0) c=(0, bits(geom|1<<24), bits(prim), 0)
+//   curve:    a=(address of its 4 control points: low, high word, 0, 0) c=(0, bits(geom|2<<24), bits(prim), 0)
 struct __align__(16) PrimRec {
   float4 a, b, c;
 };
@@ -110,6 +111,8 @@ struct SceneParams {
   int n_volvis, n_geoms;
   int integrate;  // any volume_render || isovalues (TraceRays.ispc:348-352)
   float step;     // min samplingStep*samplingRate (TraceRays.ispc:354-360)
+  int n_curves;   // round Bezier segments (PathLines) among the primitives; > 0 selects the CURVES kernels
+  int pad_curves; // (these two words fill what was alignment padding in front of vv: no offset changes)
   DevVolVis vv[GXY_MAX_VOLUME_VIS];
   const DevTF *tfs;
   const DevGeom *geoms;

@@ -123,7 +123,7 @@ void gxy_timeline_mark(const char *name, cudaStream_t st);
 
 // ---- BVH build (gxy_bvh.cu) -----------------------------------------------------------------
 struct GeomBuildInput {
-  int kind;  // 0 triangles, 1 spheres
+  int kind;  // 0 triangles, 1 spheres, 2 round Bezier curves (centers = 16 floats per segment: 4 control points x,y,z,r)
   int geom_id;
   long long n_prims;
   const float *verts;  // device

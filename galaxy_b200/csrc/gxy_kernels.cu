@@ -160,7 +160,7 @@ __device__ __forceinline__ void sample_volumes(const SceneParams &P, const VolK 
 #define GXY_MARCH_BLOCKS 8
 #endif
 
-template <int NV, bool HAS_GEOM, bool IDX32>
+template <int NV, bool HAS_GEOM, bool IDX32, bool CURVES = false>
 __global__ void __launch_bounds__(GXY_TRACE_THREADS, (NV <= 2 && !HAS_GEOM) ? GXY_MARCH_BLOCKS : 1)
     trace_kernel(const __grid_constant__ SceneParams P, Rays R, int n, float global_epsilon, int *__restrict__ hit_ids,
                  int anyhit_secondary, unsigned long long *__restrict__ sample_counter) {
@@ -234,15 +234,15 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, (NV <= 2 && !HAS_GEOM) ? GX
   if (HAS_GEOM) {
     Hit1 h1;
     bool found;
-    if (!shadeFlag && anyhit_secondary) found = traverse<true>(P, org, dir, ray_t0, ray_t, h1, stack);
-    else found = traverse<false>(P, org, dir, ray_t0, ray_t, h1, stack);
+    if (!shadeFlag && anyhit_secondary) found = traverse<true, CURVES>(P, org, dir, ray_t0, ray_t, h1, stack);
+    else found = traverse<false, CURVES>(P, org, dir, ray_t0, ray_t, h1, stack);
     if (hit_ids) { hit_ids[2 * i] = found ? h1.geom : -1; hit_ids[2 * i + 1] = found ? h1.prim : -1; }
     if (found) {
       ray_t = h1.t;
       if (shadeFlag) {
         float3 col, Ns;
         float ca;
-        shade_geometry_hit(P, h1, dir, col, ca, Ns);
+        shade_geometry_hit<CURVES>(P, h1, dir, col, ca, Ns);
         hit.color = col; hit.opacity = ca; hit.normal = Ns; hit.t = ray_t;
       }
       surface_hit = true;
@@ -620,7 +620,10 @@ static int launch_trace_nv(const SceneParams &P, Rays R, int n, float eps, int *
     const DevVolume &v = P.vv[m].vol;
     idx32 = idx32 && (unsigned long long)v.dims[0] * (unsigned long long)v.dims[1] * (unsigned long long)v.dims[2] < (1ull << 31);
   }
-  if (P.n_prims > 0) {
+  if (P.n_prims > 0 && P.n_curves > 0) {
+    // Visualizations with PathLines: the per-lane traversal with the curve test; 64-bit sampler indices (one instantiation per NV)
+    trace_kernel<NV, true, false, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, anyhit ? 1 : 0, sc);
+  } else if (P.n_prims > 0) {
     if (idx32) trace_kernel<NV, true, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, anyhit ? 1 : 0, sc);
     else trace_kernel<NV, true, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, anyhit ? 1 : 0, sc);
   } else {
@@ -636,7 +639,7 @@ int launch_trace(const SceneParams &P, Rays R, int n, float global_epsilon, int 
   if (n <= 0) return 0;
   const char *pe = getenv("GXY_TRACE_PERSISTENT");
   const bool persistent = !(pe && atoi(pe) == 0);
-  if (P.n_volvis == 0 && P.n_prims > 0 && persistent) return launch_trace_geom(P, R, n, hit_ids, anyhit_secondary, st);
+  if (P.n_volvis == 0 && P.n_prims > 0 && P.n_curves == 0 && persistent) return launch_trace_geom(P, R, n, hit_ids, anyhit_secondary, st);
   switch (P.n_volvis) {
     case 0: return launch_trace_nv<0>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st);
     case 1: return launch_trace_nv<1>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st);
@@ -648,6 +651,7 @@ int launch_trace(const SceneParams &P, Rays R, int n, float global_epsilon, int 
 
 // ------------------------------------------------------------------------------------------------
 // nearest-hit only (gxy_intersect)
+template <bool CURVES>
 __global__ void __launch_bounds__(GXY_TRACE_THREADS)
     intersect_kernel(const __grid_constant__ SceneParams P, int n, const float *__restrict__ org3, const float *__restrict__ dir3,
                      const float *__restrict__ tnear, const float *__restrict__ tfar, int *__restrict__ gp, float *__restrict__ tuv) {
@@ -656,7 +660,7 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS)
   if (i >= n) return;
   Hit1 h;
   const float3 o = f3(org3[3 * i], org3[3 * i + 1], org3[3 * i + 2]), d = f3(dir3[3 * i], dir3[3 * i + 1], dir3[3 * i + 2]);
-  const bool f = traverse<false>(P, o, d, tnear[i], tfar[i], h, stack);
+  const bool f = traverse<false, CURVES>(P, o, d, tnear[i], tfar[i], h, stack);
   gp[2 * i] = f ? h.geom : -1;
   gp[2 * i + 1] = f ? h.prim : -1;
   tuv[3 * i] = f ? h.t : tfar[i];
@@ -667,8 +671,9 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS)
 int launch_intersect(const SceneParams &P, int n, const float *org3, const float *dir3, const float *tnear, const float *tfar,
                      int *geom_prim2, float *tuv3, cudaStream_t st) {
   if (n <= 0) return 0;
-  intersect_kernel<<<(n + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS, GXY_TRACE_THREADS, 0, st>>>(P, n, org3, dir3, tnear, tfar,
-                                                                                                 geom_prim2, tuv3);
+  const int blocks = (n + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
+  if (P.n_curves > 0) intersect_kernel<true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, n, org3, dir3, tnear, tfar, geom_prim2, tuv3);
+  else intersect_kernel<false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, n, org3, dir3, tnear, tfar, geom_prim2, tuv3);
   GXY_CUDA(cudaGetLastError());
   return 0;
 }

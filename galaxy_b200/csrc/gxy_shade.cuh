@@ -13,6 +13,7 @@ namespace gxy {
 // postIntersect of a geometry hit (Model.ih:97-187 + DataDrivenTriangleMesh.ispc:34-121 /
 // DataDrivenSpheres.ispc:46-63): colour from the transfer function, shading normal normalised and
 // faced towards the ray
+template <bool CURVES = false>
 __device__ __forceinline__ void shade_geometry_hit(const SceneParams &P, const Hit1 &h1, float3 dir, float3 &col, float &ca, float3 &Ns) {
   const DevGeom g = P.geoms[h1.geom];
   float3 Ng = h1.Ng;
@@ -33,8 +34,21 @@ __device__ __forceinline__ void shade_geometry_hit(const SceneParams &P, const H
       col = tf_color(P.tfs + g.tf, d);
       ca = 1.0f;
     }
-  } else {  // DataDrivenSpheres.ispc:46-63
+  } else if (!CURVES || g.kind == 1) {  // DataDrivenSpheres.ispc:46-63
     col = tf_color(P.tfs + g.tf, g.data ? __ldg(g.data + h1.prim) : 0.f);
+    ca = 1.0f;
+  } else {  // DataDrivenPathLines_postIntersect (DataDrivenPathLines.ispc:213-277): Ng = Ns = ray.Ng; the radius between
+    // the segment's FIRST TWO control points at the curve parameter u is mapped back to a data value
+    const float w0 = __ldg(g.centers + 16 * (size_t)h1.prim + 3), w1 = __ldg(g.centers + 16 * (size_t)h1.prim + 7);
+    const float radius = ((1.f - h1.u) * w0) + (h1.u * w1);
+    float dataval;
+    if (g.radius0 == g.radius1) dataval = g.value0;
+    else if (g.radius0 < g.radius1 && radius < g.radius0) dataval = g.value0;
+    else if (g.radius0 < g.radius1 && radius > g.radius1) dataval = g.value1;
+    else if (g.radius0 > g.radius1 && radius < g.radius1) dataval = g.value1;
+    else if (g.radius0 > g.radius1 && radius > g.radius0) dataval = g.value0;
+    else dataval = g.value0 + ((radius - g.radius0) / (g.radius1 - g.radius0)) * (g.value1 - g.value0);
+    col = tf_color(P.tfs + g.tf, dataval);
     ca = 1.0f;
   }
   Ng = normalize_isp(Ng);

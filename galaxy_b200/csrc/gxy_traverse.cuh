@@ -19,6 +19,7 @@
 // ties broken on the lowest (geomID, primID) -- independent of traversal order.
 #pragma once
 #include "gxy_common.cuh"
+#include "gxy_curve.cuh"
 
 namespace gxy {
 
@@ -85,6 +86,19 @@ __device__ __forceinline__ bool sphere_test(const float4 ra, const float4 rb, fl
   if (t_in > t0 && t_in < tfar) { hit = true; t = t_in; }
   else if (t_out > (t0 + geps) && t_out < tfar) { hit = true; t = t_out; }
   return hit;
+}
+
+// one round Bezier segment (PathLines) against the ray: the record holds the address of its 4 control points.
+// Embree's sweep intersector (gxy_curve.cuh); hits in the OPEN interval (tnear, tfar), u = curve parameter.
+__device__ __forceinline__ bool curve_rec_test(const float4 ra, float3 org, float3 dir, float tnear, float tfar, gxc::CurveHit &h) {
+  const float4 *cp = reinterpret_cast<const float4 *>(((unsigned long long)__float_as_uint(ra.y) << 32) | (unsigned long long)__float_as_uint(ra.x));
+  float c[16];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float4 q = __ldg(cp + k);
+    c[4 * k] = q.x; c[4 * k + 1] = q.y; c[4 * k + 2] = q.z; c[4 * k + 3] = q.w;
+  }
+  return gxc::curve_test(c, org.x, org.y, org.z, dir.x, dir.y, dir.z, tnear, tfar, h);
 }
 
 // ---- per-ray constants and traversal state ------------------------------------------------------
@@ -294,7 +308,9 @@ __device__ __forceinline__ void node_step(const SceneParams &P, const RayCtx &rc
 }
 
 // Primitive phase: test every primitive of the group.  Returns true if the traversal is over
-// (anyhit and a candidate was accepted).
+// (anyhit and a candidate was accepted).  CURVES: the scene holds PathLines (kind 2 records); only the list-path
+// kernels of such scenes are instantiated with it, every other kernel is compiled exactly as before.
+template <bool CURVES = false>
 __device__ __forceinline__ bool prim_step(const SceneParams &P, const RayCtx &rc, TravState &s, const bool anyhit) {
   while (s.tg.y != 0u) {
     const int b = __ffs((int)s.tg.y) - 1;
@@ -310,7 +326,12 @@ __device__ __forceinline__ bool prim_step(const SceneParams &P, const RayCtx &rc
     float t, u = 0.f, v = 0.f;
     bool h;
     if ((gk >> 24) == 0) h = tri_test(ra, rb, rcq, rc.org, rc.dir, rc.tnear, rc.tfar, t, u, v);
-    else h = sphere_test(ra, rb, rc.org, rc.dir, rc.tnear, rc.tfar, t);
+    else if (!CURVES || (gk >> 24) == 1) h = sphere_test(ra, rb, rc.org, rc.dir, rc.tnear, rc.tfar, t);
+    else {
+      gxc::CurveHit ch;
+      h = curve_rec_test(ra, rc.org, rc.dir, rc.tnear, rc.tfar, ch);
+      if (h) { t = ch.t; u = ch.u; }
+    }
     if (h && (t < s.best_t || (t == s.best_t && key < s.best_key))) {
       s.best_t = t; s.best_u = u; s.best_v = v; s.best_key = key; s.best_rec = ri;
       if (anyhit) return true;
@@ -398,14 +419,16 @@ __device__ __forceinline__ bool trav_advance(TravState &s, const uint2 *__restri
 }
 
 // One per-lane traversal step (node, then its primitives).  Returns false when the traversal is complete.
+template <bool CURVES = false>
 __device__ __forceinline__ bool trav_step(const SceneParams &P, const RayCtx &rc, TravState &s, const bool anyhit,
                                           uint2 *__restrict__ stack, uint2 *__restrict__ lstack) {
   if (s.ng.y > 0x00ffffffu) node_step<0>(P, rc, s, stack, lstack);
-  if (prim_step(P, rc, s, anyhit)) return false;
+  if (prim_step<CURVES>(P, rc, s, anyhit)) return false;
   return trav_advance(s, stack, lstack);
 }
 
 // geomID / primID / Ng of the winner, recomputed from its record (saves registers in the loop)
+template <bool CURVES = false>
 __device__ __forceinline__ void trav_fetch_hit(const SceneParams &P, const RayCtx &rc, const TravState &s, Hit1 &best) {
   best.t = s.best_t; best.u = s.best_u; best.v = s.best_v;
   best.geom = (int)(s.best_key >> 28);
@@ -415,15 +438,22 @@ __device__ __forceinline__ void trav_fetch_hit(const SceneParams &P, const RayCt
   if ((__float_as_uint(rcq.y) >> 24) == 0) {
     const float3 e1 = f3(ra.w, rb.x, rb.y), e2 = f3(rb.z, rb.w, rcq.x);
     best.Ng = ecross(e2, e1);  // embree triangle.h:133-136
-  } else {
+  } else if (!CURVES || (__float_as_uint(rcq.y) >> 24) == 1) {
     best.Ng = rc.org + s.best_t * rc.dir - f3(ra.x, ra.y, ra.z);  // DataDrivenSpheres.ispc:143-150
+  } else {
+    // the same test on the same interval finds the same nearest hit of this segment again, now for its normal
+    // (curve_intersector_sweep.h:110-113); keeps Ng out of the traversal state
+    gxc::CurveHit ch;
+    ch.Ng.x = ch.Ng.y = ch.Ng.z = 0.f;
+    curve_rec_test(ra, rc.org, rc.dir, rc.tnear, rc.tfar, ch);
+    best.Ng = f3(ch.Ng.x, ch.Ng.y, ch.Ng.z);
   }
 }
 
 // Nearest hit in (tnear, tfar], run to completion.  ANYHIT: stop at the first accepted candidate
 // (occlusion rays when nothing integrates along t).  stack: shared-memory array
 // [GXY_STACK_SMEM][blockDim.x] of uint2, this thread uses column threadIdx.x.
-template <bool ANYHIT>
+template <bool ANYHIT, bool CURVES = false>
 __device__ __forceinline__ bool traverse(const SceneParams &P, float3 org, float3 dir, float tnear, float tfar, Hit1 &best,
                                          uint2 *__restrict__ stack) {
   best.geom = -1; best.prim = -1; best.t = tfar; best.u = best.v = 0.f;
@@ -434,9 +464,9 @@ __device__ __forceinline__ bool traverse(const SceneParams &P, float3 org, float
   TravState s;
   trav_init(s, rc);
   uint2 lstack[GXY_STACK_LOCAL];
-  while (trav_step(P, rc, s, ANYHIT, stack, lstack)) {}
+  while (trav_step<CURVES>(P, rc, s, ANYHIT, stack, lstack)) {}
   if (s.best_key == GXY_NO_HIT) return false;
-  trav_fetch_hit(P, rc, s, best);
+  trav_fetch_hit<CURVES>(P, rc, s, best);
   return true;
 }
 

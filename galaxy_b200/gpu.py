@@ -82,6 +82,10 @@ def lib():
         L.gxy_triangles_destroy.argtypes = [vp]
         L.gxy_particles_create.argtypes = [vp, C.c_int, fp, fp, C.POINTER(vp)]
         L.gxy_particles_destroy.argtypes = [vp]
+        L.gxy_pathlines_create.argtypes = [vp, C.c_int, fp, fp, C.c_int, ip, C.POINTER(vp)]
+        L.gxy_pathlines_destroy.argtypes = [vp]
+        L.gxy_build_curves.argtypes = [C.c_int, fp, fp, C.c_int, ip, C.c_float, C.c_float, C.c_float, C.c_float, fp]
+        L.gxy_vis_add_pathlines.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(TransferFunction)]
         L.gxy_vis_create.argtypes = [vp, C.POINTER(vp)]
         L.gxy_vis_destroy.argtypes = [vp]
         L.gxy_vis_set_partition.argtypes = [vp, fp, fp, fp, fp, ip]
@@ -255,6 +259,15 @@ class Scene:
         self._owned.append(("particles", h))
         tf = make_tf(colors, opacities, lo, hi)
         check(lib().gxy_vis_add_particles(self.h, h, radius0, radius1, value0, value1, C.byref(tf)))
+
+    def add_pathlines_vis(self, verts, data, connectivity, radius0, radius1, value0, value1, colors, opacities, lo, hi):
+        verts, data = _f32(verts), _f32(data)
+        conn = np.ascontiguousarray(connectivity, dtype=np.int32)
+        h = C.c_void_p()
+        check(lib().gxy_pathlines_create(self.ctx.h, len(verts), _f(verts), _f(data), len(conn), _i(conn), C.byref(h)))
+        self._owned.append(("pathlines", h))
+        tf = make_tf(colors, opacities, lo, hi)
+        check(lib().gxy_vis_add_pathlines(self.h, h, radius0, radius1, value0, value1, C.byref(tf)))
 
     def commit(self):
         check(lib().gxy_vis_commit(self.h))

@@ -55,6 +55,27 @@ class ParticlesDataset:
         self.data = np.ascontiguousarray(data, f32)
 
 
+class PathLinesDataset:
+    """src/data/PathLines.cpp: poly-lines over a shared point array (a .vtu with VTK_POLY_LINE cells)."""
+
+    kind = "PathLines"
+
+    def __init__(self, points, data, lines):
+        self.points = np.ascontiguousarray(points, dtype=f32).reshape(-1, 3)
+        self.data = np.ascontiguousarray(data, dtype=f32).reshape(-1)
+        self.lines = [np.asarray(l, dtype=np.int64) for l in lines]
+
+    def to_arrays(self):
+        """PathLines::load_from_vtkPointSet (PathLines.cpp:73-125): vertices duplicated per cell, in cell order;
+        connectivity[j] = index of the first vertex of every segment."""
+        ids = np.concatenate(self.lines) if self.lines else np.zeros(0, np.int64)
+        conn, k = [], 0
+        for l in self.lines:
+            conn.extend(range(k, k + len(l) - 1))
+            k += len(l)
+        return self.points[ids], self.data[ids], np.asarray(conn, np.int32)
+
+
 def radial_volume(name, n=256):
     """Closed-form fixtures of src/apps/radial.cpp:208-231 as written to .vol by scripts/vti2vol:70-80
     (note the %f rounding of origin/spacing in the header: spacing 0.007843 for n=256)."""
@@ -235,6 +256,12 @@ def parse_operator(v, base_dir=""):
         else:
             op["slices"] = []
         op["volume_render"] = bool(v.get("volume rendering", False))
+    elif t == "PathLinesVis":
+        # PathLinesVis::initialize / LoadFromJSON (PathLinesVis.cpp:46-55,105-114)
+        op["radius0"] = float(f32(v.get("radius0", -1.0)))
+        op["radius1"] = float(f32(v.get("radius1", 1.0)))
+        op["value0"] = float(f32(v.get("value0", 0.0)))
+        op["value1"] = float(f32(v.get("value1", 1.0)))
     elif t == "ParticlesVis":
         # ParticlesVis::initialize / LoadFromJSON (ParticlesVis.cpp:46-55,104-118)
         op["radius0"] = float(v.get("radius0", 0.025))
@@ -371,6 +398,42 @@ def clip_particles(ds, ext, ghost=0.1):
     return ParticlesDataset(ds.centers[inside], ds.data[inside])
 
 
+def clip_pathlines(ds, ext, ghost=0.1):
+    """Partition poly-lines as scripts/partitionVTUs.vpy:116-147 does: every run of vertices inside the ghost-extended
+    extent, plus one vertex at either end, becomes a poly-line of the piece; points are compacted in order of first use."""
+    lower = np.array([ext[0], ext[2], ext[4]], np.float64) - ghost
+    upper = np.array([ext[1], ext[3], ext[5]], np.float64) + ghost
+    pmap, order, lines = {}, [], []
+    for cell in ds.lines:
+        pts = ds.points[cell].astype(np.float64)
+        insiders = np.all(np.hstack((pts <= upper, pts >= lower)), axis=1)
+        linelen, offset, kk = len(insiders), 0, insiders
+        while len(kk) > 0:
+            s = int(np.argmax(kk))
+            if not kk[s]:
+                break
+            n = int(np.argmax(np.logical_not(kk[s:])))
+            if n == 0:
+                n = len(kk[s:]) + 1
+            n = s + n - 1
+            s, n = offset + s, offset + n
+            if s > 0:
+                s -= 1
+            if n < linelen - 1:
+                n += 1
+            seg = cell[s:n + 1]
+            offset = n + 1
+            kk = insiders[offset:]
+            for i in seg:
+                if int(i) not in pmap:
+                    pmap[int(i)] = len(order)
+                    order.append(int(i))
+            if len(seg) >= 2:
+                lines.append([pmap[int(i)] for i in seg])
+    order = np.asarray(order, np.int64)
+    return PathLinesDataset(ds.points[order], ds.data[order], lines)
+
+
 # ------------------------------------------------------------------------------------------------
 def build_partitions(backend, vis, datasets, nparts, geom_extents=None, only_rank=None, **scene_kw):
     """Instantiate one backend Scene per partition for Visualization `vis` (a parse_state entry).
@@ -421,6 +484,11 @@ def build_partitions(backend, vis, datasets, nparts, geom_extents=None, only_ran
                     p = ds if nparts == 1 else clip_particles(ds, ext)
                     sc.add_particles_vis(p.centers, p.data, op.get("radius0", 0.025), op.get("radius1", 0.0), op.get("value0", 0.0),
                                          op.get("value1", 0.0), colors, opac, lo, hi)
+                elif ds.kind == "PathLines":
+                    p = ds if nparts == 1 else clip_pathlines(ds, ext)
+                    pv, pd, pc = p.to_arrays()
+                    sc.add_pathlines_vis(pv, pd, pc, op.get("radius0", -1.0), op.get("radius1", 1.0), op.get("value0", 0.0),
+                                         op.get("value1", 1.0), colors, opac, lo, hi)
                 else:
                     raise NotImplementedError(ds.kind)
         sc.commit()

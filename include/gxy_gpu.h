@@ -36,6 +36,7 @@ typedef struct gxy_context   gxy_context;    /* one CUDA device + stream + memor
 typedef struct gxy_volume    gxy_volume;     /* src/data/Volume + src/ospray/OsprayVolume         */
 typedef struct gxy_triangles gxy_triangles;  /* src/data/Triangles + OsprayTriangles              */
 typedef struct gxy_particles gxy_particles;  /* src/data/Particles + OsprayParticles              */
+typedef struct gxy_pathlines gxy_pathlines;  /* src/data/PathLines + OsprayPathLines              */
 typedef struct gxy_vis       gxy_vis;        /* src/renderer/Visualization (one partition)        */
 typedef struct gxy_raylist   gxy_raylist;    /* src/renderer/Rays.h RayList, library-owned        */
 
@@ -123,6 +124,19 @@ void gxy_triangles_destroy(gxy_triangles *);
 int  gxy_particles_create(gxy_context *, int n, const float *centers, const float *data, gxy_particles **out);
 void gxy_particles_destroy(gxy_particles *);
 
+/* replaces ospNewGeometry("ddpathlines") (src/ospray/OsprayPathLines.cpp:25-71): poly-line vertices (float3),
+ * per-vertex data (may be NULL = 0) and the connectivity of src/data/PathLines.cpp:110-122: connectivity[i] = index
+ * of the first vertex of segment i, its second vertex is the next one.  The arrays are copied (host side): the
+ * curves are only built when a PathLinesVis maps data to radii (gxy_vis_commit). */
+int  gxy_pathlines_create(gxy_context *, int n_verts, const float *verts, const float *data, int n_segments,
+                          const int *connectivity, gxy_pathlines **out);
+void gxy_pathlines_destroy(gxy_pathlines *);
+/* DataDrivenPathLines::finalize (src/ospray/DataDrivenPathLines.cpp:28-37,103-156) on the host, as in the
+ * reference: one round cubic Bezier segment per poly-line segment, cp_out = n_segments x 4 control points
+ * (x,y,z,radius) as Embree gathers them (4 consecutive vertices from indexCurve[i]).  Needs no device. */
+int  gxy_build_curves(int n_verts, const float *verts, const float *data, int n_segments, const int *connectivity,
+                      float radius0, float radius1, float value0, float value1, float *cp_out);
+
 /* ---- Visualization ------------------------------------------------------------------------ */
 int  gxy_vis_create(gxy_context *, gxy_vis **out);
 void gxy_vis_destroy(gxy_vis *);
@@ -139,6 +153,12 @@ int  gxy_vis_add_volume(gxy_vis *, gxy_volume *, int n_slices, const float *slic
 int  gxy_vis_add_triangles(gxy_vis *, gxy_triangles *, const gxy_transfer_function *);
 /* ParticlesVis operator; radius0/1 value0/1 per ParticlesVis.cpp:136-144 */
 int  gxy_vis_add_particles(gxy_vis *, gxy_particles *, float radius0, float radius1, float value0,
+                           float value1, const gxy_transfer_function *);
+/* PathLinesVis operator; radius0/1 value0/1 per PathLinesVis.cpp:105-125,133-144 (the data value of a vertex is
+ * mapped to the tube radius there; the hit colour is the transfer function of the radius mapped back).  The
+ * segments are traced as Embree's round Bezier curves (RTC_GEOMETRY_TYPE_ROUND_BEZIER_CURVE,
+ * DataDrivenPathLines.ispc:319-324). */
+int  gxy_vis_add_pathlines(gxy_vis *, gxy_pathlines *, float radius0, float radius1, float value0,
                            float value1, const gxy_transfer_function *);
 /* Visualization::SetOsprayObjects -> ospCommit(model) (Visualization.cpp:207-285): builds the
  * BVH over all geometry operators on the device. */

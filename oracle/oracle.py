@@ -54,6 +54,9 @@ def lib():
         L.gxo_scene_add_triangles_vis.argtypes = [vp, C.c_int, fp, fp, fp, C.c_int, ip, fp, fp, C.c_float, C.c_float]
         L.gxo_scene_add_particles_vis.argtypes = [vp, C.c_int, fp, fp, C.c_float, C.c_float, C.c_float, C.c_float, fp, fp,
                                                   C.c_float, C.c_float]
+        L.gxo_scene_add_pathlines_vis.argtypes = [vp, C.c_int, fp, fp, C.c_int, ip, C.c_float, C.c_float, C.c_float, C.c_float, fp, fp,
+                                                  C.c_float, C.c_float]
+        L.gxo_build_curves.argtypes = [C.c_int, fp, fp, C.c_int, ip, C.c_float, C.c_float, C.c_float, C.c_float, fp]
         L.gxo_scene_commit.argtypes = [vp]
         L.gxo_resample_tf.argtypes = [C.c_int, fp, C.c_int, fp, fp, fp]
         L.gxo_resolve_lights.argtypes = [C.POINTER(Lighting), C.POINTER(Camera), C.POINTER(Lighting)]
@@ -153,6 +156,16 @@ class Scene:
         self._keep += [centers, data]
         return lib().gxo_scene_add_particles_vis(self.h, len(centers), _f(centers), _f(data), radius0, radius1, value0, value1,
                                                  _f(col), _f(op), lo, hi)
+
+    def add_pathlines_vis(self, verts, data, connectivity, radius0, radius1, value0, value1, colors, opacities, lo, hi):
+        verts, data = _f32(verts), _f32(data)
+        conn = np.ascontiguousarray(connectivity, dtype=np.int32)
+        col, op = _f32(colors), _f32(opacities)
+        rc = lib().gxo_scene_add_pathlines_vis(self.h, len(verts), _f(verts), _f(data), len(conn), _i(conn), radius0, radius1, value0,
+                                               value1, _f(col), _f(op), lo, hi)
+        if rc < 0:
+            raise ValueError("pathlines: bad connectivity")
+        return rc
 
     def commit(self):
         return lib().gxo_scene_commit(self.h)

@@ -15,7 +15,7 @@ FMAX = np.float32(3.4028234e38)
 
 
 def _p(a):
-    return a.ctypes.data_as(C.c_void_p)
+    return a.ctypes.data_as(C.POINTER(C.c_int if a.dtype == np.int32 else C.c_float))
 
 
 @pytest.fixture(scope="module")
