@@ -154,7 +154,7 @@ static bool load_typed(const json::Value &v, const std::string &state_dir, Datas
     out.volumes.push_back(vol);
     return true;
   }
-  if (type == "Particles" || type == "Triangles") {
+  if (type == "Particles" || type == "Triangles" || type == "PathLines") {
     Geometry g;
     g.type = type;
     std::string fn = v["filename"].GetString();
@@ -164,10 +164,6 @@ static bool load_typed(const json::Value &v, const std::string &state_dir, Datas
     g.name = name;
     out.geometries.push_back(g);
     return true;
-  }
-  if (type == "PathLines") {
-    std::cerr << "Dataset type PathLines is not supported by this driver (no curve primitive behind the C ABI yet)\n";
-    return false;
   }
   std::cerr << "invalid Dataset type: " << type << "\n";
   return false;
@@ -284,6 +280,32 @@ bool Geometry::LoadPiece(int rank, GeometryPiece &out) const {
       return false;
     }
     out.connectivity = d.connectivity;
+  }
+  if (type == "PathLines") {
+    // PathLines::load_from_vtkPointSet (PathLines.cpp:73-125): the points of every cell are copied in cell order (a point
+    // shared by two lines is duplicated), data follows them, connectivity[j] = index of the first vertex of each segment
+    out.vertices.clear();
+    out.data.clear();
+    long long prev = 0;
+    for (long long o : d.offsets) {
+      if (o < prev || (size_t)o > d.connectivity.size()) {
+        std::cerr << part_files[(size_t)rank] << ": bad cell offsets\n";
+        return false;
+      }
+      for (long long l = prev; l < o; l++) {
+        const int id = d.connectivity[(size_t)l];
+        if (id < 0 || (size_t)id >= nv) {
+          std::cerr << part_files[(size_t)rank] << ": point id " << id << " out of range\n";
+          return false;
+        }
+        const int k = (int)(out.vertices.size() / 3);
+        for (int a = 0; a < 3; a++) out.vertices.push_back(d.points[3 * (size_t)id + a]);
+        out.data.push_back(d.scalars.empty() ? 0.0f : d.scalars[(size_t)id]);
+        if (l < o - 1) out.connectivity.push_back(k);
+      }
+      prev = o;
+    }
+    return true;
   }
   out.data = d.scalars;
   if (out.data.empty()) out.data.assign(nv, 0.0f);  // Triangles.cpp:127-132 / Particles.cpp:124
@@ -507,6 +529,12 @@ bool Vis::LoadFromJSON(const json::Value &v, const std::string &base_dir) {
         for (int k = 0; k < 4; k++) slices.push_back((float)v["plane"][k].GetDouble());
       }
       volume_render = v.HasMember("volume rendering") ? v["volume rendering"].GetBool() : false;
+    } else if (type == "PathLinesVis") {  // PathLinesVis.cpp:46-55 (initialize), 105-114 (LoadFromJSON)
+      radius0 = -1.0f; radius1 = 1.0f; value0 = 0.0f; value1 = 1.0f;
+      if (v.HasMember("radius0")) radius0 = (float)v["radius0"].GetDouble();
+      if (v.HasMember("radius1")) radius1 = (float)v["radius1"].GetDouble();
+      if (v.HasMember("value0")) value0 = (float)v["value0"].GetDouble();
+      if (v.HasMember("value1")) value1 = (float)v["value1"].GetDouble();
     } else if (type == "ParticlesVis") {  // ParticlesVis.cpp:104-118
       if (v.HasMember("radius0")) radius0 = (float)v["radius0"].GetDouble();
       if (v.HasMember("radius1")) radius1 = (float)v["radius1"].GetDouble();
@@ -533,6 +561,8 @@ void Visualization::Release() {
   owned_triangles.clear();
   for (gxy_particles *p : owned_particles) gxy_particles_destroy(p);
   owned_particles.clear();
+  for (gxy_pathlines *p : owned_pathlines) gxy_pathlines_destroy(p);
+  owned_pathlines.clear();
 }
 
 bool Visualization::LoadFromJSON(const json::Value &v, const std::string &base_dir) {
@@ -588,13 +618,13 @@ bool Visualization::Commit(gxy_context *ctx, const Datasets &datasets, int npart
     bool boxes_set = false;
     std::vector<std::pair<std::string, gxy_volume *>> vols;  // one device volume per dataset and partition
     for (const Vis &op : operators) {
-      if (op.type == "TrianglesVis" || op.type == "ParticlesVis") {
+      if (op.type == "TrianglesVis" || op.type == "ParticlesVis" || op.type == "PathLinesVis") {
         const Geometry *geo = datasets.FindGeometry(op.dataset);
         if (!geo) {
           std::cerr << "Unable to find data using name: " << op.dataset << "\n";
           return false;
         }
-        if ((geo->type == "Triangles") != (op.type == "TrianglesVis")) {
+        if (geo->type + "Vis" != op.type) {
           std::cerr << op.type << " on a " << geo->type << " dataset (" << op.dataset << ")\n";
           return false;
         }
@@ -628,6 +658,14 @@ bool Visualization::Commit(gxy_context *ctx, const Datasets &datasets, int npart
             return false;
           owned_triangles.push_back(gt);
           if (!check_abi(gxy_vis_add_triangles(vis, gt, &gtf), "gxy_vis_add_triangles")) return false;
+        } else if (op.type == "PathLinesVis") {
+          gxy_pathlines *gl = nullptr;
+          if (!check_abi(gxy_pathlines_create(ctx, nv, piece.vertices.data(), piece.data.data(), (int)piece.connectivity.size(),
+                                              piece.connectivity.data(), &gl),
+                         "gxy_pathlines_create"))
+            return false;
+          owned_pathlines.push_back(gl);
+          if (!check_abi(gxy_vis_add_pathlines(vis, gl, op.radius0, op.radius1, op.value0, op.value1, &gtf), "gxy_vis_add_pathlines")) return false;
         } else {
           gxy_particles *gp = nullptr;
           if (!check_abi(gxy_particles_create(ctx, nv, piece.vertices.data(), piece.data.data(), &gp), "gxy_particles_create")) return false;

@@ -15,9 +15,9 @@
 //   Renderer (src/renderer/Renderer.cpp:125,289-296)         gxy::Renderer       (epsilon)
 //   ColorImageWriter / write_png (ImageWriter.cpp:30-67)     gxy::write_png      (zlib; libpng is not needed)
 //
-//   Geometry / Triangles / Particles (src/data/Geometry.cpp:176-344,  gxy::Geometry  (partition document + .vtu/.vtp pieces through
-//     Triangles.cpp:79-146, Particles.cpp:90-129)                          the VTK-free reader of gxy_vtu.h)
-// PathLines datasets are not supported (their Bezier-curve primitive is not part of the C ABI yet): LoadFromJSON says so.
+//   Geometry / Triangles / Particles / PathLines (src/data/Geometry.cpp:176-344,  gxy::Geometry  (partition document + .vtu/.vtp pieces
+//     Triangles.cpp:79-146, Particles.cpp:90-129, PathLines.cpp:73-125)               through the VTK-free reader of gxy_vtu.h)
+//   PathLinesVis (src/renderer/PathLinesVis.cpp:46-55,105-114)                    gxy::Vis with type "PathLinesVis"
 #pragma once
 #include <string>
 #include <vector>
@@ -53,7 +53,7 @@ class Volume {
 // One partition of a geometry dataset as the reference holds it after load_from_vtkPointSet
 struct GeometryPiece {
   std::vector<float> vertices, normals, data;  // 3, 3, 1 per vertex
-  std::vector<int> connectivity;               // Triangles: 3 per triangle
+  std::vector<int> connectivity;               // Triangles: 3 per triangle; PathLines: first vertex of every segment
 };
 
 // Geometry::local_import / get_partitioning (src/data/Geometry.cpp:176-344): the dataset file is a partition document
@@ -62,9 +62,9 @@ class Geometry {
  public:
   bool Import(const std::string &filename);
   int NumberOfParts() const { return (int)part_files.size(); }
-  bool LoadPiece(int rank, GeometryPiece &out) const;  // Triangles / Particles ::load_from_vtkPointSet
+  bool LoadPiece(int rank, GeometryPiece &out) const;  // Triangles / Particles / PathLines ::load_from_vtkPointSet
   void Boxes(int rank, float gmin[3], float gmax[3], float lmin[3], float lmax[3], int neighbors[6]) const;
-  std::string name, type, filename;                    // type: "Triangles" | "Particles"
+  std::string name, type, filename;                    // type: "Triangles" | "Particles" | "PathLines"
   std::vector<std::string> part_files;
   std::vector<float> extents;                          // 6 per part, stored as float like the reference
 };
@@ -105,7 +105,8 @@ struct Vis {
   float range[2] = {0, 1};
   std::vector<float> isovalues, slices;  // slices: k x (a,b,c,d)
   bool volume_render = false;
-  float radius0 = 0.025f, radius1 = 0.f, value0 = 0.f, value1 = 0.f;  // ParticlesVis (ParticlesVis.cpp:46-55,104-118)
+  // ParticlesVis defaults (ParticlesVis.cpp:46-55,104-118); a PathLinesVis starts from -1, 1, 0, 1 (PathLinesVis.cpp:46-55)
+  float radius0 = 0.025f, radius1 = 0.f, value0 = 0.f, value1 = 0.f;
   // base_dir: where a "colormap" / "transfer function" given as a file name (ParaView JSON, MappedVis.cpp:104-166) is looked up
   bool LoadFromJSON(const json::Value &v, const std::string &base_dir = "");
 };
@@ -125,6 +126,7 @@ class Visualization {
   std::vector<gxy_volume *> owned_volumes;
   std::vector<gxy_triangles *> owned_triangles;
   std::vector<gxy_particles *> owned_particles;
+  std::vector<gxy_pathlines *> owned_pathlines;
 };
 
 class Renderer {

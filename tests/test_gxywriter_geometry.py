@@ -106,11 +106,15 @@ def test_geometry_defaults_and_errors(tmp_path):
     os.remove(os.path.join(tmp, "m-0.vtu"))
     r = subprocess.run([EXE, "--describe", os.path.join(tmp, "a.state")], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "error reading" in r.stderr and json.loads(r.stdout)["geometries"][0]["parts"][0]["loaded"] is False
-    # PathLines are refused
-    st["Datasets"] = [{"name": "p", "type": "PathLines", "filename": "p.part"}]
+    # an unknown dataset type is refused with the reference's message (Datasets.cpp:96-155); a missing partition document too
+    st["Datasets"] = [{"name": "p", "type": "Hexahedra", "filename": "p.part"}]
     json.dump(st, open(os.path.join(tmp, "b.state"), "w"))
     r = subprocess.run([EXE, "--describe", os.path.join(tmp, "b.state")], capture_output=True, text=True, timeout=60)
-    assert r.returncode == 1 and "PathLines" in r.stderr
+    assert r.returncode == 1 and "invalid Dataset type" in r.stderr
+    st["Datasets"] = [{"name": "p", "type": "PathLines", "filename": "missing.part"}]
+    json.dump(st, open(os.path.join(tmp, "b.state"), "w"))
+    r = subprocess.run([EXE, "--describe", os.path.join(tmp, "b.state")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1
 
 
 @pytest.mark.gpu
@@ -134,3 +138,46 @@ def test_gxywriter_geometry_matches_python_binding(tmp_path, nparts):
     frac = util.image_fraction(img, ref, tol=0)
     print("partitions", nparts, "identical pixels:", frac)
     assert frac >= 0.9999
+
+
+# ---- PathLines datasets ---------------------------------------------------------------------------------
+def stage_pathlines(tmp, nparts, mode="appended-raw", compressed=False):
+    from tests.test_curve_host import pathlines_scene
+    ds = pathlines_scene(21, 10)
+    ext, _ = scenes.geometry_extents(nparts)
+    pieces = []
+    for r in range(nparts):
+        p = ds if nparts == 1 else scenes.clip_pathlines(ds, ext[r])
+        write_vtu(os.path.join(tmp, "lines-%d.vtu" % r), p.points, scalars=p.data, mode=mode, compressed=compressed, polylines=[list(l) for l in p.lines])
+        pieces.append(p)
+    json.dump({"parts": [{"filename": "lines-%d.vtu" % r, "extent": [float(x) for x in ext[r]]} for r in range(nparts)]},
+              open(os.path.join(tmp, "lines.part"), "w"))
+    state = {
+        "Datasets": [{"name": "pathlines", "type": "PathLines", "filename": "lines.part"}],
+        "Renderer": {"epsilon": 0.001},
+        "Visualizations": [{"Lighting": {"Sources": [[1, 2, -3, 0]], "shadows": True, "Ka": 0.4, "Kd": 0.6, "ao count": 0},
+                            "operators": [{"type": "PathLinesVis", "dataset": "pathlines", "colormap": [[0.0, 0.0, 1.0, 0.0], [1.2, 1.0, 0.0, 1.0]],
+                                           "radius0": 0.01, "radius1": 0.05, "value0": 0.0, "value1": 1.2}]}],
+        "Cameras": [{"viewpoint": [1.5, 1.0, -3.0], "viewcenter": [0, 0, 0], "viewup": [0, 1, 0], "aov": 35}],
+    }
+    path = os.path.join(tmp, "pathlines.state")
+    json.dump(state, open(path, "w"))
+    return path, state, pieces
+
+
+@pytest.mark.parametrize("nparts,mode,compressed", [(1, "ascii", False), (2, "appended-raw", True), (8, "binary", False)])
+def test_pathlines_pieces_load_as_the_reference_loads_them(tmp_path, nparts, mode, compressed):
+    """PathLines::load_from_vtkPointSet through the C++ host: vertices duplicated per poly-line in cell order, data beside
+    them, connectivity = first vertex of every segment -- bit-identical to the Python front end's arrays."""
+    path, state, pieces = stage_pathlines(str(tmp_path), nparts, mode, compressed)
+    out = subprocess.run([EXE, "--describe", "-P", str(nparts), path], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    d = json.loads(out.stdout)
+    g = d["geometries"][0]
+    assert g["type"] == "PathLines" and len(g["parts"]) == nparts
+    for r in range(nparts):
+        v, dat, c = pieces[r].to_arrays()
+        pr = g["parts"][r]
+        assert pr["loaded"] and pr["n_vertices"] == len(v) and pr["n_connectivity"] == len(c)
+        assert pr["hash_vertices"] == fnv(v.astype(np.float32)) and pr["hash_data"] == fnv(dat.astype(np.float32))
+        assert pr["hash_connectivity"] == fnv(c.astype(np.int32))

@@ -24,11 +24,16 @@ def _block(raw, compressed, header64, block_size=32768):
 
 
 def write_vtu(path, points, triangles=None, normals=None, scalars=None, scalars_name="data", mode="ascii", compressed=False, header64=False,
-              normals_name="Normals", declare_scalars=True):
-    """mode: ascii | binary (inline base64) | appended-raw | appended-base64.  triangles None -> one VTK_VERTEX cell per point."""
+              normals_name="Normals", declare_scalars=True, polylines=None):
+    """mode: ascii | binary (inline base64) | appended-raw | appended-base64.  triangles None -> one VTK_VERTEX cell per point;
+    polylines: list of point-id lists -> VTK_POLY_LINE cells (what vtkStreamTracer output holds, tests/create_data_driven_datasets.vpy)."""
     points = np.ascontiguousarray(points, np.float32)
     n = len(points)
-    if triangles is None:
+    if polylines is not None:
+        conn = np.asarray([i for l in polylines for i in l], dtype=np.int64)
+        offs = np.cumsum([len(l) for l in polylines], dtype=np.int64)
+        types = np.full(len(polylines), 4, np.uint8)
+    elif triangles is None:
         conn = np.arange(n, dtype=np.int64)
         offs = np.arange(1, n + 1, dtype=np.int64)
         types = np.full(n, 1, np.uint8)
