@@ -535,6 +535,10 @@ static void build_curves(int nseg, const int *indices, const float *verts, const
 struct gxo_scene {
   V3 gmin, gmax, lmin, lmax;
   std::vector<std::unique_ptr<std::vector<float>>> curve_store;
+  // Sampler (src/sampler): sampler operators of a sampling Visualization and the samples this partition collected
+  struct SamplerOp { int kind; float param; VolumeData *vol; };   // kind 0 GradientSampler (tolerance), 1 IsoSampler (isovalue)
+  std::vector<SamplerOp> svis;
+  std::vector<float> samples;   // xyz per sample (Sampler::HandleTerminatedRays, Sampler.cpp:52-92)
   int neighbors[6];
   std::vector<VolumeVisOp> vvis;
   std::map<int, std::unique_ptr<VolumeData>> volumes;
@@ -984,6 +988,73 @@ static void trace_kernel(gxo_scene &S, RL &R, float global_epsilon, int nthreads
     total += ns;
   });
   S.sample_count += total.load();
+}
+
+// ---------------------------------------------------------------------------------------------
+// SamplerTraceRays_SamplerTraceRays (src/sampler/SamplerTraceRays.ispc:128-222) with the two sampler operators
+// GradientSamplerVis (GradientSamplerVis.ispc:36-72) and IsoSamplerVis (IsoSamplerVis.ispc:36-67).  The reference keeps
+// sLast/tLast/tHit as varying members of the (shared) operator struct; they are per-ray state here.  rcp(dir) := 1/dir.
+static void sampler_trace(const gxo_scene &S, RL &R, int nthreads) {
+  const int nv = (int)S.svis.size();
+  if (nv < 1) return;   // :136: nothing is touched without a sampler operator
+  float step = S.svis[0].vol->samplingStep * S.svis[0].vol->samplingRate;
+  for (int m = 1; m < nv; m++) {
+    const float s = S.svis[m].vol->samplingStep * S.svis[m].vol->samplingRate;
+    if (s < step) step = s;
+  }
+  parallel_for(R.n, nthreads, [&](int a, int b) {
+    std::vector<V3> gLast(nv); std::vector<float> sLast(nv), tLastV(nv);
+    for (int i = a; i < b; i++) {
+      const V3 org = mk(R.ox[i], R.oy[i], R.oz[i]);
+      V3 dir = mk(R.dx[i], R.dy[i], R.dz[i]);
+      const float ray_t = R.t[i];
+      if (dir.x == 0.f) dir.x = 1e-6f;
+      if (dir.y == 0.f) dir.y = 1e-6f;
+      if (dir.z == 0.f) dir.z = 1e-6f;
+      // EntryT / ExitT (:62-86)
+      const V3 rd = mk(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+      const V3 mins = mk((S.lmin.x - org.x) * rd.x, (S.lmin.y - org.y) * rd.y, (S.lmin.z - org.z) * rd.z);
+      const V3 maxs = mk((S.lmax.x - org.x) * rd.x, (S.lmax.y - org.y) * rd.y, (S.lmax.z - org.z) * rd.z);
+      float tEntry = std::max(std::min(mins.x, maxs.x), std::max(std::min(mins.y, maxs.y), std::min(mins.z, maxs.z)));
+      const float tExit = std::min(std::max(mins.x, maxs.x), std::min(std::max(mins.y, maxs.y), std::max(mins.z, maxs.z)));
+      if (tEntry < ray_t) tEntry = ray_t;
+      float tThis = tEntry + step;
+      int hit = -1;
+      for (int m = 0; m < nv; m++) {   // init (:186-190)
+        const V3 coord = org + tEntry * dir;
+        if (S.svis[m].kind == 0) gLast[m] = vol_gradient(*S.svis[m].vol, coord);
+        else sLast[m] = vol_sample(*S.svis[m].vol, coord);
+        tLastV[m] = tEntry;
+      }
+      while (tThis <= tExit && hit == -1) {
+        hit = -1;
+        for (int m = 0; m < nv && hit == -1; m++) {   // check_interval
+          const V3 coord = org + tThis * dir;
+          bool h = false; float tHit = 0.f;
+          if (S.svis[m].kind == 0) {
+            const V3 gThis = vol_gradient(*S.svis[m].vol, coord);
+            const float dotValue = dot(gThis, gLast[m]);
+            if (dotValue < S.svis[m].param) { tHit = (tLastV[m] + tThis) / 2.0f; h = true; }
+            gLast[m] = gThis;
+          } else {
+            const float iso = S.svis[m].param, sThis = vol_sample(*S.svis[m].vol, coord);
+            if (((sLast[m] < iso) && (sThis >= iso)) || ((sLast[m] > iso) && sThis <= iso)) {
+              tHit = tLastV[m] + (((iso - sLast[m]) / (sThis - sLast[m])) * (tThis - tLastV[m]));
+              h = true;
+            }
+            sLast[m] = sThis;
+          }
+          tLastV[m] = tThis;
+          if (h) { tThis = tHit; hit = m; }
+        }
+        if (hit != -1 || tThis == tExit) break;
+        tThis = tThis + step;
+        if (tThis > tExit) tThis = tExit;
+      }
+      R.t[i] = (hit != -1) ? tThis + 0.001f : tThis;   // ISPC literals without a suffix are float
+      R.term[i] = (hit != -1) ? RAY_SURFACE : RAY_BOUNDARY;
+    }
+  });
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -142,7 +142,7 @@ def test_pathlines_state_renders_like_the_python_binding(gpu, tmp_path):
         tmp = str(tmp_path / ("p%d" % nparts))
         os.makedirs(tmp)
         path, state, pieces = stage_pathlines(tmp, nparts)
-        out = subprocess.run([EXE, "-s", "256", "192", "-P", str(nparts), path, os.path.join(tmp, "img")], capture_output=True, text=True, timeout=120)
+        out = subprocess.run([EXE, "-s", "256", "192", "-P", str(nparts), "-o", os.path.join(tmp, "img"), path], capture_output=True, text=True, timeout=120)
         assert out.returncode == 0, out.stderr
         png = np.asarray(Image.open(os.path.join(tmp, "img_00000.png")).convert("RGBA"))
         st = scenes.parse_state(state)
@@ -155,5 +155,5 @@ def test_pathlines_state_renders_like_the_python_binding(gpu, tmp_path):
     path, state, _ = stage_pathlines(str(tmp_path), 1)
     state["Visualizations"][0]["operators"][0]["type"] = "Particles"
     json.dump(state, open(path, "w"))
-    out = subprocess.run([EXE, "-s", "32", "32", path, str(tmp_path / "x")], capture_output=True, text=True, timeout=60)
+    out = subprocess.run([EXE, "-s", "32", "32", "-o", str(tmp_path / "x"), path], capture_output=True, text=True, timeout=60)
     assert out.returncode != 0 and "on a PathLines dataset" in out.stderr
