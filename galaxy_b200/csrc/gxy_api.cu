@@ -252,12 +252,23 @@ struct GeomOp {
   gxy_transfer_function tf;
 };
 
+struct SamplerOp {
+  gxy_volume *vol;
+  int kind;
+  float param;
+};
+
 struct gxy_vis {
   gxy_context *ctx;
   float gmin[3], gmax[3], lmin[3], lmax[3];
   int neighbors[6];
   std::vector<VolOp> vols;
   std::vector<GeomOp> geoms;
+  std::vector<SamplerOp> samplers;  // a sampling Visualization (src/sampler) holds only these
+  SamplerParams SP;
+  float *d_samples = nullptr;       // xyz of the samples collected by gxy_sample
+  unsigned long long samples_cap = 0, n_samples = 0;
+  unsigned long long *d_sample_count = nullptr;
   bool committed = false;
   SceneParams P;
   DevTF *d_tfs = nullptr;
@@ -515,6 +526,8 @@ void gxy_vis_destroy(gxy_vis *v) {
   vis_free_commit(v);
   v->cur.release(); v->next.release(); v->send.release(); v->recv.release(); v->hits.release(); v->fq.release(); v->rawhits.release();
   v->hit_index.release(); v->block_sums.release(); v->small.release(); v->counters.release();
+  if (v->d_samples) cudaFree(v->d_samples);
+  if (v->d_sample_count) cudaFree(v->d_sample_count);
   v->fb.release(); v->fb_tmp.release(); v->rgba8.release(); v->io_f.release(); v->io_i.release();
   if (v->ctx->copy_stream) cudaStreamSynchronize(v->ctx->copy_stream);
   for (int s = 0; s < 2; s++) {
@@ -577,6 +590,18 @@ int gxy_vis_add_particles(gxy_vis *v, gxy_particles *p, float radius0, float rad
   return 0;
 }
 
+int gxy_vis_add_sampler(gxy_vis *v, gxy_volume *vol, int kind, float param) {
+  GXY_CHECK(v && vol, "gxy_vis_add_sampler: NULL argument");
+  GXY_CHECK(kind == GXY_SAMPLER_GRADIENT || kind == GXY_SAMPLER_ISO, "unknown sampler kind %d", kind);
+  GXY_CHECK((int)v->samplers.size() < GXY_MAX_VOLUME_VIS, "more than %d sampler operators in one Visualization", GXY_MAX_VOLUME_VIS);
+  GXY_CHECK(vol->ctx == v->ctx, "volume belongs to another context");
+  SamplerOp op;
+  op.vol = vol; op.kind = kind; op.param = param;
+  v->samplers.push_back(op);
+  v->committed = false;
+  return 0;
+}
+
 int gxy_vis_add_pathlines(gxy_vis *v, gxy_pathlines *p, float radius0, float radius1, float value0, float value1,
                           const gxy_transfer_function *tf) {
   GXY_CHECK(p && tf, "gxy_vis_add_pathlines: NULL argument");
@@ -597,7 +622,18 @@ static void pack_tf(const gxy_transfer_function &in, DevTF &out) {
 
 int gxy_vis_commit(gxy_vis *v) {
   if (use_device(v->ctx)) return 1;
+  GXY_CHECK(v->samplers.empty() || (v->vols.empty() && v->geoms.empty()),
+            "a sampling Visualization holds only sampler operators (SamplerTraceRays calls every operator as a SamplerVis)");
   vis_free_commit(v);
+  // SamplerTraceRays.ispc:136-150: step = min samplingStep*samplingRate over the operators
+  memset(&v->SP, 0, sizeof v->SP);
+  v->SP.n_ops = (int)v->samplers.size();
+  v->SP.lmin = make_float3(v->lmin[0], v->lmin[1], v->lmin[2]); v->SP.lmax = make_float3(v->lmax[0], v->lmax[1], v->lmax[2]);
+  for (size_t m = 0; m < v->samplers.size(); m++) {
+    v->SP.op[m].kind = v->samplers[m].kind; v->SP.op[m].param = v->samplers[m].param; v->SP.op[m].vol = v->samplers[m].vol->dv;
+    const float s = v->samplers[m].vol->dv.samplingStep * v->samplers[m].vol->dv.samplingRate;
+    if (m == 0 || s < v->SP.step) v->SP.step = s;
+  }
   SceneParams &P = v->P;
   memset(&P, 0, sizeof P);
   P.gmin = make_float3(v->gmin[0], v->gmin[1], v->gmin[2]); P.gmax = make_float3(v->gmax[0], v->gmax[1], v->gmax[2]);
@@ -931,6 +967,166 @@ int gxy_classify(gxy_vis *v, gxy_raylist_view rays) {
   if (launch_classify(v->P, v->cur.v, rays.n, v->ctx->stream)) return 1;
   if (d2h_rays(v, v->cur, rays.base, rays.n, rays.aligned_n, 24, 1)) return 1;
   GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  return 0;
+}
+
+int gxy_sample_raylist(gxy_vis *v, gxy_raylist_view rays) {
+  if (check_vis(v)) return 1;
+  if (rays.n == 0) return 0;
+  if (h2d_rays(v, v->cur, rays)) return 1;
+  if (launch_sampler_trace(v->SP, v->cur.v, rays.n, nullptr, nullptr, 0, v->ctx->stream)) return 1;
+  if (d2h_rays(v, v->cur, rays.base, rays.n, rays.aligned_n)) return 1;
+  GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  return 0;
+}
+
+// room for `need` samples, keeping the ones already collected
+static int reserve_samples(gxy_vis *v, unsigned long long need, cudaStream_t st) {
+  if (need <= v->samples_cap) return 0;
+  unsigned long long ncap = std::max(need, v->samples_cap + v->samples_cap / 2);
+  ncap = (ncap + 1023ull) & ~1023ull;
+  float *nb = nullptr;
+  GXY_CUDA(cudaMalloc(&nb, sizeof(float) * 3 * ncap));
+  if (v->d_samples && v->n_samples) {
+    GXY_CUDA(cudaMemcpyAsync(nb, v->d_samples, sizeof(float) * 3 * v->n_samples, cudaMemcpyDeviceToDevice, st));
+    GXY_CUDA(cudaStreamSynchronize(st));
+  }
+  if (v->d_samples) cudaFree(v->d_samples);
+  v->d_samples = nb;
+  v->samples_cap = ncap;
+  return 0;
+}
+
+// Sampler over a frame (Sampler.cpp:52-133 on top of Renderer::local_render / processRays): per wave and partition
+//   sample-trace (+ sample points) -> Classify -> counting sort by destination, KEEP_HERE rays (the ones that left a sample)
+//   back into the partition's own next list, BOUNDARY rays to the neighbour; until no partition has rays left.
+int gxy_sample(int nparts, gxy_vis *const *parts, const gxy_camera *cam, int w, int h, gxy_stats *stats) {
+  GXY_CHECK(nparts >= 1 && parts && cam && w > 0 && h > 0, "gxy_sample: bad arguments");
+  for (int p = 0; p < nparts; p++) {
+    if (check_vis(parts[p])) return 1;
+    GXY_CHECK(!parts[p]->samplers.empty(), "gxy_sample: partition %d holds no sampler operator", p);
+    GXY_CHECK(parts[p]->ctx->comm == nullptr, "gxy_sample drives all partitions from one process (no communicator)");
+  }
+  const DevCamera C = make_dev_camera(*cam, w, h);
+  const int npix = w * h;
+  gxy_stats S;
+  memset(&S, 0, sizeof S);
+  gxy_context *ctx0 = parts[0]->ctx;
+  cudaEvent_t ev0, ev1;
+  if (use_device(ctx0)) return 1;
+  GXY_CUDA(cudaEventCreate(&ev0));
+  GXY_CUDA(cudaEventCreate(&ev1));
+  GXY_CUDA(cudaEventRecord(ev0, ctx0->stream));
+  std::vector<int> n_cur(nparts, 0);
+  for (int p = 0; p < nparts; p++) {
+    gxy_vis *v = parts[p];
+    if (use_device(v->ctx)) return 1;
+    cudaStream_t st = v->ctx->stream;
+    const int npix_pad = ((w + 15) / 16) * ((h + 7) / 8) * 128;
+    if (v->block_sums.reserve((size_t)std::max(npix_pad, 1 << 20) / 1024 + 2) || v->small.reserve(64 + 4 * (size_t)nparts)) return 1;
+    if (!v->d_sample_count) GXY_CUDA(cudaMalloc(&v->d_sample_count, sizeof(unsigned long long)));
+    GXY_CUDA(cudaMemsetAsync(v->d_sample_count, 0, sizeof(unsigned long long), st));
+    v->n_samples = 0;
+    if (v->cur.reserve(npix, false, st)) return 1;
+    if (launch_generate(v->P, C, w, h, tiled_order(), v->cur.v, nullptr, v->block_sums.p, v->small.p, st)) return 1;
+    S.kernel_launches += 3;
+    GXY_CUDA(cudaMemcpyAsync(&n_cur[p], v->small.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GXY_CUDA(cudaStreamSynchronize(st));
+    S.primary_rays += n_cur[p];
+  }
+  std::vector<std::vector<int>> send_counts(nparts, std::vector<int>(nparts, 0)), send_offsets(nparts, std::vector<int>(nparts + 1, 0));
+  for (int wave = 0; wave < 1000000; wave++) {
+    long long pending = 0;
+    for (int p = 0; p < nparts; p++) pending += n_cur[p];
+    if (pending == 0) break;
+    for (int p = 0; p < nparts; p++) {
+      gxy_vis *v = parts[p];
+      std::fill(send_counts[p].begin(), send_counts[p].end(), 0);
+      const int n = n_cur[p];
+      if (n == 0) continue;
+      if (use_device(v->ctx)) return 1;
+      cudaStream_t st = v->ctx->stream;
+      if (reserve_samples(v, v->n_samples + (unsigned long long)n, st)) return 1;  // at most one sample per ray and pass
+      if (launch_sampler_trace(v->SP, v->cur.v, n, v->d_samples, v->d_sample_count, v->samples_cap, st)) return 1;
+      if (launch_classify(v->P, v->cur.v, n, st)) return 1;
+      if (v->send.reserve((size_t)n, false, st)) return 1;
+      int *d_counts = v->small.p + 8, *d_offsets = d_counts + nparts, *d_cursor = d_offsets + nparts + 1;
+      if (launch_partition_by_destination(v->cur.v, n, nparts, p, v->send.v, d_counts, d_offsets, d_cursor, st)) return 1;
+      GXY_CUDA(cudaMemcpyAsync(send_counts[p].data(), d_counts, sizeof(int) * nparts, cudaMemcpyDeviceToHost, st));
+      GXY_CUDA(cudaMemcpyAsync(send_offsets[p].data(), d_offsets, sizeof(int) * (nparts + 1), cudaMemcpyDeviceToHost, st));
+      GXY_CUDA(cudaMemcpyAsync(&v->n_samples, v->d_sample_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      S.kernel_launches += 5;
+      S.traced_rays += n;
+      S.waves++;
+    }
+    for (int p = 0; p < nparts; p++) {
+      if (n_cur[p] == 0) continue;
+      if (use_device(parts[p]->ctx)) return 1;
+      GXY_CUDA(cudaStreamSynchronize(parts[p]->ctx->stream));
+    }
+    std::vector<int> n_next(nparts, 0);
+    for (int src = 0; src < nparts; src++)
+      for (int dst = 0; dst < nparts; dst++) {
+        const int cnt = send_counts[src][dst];
+        if (!cnt) continue;
+        gxy_vis *vs = parts[src], *vd = parts[dst];
+        if (src != dst) S.forwarded_rays += cnt;
+        if (use_device(vd->ctx)) return 1;
+        cudaStream_t st = vd->ctx->stream;
+        GXY_CHECK(vs->ctx->device == vd->ctx->device, "gxy_sample: all partitions of one call live on one device");
+        if (vd->next.reserve((size_t)n_next[dst] + cnt, true, st)) return 1;
+        if (launch_copy_rays(vd->next.v, (size_t)n_next[dst], vs->send.v, (size_t)send_offsets[src][dst], cnt, st)) return 1;
+        S.kernel_launches += 1;
+        n_next[dst] += cnt;
+      }
+    for (int p = 0; p < nparts; p++) {
+      if (use_device(parts[p]->ctx)) return 1;
+      GXY_CUDA(cudaStreamSynchronize(parts[p]->ctx->stream));
+      std::swap(parts[p]->cur, parts[p]->next);
+      n_cur[p] = n_next[p];
+    }
+  }
+  if (use_device(ctx0)) return 1;
+  GXY_CUDA(cudaEventRecord(ev1, ctx0->stream));
+  GXY_CUDA(cudaEventSynchronize(ev1));
+  GXY_CUDA(cudaEventElapsedTime(&S.device_ms, ev0, ev1));
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  for (int p = 0; p < nparts; p++)
+    if (check_error_flag(parts[p])) return 1;
+  if (stats) *stats = S;
+  return 0;
+}
+
+int gxy_vis_sample_count(gxy_vis *v, long long *n) {
+  GXY_CHECK(v && n, "gxy_vis_sample_count: NULL argument");
+  *n = (long long)v->n_samples;
+  return 0;
+}
+
+int gxy_vis_download_samples(gxy_vis *v, float *xyz) {
+  if (check_vis(v)) return 1;
+  GXY_CHECK(xyz || v->n_samples == 0, "gxy_vis_download_samples: NULL buffer");
+  if (v->n_samples) GXY_CUDA(cudaMemcpy(xyz, v->d_samples, sizeof(float) * 3 * v->n_samples, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int gxy_particles_from_samples(gxy_vis *v, gxy_particles **out) {
+  if (check_vis(v)) return 1;
+  GXY_CHECK(out, "gxy_particles_from_samples: NULL argument");
+  gxy_particles *p = new gxy_particles();
+  p->ctx = v->ctx; p->n = (int)v->n_samples;
+  p->d_centers = nullptr; p->d_data = nullptr;
+  const size_t n = (size_t)std::max<unsigned long long>(v->n_samples, 1);
+  if (cudaMalloc(&p->d_centers, sizeof(float) * 3 * n) != cudaSuccess || cudaMalloc(&p->d_data, sizeof(float) * n) != cudaSuccess) {
+    cudaFree(p->d_centers);
+    delete p;
+    gxy_set_error("gxy_particles_from_samples: out of device memory");
+    return 1;
+  }
+  if (v->n_samples) GXY_CUDA(cudaMemcpy(p->d_centers, v->d_samples, sizeof(float) * 3 * v->n_samples, cudaMemcpyDeviceToDevice));
+  GXY_CUDA(cudaMemset(p->d_data, 0, sizeof(float) * n));   // newsample.u.value = 0.0 (Sampler.cpp:83)
+  *out = p;
   return 0;
 }
 

@@ -35,6 +35,24 @@ int launch_copy_rays(Rays dst, size_t dst_off, Rays src, size_t src_off, int n, 
 int launch_intersect(const SceneParams &P, int n, const float *org3, const float *dir3, const float *tnear, const float *tfar,
                      int *geom_prim2, float *tuv3, cudaStream_t st);
 
+// ---- Sampler (gxy_sampler.cu) -----------------------------------------------------------------------
+// operators of a sampling Visualization (src/sampler): kind 0 GradientSamplerVis (param = tolerance), 1 IsoSamplerVis (isovalue)
+struct SamplerOpDev {
+  int kind;
+  float param;
+  DevVolume vol;
+};
+struct SamplerParams {
+  int n_ops;
+  float step;  // min samplingStep*samplingRate over the operators (SamplerTraceRays.ispc:141-150)
+  float3 lmin, lmax;
+  SamplerOpDev op[GXY_MAX_VOLUME_VIS];
+};
+// SamplerTraceRays::Trace on n rays: t and term rewritten in place; samples != NULL: the hit points (xyz) are appended at
+// *sample_count (device counter, incremented for every hit; points beyond sample_cap are counted but not written)
+int launch_sampler_trace(const SamplerParams &SP, Rays R, int n, float *samples, unsigned long long *sample_count,
+                         unsigned long long sample_cap, cudaStream_t st);
+
 // ---- TMA-staged volume march (gxy_march_tma.cu) ---------------------------------------------------------
 // one float volume operator, no geometry, < 2^31 voxels, x dimension a multiple of 4 (TMA strides are multiples of 16 bytes)
 bool march_tma_eligible(const SceneParams &P);

@@ -86,6 +86,12 @@ def lib():
         L.gxy_pathlines_destroy.argtypes = [vp]
         L.gxy_build_curves.argtypes = [C.c_int, fp, fp, C.c_int, ip, C.c_float, C.c_float, C.c_float, C.c_float, fp]
         L.gxy_vis_add_pathlines.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(TransferFunction)]
+        L.gxy_vis_add_sampler.argtypes = [vp, vp, C.c_int, C.c_float]
+        L.gxy_sample_raylist.argtypes = [vp, RayListView]
+        L.gxy_sample.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(Camera), C.c_int, C.c_int, C.POINTER(Stats)]
+        L.gxy_vis_sample_count.argtypes = [vp, C.POINTER(C.c_longlong)]
+        L.gxy_vis_download_samples.argtypes = [vp, fp]
+        L.gxy_particles_from_samples.argtypes = [vp, C.POINTER(vp)]
         L.gxy_vis_create.argtypes = [vp, C.POINTER(vp)]
         L.gxy_vis_destroy.argtypes = [vp]
         L.gxy_vis_set_partition.argtypes = [vp, fp, fp, fp, fp, ip]
@@ -227,6 +233,39 @@ class Scene:
         n = np.ascontiguousarray(neighbors, dtype=np.int32)
         check(lib().gxy_vis_set_partition(self.h, _f(a[0]), _f(a[1]), _f(a[2]), _f(a[3]), _i(n)))
 
+    def add_sampler_vis(self, dataset_id, dims, origin, spacing, voxels, kind, param):
+        """kind: "GradientSampler" (param = tolerance) | "IsoSampler" (param = isovalue)"""
+        if dataset_id not in self._volumes:
+            voxels = np.ascontiguousarray(voxels)
+            assert voxels.dtype in (np.float32, np.uint8)
+            d = np.ascontiguousarray(dims, dtype=np.int32)
+            o, s = _f32(origin), _f32(spacing)
+            h = C.c_void_p()
+            check(lib().gxy_volume_create(self.ctx.h, _i(d), _f(o), _f(s), 0 if voxels.dtype == np.float32 else 1,
+                                          voxels.ctypes.data_as(C.c_void_p), C.byref(h)))
+            self._volumes[dataset_id] = h
+            self._owned.append(("volume", h))
+        check(lib().gxy_vis_add_sampler(self.h, self._volumes[dataset_id], {"GradientSampler": 0, "IsoSampler": 1}[kind], param))
+
+    def sample_raylist(self, rays, n):
+        assert rays.dtype == np.float32 and rays.flags.c_contiguous and rays.shape[0] == 25
+        check(lib().gxy_sample_raylist(self.h, RayListView(_f(rays), n, rays.shape[1])))
+
+    def samples(self):
+        n = C.c_longlong()
+        check(lib().gxy_vis_sample_count(self.h, C.byref(n)))
+        out = np.zeros((n.value, 3), np.float32)
+        check(lib().gxy_vis_download_samples(self.h, _f(out)))
+        return out
+
+    def add_particles_from_samples(self, sampling_scene, radius0, radius1, value0, value1, colors, opacities, lo, hi):
+        """a ParticlesVis on the samples another (sampling) Scene collected; they never leave the device"""
+        h = C.c_void_p()
+        check(lib().gxy_particles_from_samples(sampling_scene.h, C.byref(h)))
+        self._owned.append(("particles", h))
+        tf = make_tf(colors, opacities, lo, hi)
+        check(lib().gxy_vis_add_particles(self.h, h, radius0, radius1, value0, value1, C.byref(tf)))
+
     def add_volume_vis(self, dataset_id, dims, origin, spacing, voxels, slices, isovalues, volume_render, colors, opacities, lo, hi):
         if dataset_id not in self._volumes:
             voxels = np.ascontiguousarray(voxels)
@@ -356,6 +395,14 @@ def pinned_array(shape, dtype):
 
 
 _PINNED_OWNERS = {}
+
+
+def sample(parts, camera, w, h):
+    """Sampler over a frame of camera rays (gxy_sample).  Returns ([samples (n,3) per partition], stats dict)."""
+    arr = (C.c_void_p * len(parts))(*[p.h for p in parts])
+    cam, st = make_camera(camera), Stats()
+    check(lib().gxy_sample(len(parts), arr, C.byref(cam), w, h, C.byref(st)))
+    return [p.samples() for p in parts], st.as_dict()
 
 
 def render_device(parts, camera, lighting, w, h, epsilon=0.001):

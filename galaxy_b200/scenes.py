@@ -256,6 +256,12 @@ def parse_operator(v, base_dir=""):
         else:
             op["slices"] = []
         op["volume_render"] = bool(v.get("volume rendering", False))
+    elif t == "GradientSamplerVis":
+        # src/sampler/GradientSamplerVis.cpp:77-85 (initialize: GradientSamplerVis.ispc:74-84 -> 0)
+        op["tolerance"] = float(f32(v.get("tolerance", 0.0)))
+    elif t == "IsoSamplerVis":
+        # src/sampler/IsoSamplerVis.cpp:77-85
+        op["isovalue"] = float(f32(v.get("isovalue", 0.0)))
     elif t == "PathLinesVis":
         # PathLinesVis::initialize / LoadFromJSON (PathLinesVis.cpp:46-55,105-114)
         op["radius0"] = float(f32(v.get("radius0", -1.0)))
@@ -465,6 +471,11 @@ def build_partitions(backend, vis, datasets, nparts, geom_extents=None, only_ran
                 go, gc = part["goffsets"], part["gcounts"]
                 brick = np.ascontiguousarray(ds.data[go[2]:go[2] + gc[2], go[1]:go[1] + gc[1], go[0]:go[0] + gc[0]])
                 origin = np.array([ds.origin[a] + f32(go[a]) * ds.deltas[a] for a in range(3)], f32)  # Volume.h:124-129
+                if op["type"] in ("GradientSamplerVis", "IsoSamplerVis"):  # a sampling Visualization (src/sampler)
+                    kind = op["type"][:-3]
+                    sc.add_sampler_vis(ds_ids[op["dataset"]], gc, origin, ds.deltas, brick, kind,
+                                       op["tolerance"] if kind == "GradientSampler" else op["isovalue"])
+                    continue
                 sc.add_volume_vis(ds_ids[op["dataset"]], gc, origin, ds.deltas, brick, op["slices"], op["isovalues"], op["volume_render"],
                                   colors, opac, lo, hi)
             else:

@@ -197,6 +197,30 @@ int  gxy_generate_rays(gxy_vis *, const gxy_camera *, int w, int h, gxy_raylist_
 int  gxy_intersect(gxy_vis *, int n, const float *org3, const float *dir3, const float *tnear,
                    const float *tfar, int *geom_prim2, float *tuv3);
 
+/* ---- Sampler (src/sampler) ---------------------------------------------------------------- */
+/* A sampling Visualization holds only sampler operators (SamplerTraceRays.ispc:128-222 calls every volumeVis through the
+ * SamplerVis function table).  kind 0 = GradientSamplerVis, param = "tolerance" (GradientSamplerVis.cpp:77-85): a sample
+ * where dot(gradient here, gradient one step back) < tolerance; kind 1 = IsoSamplerVis, param = "isovalue"
+ * (IsoSamplerVis.cpp:77-85): a sample where the value crosses it.  Replaces GradientSamplerVis_* / IsoSamplerVis_* (ispc). */
+#define GXY_SAMPLER_GRADIENT 0
+#define GXY_SAMPLER_ISO      1
+int  gxy_vis_add_sampler(gxy_vis *, gxy_volume *, int kind, float param);
+/* replaces ispc::SamplerTraceRays_SamplerTraceRays (SamplerTraceRays.cpp:48-53): t and term of every ray are rewritten
+ * in place (term = RAY_SURFACE where an operator fired, else RAY_BOUNDARY). */
+int  gxy_sample_raylist(gxy_vis *, gxy_raylist_view rays);
+/* Sampler over a frame of camera rays: Renderer::local_render with Sampler::Trace and Sampler::HandleTerminatedRays
+ * (src/sampler/Sampler.cpp:52-133) on the device.  A ray leaves one sample per firing and continues behind it until it
+ * reaches the partition's boundary, then moves to the neighbour.  Every partition keeps its samples on the device
+ * (as every rank keeps its own Particles in the reference).  One process; stats: primary_rays, traced_rays,
+ * forwarded_rays, waves, kernel_launches, device_ms. */
+int  gxy_sample(int nparts, gxy_vis *const *parts, const gxy_camera *, int w, int h, gxy_stats *stats);
+/* the samples of one partition after gxy_sample: their number; their positions (3 floats each, order unspecified as in
+ * the reference, where threads append under a lock); or as a Particles dataset (value 0, Sampler.cpp:83) without
+ * leaving the device, ready for gxy_vis_add_particles. */
+int  gxy_vis_sample_count(gxy_vis *, long long *n);
+int  gxy_vis_download_samples(gxy_vis *, float *xyz);
+int  gxy_particles_from_samples(gxy_vis *, gxy_particles **out);
+
 /* ---- frame level ------------------------------------------------------------------------- */
 /* Renderer::local_render + the processRays loop + Rendering::AddLocalPixels, all on device
  * (src/renderer/Renderer.cpp:179-269,504-656; Rendering.cpp:125-153).  parts[0..nparts) are the

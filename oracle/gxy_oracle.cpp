@@ -1326,6 +1326,12 @@ void gxo_scene_set_partition(gxo_scene *s, const float gmin[3], const float gmax
   for (int i = 0; i < 6; i++) s->neighbors[i] = neighbors[i];
 }
 
+static VolumeData *scene_volume_impl(gxo_scene *s, int dataset_id, const int dims[3], const float origin[3], const float spacing[3],
+                                     int type, const void *voxels);
+static inline VolumeData *scene_volume(gxo_scene *s, int dataset_id, const int dims[3], const float origin[3], const float spacing[3],
+                                       int type, const void *voxels) {
+  return scene_volume_impl(s, dataset_id, dims, origin, spacing, type, voxels);
+}
 static void set_tf(TF &tf, const float *colors, const float *opac, float lo, float hi) {
   memcpy(tf.color, colors, sizeof tf.color); memcpy(tf.opacity, opac, sizeof tf.opacity);
   tf.lo = lo; tf.hi = hi;
@@ -1336,6 +1342,29 @@ int gxo_scene_add_volume_vis(gxo_scene *s, int dataset_id, const int dims[3], co
                              const float *isovalues, int volume_render, const float *colors, const float *opacities,
                              float lo, float hi) {
   if ((int)s->vvis.size() >= 100) return -1;   // TraceRays.ispc:455 sLast[100]
+  VolumeData *vd = scene_volume(s, dataset_id, dims, origin, spacing, type, voxels);
+  s->vvis.emplace_back();
+  VolumeVisOp &op = s->vvis.back();
+  op.dataset_id = dataset_id; op.vol = vd;
+  set_tf(op.tf, colors, opacities, lo, hi);
+  op.slices.assign(slices4, slices4 + 4 * n_slices);
+  op.isovalues.assign(isovalues, isovalues + n_iso);
+  op.volume_render = volume_render != 0;
+  return (int)s->vvis.size() - 1;
+}
+
+/* GradientSamplerVis ("tolerance", GradientSamplerVis.cpp:77-85) / IsoSamplerVis ("isovalue", IsoSamplerVis.cpp:77-85) on a brick */
+int gxo_scene_add_sampler_vis(gxo_scene *s, int dataset_id, const int dims[3], const float origin[3], const float spacing[3],
+                              int type, const void *voxels, int kind, float param) {
+  if (kind != 0 && kind != 1) return -1;
+  gxo_scene::SamplerOp op;
+  op.kind = kind; op.param = param; op.vol = scene_volume(s, dataset_id, dims, origin, spacing, type, voxels);
+  s->svis.push_back(op);
+  return (int)s->svis.size() - 1;
+}
+
+static VolumeData *scene_volume_impl(gxo_scene *s, int dataset_id, const int dims[3], const float origin[3], const float spacing[3],
+                                     int type, const void *voxels) {
   auto it = s->volumes.find(dataset_id);
   if (it == s->volumes.end()) {
     std::unique_ptr<VolumeData> v(new VolumeData());
@@ -1350,14 +1379,7 @@ int gxo_scene_add_volume_vis(gxo_scene *s, int dataset_id, const int dims[3], co
     v->tf = nullptr;
     it = s->volumes.emplace(dataset_id, std::move(v)).first;
   }
-  s->vvis.emplace_back();
-  VolumeVisOp &op = s->vvis.back();
-  op.dataset_id = dataset_id; op.vol = it->second.get();
-  set_tf(op.tf, colors, opacities, lo, hi);
-  op.slices.assign(slices4, slices4 + 4 * n_slices);
-  op.isovalues.assign(isovalues, isovalues + n_iso);
-  op.volume_render = volume_render != 0;
-  return (int)s->vvis.size() - 1;
+  return it->second.get();
 }
 
 int gxo_scene_add_triangles_vis(gxo_scene *s, int nv, const float *verts, const float *normals, const float *data, int nt,
@@ -1510,10 +1532,17 @@ int gxo_generate_rays(gxo_scene *s, const gxo_camera *cam, int w, int h, float *
   return generate_range(*s, a, w, 0, w * h, R);
 }
 
-int gxo_render(int nparts, gxo_scene **parts, const gxo_camera *cam, const gxo_lighting *lights_in, int w, int h, float epsilon,
-               int max_rays_per_packet, int nthreads, float *fb, gxo_stats *stats) {
+}  // extern "C"
+
+// sampler = false: Renderer (frame into fb).  sampler = true: Sampler (src/sampler/Sampler.cpp): the same loop with
+// Sampler::Trace -> SamplerTraceRays and Sampler::HandleTerminatedRays -> one particle per ray whose term has RAY_SURFACE;
+// such a PRIMARY ray is KEEP_HERE (Renderer::Classify: neither BOUNDARY nor OPAQUE) and is traced again from its new t,
+// so a ray leaves one sample per crossing until it reaches the boundary of the partition and moves on.
+static int render_impl(bool sampler, int nparts, gxo_scene **parts, const gxo_camera *cam, const gxo_lighting *lights_in, int w, int h,
+                       float epsilon, int max_rays_per_packet, int nthreads, float *fb, gxo_stats *stats) {
   gxo_stats st; memset(&st, 0, sizeof st);
-  memset(fb, 0, sizeof(float) * 4 * (size_t)w * h);
+  if (fb) memset(fb, 0, sizeof(float) * 4 * (size_t)w * h);
+  if (sampler) for (int p = 0; p < nparts; p++) parts[p]->samples.clear();
   gxo_lighting L;
   gxo_resolve_lights(lights_in, cam, &L);
   CamFrame a = camera_frame(*cam, w, h);
@@ -1574,7 +1603,9 @@ int gxo_render(int nparts, gxo_scene **parts, const gxo_camera *cam, const gxo_l
       RL &R = rl->v;
       st.traced_rays += R.n;
       long long nao = 0, nsh = 0;
-      std::unique_ptr<OwnedRL> out = trace_and_spawn(S, L, R, epsilon, nthreads, nullptr, &nao, &nsh);
+      std::unique_ptr<OwnedRL> out;
+      if (sampler) sampler_trace(S, R, nthreads);
+      else out = trace_and_spawn(S, L, R, epsilon, nthreads, nullptr, &nao, &nsh);
       st.ao_rays += nao; st.shadow_rays += nsh;
       if (out) {
         // Renderer::Trace (Renderer.cpp:658-691): split to <= max list size, enqueue locally
@@ -1589,11 +1620,18 @@ int gxo_render(int nparts, gxo_scene **parts, const gxo_camera *cam, const gxo_l
         } else q.emplace_back(p, std::move(out));
       }
       classify(S, R);
+      if (sampler)   // Sampler::HandleTerminatedRays (Sampler.cpp:52-92): every ray of the list whose term has RAY_SURFACE
+        for (int i = 0; i < R.n; i++)
+          if (R.term[i] & RAY_SURFACE) {
+            S.samples.push_back(R.ox[i] + R.t[i] * R.dx[i]);
+            S.samples.push_back(R.oy[i] + R.t[i] * R.dy[i]);
+            S.samples.push_back(R.oz[i] + R.t[i] * R.dz[i]);
+          }
       // HandleTerminatedRays (Renderer.cpp:456-502) + AddLocalPixels (Rendering.cpp:125-153)
       std::vector<int> knts(nparts, 0); int nKeepers = 0;
       for (int i = 0; i < R.n; i++) {
         int c = R.classification[i];
-        if (c == TERMINATED) {
+        if (c == TERMINATED && !sampler) {
           float *ptr = fb + (((size_t)R.y[i] * w + R.x[i]) << 2);
           ptr[0] += R.r[i]; ptr[1] += R.g[i]; ptr[2] += R.b[i]; ptr[3] += R.o[i];
           st.terminated_rays++;
@@ -1616,6 +1654,31 @@ int gxo_render(int nparts, gxo_scene **parts, const gxo_camera *cam, const gxo_l
   }
   for (int p = 0; p < nparts; p++) st.volume_samples += parts[p]->sample_count.load();
   if (stats) *stats = st;
+  return 0;
+}
+
+extern "C" {
+
+int gxo_render(int nparts, gxo_scene **parts, const gxo_camera *cam, const gxo_lighting *lights_in, int w, int h, float epsilon,
+               int max_rays_per_packet, int nthreads, float *fb, gxo_stats *stats) {
+  return render_impl(false, nparts, parts, cam, lights_in, w, h, epsilon, max_rays_per_packet, nthreads, fb, stats);
+}
+
+int gxo_sample(int nparts, gxo_scene **parts, const gxo_camera *cam, int w, int h, int max_rays_per_packet, int nthreads,
+               gxo_stats *stats) {
+  gxo_lighting L; memset(&L, 0, sizeof L);
+  L.n_lights = 1; L.lights[0][0] = L.lights[0][1] = L.lights[0][2] = 1.f; L.types[0] = 2; L.Ka = L.Kd = 0.5f;   // unused by the sampler
+  return render_impl(true, nparts, parts, cam, &L, w, h, 0.001f, max_rays_per_packet, nthreads, nullptr, stats);
+}
+
+long long gxo_scene_samples(gxo_scene *s, const float **xyz) {
+  if (xyz) *xyz = s->samples.data();
+  return (long long)(s->samples.size() / 3);
+}
+
+int gxo_sample_raylist(gxo_scene *s, float *base, int n, int aligned_n) {
+  RL R = view(base, n, aligned_n);
+  sampler_trace(*s, R, 0);
   return 0;
 }
 

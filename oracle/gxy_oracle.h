@@ -142,6 +142,21 @@ int gxo_render(int nparts, gxo_scene **parts, const gxo_camera *, const gxo_ligh
                int w, int h, float epsilon, int max_rays_per_packet, int nthreads,
                float *fb, gxo_stats *stats);
 
+/* ---- Sampler (src/sampler): rays leave a sample point wherever a sampler operator fires ---------------------------
+ * A sampling Visualization holds only sampler operators (SamplerTraceRays.ispc:128-222 calls every volumeVis through the
+ * SamplerVis function table): kind 0 = GradientSamplerVis, param = "tolerance" (fires when dot(grad_this, grad_last) <
+ * tolerance, sample at the interval's midpoint); kind 1 = IsoSamplerVis, param = "isovalue" (fires when the value crosses
+ * it, sample at the linear crossing).  Volume arguments as gxo_scene_add_volume_vis. */
+int gxo_scene_add_sampler_vis(gxo_scene *, int dataset_id, const int dims[3], const float origin[3], const float spacing[3],
+                              int type, const void *voxels, int kind, float param);
+/* SamplerTraceRays::Trace on one RayList: t and term are rewritten in place (term = RAY_SURFACE on a sample, else RAY_BOUNDARY) */
+int gxo_sample_raylist(gxo_scene *, float *base, int n, int aligned_n);
+/* Sampler over a frame of camera rays (Renderer::local_render with Sampler::Trace / Sampler::HandleTerminatedRays,
+ * Sampler.cpp:52-133): every partition collects its samples; stats: primary_rays, traced_rays, forwarded_rays, waves. */
+int gxo_sample(int nparts, gxo_scene **parts, const gxo_camera *, int w, int h, int max_rays_per_packet, int nthreads, gxo_stats *stats);
+/* the samples of one partition after gxo_sample: returns their number, *xyz = 3 floats per sample (owned by the scene) */
+long long gxo_scene_samples(gxo_scene *, const float **xyz);
+
 /* ColorImageWriter::Write (ImageWriter.cpp:30-48): float RGBA (y up) -> RGBA8 rows top-down,
  * truncating (unsigned char)(255*f) with x86 cvttss2si + low-byte semantics. */
 void gxo_fb_to_rgba8(const float *fb, int w, int h, unsigned char *out);

@@ -57,6 +57,11 @@ def lib():
         L.gxo_scene_add_pathlines_vis.argtypes = [vp, C.c_int, fp, fp, C.c_int, ip, C.c_float, C.c_float, C.c_float, C.c_float, fp, fp,
                                                   C.c_float, C.c_float]
         L.gxo_build_curves.argtypes = [C.c_int, fp, fp, C.c_int, ip, C.c_float, C.c_float, C.c_float, C.c_float, fp]
+        L.gxo_scene_add_sampler_vis.argtypes = [vp, C.c_int, ip, fp, fp, C.c_int, vp, C.c_int, C.c_float]
+        L.gxo_sample_raylist.argtypes = [vp, fp, C.c_int, C.c_int]
+        L.gxo_sample.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(Camera), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Stats)]
+        L.gxo_scene_samples.argtypes = [vp, C.POINTER(fp)]
+        L.gxo_scene_samples.restype = C.c_longlong
         L.gxo_scene_commit.argtypes = [vp]
         L.gxo_resample_tf.argtypes = [C.c_int, fp, C.c_int, fp, fp, fp]
         L.gxo_resolve_lights.argtypes = [C.POINTER(Lighting), C.POINTER(Camera), C.POINTER(Lighting)]
@@ -167,6 +172,27 @@ class Scene:
             raise ValueError("pathlines: bad connectivity")
         return rc
 
+    def add_sampler_vis(self, dataset_id, dims, origin, spacing, voxels, kind, param):
+        """kind: "GradientSampler" (param = tolerance) | "IsoSampler" (param = isovalue)"""
+        voxels = np.ascontiguousarray(voxels)
+        assert voxels.dtype in (np.float32, np.uint8)
+        dims = np.ascontiguousarray(dims, dtype=np.int32)
+        o, s = _f32(origin), _f32(spacing)
+        self._keep += [voxels]
+        rc = lib().gxo_scene_add_sampler_vis(self.h, dataset_id, _i(dims), _f(o), _f(s), 0 if voxels.dtype == np.float32 else 1,
+                                             voxels.ctypes.data_as(C.c_void_p), {"GradientSampler": 0, "IsoSampler": 1}[kind], param)
+        assert rc >= 0
+        return rc
+
+    def sample_raylist(self, rays, n):
+        assert rays.dtype == np.float32 and rays.flags.c_contiguous and rays.shape[0] == 25
+        lib().gxo_sample_raylist(self.h, _f(rays), n, rays.shape[1])
+
+    def samples(self):
+        p = C.POINTER(C.c_float)()
+        n = lib().gxo_scene_samples(self.h, C.byref(p))
+        return np.ctypeslib.as_array(p, shape=(n, 3)).copy() if n else np.zeros((0, 3), np.float32)
+
     def commit(self):
         return lib().gxo_scene_commit(self.h)
 
@@ -212,6 +238,15 @@ def render(parts, camera, lighting, w, h, epsilon=0.001, max_rays_per_packet=100
     rc = lib().gxo_render(len(parts), arr, C.byref(cam), C.byref(L), w, h, epsilon, max_rays_per_packet, nthreads, _f(fb), C.byref(st))
     assert rc == 0
     return fb, st.as_dict()
+
+
+def sample(parts, camera, w, h, max_rays_per_packet=1000000, nthreads=0):
+    """Sampler over a frame of camera rays.  Returns ([samples (n,3) per partition], stats dict)."""
+    arr = (C.c_void_p * len(parts))(*[p.h for p in parts])
+    cam, st = make_camera(camera), Stats()
+    rc = lib().gxo_sample(len(parts), arr, C.byref(cam), w, h, max_rays_per_packet, nthreads, C.byref(st))
+    assert rc == 0
+    return [p.samples() for p in parts], st.as_dict()
 
 
 def resolve_lights(lighting, camera):
