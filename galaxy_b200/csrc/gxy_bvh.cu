@@ -14,6 +14,7 @@
 //      and its leaf primitives consecutive record positions (compressed-wide-BVH addressing)
 //   5. primitive records (48 B: v0,e1,e2 | centre,radius + ids) written in node order
 #include "gxy_internal.h"
+#include "gxy_curve.cuh"
 
 #include <cub/cub.cuh>
 #include <algorithm>
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(256)
     r.c = make_float4(0.f, __uint_as_float((unsigned)g.geom_id | (1u << 24)), __uint_as_float((unsigned)i), 0.f);
   } else {
     const unsigned long long cp = (unsigned long long)(g.centers + 16 * (size_t)i);   // 64-byte aligned (cudaMalloc + 64 i)
-    r.a = make_float4(__uint_as_float((unsigned)cp), __uint_as_float((unsigned)(cp >> 32)), 0.f, 0.f);
+    r.a = make_float4(__uint_as_float((unsigned)cp), __uint_as_float((unsigned)(cp >> 32)), gxc::curve_bound_radius(g.centers + 16 * (size_t)i), 0.f);
     r.b = make_float4(0.f, 0.f, 0.f, 0.f);
     r.c = make_float4(0.f, __uint_as_float((unsigned)g.geom_id | (2u << 24)), __uint_as_float((unsigned)i), 0.f);
   }

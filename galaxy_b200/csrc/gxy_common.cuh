@@ -100,7 +100,7 @@ static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
 // primitive record in leaf order, 48 bytes (3 x 16 B loads)
 //   triangle: a=(v0.xyz, e1.x) b=(e1.yz, e2.xy) c=(e2.z, bits(geom|kind<<24), bits(prim), 0)
 //   sphere:   a=(c.xyz, radius) b=(epsilon,0,0,0) c=(0, bits(geom|1<<24), bits(prim), 0)
-//   curve:    a=(address of its 4 control points: low, high word, 0, 0) c=(0, bits(geom|2<<24), bits(prim), 0)
+//   curve:    a=(address of its 4 control points: low, high word; bound radius for the cull, gxy_curve.cuh; 0) c=(0, bits(geom|2<<24), bits(prim), 0)
 struct __align__(16) PrimRec {
   float4 a, b, c;
 };

@@ -92,9 +92,16 @@ __device__ __forceinline__ bool sphere_test(const float4 ra, const float4 rb, fl
 // Embree's sweep intersector (gxy_curve.cuh); hits in the OPEN interval (tnear, tfar), u = curve parameter.
 __device__ __forceinline__ bool curve_rec_test(const float4 ra, float3 org, float3 dir, float tnear, float tfar, gxc::CurveHit &h) {
   const float4 *cp = reinterpret_cast<const float4 *>(((unsigned long long)__float_as_uint(ra.y) << 32) | (unsigned long long)__float_as_uint(ra.x));
+  const float4 q0 = __ldg(cp), q3 = __ldg(cp + 3);
+  // conservative cull (ra.z = the segment's bound radius, written with the record): most rays that reach a leaf box pass the
+  // thin tube by; they skip the sub-division
+  if (gxc::curve_precull(gxc::v3(q0.x, q0.y, q0.z), gxc::v3(q3.x, q3.y, q3.z), ra.z, gxc::v3(org.x, org.y, org.z), gxc::v3(dir.x, dir.y, dir.z)))
+    return false;
   float c[16];
+  c[0] = q0.x; c[1] = q0.y; c[2] = q0.z; c[3] = q0.w;
+  c[12] = q3.x; c[13] = q3.y; c[14] = q3.z; c[15] = q3.w;
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
+  for (int k = 1; k < 3; k++) {
     const float4 q = __ldg(cp + k);
     c[4 * k] = q.x; c[4 * k + 1] = q.y; c[4 * k + 2] = q.z; c[4 * k + 3] = q.w;
   }

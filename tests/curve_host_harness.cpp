@@ -3,6 +3,9 @@
 // (tests/test_curve_host.py builds this with g++ -ffp-contract=off into a temporary directory).
 #include "../galaxy_b200/csrc/gxy_curve.cuh"
 
+static long g_culled = 0, g_tested = 0;
+extern "C" void gxc_cull_stats(long *culled, long *tested) { *culled = g_culled; *tested = g_tested; }
+
 extern "C" int gxc_curve_intersect(int n_curves, const float *cp, int n_rays, const float *org3, const float *dir3, const float *tnear,
                                    const float *tfar, int *prim_out, float *tu_out, float *ng_out, int per_curve) {
   for (int r = 0; r < n_rays; r++) {
@@ -10,8 +13,14 @@ extern "C" int gxc_curve_intersect(int n_curves, const float *cp, int n_rays, co
     float bt = tfar[r], bu = 0.f, bn[3] = {0.f, 0.f, 0.f};
     for (int p = 0; p < n_curves; p++) {
       gxc::CurveHit h;
-      const bool hit = gxc::curve_test(cp + 16 * (long)p, org3[3 * r], org3[3 * r + 1], org3[3 * r + 2], dir3[3 * r], dir3[3 * r + 1],
-                                       dir3[3 * r + 2], tnear[r], tfar[r], h);
+      // as the device does (curve_rec_test, gxy_traverse.cuh): the conservative cull with the bound the BVH builder stores, then the test
+      const float *c = cp + 16 * (long)p;
+      const bool culled = gxc::curve_precull(gxc::v3(c[0], c[1], c[2]), gxc::v3(c[12], c[13], c[14]), gxc::curve_bound_radius(c),
+                                             gxc::v3(org3[3 * r], org3[3 * r + 1], org3[3 * r + 2]), gxc::v3(dir3[3 * r], dir3[3 * r + 1], dir3[3 * r + 2]));
+      g_culled += culled ? 1 : 0;
+      g_tested += 1;
+      const bool hit = !culled && gxc::curve_test(c, org3[3 * r], org3[3 * r + 1], org3[3 * r + 2], dir3[3 * r], dir3[3 * r + 1],
+                                                  dir3[3 * r + 2], tnear[r], tfar[r], h);
       if (per_curve) {
         const long o = (long)r * n_curves + p;
         prim_out[o] = hit ? 1 : 0;

@@ -45,6 +45,42 @@ def test_device_source_matches_oracle_bit_for_bit(host_curve, seed, radii):
             assert np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))      # Ng
 
 
+def test_cull_is_conservative_on_grazing_rays(host_curve):
+    """The device path first asks curve_precull (line-to-line distance against the bound stored with the BVH record) and only
+    then runs the sub-division.  Rays that graze the tubes -- through surface points, perpendicular to the normal, shifted by
+    -1e-3 .. +1e-3 of the radius scale along it -- must get the oracle's answer bit for bit; the cull must also do its job."""
+    O = oracle.lib()
+    v, d, c = helices(12, nlines=8)
+    cp = build(O, v, d, c, 0.004, 0.05, 0.0, 1.7)
+    org, dr, tn, tf = rays_at(cp, 20000, 77, 0.03)
+    prim, tu, ng = intersect(O, "gxo_curve_intersect", cp, org, dr, tn, tf, 0)
+    hit = prim >= 0
+    P = org[hit] + tu[hit, :1] * dr[hit]
+    N = ng[hit] / np.linalg.norm(ng[hit], axis=1, keepdims=True)
+    rng = np.random.default_rng(3)
+    T = np.cross(N, rng.normal(size=N.shape))
+    T /= np.linalg.norm(T, axis=1, keepdims=True)
+    orgs, dirs = [], []
+    for delta in (-1e-3, -1e-4, -1e-5, 0.0, 1e-5, 1e-4, 1e-3):
+        orgs.append(P + N * (delta * 0.05) - T * rng.uniform(0.5, 3.0, (len(P), 1)))
+        dirs.append(T * rng.uniform(0.5, 2.0, (len(P), 1)))
+    org2 = np.ascontiguousarray(np.concatenate(orgs), np.float32)
+    dr2 = np.ascontiguousarray(np.concatenate(dirs), np.float32)
+    tn2, tf2 = np.zeros(len(org2), np.float32), np.full(len(org2), 3.4e38, np.float32)
+    c0, t0 = C.c_long(), C.c_long()
+    host_curve.gxc_cull_stats(C.byref(c0), C.byref(t0))
+    a = intersect(O, "gxo_curve_intersect", cp, org2, dr2, tn2, tf2, 1)
+    b = intersect(host_curve, "gxc_curve_intersect", cp, org2, dr2, tn2, tf2, 1)
+    c1, t1 = C.c_long(), C.c_long()
+    host_curve.gxc_cull_stats(C.byref(c1), C.byref(t1))
+    assert 0.2 < a[0].reshape(len(org2), -1).any(1).mean() < 0.9         # really grazing: a good part hits, a good part misses
+    assert np.array_equal(a[0], b[0])
+    assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)) and np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))
+    culled = (c1.value - c0.value) / (t1.value - t0.value)
+    print("cull fraction on all ray x segment pairs: %.3f" % culled)
+    assert culled > 0.8                                                 # all-pairs: nearly every pair is a miss the cull sees
+
+
 def test_device_source_degenerate_inputs(host_curve):
     """zero-length segments, zero radius, rays along the axis, zero direction components: same answers, no hangs."""
     O = oracle.lib()
