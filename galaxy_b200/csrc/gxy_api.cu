@@ -1012,10 +1012,14 @@ int gxy_sample(int nparts, gxy_vis *const *parts, const gxy_camera *cam, int w, 
   gxy_stats S;
   memset(&S, 0, sizeof S);
   gxy_context *ctx0 = parts[0]->ctx;
-  cudaEvent_t ev0, ev1;
+  struct EventPair {  // destroyed on every return path
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  } ev;
   if (use_device(ctx0)) return 1;
-  GXY_CUDA(cudaEventCreate(&ev0));
-  GXY_CUDA(cudaEventCreate(&ev1));
+  GXY_CUDA(cudaEventCreate(&ev.a));
+  GXY_CUDA(cudaEventCreate(&ev.b));
+  cudaEvent_t ev0 = ev.a, ev1 = ev.b;
   GXY_CUDA(cudaEventRecord(ev0, ctx0->stream));
   std::vector<int> n_cur(nparts, 0);
   for (int p = 0; p < nparts; p++) {
@@ -1090,8 +1094,6 @@ int gxy_sample(int nparts, gxy_vis *const *parts, const gxy_camera *cam, int w, 
   GXY_CUDA(cudaEventRecord(ev1, ctx0->stream));
   GXY_CUDA(cudaEventSynchronize(ev1));
   GXY_CUDA(cudaEventElapsedTime(&S.device_ms, ev0, ev1));
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
   for (int p = 0; p < nparts; p++)
     if (check_error_flag(parts[p])) return 1;
   if (stats) *stats = S;
@@ -1124,8 +1126,13 @@ int gxy_particles_from_samples(gxy_vis *v, gxy_particles **out) {
     gxy_set_error("gxy_particles_from_samples: out of device memory");
     return 1;
   }
-  if (v->n_samples) GXY_CUDA(cudaMemcpy(p->d_centers, v->d_samples, sizeof(float) * 3 * v->n_samples, cudaMemcpyDeviceToDevice));
-  GXY_CUDA(cudaMemset(p->d_data, 0, sizeof(float) * n));   // newsample.u.value = 0.0 (Sampler.cpp:83)
+  cudaError_t e = v->n_samples ? cudaMemcpy(p->d_centers, v->d_samples, sizeof(float) * 3 * v->n_samples, cudaMemcpyDeviceToDevice) : cudaSuccess;
+  if (e == cudaSuccess) e = cudaMemset(p->d_data, 0, sizeof(float) * n);   // newsample.u.value = 0.0 (Sampler.cpp:83)
+  if (e != cudaSuccess) {
+    gxy_set_error("gxy_particles_from_samples: %s", cudaGetErrorString(e));
+    gxy_particles_destroy(p);
+    return 1;
+  }
   *out = p;
   return 0;
 }
