@@ -238,6 +238,15 @@ GXC_FN bool curve_level_setup(const CurveRay &ray, const V4 *cp, float u0, float
     halfplane_clip(p0, d0, dir, lo, up);
     halfplane_clip(p3, v3(-d3.x, -d3.y, -d3.z), dir, lo, up);
     const bool v = co.valid && (lo <= up);
+    if (!v) {
+      // Embree computes the inner cylinder for all 8 lanes at once; a lane the outer cylinder or the cap planes reject can set
+      // neither valid0 nor valid1, and only those lanes' u, interval and stability values are ever read: skip the rest
+      L.t0_lo[i] = L.t1_lo[i] = GXC_INF;
+      L.t1_up[i] = -GXC_INF;
+      L.uo0[i] = L.uo1[i] = 0.0f;
+      Pa = Pb; dPa = dPb;
+      continue;
+    }
     const float c0 = smin(smax(co.u0, 0.0f), 1.0f), c1 = smin(smax(co.u1, 0.0f), 1.0f);
     L.uo0[i] = fmaf(((float)i + c0) * (1.0f / 8.0f), u1 - u0, u0);   // Embree's own (step+u)*(1/VSIZEX)
     L.uo1[i] = fmaf(((float)i + c1) * (1.0f / 8.0f), u1 - u0, u0);
