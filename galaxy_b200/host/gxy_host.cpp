@@ -325,15 +325,117 @@ static std::string resolve_path(const std::string &name, const std::string &base
   return probe ? base_dir + name : name;  // the reference resolves against the working directory
 }
 
+// Camera::LoadFromPVCC (Camera.cpp:118-163): ParaView's camera configuration as XML,
+//   <PVCameraConfiguration><Proxy><Property name="CameraPosition"><Element index="0" value="1.5"/>...
+// read with boost::property_tree there; here a scan for the Property / Element tags below PVCameraConfiguration.Proxy
+// (attribute values as the stream extraction to float reads them: strtof).
+static bool xml_attr(const std::string &tag, const char *key, std::string &out) {
+  size_t p = 0;
+  const std::string k(key);
+  while ((p = tag.find(k, p)) != std::string::npos) {
+    const bool start_ok = p > 0 && isspace((unsigned char)tag[p - 1]);
+    size_t q = p + k.size();
+    while (q < tag.size() && isspace((unsigned char)tag[q])) q++;
+    if (start_ok && q < tag.size() && tag[q] == '=') {
+      q++;
+      while (q < tag.size() && isspace((unsigned char)tag[q])) q++;
+      if (q < tag.size() && (tag[q] == '"' || tag[q] == '\'')) {
+        const size_t e = tag.find(tag[q], q + 1);
+        if (e == std::string::npos) return false;
+        out = tag.substr(q + 1, e - q - 1);
+        return true;
+      }
+    }
+    p += k.size();
+  }
+  return false;
+}
+
+bool Camera::LoadFromPVCC(const std::string &filename) {
+  std::ifstream ifs(filename.c_str());
+  if (!ifs) return false;
+  std::stringstream ss;
+  ss << ifs.rdbuf();
+  const std::string s = ss.str();
+  float center[3] = {0, 0, 0};
+  bool in_config = false, in_proxy = false, seen_proxy = false;
+  std::string property;
+  float values[3] = {-1e32f, -1e32f, -1e32f};
+  auto assign = [&]() {
+    if (property == "CameraPosition") for (int i = 0; i < 3; i++) eye[i] = values[i];
+    else if (property == "CameraFocalPoint") for (int i = 0; i < 3; i++) center[i] = values[i];
+    else if (property == "CameraViewUp") for (int i = 0; i < 3; i++) up[i] = values[i];
+    else if (property == "CameraViewAngle") aov = values[0];
+    property.clear();
+  };
+  size_t pos = 0;
+  while (true) {
+    const size_t lt = s.find('<', pos);
+    if (lt == std::string::npos) break;
+    if (s.compare(lt, 4, "<!--") == 0) {
+      const size_t e = s.find("-->", lt);
+      if (e == std::string::npos) return false;
+      pos = e + 3;
+      continue;
+    }
+    const size_t gt = s.find('>', lt);
+    if (gt == std::string::npos) return false;
+    const std::string tag = s.substr(lt + 1, gt - lt - 1);
+    pos = gt + 1;
+    if (tag.empty() || tag[0] == '?' || tag[0] == '!') continue;
+    size_t n = 0;
+    while (n < tag.size() && !isspace((unsigned char)tag[n]) && tag[n] != '/') n++;
+    const bool closing = tag[0] == '/';
+    std::string name = closing ? tag.substr(1) : tag.substr(0, n);
+    if (closing) {
+      const size_t ws = name.find_first_of(" \t\r\n");
+      if (ws != std::string::npos) name.erase(ws);
+    }
+    const bool self_closing = !closing && tag.back() == '/';
+    if (name == "PVCameraConfiguration") in_config = !closing;
+    else if (name == "Proxy" && in_config) { in_proxy = !closing && !self_closing; seen_proxy = true; }
+    else if (name == "Property" && in_proxy) {
+      if (closing) assign();
+      else {
+        if (!xml_attr(tag, "name", property)) return false;   // get<std::string>("<xmlattr>.name") throws -> catch(...) -> false
+        values[0] = values[1] = values[2] = -1e32f;
+        if (self_closing) assign();
+      }
+    } else if (name == "Element" && in_proxy && !property.empty() && !closing) {
+      std::string si, sv;
+      if (!xml_attr(tag, "index", si) || !xml_attr(tag, "value", sv)) return false;
+      char *end = nullptr;
+      const long indx = strtol(si.c_str(), &end, 10);
+      if (end == si.c_str() || indx < 0 || indx > 2) return false;   // the reference writes values[indx] unchecked
+      const float val = strtof(sv.c_str(), &end);
+      if (end == sv.c_str()) return false;
+      values[indx] = val;
+    }
+  }
+  if (!seen_proxy) return false;   // get_child("PVCameraConfiguration.Proxy") throws
+  for (int k = 0; k < 3; k++) dir[k] = center[k] - eye[k];
+  return true;
+}
+
 bool Camera::LoadFromJSON(const json::Value &v, const std::string &base_dir) {
-  if (v.IsString()) {  // Camera.cpp:168-232: a ParaView camera configuration converted to JSON
+  if (v.IsString()) {  // Camera.cpp:168-232: a ParaView camera configuration, converted to JSON or as ParaView writes it (.pvcc, XML)
     const std::string fname = resolve_path(v.GetString(), base_dir);
+    {
+      std::ifstream probe(fname.c_str());
+      if (!probe) {
+        std::cerr << "unable to open " << v.GetString() << "\n";
+        return false;
+      }
+    }
     json::Value doc;
     try {
       doc = json::ParseFile(fname);
     } catch (const std::exception &e) {
-      std::cerr << "error loading camera from " << v.GetString() << " (" << e.what() << "; XML .pvcc files are not read by this driver)\n";
-      return false;
+      if (!LoadFromPVCC(fname)) {  // Camera.cpp:182-191: not JSON -> try the XML form
+        std::cerr << "error loading camera from " << v.GetString() << "\n";
+        return false;
+      }
+      return true;
     }
     try {
       if (!doc.HasMember("PVCameraConfiguration") || !doc["PVCameraConfiguration"].HasMember("Proxy") ||

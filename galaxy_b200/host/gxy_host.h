@@ -80,8 +80,9 @@ class Datasets {
 
 class Camera {
  public:
-  // v: a camera object, or the name of a ParaView camera file in JSON form (Camera.cpp:168-232; XML .pvcc files are refused)
+  // v: a camera object, or the name of a ParaView camera file, in JSON form or as ParaView writes it (.pvcc, XML) (Camera.cpp:118-232)
   bool LoadFromJSON(const json::Value &v, const std::string &base_dir = "");
+  bool LoadFromPVCC(const std::string &filename);
   static bool LoadCamerasFromJSON(const json::Value &doc, std::vector<Camera> &out, const std::string &base_dir = "");
   gxy_camera AsABI() const;
   float eye[3] = {0, 0, 0}, dir[3] = {0, 0, 1}, up[3] = {0, 1, 0}, aov = 30.f;

@@ -173,10 +173,47 @@ def _resolve(name, base_dir):
     return p if os.path.exists(p) else name
 
 
+def _strtof(s):
+    """the float a C++ stream extraction / strtof reads (no double rounding)"""
+    import ctypes
+    libc = ctypes.CDLL(None)
+    libc.strtof.restype = ctypes.c_float
+    libc.strtof.argtypes = [ctypes.c_char_p, ctypes.c_void_p]
+    return float(libc.strtof(s.strip().encode(), None))
+
+
+def _camera_from_pvcc(path):
+    import xml.etree.ElementTree as ET
+    root = ET.parse(path).getroot()
+    proxy = root.find("Proxy") if root.tag == "PVCameraConfiguration" else root.find("PVCameraConfiguration/Proxy")
+    if proxy is None:
+        raise ValueError("error loading camera from " + path)
+    cam = dict(eye=[0.0] * 3, up=[0.0, 1.0, 0.0], aov=30.0, annotation="")
+    center = [f32(0)] * 3
+    for prop in proxy.findall("Property"):
+        values = [f32(-1e32)] * 3
+        for el in prop.findall("Element"):
+            values[int(el.get("index"))] = f32(_strtof(el.get("value")))
+        name = prop.get("name")
+        if name == "CameraPosition":
+            cam["eye"] = [float(x) for x in values]
+        elif name == "CameraFocalPoint":
+            center = values
+        elif name == "CameraViewUp":
+            cam["up"] = [float(x) for x in values]
+        elif name == "CameraViewAngle":
+            cam["aov"] = float(values[0])
+    cam["dir"] = [float(f32(center[k] - f32(cam["eye"][k]))) for k in range(3)]
+    return cam
+
+
 def parse_camera(v, base_dir=""):
     """Camera::LoadFromJSON (src/renderer/Camera.cpp:165-281): an object, or the name of a ParaView camera file in JSON form."""
     if isinstance(v, str):
-        doc = json.load(open(_resolve(v, base_dir)))
+        try:
+            doc = json.load(open(_resolve(v, base_dir)))
+        except ValueError:  # Camera.cpp:182-191: not JSON -> ParaView's own XML form (.pvcc), Camera::LoadFromPVCC (:118-163)
+            return _camera_from_pvcc(_resolve(v, base_dir))
         cam = dict(eye=[0.0] * 3, up=[0.0, 1.0, 0.0], aov=30.0, annotation="")
         center = [f32(0)] * 3
         for p in doc["PVCameraConfiguration"]["Proxy"]["Property"]:

@@ -177,3 +177,57 @@ def test_camera_and_colormap_files(tmp_path):
     json.dump(doc, open(state, "w"))
     r = subprocess.run([EXE, "--describe", state], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "error loading camera" in r.stderr
+
+
+def test_pvcc_camera_file(tmp_path):
+    """"Cameras": ["cam.pvcc"]: ParaView's own XML camera configuration (Camera::LoadFromPVCC, Camera.cpp:118-163; tried when the
+    file is not JSON, :182-191) -- same camera from the C++ host and the Python front end; a broken file is refused."""
+    tmp = str(tmp_path)
+    write_vol(os.path.join(tmp, "radial-oneBall.vol"), scenes.radial_volume("oneBall", 12))
+    open(os.path.join(tmp, "cam.pvcc"), "w").write("""<?xml version="1.0"?>
+<!-- saved by ParaView -->
+<PVCameraConfiguration description="ParaView camera configuration" version="1.0">
+  <Proxy group="views" type="RenderView" id="4875" servers="21">
+    <Property name="CameraPosition" id="4875.CameraPosition" number_of_elements="3">
+      <Element index="0" value="1.2345678901234"/>
+      <Element index="1" value="-2.5"/>
+      <Element index="2" value="3.1e0"/>
+    </Property>
+    <Property name="CameraFocalPoint" id="4875.CameraFocalPoint" number_of_elements="3">
+      <Element index="2" value="0.3"/>
+      <Element index="0" value="0.1"/>
+      <Element index="1" value="0.2"/>
+    </Property>
+    <Property name="CameraViewUp" id="4875.CameraViewUp" number_of_elements="3">
+      <Element index="0" value="0"/> <Element index="1" value="0"/> <Element index="2" value="1"/>
+    </Property>
+    <Property name="CameraViewAngle" id="4875.CameraViewAngle" number_of_elements="1">
+      <Element index="0" value="27.5"/>
+    </Property>
+    <Property name="CameraParallelProjection" id="4875.CameraParallelProjection" number_of_elements="1">
+      <Element index="0" value="0"/>
+      <Domain name="bool" id="4875.CameraParallelProjection.bool"/>
+    </Property>
+  </Proxy>
+</PVCameraConfiguration>
+""")
+    doc = {"Datasets": [{"name": "oneBall", "type": "Volume", "filename": "radial-oneBall.vol"}],
+           "Visualizations": [{"operators": [{"type": "Volume", "dataset": "oneBall", "isovalues": [0.4]}]}],
+           "Cameras": ["cam.pvcc"]}
+    state = os.path.join(tmp, "pvcc.state")
+    json.dump(doc, open(state, "w"))
+    out = subprocess.run([EXE, "--describe", state], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    got = json.loads(out.stdout, parse_float=lambda t: float(np.float32(t)))
+    st = scenes.parse_state(doc, base_dir=tmp)
+    c, g = st["cameras"][0], got["cameras"][0]
+    assert g["eye"] == f32list(c["eye"]) and g["dir"] == f32list(c["dir"]) and g["up"] == f32list(c["up"]) and g["aov"] == float(np.float32(c["aov"]))
+    assert g["eye"] == f32list([1.2345678901234, -2.5, 3.1]) and g["up"] == [0.0, 0.0, 1.0] and g["aov"] == 27.5
+    assert g["dir"] == f32list([np.float32(0.1) - np.float32(1.2345678901234), np.float32(0.2) - np.float32(-2.5), np.float32(0.3) - np.float32(3.1)])
+    # neither JSON nor a camera configuration
+    open(os.path.join(tmp, "cam.pvcc"), "w").write("<NotACamera><Proxy/></NotACamera>")
+    out = subprocess.run([EXE, "--describe", state], capture_output=True, text=True, timeout=60)
+    assert out.returncode != 0 and "error loading camera from" in out.stderr
+    os.remove(os.path.join(tmp, "cam.pvcc"))
+    out = subprocess.run([EXE, "--describe", state], capture_output=True, text=True, timeout=60)
+    assert out.returncode != 0 and "unable to open" in out.stderr
