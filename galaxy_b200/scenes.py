@@ -441,6 +441,21 @@ def clip_particles(ds, ext, ghost=0.1):
     return ParticlesDataset(ds.centers[inside], ds.data[inside])
 
 
+def helix_pathlines(n_lines, n_verts=12, seed=21):
+    """A synthetic PathLines dataset: helical poly-lines inside [-1,1]^3, data = |p| (what a stream tracer through a
+    rotating field leaves; tests/create_data_driven_datasets.vpy makes the reference's with vtkStreamTracer)."""
+    rng = np.random.default_rng(seed)
+    pts, lines, k = [], [], 0
+    for _ in range(n_lines):
+        t = np.linspace(0, 3 + rng.uniform(0, 2), n_verts)
+        c = rng.uniform(-.4, .4, 3)
+        pts.append(np.stack([c[0] + 0.45 * np.cos(t), c[1] + 0.45 * np.sin(t), c[2] + 0.15 * t - 0.3], 1))
+        lines.append(list(range(k, k + n_verts)))
+        k += n_verts
+    pts = np.concatenate(pts).astype(f32)
+    return PathLinesDataset(pts, np.linalg.norm(pts, axis=1), lines)
+
+
 def clip_pathlines(ds, ext, ghost=0.1):
     """Partition poly-lines as scripts/partitionVTUs.vpy:116-147 does: every run of vertices inside the ghost-extended
     extent, plus one vertex at either end, becomes a poly-line of the piece; points are compacted in order of first use."""

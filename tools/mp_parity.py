@@ -49,16 +49,29 @@ def main():
     t = torch.tensor([s9[k] for k in keys], dtype=torch.int64, device="cuda")
     dist.all_reduce(t)
     results["nineBalls"] = (dict(zip(keys, t.tolist())), part9.download_rgba32f(w9, h9) if rank == 0 else None)
+    # PathLines (round Bezier curves): the NCCL list path with the curve kernels, poly-lines cut at the partition planes
+    pl = scenes.helix_pathlines(24)
+    vis_pl = dict(annotation="", lighting=dict(lights=[[1.0, 2.0, -3.0]], types=[2], n_ao=2, ao_radius=0.5, shadows=True, Ka=0.4, Kd=0.6),
+                  operators=[dict(type="PathLinesVis", dataset="lines", colormap=[[0.0, 0.0, 1.0, 0.0], [1.2, 1.0, 0.0, 1.0]],
+                                  opacitymap=[[0, 1], [1, 1]], data_range=None, radius0=0.01, radius1=0.05, value0=0.0, value1=1.2)])
+    cam_pl = dict(eye=[1.5, 1.0, -3.0], dir=[-1.5, -1.0, 3.0], up=[0.0, 1.0, 0.0], aov=35.0)
+    part_pl = scenes.build_partitions(gpu, vis_pl, {"lines": pl}, world, only_rank=rank, ctx=ctx)[0]
+    spl = gpu.render_device([part_pl], cam_pl, vis_pl["lighting"], w, h, 0.001)
+    t = torch.tensor([spl[k] for k in keys], dtype=torch.int64, device="cuda")
+    dist.all_reduce(t)
+    results["pathlines"] = (dict(zip(keys, t.tolist())), part_pl.download_rgba32f(w, h) if rank == 0 else None)
     ok = True
     if rank == 0:
         from oracle import oracle
+        o_pl = scenes.build_partitions(oracle, vis_pl, {"lines": pl}, world)
+        fb_opl, st_opl = oracle.render(o_pl, cam_pl, vis_pl["lighting"], w, h, 0.001)
         full, _ = scenes.c5_partition_mesh(n_lat, n_lon, 1, 0)
         o_parts = scenes.build_partitions(oracle, vis, {"mesh": full}, world)
         fb_o, st_o = oracle.render(o_parts, cam, vis["lighting"], w, h, 0.001)
         o9 = scenes.build_partitions(oracle, vis9, ds9, world)
         fb_o9, st_o9 = oracle.render(o9, cam9, vis9["lighting"], w9, h9, st9["epsilon"])
         for mode, (st, fb) in results.items():
-            ref_fb, ref_st = (fb_o9, st_o9) if mode == "nineBalls" else (fb_o, st_o)
+            ref_fb, ref_st = (fb_o9, st_o9) if mode == "nineBalls" else (fb_opl, st_opl) if mode == "pathlines" else (fb_o, st_o)
             frac = float((np.abs(fb[..., :3] - ref_fb[..., :3]).max(-1) <= 1.0 / 255).mean())
             same = all(st[k] == ref_st[k] for k in st)
             print(json.dumps({"mode": mode, "world": world, "fraction_within_1_255": frac, "stats_equal": same, "gpu": st,
