@@ -10,7 +10,13 @@
  * citations are in gxy_oracle.cpp, relative to the reference tree).  Parity pin: the oracle's
  * renders of the reference's tests/ state files are compared against the reference's gold
  * PNGs (tests/golden/, see tests/test_oracle_golds.py) and against the reference's own
- * vendored Embree 3.6.1 compiled into oracle/_ref (tests/test_oracle_embree.py).
+ * vendored Embree 3.6.1 compiled into oracle/_ref (tests/test_oracle_embree.py for triangles,
+ * tests/test_oracle_curves.py for the round Bezier curves of PathLines) and its own Box.cpp
+ * (tests/test_oracle_box.py).
+ * PARITY UNPINNED for the Sampler part (gxo_sample*, src/sampler): the reference holds no golden
+ * data for it and its kernels are ISPC, which cannot be compiled here; that part is checked
+ * against closed-form properties only (tests/test_sampler.py).  The PathLines curve BUILDER
+ * (gxo_build_curves) has a closed-form test only; the curve INTERSECTOR is pinned by Embree.
  *
  * Floating point convention (shared with the CUDA path so both can be compared tightly):
  * IEEE fp32, round-to-nearest, true divides and square roots, NO contraction of a*b+c into
