@@ -264,6 +264,11 @@ struct gxy_vis {
   int neighbors[6];
   std::vector<VolOp> vols;
   std::vector<GeomOp> geoms;
+  // interactive frame path (gxy_render_progressive): displayed image, per-pixel frame stamps, pixels touched by the last frame
+  float *prog_image = nullptr;
+  int *prog_kbuffer = nullptr;
+  unsigned char *prog_touched = nullptr;
+  int prog_w = 0, prog_h = 0, prog_frame = -1;
   std::vector<SamplerOp> samplers;  // a sampling Visualization (src/sampler) holds only these
   SamplerParams SP;
   float *d_samples = nullptr;       // xyz of the samples collected by gxy_sample
@@ -528,6 +533,9 @@ void gxy_vis_destroy(gxy_vis *v) {
   v->hit_index.release(); v->block_sums.release(); v->small.release(); v->counters.release();
   if (v->d_samples) cudaFree(v->d_samples);
   if (v->d_sample_count) cudaFree(v->d_sample_count);
+  if (v->prog_image) cudaFree(v->prog_image);
+  if (v->prog_kbuffer) cudaFree(v->prog_kbuffer);
+  if (v->prog_touched) cudaFree(v->prog_touched);
   v->fb.release(); v->fb_tmp.release(); v->rgba8.release(); v->io_f.release(); v->io_i.release();
   if (v->ctx->copy_stream) cudaStreamSynchronize(v->ctx->copy_stream);
   for (int s = 0; s < 2; s++) {
@@ -1888,6 +1896,87 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
     GXY_CHECK(t.error == 0, "device error flag %d (1: BVH traversal stack overflow, 3: ray list / inbox capacity, 4: peer barrier timeout, 6: TMA copy did not complete)", t.error);
   }
   if (stats) *stats = S;
+  return 0;
+}
+
+// ---- interactive frame path (Rendering.cpp:104-153) -----------------------------------------------
+int gxy_progressive_reset(gxy_vis *v) {
+  GXY_CHECK(v, "NULL visualization");
+  if (use_device(v->ctx)) return 1;
+  if (v->prog_image) {
+    const size_t npix = (size_t)v->prog_w * v->prog_h;
+    GXY_CUDA(cudaMemsetAsync(v->prog_image, 0, sizeof(float) * 4 * npix, v->ctx->stream));
+    GXY_CUDA(cudaMemsetAsync(v->prog_kbuffer, 0, sizeof(int) * npix, v->ctx->stream));
+    GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  }
+  v->prog_frame = -1;
+  return 0;
+}
+
+int gxy_render_progressive(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const gxy_lighting *lights, int w, int h, float epsilon,
+                           int frame, gxy_stats *stats) {
+  GXY_CHECK(nparts >= 1 && parts && cam && lights && w > 0 && h > 0, "gxy_render_progressive: bad arguments");
+  for (int p = 0; p < nparts; p++) {
+    if (check_vis(parts[p])) return 1;
+    GXY_CHECK(parts[p]->ctx->comm == nullptr, "gxy_render_progressive drives all partitions from one process (no communicator)");
+    GXY_CHECK(parts[p]->ctx->device == parts[0]->ctx->device, "gxy_render_progressive: all partitions of one call live on one device");
+  }
+  gxy_vis *own = parts[0];
+  if (use_device(own->ctx)) return 1;
+  cudaStream_t st = own->ctx->stream;
+  const size_t npix = (size_t)w * h;
+  if (!own->prog_image || own->prog_w != w || own->prog_h != h) {  // Rendering::local_commit (:218-238)
+    if (own->prog_image) cudaFree(own->prog_image);
+    if (own->prog_kbuffer) cudaFree(own->prog_kbuffer);
+    if (own->prog_touched) cudaFree(own->prog_touched);
+    own->prog_image = nullptr; own->prog_kbuffer = nullptr; own->prog_touched = nullptr;
+    GXY_CUDA(cudaMalloc(&own->prog_image, sizeof(float) * 4 * npix));
+    GXY_CUDA(cudaMalloc(&own->prog_kbuffer, sizeof(int) * npix));
+    GXY_CUDA(cudaMalloc(&own->prog_touched, npix));
+    own->prog_w = w; own->prog_h = h;
+    if (gxy_progressive_reset(own)) return 1;
+  }
+  if (stats) memset(stats, 0, sizeof *stats);
+  if (frame < own->prog_frame) return 0;  // AddLocalPixels :138: the pixels of a stale frame are dropped
+  if (gxy_render(nparts, parts, cam, lights, w, h, epsilon, stats)) return 1;
+  // the pixels this frame wrote: those for which some partition originated a primary ray
+  const DevCamera C = make_dev_camera(*cam, w, h);
+  GXY_CUDA(cudaMemsetAsync(own->prog_touched, 0, npix, st));
+  for (int p = 0; p < nparts; p++) {
+    gxy_vis *v = parts[p];
+    if (v->cur.reserve(npix, false, st) || v->block_sums.reserve(npix / 1024 + 2) || v->small.reserve(64)) return 1;
+    if (launch_generate(v->P, C, w, h, false, v->cur.v, nullptr, v->block_sums.p, v->small.p, v->ctx->stream)) return 1;
+    int n = 0;
+    GXY_CUDA(cudaMemcpyAsync(&n, v->small.p, sizeof(int), cudaMemcpyDeviceToHost, v->ctx->stream));
+    GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    if (launch_mark_touched(v->cur.v, n, w, own->prog_touched, st)) return 1;
+    GXY_CUDA(cudaStreamSynchronize(st));
+  }
+  GXY_CHECK(own->fb_result, "gxy_render_progressive: no frame on the image owner");
+  if (launch_merge_stamped(own->fb_result, own->prog_image, own->prog_kbuffer, own->prog_touched, (int)npix, frame, st)) return 1;
+  GXY_CUDA(cudaStreamSynchronize(st));
+  if (frame > own->prog_frame) own->prog_frame = frame;
+  if (stats) stats->kernel_launches += 4 * nparts + 1;
+  return 0;
+}
+
+int gxy_progressive_download_rgba32f(gxy_vis *v, float *fb) {
+  GXY_CHECK(v && fb, "gxy_progressive_download_rgba32f: NULL argument");
+  GXY_CHECK(v->prog_image, "no progressive frame yet (call gxy_render_progressive)");
+  if (use_device(v->ctx)) return 1;
+  GXY_CUDA(cudaMemcpy(fb, v->prog_image, sizeof(float) * 4 * (size_t)v->prog_w * v->prog_h, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int gxy_progressive_download_rgba8(gxy_vis *v, unsigned char *rgba) {
+  GXY_CHECK(v && rgba, "gxy_progressive_download_rgba8: NULL argument");
+  GXY_CHECK(v->prog_image, "no progressive frame yet (call gxy_render_progressive)");
+  if (use_device(v->ctx)) return 1;
+  const size_t npix = (size_t)v->prog_w * v->prog_h;
+  if (v->rgba8.reserve(npix * 4)) return 1;
+  if (launch_tonemap(v->prog_image, v->prog_w, v->prog_h, v->rgba8.p, v->ctx->stream)) return 1;
+  GXY_CUDA(cudaMemcpyAsync(rgba, v->rgba8.p, npix * 4, cudaMemcpyDeviceToHost, v->ctx->stream));
+  GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
   return 0;
 }
 

@@ -53,6 +53,13 @@ struct SamplerParams {
 int launch_sampler_trace(const SamplerParams &SP, Rays R, int n, float *samples, unsigned long long *sample_count,
                          unsigned long long sample_cap, cudaStream_t st);
 
+// ---- frame-stamped accumulation of the interactive frame path (gxy_progressive.cu; Rendering.cpp:104-153) ----------
+// touched[y*w+x] = 1 for every ray of the list
+int launch_mark_touched(Rays R, int n, int w, unsigned char *touched, cudaStream_t st);
+// per touched pixel: stamp older than `frame` -> image = frame_sum, stamp = frame; else image += frame_sum
+int launch_merge_stamped(const float *frame_sum, float *image, int *kbuffer, const unsigned char *touched, int npix, int frame,
+                         cudaStream_t st);
+
 // ---- TMA-staged volume march (gxy_march_tma.cu) ---------------------------------------------------------
 // one float volume operator, no geometry, < 2^31 voxels, x dimension a multiple of 4 (TMA strides are multiples of 16 bytes)
 bool march_tma_eligible(const SceneParams &P);

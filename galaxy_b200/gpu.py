@@ -86,6 +86,11 @@ def lib():
         L.gxy_pathlines_destroy.argtypes = [vp]
         L.gxy_build_curves.argtypes = [C.c_int, fp, fp, C.c_int, ip, C.c_float, C.c_float, C.c_float, C.c_float, fp]
         L.gxy_vis_add_pathlines.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(TransferFunction)]
+        L.gxy_render_progressive.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(Camera), C.POINTER(Lighting), C.c_int, C.c_int, C.c_float,
+                                             C.c_int, C.POINTER(Stats)]
+        L.gxy_progressive_download_rgba32f.argtypes = [vp, fp]
+        L.gxy_progressive_download_rgba8.argtypes = [vp, C.POINTER(C.c_ubyte)]
+        L.gxy_progressive_reset.argtypes = [vp]
         L.gxy_vis_add_sampler.argtypes = [vp, vp, C.c_int, C.c_float]
         L.gxy_sample_raylist.argtypes = [vp, RayListView]
         L.gxy_sample.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(Camera), C.c_int, C.c_int, C.POINTER(Stats)]
@@ -395,6 +400,21 @@ def pinned_array(shape, dtype):
 
 
 _PINNED_OWNERS = {}
+
+
+def render_progressive(parts, camera, lighting, w, h, frame, epsilon=0.001):
+    """The interactive frame path (gxy_render_progressive): the displayed image lives on parts[0] across calls.
+    Returns (displayed image float32 (h,w,4) y-up, stats dict)."""
+    arr = (C.c_void_p * len(parts))(*[p.h for p in parts])
+    cam, L, st = make_camera(camera), make_lighting(lighting), Stats()
+    check(lib().gxy_render_progressive(len(parts), arr, C.byref(cam), C.byref(L), w, h, epsilon, frame, C.byref(st)))
+    fb = np.empty((h, w, 4), np.float32)
+    check(lib().gxy_progressive_download_rgba32f(parts[0].h, _f(fb)))
+    return fb, st.as_dict()
+
+
+def progressive_reset(part):
+    check(lib().gxy_progressive_reset(part.h))
 
 
 def sample(parts, camera, w, h):

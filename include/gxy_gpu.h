@@ -197,6 +197,21 @@ int  gxy_generate_rays(gxy_vis *, const gxy_camera *, int w, int h, gxy_raylist_
 int  gxy_intersect(gxy_vis *, int n, const float *org3, const float *dir3, const float *tnear,
                    const float *tfar, int *geom_prim2, float *tuv3);
 
+/* ---- interactive / asynchronous frame path ------------------------------------------------ */
+/* Rendering::AddLocalPixels + ACCUMULATE_PIXEL as built without GXY_WRITE_IMAGES (src/renderer/Rendering.cpp:104-153),
+ * what gxyviewer displays: the image and a per-pixel frame stamp live on parts[0] across calls and are never cleared.
+ * Frame `frame` is rendered as gxy_render renders it; then every pixel that received a contribution takes the new value
+ * if its stamp is older (reset + adds) or adds it (the same frame number again), every other pixel keeps what it shows.
+ * A frame older than the newest one seen is dropped (AddLocalPixels :138).  A change of w x h re-allocates (local_commit).
+ * One process; parts as for gxy_render. */
+int  gxy_render_progressive(int nparts, gxy_vis *const *parts, const gxy_camera *, const gxy_lighting *, int w, int h,
+                            float epsilon, int frame, gxy_stats *stats);
+/* the displayed image: float RGBA, y up (w*h*4 floats) / RGBA8 rows top-down as ColorImageWriter writes them */
+int  gxy_progressive_download_rgba32f(gxy_vis *, float *fb);
+int  gxy_progressive_download_rgba8(gxy_vis *, unsigned char *rgba);
+/* Rendering::local_reset (:240-256): image and stamps to zero, current frame to -1 */
+int  gxy_progressive_reset(gxy_vis *);
+
 /* ---- Sampler (src/sampler) ---------------------------------------------------------------- */
 /* A sampling Visualization holds only sampler operators (SamplerTraceRays.ispc:128-222 calls every volumeVis through the
  * SamplerVis function table).  kind 0 = GradientSamplerVis, param = "tolerance" (GradientSamplerVis.cpp:77-85): a sample

@@ -1538,10 +1538,14 @@ int gxo_generate_rays(gxo_scene *s, const gxo_camera *cam, int w, int h, float *
 // Sampler::Trace -> SamplerTraceRays and Sampler::HandleTerminatedRays -> one particle per ray whose term has RAY_SURFACE;
 // such a PRIMARY ray is KEEP_HERE (Renderer::Classify: neither BOUNDARY nor OPAQUE) and is traced again from its new t,
 // so a ray leaves one sample per crossing until it reaches the boundary of the partition and moves on.
+// kbuffer != NULL: the interactive / asynchronous frame path (Rendering.cpp:104-153 without GXY_WRITE_IMAGES): fb and kbuffer
+// persist across frames, nothing is cleared up front; a batch of pixels of frame f is dropped when f < *rendering_frame
+// (AddLocalPixels :140-152), else every contribution first resets its pixel if the pixel's stamp is older (ACCUMULATE_PIXEL).
 static int render_impl(bool sampler, int nparts, gxo_scene **parts, const gxo_camera *cam, const gxo_lighting *lights_in, int w, int h,
-                       float epsilon, int max_rays_per_packet, int nthreads, float *fb, gxo_stats *stats) {
+                       float epsilon, int max_rays_per_packet, int nthreads, float *fb, gxo_stats *stats, int *kbuffer = nullptr,
+                       int frame = 0, int *rendering_frame = nullptr) {
   gxo_stats st; memset(&st, 0, sizeof st);
-  if (fb) memset(fb, 0, sizeof(float) * 4 * (size_t)w * h);
+  if (fb && !kbuffer) memset(fb, 0, sizeof(float) * 4 * (size_t)w * h);
   if (sampler) for (int p = 0; p < nparts; p++) parts[p]->samples.clear();
   gxo_lighting L;
   gxo_resolve_lights(lights_in, cam, &L);
@@ -1632,7 +1636,13 @@ static int render_impl(bool sampler, int nparts, gxo_scene **parts, const gxo_ca
       for (int i = 0; i < R.n; i++) {
         int c = R.classification[i];
         if (c == TERMINATED && !sampler) {
-          float *ptr = fb + (((size_t)R.y[i] * w + R.x[i]) << 2);
+          const size_t offset = (size_t)R.y[i] * w + R.x[i];
+          float *ptr = fb + (offset << 2);
+          if (kbuffer) {
+            if (!(frame >= *rendering_frame)) continue;          // a stale frame's pixels are dropped (:140)
+            if (frame > *rendering_frame) *rendering_frame = frame;
+            if (kbuffer[offset] < frame) { ptr[0] = ptr[1] = ptr[2] = ptr[3] = 0.f; kbuffer[offset] = frame; }
+          }
           ptr[0] += R.r[i]; ptr[1] += R.g[i]; ptr[2] += R.b[i]; ptr[3] += R.o[i];
           st.terminated_rays++;
         } else if (c == KEEP_HERE) nKeepers++;
@@ -1662,6 +1672,12 @@ extern "C" {
 int gxo_render(int nparts, gxo_scene **parts, const gxo_camera *cam, const gxo_lighting *lights_in, int w, int h, float epsilon,
                int max_rays_per_packet, int nthreads, float *fb, gxo_stats *stats) {
   return render_impl(false, nparts, parts, cam, lights_in, w, h, epsilon, max_rays_per_packet, nthreads, fb, stats);
+}
+
+int gxo_render_progressive(int nparts, gxo_scene **parts, const gxo_camera *cam, const gxo_lighting *lights_in, int w, int h, float epsilon,
+                           int nthreads, int frame, float *fb_inout, int *kbuffer_inout, int *rendering_frame_inout, gxo_stats *stats) {
+  return render_impl(false, nparts, parts, cam, lights_in, w, h, epsilon, 0, nthreads, fb_inout, stats, kbuffer_inout, frame,
+                     rendering_frame_inout);
 }
 
 int gxo_sample(int nparts, gxo_scene **parts, const gxo_camera *cam, int w, int h, int max_rays_per_packet, int nthreads,

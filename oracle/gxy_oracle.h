@@ -163,6 +163,14 @@ int gxo_sample(int nparts, gxo_scene **parts, const gxo_camera *, int w, int h, 
 /* the samples of one partition after gxo_sample: returns their number, *xyz = 3 floats per sample (owned by the scene) */
 long long gxo_scene_samples(gxo_scene *, const float **xyz);
 
+/* The interactive / asynchronous frame path (Rendering::AddLocalPixels + ACCUMULATE_PIXEL without GXY_WRITE_IMAGES,
+ * Rendering.cpp:104-153): the framebuffer (w*h*4 floats), the per-pixel frame stamps `kbuffer` (w*h ints, 0 after
+ * Rendering::local_commit / local_reset :233-254) and the rendering's current frame (initially -1, :57) persist across calls.  Nothing is cleared: a
+ * contribution of frame f resets its pixel first if the pixel's stamp is older; contributions of a frame older than the
+ * rendering's current one are dropped. */
+int gxo_render_progressive(int nparts, gxo_scene **parts, const gxo_camera *, const gxo_lighting *, int w, int h, float epsilon,
+                           int nthreads, int frame, float *fb_inout, int *kbuffer_inout, int *rendering_frame_inout, gxo_stats *stats);
+
 /* ColorImageWriter::Write (ImageWriter.cpp:30-48): float RGBA (y up) -> RGBA8 rows top-down,
  * truncating (unsigned char)(255*f) with x86 cvttss2si + low-byte semantics. */
 void gxo_fb_to_rgba8(const float *fb, int w, int h, unsigned char *out);

@@ -57,6 +57,8 @@ def lib():
         L.gxo_scene_add_pathlines_vis.argtypes = [vp, C.c_int, fp, fp, C.c_int, ip, C.c_float, C.c_float, C.c_float, C.c_float, fp, fp,
                                                   C.c_float, C.c_float]
         L.gxo_build_curves.argtypes = [C.c_int, fp, fp, C.c_int, ip, C.c_float, C.c_float, C.c_float, C.c_float, fp]
+        L.gxo_render_progressive.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(Camera), C.POINTER(Lighting), C.c_int, C.c_int, C.c_float,
+                                             C.c_int, C.c_int, fp, ip, ip, C.POINTER(Stats)]
         L.gxo_scene_add_sampler_vis.argtypes = [vp, C.c_int, ip, fp, fp, C.c_int, vp, C.c_int, C.c_float]
         L.gxo_sample_raylist.argtypes = [vp, fp, C.c_int, C.c_int]
         L.gxo_sample.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(Camera), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Stats)]
@@ -238,6 +240,24 @@ def render(parts, camera, lighting, w, h, epsilon=0.001, max_rays_per_packet=100
     rc = lib().gxo_render(len(parts), arr, C.byref(cam), C.byref(L), w, h, epsilon, max_rays_per_packet, nthreads, _f(fb), C.byref(st))
     assert rc == 0
     return fb, st.as_dict()
+
+
+class ProgressiveRendering:
+    """the state a Rendering keeps on the interactive path: framebuffer, per-pixel frame stamps, current frame (Rendering.cpp:55-58,218-256)"""
+
+    def __init__(self, w, h):
+        self.w, self.h = w, h
+        self.fb = np.zeros((h, w, 4), np.float32)
+        self.kbuffer = np.zeros((h, w), np.int32)
+        self.frame = np.array([-1], np.int32)
+
+    def render(self, parts, camera, lighting, frame, epsilon=0.001, nthreads=0):
+        arr = (C.c_void_p * len(parts))(*[p.h for p in parts])
+        cam, L, st = make_camera(camera), make_lighting(lighting), Stats()
+        rc = lib().gxo_render_progressive(len(parts), arr, C.byref(cam), C.byref(L), self.w, self.h, epsilon, nthreads, frame, _f(self.fb),
+                                          _i(self.kbuffer), _i(self.frame), C.byref(st))
+        assert rc == 0
+        return self.fb.copy(), st.as_dict()
 
 
 def sample(parts, camera, w, h, max_rays_per_packet=1000000, nthreads=0):

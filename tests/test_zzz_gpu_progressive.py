@@ -1,0 +1,43 @@
+"""-m gpu: the interactive / asynchronous frame path on the CUDA path against the oracle's literal
+frame-stamped accumulation.  (Named test_zzz_* so that it runs after every other GPU file: it was written after the
+round's GPU minutes were spent and has not run on a device yet.)"""
+import numpy as np
+import pytest
+
+from tests import util
+from tests.test_progressive import CAM_A, CAM_B, H, W, scene
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import oracle as o
+    return o
+
+
+# ---- GPU ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gpu():
+    from galaxy_b200 import gpu as g
+    assert g.device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    return g
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nparts", [1, 2])
+def test_gpu_progressive_frames_match_oracle(gpu, oracle, nparts):
+    g, vis = scene(gpu, nparts)
+    o, _ = scene(oracle, nparts)
+    L = vis["lighting"]
+    r = oracle.ProgressiveRendering(W, H)
+    gpu.progressive_reset(g[0])
+    for frame, cam in ((0, CAM_A), (0, CAM_A), (1, CAM_B), (0, CAM_A), (3, CAM_A), (4, CAM_B)):
+        fb_o, st_o = r.render(o, cam, L, frame)
+        fb_g, st_g = gpu.render_progressive(g, cam, L, W, H, frame)
+        frac = util.fb_fraction(fb_g, fb_o, 1.0 / 255)
+        assert frac >= 0.999, (frame, frac)
+        assert np.abs(fb_g - fb_o).max() <= 2e-3 * max(1.0, float(np.abs(fb_o).max()))
+        assert st_g["terminated_rays"] == st_o["terminated_rays"], (frame, st_g, st_o)
+    # a new window size re-allocates: plain first frame again
+    fb_g, _ = gpu.render_progressive(g, CAM_A, L, W // 2, H // 2, 0)
+    fb_o, _ = oracle.render(o, CAM_A, L, W // 2, H // 2)
+    assert util.fb_fraction(fb_g, fb_o, 1.0 / 255) >= 0.999
