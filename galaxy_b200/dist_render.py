@@ -12,7 +12,8 @@ and per wave
 and one reduce of the partial framebuffers to rank 0 at the end.  It is what INTEGRATION.md section 4
 describes (the reference's own loop running unchanged on the new trace call), it is how the N>1 path is
 covered on CPU (gloo, world_size 2), and it is NOT the fast path: `gxy_render` keeps everything on the
-devices and exchanges with NCCL.
+devices and exchanges with NCCL.  `sample_distributed` is the same loop for the Sampler (src/sampler): the way
+a sampling Visualization runs with one process per partition today (gxy_sample is single-process).
 """
 import numpy as np
 import torch
@@ -112,3 +113,78 @@ def render_distributed(scene, resolve_lights, camera, lighting, w, h, epsilon=0.
     s = torch.tensor([stats[k] for k in keys], dtype=torch.int64)
     dist.all_reduce(s, group=group)
     return (t.numpy() if rank == 0 else None), dict(zip(keys, s.tolist()))
+
+
+def _exchange(outgoing, rank, world, group):
+    """SendRaysMsg: counts first, then the columns; returns the lists received (incl. the ones addressed to this rank itself)"""
+    send = [np.concatenate(o, axis=1) if o else np.zeros((25, 0), np.float32) for o in outgoing]
+    counts = torch.tensor([s.shape[1] for s in send], dtype=torch.int64)
+    all_counts = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)
+    recv_counts = [int(all_counts[src][rank]) for src in range(world)]
+    recv = [torch.zeros((25, c), dtype=torch.float32) for c in recv_counts]
+    reqs = []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        if send[peer].shape[1]:
+            reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(send[peer])), peer, group=group))
+        if recv_counts[peer]:
+            reqs.append(dist.irecv(recv[peer], peer, group=group))
+    for r in reqs:
+        r.wait()
+    got = [send[rank]] if send[rank].shape[1] else []
+    got += [recv[peer].numpy() for peer in range(world) if peer != rank and recv_counts[peer]]
+    return got
+
+
+def sample_distributed(scene, camera, w, h, group=None):
+    """The Sampler (src/sampler/Sampler.cpp:52-133) with one partition per rank: per wave SamplerTraceRays on the local lists,
+    Classify, one sample per ray whose term has RAY_SURFACE (kept by THIS rank, as every rank keeps its own Particles), the
+    KEEP_HERE rays (those that left a sample) stay, the BOUNDARY rays move to their neighbour.  `scene` is this rank's
+    sampling Scene of either backend.  Returns (this rank's samples (n,3), stats dict summed over ranks)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    stats = dict(primary_rays=0, forwarded_rays=0, traced_rays=0, waves=0, samples=0)
+    rays, n = scene.generate_rays(camera, w, h)
+    stats["primary_rays"] = n
+    pending = [(rays, n)] if n else []
+    samples = []
+    while True:
+        keep = []
+        outgoing = [[] for _ in range(world)]
+        for rays, n in pending:
+            scene.sample_raylist(rays, n)
+            stats["traced_rays"] += n
+            stats["waves"] += 1
+            scene.classify(rays, n)
+            hit = (_icol(rays, "term", n) & 1) != 0  # RAY_SURFACE
+            if hit.any():
+                t = rays[COLS["t"], :n][hit]
+                samples.append(np.stack([rays[COLS["ox"], :n][hit] + t * rays[COLS["dx"], :n][hit],
+                                         rays[COLS["oy"], :n][hit] + t * rays[COLS["dy"], :n][hit],
+                                         rays[COLS["oz"], :n][hit] + t * rays[COLS["dz"], :n][hit]], 1).astype(np.float32))
+            cls = _icol(rays, "classification", n)
+            for dst in range(world):
+                m = cls == dst
+                if m.any():
+                    outgoing[dst].append(rays[:, :n][:, m].copy())
+                    stats["forwarded_rays"] += int(m.sum())
+            m = cls == KEEP_HERE
+            if m.any():
+                keep.append(rays[:, :n][:, m].copy())
+        keep += _exchange(outgoing, rank, world, group)
+        pending = []
+        if keep:
+            cols = np.concatenate(keep, axis=1)
+            for a in range(0, cols.shape[1], 1000000):
+                pending.append(_pack(cols[:, a:a + 1000000]))
+        left = torch.tensor([sum(n for _, n in pending)], dtype=torch.int64)
+        dist.all_reduce(left, group=group)
+        if int(left) == 0:
+            break
+    mine = np.concatenate(samples) if samples else np.zeros((0, 3), np.float32)
+    stats["samples"] = len(mine)
+    keys = sorted(stats)
+    s = torch.tensor([stats[k] for k in keys], dtype=torch.int64)
+    dist.all_reduce(s, group=group)
+    return mine, dict(zip(keys, s.tolist()))

@@ -22,6 +22,20 @@ def _worker(rank, world, port, case, out):
 
         from galaxy_b200 import dist_render, scenes
         from oracle import oracle
+        if case == "sampler":
+            vol = scenes.radial_volume("eightBalls", 48)
+            vis = dict(annotation="", lighting=scenes.parse_lighting(None),
+                       operators=[scenes.parse_operator({"type": "IsoSampler", "dataset": "v", "isovalue": 0.25})])
+            cam = dict(eye=[2.0, 1.5, -3.0], dir=[-2.0, -1.5, 3.0], up=[0.0, 1.0, 0.0], aov=35.0)
+            part = scenes.build_partitions(oracle, vis, {"v": vol}, world, only_rank=rank)[0]
+            mine, stats = dist_render.sample_distributed(part, cam, 96, 64)
+            np.save(out + ".samples%d.npy" % rank, mine)
+            if rank == 0:
+                ref, st_ref = oracle.sample(scenes.build_partitions(oracle, vis, {"v": vol}, world), cam, 96, 64)
+                for r in range(world):
+                    np.save(out + ".ref%d.npy" % r, ref[r])
+                json.dump({"dist": stats, "ref": st_ref}, open(out + ".json", "w"))
+            return
         if case == "mesh":
             vis, cam = scenes.c5_vis(), scenes.c5_camera()
             ds, _ = scenes.c5_partition_mesh(24, 48, world, rank)
@@ -57,3 +71,20 @@ def test_two_rank_gloo_loop_matches_single_process_oracle(tmp_path, case):
     assert st["dist"]["forwarded_rays"] > 0
     # same rays, same arithmetic; only the order of the framebuffer additions differs
     assert np.abs(fb - fb_ref).max() <= 1e-5
+
+
+def test_two_rank_gloo_sampler_matches_single_process_oracle(tmp_path):
+    """the Sampler with one partition per rank (dist_render.sample_distributed): every rank ends up with exactly the samples the
+    single-process oracle collects for its partition, and the ray statistics agree"""
+    import json
+    world, port = 2, 29700 + (os.getpid() % 200) + 2
+    out = str(tmp_path / "sampler")
+    mp.spawn(_worker, args=(world, port, "sampler", out), nprocs=world, join=True)
+    st = json.load(open(out + ".json"))
+    for k in ("primary_rays", "forwarded_rays", "traced_rays"):
+        assert st["dist"][k] == st["ref"][k], (k, st)
+    assert st["dist"]["forwarded_rays"] > 0 and st["dist"]["samples"] > 0
+    for r in range(world):
+        a, b = np.load(out + ".samples%d.npy" % r), np.load(out + ".ref%d.npy" % r)
+        a, b = a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))], b[np.lexsort((b[:, 2], b[:, 1], b[:, 0]))]
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), r
