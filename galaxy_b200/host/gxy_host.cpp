@@ -631,6 +631,10 @@ bool Vis::LoadFromJSON(const json::Value &v, const std::string &base_dir) {
         for (int k = 0; k < 4; k++) slices.push_back((float)v["plane"][k].GetDouble());
       }
       volume_render = v.HasMember("volume rendering") ? v["volume rendering"].GetBool() : false;
+    } else if (type == "GradientSamplerVis") {  // src/sampler/GradientSamplerVis.cpp:77-85
+      if (v.HasMember("tolerance")) tolerance = (float)v["tolerance"].GetDouble();
+    } else if (type == "IsoSamplerVis") {  // src/sampler/IsoSamplerVis.cpp:77-85
+      if (v.HasMember("isovalue")) isovalue = (float)v["isovalue"].GetDouble();
     } else if (type == "PathLinesVis") {  // PathLinesVis.cpp:46-55 (initialize), 105-114 (LoadFromJSON)
       radius0 = -1.0f; radius1 = 1.0f; value0 = 0.0f; value1 = 1.0f;
       if (v.HasMember("radius0")) radius0 = (float)v["radius0"].GetDouble();
@@ -776,7 +780,8 @@ bool Visualization::Commit(gxy_context *ctx, const Datasets &datasets, int npart
         }
         continue;
       }
-      if (op.type != "VolumeVis") {
+      const bool sampler_op = op.type == "GradientSamplerVis" || op.type == "IsoSamplerVis";
+      if (op.type != "VolumeVis" && !sampler_op) {
         std::cerr << op.type << " is not supported by this driver\n";
         return false;
       }
@@ -815,6 +820,13 @@ bool Visualization::Commit(gxy_context *ctx, const Datasets &datasets, int npart
         if (!check_abi(gxy_vis_set_partition(vis, gmin, gmax, lmin, lmax, nb), "gxy_vis_set_partition")) return false;
         boxes_set = true;
       }
+      if (sampler_op) {  // a sampling Visualization (src/sampler): no transfer function, one parameter
+        if (!check_abi(gxy_vis_add_sampler(vis, dv, op.type == "IsoSamplerVis" ? GXY_SAMPLER_ISO : GXY_SAMPLER_GRADIENT,
+                                           op.type == "IsoSamplerVis" ? op.isovalue : op.tolerance),
+                       "gxy_vis_add_sampler"))
+          return false;
+        continue;
+      }
       gxy_transfer_function tf;
       if (!check_abi(gxy_resample_transfer_function((int)op.colormap.size() / 4, op.colormap.data(), (int)op.opacitymap.size() / 2,
                                                     op.opacitymap.data(), &tf),
@@ -831,6 +843,24 @@ bool Visualization::Commit(gxy_context *ctx, const Datasets &datasets, int npart
     if (!check_abi(gxy_vis_commit(vis), "gxy_vis_commit")) return false;
   }
   return true;
+}
+
+// ---- Sampler -------------------------------------------------------------------------------------
+bool Sampler::Sample(const Camera &camera, Visualization &visualization, int width, int height) {
+  if (visualization.parts.empty()) {
+    std::cerr << "Sampler::Sample: the Visualization is not committed\n";
+    return false;
+  }
+  const gxy_camera cam = camera.AsABI();
+  return check_abi(gxy_sample((int)visualization.parts.size(), visualization.parts.data(), &cam, width, height, &stats), "gxy_sample");
+}
+
+bool Sampler::GetSamples(const Visualization &visualization, int r, std::vector<float> &xyz) const {
+  if (r < 0 || (size_t)r >= visualization.parts.size()) return false;
+  long long n = 0;
+  if (!check_abi(gxy_vis_sample_count(visualization.parts[(size_t)r], &n), "gxy_vis_sample_count")) return false;
+  xyz.resize(3 * (size_t)n);
+  return check_abi(gxy_vis_download_samples(visualization.parts[(size_t)r], xyz.data()), "gxy_vis_download_samples");
 }
 
 // ---- Renderer / Rendering ------------------------------------------------------------------------
@@ -977,6 +1007,13 @@ std::string describe_state(const Renderer &r, const std::vector<Camera> &cams, c
       put_floats(o, op.isovalues.data(), op.isovalues.size());
       o << ", \"slices\": ";
       put_floats(o, op.slices.data(), op.slices.size());
+      o << ", \"tolerance\": ";
+      put_floats(o, &op.tolerance, 1);
+      o << ", \"isovalue\": ";
+      put_floats(o, &op.isovalue, 1);
+      o << ", \"radii\": ";
+      const float rr[4] = {op.radius0, op.radius1, op.value0, op.value1};
+      put_floats(o, rr, 4);
       o << ", \"volume_render\": " << (op.volume_render ? "true" : "false") << ", \"range\": ";
       const float rg[2] = {op.has_range ? op.range[0] : op.colormap[0], op.has_range ? op.range[1] : op.colormap[op.colormap.size() - 4]};
       put_floats(o, rg, 2);

@@ -98,7 +98,7 @@ class Lighting {
 };
 
 struct Vis {
-  std::string type;     // "VolumeVis" | "TrianglesVis" | "ParticlesVis" | "PathLinesVis"
+  std::string type;     // "VolumeVis" | "TrianglesVis" | "ParticlesVis" | "PathLinesVis" | "GradientSamplerVis" | "IsoSamplerVis"
   std::string dataset;
   std::vector<float> colormap;    // n x (x,r,g,b)
   std::vector<float> opacitymap;  // m x (x,o)
@@ -108,6 +108,7 @@ struct Vis {
   bool volume_render = false;
   // ParticlesVis defaults (ParticlesVis.cpp:46-55,104-118); a PathLinesVis starts from -1, 1, 0, 1 (PathLinesVis.cpp:46-55)
   float radius0 = 0.025f, radius1 = 0.f, value0 = 0.f, value1 = 0.f;
+  float tolerance = 0.f, isovalue = 0.f;  // GradientSamplerVis.cpp:77-85 / IsoSamplerVis.cpp:77-85 (a sampling Visualization, src/sampler)
   // base_dir: where a "colormap" / "transfer function" given as a file name (ParaView JSON, MappedVis.cpp:104-166) is looked up
   bool LoadFromJSON(const json::Value &v, const std::string &base_dir = "");
 };
@@ -128,6 +129,17 @@ class Visualization {
   std::vector<gxy_triangles *> owned_triangles;
   std::vector<gxy_particles *> owned_particles;
   std::vector<gxy_pathlines *> owned_pathlines;
+};
+
+// Sampler (src/sampler/Sampler.h:34-72): a Renderer whose rays leave Particles where a sampler operator fires.  The
+// Visualization must hold only GradientSampler / IsoSampler operators; the samples stay on the device, per partition.
+class Sampler {
+ public:
+  // one frame of camera rays over all partitions of `visualization` (Sampler::Trace + HandleTerminatedRays, Sampler.cpp:52-133)
+  bool Sample(const Camera &camera, Visualization &visualization, int width, int height);
+  // Sampler::GetSamples: xyz of the samples of partition r (host copy) / as a device Particles dataset for a ParticlesVis
+  bool GetSamples(const Visualization &visualization, int r, std::vector<float> &xyz) const;
+  gxy_stats stats;
 };
 
 class Renderer {

@@ -88,6 +88,32 @@ int main(int argc, char *argv[]) {
   for (auto &c : theCameras)
     for (auto &v : theVisualizations) {
       if (skip && (k % skip) != 0) { std::cerr << "S"; k++; continue; }
+      // a sampling Visualization (only GradientSampler / IsoSampler operators, src/sampler): there is nothing to render; the rays
+      // of this camera leave samples, written as <base>_%05d.samples (raw float32 xyz, partition after partition).  Not part of
+      // the reference's gxywriter, which cannot load such a Visualization at all: the Sampler is driven from its GUI server.
+      bool sampling = !v.operators.empty();
+      for (const auto &op : v.operators) sampling = sampling && (op.type == "GradientSamplerVis" || op.type == "IsoSamplerVis");
+      if (sampling) {
+        gxy::Sampler theSampler;
+        if (!theSampler.Sample(c, v, override_windowsize ? width : c.width, override_windowsize ? height : c.height)) { std::cerr << "error sampling\n"; return 1; }
+        char name[32];
+        snprintf(name, sizeof name, "_%05d.samples", index);
+        FILE *f = fopen((base + name).c_str(), "wb");
+        if (!f) { std::cerr << "error saving " << base << name << "\n"; return 1; }
+        long long total = 0;
+        for (size_t r = 0; r < v.parts.size(); r++) {
+          std::vector<float> xyz;
+          if (!theSampler.GetSamples(v, (int)r, xyz)) { fclose(f); return 1; }
+          if (!xyz.empty()) fwrite(xyz.data(), sizeof(float), xyz.size(), f);
+          total += (long long)(xyz.size() / 3);
+        }
+        fclose(f);
+        std::cout << "samples = " << total << std::endl;
+        rays += theSampler.stats.traced_rays;
+        index++;
+        k++;
+        continue;
+      }
       gxy::Rendering theRendering;
       theRendering.camera = &c;
       theRendering.visualization = &v;

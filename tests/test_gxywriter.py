@@ -231,3 +231,25 @@ def test_pvcc_camera_file(tmp_path):
     os.remove(os.path.join(tmp, "cam.pvcc"))
     out = subprocess.run([EXE, "--describe", state], capture_output=True, text=True, timeout=60)
     assert out.returncode != 0 and "unable to open" in out.stderr
+
+
+def test_sampler_and_pathlines_operators_parse(tmp_path):
+    """examples/noise.state of the reference asks for a GradientSampler; IsoSampler and PathLines keys and defaults
+    (GradientSamplerVis.cpp:77-85, IsoSamplerVis.cpp:77-85, PathLinesVis.cpp:46-55,105-114): C++ host == Python front end."""
+    tmp = str(tmp_path)
+    write_vol(os.path.join(tmp, "radial-oneBall.vol"), scenes.radial_volume("oneBall", 12))
+    doc = {"Datasets": [{"name": "scalar", "type": "Volume", "filename": "radial-oneBall.vol"}],
+           "Visualizations": [{"annotation": "", "operators": [{"type": "GradientSampler", "dataset": "scalar", "tolerance": 0.1, "volume rendering": False},
+                                                                {"type": "IsoSampler", "dataset": "scalar", "isovalue": 0.35},
+                                                                {"type": "IsoSampler", "dataset": "scalar"}]}],
+           "Cameras": [{"aov": 30.0, "viewpoint": [0.0, 0.0, -20.0], "viewdirection": [0.0, 0.0, 1.0], "viewup": [0.0, 1.0, 0.0]}]}
+    state = os.path.join(tmp, "noise.state")
+    json.dump(doc, open(state, "w"))
+    out = subprocess.run([EXE, "--describe", state], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    got = json.loads(out.stdout, parse_float=lambda t: float(np.float32(t)))
+    st = scenes.parse_state(doc, base_dir=tmp)
+    ops_g, ops_p = got["visualizations"][0]["operators"], st["visualizations"][0]["operators"]
+    assert [o["type"] for o in ops_g] == [o["type"] for o in ops_p] == ["GradientSamplerVis", "IsoSamplerVis", "IsoSamplerVis"]
+    assert ops_g[0]["tolerance"] == [ops_p[0]["tolerance"]] == [float(np.float32(0.1))]
+    assert ops_g[1]["isovalue"] == [ops_p[1]["isovalue"]] == [float(np.float32(0.35))] and ops_g[2]["isovalue"] == [0.0]

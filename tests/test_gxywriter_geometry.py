@@ -175,6 +175,8 @@ def test_pathlines_pieces_load_as_the_reference_loads_them(tmp_path, nparts, mod
     d = json.loads(out.stdout)
     g = d["geometries"][0]
     assert g["type"] == "PathLines" and len(g["parts"]) == nparts
+    op = d["visualizations"][0]["operators"][0]
+    assert op["type"] == "PathLinesVis" and np.array_equal(np.float32(op["radii"]), np.float32([0.01, 0.05, 0.0, 1.2]))
     for r in range(nparts):
         v, dat, c = pieces[r].to_arrays()
         pr = g["parts"][r]

@@ -41,3 +41,35 @@ def test_gpu_progressive_frames_match_oracle(gpu, oracle, nparts):
     fb_g, _ = gpu.render_progressive(g, CAM_A, L, W // 2, H // 2, 0)
     fb_o, _ = oracle.render(o, CAM_A, L, W // 2, H // 2)
     assert util.fb_fraction(fb_g, fb_o, 1.0 / 255) >= 0.999
+
+
+@pytest.mark.gpu
+def test_gxywriter_samples_a_sampling_visualization(gpu, tmp_path):
+    """gxywriter on a state whose Visualization holds only sampler operators: the .samples file holds the same set of points
+    the Python binding collects (C++ gxy::Sampler on top of gxy_sample)."""
+    import json
+    import os
+    import subprocess
+
+    from galaxy_b200 import scenes
+    from tests.test_gxywriter import EXE, write_vol
+    tmp = str(tmp_path)
+    vol = scenes.radial_volume("eightBalls", 48)
+    write_vol(os.path.join(tmp, "radial-eightBalls.vol"), vol)
+    doc = {"Datasets": [{"name": "v", "type": "Volume", "filename": "radial-eightBalls.vol"}],
+           "Visualizations": [{"operators": [{"type": "IsoSampler", "dataset": "v", "isovalue": 0.25}]}],
+           "Cameras": [{"aov": 35.0, "viewpoint": [2.0, 1.5, -3.0], "viewcenter": [0.0, 0.0, 0.0], "viewup": [0.0, 1.0, 0.0]}]}
+    state = os.path.join(tmp, "sampling.state")
+    json.dump(doc, open(state, "w"))
+    for nparts in (1, 2):
+        base = os.path.join(tmp, "s%d" % nparts)
+        out = subprocess.run([EXE, "-s", "96", "64", "-P", str(nparts), "-o", base, state], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        got = np.fromfile(base + "_00000.samples", np.float32).reshape(-1, 3)
+        st = scenes.parse_state(doc, base_dir=tmp)
+        ds = scenes.load_datasets(st, scenes.default_data_provider(data_dir=tmp))
+        parts = scenes.build_partitions(gpu, st["visualizations"][0], ds, nparts)
+        want, _ = gpu.sample(parts, st["cameras"][0], 96, 64)
+        want = np.concatenate(want)
+        a, b = got[np.lexsort((got[:, 2], got[:, 1], got[:, 0]))], want[np.lexsort((want[:, 2], want[:, 1], want[:, 0]))]
+        assert len(a) > 0 and a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
