@@ -73,3 +73,22 @@ def test_gxywriter_samples_a_sampling_visualization(gpu, tmp_path):
         want = np.concatenate(want)
         a, b = got[np.lexsort((got[:, 2], got[:, 1], got[:, 0]))], want[np.lexsort((want[:, 2], want[:, 1], want[:, 0]))]
         assert len(a) > 0 and a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_gpu_sampler_with_two_operators_matches_oracle(gpu, oracle):
+    """two sampler operators on two volumes in one sampling Visualization (the first that fires ends the step, the others are
+    not evaluated in it, SamplerTraceRays.ispc:195-204): same samples as the oracle at 1 and 2 partitions"""
+    from galaxy_b200 import scenes
+    from tests.test_sampler import CAM2, sorted_rows
+    vis = dict(annotation="", lighting=scenes.parse_lighting(None),
+               operators=[scenes.parse_operator({"type": "IsoSampler", "dataset": "a", "isovalue": 0.25}),
+                          scenes.parse_operator({"type": "GradientSampler", "dataset": "b", "tolerance": 0.6})])
+    ds = {"a": scenes.radial_volume("eightBalls", 48), "b": scenes.radial_volume("oneBall", 48)}
+    for nparts in (1, 2):
+        sg, st_g = gpu.sample(scenes.build_partitions(gpu, vis, ds, nparts), CAM2, 120, 90)
+        so, st_o = oracle.sample(scenes.build_partitions(oracle, vis, ds, nparts), CAM2, 120, 90)
+        assert st_g["traced_rays"] == st_o["traced_rays"] and st_g["forwarded_rays"] == st_o["forwarded_rays"]
+        for r in range(nparts):
+            a, b = sorted_rows(sg[r]), sorted_rows(so[r])
+            assert len(b) > 0 and a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (nparts, r)
