@@ -156,6 +156,47 @@ def volume_case(which):
             scenes.parse_camera({"viewpoint": [3, 2, -4], "viewcenter": [0, 0, 0], "viewup": [0, 1, 0], "aov": 30}))
 
 
+PL_LINES, PL_VERTS = 20000, 41    # --workload pl: 20 000 helical poly-lines x 40 segments = 800 000 round Bezier segments
+
+
+def pathlines_case():
+    """(visualization, camera) of the PathLines workload: thin data-mapped tubes, primary + 1 shadow ray"""
+    op = dict(type="PathLinesVis", dataset="lines", colormap=[[0.0, 0.0, 1.0, 0.0], [1.2, 1.0, 0.0, 1.0]], opacitymap=[[0, 1], [1, 1]], data_range=None,
+              radius0=0.002, radius1=0.008, value0=0.0, value1=1.2)
+    return (dict(annotation="", lighting=scenes.parse_lighting({"Sources": [[1, 2, -3, 0]], "shadows": True, "Ka": 0.4, "Kd": 0.6, "ao count": 0}),
+                 operators=[op]),
+            scenes.parse_camera({"viewpoint": [1.5, 1.0, -3.0], "viewcenter": [0, 0, 0], "viewup": [0, 1, 0], "aov": 35}))
+
+
+def pathlines_alg_bytes_per_ray(n_segments, hit_fraction):
+    """the C5 model with curve leaves: ray I/O + L 80-byte nodes + one leaf of 3 segments (48-byte record + 64 bytes of control points each)"""
+    import math
+    L = max(1, math.ceil(math.log(max(n_segments, 8) / 3.0, 8)))
+    return 76.0 + 28.0 * hit_fraction + 80.0 * L + 3 * (48.0 + 64.0), L
+
+
+def run_cpu_baseline_pathlines(steps, warmup, lines_div=20, sample_div=4):
+    """The oracle on a bounded sample of the PathLines workload: 1/lines_div of the lines, (1080p / sample_div^2) window."""
+    from oracle import oracle
+    vis, cam = pathlines_case()
+    ds = scenes.helix_pathlines(PL_LINES // lines_div, PL_VERTS)
+    parts = scenes.build_partitions(oracle, vis, {"lines": ds}, 1)
+    w, h = W // sample_div, H // sample_div
+    cores = os.cpu_count() or 1
+    times, rays = [], 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        fb, st = oracle.render(parts, cam, vis["lighting"], w, h, EPS, nthreads=cores)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+            rays = st["primary_rays"] + st["shadow_rays"] + st["ao_rays"]
+    t = float(np.mean(times))
+    sample = "oracle port; same camera/lighting, %dx%d window, %d segments (1/%d of the lines); %d rays/frame" % (
+        w, h, (PL_LINES // lines_div) * (PL_VERTS - 1), lines_div, rays)
+    return {"value": rays / t / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample}, t * 1e3
+
+
 def run_cpu_baseline_volume(which, steps, warmup, n=192, sample_div=4):
     """The oracle on a bounded sample of the volume workload: n^3 volume, (1080p / sample_div^2) window."""
     from oracle import oracle
@@ -207,8 +248,9 @@ def main():
     ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
     ap.add_argument("--tess-div", type=int, default=1, help="divide the C5 tessellation (debug only; 1 = the 100M-triangle workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "c4"],
-                    help="c5 (default, the headline): 100M-triangle mesh; c3: volume DVR; c4: volume isosurface + shadow rays")
+    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "c4", "pl"],
+                    help="c5 (default, the headline): 100M-triangle mesh; c3: volume DVR; c4: volume isosurface + shadow rays; "
+                         "pl: PathLines (800 000 round Bezier segments), primary + shadow")
     ap.add_argument("--volume-n", type=int, default=1024, help="c3/c4: voxels per axis of the synthetic volume")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -216,7 +258,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = args.gpus
     volume = args.workload in ("c3", "c4")
-    if volume:
+    pathlines = args.workload == "pl"
+    if pathlines:
+        workload = "PathLines: %d helical poly-lines, %d round Bezier segments of radius 0.002-0.008, 1920x1080, primary + shadow (1 light), spatial partitions=%d" % (
+            PL_LINES, PL_LINES * (PL_VERTS - 1), n_gpus)
+        metric = "Mrays/s, 1080p PathLines primary+shadow"
+    elif volume:
         workload = ("C3 noise volume %d^3 float32, 1920x1080, DVR only (no secondary rays), spatial partitions=%d" if args.workload == "c3" else
                     "C4 noise volume %d^3 float32, 1920x1080, isosurface 0.35 + shadow rays (1 light), spatial partitions=%d") % (args.volume_n, n_gpus)
         metric = "Mrays/s, 1080p volume march (%s)" % ("DVR" if args.workload == "c3" else "isosurface + shadow")
@@ -226,10 +273,15 @@ def main():
         metric = "Mrays/s, 1080p primary+shadow+AO"
     config = {"workload": workload, "width": W, "height": H, "partitions": n_gpus, "timing": "value: inputs larger than L2 (scene >> 126 MB) + 256 MB L2 flush between frames; e2e: inputs larger than L2 (~1 GB of DRAM traffic per frame), no explicit flush, image k downloads while frame k+1 renders"}
 
+    if pathlines:
+        config["timing"] = ("value: 256 MB L2 flush between frames; e2e: no explicit flush and the scene (about 90 MB of records and control points) "
+                            "fits the 126 MB L2, image k downloads while frame k+1 renders")
     if args.impl == "reference":
         if rank != 0:
             return
-        if volume:
+        if pathlines:
+            cb, ms = run_cpu_baseline_pathlines(max(1, args.steps), max(0, min(args.warmup, 1)))
+        elif volume:
             cb, ms = run_cpu_baseline_volume(args.workload, max(1, args.steps), max(0, min(args.warmup, 1)))
         else:
             cb, ms = run_cpu_baseline(max(1, args.steps), max(0, min(args.warmup, 1)))
@@ -258,7 +310,11 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0])
     t0 = time.perf_counter()
-    if volume:
+    if pathlines:
+        ds = scenes.helix_pathlines(PL_LINES, PL_VERTS)
+        vis, cam = pathlines_case()
+        dsets, n_tris_local = {"lines": ds}, 0
+    elif volume:
         ds = synth_volume(args.volume_n)
         vis, cam = volume_case(args.workload)
         dsets, n_tris_local = {"v": ds}, 0
@@ -362,6 +418,13 @@ def main():
                 "kernel": "gxy::primary_trace_kernel + gxy::fused_secondary_kernel (the two persistent trace launches of a frame)",
                 "traffic_note": "dram__bytes_read+write of the two trace launches of one frame, ncu --set full, profiles/r01_e_trace_kernels_full.txt", "peak_kind": peak_kind + " (burst copy figure)", "alg_bytes_per_ray": b_alg, "bvh_levels_model": levels,
                 "trace_share_of_step": trace_ms_max / max(1e-9, ms_max)}
+    if pathlines:
+        b_alg, levels = pathlines_alg_bytes_per_ray(info["n_prims"], hfrac)
+        achieved = traced * b_alg / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                    "kernel": "gxy::trace_kernel<0,true,false,true> (per-lane wide-BVH traversal with the round-Bezier curve test)",
+                    "peak_kind": peak_kind + " (burst copy figure)", "alg_bytes_per_ray": b_alg, "bvh_levels_model": levels,
+                    "trace_share_of_step": trace_ms_max / max(1e-9, ms_max)}
     if volume:
         # 16 algorithmic bytes per trilinear sample (4 new float voxels per step when rays are >= 1 voxel apart)
         achieved = samples * 16.0 / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
@@ -381,7 +444,7 @@ def main():
             "scene": {"triangles_this_rank": n_tris_local, "bvh_nodes": info["n_nodes"], "bvh_build_ms": info["build_ms"], "mesh_gen_s": t_gen,
                       "commit_s": t_commit}}
     if n_gpus == 1 and not args.no_cpu_baseline:
-        cb, _ = run_cpu_baseline_volume(args.workload, 2, 0) if volume else run_cpu_baseline(3, 0)
+        cb, _ = run_cpu_baseline_pathlines(2, 0) if pathlines else run_cpu_baseline_volume(args.workload, 2, 0) if volume else run_cpu_baseline(3, 0)
         line["cpu_baseline"] = cb
     print(json.dumps(line))
     if world > 1:
