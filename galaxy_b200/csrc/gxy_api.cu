@@ -982,7 +982,7 @@ int gxy_sample_raylist(gxy_vis *v, gxy_raylist_view rays) {
   if (check_vis(v)) return 1;
   if (rays.n == 0) return 0;
   if (h2d_rays(v, v->cur, rays)) return 1;
-  if (launch_sampler_trace(v->SP, v->cur.v, rays.n, nullptr, nullptr, 0, v->ctx->stream)) return 1;
+  if (launch_sampler_trace(v->SP, v->cur.v, rays.n, nullptr, nullptr, 0, nullptr, false, v->ctx->stream)) return 1;
   if (d2h_rays(v, v->cur, rays.base, rays.n, rays.aligned_n)) return 1;
   GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
   return 0;
@@ -1019,6 +1019,8 @@ int gxy_sample(int nparts, gxy_vis *const *parts, const gxy_camera *cam, int w, 
   const int npix = w * h;
   gxy_stats S;
   memset(&S, 0, sizeof S);
+  const char *le = getenv("GXY_SAMPLER_LOOP");
+  const bool loop_mode = le && atoi(le) != 0;
   gxy_context *ctx0 = parts[0]->ctx;
   struct EventPair {  // destroyed on every return path
     cudaEvent_t a = nullptr, b = nullptr;
@@ -1036,8 +1038,8 @@ int gxy_sample(int nparts, gxy_vis *const *parts, const gxy_camera *cam, int w, 
     cudaStream_t st = v->ctx->stream;
     const int npix_pad = ((w + 15) / 16) * ((h + 7) / 8) * 128;
     if (v->block_sums.reserve((size_t)std::max(npix_pad, 1 << 20) / 1024 + 2) || v->small.reserve(64 + 4 * (size_t)nparts)) return 1;
-    if (!v->d_sample_count) GXY_CUDA(cudaMalloc(&v->d_sample_count, sizeof(unsigned long long)));
-    GXY_CUDA(cudaMemsetAsync(v->d_sample_count, 0, sizeof(unsigned long long), st));
+    if (!v->d_sample_count) GXY_CUDA(cudaMalloc(&v->d_sample_count, 2 * sizeof(unsigned long long)));  // [0] samples [1] passes (loop mode)
+    GXY_CUDA(cudaMemsetAsync(v->d_sample_count, 0, 2 * sizeof(unsigned long long), st));
     v->n_samples = 0;
     if (v->cur.reserve(npix, false, st)) return 1;
     if (launch_generate(v->P, C, w, h, tiled_order(), v->cur.v, nullptr, v->block_sums.p, v->small.p, st)) return 1;
@@ -1058,8 +1060,33 @@ int gxy_sample(int nparts, gxy_vis *const *parts, const gxy_camera *cam, int w, 
       if (n == 0) continue;
       if (use_device(v->ctx)) return 1;
       cudaStream_t st = v->ctx->stream;
-      if (reserve_samples(v, v->n_samples + (unsigned long long)n, st)) return 1;  // at most one sample per ray and pass
-      if (launch_sampler_trace(v->SP, v->cur.v, n, v->d_samples, v->d_sample_count, v->samples_cap, st)) return 1;
+      if (!loop_mode) {
+        if (reserve_samples(v, v->n_samples + (unsigned long long)n, st)) return 1;  // at most one sample per ray and pass
+        if (launch_sampler_trace(v->SP, v->cur.v, n, v->d_samples, v->d_sample_count, v->samples_cap, nullptr, false, st)) return 1;
+      } else {
+        // GXY_SAMPLER_LOOP=1: all passes of a ray inside one launch.  The number of samples is not bounded by n any more: start with
+        // room for 4 per ray; if the kernel counted more than fit, grow to the exact count, restore t and run the launch again
+        if (v->io_f.reserve((size_t)n)) return 1;
+        GXY_CUDA(cudaMemcpyAsync(v->io_f.p, v->cur.v.t, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+        const unsigned long long before = v->n_samples;
+        if (reserve_samples(v, before + 4ull * (unsigned long long)n, st)) return 1;
+        for (int attempt = 0; attempt < 2; attempt++) {
+          GXY_CUDA(cudaMemsetAsync(v->d_sample_count + 1, 0, sizeof(unsigned long long), st));
+          if (launch_sampler_trace(v->SP, v->cur.v, n, v->d_samples, v->d_sample_count, v->samples_cap, v->d_sample_count + 1, true, st)) return 1;
+          unsigned long long cnt[2] = {0, 0};
+          GXY_CUDA(cudaMemcpyAsync(cnt, v->d_sample_count, sizeof cnt, cudaMemcpyDeviceToHost, st));
+          GXY_CUDA(cudaStreamSynchronize(st));
+          if (cnt[0] <= v->samples_cap) {
+            S.traced_rays += (long long)cnt[1] - n;  // the passes beyond the first (the first is counted below, as in the other mode)
+            break;
+          }
+          GXY_CHECK(attempt == 0, "gxy_sample: sample buffer still too small after growing to the counted size");
+          if (reserve_samples(v, cnt[0], st)) return 1;
+          GXY_CUDA(cudaMemcpyAsync(v->d_sample_count, &before, sizeof before, cudaMemcpyHostToDevice, st));
+          GXY_CUDA(cudaMemcpyAsync(v->cur.v.t, v->io_f.p, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+          GXY_CUDA(cudaStreamSynchronize(st));
+        }
+      }
       if (launch_classify(v->P, v->cur.v, n, st)) return 1;
       if (v->send.reserve((size_t)n, false, st)) return 1;
       int *d_counts = v->small.p + 8, *d_offsets = d_counts + nparts, *d_cursor = d_offsets + nparts + 1;

@@ -50,8 +50,10 @@ struct SamplerParams {
 };
 // SamplerTraceRays::Trace on n rays: t and term rewritten in place; samples != NULL: the hit points (xyz) are appended at
 // *sample_count (device counter, incremented for every hit; points beyond sample_cap are counted but not written)
+// loop (opt-in, GXY_SAMPLER_LOOP=1): a ray that left a sample does its next pass inside the kernel until it reaches the boundary;
+// *passes (device counter) += the passes made, the reference's traced-ray count.  Needs samples != NULL.
 int launch_sampler_trace(const SamplerParams &SP, Rays R, int n, float *samples, unsigned long long *sample_count,
-                         unsigned long long sample_cap, cudaStream_t st);
+                         unsigned long long sample_cap, unsigned long long *passes, bool loop, cudaStream_t st);
 
 // ---- frame-stamped accumulation of the interactive frame path (gxy_progressive.cu; Rendering.cpp:104-153) ----------
 // touched[y*w+x] = 1 for every ray of the list

@@ -15,9 +15,15 @@
 
 namespace gxy {
 
+// LOOP = false: one pass per ray, as the reference's kernel.  LOOP = true (GXY_SAMPLER_LOOP=1, opt-in): a ray that left a sample is
+// KEEP_HERE in Renderer::Classify and would come straight back with t = the sample's t; the thread does that next pass itself,
+// with the same arithmetic (the march restarts from max(EntryT, t)), until the ray reaches the boundary -- one launch per visit
+// of a partition instead of one per crossing.  passes: number of passes (= the reference's traced-ray count).
+template <bool LOOP>
 __global__ void __launch_bounds__(128)
     sampler_trace_kernel(const __grid_constant__ SamplerParams SP, Rays R, int n, float *__restrict__ samples,
-                         unsigned long long *__restrict__ sample_count, unsigned long long sample_cap) {
+                         unsigned long long *__restrict__ sample_count, unsigned long long sample_cap,
+                         unsigned long long *__restrict__ passes) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int nv = SP.n_ops;
@@ -25,7 +31,8 @@ __global__ void __launch_bounds__(128)
   const float3 org = f3(R.ox[i], R.oy[i], R.oz[i]);
   const float3 dir0 = f3(R.dx[i], R.dy[i], R.dz[i]);
   float3 dir = dir0;
-  const float ray_t = R.t[i];
+  float ray_t = R.t[i];
+  unsigned my_passes = 0;
   if (dir.x == 0.f) dir.x = 1e-6f;  // :163-165
   if (dir.y == 0.f) dir.y = 1e-6f;
   if (dir.z == 0.f) dir.z = 1e-6f;
@@ -33,8 +40,11 @@ __global__ void __launch_bounds__(128)
   const float rx = 1.0f / dir.x, ry = 1.0f / dir.y, rz = 1.0f / dir.z;
   const float mnx = (SP.lmin.x - org.x) * rx, mny = (SP.lmin.y - org.y) * ry, mnz = (SP.lmin.z - org.z) * rz;
   const float mxx = (SP.lmax.x - org.x) * rx, mxy = (SP.lmax.y - org.y) * ry, mxz = (SP.lmax.z - org.z) * rz;
-  float tEntry = fmaxf(fminf(mnx, mxx), fmaxf(fminf(mny, mxy), fminf(mnz, mxz)));
+  const float tEntryBox = fmaxf(fminf(mnx, mxx), fmaxf(fminf(mny, mxy), fminf(mnz, mxz)));
   const float tExit = fminf(fmaxf(mnx, mxx), fminf(fmaxf(mny, mxy), fmaxf(mnz, mxz)));
+  for (;;) {  // one iteration = one pass of the reference's kernel over this ray
+  my_passes++;
+  float tEntry = tEntryBox;
   if (tEntry < ray_t) tEntry = ray_t;  // :176-179
   float tThis = tEntry + step;
   int hit = -1;
@@ -73,8 +83,6 @@ __global__ void __launch_bounds__(128)
     if (tThis > tExit) tThis = tExit;
   }
   const float t_out = (hit != -1) ? tThis + 0.001f : tThis;  // :214-217
-  R.t[i] = t_out;
-  R.term[i] = (hit != -1) ? RAY_SURFACE : RAY_BOUNDARY;
   if (hit != -1 && samples) {  // Sampler.cpp:74-86: position from the list's own (unpatched) direction
     const unsigned long long k = atomicAdd(sample_count, 1ull);
     if (k < sample_cap) {
@@ -83,12 +91,22 @@ __global__ void __launch_bounds__(128)
       samples[3 * k + 2] = org.z + t_out * dir0.z;
     }
   }
+  if (LOOP && hit != -1) {  // RAY_SURFACE only: KEEP_HERE (Renderer.cpp:304-421) -> the next pass starts behind the sample
+    ray_t = t_out;
+    continue;
+  }
+  R.t[i] = t_out;
+  R.term[i] = (hit != -1) ? RAY_SURFACE : RAY_BOUNDARY;
+  break;
+  }
+  if (LOOP && passes) atomicAdd(passes, (unsigned long long)my_passes);
 }
 
 int launch_sampler_trace(const SamplerParams &SP, Rays R, int n, float *samples, unsigned long long *sample_count,
-                         unsigned long long sample_cap, cudaStream_t st) {
+                         unsigned long long sample_cap, unsigned long long *passes, bool loop, cudaStream_t st) {
   if (n <= 0 || SP.n_ops < 1) return 0;  // SamplerTraceRays.ispc:136: nothing is touched without a sampler operator
-  sampler_trace_kernel<<<(n + 127) / 128, 128, 0, st>>>(SP, R, n, samples, sample_count, sample_cap);
+  if (loop) sampler_trace_kernel<true><<<(n + 127) / 128, 128, 0, st>>>(SP, R, n, samples, sample_count, sample_cap, passes);
+  else sampler_trace_kernel<false><<<(n + 127) / 128, 128, 0, st>>>(SP, R, n, samples, sample_count, sample_cap, passes);
   GXY_CUDA(cudaGetLastError());
   return 0;
 }

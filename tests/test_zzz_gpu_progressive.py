@@ -91,3 +91,24 @@ def test_gpu_sampler_with_two_operators_matches_oracle(gpu, oracle):
         for r in range(nparts):
             a, b = sorted_rows(sg[r]), sorted_rows(so[r])
             assert len(b) > 0 and a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (nparts, r)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nparts", [1, 2, 8])
+def test_gpu_sampler_loop_mode_matches_oracle(gpu, oracle, nparts, monkeypatch):
+    """GXY_SAMPLER_LOOP=1: a ray makes all its passes through a partition inside one launch (and the sample buffer grows by a
+    second run when 4 samples per ray were not enough): the same sample sets and the same pass count as the oracle"""
+    from galaxy_b200 import scenes
+    from tests.test_sampler import CAM2, sampler_vis, sorted_rows
+    monkeypatch.setenv("GXY_SAMPLER_LOOP", "1")
+    for kind, param, name in (("IsoSampler", 0.25, "eightBalls"), ("GradientSampler", 0.9995, "oneBall")):   # the second: > 4 samples per ray
+        vol = scenes.radial_volume(name, 48)
+        vis = sampler_vis(kind, param)
+        sg, st_g = gpu.sample(scenes.build_partitions(gpu, vis, {"v": vol}, nparts), CAM2, 96, 72)
+        so, st_o = oracle.sample(scenes.build_partitions(oracle, vis, {"v": vol}, nparts), CAM2, 96, 72)
+        for k in ("primary_rays", "traced_rays", "forwarded_rays"):
+            assert st_g[k] == st_o[k], (kind, k, st_g, st_o)
+        for r in range(nparts):
+            a, b = sorted_rows(sg[r]), sorted_rows(so[r])
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (kind, r)
+        assert st_g["waves"] < st_o["traced_rays"]
