@@ -91,7 +91,9 @@ __global__ void __launch_bounds__(128)
       samples[3 * k + 2] = org.z + t_out * dir0.z;
     }
   }
-  if (LOOP && hit != -1) {  // RAY_SURFACE only: KEEP_HERE (Renderer.cpp:304-421) -> the next pass starts behind the sample
+  // RAY_SURFACE only: KEEP_HERE (Renderer.cpp:304-421) -> the next pass starts behind the sample.  Only while t advances (at
+  // |t| >= 2^14 the +0.001 is below one ulp): a ray that does not move goes back to the host loop like in the default mode.
+  if (LOOP && hit != -1 && t_out > ray_t && my_passes < (1u << 20)) {
     ray_t = t_out;
     continue;
   }
