@@ -81,6 +81,26 @@ def test_cull_is_conservative_on_grazing_rays(host_curve):
     assert culled > 0.8                                                 # all-pairs: nearly every pair is a miss the cull sees
 
 
+def test_device_source_with_cull_against_embree_itself(host_curve):
+    """the device source (cull + test) against the REFERENCE'S OWN compiled intersector (oracle/_ref, skipped where absent):
+    every ray x segment pair Embree hits is hit, none it misses is hit"""
+    so = os.path.join(ROOT, "oracle", "_ref", "libgxy_embree_curve_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libgxy_embree_curve_ref.so not built (needs /root/reference: make -C oracle ref)")
+    R, O = C.CDLL(so), oracle.lib()
+    hits = lost = extra = 0
+    for seed in range(200, 206):
+        rng = np.random.default_rng(seed)
+        radii = (float(10 ** rng.uniform(-3, -1)), float(10 ** rng.uniform(-3, -1)), 0.0, float(rng.uniform(0.5, 2)))
+        v, d, c = helices(seed, nlines=int(rng.integers(2, 10)))
+        cp = build(O, v, d, c, *radii)
+        org, dr, tn, tf = rays_at(cp, 5000, seed + 7, float(10 ** rng.uniform(-3, -1)))
+        a = intersect(R, "gxr_curve_intersect", cp, org, dr, tn, tf, 1)
+        b = intersect(host_curve, "gxc_curve_intersect", cp, org, dr, tn, tf, 1)
+        hits += int(a[0].sum()); lost += int(((a[0] == 1) & (b[0] == 0)).sum()); extra += int(((a[0] == 0) & (b[0] == 1)).sum())
+    assert hits > 10000 and lost + extra <= max(1, hits // 20000), (hits, lost, extra)
+
+
 def test_device_source_degenerate_inputs(host_curve):
     """zero-length segments, zero radius, rays along the axis, zero direction components: same answers, no hangs."""
     O = oracle.lib()
