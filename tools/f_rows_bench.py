@@ -73,13 +73,17 @@ def main():
     t0 = time.time()
     vol = scenes.radial_volume("eightBalls", vol_n)
     sp = scenes.build_partitions(gpu, svis, {"v": vol}, 1)
-    ms = []
-    for it in range(4):
-        samp, st = gpu.sample(sp, cam, 1920, 1080)
-        ms.append(st["device_ms"])
-    best = float(np.median(ms[1:]))
-    out["sampler"] = dict(volume=vol_n, samples=int(len(samp[0])), traced_rays=st["traced_rays"], waves=st["waves"], ms_per_frame=best,
-                          mrays_per_s=st["traced_rays"] / best / 1e3, wall_s=time.time() - t0)
+    import os
+    for mode, key in (("0", "sampler"), ("1", "sampler_loop_mode")):   # GXY_SAMPLER_LOOP: one launch per crossing / per visit of a partition
+        os.environ["GXY_SAMPLER_LOOP"] = mode
+        ms = []
+        for it in range(4):
+            samp, st = gpu.sample(sp, cam, 1920, 1080)
+            ms.append(st["device_ms"])
+        best = float(np.median(ms[1:]))
+        out[key] = dict(volume=vol_n, samples=int(len(samp[0])), traced_rays=st["traced_rays"], waves=st["waves"], ms_per_frame=best,
+                        mrays_per_s=st["traced_rays"] / best / 1e3, wall_s=time.time() - t0)
+    os.environ.pop("GXY_SAMPLER_LOOP", None)
     print(json.dumps(out))
 
 
