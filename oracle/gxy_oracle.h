@@ -15,8 +15,9 @@
  * (tests/test_oracle_box.py).
  * PARITY UNPINNED for the Sampler part (gxo_sample*, src/sampler): the reference holds no golden
  * data for it and its kernels are ISPC, which cannot be compiled here; that part is checked
- * against closed-form properties only (tests/test_sampler.py).  The PathLines curve BUILDER
- * (gxo_build_curves) has a closed-form test only; the curve INTERSECTOR is pinned by Embree.
+ * against closed-form properties only (tests/test_sampler.py).  PathLines: the curve builder
+ * (gxo_build_curves) is pinned bit for bit by the reference's own DataDrivenPathLines::finalize
+ * and the curve intersector by Embree's own header, both compiled into oracle/_ref.
  *
  * Floating point convention (shared with the CUDA path so both can be compared tightly):
  * IEEE fp32, round-to-nearest, true divides and square roots, NO contraction of a*b+c into

@@ -180,3 +180,26 @@ def test_built_pathlines_match_embree(orc, ref, radii):
     a = intersect(ref, "gxr_curve_intersect", cp, org, d, tn2, tf2, 0)
     b = intersect(orc, "gxo_curve_intersect", cp, org, d, tn2, tf2, 0)
     compare(a, b, 0)
+
+
+def test_curve_builder_matches_the_references_own_finalize(orc):
+    """gxo_build_curves against ospray::DataDrivenPathLines::finalize ITSELF (src/ospray/DataDrivenPathLines.cpp compiled from the
+    reference tree into oracle/_ref behind oracle/ddpathlines_ref.cpp, whose stand-in for the ISPC export setCurve captures the
+    curve vertices Embree would be handed): bit for bit, for data-mapped, constant, negative-default and shrinking radii, single
+    segments and lines that share no vertices."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libgxy_ddpathlines_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libgxy_ddpathlines_ref.so not built (needs /root/reference: make -C oracle ref)")
+    R = C.CDLL(so)
+    cases = [(helices(seed, nlines=9), radii) for seed, radii in ((3, (0.002, 0.02, 0.0, 1.7)), (4, (0.05, 0.05, 1.0, 1.0)), (5, (-1.0, 1.0, 0.0, 1.0)),
+                                                                   (6, (0.04, 0.01, 0.3, 0.9)))]
+    v = np.array([[0, 0, 0], [1, 0, 0], [2, 1, 0], [3, 1, 0], [5, 5, 5], [5, 5, 6]], np.float32)
+    cases.append(((v, np.array([0, 1, 2, 3, 1, 1], np.float32), np.array([0, 1, 2, 4], np.int32)), (0.1, 0.4, 0.0, 3.0)))
+    cases.append(((v, np.array([0, 1, 2, 3, 1, 1], np.float32), np.array([3], np.int32)), (0.1, 0.4, 0.0, 3.0)))          # one segment
+    cases.append(((v, np.array([9, -1, 2, 7, 1, 1], np.float32), np.array([0, 2, 4], np.int32)), (0.1, 0.4, 0.0, 3.0)))     # no segment continues
+    for (verts, data, conn), radii in cases:
+        want = build(orc, verts, data, conn, *radii)
+        got = np.zeros_like(want)
+        rc = R.gxr_build_curves(C.c_int(len(verts)), _p(verts), _p(data), C.c_int(len(conn)), _p(conn), *[C.c_float(x) for x in radii], _p(got))
+        assert rc == 0
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
