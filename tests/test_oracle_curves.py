@@ -203,3 +203,19 @@ def test_curve_builder_matches_the_references_own_finalize(orc):
         rc = R.gxr_build_curves(C.c_int(len(verts)), _p(verts), _p(data), C.c_int(len(conn)), _p(conn), *[C.c_float(x) for x in radii], _p(got))
         assert rc == 0
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_committed_reference_fixtures(orc):
+    """tests/golden/curve_fixtures.npz holds what the reference's own compiled code answered in the build container
+    (tests/golden/make_curve_fixtures.py: DataDrivenPathLines::finalize control points, Embree sweep-intersector hits).  It keeps
+    both PathLines pins alive where oracle/_ref does not exist: control points bit for bit, hit decisions and nearest segments
+    identical but for grazing rays, t within 1e-5."""
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "curve_fixtures.npz"))
+    for k in range(3):
+        verts, data, conn, radii = fx["verts%d" % k], fx["data%d" % k], fx["conn%d" % k], [float(x) for x in fx["radii%d" % k]]
+        cp = build(orc, verts, data, conn, *radii)
+        assert np.array_equal(cp.view(np.uint32), fx["cp%d" % k].view(np.uint32))
+        org, d = fx["org%d" % k], fx["dir%d" % k]
+        tn, tf = np.zeros(len(org), np.float32), np.full(len(org), FMAX, np.float32)
+        b = intersect(orc, "gxo_curve_intersect", cp, org, d, tn, tf, 0)
+        compare((fx["prim%d" % k], fx["tu%d" % k], fx["ng%d" % k]), b, 0)
