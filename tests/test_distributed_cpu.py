@@ -36,7 +36,13 @@ def _worker(rank, world, port, case, out):
                     np.save(out + ".ref%d.npy" % r, ref[r])
                 json.dump({"dist": stats, "ref": st_ref}, open(out + ".json", "w"))
             return
-        if case == "mesh":
+        if case == "pathlines":
+            vis = dict(annotation="", lighting=dict(lights=[[1.0, 2.0, -3.0]], types=[2], n_ao=2, ao_radius=0.5, shadows=True, Ka=0.4, Kd=0.6),
+                       operators=[dict(type="PathLinesVis", dataset="lines", colormap=[[0.0, 0.0, 1.0, 0.0], [1.2, 1.0, 0.0, 1.0]],
+                                       opacitymap=[[0, 1], [1, 1]], data_range=None, radius0=0.01, radius1=0.05, value0=0.0, value1=1.2)])
+            cam = dict(eye=[1.5, 1.0, -3.0], dir=[-1.5, -1.0, 3.0], up=[0.0, 1.0, 0.0], aov=35.0)
+            datasets, w, h, eps = {"lines": scenes.helix_pathlines(16)}, 96, 64, 0.001      # build_partitions cuts the lines per rank
+        elif case == "mesh":
             vis, cam = scenes.c5_vis(), scenes.c5_camera()
             ds, _ = scenes.c5_partition_mesh(24, 48, world, rank)
             datasets, w, h, eps = {"mesh": ds}, 96, 64, 0.001
@@ -58,10 +64,10 @@ def _worker(rank, world, port, case, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["mesh", "volume"])
+@pytest.mark.parametrize("case", ["mesh", "volume", "pathlines"])
 def test_two_rank_gloo_loop_matches_single_process_oracle(tmp_path, case):
     import json
-    world, port = 2, 29700 + (os.getpid() % 200) + (0 if case == "mesh" else 1)
+    world, port = 2, 29700 + (os.getpid() % 200) + {"mesh": 0, "volume": 1, "pathlines": 3}[case]
     out = str(tmp_path / case)
     mp.spawn(_worker, args=(world, port, case, out), nprocs=world, join=True)
     fb, fb_ref = np.load(out + ".fb.npy")
