@@ -183,3 +183,25 @@ def test_pathlines_pieces_load_as_the_reference_loads_them(tmp_path, nparts, mod
         assert pr["loaded"] and pr["n_vertices"] == len(v) and pr["n_connectivity"] == len(c)
         assert pr["hash_vertices"] == fnv(v.astype(np.float32)) and pr["hash_data"] == fnv(dat.astype(np.float32))
         assert pr["hash_connectivity"] == fnv(c.astype(np.int32))
+
+
+def test_reference_data_driven_state_loads_verbatim(tmp_path):
+    """tests/data-driven.state of the reference, unchanged, on the stand-in datasets of tools/make_data_driven.py (8 partitions):
+    all four datasets load through the C++ host, the operators parse with the state's values"""
+    import shutil
+    import sys
+    sys.path.insert(0, ROOT)
+    from tools.make_data_driven import write
+    tmp = str(tmp_path)
+    lines, parts, mesh, vol = write(tmp, 8, n=34)
+    shutil.copy(os.path.join(ROOT, "tests", "golden", "states", "data-driven.state"), tmp)
+    out = subprocess.run([EXE, "--describe", "-P", "8", os.path.join(tmp, "data-driven.state")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    d = json.loads(out.stdout)
+    assert [o["type"] for o in d["visualizations"][0]["operators"]] == ["VolumeVis", "PathLinesVis", "ParticlesVis", "TrianglesVis"]
+    assert np.array_equal(np.float32(d["visualizations"][0]["operators"][1]["radii"]), np.float32([0.002, 0.02, 0.0, 1.7]))
+    geo = {g["name"]: g for g in d["geometries"]}
+    assert set(geo) == {"pathlines", "particles", "tmesh"} and all(len(g["parts"]) == 8 and all(p["loaded"] for p in g["parts"]) for g in geo.values())
+    assert sum(p["n_vertices"] for p in geo["particles"]["parts"]) >= len(parts.centers)          # ghost zones duplicate some
+    assert sum(p["n_connectivity"] for p in geo["tmesh"]["parts"]) >= 3 * len(mesh.indices)
+    assert sum(p["n_connectivity"] for p in geo["pathlines"]["parts"]) > 0

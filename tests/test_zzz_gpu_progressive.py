@@ -112,3 +112,45 @@ def test_gpu_sampler_loop_mode_matches_oracle(gpu, oracle, nparts, monkeypatch):
             a, b = sorted_rows(sg[r]), sorted_rows(so[r])
             assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (kind, r)
         assert st_g["waves"] < st_o["traced_rays"]
+
+
+@pytest.mark.gpu
+def test_data_driven_state_renders_unchanged(gpu, oracle, tmp_path):
+    """the reference's tests/data-driven.state VERBATIM on the stand-in datasets of tools/make_data_driven.py: gxywriter's PNG at 1 and
+    2 partitions, the Python binding and the oracle agree; and the picture resembles the reference's gold"""
+    import json
+    import os
+    import shutil
+    import subprocess
+
+    from PIL import Image
+
+    from galaxy_b200 import scenes
+    from tests.test_gxywriter import EXE
+    from tools.make_data_driven import make_datasets, write
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    state_src = os.path.join(root, "tests", "golden", "states", "data-driven.state")
+    st = scenes.parse_state(json.load(open(state_src)))
+    vis, cam = st["visualizations"][0], st["cameras"][0]
+    lines, parts, mesh = make_datasets()
+    write(str(tmp_path / "p1"), 1, n=96)
+    # the volume as the .vol file describes it (its header rounds origin and spacing to 6 digits, scripts/vti2vol:70-80)
+    ds = {"volume": scenes.load_vol_file(str(tmp_path / "p1" / "radial-eightBalls.vol")), "pathlines": lines, "particles": parts, "tmesh": mesh}
+    o = scenes.build_partitions(oracle, vis, ds, 1)
+    fb_o, st_o = oracle.render(o, cam, vis["lighting"], 256, 256, st["epsilon"])
+    g = scenes.build_partitions(gpu, vis, ds, 1)
+    fb_g, st_g = gpu.render(g, cam, vis["lighting"], 256, 256, st["epsilon"])
+    for k in ("primary_rays", "shadow_rays", "terminated_rays"):
+        assert st_g[k] == st_o[k], (k, st_g, st_o)
+    assert util.fb_fraction(fb_g, fb_o, 1.0 / 255) >= 0.999
+    img_g = g[0].download_rgba8(256, 256)
+    for nparts in (1, 2):
+        tmp = str(tmp_path / ("p%d" % nparts))
+        if nparts > 1:
+            write(tmp, nparts, n=96)
+        shutil.copy(state_src, tmp)
+        out = subprocess.run([EXE, "-s", "256", "256", "-P", str(nparts), "-o", os.path.join(tmp, "dd"), os.path.join(tmp, "data-driven.state")],
+                             capture_output=True, text=True, timeout=180)
+        assert out.returncode == 0, out.stderr
+        png = np.asarray(Image.open(os.path.join(tmp, "dd_00000.png")).convert("RGBA"))
+        assert util.image_fraction(png, img_g, 1) >= (1.0 if nparts == 1 else 0.99)     # 2 partitions: cut stream lines end in doubled end points
