@@ -154,3 +154,21 @@ def test_data_driven_state_renders_unchanged(gpu, oracle, tmp_path):
         assert out.returncode == 0, out.stderr
         png = np.asarray(Image.open(os.path.join(tmp, "dd_00000.png")).convert("RGBA"))
         assert util.image_fraction(png, img_g, 1) >= (1.0 if nparts == 1 else 0.99)     # 2 partitions: cut stream lines end in doubled end points
+
+
+@pytest.mark.gpu
+def test_gpu_data_driven_gold(gpu, golden_dir):
+    """the 12th gold on the CUDA path: tests/data-driven.state unchanged, datasets regenerated by tools/make_data_driven.py,
+    512 x 512: within 1/255 of the reference's gold on >= 99.9 % of the pixels (the oracle reaches 99.99 %)"""
+    import json
+    import os
+
+    from galaxy_b200 import scenes
+    from tests.test_oracle_golds import data_driven_datasets, gold_fraction
+    st = scenes.parse_state(json.load(open(os.path.join(golden_dir, "states", "data-driven.state"))))
+    vis, cam = st["visualizations"][0], st["cameras"][0]
+    g = scenes.build_partitions(gpu, vis, data_driven_datasets(), 1)
+    gpu.render(g, cam, vis["lighting"], 512, 512, st["epsilon"])
+    frac = gold_fraction(golden_dir, g[0].download_rgba8(512, 512), "data-driven", 0)
+    print("data-driven on the GPU: fraction within 1/255 of the gold:", frac)
+    assert frac >= 0.999

