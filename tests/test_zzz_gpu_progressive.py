@@ -153,7 +153,7 @@ def test_data_driven_state_renders_unchanged(gpu, oracle, tmp_path):
                              capture_output=True, text=True, timeout=180)
         assert out.returncode == 0, out.stderr
         png = np.asarray(Image.open(os.path.join(tmp, "dd_00000.png")).convert("RGBA"))
-        assert util.image_fraction(png, img_g, 1) >= (1.0 if nparts == 1 else 0.99)     # 2 partitions: cut stream lines end in doubled end points
+        assert util.image_fraction(png, img_g, 1) >= (1.0 if nparts == 1 else 0.97)     # 2 partitions: cut stream lines end in doubled end points, bricks restart the march
 
 
 @pytest.mark.gpu
