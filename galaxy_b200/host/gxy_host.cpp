@@ -885,6 +885,23 @@ bool Rendering::Render(const Renderer &renderer) {
   return check_abi(gxy_frame_download_rgba8(visualization->parts[0], rgba8.data()), "gxy_frame_download_rgba8");
 }
 
+// The interactive viewer's frame (Rendering::AddLocalPixels without GXY_WRITE_IMAGES, Rendering.cpp:104-153): the image owner keeps
+// the displayed image and the per-pixel frame stamps across calls; rgba8 receives what is displayed after frame `frame`.
+bool Rendering::RenderProgressive(const Renderer &renderer, int frame) {
+  if (!camera || !visualization || visualization->parts.empty()) {
+    std::cerr << "Rendering: camera and a committed visualization are needed\n";
+    return false;
+  }
+  const gxy_camera cam = camera->AsABI();
+  memset(&stats, 0, sizeof stats);
+  if (!check_abi(gxy_render_progressive((int)visualization->parts.size(), visualization->parts.data(), &cam, &visualization->lighting.abi, width,
+                                        height, renderer.epsilon, frame, &stats),
+                 "gxy_render_progressive"))
+    return false;
+  rgba8.resize((size_t)width * height * 4);
+  return check_abi(gxy_progressive_download_rgba8(visualization->parts[0], rgba8.data()), "gxy_progressive_download_rgba8");
+}
+
 std::string Rendering::ImageName(const std::string &base, int index) const {
   const std::string va = visualization ? visualization->annotation : std::string(""), ca = camera ? camera->annotation : std::string("");
   if (!va.empty() || !ca.empty()) return base + va + ca + ".png";

@@ -156,6 +156,8 @@ class Rendering {
   std::vector<unsigned char> rgba8;  // rows top-down
   gxy_stats stats;
   bool Render(const Renderer &renderer);
+  // frame-stamped accumulation of the interactive path (Rendering.cpp:104-153): nothing is cleared between frames
+  bool RenderProgressive(const Renderer &renderer, int frame);
   // Rendering::SaveImage (Rendering.cpp:272-293): <base>_%05d<vis annotation><camera annotation>.png, or
   // <base><annotations>.png when an annotation is present
   std::string ImageName(const std::string &base, int index) const;
