@@ -252,6 +252,8 @@ def main():
                     help="c5 (default, the headline): 100M-triangle mesh; c3: volume DVR; c4: volume isosurface + shadow rays; "
                          "pl: PathLines (800 000 round Bezier segments), primary + shadow")
     ap.add_argument("--volume-n", type=int, default=1024, help="c3/c4: voxels per axis of the synthetic volume")
+    ap.add_argument("--in-flight", type=int, default=None,
+                    help="frames of the RenderingSet kept in flight (gxy_render_submit/wait); default 4 for the geometry workloads, 1 otherwise")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -271,7 +273,13 @@ def main():
         workload = "C5 eightBalls-100M: %d triangles, 1920x1080, primary + shadow (1 light) + 8 AO rays, Triangles vis, spatial partitions=%d" % (
             8 * 2 * (scenes.C5_FULL[0] // args.tess_div) * (scenes.C5_FULL[1] // args.tess_div), n_gpus)
         metric = "Mrays/s, 1080p primary+shadow+AO"
-    config = {"workload": workload, "width": W, "height": H, "partitions": n_gpus, "timing": "value: inputs larger than L2 (scene >> 126 MB) + 256 MB L2 flush between frames; e2e: inputs larger than L2 (~1 GB of DRAM traffic per frame), no explicit flush, image k downloads while frame k+1 renders"}
+    config = {"workload": workload, "width": W, "height": H, "partitions": n_gpus,
+              "timing": ("a RenderingSet of frames in flight (frames_in_flight; gxy_render_submit/gxy_render_wait): every step renders and delivers its own "
+                         "complete image, steps overlap on the device, ms_per_step = (last frame's end - first frame's start, CUDA events on the frames' "
+                         "streams, max over ranks) / steps, so pipeline fill and drain are inside the timed region.  No explicit L2 flush: inputs larger "
+                         "than L2 (a frame touches ~1 GB of a >= 4 GB scene, 8x the 126 MB L2).  e2e: the same with every image converted to RGBA8 and "
+                         "copied to pinned host memory inside the timed region.  With --in-flight 1 (and for the volume / PathLines workloads): one "
+                         "frame at a time, 256 MB L2 flush between frames, ms_per_step = mean per-frame device time")}
 
     if pathlines:
         config["timing"] = ("value: 256 MB L2 flush between frames; e2e: no explicit flush and the scene (about 90 MB of records and control points) "
@@ -331,6 +339,12 @@ def main():
     del ds, dsets
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    # frames in flight: a RenderingSet of `depth` frames is kept on the device at any time (the reference keeps every Rendering
+    # of a set in flight, gxywriter.cpp:196-264).  Every step still delivers its own complete image; steps are counted as they
+    # complete.  Geometry workloads only: the volume / PathLines schedules are synchronous per frame (depth 1).
+    depth = args.in_flight if args.in_flight is not None else (4 if not (volume or pathlines) else 1)
+    depth = max(1, min(depth, gpu.max_slots(), max(1, args.steps)))
+    use_flush = depth == 1   # depth 1: 256 MB L2 flush between frames; depth > 1: the frames' inputs are >> L2 (config.timing)
 
     def barrier():
         torch.cuda.synchronize()
@@ -338,53 +352,73 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def frame():
-        return gpu.render_device([part], cam, vis["lighting"], W, H, EPS)
+    def submit(slot):
+        gpu.render_submit([part], cam, vis["lighting"], W, H, EPS, slot)
+
+    def run_pipeline(n_steps, on_frame=None):
+        """n_steps frames, `depth` in flight; returns the per-frame stats in completion order"""
+        out = []
+        for k in range(min(depth, n_steps)):
+            if use_flush:
+                flush.zero_()
+                torch.cuda.synchronize()
+            submit(k % depth)
+        for k in range(n_steps):
+            st = gpu.render_wait([part], k % depth)
+            out.append(st)
+            if on_frame is not None:
+                on_frame(k)
+            if k + depth < n_steps:
+                if use_flush:
+                    flush.zero_()
+                    torch.cuda.synchronize()
+                submit(k % depth)
+        return out
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(max(3, args.warmup)):
-        flush.zero_()
-        st = frame()
-    # ---- timed region: K frames, device-timed (CUDA events on the library's stream) ------------
+    run_pipeline(max(3, args.warmup) + depth - 1)
+    # ---- timed region: K frames, device-timed: CUDA events of the library on the frames' own streams, stamps relative to ctx.mark()
+    barrier()
+    ctx.mark()
     barrier()
     sampler.mark_begin()
     t_wall0 = time.perf_counter()
-    dev_ms, trace_ms, launches, traced, samples = [], 0.0, 0, 0, 0
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        st = frame()
-        dev_ms.append(st["device_ms"])
-        trace_ms += st["trace_ms"]
-        launches += st["kernel_launches"]
-        traced += st["traced_rays"]
-        samples += st["volume_samples"]
+    frames = run_pipeline(args.steps)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     sampler.mark_end()
     clocks = sampler.stop()
-    ms_local = float(np.sum(dev_ms))
+    if use_flush:   # frames run one after the other with a flush in between: the sum of their device times
+        ms_local = float(np.sum([f["device_ms"] for f in frames]))
+    else:           # frames overlap: first start to last end on the device
+        ms_local = max(f["t_end_ms"] for f in frames) - min(f["t_begin_ms"] for f in frames)
+    trace_ms = float(np.sum([f["trace_ms"] for f in frames]))
+    launches = int(np.sum([f["kernel_launches"] for f in frames]))
+    traced = int(np.sum([f["traced_rays"] for f in frames]))
+    dequeued = int(np.sum([f["dequeued_rays"] for f in frames]))
+    samples = int(np.sum([f["volume_samples"] for f in frames]))
+    latency_ms = float(np.mean([f["device_ms"] for f in frames]))
+    st = frames[-1]
     rays_local = st["primary_rays"] + st["shadow_rays"] + st["ao_rays"]
     hit_local = st["shadow_rays"]  # one shadow ray per surface-hit primary (1 light)
 
     # ---- e2e: through the public calls with host buffers: camera/lights H2D, RGBA8 image D2H into pinned memory ------
     # Every frame's image is delivered to the host inside the timed region; the transfer of frame k (copy stream, one of
-    # two pinned buffers) overlaps the rendering of frame k+1, as a viewer or an image writer thread would run it.
+    # two pinned buffers) overlaps the frames behind it, as a viewer or an image writer thread would run it.
     imgs = [gpu.pinned_array((H, W, 4), np.uint8) for _ in range(2)] if rank == 0 else None
-    for k in range(2):
-        frame()
+
+    def deliver(k):
         if rank == 0:
+            part.download_wait()  # image k-1 (it travelled while frame k rendered)
             part.download_rgba8_async(imgs[k & 1])
+
+    run_pipeline(2, deliver)
     if rank == 0:
         part.download_wait()
     barrier()
     t0 = time.perf_counter()
-    for k in range(args.steps):
-        frame()  # no explicit L2 flush here: a frame touches ~1 GB of a >= 4 GB scene, 8x the 126 MB L2 (config.timing)
-        if rank == 0:
-            part.download_wait()  # image k-1 (it travelled while frame k rendered)
-            part.download_rgba8_async(imgs[k & 1])
+    run_pipeline(args.steps, deliver)   # no explicit L2 flush here (config.timing)
     if rank == 0:
         part.download_wait()
     barrier()
@@ -394,12 +428,13 @@ def main():
         t = torch.tensor([ms_local, t_e2e, trace_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_max, t_e2e, trace_ms_max = t.tolist()
-        c = torch.tensor([rays_local, launches, traced, hit_local, st["primary_rays"]], dtype=torch.float64, device="cuda")
+        c = torch.tensor([rays_local, launches, traced, hit_local, st["primary_rays"], dequeued, latency_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        rays_total, launches_total, traced_total, hits_total, prim_total = c.tolist()
+        rays_total, launches_total, traced_total, hits_total, prim_total, dequeued_total, latency_sum = c.tolist()
+        latency_ms = latency_sum / world
     else:
         ms_max, trace_ms_max = ms_local, trace_ms
-        rays_total, launches_total, traced_total, hits_total, prim_total = rays_local, launches, traced, hit_local, st["primary_rays"]
+        rays_total, launches_total, traced_total, hits_total, prim_total, dequeued_total = rays_local, launches, traced, hit_local, st["primary_rays"], dequeued
 
     if rank != 0:
         if world > 1:
@@ -412,12 +447,22 @@ def main():
     hbm = float(peaks["hbm_gbs"])
     hfrac = hits_total / max(1.0, prim_total)
     b_alg, levels = c5_alg_bytes_per_ray(n_tris_local, hfrac)
-    # dominant kernel = trace_kernel: algorithmic bytes of the rays it traced / its summed CUDA-event time (this rank)
-    achieved = (traced / max(1, 1)) * b_alg / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": NCU_TRAFFIC_BYTES_PER_FRAME,
-                "kernel": "gxy::primary_trace_kernel + gxy::fused_secondary_kernel (the two persistent trace launches of a frame)",
-                "traffic_note": "dram__bytes_read+write of the two trace launches of one frame, ncu --set full, profiles/r01_e_trace_kernels_full.txt", "peak_kind": peak_kind + " (burst copy figure)", "alg_bytes_per_ray": b_alg, "bvh_levels_model": levels,
-                "trace_share_of_step": trace_ms_max / max(1e-9, ms_max)}
+    # dominant kernels = the persistent trace launches.  Units: the rays those launches DEQUEUE (primaries the generation kernel
+    # finishes itself -- they can reach no primitive -- are not counted), times the algorithmic bytes per ray of SURVEY 8(d).
+    # Time: depth 1 -> the summed CUDA-event durations of the trace launches; frames in flight -> the launches of different
+    # frames overlap, so the time they occupy the device is the timed region itself (first start to last end on this rank,
+    # which also contains the ~3 % of generation/shading kernels: a lower bound for the trace kernels alone).
+    kernel_ms = trace_ms if use_flush else ms_local
+    achieved = dequeued * b_alg / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    traffic = NCU_TRAFFIC_BYTES_PER_FRAME if n_gpus == 1 and args.tess_div == 1 else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+                "kernel": "gxy::primary_trace_kernel + gxy::fused_secondary_kernel (+ gxy::inbox_trace_kernel across ranks): the persistent trace launches",
+                "traffic_note": "dram__bytes_read+write of the trace launches of one frame, ncu --set full, profiles/r01_e_trace_kernels_full.txt",
+                "dram_util": (traffic / (ms_per_step * 1e-3) / 1e9 / hbm) if traffic else None,
+                "peak_kind": peak_kind + " (burst copy figure)", "alg_bytes_per_ray": b_alg, "bvh_levels_model": levels,
+                "units_per_frame": dequeued / args.steps, "units": "rays dequeued by the trace launches of this rank (culled primaries excluded)",
+                "kernel_time": "sum of trace-launch CUDA-event durations" if use_flush else "timed region of this rank (launches of frames in flight overlap)",
+                "trace_share_of_step": trace_ms_max / max(1e-9, ms_max) if use_flush else None}
     if pathlines:
         b_alg, levels = pathlines_alg_bytes_per_ray(info["n_prims"], hfrac)
         achieved = traced * b_alg / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
@@ -426,13 +471,20 @@ def main():
                     "peak_kind": peak_kind + " (burst copy figure)", "alg_bytes_per_ray": b_alg, "bvh_levels_model": levels,
                     "trace_share_of_step": trace_ms_max / max(1e-9, ms_max)}
     if volume:
-        # 16 algorithmic bytes per trilinear sample (4 new float voxels per step when rays are >= 1 voxel apart)
-        achieved = samples * 16.0 / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
+        # B_alg = min(16 B x samples, 4 B x voxels in the frustum): 16 algorithmic bytes per trilinear sample (4 new
+        # float voxels per step) when rays are >= 1 voxel apart, but never more than reading every voxel of this rank's brick once
+        vox_rank = float(args.volume_n) ** 3 / max(1, nparts)
+        spf = samples / args.steps
+        alg_frame = min(16.0 * spf, 4.0 * vox_rank)
+        achieved = alg_frame * args.steps / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
+        vtraffic = NCU_VOLUME_TRAFFIC.get(args.workload) if (args.volume_n == 1024 and n_gpus == 1) else None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                    "traffic": NCU_VOLUME_TRAFFIC.get(args.workload) if args.volume_n == 1024 else None,
+                    "traffic": vtraffic,
                     "kernel": "gxy::trace_kernel<1,false,true> (volume march: trilinear sample + transfer function + compositing / isosurface search)",
                     "traffic_note": "dram__bytes_read+write per frame at 1024^3, ncu --set full, profiles/r01_e_volume_full.txt",
-                    "peak_kind": peak_kind + " (burst copy figure)", "alg_bytes_per_sample": 16.0, "samples_per_frame": samples / args.steps,
+                    "dram_util": (vtraffic / (ms_per_step * 1e-3) / 1e9 / hbm) if vtraffic else None,
+                    "peak_kind": peak_kind + " (burst copy figure)", "alg_bytes_per_frame": alg_frame,
+                    "alg_bytes_rule": "min(16 B x samples, 4 B x voxels of this rank's brick)", "samples_per_frame": spf,
                     "gsamples_per_s": samples / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0,
                     "trace_share_of_step": trace_ms_max / max(1e-9, ms_max)}
     line = {"metric": metric, "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps,
@@ -440,7 +492,9 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 40 + 276, "d2h_bytes_per_step": W * H * 4},
             "gpu_launches": int(launches_total), "roofline": roofline, "clocks": clocks,
-            "rays_per_frame": int(rays_total), "traced_rays_per_frame": int(traced_total / args.steps), "wall_ms_per_step": t_wall / args.steps * 1e3,
+            "rays_per_frame": int(rays_total), "traced_rays_per_frame": int(traced_total / args.steps),
+            "dequeued_rays_per_frame": int(dequeued_total / args.steps), "wall_ms_per_step": t_wall / args.steps * 1e3,
+            "frames_in_flight": depth, "frame_latency_ms": latency_ms,
             "scene": {"triangles_this_rank": n_tris_local, "bvh_nodes": info["n_nodes"], "bvh_build_ms": info["build_ms"], "mesh_gen_s": t_gen,
                       "commit_s": t_commit}}
     if n_gpus == 1 and not args.no_cpu_baseline:

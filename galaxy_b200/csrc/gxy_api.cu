@@ -161,6 +161,7 @@ struct gxy_context {
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
   PeerArena arena;
+  cudaEvent_t ev_ref = nullptr;  // origin of gxy_stats::t_begin_ms / t_end_ms (context creation, or the last gxy_context_mark)
 };
 
 struct gxy_volume {
@@ -225,9 +226,16 @@ struct Scratch {
   size_t cap = 0;
   int reserve(size_t n) {
     if (n <= cap) return 0;
+    const size_t ncap = (n + n / 4 + 255) & ~(size_t)255;
+    T *np = nullptr;
+    if (cudaMalloc(&np, sizeof(T) * ncap) != cudaSuccess) {  // the old buffer goes too: nothing may write through a stale size
+      gxy_set_error("cudaMalloc of %zu bytes failed: %s", sizeof(T) * ncap, cudaGetErrorString(cudaGetLastError()));
+      release();
+      return 1;
+    }
     if (p) cudaFree(p);
-    cap = (n + n / 4 + 255) & ~(size_t)255;
-    GXY_CUDA(cudaMalloc(&p, sizeof(T) * cap));
+    p = np;
+    cap = ncap;
     return 0;
   }
   void release() {
@@ -235,6 +243,34 @@ struct Scratch {
     p = nullptr;
     cap = 0;
   }
+};
+
+
+// One frame in flight on the fused frame paths (geometry-only Visualizations): its own streams, queues, hit records,
+// partial framebuffer, error flag and -- one process per GPU -- its own peer arena, so that several frames of a
+// RenderingSet overlap on the device the way the reference keeps all Renderings of a set in flight at once
+// (src/apps/gxywriter.cpp:196-264 starts every Rendering before the first wait; RayQManager.cpp:69-82 interleaves their lists).
+#define GXY_MAX_FLIGHTS 8
+struct Flight {
+  bool pending = false, peer = false, sync_done = false;
+  cudaStream_t st = nullptr, lanes[16] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[16] = {}, ev0 = nullptr, ev1 = nullptr;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_ev;  // pool, reused by every frame of this flight
+  size_t n_trace_ev = 0;
+  RayBuf hits, next, cur;
+  Scratch<unsigned long long> fq;
+  Scratch<unsigned> rawhits;
+  Scratch<float> fb;
+  Scratch<unsigned char> proxies;
+  Scratch<int> err;  // this flight's device error flag (SceneParams::error_flag of its launches)
+  PeerArena arena;
+  struct Tail { FusedQueues q[16]; unsigned long long trav[2]; int error, pad; } *h_tail = nullptr;  // page-locked: end-of-frame counters
+  float *fb_result = nullptr;
+  int w = 0, h = 0, n_bands = 1, n_sec_per_hit = 0, peer_k = 0;
+  float epsilon = 0.f;
+  gxy_lighting lights;
+  DevLights L;
+  gxy_stats S;
 };
 
 struct VolOp {
@@ -299,6 +335,7 @@ struct gxy_vis {
   Scratch<float> io_f;
   Scratch<int> io_i;
   int fb_w = 0, fb_h = 0;
+  Flight *flights[GXY_MAX_FLIGHTS] = {};  // frames in flight (gxy_render_submit / gxy_render_wait); [0] also serves gxy_render
 };
 
 static int use_device(gxy_context *c) {
@@ -335,6 +372,8 @@ int gxy_context_create(int device, gxy_context **out) {
   gxy_context *c = new gxy_context();
   c->device = device;
   GXY_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  GXY_CUDA(cudaEventCreate(&c->ev_ref));
+  GXY_CUDA(cudaEventRecord(c->ev_ref, c->stream));
   *out = c;
   return 0;
 }
@@ -348,12 +387,21 @@ void gxy_context_destroy(gxy_context *c) {
     if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
   }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_ref) cudaEventDestroy(c->ev_ref);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 int gxy_context_synchronize(gxy_context *c) {
   if (use_device(c)) return 1;
   GXY_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int gxy_context_mark(gxy_context *c) {
+  GXY_CHECK(c, "NULL context");
+  if (use_device(c)) return 1;
+  GXY_CUDA(cudaDeviceSynchronize());
+  GXY_CUDA(cudaEventRecord(c->ev_ref, c->stream));
+  GXY_CUDA(cudaEventSynchronize(c->ev_ref));
   return 0;
 }
 
@@ -512,6 +560,7 @@ int gxy_vis_create(gxy_context *c, gxy_vis **out) {
   return 0;
 }
 
+static void flight_destroy(gxy_vis *v, Flight *F);
 static void vis_free_commit(gxy_vis *v) {
   if (v->d_tfs) cudaFree(v->d_tfs);
   if (v->d_geoms) cudaFree(v->d_geoms);
@@ -545,6 +594,7 @@ void gxy_vis_destroy(gxy_vis *v) {
   }
   v->proxies.release();
   if (v->h_tail) cudaFreeHost(v->h_tail);
+  for (int k = 0; k < GXY_MAX_FLIGHTS; k++) flight_destroy(v, v->flights[k]);
   delete v;
 }
 
@@ -896,6 +946,7 @@ static int check_error_flag(gxy_vis *v) {
   int e = 0;
   GXY_CUDA(cudaMemcpyAsync(&e, v->d_error, sizeof(int), cudaMemcpyDeviceToHost, v->ctx->stream));
   GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  if (e != 0) GXY_CUDA(cudaMemsetAsync(v->d_error, 0, sizeof(int), v->ctx->stream));  // reported once
   GXY_CHECK(e == 0, "device error flag %d (1: BVH traversal stack overflow, 3: ray list / inbox capacity, 4: peer barrier timeout, 6: TMA copy did not complete)", e);
   return 0;
 }
@@ -1226,8 +1277,7 @@ static int peer_allgather_bytes(gxy_context *c, const void *mine, void *all, siz
   return 0;
 }
 
-static int ensure_peer_arena(gxy_context *c, unsigned npix, unsigned inbox_cap) {
-  PeerArena &A = c->arena;
+static int ensure_peer_arena(gxy_context *c, PeerArena &A, unsigned npix, unsigned inbox_cap) {
   if (A.disabled) return 0;
   if (A.base && A.T.npix >= npix && A.T.inbox_cap >= inbox_cap) return 0;
   GXY_CHECK(c->nranks <= GXY_MAX_RANKS, "peer arenas support up to %d ranks", GXY_MAX_RANKS);
@@ -1293,150 +1343,339 @@ static int ensure_peer_arena(gxy_context *c, unsigned npix, unsigned inbox_cap) 
   return 0;
 }
 
-// The frame on one rank of a multi-process run, geometry-only Visualization: a fixed schedule of kernel
-// launches with no host round trip until the end of the frame.
+// ------------------------------------------------------------------------------------------------
+// Frames in flight.  A Flight owns everything one frame of a geometry-only Visualization mutates, so a frame is
+// SUBMITTED (all its launches enqueued on the flight's streams, no host round trip) and later WAITED for; in between the
+// host submits other flights.  Two frame schedules are submitted this way:
+//   single  one partition without neighbours (the single-GPU frame): the band pipeline
+//   peer    one process per GPU: a fixed schedule of waves over the peer arenas (below)
+// Everything else (volumes, several partitions in one process, the NCCL list exchange) renders synchronously inside the
+// submit call and only hands its image over at the wait.
+static int flight_get(gxy_vis *v, int slot, Flight **out) {
+  GXY_CHECK(slot >= 0 && slot < GXY_MAX_FLIGHTS, "frame slot %d out of range (0..%d)", slot, GXY_MAX_FLIGHTS - 1);
+  Flight *F = v->flights[slot];
+  if (!F) {
+    F = new Flight();
+    v->flights[slot] = F;
+    memset(&F->S, 0, sizeof F->S);
+    GXY_CUDA(cudaStreamCreateWithFlags(&F->st, cudaStreamNonBlocking));
+    GXY_CUDA(cudaEventCreate(&F->ev0));
+    GXY_CUDA(cudaEventCreate(&F->ev1));
+    GXY_CUDA(cudaEventCreateWithFlags(&F->ev_fork, cudaEventDisableTiming));
+    GXY_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&F->h_tail), sizeof(Flight::Tail), cudaHostAllocPortable));
+    memset(F->h_tail, 0, sizeof(Flight::Tail));
+    if (F->err.reserve(4)) return 1;
+    GXY_CUDA(cudaMemsetAsync(F->err.p, 0, sizeof(int) * 4, F->st));
+  }
+  *out = F;
+  return 0;
+}
+
+static void flight_destroy(gxy_vis *v, Flight *F) {
+  if (!F) return;
+  if (F->st) cudaStreamSynchronize(F->st);
+  for (int k = 0; k < 16; k++) {
+    if (F->lanes[k]) { cudaStreamSynchronize(F->lanes[k]); cudaStreamDestroy(F->lanes[k]); }
+    if (F->ev_join[k]) cudaEventDestroy(F->ev_join[k]);
+  }
+  for (auto &e : F->trace_ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  if (F->ev_fork) cudaEventDestroy(F->ev_fork);
+  if (F->ev0) cudaEventDestroy(F->ev0);
+  if (F->ev1) cudaEventDestroy(F->ev1);
+  if (F->st) cudaStreamDestroy(F->st);
+  F->hits.release(); F->next.release(); F->cur.release(); F->fq.release(); F->rawhits.release(); F->fb.release();
+  F->proxies.release(); F->err.release();
+  peer_arena_unmap(F->arena, v->ctx->rank);
+  if (F->arena.base) cudaFree(F->arena.base);
+  if (F->h_tail) cudaFreeHost(F->h_tail);
+  delete F;
+}
+
+static int flight_lane(Flight &F, int k, cudaStream_t *out) {
+  if (!F.lanes[k]) {
+    GXY_CUDA(cudaStreamCreateWithFlags(&F.lanes[k], cudaStreamNonBlocking));
+    GXY_CUDA(cudaEventCreateWithFlags(&F.ev_join[k], cudaEventDisableTiming));
+  }
+  *out = F.lanes[k];
+  return 0;
+}
+static int flight_trace_begin(Flight &F, cudaStream_t st) {
+  if (F.n_trace_ev == F.trace_ev.size()) {
+    cudaEvent_t ta, tb;
+    GXY_CUDA(cudaEventCreate(&ta));
+    GXY_CUDA(cudaEventCreate(&tb));
+    F.trace_ev.push_back(std::make_pair(ta, tb));
+  }
+  GXY_CUDA(cudaEventRecord(F.trace_ev[F.n_trace_ev].first, st));
+  return 0;
+}
+static int flight_trace_end(Flight &F, cudaStream_t st) {
+  GXY_CUDA(cudaEventRecord(F.trace_ev[F.n_trace_ev].second, st));
+  F.n_trace_ev++;
+  return 0;
+}
+// the frame's counters and error flag travel to page-locked memory behind the end-of-frame event; the flag is cleared for
+// the next frame of this flight (a reported error does not poison later frames)
+static int flight_tail(gxy_vis *v, Flight &F, int n_queues) {
+  cudaStream_t st = F.st;
+  GXY_CUDA(cudaMemcpyAsync(F.h_tail->q, F.fq.p, (size_t)n_queues * sizeof(FusedQueues), cudaMemcpyDeviceToHost, st));
+  GXY_CUDA(cudaMemcpyAsync(&F.h_tail->error, F.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GXY_CUDA(cudaMemsetAsync(F.err.p, 0, sizeof(int), st));
+  (void)v;
+  return 0;
+}
+
+// ---- single partition without neighbours: the band pipeline (one GPU) --------------------------------
+// The window is split into interleaved bands of tile rows, each band runs gen -> primary trace -> shade -> secondary
+// trace with its own queues on its own stream.  A persistent trace kernel ends with a drain phase -- the last rays fetched
+// still need their ~30 dependent node visits while most warps have nothing left (ncu: the primary kernel issues on 60 % of
+// its active cycles but only 31 % of all cycles) -- and a frame has two of them; with bands the CTAs of another band's
+// kernel move into the SMs a draining kernel vacates, and primary and secondary phases of different bands overlap.
+// measured on C5 (tools/band_sweep.py; bands on as many streams): 1: 1.69 ms, 2: 1.61, 3: 1.53, 4: 1.43, 6: 1.44-1.51,
+// 8: 1.43-1.53, 16: 1.81; fewer streams than bands is worse than no bands at all (4 bands on 2 streams: 1.99 ms)
+static int flight_submit_single(gxy_vis *v, Flight &F, const DevCamera &C, int w, int h, float epsilon) {
+  const int npix = w * h;
+  const int n_sec_per_hit = F.n_sec_per_hit;
+  int n_bands = 4;
+  if (const char *e = getenv("GXY_BANDS")) n_bands = std::max(1, std::min(16, atoi(e)));
+  int n_lanes = n_bands;
+  if (const char *e = getenv("GXY_BAND_STREAMS")) n_lanes = std::max(1, std::min(16, atoi(e)));
+  n_lanes = std::min(n_lanes, n_bands);
+  const int tiles_x8 = (w + 7) / 8, tiles_y4 = (h + 3) / 4;
+  const size_t qcap = (size_t)tiles_x8 * tiles_y4 * 32;  // queue slots of all bands together (>= npix)
+  cudaStream_t st = F.st;
+  SceneParams P = v->P;
+  P.error_flag = F.err.p;
+  if (F.hits.reserve(qcap, false, st) || F.fq.reserve((size_t)n_bands * sizeof(FusedQueues) / 8) || F.rawhits.reserve((size_t)6 * qcap) ||
+      F.next.reserve(qcap, false, st) || F.cur.reserve(64, false, st) || F.fb.reserve((size_t)npix * 4))
+    return 1;
+  F.n_bands = n_bands;
+  F.fb_result = F.fb.p;
+  F.n_trace_ev = 0;
+  gxy_stats &S = F.S;
+  GXY_CUDA(cudaEventRecord(F.ev0, st));
+  GXY_CUDA(cudaMemsetAsync(F.fb.p, 0, sizeof(float) * 4 * npix, st));
+  GXY_CUDA(cudaMemsetAsync(F.fq.p, 0, (size_t)n_bands * sizeof(FusedQueues), st));
+  auto rays_offset = [](Rays r, size_t off) {
+    float **fcol = &r.ox;
+    for (int k = 0; k < 20; k++) fcol[k] += off;
+    int **icol = &r.x;
+    for (int k = 0; k < 5; k++) icol[k] += off;
+    return r;
+  };
+  if (flight_trace_begin(F, st)) return 1;
+  GXY_CUDA(cudaEventRecord(F.ev_fork, st));
+  for (int k = 1; k < n_lanes; k++) {
+    cudaStream_t sk;
+    if (flight_lane(F, k, &sk)) return 1;
+    GXY_CUDA(cudaStreamWaitEvent(sk, F.ev_fork, 0));
+  }
+  size_t off = 0;
+  for (int b = 0; b < n_bands; b++) {
+    cudaStream_t sb = (b % n_lanes) ? F.lanes[b % n_lanes] : st;
+    const int rows = (tiles_y4 - b + n_bands - 1) / n_bands;
+    if (rows <= 0) continue;
+    const size_t nq = (size_t)tiles_x8 * rows * 32;
+    FusedQueues *qb = reinterpret_cast<FusedQueues *>(F.fq.p) + b;
+    if (launch_fused_primary(P, C, F.L, w, h, F.fb.p, rays_offset(F.next.v, off), F.rawhits.p + off, (unsigned)qcap, rays_offset(F.hits.v, off),
+                             F.cur.v, 0u, qb, epsilon, nullptr, nullptr, b, n_bands, sb))
+      return 1;
+    S.kernel_launches += 3;
+    if (n_sec_per_hit > 0) {
+      if (launch_fused_secondary(P, F.L, w, h, n_sec_per_hit, (long long)nq * n_sec_per_hit, F.fb.p, rays_offset(F.hits.v, off), F.cur.v, 0u, qb,
+                                 epsilon, !v->has_dvr, nullptr, 0, sb))
+        return 1;
+      S.kernel_launches += 1;
+    }
+    off += nq;
+  }
+  for (int k = 1; k < n_lanes; k++) {
+    GXY_CUDA(cudaEventRecord(F.ev_join[k], F.lanes[k]));
+    GXY_CUDA(cudaStreamWaitEvent(st, F.ev_join[k], 0));
+  }
+  if (flight_trace_end(F, st)) return 1;
+  S.waves += n_sec_per_hit > 0 ? 2 : 1;
+  if (flight_tail(v, F, n_bands)) return 1;
+  GXY_CUDA(cudaEventRecord(F.ev1, st));
+  return 0;
+}
+
+// ---- one process per GPU: the frame on one rank ------------------------------------------------------
+// A fixed schedule of kernel launches with no host round trip:
 //   wave 0     generate -> trace primaries -> shade hits; rays that leave go to peer inboxes[0]
 //   wave k>=1  AO/shadow rays of the hits of wave k-1 -> trace inbox[(k-1)&1] -> shade the new hits; leavers go to inboxes[k&1]
 // each wave ends with the flag barrier.  The secondaries of a wave's hits run one wave later on purpose: the rays a rank
 // forwards while tracing reach its neighbours one barrier earlier, so a back partition traces the forwarded primaries
-// while the front partition is busy with its AO/shadow rays (measured on 2 GPUs: the two phases used to run back to
-// back).  A ray crosses at most H = sum(grid_i - 1) partition faces and so does each of its secondaries: 2H + 1 waves
-// after wave 0 suffice for a regular grid; the global count of outstanding work (rays in flight + hits without
-// secondaries) the last barrier leaves behind is checked anyway and further waves run until it is zero.
-static int render_peer(gxy_vis *v, const DevCamera &C, const DevLights &L, const gxy_lighting &lights, int w, int h, float epsilon,
-                       int n_sec_per_hit, gxy_stats *stats) {
-  gxy_context *c = v->ctx;
-  PeerArena &A = c->arena;
-  const PeerTable &T = A.T;
-  cudaStream_t st = c->stream;
+// while the front partition is busy with its AO/shadow rays.  A ray crosses at most H = sum(grid_i - 1) partition faces
+// and so does each of its secondaries: 2H + 1 waves after wave 0 suffice for a regular grid; the global count of
+// outstanding work (rays in flight + hits without secondaries) the last barrier leaves behind is checked at the wait and
+// further waves run until it is zero.  The barriers cost latency, not throughput: while a rank waits in frame f its SMs
+// trace the frames submitted behind it.
+static int peer_wave(gxy_vis *v, Flight &F, const SceneParams &P, int w, int h, bool spawn, bool overlap) {
+  const PeerTable &T = F.arena.T;
+  FusedQueues *q = reinterpret_cast<FusedQueues *>(F.fq.p);
+  float *fb = reinterpret_cast<float *>(F.arena.base + T.off_fb);
+  cudaStream_t st = F.st;
   const int npix = w * h;
-  gxy_stats S;
-  memset(&S, 0, sizeof S);
-  if (v->hits.reserve(npix, false, st) || v->fq.reserve(sizeof(FusedQueues) / 8) || v->rawhits.reserve((size_t)6 * npix) ||
-      v->next.reserve(npix, false, st) || v->cur.reserve(64, false, st) || v->counters.reserve(4) ||
-      v->proxies.reserve(sizeof(PartProxy) * (size_t)c->nranks))
+  gxy_stats &S = F.S;
+  const int k = ++F.peer_k;
+  const int parity_in = (k - 1) & 1;
+  if (flight_trace_begin(F, st)) return 1;
+  // AO/shadow rays of the hits the previous wave found (leavers go to inboxes[k&1]) on a second stream ...
+  cudaStream_t s2 = st;
+  if (spawn && overlap) {
+    if (flight_lane(F, 1, &s2)) return 1;
+    GXY_CUDA(cudaEventRecord(F.ev_fork, st));
+    GXY_CUDA(cudaStreamWaitEvent(s2, F.ev_fork, 0));
+  }
+  if (spawn && launch_fused_secondary(P, F.L, w, h, F.n_sec_per_hit, (long long)npix * F.n_sec_per_hit, fb, F.hits.v, F.cur.v, 0u, q, F.epsilon,
+                                      !v->has_dvr, &T, k & 1, s2))
+    return 1;
+  gxy_timeline_mark("secondary", s2);
+  // ... while this stream traces the rays the neighbours sent during the previous wave (the two only share atomic counters)
+  if (launch_inbox_wave(P, F.L, T, parity_in, w, h, fb, F.rawhits.p, (unsigned)npix, F.hits.v, q, F.epsilon, !v->has_dvr, st)) return 1;
+  if (s2 != st) {
+    GXY_CUDA(cudaEventRecord(F.ev_join[1], s2));
+    GXY_CUDA(cudaStreamWaitEvent(st, F.ev_join[1], 0));
+  }
+  if (flight_trace_end(F, st)) return 1;
+  gxy_timeline_mark("inbox+shade", st);
+  if (launch_wave_epilogue(T, q, ++F.arena.epoch, parity_in, spawn, F.err.p, st)) return 1;
+  gxy_timeline_mark("barrier", st);
+  S.kernel_launches += 3 + (spawn ? 1 : 0);
+  S.waves++;
+  return 0;
+}
+static int peer_finish(gxy_vis *v, Flight &F) {
+  const PeerTable &T = F.arena.T;
+  FusedQueues *q = reinterpret_cast<FusedQueues *>(F.fq.p);
+  cudaStream_t st = F.st;
+  // the queue counters as the last wave's barrier left them (global_pending is the termination test of the wait)
+  if (flight_tail(v, F, 1)) return 1;
+  // framebuffer: every rank sums its slice of all partial images into the owner's final image
+  if (launch_fb_gather(T, st)) return 1;
+  gxy_timeline_mark("fb_gather", st);
+  if (launch_wave_epilogue(T, q, ++F.arena.epoch, -1, false, F.err.p, st)) return 1;
+  gxy_timeline_mark("barrier_end", st);
+  F.S.kernel_launches += 2;
+  GXY_CUDA(cudaEventRecord(F.ev1, st));
+  return 0;
+}
+static int flight_submit_peer(gxy_vis *v, Flight &F, const DevCamera &C, int w, int h, float epsilon) {
+  gxy_context *c = v->ctx;
+  PeerArena &A = F.arena;
+  const PeerTable &T = A.T;
+  cudaStream_t st = F.st;
+  const int npix = w * h;
+  gxy_stats &S = F.S;
+  SceneParams P = v->P;
+  P.error_flag = F.err.p;
+  if (F.hits.reserve(npix, false, st) || F.fq.reserve(sizeof(FusedQueues) / 8) || F.rawhits.reserve((size_t)6 * npix) ||
+      F.next.reserve(npix, false, st) || F.cur.reserve(64, false, st) || F.proxies.reserve(sizeof(PartProxy) * (size_t)c->nranks))
     return 1;
   float *fb = reinterpret_cast<float *>(A.base + T.off_fb);
-  FusedQueues *q = reinterpret_cast<FusedQueues *>(v->fq.p);
-  v->fb_w = w; v->fb_h = h;
-  v->fb_result = c->rank == 0 ? reinterpret_cast<float *>(A.base + T.off_final) : fb;
-  cudaEvent_t ev0, ev1;
-  GXY_CUDA(cudaEventCreate(&ev0));
-  GXY_CUDA(cudaEventCreate(&ev1));
-  GXY_CUDA(cudaEventRecord(ev0, st));
+  FusedQueues *q = reinterpret_cast<FusedQueues *>(F.fq.p);
+  F.n_bands = 1;
+  F.fb_result = c->rank == 0 ? reinterpret_cast<float *>(A.base + T.off_final) : fb;
+  F.n_trace_ev = 0;
+  F.peer_k = 0;
+  GXY_CUDA(cudaEventRecord(F.ev0, st));
   gxy_timeline_mark("start", st);
   GXY_CUDA(cudaMemsetAsync(fb, 0, sizeof(float) * 4 * npix, st));
   GXY_CUDA(cudaMemsetAsync(q, 0, sizeof(FusedQueues), st));
   gxy_timeline_mark("memset", st);
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_events;
-  auto ev_begin = [&]() -> int {
-    cudaEvent_t ta, tb;
-    GXY_CUDA(cudaEventCreate(&ta));
-    GXY_CUDA(cudaEventCreate(&tb));
-    GXY_CUDA(cudaEventRecord(ta, st));
-    trace_events.push_back(std::make_pair(ta, tb));
-    return 0;
-  };
-  auto ev_end = [&]() -> int {
-    GXY_CUDA(cudaEventRecord(trace_events.back().second, st));
-    return 0;
-  };
   // ---- every rank publishes its partition proxy (box, neighbours, top of the BVH) and collects everybody's
-  const bool spawn = n_sec_per_hit > 0;
+  const bool spawn = F.n_sec_per_hit > 0;
   const bool peer_overlap = !(getenv("GXY_PEER_OVERLAP") && atoi(getenv("GXY_PEER_OVERLAP")) == 0);
-  PartProxy *proxies = reinterpret_cast<PartProxy *>(v->proxies.p);
-  if (launch_proxy_publish(v->P, T, st)) return 1;
-  if (launch_wave_epilogue(T, q, ++A.epoch, -1, false, v->d_error, st)) return 1;
+  PartProxy *proxies = reinterpret_cast<PartProxy *>(F.proxies.p);
+  if (launch_proxy_publish(P, T, st)) return 1;
+  if (launch_wave_epilogue(T, q, ++A.epoch, -1, false, F.err.p, st)) return 1;
   if (launch_proxy_gather(T, proxies, st)) return 1;
   gxy_timeline_mark("proxies", st);
   S.kernel_launches += 3;
   // ---- wave 0: generation, trace of the primaries, shading of the hits (their AO/shadow rays follow in wave 1)
-  if (ev_begin()) return 1;
-  if (launch_fused_primary(v->P, C, L, w, h, fb, v->next.v, v->rawhits.p, (unsigned)npix, v->hits.v, v->cur.v, 0u, q, epsilon, &T, proxies, 0, 1, st))
-    return 1;
-  if (ev_end()) return 1;
+  if (flight_trace_begin(F, st)) return 1;
+  if (launch_fused_primary(P, C, F.L, w, h, fb, F.next.v, F.rawhits.p, (unsigned)npix, F.hits.v, F.cur.v, 0u, q, epsilon, &T, proxies, 0, 1, st)) return 1;
+  if (flight_trace_end(F, st)) return 1;
   S.kernel_launches += 3;
-  if (launch_wave_epilogue(T, q, ++A.epoch, -1, spawn, v->d_error, st)) return 1;
+  if (launch_wave_epilogue(T, q, ++A.epoch, -1, spawn, F.err.p, st)) return 1;
   gxy_timeline_mark("barrier0", st);
   S.kernel_launches += 1;
   S.waves = 1;
-  // ---- waves 1..: the bound first, then as long as anything is in flight anywhere
+  // ---- waves 1..bound
   int f[3];
   gxy_factor(c->nranks, f);
   const int bound = 2 * ((f[0] - 1) + (f[1] - 1) + (f[2] - 1)) + (spawn ? 1 : 0);
-  int k = 0;
-  FusedQueues hq;
-  while (true) {
-    const int batch = k == 0 ? bound : 1;
-    for (int b = 0; b < batch; b++) {
-      k++;
-      const int parity_in = (k - 1) & 1;
-      if (ev_begin()) return 1;
-      // AO/shadow rays of the hits the previous wave found (leavers go to inboxes[k&1]) on a second stream ...
-      cudaStream_t s2 = st;
-      if (spawn && peer_overlap) {
-        if (!c->ev_fork) GXY_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        if (!c->lanes[1]) {
-          GXY_CUDA(cudaStreamCreateWithFlags(&c->lanes[1], cudaStreamNonBlocking));
-          GXY_CUDA(cudaEventCreateWithFlags(&c->ev_join[1], cudaEventDisableTiming));
-        }
-        s2 = c->lanes[1];
-        GXY_CUDA(cudaEventRecord(c->ev_fork, st));
-        GXY_CUDA(cudaStreamWaitEvent(s2, c->ev_fork, 0));
+  for (int b = 0; b < bound; b++)
+    if (peer_wave(v, F, P, w, h, spawn, peer_overlap)) return 1;
+  return peer_finish(v, F);
+}
+
+static int flight_wait(gxy_vis *v, Flight &F, gxy_stats *stats) {
+  gxy_context *c = v->ctx;
+  GXY_CHECK(F.pending, "no frame was submitted to this slot");
+  F.pending = false;
+  if (!F.sync_done) {
+    GXY_CUDA(cudaEventSynchronize(F.ev1));
+    int err = F.h_tail->error;
+    if (F.peer && err == 0) {
+      // anything still in flight after the scheduled waves (cannot happen on a regular grid): one wave at a time, every rank alike
+      SceneParams P = v->P;
+      P.error_flag = F.err.p;
+      const bool peer_overlap = !(getenv("GXY_PEER_OVERLAP") && atoi(getenv("GXY_PEER_OVERLAP")) == 0);
+      while (F.h_tail->q[0].global_pending != 0u && F.h_tail->error == 0) {
+        GXY_CHECK(F.peer_k < 4096, "peer wave loop does not terminate (%u units of work in flight)", F.h_tail->q[0].global_pending);
+        if (peer_wave(v, F, P, F.w, F.h, F.n_sec_per_hit > 0, peer_overlap) || peer_finish(v, F)) return 1;
+        GXY_CUDA(cudaEventSynchronize(F.ev1));
       }
-      if (spawn && launch_fused_secondary(v->P, L, w, h, n_sec_per_hit, (long long)npix * n_sec_per_hit, fb, v->hits.v, v->cur.v, 0u, q, epsilon,
-                                          !v->has_dvr, &T, k & 1, s2))
-        return 1;
-      gxy_timeline_mark("secondary", s2);
-      // ... while this stream traces the rays the neighbours sent during the previous wave (the two only share atomic counters)
-      if (launch_inbox_wave(v->P, L, T, parity_in, w, h, fb, v->rawhits.p, (unsigned)npix, v->hits.v, q, epsilon, !v->has_dvr, st)) return 1;
-      if (s2 != st) {
-        GXY_CUDA(cudaEventRecord(c->ev_join[1], s2));
-        GXY_CUDA(cudaStreamWaitEvent(st, c->ev_join[1], 0));
-      }
-      if (ev_end()) return 1;
-      gxy_timeline_mark("inbox+shade", st);
-      if (launch_wave_epilogue(T, q, ++A.epoch, parity_in, spawn, v->d_error, st)) return 1;
-      gxy_timeline_mark("barrier", st);
-      S.kernel_launches += 3 + (spawn ? 1 : 0);
-      S.waves++;
+      err = F.h_tail->error;
     }
-    GXY_CUDA(cudaMemcpyAsync(&hq, q, sizeof hq, cudaMemcpyDeviceToHost, st));
-    GXY_CUDA(cudaStreamSynchronize(st));
-    if (check_error_flag(v)) return 1;
-    if (hq.global_pending == 0u) break;
-    GXY_CHECK(k < 4096, "peer wave loop does not terminate (%u units of work in flight)", hq.global_pending);
+    GXY_CHECK(err == 0, "device error flag %d (1: BVH traversal stack overflow, 3: ray list / inbox capacity, 4: peer barrier timeout, 6: TMA copy did not complete)", err);
+    gxy_stats &S = F.S;
+    FusedQueues t = F.h_tail->q[0];
+    for (int b = 1; b < F.n_bands; b++) {
+      const FusedQueues &o = F.h_tail->q[b];
+      t.n_generated += o.n_generated; t.n_hits += o.n_hits; t.n_terminated += o.n_terminated; t.n_primary32 += o.n_primary32;
+      t.nodes += o.nodes; t.prims += o.prims; t.n_spill += o.n_spill;
+    }
+    const int nsec = F.n_sec_per_hit;
+    S.primary_rays = (long long)t.n_generated;
+    S.ao_rays = (long long)t.n_hits * F.lights.n_ao;
+    S.shadow_rays = (long long)t.n_hits * (F.lights.shadows ? F.lights.n_lights : 0);
+    S.terminated_rays = (long long)t.n_terminated;
+    S.nodes_visited = (long long)t.nodes;
+    S.prims_tested = (long long)t.prims;
+    if (F.peer) {
+      S.forwarded_rays = (long long)t.n_spill + (long long)t.n_virtual;
+      S.traced_rays = (long long)t.n_generated + (long long)t.n_hits * nsec + (long long)t.n_inbox;
+      S.dequeued_rays = (long long)t.n_primary32 + (long long)t.n_hits * nsec + (long long)t.n_inbox;
+    } else {
+      S.traced_rays = (long long)t.n_generated + (long long)t.n_hits * nsec;
+      S.dequeued_rays = (long long)t.n_primary32 + (long long)t.n_hits * nsec;
+    }
+    cudaEventElapsedTime(&S.device_ms, F.ev0, F.ev1);
+    cudaEventElapsedTime(&S.t_begin_ms, c->ev_ref, F.ev0);
+    cudaEventElapsedTime(&S.t_end_ms, c->ev_ref, F.ev1);
+    S.trace_ms = 0.f;
+    for (size_t k = 0; k < F.n_trace_ev; k++) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, F.trace_ev[k].first, F.trace_ev[k].second);
+      S.trace_ms += ms;
+    }
+#ifdef GXY_TRAV_COUNTERS
+    {
+      unsigned long long trav[2] = {0ull, 0ull};
+      GXY_CUDA(cudaMemcpy(trav, v->P.trav_counters, sizeof trav, cudaMemcpyDeviceToHost));
+      GXY_CUDA(cudaMemset(v->P.trav_counters, 0, sizeof trav));
+      S.nodes_visited += (long long)trav[0];
+      S.prims_tested += (long long)trav[1];
+    }
+#endif
+    if (F.peer) timeline_print(c->rank);
   }
-  // ---- framebuffer: every rank sums its slice of all partial images into the owner's final image
-  gxy_timeline_mark("hostsync", st);
-  if (launch_fb_gather(T, st)) return 1;
-  gxy_timeline_mark("fb_gather", st);
-  if (launch_wave_epilogue(T, q, ++A.epoch, -1, false, v->d_error, st)) return 1;
-  gxy_timeline_mark("barrier_end", st);
-  S.kernel_launches += 2;
-  GXY_CUDA(cudaEventRecord(ev1, st));
-  GXY_CUDA(cudaEventSynchronize(ev1));
-  cudaEventElapsedTime(&S.device_ms, ev0, ev1);
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
-  timeline_print(c->rank);
-  for (auto &e : trace_events) {
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e.first, e.second);
-    S.trace_ms += ms;
-    cudaEventDestroy(e.first);
-    cudaEventDestroy(e.second);
-  }
-  if (check_error_flag(v)) return 1;
-  S.primary_rays = (long long)hq.n_generated;
-  S.ao_rays = (long long)hq.n_hits * lights.n_ao;
-  S.shadow_rays = (long long)hq.n_hits * (lights.shadows ? lights.n_lights : 0);
-  S.forwarded_rays = (long long)hq.n_spill + (long long)hq.n_virtual;
-  S.terminated_rays = (long long)hq.n_terminated;
-  S.traced_rays = (long long)hq.n_generated + (long long)hq.n_hits * n_sec_per_hit + (long long)hq.n_inbox;
-  S.nodes_visited = (long long)hq.nodes;
-  S.prims_tested = (long long)hq.prims;
-  if (stats) *stats = S;
+  v->fb_w = F.w; v->fb_h = F.h;
+  v->fb_result = F.fb_result;
+  if (stats) *stats = F.S;
   return 0;
 }
 
@@ -1450,8 +1689,8 @@ static int render_peer(gxy_vis *v, const DevCamera &C, const DevLights &L, const
 // send/recv across processes) and appended to the destination's next list.  The loop ends when no
 // partition has rays left (global sum), which replaces the reference's busy/idle tree +
 // MPI_Allreduce termination protocol (RenderingSet.cpp:289-589).
-int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const gxy_lighting *lights_in, int w, int h, float epsilon,
-               gxy_stats *stats) {
+static int render_sync(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const gxy_lighting *lights_in, int w, int h, float epsilon,
+                       gxy_stats *stats) {
   GXY_CHECK(nparts >= 1 && parts && cam && lights_in && w > 0 && h > 0, "gxy_render: bad arguments");
   for (int p = 0; p < nparts; p++)
     if (check_vis(parts[p])) return 1;
@@ -1487,19 +1726,6 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
   for (int p = 0; p < nparts; p++)
     for (const GeomOp &g : parts[p]->geoms) fused = fused && g.kind != 2;
   if (const char *e = getenv("GXY_FUSED")) fused = fused && atoi(e) != 0;
-  if (multi_proc && fused) {
-    // one process per GPU, geometry only: rays and pixels move through peer arenas, not through NCCL
-    if (const char *e = getenv("GXY_PEER"))
-      if (atoi(e) == 0) ctx0->arena.disabled = true;
-    const unsigned long long cap = (unsigned long long)npix * (unsigned long long)(1 + n_sec_per_hit);
-    GXY_CHECK(cap < (1ull << 31), "peer inbox too large (%llu records)", cap);
-    if (ensure_peer_arena(ctx0, (unsigned)npix, (unsigned)cap)) return 1;
-    if (!ctx0->arena.disabled) {
-      cudaEventDestroy(ev0);
-      cudaEventDestroy(ev1);
-      return render_peer(parts[0], C, L, lights, w, h, epsilon, n_sec_per_hit, stats);
-    }
-  }
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_events;
   for (int p = 0; p < nparts; p++) {
     gxy_vis *v = parts[p];
@@ -1518,32 +1744,10 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
     static_assert(sizeof(FusedQueues) == 96, "FusedQueues layout");
     std::vector<FusedQueues> fq(nparts);
     std::vector<bool> can_spill(nparts, false);
-    // Band pipeline (one partition without neighbours, i.e. the single-GPU frame): the window is split into interleaved
-    // bands of tile rows, each band runs gen -> primary trace -> shade -> secondary trace with its own queues on its own
-    // stream.  A persistent trace kernel ends with a drain phase -- the last rays fetched still need their ~30 dependent
-    // node visits while most warps have nothing left (ncu: the primary kernel issues on 60 % of its active cycles but
-    // only 31 % of all cycles) -- and a frame has two of them; with bands the CTAs of another band's kernel move into
-    // the SMs a draining kernel vacates, and primary and secondary phases of different bands overlap.
-    int n_bands = 1;
-    {
-      bool alone = nparts == 1;
-      for (int f = 0; f < 6 && alone; f++) alone = parts[0]->neighbors[f] < 0;
-      if (alone) {
-        // measured on C5 (tools/band_sweep.py; bands on as many streams): 1: 1.69 ms, 2: 1.61, 3: 1.53, 4: 1.43, 6: 1.44-1.51, 8: 1.43-1.53,
-        // 16: 1.81; fewer streams than bands is worse than no bands at all (4 bands on 2 streams: 1.99 ms)
-        n_bands = 4;
-        if (const char *e = getenv("GXY_BANDS")) n_bands = std::max(1, std::min(16, atoi(e)));
-      }
-    }
+    // (a single partition without neighbours never gets here: it is a Flight, flight_submit_single)
+    const int n_bands = 1;
     const int tiles_x8 = (w + 7) / 8, tiles_y4 = (h + 3) / 4;
     const size_t qcap = (size_t)tiles_x8 * tiles_y4 * 32;  // queue slots of all bands together (>= npix)
-    auto rays_offset = [](Rays r, size_t off) {
-      float **fcol = &r.ox;
-      for (int k = 0; k < 20; k++) fcol[k] += off;
-      int **icol = &r.x;
-      for (int k = 0; k < 5; k++) icol[k] += off;
-      return r;
-    };
     // ---- primary rays: generate -> trace -> light -> framebuffer, hit records for the secondaries
     for (int p = 0; p < nparts; p++) {
       gxy_vis *v = parts[p];
@@ -1558,45 +1762,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       GXY_CUDA(cudaEventCreate(&ta));
       GXY_CUDA(cudaEventCreate(&tb));
       GXY_CUDA(cudaEventRecord(ta, st));
-      if (n_bands > 1) {
-        gxy_context *c = v->ctx;
-        int n_lanes = n_bands;
-        if (const char *e = getenv("GXY_BAND_STREAMS")) n_lanes = std::max(1, std::min(16, atoi(e)));
-        n_lanes = std::min(n_lanes, n_bands);
-        if (!c->ev_fork) GXY_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        GXY_CUDA(cudaEventRecord(c->ev_fork, st));
-        for (int k = 1; k < n_lanes; k++) {
-          if (!c->lanes[k]) {
-            GXY_CUDA(cudaStreamCreateWithFlags(&c->lanes[k], cudaStreamNonBlocking));
-            GXY_CUDA(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
-          }
-          GXY_CUDA(cudaStreamWaitEvent(c->lanes[k], c->ev_fork, 0));
-        }
-        size_t off = 0;
-        for (int b = 0; b < n_bands; b++) {
-          cudaStream_t sb = (b % n_lanes) ? c->lanes[b % n_lanes] : st;
-          const int rows = (tiles_y4 - b + n_bands - 1) / n_bands;
-          if (rows <= 0) continue;
-          const size_t nq = (size_t)tiles_x8 * rows * 32;
-          FusedQueues *qb = reinterpret_cast<FusedQueues *>(v->fq.p) + b;
-          if (launch_fused_primary(v->P, C, L, w, h, v->fb.p, rays_offset(v->next.v, off), v->rawhits.p + off, (unsigned)qcap,
-                                   rays_offset(v->hits.v, off), v->cur.v, 0u, qb, epsilon, nullptr, nullptr, b, n_bands, sb))
-            return 1;
-          S.kernel_launches += 3;
-          if (n_sec_per_hit > 0) {
-            if (launch_fused_secondary(v->P, L, w, h, n_sec_per_hit, (long long)nq * n_sec_per_hit, v->fb.p, rays_offset(v->hits.v, off), v->cur.v, 0u,
-                                       qb, epsilon, !v->has_dvr, nullptr, 0, sb))
-              return 1;
-            S.kernel_launches += 1;
-          }
-          off += nq;
-        }
-        for (int k = 1; k < n_lanes; k++) {
-          GXY_CUDA(cudaEventRecord(c->ev_join[k], c->lanes[k]));
-          GXY_CUDA(cudaStreamWaitEvent(st, c->ev_join[k], 0));
-        }
-        S.waves += n_sec_per_hit > 0 ? 2 : 1;
-      } else {
+      {
         if (launch_fused_primary(v->P, C, L, w, h, v->fb.p, v->next.v, v->rawhits.p, (unsigned)qcap, v->hits.v, v->cur.v,
                                  can_spill[p] ? (unsigned)v->cur.cap : 0u, reinterpret_cast<FusedQueues *>(v->fq.p), epsilon, nullptr, nullptr, 0, 1,
                                  st))
@@ -1611,7 +1777,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
     // ---- secondary rays.  A partition without neighbours cannot spill: no host round trip at all.
     for (int p = 0; p < nparts; p++) {
       gxy_vis *v = parts[p];
-      if (n_sec_per_hit == 0 || n_bands > 1) continue;
+      if (n_sec_per_hit == 0) continue;
       if (use_device(v->ctx)) return 1;
       cudaStream_t st = v->ctx->stream;
       long long max_rays = (long long)npix * n_sec_per_hit;
@@ -1634,28 +1800,20 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       S.kernel_launches += 1;
       S.waves++;
     }
-    std::vector<FusedQueues> bq((size_t)n_bands);
     for (int p = 0; p < nparts; p++) {
       gxy_vis *v = parts[p];
       if (use_device(v->ctx)) return 1;
-      GXY_CUDA(cudaMemcpyAsync(n_bands > 1 ? bq.data() : &fq[p], v->fq.p, (size_t)n_bands * sizeof(FusedQueues), cudaMemcpyDeviceToHost,
-                               v->ctx->stream));
+      GXY_CUDA(cudaMemcpyAsync(&fq[p], v->fq.p, sizeof(FusedQueues), cudaMemcpyDeviceToHost, v->ctx->stream));
     }
     for (int p = 0; p < nparts; p++) {
       gxy_vis *v = parts[p];
       if (use_device(v->ctx)) return 1;
       GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
-      if (n_bands > 1) {  // the sum over the bands is the partition's frame
-        fq[p] = bq[0];
-        for (int b = 1; b < n_bands; b++) {
-          fq[p].n_generated += bq[b].n_generated; fq[p].n_hits += bq[b].n_hits; fq[p].n_terminated += bq[b].n_terminated;
-          fq[p].nodes += bq[b].nodes; fq[p].prims += bq[b].prims; fq[p].n_spill += bq[b].n_spill;
-        }
-      }
       S.primary_rays += (long long)fq[p].n_generated;
       S.ao_rays += (long long)fq[p].n_hits * lights.n_ao;
       S.shadow_rays += (long long)fq[p].n_hits * (lights.shadows ? lights.n_lights : 0);
       S.traced_rays += (long long)fq[p].n_generated + (long long)fq[p].n_hits * n_sec_per_hit;
+      S.dequeued_rays += (long long)fq[p].n_primary32 + (long long)fq[p].n_hits * n_sec_per_hit;
       S.terminated_rays += (long long)fq[p].n_terminated;
       S.nodes_visited += (long long)fq[p].nodes;
       S.prims_tested += (long long)fq[p].prims;
@@ -1684,7 +1842,9 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
   std::vector<std::vector<int>> send_counts(nparts, std::vector<int>(nranks, 0)), send_offsets(nparts, std::vector<int>(nranks + 1, 0));
   std::vector<int> n_spawn(nparts, 0);
   std::vector<int> all_counts;  // multi-process: nranks x (nranks+1)
-  for (int wave = 0; wave < 100000; wave++) {
+  const int wave_cap = 100000;
+  int wave = 0;
+  for (; wave < wave_cap; wave++) {
     // the spill lists of the fused kernels enter the loop at its exchange step
     const bool lists_classified = fused && wave == 0;
     long long pending_local = 0;
@@ -1714,6 +1874,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
       if (launch_hit_scan(v->cur.v, n, v->hit_index.p, v->block_sums.p, v->small.p, st)) return 1;
       S.kernel_launches += 4;
       S.traced_rays += n;
+      S.dequeued_rays += n;
       S.waves++;
     }
     // ---- read hit counts, size the next lists, shade + spawn, classify, accumulate, sort ----
@@ -1858,6 +2019,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
     }
   }
 
+  GXY_CHECK(wave < wave_cap, "the wave loop did not terminate after %d waves", wave_cap);
   PT.mark("exchange_tail");
   // ---- framebuffer: partial sums -> owner (SendPixelsMsg / AddLocalPixels) ----
   if (!multi_proc) {
@@ -1893,6 +2055,7 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
     GXY_CUDA(cudaMemcpyAsync(v->h_tail->trav, v->P.trav_counters, sizeof v->h_tail->trav, cudaMemcpyDeviceToHost, st));
     GXY_CUDA(cudaMemsetAsync(v->P.trav_counters, 0, sizeof v->h_tail->trav, st));
     GXY_CUDA(cudaMemcpyAsync(&v->h_tail->error, v->d_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GXY_CUDA(cudaMemsetAsync(v->d_error, 0, sizeof(int), st));  // reported once: a transient error does not poison the Visualization
   }
   if (use_device(ctx0)) return 1;
   GXY_CUDA(cudaEventSynchronize(ev1));
@@ -1924,6 +2087,100 @@ int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const g
   }
   if (stats) *stats = S;
   return 0;
+}
+
+// which frame schedule a set of partitions takes: 0 = synchronous list/fused loop (render_sync), 1 = single-partition band
+// pipeline as a Flight, 2 = one process per GPU over peer arenas as a Flight
+static int frame_kind(int nparts, gxy_vis *const *parts) {
+  bool fused = true;
+  for (int p = 0; p < nparts; p++) fused = fused && parts[p]->P.n_volvis == 0 && !parts[p]->geoms.empty();
+  for (int p = 0; p < nparts; p++)
+    for (const GeomOp &g : parts[p]->geoms) fused = fused && g.kind != 2;  // PathLines: list-path kernels only
+  if (const char *e = getenv("GXY_FUSED")) fused = fused && atoi(e) != 0;
+  if (!fused) return 0;
+  if (parts[0]->ctx->comm) {
+    if (const char *e = getenv("GXY_PEER"))
+      if (atoi(e) == 0) return 0;
+    return 2;
+  }
+  bool alone = nparts == 1;
+  for (int f = 0; f < 6 && alone; f++) alone = parts[0]->neighbors[f] < 0;
+  return alone ? 1 : 0;
+}
+
+int gxy_render_submit(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const gxy_lighting *lights_in, int w, int h, float epsilon,
+                      int slot) {
+  GXY_CHECK(nparts >= 1 && parts && cam && lights_in && w > 0 && h > 0, "gxy_render: bad arguments");
+  for (int p = 0; p < nparts; p++)
+    if (check_vis(parts[p])) return 1;
+  gxy_vis *v = parts[0];
+  gxy_context *c = v->ctx;
+  GXY_CHECK(!c->comm || nparts == 1, "with a communicator attached each process drives exactly one partition");
+  if (use_device(c)) return 1;
+  Flight *Fp = nullptr;
+  if (flight_get(v, slot, &Fp)) return 1;
+  Flight &F = *Fp;
+  GXY_CHECK(!F.pending, "frame slot %d is still in flight (call gxy_render_wait first)", slot);
+  gxy_lighting lights;
+  if (gxy_resolve_lights(lights_in, cam, &lights)) return 1;
+  GXY_CHECK(lights.n_lights >= 1, "lighting needs at least one light");
+  memset(&F.S, 0, sizeof F.S);
+  F.lights = lights;
+  F.L = make_dev_lights(lights);
+  F.n_sec_per_hit = lights.n_ao + (lights.shadows ? lights.n_lights : 0);
+  F.w = w; F.h = h; F.epsilon = epsilon;
+  F.sync_done = false;
+  F.peer = false;
+  const DevCamera C = make_dev_camera(*cam, w, h);
+  // an image still being converted for a download reads the framebuffer this frame is about to clear
+  for (int s = 0; s < 2; s++)
+    if (v->async_ready[s]) GXY_CUDA(cudaStreamWaitEvent(F.st, v->async_ready[s], 0));
+  int kind = frame_kind(nparts, parts);
+  if (kind == 2) {
+    const unsigned long long cap = (unsigned long long)w * h * (unsigned long long)(1 + F.n_sec_per_hit);
+    GXY_CHECK(cap < (1ull << 31), "peer inbox too large (%llu records)", cap);
+    if (c->arena.disabled) F.arena.disabled = true;  // (decided once, by flight 0, on every rank alike)
+    if (ensure_peer_arena(c, F.arena, (unsigned)(w * h), (unsigned)cap)) return 1;
+    if (F.arena.disabled) { c->arena.disabled = true; kind = 0; }
+  }
+  if (kind == 1) {
+    if (flight_submit_single(v, F, C, w, h, epsilon)) return 1;
+  } else if (kind == 2) {
+    F.peer = true;
+    if (flight_submit_peer(v, F, C, w, h, epsilon)) return 1;
+  } else {
+    // synchronous schedules render here; the image is kept in the flight's own buffer until the wait
+    if (render_sync(nparts, parts, cam, lights_in, w, h, epsilon, &F.S)) return 1;
+    if (c->rank == 0 || !c->comm) {
+      if (F.fb.reserve((size_t)w * h * 4)) return 1;
+      GXY_CUDA(cudaMemcpyAsync(F.fb.p, v->fb_result, sizeof(float) * 4 * (size_t)w * h, cudaMemcpyDeviceToDevice, c->stream));
+      GXY_CUDA(cudaStreamSynchronize(c->stream));
+      F.fb_result = F.fb.p;
+    } else F.fb_result = v->fb_result;
+    F.sync_done = true;
+  }
+  F.pending = true;
+  return 0;
+}
+
+int gxy_render_wait(int nparts, gxy_vis *const *parts, int slot, gxy_stats *stats) {
+  GXY_CHECK(nparts >= 1 && parts && parts[0], "gxy_render_wait: bad arguments");
+  gxy_vis *v = parts[0];
+  GXY_CHECK(slot >= 0 && slot < GXY_MAX_FLIGHTS && v->flights[slot], "frame slot %d was never submitted", slot);
+  if (use_device(v->ctx)) return 1;
+  return flight_wait(v, *v->flights[slot], stats);
+}
+
+int gxy_render_max_slots(void) { return GXY_MAX_FLIGHTS; }
+
+int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const gxy_lighting *lights_in, int w, int h, float epsilon,
+               gxy_stats *stats) {
+  GXY_CHECK(nparts >= 1 && parts && cam && lights_in && w > 0 && h > 0, "gxy_render: bad arguments");
+  for (int p = 0; p < nparts; p++)
+    if (check_vis(parts[p])) return 1;
+  if (frame_kind(nparts, parts) == 0 || (parts[0]->ctx->comm && parts[0]->ctx->arena.disabled)) return render_sync(nparts, parts, cam, lights_in, w, h, epsilon, stats);
+  if (gxy_render_submit(nparts, parts, cam, lights_in, w, h, epsilon, 0)) return 1;
+  return gxy_render_wait(nparts, parts, 0, stats);
 }
 
 // ---- interactive frame path (Rendering.cpp:104-153) -----------------------------------------------

@@ -39,7 +39,8 @@ class RayListView(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in ("primary_rays", "shadow_rays", "ao_rays", "forwarded_rays", "terminated_rays", "traced_rays",
                                             "waves", "kernel_launches")] + [("device_ms", C.c_float), ("trace_ms", C.c_float),
-                                                                                ("nodes_visited", C.c_longlong), ("prims_tested", C.c_longlong), ("volume_samples", C.c_longlong), ("staged_samples", C.c_longlong)]
+                                                                                ("nodes_visited", C.c_longlong), ("prims_tested", C.c_longlong), ("volume_samples", C.c_longlong), ("staged_samples", C.c_longlong),
+                                                                                ("dequeued_rays", C.c_longlong), ("t_begin_ms", C.c_float), ("t_end_ms", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -116,6 +117,9 @@ def lib():
         L.gxy_generate_rays.argtypes = [vp, C.POINTER(Camera), C.c_int, C.c_int, RayListView, ip]
         L.gxy_intersect.argtypes = [vp, C.c_int, fp, fp, fp, fp, ip, fp]
         L.gxy_render.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(Camera), C.POINTER(Lighting), C.c_int, C.c_int, C.c_float, C.POINTER(Stats)]
+        L.gxy_render_submit.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(Camera), C.POINTER(Lighting), C.c_int, C.c_int, C.c_float, C.c_int]
+        L.gxy_render_wait.argtypes = [C.c_int, C.POINTER(vp), C.c_int, C.POINTER(Stats)]
+        L.gxy_context_mark.argtypes = [vp]
         L.gxy_frame_download_rgba32f.argtypes = [vp, fp]
         L.gxy_frame_download_rgba8.argtypes = [vp, C.POINTER(C.c_ubyte)]
         L.gxy_frame_download_rgba8_async.argtypes = [vp, C.POINTER(C.c_ubyte)]
@@ -196,6 +200,10 @@ class Context:
         if device not in cls._default:
             cls._default[device] = Context(device)
         return cls._default[device]
+
+    def mark(self):
+        """device idle + origin of the t_begin_ms / t_end_ms frame stamps (gxy_context_mark)"""
+        check(lib().gxy_context_mark(self.h))
 
     def synchronize(self):
         check(lib().gxy_context_synchronize(self.h))
@@ -394,12 +402,8 @@ def pinned_array(shape, dtype):
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
     owner = _Pinned(n)
     buf = (C.c_ubyte * n).from_address(owner.p.value)
-    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-    _PINNED_OWNERS[id(buf)] = owner  # keep the allocation alive as long as the module is
-    return arr
-
-
-_PINNED_OWNERS = {}
+    buf._gxy_owner = owner  # the ctypes buffer is the base object of the array: the allocation lives exactly as long as any view of it
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
 
 def render_progressive(parts, camera, lighting, w, h, frame, epsilon=0.001):
@@ -423,6 +427,25 @@ def sample(parts, camera, w, h):
     cam, st = make_camera(camera), Stats()
     check(lib().gxy_sample(len(parts), arr, C.byref(cam), w, h, C.byref(st)))
     return [p.samples() for p in parts], st.as_dict()
+
+
+def render_submit(parts, camera, lighting, w, h, epsilon=0.001, slot=0):
+    """Enqueue one frame of a RenderingSet on frame slot `slot` (gxy_render_submit); returns without waiting for the device."""
+    arr = (C.c_void_p * len(parts))(*[p.h for p in parts])
+    cam, L = make_camera(camera), make_lighting(lighting)
+    check(lib().gxy_render_submit(len(parts), arr, C.byref(cam), C.byref(L), w, h, epsilon, slot))
+
+
+def render_wait(parts, slot=0):
+    """Wait for the frame on `slot`; it becomes the last frame of parts[0] for the download calls.  Returns its stats."""
+    arr = (C.c_void_p * len(parts))(*[p.h for p in parts])
+    st = Stats()
+    check(lib().gxy_render_wait(len(parts), arr, slot, C.byref(st)))
+    return st.as_dict()
+
+
+def max_slots():
+    return lib().gxy_render_max_slots()
 
 
 def render_device(parts, camera, lighting, w, h, epsilon=0.001):

@@ -92,6 +92,10 @@ typedef struct {
   long long prims_tested;     /* the library was compiled with -DGXY_TRAV_COUNTERS            */
   long long volume_samples;   /* trilinear volume samples taken by the march (SampleVolumes x volumes) */
   long long staged_samples;   /* ... of which served from TMA-staged shared-memory boxes (GXY_MARCH_TMA=1)      */
+  long long dequeued_rays;    /* rays the trace launches actually took from a queue or list: traced_rays minus the
+                                 primaries the generation kernel finished itself (they can reach no primitive)    */
+  float     t_begin_ms;       /* frames in flight: start and end of this frame on the device, relative to the    */
+  float     t_end_ms;         /* last gxy_context_mark (or the creation of the context)                          */
 } gxy_stats;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -104,6 +108,8 @@ int gxy_device_count(void);
 int  gxy_context_create(int device, gxy_context **out);
 void gxy_context_destroy(gxy_context *);
 int  gxy_context_synchronize(gxy_context *);
+/* waits for the device to go idle and makes "now" the origin of gxy_stats::t_begin_ms / t_end_ms */
+int  gxy_context_mark(gxy_context *);
 
 /* ---- datasets (partition-local data, copied H2D once) -------------------------------------- */
 /* replaces ospNewVolume("shared_structured_volume") + ospSet* in OsprayVolume::OsprayVolume
@@ -246,6 +252,21 @@ int  gxy_particles_from_samples(gxy_vis *, gxy_particles **out);
  * on the device of parts[0] (image owner = rank 0); fetch it with gxy_frame_download_*. */
 int  gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *, const gxy_lighting *, int w, int h,
                 float epsilon, gxy_stats *stats);
+/* A RenderingSet in flight.  The reference starts every Rendering of a set before it waits for any of them
+ * (src/apps/gxywriter.cpp:196-264; RenderingSet::WaitForDone, RenderingSet.cpp:289-589) and its ray queue interleaves their
+ * lists (src/renderer/RayQManager.cpp:69-82), so a rank that has nothing left to do for one Rendering works on the next.
+ * gxy_render_submit enqueues one frame on frame slot `slot` (0 .. gxy_render_max_slots()-1) and returns without waiting for
+ * the device; gxy_render_wait blocks until that frame is complete, fills `stats` and makes it "the last frame" of parts[0]
+ * for gxy_frame_download_*.  Every slot owns its queues, framebuffer and (one process per GPU) peer arena: frames on
+ * different slots overlap on the device, and a barrier a rank waits at in one frame costs latency, not throughput.
+ * With a communicator attached the calls are collective: every rank submits and waits for the same slots in the same order.
+ * Geometry-only Visualizations are enqueued without any host round trip; all others (volumes, PathLines, several partitions
+ * in one process) render synchronously inside the submit call and hand their image over at the wait.
+ * gxy_render == submit + wait on slot 0. */
+int  gxy_render_submit(int nparts, gxy_vis *const *parts, const gxy_camera *, const gxy_lighting *, int w, int h,
+                       float epsilon, int slot);
+int  gxy_render_wait(int nparts, gxy_vis *const *parts, int slot, gxy_stats *stats);
+int  gxy_render_max_slots(void);
 /* D2H of the last frame: float RGBA (y up) ... */
 int  gxy_frame_download_rgba32f(gxy_vis *owner, float *fb);
 /* ... or RGBA8 rows top-down exactly as ColorImageWriter::Write does (ImageWriter.cpp:30-48) */

@@ -40,6 +40,20 @@ def main():
         dist.all_reduce(t)
         results[mode] = (dict(zip(keys, t.tolist())), part.download_rgba32f(w, h) if rank == 0 else None)
     os.environ.pop("GXY_FUSED", None)
+    # frames in flight over the peer arenas (gxy_render_submit / gxy_render_wait): three cameras on three slots, submitted before
+    # the first wait; every slot must deliver the frame of ITS camera
+    fl_cams = [scenes.parse_camera({"viewpoint": vp, "viewcenter": [0, 0, 0], "viewup": [0, 1, 0], "aov": 30}) for vp in ([3, 2, -4], [-3, 1, -4], [0.5, 3, -4.5], [4, -1, 2])]
+    depth = 3
+    for k in range(depth):
+        gpu.render_submit([part], fl_cams[k], vis["lighting"], w, h, 0.001, k)
+    flights = []
+    for k in range(len(fl_cams)):
+        st = gpu.render_wait([part], k % depth)
+        t = torch.tensor([st[key] for key in keys], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        flights.append((dict(zip(keys, t.tolist())), part.download_rgba32f(w, h) if rank == 0 else None))
+        if k + depth < len(fl_cams):
+            gpu.render_submit([part], fl_cams[k + depth], vis["lighting"], w, h, 0.001, k % depth)
     # BASELINE.json configs[1]: tests/nineBalls.state (two volumes: DVR + isosurfaces + slice, shadows), volume bricks over the ranks
     st9 = scenes.parse_state(json.load(open(os.path.join(ROOT, "tests", "golden", "states", "nineBalls.state"))))
     ds9 = scenes.load_datasets(st9, scenes.default_data_provider(n=96))
@@ -70,6 +84,13 @@ def main():
         fb_o, st_o = oracle.render(o_parts, cam, vis["lighting"], w, h, 0.001)
         o9 = scenes.build_partitions(oracle, vis9, ds9, world)
         fb_o9, st_o9 = oracle.render(o9, cam9, vis9["lighting"], w9, h9, st9["epsilon"])
+        for k, (st, fb) in enumerate(flights):
+            fb_f, st_f = oracle.render(o_parts, fl_cams[k], vis["lighting"], w, h, 0.001)
+            frac = float((np.abs(fb[..., :3] - fb_f[..., :3]).max(-1) <= 1.0 / 255).mean())
+            same = all(st[key] == st_f[key] for key in st)
+            print(json.dumps({"mode": "flight %d (slot %d)" % (k, k % depth), "world": world, "fraction_within_1_255": frac, "stats_equal": same,
+                              "gpu": st, "oracle": {key: st_f[key] for key in st}}), flush=True)
+            ok = ok and same and frac >= 0.999
         for mode, (st, fb) in results.items():
             ref_fb, ref_st = (fb_o9, st_o9) if mode == "nineBalls" else (fb_opl, st_opl) if mode == "pathlines" else (fb_o, st_o)
             frac = float((np.abs(fb[..., :3] - ref_fb[..., :3]).max(-1) <= 1.0 / 255).mean())
