@@ -365,6 +365,8 @@ int gxy_device_count(void) {
 }
 
 int gxy_context_create(int device, gxy_context **out) {
+  // frames in flight use many streams; effective only if the CUDA context does not exist yet (see gxy_render_submit)
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int n = gxy_device_count();
   GXY_CHECK(n > 0, "no CUDA device available: galaxy_b200 has no CPU fallback");
   GXY_CHECK(device >= 0 && device < n, "invalid device %d (have %d)", device, n);
@@ -1436,7 +1438,12 @@ static int flight_tail(gxy_vis *v, Flight &F, int n_queues) {
 static int flight_submit_single(gxy_vis *v, Flight &F, const DevCamera &C, int w, int h, float epsilon) {
   const int npix = w * h;
   const int n_sec_per_hit = F.n_sec_per_hit;
-  int n_bands = 4;
+  // alone on the device a frame fills the drain phases of its trace kernels with its own bands (4); behind other frames in flight
+  // their kernels do that, and one band per frame is faster (measured on C5, tools/flight_sweep.py: 4 in flight, 4 bands 1.215 ms,
+  // 2 bands 1.160, 1 band 1.102 per frame; 1 in flight: 1.447 / 1.635 / 1.703)
+  bool others = false;
+  for (int k = 0; k < GXY_MAX_FLIGHTS; k++) others = others || (v->flights[k] && v->flights[k] != &F && v->flights[k]->pending);
+  int n_bands = others ? 1 : 4;
   if (const char *e = getenv("GXY_BANDS")) n_bands = std::max(1, std::min(16, atoi(e)));
   int n_lanes = n_bands;
   if (const char *e = getenv("GXY_BAND_STREAMS")) n_lanes = std::max(1, std::min(16, atoi(e)));

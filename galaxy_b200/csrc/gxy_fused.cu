@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     gen_primary_peer_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevCamera C, int w, int h, int tiles_x,
                             unsigned n_queue, Rays out, unsigned queue_cap, FusedQueues *__restrict__ q, int me, int nranks,
-                            const PartProxy *__restrict__ prox) {
+                            const PartProxy *__restrict__ prox, int skip_far) {
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
   int x = 0, y = 0;
@@ -171,6 +171,27 @@ __global__ void __launch_bounds__(256)
   if (idx < n_queue) {
     tile_pixel(idx, tiles_x, 0, 1, x, y);
     in_data = x < w && y < h && camera_ray(P, C, x, y, o3, d3, gmin);
+  }
+  if (in_data && skip_far) {
+    // A ray that stays clear of this rank's box cannot be originated, forwarded, terminated or queued HERE (all of that needs the
+    // ray inside the box, at worst grazing a face): it is somebody else's pixel.  Plain slab test against the box grown by a
+    // margin that is orders of magnitude above the rounding of the box arithmetic below, so grazing rays still take the full path.
+    const float3 lo = prox[me].lmin, hi = prox[me].lmax;
+    const float mx = 1e-3f * (hi.x - lo.x) + 1e-4f, my = 1e-3f * (hi.y - lo.y) + 1e-4f, mz = 1e-3f * (hi.z - lo.z) + 1e-4f;
+    float t0 = 0.f, t1 = FLT_MAX;
+    const float dd[3] = {d3.x, d3.y, d3.z}, oo[3] = {o3.x, o3.y, o3.z}, l3[3] = {lo.x - mx, lo.y - my, lo.z - mz}, h3[3] = {hi.x + mx, hi.y + my, hi.z + mz};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      if (fabsf(dd[a]) < 1e-12f) {
+        if (oo[a] < l3[a] || oo[a] > h3[a]) t1 = -1.f;
+      } else {
+        const float r = 1.0f / dd[a];
+        const float ta = (l3[a] - oo[a]) * r, tb = (h3[a] - oo[a]) * r;
+        t0 = fmaxf(t0, fminf(ta, tb));
+        t1 = fminf(t1, fmaxf(ta, tb));
+      }
+    }
+    if (t0 > t1) in_data = false;
   }
   unsigned n_gen = 0u, n_fwd = 0u, n_term = 0u;
   bool queued = false;
@@ -788,7 +809,8 @@ int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLigh
   if (rows <= 0) return 0;
   const unsigned n_queue = (unsigned)tiles_x * (unsigned)rows * 32u;
   const PeerTable T = peer ? *peer : no_peers();
-  if (peer) gen_primary_peer_kernel<<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, n_queue, prim, raw_stride, q, T.rank, T.nranks, proxies);
+  const int skip_far = !(getenv("GXY_GEN_SKIP_FAR") && atoi(getenv("GXY_GEN_SKIP_FAR")) == 0);
+  if (peer) gen_primary_peer_kernel<<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, n_queue, prim, raw_stride, q, T.rank, T.nranks, proxies, skip_far);
   else gen_primary_kernel<<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, band, n_bands, n_queue, prim, spill, spill_cap, q);
   gxy_timeline_mark("gen", st);
   const unsigned needed = (n_queue + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;

@@ -12,6 +12,10 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+# Frames in flight put up to 8 x 17 streams on the device.  With the default of 8 hardware queues several streams share a queue and a
+# kernel that waits at a cross-rank flag barrier can hold up an unrelated stream behind it; 32 queues (the maximum) before the CUDA
+# context exists.  The library does the same in gxy_context_create; both are no-ops when the caller has set the variable.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 MAX_LIGHTS = 16
 
 

@@ -10,6 +10,8 @@
 #include <fstream>
 #include <map>
 #include <sstream>
+#include <stdexcept>
+#include <new>
 
 namespace gxy {
 namespace {
@@ -125,9 +127,14 @@ bool inflate_blocks(const unsigned char *blocks, size_t avail, const std::vector
                     unsigned long long last_size, std::vector<unsigned char> &out, std::string &err) {
   size_t off = 0;
   out.clear();
+  // sizes come from the file: compare by subtraction (no wrap-around) and bound what a block may inflate to (zlib cannot expand
+  // beyond ~1032x; VTK writes blocks of 32 KiB .. a few MiB)
+  const unsigned long long max_block = 1ull << 30;
+  if (block_size > max_block || last_size > max_block) { err = "compressed block size field out of range"; return false; }
   for (size_t k = 0; k < csizes.size(); k++) {
-    if (off + csizes[k] > avail) { err = "compressed block runs past the end of the data"; return false; }
+    if (csizes[k] > avail - off) { err = "compressed block runs past the end of the data"; return false; }
     const unsigned long long usz = (k + 1 == csizes.size() && last_size) ? last_size : block_size;
+    if (usz / 1100 > csizes[k] + 1) { err = "compressed block claims an impossible inflated size"; return false; }
     const size_t at = out.size();
     out.resize(at + (size_t)usz);
     uLongf dl = (uLongf)usz;
@@ -160,6 +167,7 @@ bool bytes_from_base64(const std::string &text, size_t pos, size_t end, const Ct
   std::vector<unsigned char> h1 = b64_decode(text, p, end, hw);
   if (h1.size() < hw) { err = "truncated compressed header"; return false; }
   const unsigned long long nblocks = header_word(h1.data(), c.header64);
+  if (nblocks > (end - pos) / hw) { err = "compressed header claims more blocks than the data can hold"; return false; }
   const size_t hbytes = hw * (3 + (size_t)nblocks);
   p = pos;
   std::vector<unsigned char> hdr = b64_decode(text, p, std::min(end, pos + b64_chars(hbytes)), hbytes);
@@ -175,16 +183,17 @@ bool bytes_from_base64(const std::string &text, size_t pos, size_t end, const Ct
 bool bytes_from_raw(const std::string &file, size_t pos, const Ctx &c, std::vector<unsigned char> &out, std::string &err) {
   const size_t hw = c.header64 ? 8 : 4;
   const unsigned char *base = reinterpret_cast<const unsigned char *>(file.data());
-  if (pos + hw > file.size()) { err = "appended data offset past the end of the file"; return false; }
+  if (pos > file.size() || hw > file.size() - pos) { err = "appended data offset past the end of the file"; return false; }
   if (!c.compressed) {
     const unsigned long long nbytes = header_word(base + pos, c.header64);
-    if (pos + hw + nbytes > file.size()) { err = "appended array runs past the end of the file"; return false; }
+    if (nbytes > file.size() - pos - hw) { err = "appended array runs past the end of the file"; return false; }
     out.assign(base + pos + hw, base + pos + hw + nbytes);
     return true;
   }
   const unsigned long long nblocks = header_word(base + pos, c.header64);
+  if (nblocks > (file.size() - pos) / hw) { err = "appended compressed header past the end of the file"; return false; }
   const size_t hbytes = hw * (3 + (size_t)nblocks);
-  if (pos + hbytes > file.size()) { err = "appended compressed header past the end of the file"; return false; }
+  if (hbytes > file.size() - pos) { err = "appended compressed header past the end of the file"; return false; }
   std::vector<unsigned long long> cs(nblocks);
   for (size_t k = 0; k < nblocks; k++) cs[k] = header_word(base + pos + hw * (3 + k), c.header64);
   return inflate_blocks(base + pos + hbytes, file.size() - pos - hbytes, cs, header_word(base + pos + hw, c.header64),
@@ -249,7 +258,7 @@ bool numbers_from_ascii(const std::string &text, size_t pos, size_t end, const s
 
 }  // namespace
 
-bool read_vtu(const std::string &path, VtuData &out, std::string &error) {
+static bool read_vtu_impl(const std::string &path, VtuData &out, std::string &error) {
   std::ifstream in(path.c_str(), std::ios::in | std::ios::binary);
   if (!in) { error = "cannot open " + path; return false; }
   std::stringstream ss;
@@ -373,6 +382,22 @@ bool read_vtu(const std::string &path, VtuData &out, std::string &error) {
   for (int id : out.connectivity)
     if (id < 0 || id >= out.n_points) { error = "connectivity refers to a point that does not exist"; return false; }
   return true;
+}
+
+// a truncated or malformed dataset is an error return ("print and return false", Geometry.cpp:176-257), never a crash: size fields
+// of the file that slip through the range checks can still ask for more memory than there is
+bool read_vtu(const std::string &path, VtuData &out, std::string &error) {
+  try {
+    return read_vtu_impl(path, out, error);
+  } catch (const std::bad_alloc &) {
+    error = "out of memory while reading " + path + " (corrupt size field?)";
+  } catch (const std::length_error &) {
+    error = "impossible array size in " + path;
+  } catch (const std::out_of_range &) {
+    error = "malformed " + path;
+  }
+  out = VtuData();
+  return false;
 }
 
 }  // namespace gxy

@@ -25,7 +25,7 @@ def lib():
         L.gxy_embree_scene_build_seconds.argtypes = [C.c_void_p]
         L.gxy_embree_scene_destroy.argtypes = [C.c_void_p]
         L.gxy_embree_intersect.restype = C.c_double
-        L.gxy_embree_intersect.argtypes = [C.c_void_p, C.c_size_t, fp, fp, fp, fp, ip, ip, fp, fp, fp, C.c_int, C.c_int]
+        L.gxy_embree_intersect.argtypes = [C.c_void_p, C.c_size_t, fp, fp, fp, fp, ip, ip, fp, fp, fp, fp, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -59,8 +59,48 @@ class EmbreeScene:
         if want:
             prim, t, u, v = np.empty(n, np.int32), np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.float32)
             s = lib().gxy_embree_intersect(self.h, n, _p(org, C.c_float), _p(d, C.c_float), _p(tn, C.c_float), _p(tf, C.c_float), None,
-                                           _p(prim, C.c_int32), _p(t, C.c_float), _p(u, C.c_float), _p(v, C.c_float), packet, threads)
+                                           _p(prim, C.c_int32), _p(t, C.c_float), _p(u, C.c_float), _p(v, C.c_float), None, packet, threads)
             return prim, np.stack([t, u, v], 1), s
         s = lib().gxy_embree_intersect(self.h, n, _p(org, C.c_float), _p(d, C.c_float), _p(tn, C.c_float), _p(tf, C.c_float), None, None, None,
-                                       None, None, packet, threads)
+                                       None, None, None, packet, threads)
         return None, None, s
+
+
+def attach_to_oracle_scene(oracle_scene, verts, indices, threads=0):
+    """bench.py's CPU arm "reference": the oracle Scene `oracle_scene` (one TrianglesVis, not yet committed) takes its nearest hits
+    from a committed EmbreeScene over the same triangles (rtcIntersect8 packets).  Returns the EmbreeScene (keep it alive)."""
+    from oracle import oracle
+    es = EmbreeScene(verts, indices, threads)
+    fn = C.cast(lib().gxy_embree_intersect_cb, C.c_void_p)
+    oracle.lib().gxo_scene_set_intersector(oracle_scene.h, fn, C.c_void_p(es.h))
+    return es
+
+
+def oracle_backend(threads=0):
+    """A `backend` for scenes.build_partitions: oracle Scenes whose TrianglesVis is traced by the reference's Embree (one geometry
+    operator, one partition: what bench.py's CPU arm renders).  Everything but the nearest-hit search stays the oracle's."""
+    from oracle import oracle
+
+    class Scene(oracle.Scene):
+        def add_triangles_vis(self, verts, normals, data, indices, *rest):
+            self._embree_mesh = (verts, indices)
+            return super().add_triangles_vis(verts, normals, data, indices, *rest)
+
+        def commit(self):
+            mesh = getattr(self, "_embree_mesh", None)
+            if mesh is not None:
+                self.embree = attach_to_oracle_scene(self, mesh[0], mesh[1], threads)
+            return super().commit()
+
+    class Backend:
+        pass
+
+    Backend.Scene = Scene
+    return Backend
+
+
+def raylist_columns(rays, n):
+    """(org (n,3), dir (n,3), t, tMax) of a 25-column RayList array as the oracle / the product hand it out"""
+    org = np.ascontiguousarray(rays[0:3, :n].T)
+    d = np.ascontiguousarray(rays[3:6, :n].T)
+    return org, d, np.ascontiguousarray(rays[18, :n]), np.ascontiguousarray(rays[19, :n])

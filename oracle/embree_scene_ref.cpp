@@ -69,11 +69,11 @@ void gxy_embree_scene_destroy(void *h)
     delete s;
 }
 
-// Nearest hit of n rays in (tnear, tfar].  org/dir: n x 3 floats.  Outputs (any may be null): geomID/primID (-1 on a miss),
+// Nearest hit of n rays in (tnear, tfar].  ng3 (may be null): Embree's unnormalised geometric normal, 3 floats per ray.  org/dir: n x 3 floats.  Outputs (any may be null): geomID/primID (-1 on a miss),
 // t (tfar on a miss), u, v.  packet = 8: rtcIntersect8 over groups of 8 consecutive rays; 1: rtcIntersect1.
 // Returns the wall-clock seconds of the intersect loop (threads joined).
 double gxy_embree_intersect(void *h, size_t n, const float *org, const float *dir, const float *tnear, const float *tfar,
-                            int32_t *geom_id, int32_t *prim_id, float *t, float *u, float *v, int packet, int threads)
+                            int32_t *geom_id, int32_t *prim_id, float *t, float *u, float *v, float *ng3, int packet, int threads)
 {
     Scene *s = static_cast<Scene *>(h);
     if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
@@ -81,6 +81,7 @@ double gxy_embree_intersect(void *h, size_t n, const float *org, const float *di
     const size_t chunk = 4096; // multiple of 8
     std::atomic<size_t> next(0);
     auto work = [&]() {
+        const unsigned mxcsr = _mm_getcsr();                  // restored below: the calling thread may be the caller's own
         _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);           // as Embree asks of its callers
         _MM_SET_DENORMALS_ZERO_MODE(_MM_DENORMALS_ZERO_ON);
         for (;;) {
@@ -114,6 +115,7 @@ double gxy_embree_intersect(void *h, size_t n, const float *org, const float *di
                         if (t) t[j] = rh.ray.tfar[k];
                         if (u) u[j] = rh.hit.u[k];
                         if (v) v[j] = rh.hit.v[k];
+                        if (ng3) { ng3[3 * j] = rh.hit.Ng_x[k]; ng3[3 * j + 1] = rh.hit.Ng_y[k]; ng3[3 * j + 2] = rh.hit.Ng_z[k]; }
                     }
                 }
             } else {
@@ -134,9 +136,11 @@ double gxy_embree_intersect(void *h, size_t n, const float *org, const float *di
                     if (t) t[j] = rh.ray.tfar;
                     if (u) u[j] = rh.hit.u;
                     if (v) v[j] = rh.hit.v;
+                    if (ng3) { ng3[3 * j] = rh.hit.Ng_x; ng3[3 * j + 1] = rh.hit.Ng_y; ng3[3 * j + 2] = rh.hit.Ng_z; }
                 }
             }
         }
+        _mm_setcsr(mxcsr);
     };
     double t0 = now();
     std::vector<std::thread> pool;
@@ -144,6 +148,14 @@ double gxy_embree_intersect(void *h, size_t n, const float *org, const float *di
     work();
     for (auto &th : pool) th.join();
     return now() - t0;
+}
+
+// the same as a callback of the oracle (gxo_intersect_fn, oracle/gxy_oracle.h): user = the scene; rtcIntersect8 packets on the
+// calling thread (the oracle's trace loop is already one thread per chunk of the RayList)
+void gxy_embree_intersect_cb(void *user, int n, const float *org3, const float *dir3, const float *tnear, const float *tfar,
+                             int *geom_id, int *prim_id, float *t, float *u, float *v, float *ng3)
+{
+    gxy_embree_intersect(user, (size_t)n, org3, dir3, tnear, tfar, geom_id, prim_id, t, u, v, ng3, 8, 1);
 }
 
 } // extern "C"

@@ -550,6 +550,11 @@ struct gxo_scene {
   std::vector<float> secondary;
   int secondary_n = 0, secondary_aligned = 0;
   std::atomic<long long> sample_count{0};
+  // external nearest-hit provider for the triangles of geometry operator 0 (the reference's own Embree, oracle/embree_scene_ref.cpp):
+  // when set, trace_kernel takes the nearest hit of every ray from it (in blocks, so that it can run 8-ray packets) instead of walking
+  // the median-split tree below, and commit does not build that tree.  bench.py's CPU arm "reference"; never set by a parity test.
+  gxo_intersect_fn ext_fn = nullptr;
+  void *ext_user = nullptr;
 };
 
 namespace {
@@ -751,7 +756,7 @@ struct Hit {   // TraceRays.ispc:79-88
 // ---------------------------------------------------------------------------------------------
 // TraceRays_TraceRays, one ray (TraceRays.ispc:326-623)
 static void trace_one(gxo_scene &S, RL &R, int i, bool integrate, float step, float epsilon,
-                      long long &nsamples, int *hit_ids) {
+                      long long &nsamples, int *hit_ids, const Hit1 *pre = nullptr) {
   const int nvv = (int)S.vvis.size();
   bool shadeFlag = R.type[i] == RAY_PRIMARY;
   V3 org = mk(R.ox[i], R.oy[i], R.oz[i]);
@@ -812,7 +817,10 @@ static void trace_one(gxo_scene &S, RL &R, int i, bool integrate, float step, fl
   if (hit_ids) { hit_ids[2 * i] = -1; hit_ids[2 * i + 1] = -1; }
   if (!S.geoms.empty()) {
     Hit1 h1;
-    if (nearest_hit(S, org, dir, ray_t0, ray_t, h1)) {
+    bool found1;
+    if (pre) { h1 = *pre; found1 = h1.geomID >= 0; }
+    else found1 = nearest_hit(S, org, dir, ray_t0, ray_t, h1);
+    if (found1) {
       ray_t = h1.t;
       if (hit_ids) { hit_ids[2 * i] = h1.geomID; hit_ids[2 * i + 1] = h1.primID; }
       if (shadeFlag) {
@@ -982,9 +990,45 @@ static void trace_kernel(gxo_scene &S, RL &R, float global_epsilon, int nthreads
   bool integrate; float step, epsilon;
   trace_setup(S, global_epsilon, integrate, step, epsilon);
   std::atomic<long long> total{0};
+  const bool ext = S.ext_fn && S.vvis.empty() && S.geoms.size() == 1 && S.geoms[0].kind == 0;
   parallel_for(R.n, nthreads, [&](int a, int b) {
     long long ns = 0;
-    for (int i = a; i < b; i++) trace_one(S, R, i, integrate, step, epsilon, ns, hit_ids);
+    if (!ext) {
+      for (int i = a; i < b; i++) trace_one(S, R, i, integrate, step, epsilon, ns, hit_ids);
+    } else {
+      // the interval of LookForGeometryHit for a scene without slices: the clip of trace_one (:377-418), block by block
+      const int B = 2048;
+      std::vector<float> org(3 * B), dir(3 * B), tn(B), tf(B), t(B), u(B), v(B), ng(3 * B);
+      std::vector<int> gid(B), pid(B);
+      for (int a0 = a; a0 < b; a0 += B) {
+        const int m = std::min(B, b - a0);
+        for (int k = 0; k < m; k++) {
+          const int i = a0 + k;
+          V3 o = mk(R.ox[i], R.oy[i], R.oz[i]), d = mk(R.dx[i], R.dy[i], R.dz[i]);
+          if (d.x == 0.f) d.x = 1e-6f;
+          if (d.y == 0.f) d.y = 1e-6f;
+          if (d.z == 0.f) d.z = 1e-6f;
+          float ray_t0 = R.t[i], ray_t = R.tMax[i];
+          V3 rd = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+          V3 mins = mk((S.lmin.x - o.x) * rd.x, (S.lmin.y - o.y) * rd.y, (S.lmin.z - o.z) * rd.z);
+          V3 maxs = mk((S.lmax.x - o.x) * rd.x, (S.lmax.y - o.y) * rd.y, (S.lmax.z - o.z) * rd.z);
+          float tEntry = std::max(std::min(mins.x, maxs.x), std::max(std::min(mins.y, maxs.y), std::min(mins.z, maxs.z)));
+          float tExit = std::min(std::max(mins.x, maxs.x), std::min(std::max(mins.y, maxs.y), std::max(mins.z, maxs.z)));
+          if (tEntry < ray_t0) tEntry = ray_t0; else if (tEntry > ray_t0) ray_t0 = tEntry;
+          ray_t = std::min(ray_t, tExit);
+          org[3 * k] = o.x; org[3 * k + 1] = o.y; org[3 * k + 2] = o.z;
+          dir[3 * k] = d.x; dir[3 * k + 1] = d.y; dir[3 * k + 2] = d.z;
+          tn[k] = ray_t0; tf[k] = ray_t;
+        }
+        S.ext_fn(S.ext_user, m, org.data(), dir.data(), tn.data(), tf.data(), gid.data(), pid.data(), t.data(), u.data(), v.data(), ng.data());
+        for (int k = 0; k < m; k++) {
+          Hit1 h;
+          h.geomID = (pid[k] >= 0 && tn[k] <= tf[k]) ? 0 : -1; h.primID = pid[k]; h.t = t[k]; h.u = u[k]; h.v = v[k];
+          h.Ng = mk(ng[3 * k], ng[3 * k + 1], ng[3 * k + 2]);
+          trace_one(S, R, a0 + k, integrate, step, epsilon, ns, hit_ids, &h);
+        }
+      }
+    }
     total += ns;
   });
   S.sample_count += total.load();
@@ -1082,12 +1126,16 @@ static std::unique_ptr<OwnedRL> trace_and_spawn(gxo_scene &S, const gxo_lighting
   std::unique_ptr<OwnedRL> out;
   if (nOut) out.reset(new OwnedRL(nOut, 1));
 
+  // (the four loops below are independent per ray -- own columns, own precomputed output slots -- and run threaded; the reference runs
+  // them serially inside one pool thread per RayList, Renderer.cpp:504-556)
   // ambientLighting :735-761
-  for (int i = 0; i < n; i++)
+  parallel_for(n, nthreads, [&](int lo_, int hi_) {
+  for (int i = lo_; i < hi_; i++)
     if (R.type[i] == RAY_PRIMARY && (R.term[i] & RAY_SURFACE)) {
       float ambient_scale = L.Ka * (1.0f - R.o[i]);
       R.r[i] += ambient_scale * R.sr[i]; R.g[i] += ambient_scale * R.sg[i]; R.b[i] += ambient_scale * R.sb[i];
     }
+  });
 
   // generateAORays :625-733
   if (ao_knt) {
@@ -1096,7 +1144,8 @@ static std::unique_ptr<OwnedRL> trace_and_spawn(gxo_scene &S, const gxo_lighting
     RL &O = out->v;
     float Ka = -L.Ka / L.n_ao;
     const float epsilon = eps;
-    for (int i = 0; i < n; i++)
+    parallel_for(n, nthreads, [&](int lo_, int hi_) {
+    for (int i = lo_; i < hi_; i++)
       if (R.type[i] == RAY_PRIMARY && (R.term[i] & RAY_SURFACE)) {
         V3 sn = mk(R.nx[i], R.ny[i], R.nz[i]);
         float ambient_scale = Ka * (1.0f - R.o[i]);
@@ -1123,12 +1172,14 @@ static std::unique_ptr<OwnedRL> trace_and_spawn(gxo_scene &S, const gxo_lighting
           O.x[offset] = R.x[i]; O.y[offset] = R.y[i]; O.type[offset] = RAY_AO; O.term[offset] = 0;
         }
       }
+    });
   }
 
   // diffuseLighting :859-923
   {
     float Kd = L.Kd / L.n_lights;
-    for (int i = 0; i < n; i++)
+    parallel_for(n, nthreads, [&](int lo_, int hi_) {
+    for (int i = lo_; i < hi_; i++)
       if (R.type[i] == RAY_PRIMARY && (R.term[i] & RAY_SURFACE)) {
         V3 sn = mk(R.nx[i], R.ny[i], R.nz[i]);
         float tr = 0, tg = 0, tb = 0;
@@ -1150,6 +1201,7 @@ static std::unique_ptr<OwnedRL> trace_and_spawn(gxo_scene &S, const gxo_lighting
         R.b[i] = R.b[i] + Kd * (1 - R.o[i]) * tb;
         R.o[i] = R.o[i] + Kd * (1 - R.o[i]) * R.o[i];
       }
+    });
   }
 
   // generateShadowRays :763-857
@@ -1157,7 +1209,8 @@ static std::unique_ptr<OwnedRL> trace_and_spawn(gxo_scene &S, const gxo_lighting
     RL &O = out->v;
     float Kd = -L.Kd / L.n_lights;
     const float epsilon = eps;
-    for (int i = 0; i < n; i++) {
+    parallel_for(n, nthreads, [&](int lo_, int hi_) {
+    for (int i = lo_; i < hi_; i++) {
       int offset = shadow_offsets[i];
       if (offset == -1) continue;
       V3 sn = mk(R.nx[i], R.ny[i], R.nz[i]);
@@ -1179,6 +1232,7 @@ static std::unique_ptr<OwnedRL> trace_and_spawn(gxo_scene &S, const gxo_lighting
         offset++;
       }
     }
+    });
   }
   return out;
 }
@@ -1458,8 +1512,13 @@ int gxo_scene_commit(gxo_scene *s) {
   // MappedVis::SetTheOsprayDataObject (MappedVis.cpp:206-212): the volume object's TF is the
   // one of the last Vis committed on that dataset.
   for (VolumeVisOp &op : s->vvis) op.vol->tf = &op.tf;
-  build_accel(*s);
+  if (!s->ext_fn) build_accel(*s);
   return 0;
+}
+
+void gxo_scene_set_intersector(gxo_scene *s, gxo_intersect_fn fn, void *user) {
+  s->ext_fn = fn;
+  s->ext_user = user;
 }
 
 void gxo_resample_tf(int n, const float *cmap, int m, const float *omap, float *colors_out, float *opac_out) {

@@ -182,6 +182,13 @@ void gxo_factor(int n, int factors[3]);
 void gxo_partition(int n, const int factors[3], const int grid[3], int *out);
 
 /* Diagnostic switches for tests ("dvr_before_iso": see gxy_oracle.cpp). */
+/* CPU arm "reference" of bench.py only: take the nearest hit of geometry operator 0's triangles from an external provider (the
+ * reference's own Embree 3.6.1, oracle/embree_scene_ref.cpp) instead of the oracle's own tree.  fn gets n rays (org/dir 3 floats each,
+ * interval (tnear, tfar]) and fills primID (-1: miss; geomID is ignored), t, u, v and the unnormalised geometric normal.  Set before
+ * gxo_scene_commit (which then builds no tree).  Never used by the parity tests: they check the oracle's own arithmetic. */
+typedef void (*gxo_intersect_fn)(void *user, int n, const float *org3, const float *dir3, const float *tnear, const float *tfar,
+                                 int *geom_id, int *prim_id, float *t, float *u, float *v, float *ng3);
+void gxo_scene_set_intersector(gxo_scene *, gxo_intersect_fn fn, void *user);
 void gxo_set_option(const char *name, int value);
 /* Box::exit_face / Box::intersect restatements on arrays (pinned against the reference's compiled Box.cpp) */
 void gxo_exit_face(int n, const float *boxes6, const float *rays6, int *faces);

@@ -78,6 +78,7 @@ def lib():
         L.gxo_factor.argtypes = [C.c_int, ip]
         L.gxo_partition.argtypes = [C.c_int, ip, ip, ip]
         L.gxo_intersect.argtypes = [vp, C.c_int, fp, fp, fp, fp, ip, fp]
+        L.gxo_scene_set_intersector.argtypes = [vp, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
 

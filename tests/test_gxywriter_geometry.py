@@ -205,3 +205,40 @@ def test_reference_data_driven_state_loads_verbatim(tmp_path):
     assert sum(p["n_vertices"] for p in geo["particles"]["parts"]) >= len(parts.centers)          # ghost zones duplicate some
     assert sum(p["n_connectivity"] for p in geo["tmesh"]["parts"]) >= 3 * len(mesh.indices)
     assert sum(p["n_connectivity"] for p in geo["pathlines"]["parts"]) > 0
+
+
+@pytest.mark.parametrize("header64", [False, True])
+@pytest.mark.parametrize("compressed", [False, True])
+def test_corrupt_size_fields_are_errors_not_crashes(tmp_path, header64, compressed):
+    """Size and count fields of an appended-raw .vtu are file content: a huge byte count, a huge block count, a huge block size and a
+    truncated file must all come back as 'error reading' (Geometry.cpp:176-257 prints and goes on), never as a crash or an
+    out-of-bounds read (arithmetic on them used to wrap around)."""
+    import struct
+    tmp = str(tmp_path)
+    mesh = scenes.eightballs_mesh(6, 12)
+    good = os.path.join(tmp, "good.vtu")
+    write_vtu(good, mesh.verts, mesh.indices, mesh.normals, mesh.data, mode="appended-raw", compressed=compressed, header64=header64)
+    blob = open(good, "rb").read()
+    start = blob.index(b"_", blob.index(b"<AppendedData")) + 1
+    hw = 8 if header64 else 4
+    fmt = "<Q" if header64 else "<I"
+    big = (1 << 64) - 16 if header64 else (1 << 32) - 16
+    variants = {"huge first word": blob[:start] + struct.pack(fmt, big) + blob[start + hw:],
+                "truncated": blob[:start + 3 * hw + 5],
+                "cut in the middle": blob[:start + (len(blob) - start) // 2]}
+    if compressed:
+        variants["huge block size"] = blob[:start + hw] + struct.pack(fmt, big) + blob[start + 2 * hw:]
+        variants["huge compressed size"] = blob[:start + 3 * hw] + struct.pack(fmt, big) + blob[start + 4 * hw:]
+    json.dump({"parts": [{"filename": "m-0.vtu", "extent": [-1, 1, -1, 1, -1, 1]}]}, open(os.path.join(tmp, "m.part"), "w"))
+    st = {"Datasets": [{"name": "m", "type": "Triangles", "filename": "m.part"}], "Cameras": [], "Visualizations": []}
+    json.dump(st, open(os.path.join(tmp, "a.state"), "w"))
+    for what, data in variants.items():
+        open(os.path.join(tmp, "m-0.vtu"), "wb").write(data)
+        r = subprocess.run([EXE, "--describe", os.path.join(tmp, "a.state")], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0, (what, r.returncode, r.stderr[-400:])
+        assert "error reading" in r.stderr, (what, r.stderr[-400:])
+        assert json.loads(r.stdout)["geometries"][0]["parts"][0]["loaded"] is False, what
+    # and the untouched file still loads
+    open(os.path.join(tmp, "m-0.vtu"), "wb").write(blob)
+    r = subprocess.run([EXE, "--describe", os.path.join(tmp, "a.state")], capture_output=True, text=True, timeout=60)
+    assert json.loads(r.stdout)["geometries"][0]["parts"][0]["loaded"] is True
