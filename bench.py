@@ -126,20 +126,10 @@ CMAP = [[0.0, 1.0, 0.5, 0.5], [0.25, 0.5, 1.0, 0.5], [0.5, 0.5, 0.5, 1.0], [0.75
 
 
 def synth_volume(n, device="cuda"):
-    """C3/C4 throughput volume: eightBalls distance field + 0.15 * a sine lattice, n^3 float32 on [-1,1]^3,
-    synthesised slab-wise with torch (closed form: no seed, no files)."""
+    """C3/C4 throughput volume: v = eightBalls(p) + 0.15 * fbm(8p), 5-octave value noise on a PCG32-hashed lattice (seed 7),
+    n^3 float32 on [-1,1]^3; every partition's brick is synthesised on demand, slab by slab, on the device (scenes.noise_volume)."""
     import torch
-    dev = device if torch.cuda.is_available() else "cpu"
-    c = torch.linspace(-1.0, 1.0, n, device=dev, dtype=torch.float32)
-    data = np.empty((n, n, n), np.float32)
-    Y, X = torch.meshgrid(c, c, indexing="ij")
-    for k0 in range(0, n, 64):
-        Z = c[k0:k0 + 64].view(-1, 1, 1)
-        eb = torch.sqrt((X.abs() - .5) ** 2 + (Y.abs() - .5) ** 2 + (Z.abs() - .5) ** 2)
-        v = eb + 0.15 * (torch.sin(37.0 * X) * torch.sin(41.0 * Y) * torch.sin(43.0 * Z) * 0.5 + 0.5)
-        data[k0:k0 + 64] = v.cpu().numpy()
-    sp = 2.0 / (n - 1)
-    return scenes.VolumeDataset([-1.0, -1.0, -1.0], (n, n, n), [sp, sp, sp], data)
+    return scenes.noise_volume(n, device if (device != "cpu" and torch.cuda.is_available()) else "cpu")
 
 
 def volume_case(which):
@@ -150,11 +140,11 @@ def volume_case(which):
                   slices=[], isovalues=[], volume_render=True)
         return (dict(annotation="", lighting=scenes.parse_lighting({}), operators=[op]),
                 scenes.parse_camera({"viewpoint": [0, 0, -4], "viewcenter": [0, 0, 0], "viewup": [0, 1, 0], "aov": 30}))
-    op = dict(type="VolumeVis", dataset="v", colormap=CMAP, opacitymap=[[0, 1], [1, 1]], data_range=None, slices=[], isovalues=[0.35],
+    op = dict(type="VolumeVis", dataset="v", colormap=CMAP, opacitymap=[[0, 1], [1, 1]], data_range=None, slices=[], isovalues=[0.6],
               volume_render=False)
     return (dict(annotation="", lighting=scenes.parse_lighting({"Sources": [[1, 1, -2, 0]], "shadows": True, "Ka": 0.4, "Kd": 0.6, "ao count": 0}),
                  operators=[op]),
-            scenes.parse_camera({"viewpoint": [3, 2, -4], "viewcenter": [0, 0, 0], "viewup": [0, 1, 0], "aov": 30}))
+            scenes.parse_camera({"viewpoint": [0, 0, -3], "viewdirection": [0, 0, 1], "viewup": [0, 1, 0], "aov": 30}))  # examples/noise_isovalue.state:25-30
 
 
 PL_LINES, PL_VERTS = 20000, 41    # --workload pl: 20 000 helical poly-lines x 40 segments = 800 000 round Bezier segments
@@ -304,6 +294,42 @@ def run_cpu_reference(steps, warmup, tess_div=1, budget_s=120.0):
             "embree_build_s": build_s, "scene_setup_s": setup_s, "frames_timed": len(times)}, t * 1e3
 
 
+def parity_after_timing(gpu, ctx, world, rank, dist):
+    """Driver-visible parity of exactly the code path that was timed (frames in flight, spatial partitions, peer exchange): after the
+    timed region every rank builds ITS partition of a small version of the scene (1/16 tessellation per axis) and two cameras are
+    rendered on two frame slots; rank 0 renders the same partitions with the CPU oracle and compares image and ray statistics."""
+    import torch
+    n_lat, n_lon, w, h = scenes.C5_FULL[0] // 16, scenes.C5_FULL[1] // 16, 480, 270
+    vis = scenes.c5_vis()
+    cams = [scenes.c5_camera(), scenes.parse_camera({"viewpoint": [-3, 1, -4], "viewcenter": [0, 0, 0], "viewup": [0, 1, 0], "aov": 30})]
+    ds, _ = scenes.c5_partition_mesh(n_lat, n_lon, world, rank)
+    part = scenes.build_partitions(gpu, vis, {"mesh": ds}, world, only_rank=rank, ctx=ctx)[0]
+    keys = ["primary_rays", "shadow_rays", "ao_rays", "forwarded_rays", "terminated_rays"]
+    for k, cam in enumerate(cams):
+        gpu.render_submit([part], cam, vis["lighting"], w, h, EPS, k)
+    got = []
+    for k in range(len(cams)):
+        st = gpu.render_wait([part], k)
+        t = torch.tensor([st[key] for key in keys], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t)
+        got.append((dict(zip(keys, t.tolist())), part.download_rgba32f(w, h) if rank == 0 else None))
+    if rank != 0:
+        return None
+    from oracle import oracle
+    full, _ = scenes.c5_partition_mesh(n_lat, n_lon, 1, 0)
+    o_parts = scenes.build_partitions(oracle, vis, {"mesh": full}, world)
+    fracs, same = [], True
+    for k, cam in enumerate(cams):
+        fb_o, st_o = oracle.render(o_parts, cam, vis["lighting"], w, h, EPS)
+        st_g, fb_g = got[k]
+        fracs.append(float((np.abs(fb_g[..., :3] - fb_o[..., :3]).max(-1) <= 1.0 / 255).mean()))
+        same = same and all(st_g[key] == st_o[key] for key in keys)
+    return {"fraction": min(fracs), "stats_equal": bool(same), "frames": len(cams), "checked_against": "CPU oracle, same %d partitions" % world,
+            "scene": "C5 at 1/16 tessellation per axis (%d triangles), %dx%d, 2 cameras on 2 frame slots" % (len(full.indices), w, h),
+            "tolerance": "1/255 per channel on the float framebuffer; primary/shadow/AO/forwarded/terminated ray counts equal"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,7 +357,7 @@ def main():
         metric = "Mrays/s, 1080p PathLines primary+shadow"
     elif volume:
         workload = ("C3 noise volume %d^3 float32, 1920x1080, DVR only (no secondary rays), spatial partitions=%d" if args.workload == "c3" else
-                    "C4 noise volume %d^3 float32, 1920x1080, isosurface 0.35 + shadow rays (1 light), spatial partitions=%d") % (args.volume_n, n_gpus)
+                    "C4 noise volume %d^3 float32, 1920x1080, isosurface 0.6 + shadow rays (1 light), spatial partitions=%d") % (args.volume_n, n_gpus)
         metric = "Mrays/s, 1080p volume march (%s)" % ("DVR" if args.workload == "c3" else "isosurface + shadow")
     else:
         workload = "C5 eightBalls-100M: %d triangles, 1920x1080, primary + shadow (1 light) + 8 AO rays, Triangles vis, spatial partitions=%d" % (
@@ -492,6 +518,10 @@ def main():
     barrier()
     t_e2e = time.perf_counter() - t0
 
+    parity = None
+    if not (volume or pathlines):
+        parity = parity_after_timing(gpu, ctx, world, rank, dist)
+
     if world > 1:
         t = torch.tensor([ms_local, t_e2e, trace_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -565,6 +595,8 @@ def main():
             "frames_in_flight": depth, "frame_latency_ms": latency_ms,
             "scene": {"triangles_this_rank": n_tris_local, "bvh_nodes": info["n_nodes"], "bvh_build_ms": info["build_ms"], "mesh_gen_s": t_gen,
                       "commit_s": t_commit}}
+    if parity is not None:
+        line["parity"] = parity
     if n_gpus == 1 and not args.no_cpu_baseline:
         if pathlines:
             cb, _ = run_cpu_baseline_pathlines(2, 0)

@@ -12,7 +12,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -250,7 +253,7 @@ struct Scratch {
 // partial framebuffer, error flag and -- one process per GPU -- its own peer arena, so that several frames of a
 // RenderingSet overlap on the device the way the reference keeps all Renderings of a set in flight at once
 // (src/apps/gxywriter.cpp:196-264 starts every Rendering before the first wait; RayQManager.cpp:69-82 interleaves their lists).
-#define GXY_MAX_FLIGHTS 8
+#define GXY_MAX_FLIGHTS 16
 struct Flight {
   bool pending = false, peer = false, sync_done = false;
   cudaStream_t st = nullptr, lanes[16] = {};
@@ -271,6 +274,26 @@ struct Flight {
   gxy_lighting lights;
   DevLights L;
   gxy_stats S;
+};
+
+
+// Scratch of ONE call of a per-RayList entry point (gxy_trace_raylist, gxy_classify, gxy_sample_raylist, gxy_generate_rays,
+// gxy_intersect and their device-list forms).  The reference calls TraceRays::Trace from GXY_NTHREADS pool threads at once, each with
+// its own TraceRays object, all sharing one Visualization (src/framework/Application.cpp:75, src/renderer/Renderer.cpp:504-556): a
+// call takes a free lane of the Visualization (own stream, own lists, own error flag), concurrent calls run side by side on the
+// device, and more callers than lanes wait for one.  The committed scene (SceneParams, BVH, volumes) is read-only during calls.
+#define GXY_LIST_LANES 8
+struct ListLane {
+  bool busy = false;
+  cudaStream_t st = nullptr;
+  RayBuf cur, next;
+  Scratch<int> hit_index, block_sums, small, io_i, err;
+  Scratch<float> io_f;
+};
+struct gxy_dev_raylist {  // a RayList that lives on the device between calls (SURVEY 8b "Ownership")
+  gxy_context *ctx;
+  RayBuf buf;
+  int n;
 };
 
 struct VolOp {
@@ -335,7 +358,10 @@ struct gxy_vis {
   Scratch<float> io_f;
   Scratch<int> io_i;
   int fb_w = 0, fb_h = 0;
-  Flight *flights[GXY_MAX_FLIGHTS] = {};  // frames in flight (gxy_render_submit / gxy_render_wait); [0] also serves gxy_render
+  Flight *flights[GXY_MAX_FLIGHTS] = {};
+  std::mutex lanes_mu;
+  std::condition_variable lanes_cv;
+  ListLane *list_lanes[GXY_LIST_LANES] = {};  // frames in flight (gxy_render_submit / gxy_render_wait); [0] also serves gxy_render
 };
 
 static int use_device(gxy_context *c) {
@@ -597,6 +623,13 @@ void gxy_vis_destroy(gxy_vis *v) {
   v->proxies.release();
   if (v->h_tail) cudaFreeHost(v->h_tail);
   for (int k = 0; k < GXY_MAX_FLIGHTS; k++) flight_destroy(v, v->flights[k]);
+  for (int k = 0; k < GXY_LIST_LANES; k++)
+    if (ListLane *l = v->list_lanes[k]) {
+      if (l->st) { cudaStreamSynchronize(l->st); cudaStreamDestroy(l->st); }
+      l->cur.release(); l->next.release(); l->hit_index.release(); l->block_sums.release(); l->small.release(); l->io_i.release();
+      l->err.release(); l->io_f.release();
+      delete l;
+    }
   delete v;
 }
 
@@ -953,18 +986,88 @@ static int check_error_flag(gxy_vis *v) {
   return 0;
 }
 
-static int h2d_rays(gxy_vis *v, RayBuf &buf, gxy_raylist_view r) {
-  cudaStream_t st = v->ctx->stream;
+static int h2d_rays(cudaStream_t st, RayBuf &buf, gxy_raylist_view r) {
   if (buf.reserve((size_t)std::max(r.n, 1), false, st)) return 1;
   if (r.n > 0)
     GXY_CUDA(cudaMemcpy2DAsync(buf.base, buf.cap * 4, r.base, (size_t)r.aligned_n * 4, (size_t)r.n * 4, GXY_RAYLIST_COLUMNS,
                                cudaMemcpyHostToDevice, st));
   return 0;
 }
-static int d2h_rays(gxy_vis *v, RayBuf &buf, float *base, int n, int aligned_n, int first_col = 0, int ncols = GXY_RAYLIST_COLUMNS) {
+static int d2h_rays(cudaStream_t st, RayBuf &buf, float *base, int n, int aligned_n, int first_col = 0, int ncols = GXY_RAYLIST_COLUMNS) {
   if (n > 0)
     GXY_CUDA(cudaMemcpy2DAsync(base + (size_t)first_col * aligned_n, (size_t)aligned_n * 4, buf.base + (size_t)first_col * buf.cap, buf.cap * 4,
-                               (size_t)n * 4, ncols, cudaMemcpyDeviceToHost, v->ctx->stream));
+                               (size_t)n * 4, ncols, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+// a free lane of the Visualization for the duration of one call (waits if all GXY_LIST_LANES are taken)
+struct LaneGuard {
+  gxy_vis *v;
+  ListLane *l = nullptr;
+  explicit LaneGuard(gxy_vis *vis) : v(vis) {
+    std::unique_lock<std::mutex> lk(v->lanes_mu);
+    for (;;) {
+      for (int k = 0; k < GXY_LIST_LANES && !l; k++) {
+        if (!v->list_lanes[k]) v->list_lanes[k] = new ListLane();
+        if (!v->list_lanes[k]->busy) l = v->list_lanes[k];
+      }
+      if (l) break;
+      v->lanes_cv.wait(lk);
+    }
+    l->busy = true;
+  }
+  ~LaneGuard() {
+    {
+      std::lock_guard<std::mutex> lk(v->lanes_mu);
+      l->busy = false;
+    }
+    v->lanes_cv.notify_one();
+  }
+  // stream and error flag are created by the first call that uses the lane (the device is current: check_vis)
+  int prepare() {
+    if (!l->st) GXY_CUDA(cudaStreamCreateWithFlags(&l->st, cudaStreamNonBlocking));
+    if (!l->err.p) {
+      if (l->err.reserve(4)) return 1;
+      GXY_CUDA(cudaMemsetAsync(l->err.p, 0, sizeof(int) * 4, l->st));
+    }
+    return 0;
+  }
+  // the scene as this call's kernels see it: the lane's own error flag
+  SceneParams params() const {
+    SceneParams P = v->P;
+    P.error_flag = l->err.p;
+    return P;
+  }
+  int check_error() {
+    int e = 0;
+    GXY_CUDA(cudaMemcpyAsync(&e, l->err.p, sizeof(int), cudaMemcpyDeviceToHost, l->st));
+    GXY_CUDA(cudaStreamSynchronize(l->st));
+    if (e != 0) GXY_CUDA(cudaMemsetAsync(l->err.p, 0, sizeof(int), l->st));  // reported once
+    GXY_CHECK(e == 0, "device error flag %d (1: BVH traversal stack overflow, 3: ray list / inbox capacity, 4: peer barrier timeout, 6: TMA copy did not complete)", e);
+    return 0;
+  }
+};
+
+// TraceRays::Trace on a list that is already on the device (lane stream): trace in place, hit scan, AO/shadow spawn into `sec`
+// (reserved here); *n_sec = rays spawned.  d_hits may be NULL.
+static int trace_list_on_lane(gxy_vis *v, LaneGuard &G, const gxy_lighting *lights, RayBuf &rays, int n, float epsilon, int *d_hits, RayBuf &sec,
+                              long long *n_sec) {
+  ListLane &l = *G.l;
+  cudaStream_t st = l.st;
+  const SceneParams P = G.params();
+  if (launch_trace(P, rays.v, n, epsilon, d_hits, false, nullptr, st)) return 1;
+  if (l.hit_index.reserve((size_t)2 * n) || l.block_sums.reserve((size_t)n / 1024 + 2) || l.small.reserve(64)) return 1;
+  if (launch_hit_scan(rays.v, n, l.hit_index.p, l.block_sums.p, l.small.p, st)) return 1;
+  int nhit = 0;
+  GXY_CUDA(cudaMemcpyAsync(&nhit, l.small.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GXY_CUDA(cudaStreamSynchronize(st));
+  const long long n_out = (long long)nhit * (lights->n_ao + (lights->shadows ? lights->n_lights : 0));
+  GXY_CHECK(n_out < (1ll << 31), "secondary ray list too large (%lld)", n_out);
+  const DevLights L = make_dev_lights(*lights);
+  if (sec.reserve((size_t)std::max<long long>(n_out, 1), false, st)) return 1;
+  if (launch_shade_spawn(L, rays.v, n, l.hit_index.p, l.small.p, sec.v, epsilon, st)) return 1;
+  *n_sec = n_out;
+  (void)v;
   return 0;
 }
 
@@ -977,25 +1080,19 @@ int gxy_trace_raylist(gxy_vis *v, const gxy_lighting *lights, gxy_raylist_view r
   if (out) *out = nullptr;
   const int n = rays.n;
   if (n == 0) return 0;
-  cudaStream_t st = v->ctx->stream;
-  if (h2d_rays(v, v->cur, rays)) return 1;
+  LaneGuard G(v);
+  if (G.prepare()) return 1;
+  ListLane &l = *G.l;
+  cudaStream_t st = l.st;
+  if (h2d_rays(st, l.cur, rays)) return 1;
   int *d_hits = nullptr;
   if (hit_ids) {
-    if (v->io_i.reserve((size_t)2 * n)) return 1;
-    d_hits = v->io_i.p;
+    if (l.io_i.reserve((size_t)2 * n)) return 1;
+    d_hits = l.io_i.p;
   }
-  if (launch_trace(v->P, v->cur.v, n, epsilon, d_hits, false, nullptr, st)) return 1;
-  if (v->hit_index.reserve((size_t)2 * n) || v->block_sums.reserve((size_t)n / 1024 + 2) || v->small.reserve(64)) return 1;
-  if (launch_hit_scan(v->cur.v, n, v->hit_index.p, v->block_sums.p, v->small.p, st)) return 1;
-  int nhit = 0;
-  GXY_CUDA(cudaMemcpyAsync(&nhit, v->small.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  GXY_CUDA(cudaStreamSynchronize(st));
-  const long long n_out = (long long)nhit * (lights->n_ao + (lights->shadows ? lights->n_lights : 0));
-  GXY_CHECK(n_out < (1ll << 31), "secondary ray list too large (%lld)", n_out);
-  const DevLights L = make_dev_lights(*lights);
-  if (v->next.reserve((size_t)std::max<long long>(n_out, 1), false, st)) return 1;
-  if (launch_shade_spawn(L, v->cur.v, n, v->hit_index.p, v->small.p, v->next.v, epsilon, st)) return 1;
-  if (d2h_rays(v, v->cur, rays.base, n, rays.aligned_n)) return 1;
+  long long n_out = 0;
+  if (trace_list_on_lane(v, G, lights, l.cur, n, epsilon, d_hits, l.next, &n_out)) return 1;
+  if (d2h_rays(st, l.cur, rays.base, n, rays.aligned_n)) return 1;
   if (hit_ids) GXY_CUDA(cudaMemcpyAsync(hit_ids, d_hits, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, st));
   if (n_out > 0 && out) {
     gxy_raylist *o = new gxy_raylist();
@@ -1003,11 +1100,11 @@ int gxy_trace_raylist(gxy_vis *v, const gxy_lighting *lights, gxy_raylist_view r
     o->aligned_n = std::max(16, (o->n + 15) & ~15);  // Rays.cpp:57-58
     o->base = (float *)calloc((size_t)GXY_RAYLIST_COLUMNS * o->aligned_n, sizeof(float));
     if (!o->base) { delete o; gxy_set_error("out of host memory for the secondary list"); return 1; }
-    if (d2h_rays(v, v->next, o->base, o->n, o->aligned_n)) return 1;
+    if (d2h_rays(st, l.next, o->base, o->n, o->aligned_n)) { free(o->base); delete o; return 1; }
     *out = o;
   }
   GXY_CUDA(cudaStreamSynchronize(st));
-  return check_error_flag(v);
+  return G.check_error();
 }
 
 int gxy_raylist_get_view(gxy_raylist *l, gxy_raylist_view *view) {
@@ -1021,23 +1118,90 @@ void gxy_raylist_free(gxy_raylist *l) {
   delete l;
 }
 
+// ---- device-resident RayLists ---------------------------------------------------------------------
+int gxy_raylist_upload(gxy_vis *v, gxy_raylist_view rays, gxy_dev_raylist **out) {
+  if (check_vis(v)) return 1;
+  GXY_CHECK(out && rays.n >= 0 && rays.aligned_n >= rays.n && (rays.base || rays.n == 0), "gxy_raylist_upload: bad arguments");
+  LaneGuard G(v);
+  if (G.prepare()) return 1;
+  std::unique_ptr<gxy_dev_raylist> d(new gxy_dev_raylist());
+  d->ctx = v->ctx;
+  d->n = rays.n;
+  if (h2d_rays(G.l->st, d->buf, rays)) { d->buf.release(); return 1; }
+  GXY_CUDA(cudaStreamSynchronize(G.l->st));
+  *out = d.release();
+  return 0;
+}
+int gxy_raylist_size(gxy_dev_raylist *d, int *n) {
+  GXY_CHECK(d && n, "gxy_raylist_size: NULL argument");
+  *n = d->n;
+  return 0;
+}
+int gxy_raylist_download(gxy_dev_raylist *d, gxy_raylist_view rays) {
+  GXY_CHECK(d && rays.aligned_n >= d->n && (rays.base || d->n == 0), "gxy_raylist_download: the host list is too small (%d rays)", d ? d->n : 0);
+  if (use_device(d->ctx)) return 1;
+  if (d->n > 0)  // (the default stream of the library's context: the list is at rest between calls)
+    GXY_CUDA(cudaMemcpy2D(rays.base, (size_t)rays.aligned_n * 4, d->buf.base, d->buf.cap * 4, (size_t)d->n * 4, GXY_RAYLIST_COLUMNS,
+                          cudaMemcpyDeviceToHost));
+  return 0;
+}
+void gxy_dev_raylist_free(gxy_dev_raylist *d) {
+  if (!d) return;
+  cudaSetDevice(d->ctx->device);
+  d->buf.release();
+  delete d;
+}
+int gxy_trace_raylist_dev(gxy_vis *v, const gxy_lighting *lights, gxy_dev_raylist *rays, float epsilon, gxy_dev_raylist **secondary) {
+  if (check_vis(v)) return 1;
+  GXY_CHECK(lights && rays, "gxy_trace_raylist_dev: bad arguments");
+  GXY_CHECK(lights->n_lights >= 1 && lights->n_lights <= GXY_MAX_LIGHTS, "lighting needs 1..%d lights", GXY_MAX_LIGHTS);
+  if (secondary) *secondary = nullptr;
+  if (rays->n == 0) return 0;
+  LaneGuard G(v);
+  if (G.prepare()) return 1;
+  std::unique_ptr<gxy_dev_raylist> sec(new gxy_dev_raylist());
+  sec->ctx = v->ctx;
+  long long n_out = 0;
+  if (trace_list_on_lane(v, G, lights, rays->buf, rays->n, epsilon, nullptr, sec->buf, &n_out)) { sec->buf.release(); return 1; }
+  GXY_CUDA(cudaStreamSynchronize(G.l->st));
+  if (G.check_error()) { sec->buf.release(); return 1; }
+  sec->n = (int)n_out;
+  if (n_out > 0 && secondary) *secondary = sec.release();
+  else sec->buf.release();
+  return 0;
+}
+int gxy_classify_dev(gxy_vis *v, gxy_dev_raylist *rays) {
+  if (check_vis(v)) return 1;
+  GXY_CHECK(rays, "gxy_classify_dev: NULL list");
+  if (rays->n == 0) return 0;
+  LaneGuard G(v);
+  if (G.prepare()) return 1;
+  if (launch_classify(G.params(), rays->buf.v, rays->n, G.l->st)) return 1;
+  GXY_CUDA(cudaStreamSynchronize(G.l->st));
+  return 0;
+}
+
 int gxy_classify(gxy_vis *v, gxy_raylist_view rays) {
   if (check_vis(v)) return 1;
   if (rays.n == 0) return 0;
-  if (h2d_rays(v, v->cur, rays)) return 1;
-  if (launch_classify(v->P, v->cur.v, rays.n, v->ctx->stream)) return 1;
-  if (d2h_rays(v, v->cur, rays.base, rays.n, rays.aligned_n, 24, 1)) return 1;
-  GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  LaneGuard G(v);
+  if (G.prepare()) return 1;
+  if (h2d_rays(G.l->st, G.l->cur, rays)) return 1;
+  if (launch_classify(G.params(), G.l->cur.v, rays.n, G.l->st)) return 1;
+  if (d2h_rays(G.l->st, G.l->cur, rays.base, rays.n, rays.aligned_n, 24, 1)) return 1;
+  GXY_CUDA(cudaStreamSynchronize(G.l->st));
   return 0;
 }
 
 int gxy_sample_raylist(gxy_vis *v, gxy_raylist_view rays) {
   if (check_vis(v)) return 1;
   if (rays.n == 0) return 0;
-  if (h2d_rays(v, v->cur, rays)) return 1;
-  if (launch_sampler_trace(v->SP, v->cur.v, rays.n, nullptr, nullptr, 0, nullptr, false, v->ctx->stream)) return 1;
-  if (d2h_rays(v, v->cur, rays.base, rays.n, rays.aligned_n)) return 1;
-  GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  LaneGuard G(v);
+  if (G.prepare()) return 1;
+  if (h2d_rays(G.l->st, G.l->cur, rays)) return 1;
+  if (launch_sampler_trace(v->SP, G.l->cur.v, rays.n, nullptr, nullptr, 0, nullptr, false, G.l->st)) return 1;
+  if (d2h_rays(G.l->st, G.l->cur, rays.base, rays.n, rays.aligned_n)) return 1;
+  GXY_CUDA(cudaStreamSynchronize(G.l->st));
   return 0;
 }
 
@@ -1228,15 +1392,18 @@ int gxy_particles_from_samples(gxy_vis *v, gxy_particles **out) {
 int gxy_generate_rays(gxy_vis *v, const gxy_camera *cam, int w, int h, gxy_raylist_view rays, int *n_out) {
   if (check_vis(v)) return 1;
   GXY_CHECK(cam && rays.base && w > 0 && h > 0 && rays.aligned_n >= w * h, "gxy_generate_rays: bad arguments");
-  cudaStream_t st = v->ctx->stream;
+  LaneGuard G(v);
+  if (G.prepare()) return 1;
+  ListLane &l = *G.l;
+  cudaStream_t st = l.st;
   const int npix = w * h;
-  if (v->cur.reserve(npix, false, st) || v->block_sums.reserve((size_t)npix / 1024 + 2) || v->small.reserve(64)) return 1;
+  if (l.cur.reserve(npix, false, st) || l.block_sums.reserve((size_t)npix / 1024 + 2) || l.small.reserve(64)) return 1;
   const DevCamera C = make_dev_camera(*cam, w, h);
-  if (launch_generate(v->P, C, w, h, false, v->cur.v, nullptr, v->block_sums.p, v->small.p, st)) return 1;
+  if (launch_generate(G.params(), C, w, h, false, l.cur.v, nullptr, l.block_sums.p, l.small.p, st)) return 1;
   int n = 0;
-  GXY_CUDA(cudaMemcpyAsync(&n, v->small.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GXY_CUDA(cudaMemcpyAsync(&n, l.small.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   GXY_CUDA(cudaStreamSynchronize(st));
-  if (d2h_rays(v, v->cur, rays.base, n, rays.aligned_n)) return 1;
+  if (d2h_rays(st, l.cur, rays.base, n, rays.aligned_n)) return 1;
   GXY_CUDA(cudaStreamSynchronize(st));
   *n_out = n;
   return 0;
@@ -1246,18 +1413,21 @@ int gxy_intersect(gxy_vis *v, int n, const float *org3, const float *dir3, const
                   float *tuv3) {
   if (check_vis(v)) return 1;
   if (n <= 0) return 0;
-  cudaStream_t st = v->ctx->stream;
-  if (v->io_f.reserve((size_t)11 * n) || v->io_i.reserve((size_t)2 * n)) return 1;
-  float *d_org = v->io_f.p, *d_dir = d_org + 3 * (size_t)n, *d_tn = d_dir + 3 * (size_t)n, *d_tf = d_tn + n, *d_tuv = d_tf + n;
+  LaneGuard G(v);
+  if (G.prepare()) return 1;
+  ListLane &l = *G.l;
+  cudaStream_t st = l.st;
+  if (l.io_f.reserve((size_t)11 * n) || l.io_i.reserve((size_t)2 * n)) return 1;
+  float *d_org = l.io_f.p, *d_dir = d_org + 3 * (size_t)n, *d_tn = d_dir + 3 * (size_t)n, *d_tf = d_tn + n, *d_tuv = d_tf + n;
   GXY_CUDA(cudaMemcpyAsync(d_org, org3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, st));
   GXY_CUDA(cudaMemcpyAsync(d_dir, dir3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, st));
   GXY_CUDA(cudaMemcpyAsync(d_tn, tnear, sizeof(float) * n, cudaMemcpyHostToDevice, st));
   GXY_CUDA(cudaMemcpyAsync(d_tf, tfar, sizeof(float) * n, cudaMemcpyHostToDevice, st));
-  if (launch_intersect(v->P, n, d_org, d_dir, d_tn, d_tf, v->io_i.p, d_tuv, st)) return 1;
-  GXY_CUDA(cudaMemcpyAsync(geom_prim2, v->io_i.p, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, st));
+  if (launch_intersect(G.params(), n, d_org, d_dir, d_tn, d_tf, l.io_i.p, d_tuv, st)) return 1;
+  GXY_CUDA(cudaMemcpyAsync(geom_prim2, l.io_i.p, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, st));
   GXY_CUDA(cudaMemcpyAsync(tuv3, d_tuv, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
   GXY_CUDA(cudaStreamSynchronize(st));
-  return check_error_flag(v);
+  return G.check_error();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1527,6 +1697,12 @@ static int peer_wave(gxy_vis *v, Flight &F, const SceneParams &P, int w, int h, 
   gxy_stats &S = F.S;
   const int k = ++F.peer_k;
   const int parity_in = (k - 1) & 1;
+  // waves 1 and 2 carry the bulk (the secondaries of the local hits; what the neighbours forwarded and its secondaries): full grids.
+  // Later waves only move the few rays that cross a second or third partition face: small grids, the CTAs are persistent anyway
+  // and a launch of 1184 CTAs that find an empty queue is not free.
+  int late = 2;
+  if (const char *e = getenv("GXY_LATE_BLOCKS")) late = std::max(1, std::min(8, atoi(e)));
+  const int bps = k <= 2 ? 0 : late;
   if (flight_trace_begin(F, st)) return 1;
   // AO/shadow rays of the hits the previous wave found (leavers go to inboxes[k&1]) on a second stream ...
   cudaStream_t s2 = st;
@@ -1536,11 +1712,11 @@ static int peer_wave(gxy_vis *v, Flight &F, const SceneParams &P, int w, int h, 
     GXY_CUDA(cudaStreamWaitEvent(s2, F.ev_fork, 0));
   }
   if (spawn && launch_fused_secondary(P, F.L, w, h, F.n_sec_per_hit, (long long)npix * F.n_sec_per_hit, fb, F.hits.v, F.cur.v, 0u, q, F.epsilon,
-                                      !v->has_dvr, &T, k & 1, s2))
+                                      !v->has_dvr, &T, k & 1, s2, bps))
     return 1;
   gxy_timeline_mark("secondary", s2);
   // ... while this stream traces the rays the neighbours sent during the previous wave (the two only share atomic counters)
-  if (launch_inbox_wave(P, F.L, T, parity_in, w, h, fb, F.rawhits.p, (unsigned)npix, F.hits.v, q, F.epsilon, !v->has_dvr, st)) return 1;
+  if (launch_inbox_wave(P, F.L, T, parity_in, w, h, fb, F.rawhits.p, (unsigned)npix, F.hits.v, q, F.epsilon, !v->has_dvr, st, bps)) return 1;
   if (s2 != st) {
     GXY_CUDA(cudaEventRecord(F.ev_join[1], s2));
     GXY_CUDA(cudaStreamWaitEvent(st, F.ev_join[1], 0));
@@ -1568,6 +1744,50 @@ static int peer_finish(gxy_vis *v, Flight &F) {
   GXY_CUDA(cudaEventRecord(F.ev1, st));
   return 0;
 }
+
+// The rectangle of 8x4-pixel tiles that the box [lo - margin, hi + margin] projects into (x0, y0, nx, ny), for the generation
+// kernel of one rank: a pixel whose ray touches the box lies inside the bounding rectangle of the projected corners (the box is
+// convex, the projection maps lines to lines) as long as every corner is in front of the eye; 2 pixels are added for the rounding of
+// the per-pixel ray arithmetic.  Returns false (whole image) when a corner is at or behind the eye plane.
+static bool peer_tile_rect(const DevCamera &C, const float lo[3], const float hi[3], int w, int h, int rect[4]) {
+  const double vr[3] = {C.vr.x, C.vr.y, C.vr.z}, vu[3] = {C.vu.x, C.vu.y, C.vu.z}, vd[3] = {C.vdir.x, C.vdir.y, C.vdir.z};
+  const double eye[3] = {C.veye.x, C.veye.y, C.veye.z}, cen[3] = {C.center.x, C.center.y, C.center.z};
+  auto dot = [](const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+  const double rr = dot(vr, vr), uu = dot(vu, vu), ru = dot(vr, vu);
+  const double det = rr * uu - ru * ru;
+  if (!(det > 1e-20) || !(C.scaling > 0.f)) return false;
+  double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+  double c[3] = {cen[0] - eye[0], cen[1] - eye[1], cen[2] - eye[2]};  // eye -> image plane (perspective)
+  const double cc = dot(c, c);
+  for (int k = 0; k < 8; k++) {
+    double m[3], p[3], rel[3];
+    for (int a = 0; a < 3; a++) {
+      m[a] = 1e-3 * ((double)hi[a] - (double)lo[a]) + 1e-4;
+      p[a] = (k >> a) & 1 ? (double)hi[a] + 2.0 * m[a] : (double)lo[a] - 2.0 * m[a];
+    }
+    if (C.ortho) {
+      for (int a = 0; a < 3; a++) rel[a] = p[a] - cen[a];
+    } else {
+      const double q[3] = {p[0] - eye[0], p[1] - eye[1], p[2] - eye[2]};
+      const double qc = dot(q, c);
+      if (!(cc > 0.0) || !(qc > 1e-6 * cc)) return false;  // at or behind the eye plane
+      const double sc = cc / qc;
+      for (int a = 0; a < 3; a++) rel[a] = eye[a] + sc * q[a] - cen[a];
+    }
+    const double br = dot(rel, vr), bu = dot(rel, vu);
+    const double fx = (br * uu - bu * ru) / det, fy = (bu * rr - br * ru) / det;
+    const double x = fx / (double)C.scaling + (double)C.off_x, y = fy / (double)C.scaling + (double)C.off_y;
+    xmin = std::min(xmin, x); xmax = std::max(xmax, x); ymin = std::min(ymin, y); ymax = std::max(ymax, y);
+  }
+  if (!(xmin <= xmax) || !(ymin <= ymax)) return false;
+  const int x0 = (int)std::max(0.0, std::floor(xmin) - 2.0), x1 = (int)std::min((double)(w - 1), std::ceil(xmax) + 2.0);
+  const int y0 = (int)std::max(0.0, std::floor(ymin) - 2.0), y1 = (int)std::min((double)(h - 1), std::ceil(ymax) + 2.0);
+  if (x1 < x0 || y1 < y0) { rect[0] = rect[1] = rect[2] = rect[3] = 0; return true; }  // the box is off screen: nothing to generate
+  rect[0] = x0 / 8; rect[1] = y0 / 4;
+  rect[2] = x1 / 8 - rect[0] + 1; rect[3] = y1 / 4 - rect[1] + 1;
+  return true;
+}
+
 static int flight_submit_peer(gxy_vis *v, Flight &F, const DevCamera &C, int w, int h, float epsilon) {
   gxy_context *c = v->ctx;
   PeerArena &A = F.arena;
@@ -1602,7 +1822,11 @@ static int flight_submit_peer(gxy_vis *v, Flight &F, const DevCamera &C, int w, 
   S.kernel_launches += 3;
   // ---- wave 0: generation, trace of the primaries, shading of the hits (their AO/shadow rays follow in wave 1)
   if (flight_trace_begin(F, st)) return 1;
-  if (launch_fused_primary(P, C, F.L, w, h, fb, F.next.v, F.rawhits.p, (unsigned)npix, F.hits.v, F.cur.v, 0u, q, epsilon, &T, proxies, 0, 1, st)) return 1;
+  int rect[4];
+  const bool have_rect = peer_tile_rect(C, v->lmin, v->lmax, w, h, rect) && !(getenv("GXY_GEN_RECT") && atoi(getenv("GXY_GEN_RECT")) == 0);
+  if (launch_fused_primary(P, C, F.L, w, h, fb, F.next.v, F.rawhits.p, (unsigned)npix, F.hits.v, F.cur.v, 0u, q, epsilon, &T, proxies, 0, 1, st,
+                           have_rect ? rect : nullptr))
+    return 1;
   if (flight_trace_end(F, st)) return 1;
   S.kernel_launches += 3;
   if (launch_wave_epilogue(T, q, ++A.epoch, -1, spawn, F.err.p, st)) return 1;

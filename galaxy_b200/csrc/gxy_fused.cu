@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     gen_primary_peer_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevCamera C, int w, int h, int tiles_x,
                             unsigned n_queue, Rays out, unsigned queue_cap, FusedQueues *__restrict__ q, int me, int nranks,
-                            const PartProxy *__restrict__ prox, int skip_far) {
+                            const PartProxy *__restrict__ prox, int skip_far, int tile_x0, int tile_y0) {
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
   int x = 0, y = 0;
@@ -169,7 +169,10 @@ __global__ void __launch_bounds__(256)
   float gmin = 0.f;
   bool in_data = false;
   if (idx < n_queue) {
+    // tiles_x tiles per row of the launch's window, which starts at tile (tile_x0, tile_y0): the screen rectangle this rank's box
+    // projects into (peer_tile_rect), or the whole image
     tile_pixel(idx, tiles_x, 0, 1, x, y);
+    x += tile_x0 * 8; y += tile_y0 * 4;
     in_data = x < w && y < h && camera_ray(P, C, x, y, o3, d3, gmin);
   }
   if (in_data && skip_far) {
@@ -283,13 +286,33 @@ __global__ void __launch_bounds__(256) proxy_gather_kernel(const __grid_constant
   }
 }
 
+// One iteration of a persistent trace warp (all 32 lanes, converged): a node step for every lane that has no primitives pending, then
+// the cooperative primitive passes -- but only once prim_t lanes hold a primitive group, or no lane is left that could do a node
+// step.  A pass costs the whole warp ~330 instructions whether it serves one owner or eight; with a node step per lane and
+// iteration about 1.3 lanes of a warp reach a leaf, so running the passes every iteration (prim_t = 1) spends almost as many issue
+// slots on them as on the node steps.  Lanes that wait keep their node group; the order in which primitives are tested never
+// decides a result (smallest t, ties on the lowest ids).
+__device__ __forceinline__ void trace_iteration(const SceneParams &P, const RayCtx &rc, TravState &st, bool &trav, const bool anyhit,
+                                                uint2 *__restrict__ stack, uint2 *__restrict__ lstack, unsigned char *owner_slot,
+                                                const unsigned lane, const unsigned lt_mask, const int prim_t) {
+  const bool node_ready = trav && st.tg.y == 0u;
+  if (node_ready) node_step<0>(P, rc, st, stack, lstack);
+  const unsigned owners = __ballot_sync(FULLMASK, trav && st.tg.y != 0u);
+  if (owners != 0u) {
+    // lanes that will still be able to take a node step next iteration without a primitive pass
+    const unsigned can_node = __ballot_sync(FULLMASK, trav && st.tg.y == 0u && (st.ng.y > 0x00ffffffu || st.sp > 0));
+    if (__popc(owners) >= prim_t || can_node == 0u) coop_prim_passes(P, rc, st, trav, anyhit, owner_slot, lane, lt_mask);
+  }
+  if (trav) trav = trav_advance(st, stack, lstack);
+}
+
 // Trace of the generated primaries (persistent warps, dynamic fetch, cooperative primitive tests).
 // A surface hit leaves a 6-word raw record (ray, t, u, v, ids, record) for shade_hits_kernel; a miss is
 // classified here: TERMINATED (adds nothing: its colour is 0) or spilled towards a neighbour.
 template <int FETCH_T, int MIN_BLOCKS, bool PEER>
 __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
     primary_trace_kernel(const __grid_constant__ SceneParams P, Rays R, unsigned *__restrict__ raw, unsigned raw_stride, Rays spill,
-                         unsigned spill_cap, FusedQueues *__restrict__ q, const __grid_constant__ PeerTable T) {
+                         unsigned spill_cap, FusedQueues *__restrict__ q, const __grid_constant__ PeerTable T, int prim_t) {
   __shared__ uint2 stack[GXY_STACK_SMEM * GXY_TRACE_THREADS];
   __shared__ unsigned char owner_of[GXY_TRACE_THREADS / 32][8];
   uint2 lstack[GXY_STACK_LOCAL];
@@ -371,9 +394,7 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
       exhausted = exhausted || __any_sync(FULLMASK, ex_local);
       if (exhausted && __ballot_sync(FULLMASK, pr.ray >= 0) == 0u) break;
     }
-    if (trav) node_step<0>(P, rc, st, stack, lstack);
-    coop_prim_passes(P, rc, st, trav, false, owner_of[warp], lane, lt_mask);
-    if (trav) trav = trav_advance(st, stack, lstack);
+    trace_iteration(P, rc, st, trav, false, stack, lstack, owner_of[warp], lane, lt_mask, prim_t);
   }
 }
 
@@ -479,7 +500,7 @@ template <int FETCH_T, int MIN_BLOCKS, bool PEER>
 __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
     fused_secondary_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevLights L, int w, int h, int nsec,
                            float4 *__restrict__ fb, Rays hits, Rays spill, unsigned spill_cap, FusedQueues *__restrict__ q, float epsilon,
-                           int anyhit_secondary, const __grid_constant__ PeerTable T, int parity_out) {
+                           int anyhit_secondary, const __grid_constant__ PeerTable T, int parity_out, int prim_t) {
   __shared__ uint2 stack[GXY_STACK_SMEM * GXY_TRACE_THREADS];
   __shared__ unsigned char owner_of[GXY_TRACE_THREADS / 32][8];
   __shared__ float ao_tab[3][256];  // divergent indices: shared memory, not the constant cache
@@ -576,9 +597,7 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
       exhausted = exhausted || __any_sync(FULLMASK, ex_local);
       if (exhausted && __ballot_sync(FULLMASK, pr.ray >= 0) == 0u) break;
     }
-    if (trav) node_step<0>(P, rc, st, stack, lstack);
-    coop_prim_passes(P, rc, st, trav, pr.anyhit, owner_of[warp], lane, lt_mask);
-    if (trav) trav = trav_advance(st, stack, lstack);
+    trace_iteration(P, rc, st, trav, pr.anyhit, stack, lstack, owner_of[warp], lane, lt_mask, prim_t);
   }
 }
 
@@ -593,7 +612,7 @@ template <int FETCH_T, int MIN_BLOCKS>
 __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
     inbox_trace_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ PeerTable T, int parity_in, int w,
                        float4 *__restrict__ fb, unsigned *__restrict__ raw, unsigned raw_stride, FusedQueues *__restrict__ q,
-                       int anyhit_secondary) {
+                       int anyhit_secondary, int prim_t) {
   __shared__ uint2 stack[GXY_STACK_SMEM * GXY_TRACE_THREADS];
   __shared__ unsigned char owner_of[GXY_TRACE_THREADS / 32][8];
   uint2 lstack[GXY_STACK_LOCAL];
@@ -684,9 +703,7 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
       exhausted = exhausted || __any_sync(FULLMASK, ex_local);
       if (exhausted && __ballot_sync(FULLMASK, pr.ray >= 0) == 0u) break;
     }
-    if (trav) node_step<0>(P, rc, st, stack, lstack);
-    coop_prim_passes(P, rc, st, trav, pr.anyhit, owner_of[warp], lane, lt_mask);
-    if (trav) trav = trav_advance(st, stack, lstack);
+    trace_iteration(P, rc, st, trav, pr.anyhit, stack, lstack, owner_of[warp], lane, lt_mask, prim_t);
   }
 }
 
@@ -760,12 +777,17 @@ __global__ void __launch_bounds__(256) fb_gather_kernel(const __grid_constant__ 
   const unsigned per = (T.npix + (unsigned)T.nranks - 1u) / (unsigned)T.nranks;
   const unsigned lo = per * (unsigned)T.rank, hi = min(T.npix, lo + per);
   float4 *__restrict__ dst = reinterpret_cast<float4 *>(T.base[0] + T.off_final);
+  // all peer loads of a pixel are issued before the first is used (8 ranks: 8 x 16 bytes in flight per thread); the launch is one
+  // CTA per SM on purpose: enough loads in flight to fill NVLink, while the SMs stay with the trace kernels of the frames behind
   for (unsigned i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
-    float4 acc = reinterpret_cast<const float4 *>(T.base[0] + T.off_fb)[i];
-    for (int r = 1; r < T.nranks; r++) {
-      const float4 v = reinterpret_cast<const float4 *>(T.base[r] + T.off_fb)[i];
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
+    float4 v[GXY_MAX_RANKS];
+#pragma unroll
+    for (int r = 0; r < GXY_MAX_RANKS; r++)
+      if (r < T.nranks) v[r] = __ldcs(reinterpret_cast<const float4 *>(T.base[r] + T.off_fb) + i);
+    float4 acc = v[0];
+#pragma unroll
+    for (int r = 1; r < GXY_MAX_RANKS; r++)
+      if (r < T.nranks) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
     dst[i] = acc;
   }
 }
@@ -794,6 +816,13 @@ static unsigned fused_blocks_per_sm() {
   return b;
 }
 
+// lanes of a warp that must hold a primitive group before the cooperative primitive passes run (trace_iteration)
+static int prim_threshold() {
+  int t = 1;
+  if (const char *e = getenv("GXY_PRIM_T")) t = std::max(1, std::min(32, atoi(e)));
+  return t;
+}
+
 static int fetch_threshold(const char *env) {
   int ft = 12;  // measured optimum on the 100M-triangle scene (tools/trace_sweep.py, GXY_FETCH_SWEEP)
   if (const char *e = getenv(env)) ft = atoi(e);
@@ -802,23 +831,31 @@ static int fetch_threshold(const char *env) {
 
 int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLights &L, int w, int h, float *fb, Rays prim, unsigned *raw,
                          unsigned raw_stride, Rays hits, Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, const PeerTable *peer,
-                         const PartProxy *proxies, int band, int n_bands, cudaStream_t st) {
+                         const PartProxy *proxies, int band, int n_bands, cudaStream_t st, const int *tile_rect) {
   if (ensure_ao_tables()) return 1;
   const int tiles_x = (w + 7) / 8, tiles_y = (h + 3) / 4;
   const int rows = (tiles_y - band + n_bands - 1) / n_bands;  // tile rows band, band + n_bands, ...
   if (rows <= 0) return 0;
-  const unsigned n_queue = (unsigned)tiles_x * (unsigned)rows * 32u;
+  unsigned n_queue = (unsigned)tiles_x * (unsigned)rows * 32u;
   const PeerTable T = peer ? *peer : no_peers();
   const int skip_far = !(getenv("GXY_GEN_SKIP_FAR") && atoi(getenv("GXY_GEN_SKIP_FAR")) == 0);
-  if (peer) gen_primary_peer_kernel<<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, n_queue, prim, raw_stride, q, T.rank, T.nranks, proxies, skip_far);
+  if (peer) {
+    // generation only over the tiles this rank's box can project into (tile_rect = x0, y0, nx, ny in 8x4 tiles; NULL: all)
+    int tx0 = 0, ty0 = 0, ntx = tiles_x, nty = tiles_y;
+    if (tile_rect && skip_far) { tx0 = tile_rect[0]; ty0 = tile_rect[1]; ntx = tile_rect[2]; nty = tile_rect[3]; }
+    const unsigned n_gen = (unsigned)ntx * (unsigned)nty * 32u;
+    if (n_gen > 0u)
+      gen_primary_peer_kernel<<<(n_gen + 255) / 256, 256, 0, st>>>(P, C, w, h, ntx, n_gen, prim, raw_stride, q, T.rank, T.nranks, proxies, skip_far,
+                                                                    tx0, ty0);
+  }
   else gen_primary_kernel<<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, band, n_bands, n_queue, prim, spill, spill_cap, q);
   gxy_timeline_mark("gen", st);
   const unsigned needed = (n_queue + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
   const unsigned blocks = std::min<unsigned>(needed, (unsigned)sm_count() * fused_blocks_per_sm());
 #define GXY_LAUNCH_P(FT)                                                                                                                 \
   do {                                                                                                                                   \
-    if (peer) primary_trace_kernel<FT, 8, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T); \
-    else primary_trace_kernel<FT, 8, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T);      \
+    if (peer) primary_trace_kernel<FT, 8, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T, prim_threshold()); \
+    else primary_trace_kernel<FT, 8, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T, prim_threshold());      \
   } while (0)
   switch (fetch_threshold("GXY_FETCH_P")) {
     case 4: GXY_LAUNCH_P(4); break;
@@ -829,28 +866,30 @@ int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLigh
   }
 #undef GXY_LAUNCH_P
   gxy_timeline_mark("primary", st);
-  shade_hits_kernel<false><<<(n_queue + 255) / 256, 256, 0, st>>>(P, L, prim, nullptr, raw, raw_stride, w, reinterpret_cast<float4 *>(fb), hits, q,
-                                                                  epsilon);
+  // grid-stride over the hits the trace found (far fewer than pixels across ranks): no more CTAs than the device holds at once
+  const unsigned shade_blocks = std::min<unsigned>((n_queue + 255) / 256, (unsigned)sm_count() * 8u);
+  shade_hits_kernel<false><<<shade_blocks, 256, 0, st>>>(P, L, prim, nullptr, raw, raw_stride, w, reinterpret_cast<float4 *>(fb), hits, q, epsilon);
   GXY_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_fused_secondary(const SceneParams &P, const DevLights &L, int w, int h, int nsec, long long max_rays, float *fb, Rays hits,
                            Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, bool anyhit, const PeerTable *peer, int parity_out,
-                           cudaStream_t st) {
+                           cudaStream_t st, int blocks_per_sm) {
   if (nsec <= 0 || max_rays <= 0) return 0;
   if (ensure_ao_tables()) return 1;
   const long long needed = (max_rays + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
-  const unsigned blocks = (unsigned)std::min<long long>(needed, (long long)sm_count() * fused_blocks_per_sm());
+  const unsigned bps = blocks_per_sm > 0 ? (unsigned)std::min(8, blocks_per_sm) : fused_blocks_per_sm();
+  const unsigned blocks = (unsigned)std::min<long long>(needed, (long long)sm_count() * bps);
   const PeerTable T = peer ? *peer : no_peers();
 #define GXY_LAUNCH_S(FT)                                                                                                              \
   do {                                                                                                                                \
     if (peer)                                                                                                                         \
       fused_secondary_kernel<FT, 8, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, L, w, h, nsec, reinterpret_cast<float4 *>(fb), hits, spill, \
-                                                                                spill_cap, q, epsilon, anyhit ? 1 : 0, T, parity_out);     \
+                                                                                spill_cap, q, epsilon, anyhit ? 1 : 0, T, parity_out, prim_threshold());     \
     else                                                                                                                              \
       fused_secondary_kernel<FT, 8, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, L, w, h, nsec, reinterpret_cast<float4 *>(fb), hits, spill, \
-                                                                                 spill_cap, q, epsilon, anyhit ? 1 : 0, T, parity_out);    \
+                                                                                 spill_cap, q, epsilon, anyhit ? 1 : 0, T, parity_out, prim_threshold());    \
   } while (0)
   switch (fetch_threshold("GXY_FETCH_S")) {
     case 4: GXY_LAUNCH_S(4); break;
@@ -865,15 +904,16 @@ int launch_fused_secondary(const SceneParams &P, const DevLights &L, int w, int 
 }
 
 int launch_inbox_wave(const SceneParams &P, const DevLights &L, const PeerTable &T, int parity_in, int w, int h, float *fb, unsigned *raw,
-                      unsigned raw_stride, Rays hits, FusedQueues *q, float epsilon, bool anyhit, cudaStream_t st) {
+                      unsigned raw_stride, Rays hits, FusedQueues *q, float epsilon, bool anyhit, cudaStream_t st, int blocks_per_sm) {
   (void)h;
-  const unsigned blocks = (unsigned)sm_count() * 8u;
+  const unsigned bps = blocks_per_sm > 0 ? (unsigned)std::min(8, blocks_per_sm) : 8u;
+  const unsigned blocks = (unsigned)sm_count() * bps;
   inbox_trace_kernel<12, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, T, parity_in, w, reinterpret_cast<float4 *>(fb), raw, raw_stride, q,
-                                                                   anyhit ? 1 : 0);
+                                                                   anyhit ? 1 : 0, prim_threshold());
   gxy_timeline_mark("inbox", st);
   const float4 *inbox = reinterpret_cast<const float4 *>(T.base[T.rank] + T.off_inbox[parity_in]);
-  shade_hits_kernel<true><<<(unsigned)sm_count() * 4u, 256, 0, st>>>(P, L, hits, inbox, raw, raw_stride, w, reinterpret_cast<float4 *>(fb), hits, q,
-                                                                    epsilon);
+  shade_hits_kernel<true><<<(unsigned)sm_count() * std::min(4u, bps), 256, 0, st>>>(P, L, hits, inbox, raw, raw_stride, w, reinterpret_cast<float4 *>(fb),
+                                                                                  hits, q, epsilon);
   GXY_CUDA(cudaGetLastError());
   return 0;
 }
@@ -900,7 +940,9 @@ int launch_proxy_gather(const PeerTable &T, PartProxy *out, cudaStream_t st) {
 }
 
 int launch_fb_gather(const PeerTable &T, cudaStream_t st) {
-  fb_gather_kernel<<<(unsigned)sm_count() * 4u, 256, 0, st>>>(T);
+  unsigned per_sm = 1u;
+  if (const char *e = getenv("GXY_GATHER_BLOCKS")) per_sm = (unsigned)std::max(1, std::min(8, atoi(e)));
+  fb_gather_kernel<<<(unsigned)sm_count() * per_sm, 256, 0, st>>>(T);
   GXY_CUDA(cudaGetLastError());
   return 0;
 }

@@ -126,7 +126,7 @@ struct PeerTable {  // kernel parameter: every rank's arena as mapped in THIS pr
 // raw_stride: words per plane of `raw` (>= the number of rays this launch can queue)
 int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLights &L, int w, int h, float *fb, Rays prim, unsigned *raw,
                          unsigned raw_stride, Rays hits, Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, const PeerTable *peer,
-                         const PartProxy *proxies, int band, int n_bands, cudaStream_t st);
+                         const PartProxy *proxies, int band, int n_bands, cudaStream_t st, const int *tile_rect = nullptr);
 // write this rank's PartProxy into its arena; after the next flag barrier ...
 int launch_proxy_publish(const SceneParams &P, const PeerTable &T, cudaStream_t st);
 // ... copy every rank's published PartProxy (peer loads) into the local table `out` (nranks entries)
@@ -134,11 +134,11 @@ int launch_proxy_gather(const PeerTable &T, PartProxy *out, cudaStream_t st);
 // AO + shadow rays of the hit records [q->hits_done, q->n_hits): generate -> trace -> classify -> framebuffer
 int launch_fused_secondary(const SceneParams &P, const DevLights &L, int w, int h, int nsec, long long max_rays, float *fb, Rays hits,
                            Rays spill, unsigned spill_cap, FusedQueues *q, float epsilon, bool anyhit, const PeerTable *peer, int parity_out,
-                           cudaStream_t st);
+                           cudaStream_t st, int blocks_per_sm = 0);
 // one wave >= 1 of the peer path: trace the records of inbox[parity_in]; PRIMARY hits -> raw records -> shading
 // (hit records appended to `hits`); everything else is classified: framebuffer, dropped, or the next inbox
 int launch_inbox_wave(const SceneParams &P, const DevLights &L, const PeerTable &T, int parity_in, int w, int h, float *fb, unsigned *raw,
-                      unsigned raw_stride, Rays hits, FusedQueues *q, float epsilon, bool anyhit, cudaStream_t st);
+                      unsigned raw_stride, Rays hits, FusedQueues *q, float epsilon, bool anyhit, cudaStream_t st, int blocks_per_sm = 0);
 // end of a wave: queue bookkeeping, reset of the consumed inbox, flag barrier across ranks, global pending count
 int launch_wave_epilogue(const PeerTable &T, FusedQueues *q, unsigned epoch, int parity_consumed, bool hits_spawn, int *error_flag,
                          cudaStream_t st);

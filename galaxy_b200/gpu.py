@@ -118,6 +118,12 @@ def lib():
         L.gxy_raylist_get_view.argtypes = [vp, C.POINTER(RayListView)]
         L.gxy_raylist_free.argtypes = [vp]
         L.gxy_classify.argtypes = [vp, RayListView]
+        L.gxy_raylist_upload.argtypes = [vp, RayListView, C.POINTER(vp)]
+        L.gxy_raylist_size.argtypes = [vp, ip]
+        L.gxy_raylist_download.argtypes = [vp, RayListView]
+        L.gxy_dev_raylist_free.argtypes = [vp]
+        L.gxy_trace_raylist_dev.argtypes = [vp, C.POINTER(Lighting), vp, C.c_float, C.POINTER(vp)]
+        L.gxy_classify_dev.argtypes = [vp, vp]
         L.gxy_generate_rays.argtypes = [vp, C.POINTER(Camera), C.c_int, C.c_int, RayListView, ip]
         L.gxy_intersect.argtypes = [vp, C.c_int, fp, fp, fp, fp, ip, fp]
         L.gxy_render.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(Camera), C.POINTER(Lighting), C.c_int, C.c_int, C.c_float, C.POINTER(Stats)]
@@ -353,6 +359,12 @@ class Scene:
     def classify(self, rays, n):
         check(lib().gxy_classify(self.h, RayListView(_f(rays), n, rays.shape[1])))
 
+    def upload_raylist(self, rays, n):
+        """A device-resident copy of the first n rays of a (25, aligned_n) RayList array (gxy_raylist_upload)."""
+        h = C.c_void_p()
+        check(lib().gxy_raylist_upload(self.h, RayListView(_f(rays), n, rays.shape[1]), C.byref(h)))
+        return DevRayList(self, h)
+
     def generate_rays(self, camera, w, h):
         al = max(16, (w * h + 15) & ~15)
         rays = np.zeros((25, al), np.float32)
@@ -387,6 +399,45 @@ class Scene:
 
     def download_wait(self):
         check(lib().gxy_frame_download_wait(self.h))
+
+
+class DevRayList:
+    """A RayList that stays on the device between Trace / Classify calls (gxy_dev_raylist)."""
+
+    def __init__(self, scene, h):
+        self.scene, self.h = scene, h
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().gxy_dev_raylist_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @property
+    def n(self):
+        n = C.c_int()
+        check(lib().gxy_raylist_size(self.h, C.byref(n)))
+        return n.value
+
+    def trace(self, lighting, epsilon=0.001):
+        """TraceRays::Trace in place; returns the spawned SECONDARY list as another DevRayList, or None"""
+        L = make_lighting(lighting)
+        out = C.c_void_p()
+        check(lib().gxy_trace_raylist_dev(self.scene.h, C.byref(L), self.h, epsilon, C.byref(out)))
+        return DevRayList(self.scene, out) if out else None
+
+    def classify(self):
+        check(lib().gxy_classify_dev(self.scene.h, self.h))
+
+    def download(self):
+        """-> ((25, aligned_n) float32 array, n)"""
+        n = self.n
+        al = max(16, (n + 15) & ~15)
+        rays = np.zeros((25, al), np.float32)
+        check(lib().gxy_raylist_download(self.h, RayListView(_f(rays), n, al)))
+        return rays, n
 
 
 class _Pinned:

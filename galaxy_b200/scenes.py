@@ -603,6 +603,78 @@ def fbm3(p, seed, octaves=5):
     return s / norm
 
 
+# ---- the noise volume of the volume workloads C3 / C4 ---------------------------------------------------------------
+NOISE_SEED = 7
+
+
+def noise_volume_block(n, z0, z1, y0, y1, x0, x1, device="cpu"):
+    """voxels [z0:z1, y0:y1, x0:x1] of the n^3 noise volume: v = eightBalls(p) + 0.15 * fbm(8 p), p in [-1,1]^3 (origin -1, spacing
+    2/(n-1)), fbm = 5 octaves of trilinear value noise whose lattice values are PCG32 hashes (seed 7): exactly fbm3() above, written
+    with torch so that a 2048^3 volume is synthesised slab by slab on the device.  float64 arithmetic, float32 result."""
+    import torch
+    dev = torch.device(device)
+    sp = 2.0 / (n - 1)
+    cz = (-1.0 + torch.arange(z0, z1, device=dev, dtype=torch.float64) * sp).view(-1, 1, 1)
+    cy = (-1.0 + torch.arange(y0, y1, device=dev, dtype=torch.float64) * sp).view(1, -1, 1)
+    cx = (-1.0 + torch.arange(x0, x1, device=dev, dtype=torch.float64) * sp).view(1, 1, -1)
+    eb = torch.sqrt((cx.abs() - 0.5) ** 2 + (cy.abs() - 0.5) ** 2 + (cz.abs() - 0.5) ** 2)
+    M = 0xFFFFFFFF
+
+    def pcg(x):
+        x = (x * 747796405 + 2891336453) & M
+        w = (((x >> ((x >> 28) + 4)) ^ x) * 277803737) & M
+        return ((w >> 22) ^ w) & M
+
+    def axis(c, f):
+        p = c * f
+        pf = torch.floor(p)
+        fr = p - pf
+        return pf.to(torch.int64), fr * fr * (3 - 2 * fr)
+
+    s, a, f, norm = 0.0, 0.5, 1.0, 0.0
+    for o in range(5):
+        (ix, fx), (iy, fy), (iz, fz) = axis(cx, 8.0 * f), axis(cy, 8.0 * f), axis(cz, 8.0 * f)
+        val = 0.0
+        for dz in (0, 1):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    h = ((ix + dx) * 73856093) ^ ((iy + dy) * 19349663) ^ ((iz + dz) * 83492791) ^ ((NOISE_SEED + o) * 2654435761)
+                    v = pcg(h & M).to(torch.float64) / 4294967296.0
+                    w = (fx if dx else 1 - fx) * (fy if dy else 1 - fy) * (fz if dz else 1 - fz)
+                    val = val + w * v
+        s = s + a * val
+        norm += a
+        a *= 0.5
+        f *= 2.0
+    return (eb + 0.15 * (s / norm)).to(torch.float32)
+
+
+class _LazyNoiseData:
+    """data[z, y, x] of a noise volume, synthesised on demand block by block (what build_partitions slices out per partition)"""
+
+    def __init__(self, n, device):
+        self.n, self.device, self.shape = n, device, (n, n, n)
+
+    def __getitem__(self, key):
+        zs, ys, xs = [k.indices(self.n) for k in key]
+        out = np.empty((zs[1] - zs[0], ys[1] - ys[0], xs[1] - xs[0]), np.float32)
+        for z in range(zs[0], zs[1], 32):   # slabs of 32 planes: ~1 GB of float64 temporaries at 2048^2 per plane
+            z1 = min(z + 32, zs[1])
+            out[z - zs[0]:z1 - zs[0]] = noise_volume_block(self.n, z, z1, ys[0], ys[1], xs[0], xs[1], self.device).cpu().numpy()
+        return out
+
+
+def noise_volume(n, device="cpu"):
+    """the C3/C4 volume as a VolumeDataset whose voxels are generated when a partition asks for its brick"""
+    sp = 2.0 / (n - 1)
+    ds = VolumeDataset.__new__(VolumeDataset)
+    ds.origin = np.asarray([-1.0, -1.0, -1.0], f32)
+    ds.counts = (n, n, n)
+    ds.deltas = np.asarray([sp, sp, sp], f32)
+    ds.data = _LazyNoiseData(n, device)
+    return ds
+
+
 def eightballs_mesh(n_lat, n_lon, seed=11, bump=0.05):
     """C5 mesh: 8 UV-spheres centred (+-.5,+-.5,+-.5), radius 0.3*(1+bump*fbm(6*dir)),
     n_lat x n_lon quads each split in two (polar quads keep one zero-area triangle), data = |p|."""
@@ -632,19 +704,6 @@ def eightballs_mesh(n_lat, n_lon, seed=11, bump=0.05):
     I = np.concatenate(I).astype(np.int32)
     D = np.sqrt((V.astype(np.float64) ** 2).sum(1)).astype(f32)
     return TrianglesDataset(V, N, D, I)
-
-
-def noise_volume(n, seed=7):
-    """C3/C4 volume: v = eightBalls(p) + 0.15*fbm(8p) on [-1,1]^3, n^3 float32 (built slab-wise)."""
-    c = np.linspace(-1.0, 1.0, n)
-    out = np.empty((n, n, n), f32)
-    Y, X = np.meshgrid(c, c, indexing="ij")
-    for k in range(n):
-        Z = np.full_like(X, c[k])
-        eb = np.sqrt((np.abs(X) - .5) ** 2 + (np.abs(Y) - .5) ** 2 + (np.abs(Z) - .5) ** 2)
-        out[k] = (eb + 0.15 * fbm3(8.0 * np.stack([X, Y, Z], -1) + 31.0, seed)).astype(f32)
-    sp = 2.0 / (n - 1)
-    return VolumeDataset([-1.0, -1.0, -1.0], (n, n, n), [sp, sp, sp], out)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -39,6 +39,7 @@ typedef struct gxy_particles gxy_particles;  /* src/data/Particles + OsprayParti
 typedef struct gxy_pathlines gxy_pathlines;  /* src/data/PathLines + OsprayPathLines              */
 typedef struct gxy_vis       gxy_vis;        /* src/renderer/Visualization (one partition)        */
 typedef struct gxy_raylist   gxy_raylist;    /* src/renderer/Rays.h RayList, library-owned        */
+typedef struct gxy_dev_raylist gxy_dev_raylist; /* ... a RayList that stays on the device between calls */
 
 /* Lighting_ispc (src/renderer/Lighting.ih:23-32; Lighting_Set{Lights,K,AO,ShadowFlag},
  * Lighting.ispc:54-134). */
@@ -185,6 +186,13 @@ void gxy_factor(int n, int factors[3]);
 void gxy_partition(int n, const int factors[3], const int grid[3], int *out);
 
 /* ---- per-RayList entry points (the reference's hot call) ------------------------------------ */
+/* Threading: the reference calls TraceRays::Trace from GXY_NTHREADS pool threads (default 5) at once, every thread with its
+ * own TraceRays object, all sharing one Visualization and Lighting that are read-only while rendering
+ * (src/framework/Application.cpp:75, src/renderer/Renderer.cpp:504-556).  The entry points of this section may be called concurrently
+ * from any number of host threads on ONE gxy_vis: each call takes one of the Visualization's 8 list lanes (own CUDA stream, own device
+ * lists, own error flag) and concurrent calls overlap on the device; a ninth caller waits for a free lane.  gxy_vis_commit and the
+ * gxy_vis_add_* calls must not run at the same time (commits happen while rendering is quiescent, as in the reference).
+ * gxy_last_error() is per thread. */
 /* TraceRays::Trace (src/renderer/TraceRays.cpp:68-146), i.e. ispc::TraceRays_TraceRays +
  * _ambientLighting + _generateAORays + _diffuseLighting + _generateShadowRays
  * (TraceRays.ispc:326,625,735,763,859).  rays (host) are traced in place; *out receives the
@@ -196,6 +204,18 @@ int  gxy_raylist_get_view(gxy_raylist *, gxy_raylist_view *view);
 void gxy_raylist_free(gxy_raylist *);
 /* Renderer::Classify + AssignDestinations (src/renderer/Renderer.cpp:304-454) */
 int  gxy_classify(gxy_vis *, gxy_raylist_view rays);
+/* Device-resident RayLists (SURVEY 8b "Ownership": the reference's RayList is one refcounted smem block that travels between
+ * Renderer::Trace, Classify and the message layer, Renderer.h:223; here the list may stay in HBM between those calls).
+ * upload copies the 25 columns H2D once; trace / classify then work on the device copy -- the secondary list of a trace is itself a
+ * device list, so the waves of a frame driven list by list (Renderer::ProcessRays) never cross PCIe; download copies all columns
+ * back (host list with aligned_n >= gxy_raylist_size). */
+int  gxy_raylist_upload(gxy_vis *, gxy_raylist_view rays, gxy_dev_raylist **out);
+int  gxy_raylist_size(gxy_dev_raylist *, int *n);
+int  gxy_raylist_download(gxy_dev_raylist *, gxy_raylist_view rays);
+void gxy_dev_raylist_free(gxy_dev_raylist *);
+/* TraceRays::Trace on a device list: rays traced in place; *secondary (may be NULL) receives the spawned AO/shadow list or NULL */
+int  gxy_trace_raylist_dev(gxy_vis *, const gxy_lighting *lights, gxy_dev_raylist *rays, float epsilon, gxy_dev_raylist **secondary);
+int  gxy_classify_dev(gxy_vis *, gxy_dev_raylist *rays);
 /* Camera::generate_initial_rays + SpawnRays (src/renderer/Camera.cpp:379-493,528-829) for this
  * partition; rays.aligned_n >= w*h; *n_out = number of rays kept, in pixel order. */
 int  gxy_generate_rays(gxy_vis *, const gxy_camera *, int w, int h, gxy_raylist_view rays, int *n_out);

@@ -10,9 +10,7 @@ from tests import util
 
 pytestmark = pytest.mark.gpu
 
-GOLDS = [("infinite", 0, 0.999), ("infinite-shadow", 0, 0.999), ("absolute", 0, 0.999), ("absolute-shadow", 0, 0.999),
-         ("camera", 0, 0.999), ("camera-shadow", 0, 0.999), ("xyz", 0, 0.999), ("oneBall", 0, 0.999),
-         ("nineBalls", 0, 0.997), ("nineBalls", 1, 0.998), ("nineBalls", 2, 0.999)]
+from tests.test_oracle_golds import GOLDS, check_gold_fraction  # 99.9 % for every gold; nineBalls_0/_1: documented deviation -> xfail
 
 
 @pytest.fixture(scope="module")
@@ -49,8 +47,8 @@ def test_state_files_match_oracle_and_golds(gpu, oracle, golden_dir, provider, n
     rel = np.abs(fb_g - fb_o).max() / max(1e-12, np.abs(fb_o).max())
     print(name, cam_idx, "fb<=1/255: %.6f img: %.6f gold: %.6f max rel fb err %.3g" % (frac_fb, frac_img, frac_gold, rel), st_g)
     assert frac_fb >= 0.999 and frac_img >= 0.999
-    assert frac_gold >= min_gold
     assert rel <= 1e-3  # volume-integrated colour/opacity within 1e-3 relative (north star)
+    check_gold_fraction(name, cam_idx, frac_gold, min_gold)  # last: an expected failure must not hide the asserts above
 
 
 @pytest.mark.parametrize("name", ["oneBall", "nineBalls", "xyz", "camera-shadow"])

@@ -107,18 +107,22 @@ def test_errors_are_reported_not_fatal(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,n_images,min_gold", [("oneBall", 1, 0.999), ("nineBalls", 3, 0.997), ("xyz", 1, 0.999), ("camera-shadow", 1, 0.999)])
-def test_gxywriter_renders_reference_states_to_gold(tmp_path, golden_dir, name, n_images, min_gold):
+@pytest.mark.parametrize("name,n_images", [("oneBall", 1), ("nineBalls", 3), ("xyz", 1), ("camera-shadow", 1)])
+def test_gxywriter_renders_reference_states_to_gold(tmp_path, golden_dir, name, n_images):
+    from tests.test_oracle_golds import check_gold_fraction  # 99.9 % for every gold; nineBalls_0/_1: documented deviation -> xfail
     state, _ = stage(str(tmp_path), name, 256)
     r = subprocess.run([EXE, "-s", "512", "512", state], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
     assert r.returncode == 0, r.stderr + r.stdout
     assert "TIMING total" in r.stdout
+    fracs = []
     for k in range(n_images):
         img = np.asarray(Image.open(os.path.join(str(tmp_path), "image_%05d.png" % k)).convert("RGBA"))
         gold = np.asarray(Image.open(os.path.join(golden_dir, "golds", "%s_%05d.png" % (name, k))).convert("RGBA"))
-        frac = util.image_fraction(img, gold)
-        print(name, k, "fraction within 1/255 of the gold:", frac)
-        assert img.shape == gold.shape and frac >= min_gold
+        assert img.shape == gold.shape
+        fracs.append(util.image_fraction(img, gold))
+        print(name, k, "fraction within 1/255 of the gold:", fracs[-1])
+    for k in reversed(range(n_images)):   # (the documented deviations, nineBalls_0/_1, last: an xfail ends the test)
+        check_gold_fraction(name, k, fracs[k])
 
 
 @pytest.mark.gpu

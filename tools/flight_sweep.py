@@ -78,12 +78,16 @@ for env in envs:
             c = torch.tensor([rays, busy, fr[-1]["dequeued_rays"]], dtype=torch.float64, device="cuda")
             if world > 1:
                 dist.all_reduce(c)
-            res.append((t[0].item() / steps, t[1].item() / steps, c[1].item() / world, c[0].item(), c[2].item()))
+            pr = torch.zeros(world, dtype=torch.float64, device="cuda")
+            pr[rank] = fr[-1]["dequeued_rays"]
+            if world > 1:
+                dist.all_reduce(pr)
+            res.append((t[0].item() / steps, t[1].item() / steps, c[1].item() / world, c[0].item(), c[2].item(), [int(x) for x in pr.tolist()]))
         if rank == 0:
             best = min(res)
             print(json.dumps({"world": world, "env": env, "depth": depth, "ms_per_frame_device": round(best[0], 4), "ms_per_frame_wall": round(best[1], 4),
                               "frame_latency_ms": round(best[2], 4), "Mrays/s": round(best[3] / best[0] / 1e3, 1), "rays": int(best[3]),
-                              "dequeued": int(best[4]), "all": [round(r[0], 4) for r in res]}), flush=True)
+                              "dequeued": int(best[4]), "dequeued_per_rank": best[5], "all": [round(r[0], 4) for r in res]}), flush=True)
     for k, v in sets:
         os.environ.pop(k, None)
 if world > 1:
