@@ -274,6 +274,8 @@ struct Flight {
   gxy_lighting lights;
   DevLights L;
   gxy_stats S;
+  int prog_frame = 0;     // gxy_render_progressive_submit: the frame number and camera of the frame on this slot
+  gxy_camera prog_cam;
 };
 
 
@@ -1027,15 +1029,17 @@ struct LaneGuard {
   int prepare() {
     if (!l->st) GXY_CUDA(cudaStreamCreateWithFlags(&l->st, cudaStreamNonBlocking));
     if (!l->err.p) {
-      if (l->err.reserve(4)) return 1;
-      GXY_CUDA(cudaMemsetAsync(l->err.p, 0, sizeof(int) * 4, l->st));
+      if (l->err.reserve(8)) return 1;
+      GXY_CUDA(cudaMemsetAsync(l->err.p, 0, sizeof(int) * 8, l->st));
     }
     return 0;
   }
-  // the scene as this call's kernels see it: the lane's own error flag
+  // the scene as this call's kernels see it: the lane's own error flag and its own ray-queue head (the persistent trace kernel
+  // pulls rays through SceneParams::work_counter; two concurrent launches must not share one)
   SceneParams params() const {
     SceneParams P = v->P;
     P.error_flag = l->err.p;
+    P.work_counter = reinterpret_cast<unsigned *>(l->err.p + 4);
     return P;
   }
   int check_error() {
@@ -2428,33 +2432,46 @@ int gxy_progressive_reset(gxy_vis *v) {
   return 0;
 }
 
-int gxy_render_progressive(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const gxy_lighting *lights, int w, int h, float epsilon,
-                           int frame, gxy_stats *stats) {
-  GXY_CHECK(nparts >= 1 && parts && cam && lights && w > 0 && h > 0, "gxy_render_progressive: bad arguments");
+static int progressive_check(int nparts, gxy_vis *const *parts) {
   for (int p = 0; p < nparts; p++) {
     if (check_vis(parts[p])) return 1;
     GXY_CHECK(parts[p]->ctx->comm == nullptr, "gxy_render_progressive drives all partitions from one process (no communicator)");
     GXY_CHECK(parts[p]->ctx->device == parts[0]->ctx->device, "gxy_render_progressive: all partitions of one call live on one device");
   }
-  gxy_vis *own = parts[0];
-  if (use_device(own->ctx)) return 1;
-  cudaStream_t st = own->ctx->stream;
+  return use_device(parts[0]->ctx);
+}
+// Rendering::local_commit (:218-238): the displayed image, its frame stamps and the touched mask for a w x h window
+static int progressive_prepare(gxy_vis *own, int w, int h) {
   const size_t npix = (size_t)w * h;
-  if (!own->prog_image || own->prog_w != w || own->prog_h != h) {  // Rendering::local_commit (:218-238)
+  if (!own->prog_image || own->prog_w != w || own->prog_h != h) {
     if (own->prog_image) cudaFree(own->prog_image);
     if (own->prog_kbuffer) cudaFree(own->prog_kbuffer);
     if (own->prog_touched) cudaFree(own->prog_touched);
     own->prog_image = nullptr; own->prog_kbuffer = nullptr; own->prog_touched = nullptr;
-    GXY_CUDA(cudaMalloc(&own->prog_image, sizeof(float) * 4 * npix));
-    GXY_CUDA(cudaMalloc(&own->prog_kbuffer, sizeof(int) * npix));
-    GXY_CUDA(cudaMalloc(&own->prog_touched, npix));
+    own->prog_w = 0; own->prog_h = 0;
+    float *img = nullptr;
+    int *kb = nullptr;
+    unsigned char *tc = nullptr;
+    if (cudaMalloc(&img, sizeof(float) * 4 * npix) != cudaSuccess || cudaMalloc(&kb, sizeof(int) * npix) != cudaSuccess ||
+        cudaMalloc(&tc, npix) != cudaSuccess) {
+      gxy_set_error("out of device memory for the progressive image (%d x %d): %s", w, h, cudaGetErrorString(cudaGetLastError()));
+      if (img) cudaFree(img);
+      if (kb) cudaFree(kb);
+      if (tc) cudaFree(tc);
+      return 1;
+    }
+    own->prog_image = img; own->prog_kbuffer = kb; own->prog_touched = tc;
     own->prog_w = w; own->prog_h = h;
     if (gxy_progressive_reset(own)) return 1;
   }
-  if (stats) memset(stats, 0, sizeof *stats);
-  if (frame < own->prog_frame) return 0;  // AddLocalPixels :138: the pixels of a stale frame are dropped
-  if (gxy_render(nparts, parts, cam, lights, w, h, epsilon, stats)) return 1;
-  // the pixels this frame wrote: those for which some partition originated a primary ray
+  return 0;
+}
+// ACCUMULATE_PIXEL for a whole finished frame (own->fb_result): the pixels this frame wrote are those for which some partition
+// originated a primary ray; each takes the new sum if its stamp is older, adds it if the frame number repeats
+static int progressive_merge(int nparts, gxy_vis *const *parts, const gxy_camera *cam, int w, int h, int frame) {
+  gxy_vis *own = parts[0];
+  cudaStream_t st = own->ctx->stream;
+  const size_t npix = (size_t)w * h;
   const DevCamera C = make_dev_camera(*cam, w, h);
   GXY_CUDA(cudaMemsetAsync(own->prog_touched, 0, npix, st));
   for (int p = 0; p < nparts; p++) {
@@ -2471,7 +2488,50 @@ int gxy_render_progressive(int nparts, gxy_vis *const *parts, const gxy_camera *
   if (launch_merge_stamped(own->fb_result, own->prog_image, own->prog_kbuffer, own->prog_touched, (int)npix, frame, st)) return 1;
   GXY_CUDA(cudaStreamSynchronize(st));
   if (frame > own->prog_frame) own->prog_frame = frame;
+  return 0;
+}
+
+int gxy_render_progressive(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const gxy_lighting *lights, int w, int h, float epsilon,
+                           int frame, gxy_stats *stats) {
+  GXY_CHECK(nparts >= 1 && parts && cam && lights && w > 0 && h > 0, "gxy_render_progressive: bad arguments");
+  if (progressive_check(nparts, parts)) return 1;
+  gxy_vis *own = parts[0];
+  if (progressive_prepare(own, w, h)) return 1;
+  if (stats) memset(stats, 0, sizeof *stats);
+  if (frame < own->prog_frame) return 0;  // AddLocalPixels :138: the pixels of a stale frame are dropped
+  if (gxy_render(nparts, parts, cam, lights, w, h, epsilon, stats)) return 1;
+  if (progressive_merge(nparts, parts, cam, w, h, frame)) return 1;
   if (stats) stats->kernel_launches += 4 * nparts + 1;
+  return 0;
+}
+
+// The same with frames in flight (gxyviewer keeps rendering while older frames are still on their way, Rendering.cpp:104-153):
+// a frame is submitted to a frame slot and merged into the displayed image when it is waited for.  Frames may be waited for in any
+// order: one that arrives after a newer frame was merged is stale and dropped, exactly as AddLocalPixels drops the pixels of a
+// superseded frame (:138-152).
+int gxy_render_progressive_submit(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const gxy_lighting *lights, int w, int h,
+                                  float epsilon, int frame, int slot) {
+  GXY_CHECK(nparts >= 1 && parts && cam && lights && w > 0 && h > 0, "gxy_render_progressive_submit: bad arguments");
+  if (progressive_check(nparts, parts)) return 1;
+  gxy_vis *own = parts[0];
+  if (progressive_prepare(own, w, h)) return 1;
+  if (gxy_render_submit(nparts, parts, cam, lights, w, h, epsilon, slot)) return 1;
+  Flight &F = *own->flights[slot];
+  F.prog_frame = frame;
+  F.prog_cam = *cam;
+  return 0;
+}
+int gxy_render_progressive_wait(int nparts, gxy_vis *const *parts, int slot, gxy_stats *stats, int *merged) {
+  GXY_CHECK(nparts >= 1 && parts && parts[0], "gxy_render_progressive_wait: bad arguments");
+  if (progressive_check(nparts, parts)) return 1;
+  gxy_vis *own = parts[0];
+  if (merged) *merged = 0;
+  if (gxy_render_wait(nparts, parts, slot, stats)) return 1;
+  Flight &F = *own->flights[slot];
+  GXY_CHECK(own->prog_image && own->prog_w == F.w && own->prog_h == F.h, "the progressive image was re-allocated while this frame was in flight");
+  if (F.prog_frame < own->prog_frame) return 0;  // superseded while in flight: dropped
+  if (progressive_merge(nparts, parts, &F.prog_cam, F.w, F.h, F.prog_frame)) return 1;
+  if (merged) *merged = 1;
   return 0;
 }
 

@@ -28,6 +28,13 @@ namespace gxy {
 
 #define FULLMASK 0xffffffffu
 // BVH levels below the root's children that the generation kernel tests before it queues a primary ray for the trace kernel
+// experiment switches of the persistent trace kernels (variant builds: make VARIANT=.. EXTRA=-D.. variant)
+#ifndef GXY_NODE_PREFETCH
+#define GXY_NODE_PREFETCH 0   // node_step<>: 1 = L2 prefetch of the next node + the new primitive records, 2 = the same into L1
+#endif
+#ifndef GXY_MIN_BLOCKS
+#define GXY_MIN_BLOCKS 8      // __launch_bounds__(128, N): 8 -> 64 registers; 10 -> 48; 12 -> 40 (spills)
+#endif
 #ifndef GXY_CULL_LEVELS
 #define GXY_CULL_LEVELS 3  // measured on C5: 1 -> 1.449 ms, 2 -> 1.449, 3 -> 1.416, 4 -> 1.425 per frame
 #endif
@@ -289,19 +296,22 @@ __global__ void __launch_bounds__(256) proxy_gather_kernel(const __grid_constant
 // One iteration of a persistent trace warp (all 32 lanes, converged): a node step for every lane that has no primitives pending, then
 // the cooperative primitive passes -- but only once prim_t lanes hold a primitive group, or no lane is left that could do a node
 // step.  A pass costs the whole warp ~330 instructions whether it serves one owner or eight; with a node step per lane and
-// iteration about 1.3 lanes of a warp reach a leaf, so running the passes every iteration (prim_t = 1) spends almost as many issue
-// slots on them as on the node steps.  Lanes that wait keep their node group; the order in which primitives are tested never
-// decides a result (smallest t, ties on the lowest ids).
+// iteration only a lane or two of a warp reach a leaf, so deferring the passes (prim_t > 1) looked like a saving.  MEASURED on C5 with 4
+// frames in flight (tools/flight_sweep.py, profiles/r02_b_primt_sweep.jsonl): prim_t 1: 1.111 ms per frame, 2: 1.116, 3: 1.120, 4: 1.132,
+// 6: 1.155, 8: 1.180, 12: 1.224 -- the lanes that wait lose more node steps than the fuller passes save, so the default stays 1
+// (GXY_PRIM_T).  Lanes that wait keep their node group; the order in which primitives are tested never decides a result (smallest t,
+// ties on the lowest ids), and the parity tests pass with prim_t = 4.
 __device__ __forceinline__ void trace_iteration(const SceneParams &P, const RayCtx &rc, TravState &st, bool &trav, const bool anyhit,
                                                 uint2 *__restrict__ stack, uint2 *__restrict__ lstack, unsigned char *owner_slot,
                                                 const unsigned lane, const unsigned lt_mask, const int prim_t) {
   const bool node_ready = trav && st.tg.y == 0u;
-  if (node_ready) node_step<0>(P, rc, st, stack, lstack);
+  if (node_ready) node_step<GXY_NODE_PREFETCH>(P, rc, st, stack, lstack);
   const unsigned owners = __ballot_sync(FULLMASK, trav && st.tg.y != 0u);
   if (owners != 0u) {
-    // lanes that will still be able to take a node step next iteration without a primitive pass
-    const unsigned can_node = __ballot_sync(FULLMASK, trav && st.tg.y == 0u && (st.ng.y > 0x00ffffffu || st.sp > 0));
-    if (__popc(owners) >= prim_t || can_node == 0u) coop_prim_passes(P, rc, st, trav, anyhit, owner_slot, lane, lt_mask);
+    // (second ballot: lanes that will still be able to take a node step next iteration without a primitive pass)
+    if (prim_t <= 1 || __popc(owners) >= prim_t ||
+        __ballot_sync(FULLMASK, trav && st.tg.y == 0u && (st.ng.y > 0x00ffffffu || st.sp > 0)) == 0u)
+      coop_prim_passes(P, rc, st, trav, anyhit, owner_slot, lane, lt_mask);
   }
   if (trav) trav = trav_advance(st, stack, lstack);
 }
@@ -811,8 +821,8 @@ static PeerTable no_peers() {
 // resident CTAs per SM a persistent trace launch asks for (8 = all the kernel is compiled for; the band pipeline of
 // gxy_render may ask for fewer so that the kernels of several bands share the SMs from the start)
 static unsigned fused_blocks_per_sm() {
-  unsigned b = 8u;
-  if (const char *e = getenv("GXY_FUSED_BLOCKS_PER_SM")) b = (unsigned)std::max(1, std::min(8, atoi(e)));
+  unsigned b = (unsigned)GXY_MIN_BLOCKS;
+  if (const char *e = getenv("GXY_FUSED_BLOCKS_PER_SM")) b = (unsigned)std::max(1, std::min(GXY_MIN_BLOCKS, atoi(e)));
   return b;
 }
 
@@ -854,8 +864,8 @@ int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLigh
   const unsigned blocks = std::min<unsigned>(needed, (unsigned)sm_count() * fused_blocks_per_sm());
 #define GXY_LAUNCH_P(FT)                                                                                                                 \
   do {                                                                                                                                   \
-    if (peer) primary_trace_kernel<FT, 8, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T, prim_threshold()); \
-    else primary_trace_kernel<FT, 8, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T, prim_threshold());      \
+    if (peer) primary_trace_kernel<FT, GXY_MIN_BLOCKS, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T, prim_threshold()); \
+    else primary_trace_kernel<FT, GXY_MIN_BLOCKS, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T, prim_threshold());      \
   } while (0)
   switch (fetch_threshold("GXY_FETCH_P")) {
     case 4: GXY_LAUNCH_P(4); break;
@@ -885,10 +895,10 @@ int launch_fused_secondary(const SceneParams &P, const DevLights &L, int w, int 
 #define GXY_LAUNCH_S(FT)                                                                                                              \
   do {                                                                                                                                \
     if (peer)                                                                                                                         \
-      fused_secondary_kernel<FT, 8, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, L, w, h, nsec, reinterpret_cast<float4 *>(fb), hits, spill, \
+      fused_secondary_kernel<FT, GXY_MIN_BLOCKS, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, L, w, h, nsec, reinterpret_cast<float4 *>(fb), hits, spill, \
                                                                                 spill_cap, q, epsilon, anyhit ? 1 : 0, T, parity_out, prim_threshold());     \
     else                                                                                                                              \
-      fused_secondary_kernel<FT, 8, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, L, w, h, nsec, reinterpret_cast<float4 *>(fb), hits, spill, \
+      fused_secondary_kernel<FT, GXY_MIN_BLOCKS, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, L, w, h, nsec, reinterpret_cast<float4 *>(fb), hits, spill, \
                                                                                  spill_cap, q, epsilon, anyhit ? 1 : 0, T, parity_out, prim_threshold());    \
   } while (0)
   switch (fetch_threshold("GXY_FETCH_S")) {
@@ -908,7 +918,7 @@ int launch_inbox_wave(const SceneParams &P, const DevLights &L, const PeerTable 
   (void)h;
   const unsigned bps = blocks_per_sm > 0 ? (unsigned)std::min(8, blocks_per_sm) : 8u;
   const unsigned blocks = (unsigned)sm_count() * bps;
-  inbox_trace_kernel<12, 8><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, T, parity_in, w, reinterpret_cast<float4 *>(fb), raw, raw_stride, q,
+  inbox_trace_kernel<12, GXY_MIN_BLOCKS><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, T, parity_in, w, reinterpret_cast<float4 *>(fb), raw, raw_stride, q,
                                                                    anyhit ? 1 : 0, prim_threshold());
   gxy_timeline_mark("inbox", st);
   const float4 *inbox = reinterpret_cast<const float4 *>(T.base[T.rank] + T.off_inbox[parity_in]);

@@ -93,6 +93,9 @@ def lib():
         L.gxy_vis_add_pathlines.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(TransferFunction)]
         L.gxy_render_progressive.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(Camera), C.POINTER(Lighting), C.c_int, C.c_int, C.c_float,
                                              C.c_int, C.POINTER(Stats)]
+        L.gxy_render_progressive_submit.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(Camera), C.POINTER(Lighting), C.c_int, C.c_int, C.c_float,
+                                                    C.c_int, C.c_int]
+        L.gxy_render_progressive_wait.argtypes = [C.c_int, C.POINTER(vp), C.c_int, C.POINTER(Stats), ip]
         L.gxy_progressive_download_rgba32f.argtypes = [vp, fp]
         L.gxy_progressive_download_rgba8.argtypes = [vp, C.POINTER(C.c_ubyte)]
         L.gxy_progressive_reset.argtypes = [vp]
@@ -470,6 +473,23 @@ def render_progressive(parts, camera, lighting, w, h, frame, epsilon=0.001):
     fb = np.empty((h, w, 4), np.float32)
     check(lib().gxy_progressive_download_rgba32f(parts[0].h, _f(fb)))
     return fb, st.as_dict()
+
+
+def render_progressive_submit(parts, camera, lighting, w, h, frame, slot, epsilon=0.001):
+    """frame `frame` of the interactive path onto frame slot `slot` (gxy_render_progressive_submit)"""
+    arr = (C.c_void_p * len(parts))(*[p.h for p in parts])
+    cam, L = make_camera(camera), make_lighting(lighting)
+    check(lib().gxy_render_progressive_submit(len(parts), arr, C.byref(cam), C.byref(L), w, h, epsilon, frame, slot))
+
+
+def render_progressive_wait(parts, w, h, slot):
+    """-> (displayed image float32 (h,w,4) y-up, stats, merged: False if the frame was superseded while in flight and dropped)"""
+    arr = (C.c_void_p * len(parts))(*[p.h for p in parts])
+    st, merged = Stats(), C.c_int()
+    check(lib().gxy_render_progressive_wait(len(parts), arr, slot, C.byref(st), C.byref(merged)))
+    fb = np.empty((h, w, 4), np.float32)
+    check(lib().gxy_progressive_download_rgba32f(parts[0].h, _f(fb)))
+    return fb, st.as_dict(), bool(merged.value)
 
 
 def progressive_reset(part):

@@ -232,6 +232,12 @@ int  gxy_intersect(gxy_vis *, int n, const float *org3, const float *dir3, const
  * One process; parts as for gxy_render. */
 int  gxy_render_progressive(int nparts, gxy_vis *const *parts, const gxy_camera *, const gxy_lighting *, int w, int h,
                             float epsilon, int frame, gxy_stats *stats);
+/* The same with frames in flight: frame `frame` goes onto frame slot `slot` (see gxy_render_submit) and is merged into the displayed
+ * image when it is waited for; *merged = 0 if a newer frame was merged while this one was in flight (it is dropped, as AddLocalPixels
+ * drops the pixels of a superseded frame, :138-152).  Slots may be waited for in any order. */
+int  gxy_render_progressive_submit(int nparts, gxy_vis *const *parts, const gxy_camera *, const gxy_lighting *, int w, int h,
+                                   float epsilon, int frame, int slot);
+int  gxy_render_progressive_wait(int nparts, gxy_vis *const *parts, int slot, gxy_stats *stats, int *merged);
 /* the displayed image: float RGBA, y up (w*h*4 floats) / RGBA8 rows top-down as ColorImageWriter writes them */
 int  gxy_progressive_download_rgba32f(gxy_vis *, float *fb);
 int  gxy_progressive_download_rgba8(gxy_vis *, unsigned char *rgba);

@@ -1,6 +1,5 @@
 """-m gpu: the interactive / asynchronous frame path on the CUDA path against the oracle's literal
-frame-stamped accumulation.  (Named test_zzz_* so that it runs after every other GPU file: it was written after the
-round's GPU minutes were spent and has not run on a device yet.)"""
+frame-stamped accumulation.  (Green on the B200 since round 1's driver run; round 2 added the frames-in-flight form.)"""
 import numpy as np
 import pytest
 
@@ -40,6 +39,33 @@ def test_gpu_progressive_frames_match_oracle(gpu, oracle, nparts):
     fb_g, _ = gpu.render_progressive(g, CAM_A, L, W // 2, H // 2, 0)
     fb_o, _ = oracle.render(o, CAM_A, L, W // 2, H // 2)
     assert util.fb_fraction(fb_g, fb_o, 1.0 / 255) >= 0.999
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nparts", [1, 2])
+def test_gpu_progressive_frames_in_flight(gpu, oracle, nparts):
+    """frames 1, 2, 3 are submitted to three frame slots before the first wait (gxyviewer keeps rendering while frames are on their
+    way) and waited for in the order 1, 3, 2: frame 2 arrives after frame 3 was merged, so it is stale and dropped -- the oracle,
+    which applies the reference's rule per contribution (Rendering.cpp:104-153), does the same with that arrival order."""
+    g, vis = scene(gpu, nparts)
+    o, _ = scene(oracle, nparts)
+    L = vis["lighting"]
+    r = oracle.ProgressiveRendering(W, H)
+    gpu.progressive_reset(g[0])
+    frames = [(1, CAM_A, 0), (2, CAM_B, 1), (3, CAM_A, 2)]
+    for frame, cam, slot in frames:
+        gpu.render_progressive_submit(g, cam, L, W, H, frame, slot)
+    for k, expect_merged in ((0, True), (2, True), (1, False)):
+        frame, cam, slot = frames[k]
+        fb_o, _ = r.render(o, cam, L, frame)
+        fb_g, st_g, merged = gpu.render_progressive_wait(g, W, H, slot)
+        assert merged == expect_merged, (frame, merged)
+        assert util.fb_fraction(fb_g, fb_o, 1.0 / 255) >= 0.999, frame
+    # the same frame number again adds (ACCUMULATE_PIXEL), also through a slot
+    gpu.render_progressive_submit(g, CAM_A, L, W, H, 3, 0)
+    fb_o, _ = r.render(o, CAM_A, L, 3)
+    fb_g, _, merged = gpu.render_progressive_wait(g, W, H, 0)
+    assert merged and util.fb_fraction(fb_g, fb_o, 1.0 / 255) >= 0.999
 
 
 @pytest.mark.gpu
