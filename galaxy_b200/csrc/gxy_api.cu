@@ -274,6 +274,8 @@ struct Flight {
   gxy_lighting lights;
   DevLights L;
   gxy_stats S;
+  bool graph_frame = false;        // this frame was submitted as one CUDA graph launch (GXY_GRAPH=1, flight_submit_peer)
+  cudaGraphExec_t gexec = nullptr;
   int prog_frame = 0;     // gxy_render_progressive_submit: the frame number and camera of the frame on this slot
   gxy_camera prog_cam;
 };
@@ -1555,6 +1557,7 @@ static void flight_destroy(gxy_vis *v, Flight *F) {
     if (F->ev_join[k]) cudaEventDestroy(F->ev_join[k]);
   }
   for (auto &e : F->trace_ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  if (F->gexec) cudaGraphExecDestroy(F->gexec);
   if (F->ev_fork) cudaEventDestroy(F->ev_fork);
   if (F->ev0) cudaEventDestroy(F->ev0);
   if (F->ev1) cudaEventDestroy(F->ev1);
@@ -1576,6 +1579,7 @@ static int flight_lane(Flight &F, int k, cudaStream_t *out) {
   return 0;
 }
 static int flight_trace_begin(Flight &F, cudaStream_t st) {
+  if (F.graph_frame) return 0;  // (no timing events inside a captured frame: gxy_stats::trace_ms is 0 for it)
   if (F.n_trace_ev == F.trace_ev.size()) {
     cudaEvent_t ta, tb;
     GXY_CUDA(cudaEventCreate(&ta));
@@ -1586,6 +1590,7 @@ static int flight_trace_begin(Flight &F, cudaStream_t st) {
   return 0;
 }
 static int flight_trace_end(Flight &F, cudaStream_t st) {
+  if (F.graph_frame) return 0;
   GXY_CUDA(cudaEventRecord(F.trace_ev[F.n_trace_ev].second, st));
   F.n_trace_ev++;
   return 0;
@@ -1745,7 +1750,6 @@ static int peer_finish(gxy_vis *v, Flight &F) {
   if (launch_wave_epilogue(T, q, ++F.arena.epoch, -1, false, F.err.p, st)) return 1;
   gxy_timeline_mark("barrier_end", st);
   F.S.kernel_launches += 2;
-  GXY_CUDA(cudaEventRecord(F.ev1, st));
   return 0;
 }
 
@@ -1792,7 +1796,7 @@ static bool peer_tile_rect(const DevCamera &C, const float lo[3], const float hi
   return true;
 }
 
-static int flight_submit_peer(gxy_vis *v, Flight &F, const DevCamera &C, int w, int h, float epsilon) {
+static int flight_enqueue_peer(gxy_vis *v, Flight &F, const DevCamera &C, int w, int h, float epsilon) {
   gxy_context *c = v->ctx;
   PeerArena &A = F.arena;
   const PeerTable &T = A.T;
@@ -1801,16 +1805,12 @@ static int flight_submit_peer(gxy_vis *v, Flight &F, const DevCamera &C, int w, 
   gxy_stats &S = F.S;
   SceneParams P = v->P;
   P.error_flag = F.err.p;
-  if (F.hits.reserve(npix, false, st) || F.fq.reserve(sizeof(FusedQueues) / 8) || F.rawhits.reserve((size_t)6 * npix) ||
-      F.next.reserve(npix, false, st) || F.cur.reserve(64, false, st) || F.proxies.reserve(sizeof(PartProxy) * (size_t)c->nranks))
-    return 1;
   float *fb = reinterpret_cast<float *>(A.base + T.off_fb);
   FusedQueues *q = reinterpret_cast<FusedQueues *>(F.fq.p);
   F.n_bands = 1;
   F.fb_result = c->rank == 0 ? reinterpret_cast<float *>(A.base + T.off_final) : fb;
   F.n_trace_ev = 0;
   F.peer_k = 0;
-  GXY_CUDA(cudaEventRecord(F.ev0, st));
   gxy_timeline_mark("start", st);
   GXY_CUDA(cudaMemsetAsync(fb, 0, sizeof(float) * 4 * npix, st));
   GXY_CUDA(cudaMemsetAsync(q, 0, sizeof(FusedQueues), st));
@@ -1846,6 +1846,55 @@ static int flight_submit_peer(gxy_vis *v, Flight &F, const DevCamera &C, int w, 
   return peer_finish(v, F);
 }
 
+// Submission of a peer frame.  Direct: ~75 runtime calls (37 launches on two streams, their fork/join events, memsets, the tail
+// copies).  GXY_GRAPH=1: the same calls are CAPTURED into a CUDA graph, the flight's executable graph is updated in place
+// (cudaGraphExecUpdate: same topology, new kernel parameters -- camera, tile rectangle, barrier epochs) and launched with one call;
+// the host then spends its time on the next frame's capture instead of on driver submissions.  The first peer frame of a process
+// always goes direct (constant tables are uploaded and streams created on first use, which a capture must not contain).
+static bool g_peer_warm = false;
+static int flight_submit_peer(gxy_vis *v, Flight &F, const DevCamera &C, int w, int h, float epsilon) {
+  gxy_context *c = v->ctx;
+  cudaStream_t st = F.st;
+  const int npix = w * h;
+  if (F.hits.reserve(npix, false, st) || F.fq.reserve(sizeof(FusedQueues) / 8) || F.rawhits.reserve((size_t)6 * npix) ||
+      F.next.reserve(npix, false, st) || F.cur.reserve(64, false, st) || F.proxies.reserve(sizeof(PartProxy) * (size_t)c->nranks))
+    return 1;
+  cudaStream_t s2;
+  if (flight_lane(F, 1, &s2)) return 1;
+  const bool graph = g_peer_warm && !timeline_on() && getenv("GXY_GRAPH") && atoi(getenv("GXY_GRAPH")) != 0;
+  F.graph_frame = graph;
+  GXY_CUDA(cudaEventRecord(F.ev0, st));
+  if (!graph) {
+    if (flight_enqueue_peer(v, F, C, w, h, epsilon)) return 1;
+    g_peer_warm = true;
+  } else {
+    GXY_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = flight_enqueue_peer(v, F, C, w, h, epsilon);
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &g);
+    if (rc || ce != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      if (!rc) gxy_set_error("stream capture of the frame failed: %s", cudaGetErrorString(ce));
+      cudaGetLastError();
+      return 1;
+    }
+    bool ok = false;
+    if (F.gexec) {
+      cudaGraphExecUpdateResultInfo info;
+      ok = cudaGraphExecUpdate(F.gexec, g, &info) == cudaSuccess;
+      if (!ok) { cudaGetLastError(); cudaGraphExecDestroy(F.gexec); F.gexec = nullptr; }
+    }
+    if (!ok) {
+      const cudaError_t ie = cudaGraphInstantiate(&F.gexec, g, 0);
+      if (ie != cudaSuccess) { cudaGraphDestroy(g); F.gexec = nullptr; gxy_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); return 1; }
+    }
+    cudaGraphDestroy(g);
+    GXY_CUDA(cudaGraphLaunch(F.gexec, st));
+  }
+  GXY_CUDA(cudaEventRecord(F.ev1, st));
+  return 0;
+}
+
 static int flight_wait(gxy_vis *v, Flight &F, gxy_stats *stats) {
   gxy_context *c = v->ctx;
   GXY_CHECK(F.pending, "no frame was submitted to this slot");
@@ -1860,7 +1909,9 @@ static int flight_wait(gxy_vis *v, Flight &F, gxy_stats *stats) {
       const bool peer_overlap = !(getenv("GXY_PEER_OVERLAP") && atoi(getenv("GXY_PEER_OVERLAP")) == 0);
       while (F.h_tail->q[0].global_pending != 0u && F.h_tail->error == 0) {
         GXY_CHECK(F.peer_k < 4096, "peer wave loop does not terminate (%u units of work in flight)", F.h_tail->q[0].global_pending);
+        F.graph_frame = false;
         if (peer_wave(v, F, P, F.w, F.h, F.n_sec_per_hit > 0, peer_overlap) || peer_finish(v, F)) return 1;
+        GXY_CUDA(cudaEventRecord(F.ev1, F.st));
         GXY_CUDA(cudaEventSynchronize(F.ev1));
       }
       err = F.h_tail->error;

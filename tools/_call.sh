@@ -1,3 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_threads_devlists.py tests/test_zzz_gpu_progressive.py tests/test_gpu_flights.py -m gpu -x -q > gpurun_out/r2g_tests.log 2>&1; echo "tests rc $?" >> gpurun_out/r2g_tests.log
-timeout 900 python bench.py --workload c3 --volume-n 2048 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2g_bench_c3_2048.json 2> gpurun_out/r2g_bench_c3_2048.err
-FLIGHT_DEPTHS=4 FLIGHT_ENVS="GXY_PRIM_T=1" timeout 300 python tools/flight_sweep.py 1 24 > gpurun_out/r2g_sweep.log 2>&1
+for t in 1 8; do GXY_LIB=$PWD/galaxy_b200/libgxy_b200_counters.so timeout 300 python tools/prof_frame.py $t 4 > gpurun_out/r2i_counters_tess$t.log 2>&1; done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"primary_trace_kernel|fused_secondary_kernel" -s 6 -c 2 -o gpurun_out/r2i_trace python tools/prof_frame.py 1 5 > gpurun_out/r2i_ncu.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2i_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r2i_launches_bench.log 2>&1
+ls -la gpurun_out/ > gpurun_out/r2i_ls.txt

@@ -41,14 +41,24 @@ def barrier():
     torch.cuda.synchronize()
 
 
+HOST = {"submit_s": 0.0, "n": 0}
+
+
+def submit(slot):
+    t0 = time.perf_counter()
+    gpu.render_submit([part], cam, vis["lighting"], W, H, 0.001, slot)
+    HOST["submit_s"] += time.perf_counter() - t0
+    HOST["n"] += 1
+
+
 def pipeline(n, depth):
     out = []
     for k in range(min(depth, n)):
-        gpu.render_submit([part], cam, vis["lighting"], W, H, 0.001, k % depth)
+        submit(k % depth)
     for k in range(n):
         out.append(gpu.render_wait([part], k % depth))
         if k + depth < n:
-            gpu.render_submit([part], cam, vis["lighting"], W, H, 0.001, k % depth)
+            submit(k % depth)
     return out
 
 
@@ -60,6 +70,7 @@ for env in envs:
         os.environ[k] = v
     for depth in depths:
         pipeline(depth + 3, depth)
+        HOST["submit_s"], HOST["n"] = 0.0, 0
         res = []
         for rep in range(3):
             barrier()
@@ -87,7 +98,7 @@ for env in envs:
             best = min(res)
             print(json.dumps({"world": world, "env": env, "depth": depth, "ms_per_frame_device": round(best[0], 4), "ms_per_frame_wall": round(best[1], 4),
                               "frame_latency_ms": round(best[2], 4), "Mrays/s": round(best[3] / best[0] / 1e3, 1), "rays": int(best[3]),
-                              "dequeued": int(best[4]), "dequeued_per_rank": best[5], "all": [round(r[0], 4) for r in res]}), flush=True)
+                              "dequeued": int(best[4]), "dequeued_per_rank": best[5], "host_submit_ms_per_frame": round(HOST["submit_s"] / max(1, HOST["n"]) * 1e3, 4), "all": [round(r[0], 4) for r in res]}), flush=True)
     for k, v in sets:
         os.environ.pop(k, None)
 if world > 1:
