@@ -343,7 +343,7 @@ def main():
                          "pl: PathLines (800 000 round Bezier segments), primary + shadow")
     ap.add_argument("--volume-n", type=int, default=1024, help="c3/c4: voxels per axis of the synthetic volume")
     ap.add_argument("--in-flight", type=int, default=None,
-                    help="frames of the RenderingSet kept in flight (gxy_render_submit/wait); default 4 for the geometry workloads, 1 otherwise")
+                    help="frames of the RenderingSet kept in flight (gxy_render_submit/wait); default 8 for the geometry workloads, 1 otherwise")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -436,7 +436,8 @@ def main():
     # frames in flight: a RenderingSet of `depth` frames is kept on the device at any time (the reference keeps every Rendering
     # of a set in flight, gxywriter.cpp:196-264).  Every step still delivers its own complete image; steps are counted as they
     # complete.  Geometry workloads only: the volume / PathLines schedules are synchronous per frame (depth 1).
-    depth = args.in_flight if args.in_flight is not None else (4 if not (volume or pathlines) else 1)
+    # measured (tools/flight_sweep.py, ms per frame at 1/2/4/8 GPUs): 4 in flight 1.10/0.85/0.63/0.57, 8 in flight 1.10/0.81/0.52/0.42
+    depth = args.in_flight if args.in_flight is not None else (8 if not (volume or pathlines) else 1)
     depth = max(1, min(depth, gpu.max_slots(), max(1, args.steps)))
     use_flush = depth == 1   # depth 1: 256 MB L2 flush between frames; depth > 1: the frames' inputs are >> L2 (config.timing)
 

@@ -293,6 +293,16 @@ __global__ void __launch_bounds__(256) proxy_gather_kernel(const __grid_constant
   }
 }
 
+// A persistent trace launch is sized for the worst case (every pixel hits, every secondary ray exists); the real length of its queue
+// is only known on the device, and it is final when the kernel starts.  CTAs that the queue cannot give rays_per_thread rays per thread
+// leave at once, so a launch with little work holds few SM slots and the launches of OTHER frames in flight run beside it instead of
+// behind it: across ranks a wave often carries a few ten thousand rays, and 1184 resident CTAs of such a launch would block the SMs for
+// the whole latency-bound lifetime of those rays.  rays_per_thread = 0: every CTA stays (the behaviour before).
+__device__ __forceinline__ bool surplus_cta(unsigned n_queue, int rays_per_thread) {
+  return rays_per_thread > 0 && blockIdx.x > 0u &&
+         (unsigned long long)blockIdx.x * (unsigned long long)(GXY_TRACE_THREADS * rays_per_thread) >= (unsigned long long)n_queue;
+}
+
 // One iteration of a persistent trace warp (all 32 lanes, converged): a node step for every lane that has no primitives pending, then
 // the cooperative primitive passes -- but only once prim_t lanes hold a primitive group, or no lane is left that could do a node
 // step.  A pass costs the whole warp ~330 instructions whether it serves one owner or eight; with a node step per lane and
@@ -322,13 +332,14 @@ __device__ __forceinline__ void trace_iteration(const SceneParams &P, const RayC
 template <int FETCH_T, int MIN_BLOCKS, bool PEER>
 __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
     primary_trace_kernel(const __grid_constant__ SceneParams P, Rays R, unsigned *__restrict__ raw, unsigned raw_stride, Rays spill,
-                         unsigned spill_cap, FusedQueues *__restrict__ q, const __grid_constant__ PeerTable T, int prim_t) {
+                         unsigned spill_cap, FusedQueues *__restrict__ q, const __grid_constant__ PeerTable T, int prim_t, int rays_per_thread) {
   __shared__ uint2 stack[GXY_STACK_SMEM * GXY_TRACE_THREADS];
   __shared__ unsigned char owner_of[GXY_TRACE_THREADS / 32][8];
   uint2 lstack[GXY_STACK_LOCAL];
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const unsigned n_queue = q->n_primary32;
+  if (surplus_cta(n_queue, rays_per_thread)) return;
   RayCtx rc;
   TravState st;
   PendingRay pr;
@@ -510,7 +521,7 @@ template <int FETCH_T, int MIN_BLOCKS, bool PEER>
 __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
     fused_secondary_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevLights L, int w, int h, int nsec,
                            float4 *__restrict__ fb, Rays hits, Rays spill, unsigned spill_cap, FusedQueues *__restrict__ q, float epsilon,
-                           int anyhit_secondary, const __grid_constant__ PeerTable T, int parity_out, int prim_t) {
+                           int anyhit_secondary, const __grid_constant__ PeerTable T, int parity_out, int prim_t, int rays_per_thread) {
   __shared__ uint2 stack[GXY_STACK_SMEM * GXY_TRACE_THREADS];
   __shared__ unsigned char owner_of[GXY_TRACE_THREADS / 32][8];
   __shared__ float ao_tab[3][256];  // divergent indices: shared memory, not the constant cache
@@ -527,6 +538,7 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
   if (n_hits == 0u) return;
   const unsigned long long total64 = (unsigned long long)n_hits * (unsigned)nsec;
   const unsigned n_queue = total64 > 0xfffffff0ull ? 0xfffffff0u : (unsigned)total64;
+  if (surplus_cta(n_queue, rays_per_thread)) return;
   RayCtx rc;
   TravState st;
   PendingRay pr;
@@ -622,14 +634,14 @@ template <int FETCH_T, int MIN_BLOCKS>
 __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
     inbox_trace_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ PeerTable T, int parity_in, int w,
                        float4 *__restrict__ fb, unsigned *__restrict__ raw, unsigned raw_stride, FusedQueues *__restrict__ q,
-                       int anyhit_secondary, int prim_t) {
+                       int anyhit_secondary, int prim_t, int rays_per_thread) {
   __shared__ uint2 stack[GXY_STACK_SMEM * GXY_TRACE_THREADS];
   __shared__ unsigned char owner_of[GXY_TRACE_THREADS / 32][8];
   uint2 lstack[GXY_STACK_LOCAL];
   const float4 *__restrict__ inbox = peer_inbox(T, T.rank, parity_in);
   const unsigned n_in = peer_ctrl(T, T.rank)->inbox_count[parity_in];
   const unsigned n_queue = n_in < T.inbox_cap ? n_in : T.inbox_cap;
-  if (n_queue == 0u) return;
+  if (n_queue == 0u || surplus_cta(n_queue, rays_per_thread)) return;
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   RayCtx rc;
@@ -833,6 +845,13 @@ static int prim_threshold() {
   return t;
 }
 
+// rays a queue must hold per thread of a CTA for that CTA to stay (surplus_cta); 0 = off
+static int rays_per_thread() {
+  int r = 4;
+  if (const char *e = getenv("GXY_RAYS_PER_THREAD")) r = std::max(0, std::min(64, atoi(e)));
+  return r;
+}
+
 static int fetch_threshold(const char *env) {
   int ft = 12;  // measured optimum on the 100M-triangle scene (tools/trace_sweep.py, GXY_FETCH_SWEEP)
   if (const char *e = getenv(env)) ft = atoi(e);
@@ -864,8 +883,8 @@ int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLigh
   const unsigned blocks = std::min<unsigned>(needed, (unsigned)sm_count() * fused_blocks_per_sm());
 #define GXY_LAUNCH_P(FT)                                                                                                                 \
   do {                                                                                                                                   \
-    if (peer) primary_trace_kernel<FT, GXY_MIN_BLOCKS, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T, prim_threshold()); \
-    else primary_trace_kernel<FT, GXY_MIN_BLOCKS, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T, prim_threshold());      \
+    if (peer) primary_trace_kernel<FT, GXY_MIN_BLOCKS, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T, prim_threshold(), rays_per_thread()); \
+    else primary_trace_kernel<FT, GXY_MIN_BLOCKS, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T, prim_threshold(), rays_per_thread());      \
   } while (0)
   switch (fetch_threshold("GXY_FETCH_P")) {
     case 4: GXY_LAUNCH_P(4); break;
@@ -896,10 +915,10 @@ int launch_fused_secondary(const SceneParams &P, const DevLights &L, int w, int 
   do {                                                                                                                                \
     if (peer)                                                                                                                         \
       fused_secondary_kernel<FT, GXY_MIN_BLOCKS, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, L, w, h, nsec, reinterpret_cast<float4 *>(fb), hits, spill, \
-                                                                                spill_cap, q, epsilon, anyhit ? 1 : 0, T, parity_out, prim_threshold());     \
+                                                                                spill_cap, q, epsilon, anyhit ? 1 : 0, T, parity_out, prim_threshold(), rays_per_thread());     \
     else                                                                                                                              \
       fused_secondary_kernel<FT, GXY_MIN_BLOCKS, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, L, w, h, nsec, reinterpret_cast<float4 *>(fb), hits, spill, \
-                                                                                 spill_cap, q, epsilon, anyhit ? 1 : 0, T, parity_out, prim_threshold());    \
+                                                                                 spill_cap, q, epsilon, anyhit ? 1 : 0, T, parity_out, prim_threshold(), rays_per_thread());    \
   } while (0)
   switch (fetch_threshold("GXY_FETCH_S")) {
     case 4: GXY_LAUNCH_S(4); break;
@@ -919,7 +938,7 @@ int launch_inbox_wave(const SceneParams &P, const DevLights &L, const PeerTable 
   const unsigned bps = blocks_per_sm > 0 ? (unsigned)std::min(8, blocks_per_sm) : 8u;
   const unsigned blocks = (unsigned)sm_count() * bps;
   inbox_trace_kernel<12, GXY_MIN_BLOCKS><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, T, parity_in, w, reinterpret_cast<float4 *>(fb), raw, raw_stride, q,
-                                                                   anyhit ? 1 : 0, prim_threshold());
+                                                                   anyhit ? 1 : 0, prim_threshold(), rays_per_thread());
   gxy_timeline_mark("inbox", st);
   const float4 *inbox = reinterpret_cast<const float4 *>(T.base[T.rank] + T.off_inbox[parity_in]);
   shade_hits_kernel<true><<<(unsigned)sm_count() * std::min(4u, bps), 256, 0, st>>>(P, L, hits, inbox, raw, raw_stride, w, reinterpret_cast<float4 *>(fb),

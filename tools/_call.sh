@@ -1,4 +1,3 @@
-for t in 1 8; do GXY_LIB=$PWD/galaxy_b200/libgxy_b200_counters.so timeout 300 python tools/prof_frame.py $t 4 > gpurun_out/r2i_counters_tess$t.log 2>&1; done
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"primary_trace_kernel|fused_secondary_kernel" -s 6 -c 2 -o gpurun_out/r2i_trace python tools/prof_frame.py 1 5 > gpurun_out/r2i_ncu.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2i_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r2i_launches_bench.log 2>&1
-ls -la gpurun_out/ > gpurun_out/r2i_ls.txt
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1"
+FLIGHT_DEPTHS=8,16 FLIGHT_ENVS="GXY_RAYS_PER_THREAD=0;GXY_RAYS_PER_THREAD=2;GXY_RAYS_PER_THREAD=4;GXY_RAYS_PER_THREAD=8;GXY_RAYS_PER_THREAD=16" timeout 600 $TR --master-port 29513 tools/flight_sweep.py 1 32 > gpurun_out/r2l_sweep4.log 2>&1
+timeout 600 $TR --master-port 29511 tools/mp_parity.py > gpurun_out/r2l_parity4.log 2>&1; echo "parity rc $?" >> gpurun_out/r2l_parity4.log
