@@ -1242,8 +1242,11 @@ int gxy_sample(int nparts, gxy_vis *const *parts, const gxy_camera *cam, int w, 
   const int npix = w * h;
   gxy_stats S;
   memset(&S, 0, sizeof S);
+  // all passes of a ray through a partition inside one launch (default; measured on one B200, IsoSampler on eightBalls 128^3, 1080p:
+  // 10 waves x 5 kernels with a host synchronisation each 2.87 ms -> 1 wave 1.29 ms, 1.69 G ray passes/s; same sample sets and pass
+  // counts, tests/test_sampler.py).  GXY_SAMPLER_LOOP=0: one launch per crossing
   const char *le = getenv("GXY_SAMPLER_LOOP");
-  const bool loop_mode = le && atoi(le) != 0;
+  const bool loop_mode = !(le && atoi(le) == 0);
   gxy_context *ctx0 = parts[0]->ctx;
   struct EventPair {  // destroyed on every return path
     cudaEvent_t a = nullptr, b = nullptr;
@@ -2011,9 +2014,9 @@ static int render_sync(int nparts, gxy_vis *const *parts, const gxy_camera *cam,
   bool fused = true;
   // (decided from the operator list, which is the same on every rank, not from the clipped primitive count)
   for (int p = 0; p < nparts; p++) fused = fused && parts[p]->P.n_volvis == 0 && !parts[p]->geoms.empty();
-  // PathLines operators: the curve test lives in the list-path kernels only (trace_kernel<.., CURVES>)
-  for (int p = 0; p < nparts; p++)
-    for (const GeomOp &g : parts[p]->geoms) fused = fused && g.kind != 2;
+  if (getenv("GXY_FUSED_CURVES") && atoi(getenv("GXY_FUSED_CURVES")) == 0)  // PathLines on the list-path kernels, as in round 1
+    for (int p = 0; p < nparts; p++)
+      for (const GeomOp &g : parts[p]->geoms) fused = fused && g.kind != 2;
   if (const char *e = getenv("GXY_FUSED")) fused = fused && atoi(e) != 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_events;
   for (int p = 0; p < nparts; p++) {
@@ -2383,8 +2386,10 @@ static int render_sync(int nparts, gxy_vis *const *parts, const gxy_camera *cam,
 static int frame_kind(int nparts, gxy_vis *const *parts) {
   bool fused = true;
   for (int p = 0; p < nparts; p++) fused = fused && parts[p]->P.n_volvis == 0 && !parts[p]->geoms.empty();
-  for (int p = 0; p < nparts; p++)
-    for (const GeomOp &g : parts[p]->geoms) fused = fused && g.kind != 2;  // PathLines: list-path kernels only
+  // PathLines take the CURVES instantiations of the frame kernels (GXY_FUSED_CURVES=0: the list-path kernels, as in round 1)
+  if (getenv("GXY_FUSED_CURVES") && atoi(getenv("GXY_FUSED_CURVES")) == 0)
+    for (int p = 0; p < nparts; p++)
+      for (const GeomOp &g : parts[p]->geoms) fused = fused && g.kind != 2;
   if (const char *e = getenv("GXY_FUSED")) fused = fused && atoi(e) != 0;
   if (!fused) return 0;
   if (parts[0]->ctx->comm) {

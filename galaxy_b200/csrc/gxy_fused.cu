@@ -35,6 +35,9 @@ namespace gxy {
 #ifndef GXY_MIN_BLOCKS
 #define GXY_MIN_BLOCKS 8      // __launch_bounds__(128, N): 8 -> 64 registers; 10 -> 48; 12 -> 40 (spills)
 #endif
+#ifndef GXY_CURVE_BLOCKS
+#define GXY_CURVE_BLOCKS 3    // resident CTAs of the CURVES instantiations (PathLines: the round-Bezier test needs ~150 registers)
+#endif
 #ifndef GXY_CULL_LEVELS
 #define GXY_CULL_LEVELS 3  // measured on C5: 1 -> 1.449 ms, 2 -> 1.449, 3 -> 1.416, 4 -> 1.425 per frame
 #endif
@@ -311,6 +314,7 @@ __device__ __forceinline__ bool surplus_cta(unsigned n_queue, int rays_per_threa
 // 6: 1.155, 8: 1.180, 12: 1.224 -- the lanes that wait lose more node steps than the fuller passes save, so the default stays 1
 // (GXY_PRIM_T).  Lanes that wait keep their node group; the order in which primitives are tested never decides a result (smallest t,
 // ties on the lowest ids), and the parity tests pass with prim_t = 4.
+template <bool CURVES>
 __device__ __forceinline__ void trace_iteration(const SceneParams &P, const RayCtx &rc, TravState &st, bool &trav, const bool anyhit,
                                                 uint2 *__restrict__ stack, uint2 *__restrict__ lstack, unsigned char *owner_slot,
                                                 const unsigned lane, const unsigned lt_mask, const int prim_t) {
@@ -321,7 +325,7 @@ __device__ __forceinline__ void trace_iteration(const SceneParams &P, const RayC
     // (second ballot: lanes that will still be able to take a node step next iteration without a primitive pass)
     if (prim_t <= 1 || __popc(owners) >= prim_t ||
         __ballot_sync(FULLMASK, trav && st.tg.y == 0u && (st.ng.y > 0x00ffffffu || st.sp > 0)) == 0u)
-      coop_prim_passes(P, rc, st, trav, anyhit, owner_slot, lane, lt_mask);
+      coop_prim_passes<CURVES>(P, rc, st, trav, anyhit, owner_slot, lane, lt_mask);
   }
   if (trav) trav = trav_advance(st, stack, lstack);
 }
@@ -329,8 +333,8 @@ __device__ __forceinline__ void trace_iteration(const SceneParams &P, const RayC
 // Trace of the generated primaries (persistent warps, dynamic fetch, cooperative primitive tests).
 // A surface hit leaves a 6-word raw record (ray, t, u, v, ids, record) for shade_hits_kernel; a miss is
 // classified here: TERMINATED (adds nothing: its colour is 0) or spilled towards a neighbour.
-template <int FETCH_T, int MIN_BLOCKS, bool PEER>
-__global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
+template <int FETCH_T, int MIN_BLOCKS, bool PEER, bool CURVES = false>
+__global__ void __launch_bounds__(GXY_TRACE_THREADS, CURVES ? GXY_CURVE_BLOCKS : MIN_BLOCKS)
     primary_trace_kernel(const __grid_constant__ SceneParams P, Rays R, unsigned *__restrict__ raw, unsigned raw_stride, Rays spill,
                          unsigned spill_cap, FusedQueues *__restrict__ q, const __grid_constant__ PeerTable T, int prim_t, int rays_per_thread) {
   __shared__ uint2 stack[GXY_STACK_SMEM * GXY_TRACE_THREADS];
@@ -415,7 +419,7 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
       exhausted = exhausted || __any_sync(FULLMASK, ex_local);
       if (exhausted && __ballot_sync(FULLMASK, pr.ray >= 0) == 0u) break;
     }
-    trace_iteration(P, rc, st, trav, false, stack, lstack, owner_of[warp], lane, lt_mask, prim_t);
+    trace_iteration<CURVES>(P, rc, st, trav, false, stack, lstack, owner_of[warp], lane, lt_mask, prim_t);
   }
 }
 
@@ -423,7 +427,7 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
 // thread per hit (full SIMD efficiency, unlike a finish inside the persistent kernel), and the record the
 // secondary kernel generates AO/shadow rays from.  The traced ray is read from the primary list (AOS = false)
 // or from the 64-byte records of an inbox (AOS = true; the ray's own colour is 0 on this path).
-template <bool AOS>
+template <bool AOS, bool CURVES = false>
 __global__ void __launch_bounds__(256)
     shade_hits_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevLights L, Rays R, const float4 *__restrict__ inbox,
                       const unsigned *__restrict__ raw, unsigned raw_stride, int w, float4 *__restrict__ fb, Rays hits,
@@ -450,16 +454,25 @@ __global__ void __launch_bounds__(256)
     if (rc.dir.y == 0.f) rc.dir.y = 1e-6f;
     if (rc.dir.z == 0.f) rc.dir.z = 1e-6f;
     TravState st;
+    if (CURVES) {
+      // the normal of a curve hit is recomputed by running the segment's test again (trav_fetch_hit<true>): it needs the very
+      // interval the trace used, i.e. the same box clip
+      PendingRay pr0;
+      float t0 = 0.f, t1 = FLT_MAX;
+      if (AOS) { const float4 b = inbox[4 * (size_t)i + 1]; t0 = b.z; t1 = b.w; }
+      else t0 = R.t[i];
+      setup_ray_values(P, 0, true, rc.org, dir0, t0, t1, 0, rc, st, pr0);
+    }
     st.best_t = __uint_as_float(raw[hidx + raw_stride]);
     st.best_u = __uint_as_float(raw[hidx + 2u * raw_stride]);
     st.best_v = __uint_as_float(raw[hidx + 3u * raw_stride]);
     st.best_key = raw[hidx + 4u * raw_stride];
     st.best_rec = raw[hidx + 5u * raw_stride];
     Hit1 h1;
-    trav_fetch_hit(P, rc, st, h1);
+    trav_fetch_hit<CURVES>(P, rc, st, h1);
     float3 col, Ns;
     float opacity;
-    shade_geometry_hit(P, h1, rc.dir, col, opacity, Ns);
+    shade_geometry_hit<CURVES>(P, h1, rc.dir, col, opacity, Ns);
     int term = RAY_SURFACE;
     if (opacity > 0.999f) term |= RAY_OPAQUE;
     HitPoint hp;
@@ -517,8 +530,8 @@ __device__ __forceinline__ SecRay make_secondary(const DevLights &L, const Rays 
   return make_shadow_ray(L, hp, j - L.n_ao, epsilon, o_lit);
 }
 
-template <int FETCH_T, int MIN_BLOCKS, bool PEER>
-__global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
+template <int FETCH_T, int MIN_BLOCKS, bool PEER, bool CURVES = false>
+__global__ void __launch_bounds__(GXY_TRACE_THREADS, CURVES ? GXY_CURVE_BLOCKS : MIN_BLOCKS)
     fused_secondary_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ DevLights L, int w, int h, int nsec,
                            float4 *__restrict__ fb, Rays hits, Rays spill, unsigned spill_cap, FusedQueues *__restrict__ q, float epsilon,
                            int anyhit_secondary, const __grid_constant__ PeerTable T, int parity_out, int prim_t, int rays_per_thread) {
@@ -619,7 +632,7 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
       exhausted = exhausted || __any_sync(FULLMASK, ex_local);
       if (exhausted && __ballot_sync(FULLMASK, pr.ray >= 0) == 0u) break;
     }
-    trace_iteration(P, rc, st, trav, pr.anyhit, stack, lstack, owner_of[warp], lane, lt_mask, prim_t);
+    trace_iteration<CURVES>(P, rc, st, trav, pr.anyhit, stack, lstack, owner_of[warp], lane, lt_mask, prim_t);
   }
 }
 
@@ -630,8 +643,8 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
 // (TraceRays.ispc:377-441, 563-610), then Renderer::Classify (Renderer.cpp:304-454): a PRIMARY hit leaves a
 // raw record for shade_hits_kernel<true>; everything else adds to the framebuffer, is dropped, or is
 // written on into the next partition's inbox[parity_in ^ 1].
-template <int FETCH_T, int MIN_BLOCKS>
-__global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
+template <int FETCH_T, int MIN_BLOCKS, bool CURVES = false>
+__global__ void __launch_bounds__(GXY_TRACE_THREADS, CURVES ? GXY_CURVE_BLOCKS : MIN_BLOCKS)
     inbox_trace_kernel(const __grid_constant__ SceneParams P, const __grid_constant__ PeerTable T, int parity_in, int w,
                        float4 *__restrict__ fb, unsigned *__restrict__ raw, unsigned raw_stride, FusedQueues *__restrict__ q,
                        int anyhit_secondary, int prim_t, int rays_per_thread) {
@@ -725,7 +738,7 @@ __global__ void __launch_bounds__(GXY_TRACE_THREADS, MIN_BLOCKS)
       exhausted = exhausted || __any_sync(FULLMASK, ex_local);
       if (exhausted && __ballot_sync(FULLMASK, pr.ray >= 0) == 0u) break;
     }
-    trace_iteration(P, rc, st, trav, pr.anyhit, stack, lstack, owner_of[warp], lane, lt_mask, prim_t);
+    trace_iteration<CURVES>(P, rc, st, trav, pr.anyhit, stack, lstack, owner_of[warp], lane, lt_mask, prim_t);
   }
 }
 
@@ -880,7 +893,17 @@ int launch_fused_primary(const SceneParams &P, const DevCamera &C, const DevLigh
   else gen_primary_kernel<<<(n_queue + 255) / 256, 256, 0, st>>>(P, C, w, h, tiles_x, band, n_bands, n_queue, prim, spill, spill_cap, q);
   gxy_timeline_mark("gen", st);
   const unsigned needed = (n_queue + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
-  const unsigned blocks = std::min<unsigned>(needed, (unsigned)sm_count() * fused_blocks_per_sm());
+  const bool curves = P.n_curves > 0;  // PathLines: the CURVES instantiations (round-Bezier test in the cooperative passes; 3 CTAs per SM)
+  const unsigned blocks = std::min<unsigned>(needed, (unsigned)sm_count() * (curves ? (unsigned)GXY_CURVE_BLOCKS : fused_blocks_per_sm()));
+  if (curves) {
+    if (peer) primary_trace_kernel<12, GXY_MIN_BLOCKS, true, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T, prim_threshold(), rays_per_thread());
+    else primary_trace_kernel<12, GXY_MIN_BLOCKS, false, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T, prim_threshold(), rays_per_thread());
+    gxy_timeline_mark("primary", st);
+    const unsigned sb = std::min<unsigned>((n_queue + 255) / 256, (unsigned)sm_count() * 4u);
+    shade_hits_kernel<false, true><<<sb, 256, 0, st>>>(P, L, prim, nullptr, raw, raw_stride, w, reinterpret_cast<float4 *>(fb), hits, q, epsilon);
+    GXY_CUDA(cudaGetLastError());
+    return 0;
+  }
 #define GXY_LAUNCH_P(FT)                                                                                                                 \
   do {                                                                                                                                   \
     if (peer) primary_trace_kernel<FT, GXY_MIN_BLOCKS, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, prim, raw, raw_stride, spill, spill_cap, q, T, prim_threshold(), rays_per_thread()); \
@@ -911,6 +934,17 @@ int launch_fused_secondary(const SceneParams &P, const DevLights &L, int w, int 
   const unsigned bps = blocks_per_sm > 0 ? (unsigned)std::min(8, blocks_per_sm) : fused_blocks_per_sm();
   const unsigned blocks = (unsigned)std::min<long long>(needed, (long long)sm_count() * bps);
   const PeerTable T = peer ? *peer : no_peers();
+  if (P.n_curves > 0) {
+    const unsigned cb = (unsigned)std::min<long long>(needed, (long long)sm_count() * std::min<unsigned>(bps, (unsigned)GXY_CURVE_BLOCKS));
+    if (peer)
+      fused_secondary_kernel<12, GXY_MIN_BLOCKS, true, true><<<cb, GXY_TRACE_THREADS, 0, st>>>(P, L, w, h, nsec, reinterpret_cast<float4 *>(fb), hits, spill, spill_cap, q, epsilon,
+                                                                                             anyhit ? 1 : 0, T, parity_out, prim_threshold(), rays_per_thread());
+    else
+      fused_secondary_kernel<12, GXY_MIN_BLOCKS, false, true><<<cb, GXY_TRACE_THREADS, 0, st>>>(P, L, w, h, nsec, reinterpret_cast<float4 *>(fb), hits, spill, spill_cap, q, epsilon,
+                                                                                              anyhit ? 1 : 0, T, parity_out, prim_threshold(), rays_per_thread());
+    GXY_CUDA(cudaGetLastError());
+    return 0;
+  }
 #define GXY_LAUNCH_S(FT)                                                                                                              \
   do {                                                                                                                                \
     if (peer)                                                                                                                         \
@@ -937,6 +971,17 @@ int launch_inbox_wave(const SceneParams &P, const DevLights &L, const PeerTable 
   (void)h;
   const unsigned bps = blocks_per_sm > 0 ? (unsigned)std::min(8, blocks_per_sm) : 8u;
   const unsigned blocks = (unsigned)sm_count() * bps;
+  if (P.n_curves > 0) {
+    const unsigned cb = (unsigned)sm_count() * std::min<unsigned>(bps, (unsigned)GXY_CURVE_BLOCKS);
+    inbox_trace_kernel<12, GXY_MIN_BLOCKS, true><<<cb, GXY_TRACE_THREADS, 0, st>>>(P, T, parity_in, w, reinterpret_cast<float4 *>(fb), raw, raw_stride, q, anyhit ? 1 : 0,
+                                                                                  prim_threshold(), rays_per_thread());
+    gxy_timeline_mark("inbox", st);
+    const float4 *inbox_c = reinterpret_cast<const float4 *>(T.base[T.rank] + T.off_inbox[parity_in]);
+    shade_hits_kernel<true, true><<<(unsigned)sm_count() * std::min(4u, bps), 256, 0, st>>>(P, L, hits, inbox_c, raw, raw_stride, w, reinterpret_cast<float4 *>(fb), hits, q,
+                                                                                           epsilon);
+    GXY_CUDA(cudaGetLastError());
+    return 0;
+  }
   inbox_trace_kernel<12, GXY_MIN_BLOCKS><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, T, parity_in, w, reinterpret_cast<float4 *>(fb), raw, raw_stride, q,
                                                                    anyhit ? 1 : 0, prim_threshold(), rays_per_thread());
   gxy_timeline_mark("inbox", st);

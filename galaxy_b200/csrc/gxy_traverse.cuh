@@ -351,6 +351,7 @@ __device__ __forceinline__ bool prim_step(const SceneParams &P, const RayCtx &rc
 // the k-th pending primitive of the g-th lane that holds a primitive group, the owner then takes the
 // (t, geomID, primID)-smallest candidate of its helpers.  On return no lane has pending primitives.
 // owner_slot: 8 bytes of shared memory private to the warp.
+template <bool CURVES = false>
 __device__ __forceinline__ void coop_prim_passes(const SceneParams &P, const RayCtx &rc, TravState &st, bool &trav, const bool anyhit,
                                                  unsigned char *owner_slot, const unsigned lane, const unsigned lt_mask) {
   const unsigned FULL = 0xffffffffu;
@@ -385,7 +386,12 @@ __device__ __forceinline__ void coop_prim_passes(const SceneParams &P, const Ray
       float t, u = 0.f, v = 0.f;
       bool h;
       if ((gk >> 24) == 0) h = tri_test(ra, rb, rcq, oorg, odir, otn, otf, t, u, v);
-      else h = sphere_test(ra, rb, oorg, odir, otn, otf, t);
+      else if (!CURVES || (gk >> 24) == 1) h = sphere_test(ra, rb, oorg, odir, otn, otf, t);
+      else {  // a round Bezier segment of a PathLines operator (only the CURVES instantiations of the frame kernels get here)
+        gxc::CurveHit ch;
+        h = curve_rec_test(ra, oorg, odir, otn, otf, ch);
+        if (h) { t = ch.t; u = ch.u; }
+      }
       if (h) { ct = t; cu = u; cv = v; ckey = ((gk & 0xffffffu) << 28) | __float_as_uint(rcq.z); }
     }
     // the owner (rank r < 8) picks the best of its helpers, lanes 4r .. 4r+3
