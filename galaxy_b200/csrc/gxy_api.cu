@@ -2014,7 +2014,7 @@ static int render_sync(int nparts, gxy_vis *const *parts, const gxy_camera *cam,
   bool fused = true;
   // (decided from the operator list, which is the same on every rank, not from the clipped primitive count)
   for (int p = 0; p < nparts; p++) fused = fused && parts[p]->P.n_volvis == 0 && !parts[p]->geoms.empty();
-  if (getenv("GXY_FUSED_CURVES") && atoi(getenv("GXY_FUSED_CURVES")) == 0)  // PathLines on the list-path kernels, as in round 1
+  if (!(getenv("GXY_FUSED_CURVES") && atoi(getenv("GXY_FUSED_CURVES")) != 0))  // PathLines on the list-path kernels (frame_kind)
     for (int p = 0; p < nparts; p++)
       for (const GeomOp &g : parts[p]->geoms) fused = fused && g.kind != 2;
   if (const char *e = getenv("GXY_FUSED")) fused = fused && atoi(e) != 0;
@@ -2386,8 +2386,11 @@ static int render_sync(int nparts, gxy_vis *const *parts, const gxy_camera *cam,
 static int frame_kind(int nparts, gxy_vis *const *parts) {
   bool fused = true;
   for (int p = 0; p < nparts; p++) fused = fused && parts[p]->P.n_volvis == 0 && !parts[p]->geoms.empty();
-  // PathLines take the CURVES instantiations of the frame kernels (GXY_FUSED_CURVES=0: the list-path kernels, as in round 1)
-  if (getenv("GXY_FUSED_CURVES") && atoi(getenv("GXY_FUSED_CURVES")) == 0)
+  // PathLines take the list-path kernels (one thread per ray).  GXY_FUSED_CURVES=1: the CURVES instantiations of the persistent frame
+  // kernels (round-Bezier test inside the cooperative primitive passes, 140 registers, 3 CTAs per SM) -- parity-green on the B200 but
+  // SLOWER: 40 000 segments 12.6 -> 18.1 ms per frame, 800 000 segments 18.1 -> 24.7 ms (profiles/r02_f_*): a warp-wide pass whose
+  // lanes each run a divergent sub-division loop costs more than it saves
+  if (!(getenv("GXY_FUSED_CURVES") && atoi(getenv("GXY_FUSED_CURVES")) != 0))
     for (int p = 0; p < nparts; p++)
       for (const GeomOp &g : parts[p]->geoms) fused = fused && g.kind != 2;
   if (const char *e = getenv("GXY_FUSED")) fused = fused && atoi(e) != 0;
