@@ -437,7 +437,10 @@ def main():
     # of a set in flight, gxywriter.cpp:196-264).  Every step still delivers its own complete image; steps are counted as they
     # complete.  Geometry workloads only: the volume / PathLines schedules are synchronous per frame (depth 1).
     # measured (tools/flight_sweep.py, ms per frame at 1/2/4/8 GPUs): 4 in flight 1.10/0.85/0.63/0.57, 8 in flight 1.10/0.81/0.52/0.42
-    depth = args.in_flight if args.in_flight is not None else (8 if not (volume or pathlines) else 1)
+    # volumes across ranks: frames in flight only with the device-side-length schedule (GXY_VOLUME_FLIGHTS=1), else one frame at a time
+    vol_flights = volume and world > 1 and os.environ.get("GXY_VOLUME_FLIGHTS", "1") != "0" and os.environ.get("GXY_PEER", "1") != "0"
+    # (volumes: 4 in flight -- enough to keep the bricks along a ray busy; more concurrent marches only fight for the caches)
+    depth = args.in_flight if args.in_flight is not None else (8 if not (volume or pathlines) else 4 if vol_flights else 1)
     depth = max(1, min(depth, gpu.max_slots(), max(1, args.steps)))
     use_flush = depth == 1   # depth 1: 256 MB L2 flush between frames; depth > 1: the frames' inputs are >> L2 (config.timing)
 
@@ -575,7 +578,8 @@ def main():
         vox_rank = float(args.volume_n) ** 3 / max(1, nparts)
         spf = samples / args.steps
         alg_frame = min(16.0 * spf, 4.0 * vox_rank)
-        achieved = alg_frame * args.steps / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
+        vol_ms = trace_ms if use_flush else ms_local   # frames in flight: the march launches of different frames overlap (see the C5 note)
+        achieved = alg_frame * args.steps / (vol_ms * 1e-3) / 1e9 if vol_ms > 0 else 0.0
         vtraffic = NCU_VOLUME_TRAFFIC.get(args.workload) if (args.volume_n == 1024 and n_gpus == 1) else None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                     "traffic": vtraffic,
@@ -584,8 +588,8 @@ def main():
                     "dram_util": (vtraffic / (ms_per_step * 1e-3) / 1e9 / hbm) if vtraffic else None,
                     "peak_kind": peak_kind + " (burst copy figure)", "alg_bytes_per_frame": alg_frame,
                     "alg_bytes_rule": "min(16 B x samples, 4 B x voxels of this rank's brick)", "samples_per_frame": spf,
-                    "gsamples_per_s": samples / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0,
-                    "trace_share_of_step": trace_ms_max / max(1e-9, ms_max)}
+                    "gsamples_per_s": samples / (vol_ms * 1e-3) / 1e9 if vol_ms > 0 else 0.0,
+                    "trace_share_of_step": trace_ms_max / max(1e-9, ms_max) if use_flush else None}
     line = {"metric": metric, "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,

@@ -274,6 +274,11 @@ struct Flight {
   gxy_lighting lights;
   DevLights L;
   gxy_stats S;
+  bool volume = false;             // peer frame of a Visualization with volumes: list kernels with device-side lengths (flight_enqueue_volume)
+  RayBuf vl[2];                    // ... its two device lists
+  Scratch<int> v_hit_index, v_block_sums;
+  Scratch<unsigned long long> vq;  // VolQueues
+  int v_cap = 0, v_k = 0;
   bool graph_frame = false;        // this frame was submitted as one CUDA graph launch (GXY_GRAPH=1, flight_submit_peer)
   cudaGraphExec_t gexec = nullptr;
   int prog_frame = 0;     // gxy_render_progressive_submit: the frame number and camera of the frame on this slot
@@ -1566,6 +1571,7 @@ static void flight_destroy(gxy_vis *v, Flight *F) {
   if (F->ev1) cudaEventDestroy(F->ev1);
   if (F->st) cudaStreamDestroy(F->st);
   F->hits.release(); F->next.release(); F->cur.release(); F->fq.release(); F->rawhits.release(); F->fb.release();
+  F->vl[0].release(); F->vl[1].release(); F->v_hit_index.release(); F->v_block_sums.release(); F->vq.release();
   F->proxies.release(); F->err.release();
   peer_arena_unmap(F->arena, v->ctx->rank);
   if (F->arena.base) cudaFree(F->arena.base);
@@ -1849,6 +1855,83 @@ static int flight_enqueue_peer(gxy_vis *v, Flight &F, const DevCamera &C, int w,
   return peer_finish(v, F);
 }
 
+// ---- one process per GPU, Visualization with volumes: the frame on one rank ----------------------------
+// The list kernels of the synchronous loop (render_sync) on two device lists whose lengths stay on the device, one wave = trace ->
+// hit scan -> AO/shadow spawn into the next list -> classify -> framebuffer -> forward (records into the neighbours' inboxes) ->
+// flag barrier -> the own inbox is appended to the next list.  A ray and each of its secondaries cross at most H partition faces:
+// 2H + 2 waves, and whatever the last barrier still reports is traced at the wait.  No host round trip, so frames overlap across
+// ranks: the brick behind marches frame f while the brick in front marches frame f + 1 -- the only way a DVR frame whose bricks
+// depend on each other front to back can use more than one GPU at a time.
+static int vol_wave(gxy_vis *v, Flight &F, const SceneParams &P, int w, int h) {
+  const PeerTable &T = F.arena.T;
+  VolQueues *q = reinterpret_cast<VolQueues *>(F.vq.p);
+  float *fb = reinterpret_cast<float *>(F.arena.base + T.off_fb);
+  cudaStream_t st = F.st;
+  const int k = F.v_k++;
+  const int cur = k & 1, cap = F.v_cap;
+  const int n_ao = F.lights.n_ao, n_sh = F.lights.shadows ? F.lights.n_lights : 0;
+  Rays L0 = F.vl[cur].v, L1 = F.vl[cur ^ 1].v;
+  if (flight_trace_begin(F, st)) return 1;
+  if (launch_trace(P, L0, cap, F.epsilon, nullptr, !v->has_dvr, &q->samples, st, &q->cnt[cur])) return 1;
+  if (flight_trace_end(F, st)) return 1;
+  if (launch_hit_scan(L0, cap, F.v_hit_index.p, F.v_block_sums.p, &q->nhit, st, &q->cnt[cur])) return 1;
+  if (launch_vol_wave_counts(q, cur, n_ao, n_sh, k == 0, st)) return 1;
+  if (launch_shade_spawn(F.L, L0, cap, F.v_hit_index.p, &q->nhit, L1, F.epsilon, st, w * h)) return 1;
+  if (launch_classify(P, L0, cap, st, &q->cnt[cur])) return 1;
+  if (launch_accumulate(L0, cap, fb, w, h, &q->terminated, st, &q->cnt[cur])) return 1;
+  if (launch_vol_forward(L0, cap, L1, cap, q, cur, T, k & 1, F.err.p, st)) return 1;
+  if (launch_vol_epilogue(T, q, cur, ++F.arena.epoch, F.err.p, st)) return 1;
+  if (launch_vol_unpack(T, k & 1, L1, cap, q, cur, F.err.p, st)) return 1;
+  F.S.kernel_launches += 13 + (n_ao > 0 ? 1 : 0);
+  F.S.waves++;
+  return 0;
+}
+static int vol_finish(gxy_vis *v, Flight &F) {
+  const PeerTable &T = F.arena.T;
+  cudaStream_t st = F.st;
+  VolQueues *q = reinterpret_cast<VolQueues *>(F.vq.p);
+  GXY_CUDA(cudaMemcpyAsync(F.h_tail->q, q, sizeof(VolQueues), cudaMemcpyDeviceToHost, st));
+  GXY_CUDA(cudaMemcpyAsync(&F.h_tail->error, F.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GXY_CUDA(cudaMemsetAsync(F.err.p, 0, sizeof(int), st));
+  if (launch_fb_gather(T, st)) return 1;
+  // (the end barrier only needs an all-rank rendezvous: reuse the wave barrier with an empty next list's count)
+  if (launch_vol_epilogue(T, q, F.v_k & 1, ++F.arena.epoch, F.err.p, st)) return 1;
+  F.S.kernel_launches += 2;
+  (void)v;
+  return 0;
+}
+static int flight_enqueue_volume(gxy_vis *v, Flight &F, const DevCamera &C, int w, int h, float epsilon) {
+  gxy_context *c = v->ctx;
+  PeerArena &A = F.arena;
+  const PeerTable &T = A.T;
+  cudaStream_t st = F.st;
+  const int npix = w * h;
+  SceneParams P = v->P;
+  P.error_flag = F.err.p;
+  float *fb = reinterpret_cast<float *>(A.base + T.off_fb);
+  VolQueues *q = reinterpret_cast<VolQueues *>(F.vq.p);
+  F.n_bands = 1;
+  F.fb_result = c->rank == 0 ? reinterpret_cast<float *>(A.base + T.off_final) : fb;
+  F.n_trace_ev = 0;
+  F.v_k = 0;
+  (void)epsilon;
+  GXY_CUDA(cudaMemsetAsync(fb, 0, sizeof(float) * 4 * npix, st));
+  GXY_CUDA(cudaMemsetAsync(q, 0, sizeof(VolQueues), st));
+  // a rendezvous before anybody writes into anybody's inbox for this frame: the previous frame on this slot is over everywhere
+  if (launch_vol_epilogue(T, q, 0, ++A.epoch, F.err.p, st)) return 1;
+  // Camera::generate_initial_rays: the rays whose first brick is this one, in 16x8-pixel tile order; the count stays in q->cnt[0]
+  if (launch_generate(P, C, w, h, tiled_order(), F.vl[0].v, nullptr, F.v_block_sums.p, &q->cnt[0], st)) return 1;
+  F.S.kernel_launches += 4;
+  int f[3];
+  gxy_factor(c->nranks, f);
+  const int H = (f[0] - 1) + (f[1] - 1) + (f[2] - 1);
+  const bool spawn = F.n_sec_per_hit > 0;
+  const int waves = (spawn ? 2 : 1) * H + (spawn ? 2 : 1);
+  for (int k = 0; k < waves; k++)
+    if (vol_wave(v, F, P, w, h)) return 1;
+  return vol_finish(v, F);
+}
+
 // Submission of a peer frame.  Direct: ~75 runtime calls (37 launches on two streams, their fork/join events, memsets, the tail
 // copies).  As a graph: the same calls are CAPTURED into a CUDA graph, the flight's executable graph is updated in place
 // (cudaGraphExecUpdate: same topology, new kernel parameters -- camera, tile rectangle, barrier epochs) and launched with one call;
@@ -1860,22 +1943,28 @@ static int flight_submit_peer(gxy_vis *v, Flight &F, const DevCamera &C, int w, 
   gxy_context *c = v->ctx;
   cudaStream_t st = F.st;
   const int npix = w * h;
-  if (F.hits.reserve(npix, false, st) || F.fq.reserve(sizeof(FusedQueues) / 8) || F.rawhits.reserve((size_t)6 * npix) ||
-      F.next.reserve(npix, false, st) || F.cur.reserve(64, false, st) || F.proxies.reserve(sizeof(PartProxy) * (size_t)c->nranks))
+  if (F.volume) {
+    const size_t cap = (size_t)F.v_cap;
+    if (F.vl[0].reserve(cap, false, st) || F.vl[1].reserve(cap, false, st) || F.v_hit_index.reserve(2 * cap) ||
+        F.v_block_sums.reserve(cap / 1024 + 2) || F.vq.reserve((sizeof(VolQueues) + 7) / 8))
+      return 1;
+  } else if (F.hits.reserve(npix, false, st) || F.fq.reserve(sizeof(FusedQueues) / 8) || F.rawhits.reserve((size_t)6 * npix) ||
+             F.next.reserve(npix, false, st) || F.cur.reserve(64, false, st) || F.proxies.reserve(sizeof(PartProxy) * (size_t)c->nranks))
     return 1;
   cudaStream_t s2;
   if (flight_lane(F, 1, &s2)) return 1;
   // measured on 8 GPUs (tools/flight_sweep.py, 8 frames in flight): host time per submitted frame 0.271 ms direct, 0.067 ms as a graph;
   // frame 0.482 -> 0.389 ms (the direct submission was host bound); on 2 GPUs 0.156 -> 0.045 ms of host time, frame unchanged
-  const bool graph = g_peer_warm && !timeline_on() && !(getenv("GXY_GRAPH") && atoi(getenv("GXY_GRAPH")) == 0);
+  static bool g_vol_warm = false;
+  const bool graph = (F.volume ? g_vol_warm : g_peer_warm) && !timeline_on() && !(getenv("GXY_GRAPH") && atoi(getenv("GXY_GRAPH")) == 0);
   F.graph_frame = graph;
   GXY_CUDA(cudaEventRecord(F.ev0, st));
   if (!graph) {
-    if (flight_enqueue_peer(v, F, C, w, h, epsilon)) return 1;
-    g_peer_warm = true;
+    if (F.volume ? flight_enqueue_volume(v, F, C, w, h, epsilon) : flight_enqueue_peer(v, F, C, w, h, epsilon)) return 1;
+    (F.volume ? g_vol_warm : g_peer_warm) = true;
   } else {
     GXY_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    const int rc = flight_enqueue_peer(v, F, C, w, h, epsilon);
+    const int rc = F.volume ? flight_enqueue_volume(v, F, C, w, h, epsilon) : flight_enqueue_peer(v, F, C, w, h, epsilon);
     cudaGraph_t g = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(st, &g);
     if (rc || ce != cudaSuccess || !g) {
@@ -1901,6 +1990,12 @@ static int flight_submit_peer(gxy_vis *v, Flight &F, const DevCamera &C, int w, 
   return 0;
 }
 
+static VolQueues tail_vq(const Flight &F) {  // the end-of-frame counters of a volume frame (copied into the page-locked tail by vol_finish)
+  VolQueues q;
+  memcpy(&q, F.h_tail->q, sizeof q);
+  return q;
+}
+
 static int flight_wait(gxy_vis *v, Flight &F, gxy_stats *stats) {
   gxy_context *c = v->ctx;
   GXY_CHECK(F.pending, "no frame was submitted to this slot");
@@ -1908,7 +2003,18 @@ static int flight_wait(gxy_vis *v, Flight &F, gxy_stats *stats) {
   if (!F.sync_done) {
     GXY_CUDA(cudaEventSynchronize(F.ev1));
     int err = F.h_tail->error;
-    if (F.peer && err == 0) {
+    if (F.peer && F.volume && err == 0) {
+      SceneParams P = v->P;
+      P.error_flag = F.err.p;
+      while (tail_vq(F).global_pending != 0u && F.h_tail->error == 0) {
+        GXY_CHECK(F.v_k < 4096, "volume wave loop does not terminate (%u units of work in flight)", tail_vq(F).global_pending);
+        F.graph_frame = false;
+        if (vol_wave(v, F, P, F.w, F.h) || vol_finish(v, F)) return 1;
+        GXY_CUDA(cudaEventRecord(F.ev1, F.st));
+        GXY_CUDA(cudaEventSynchronize(F.ev1));
+      }
+      err = F.h_tail->error;
+    } else if (F.peer && err == 0) {
       // anything still in flight after the scheduled waves (cannot happen on a regular grid): one wave at a time, every rank alike
       SceneParams P = v->P;
       P.error_flag = F.err.p;
@@ -1925,6 +2031,7 @@ static int flight_wait(gxy_vis *v, Flight &F, gxy_stats *stats) {
     GXY_CHECK(err == 0, "device error flag %d (1: BVH traversal stack overflow, 3: ray list / inbox capacity, 4: peer barrier timeout, 6: TMA copy did not complete)", err);
     gxy_stats &S = F.S;
     FusedQueues t = F.h_tail->q[0];
+    if (F.volume) memset(&t, 0, sizeof t);
     for (int b = 1; b < F.n_bands; b++) {
       const FusedQueues &o = F.h_tail->q[b];
       t.n_generated += o.n_generated; t.n_hits += o.n_hits; t.n_terminated += o.n_terminated; t.n_primary32 += o.n_primary32;
@@ -1937,7 +2044,13 @@ static int flight_wait(gxy_vis *v, Flight &F, gxy_stats *stats) {
     S.terminated_rays = (long long)t.n_terminated;
     S.nodes_visited = (long long)t.nodes;
     S.prims_tested = (long long)t.prims;
-    if (F.peer) {
+    if (F.volume) {
+      const VolQueues vq = tail_vq(F);
+      S.primary_rays = (long long)vq.generated; S.ao_rays = (long long)vq.ao; S.shadow_rays = (long long)vq.shadow;
+      S.forwarded_rays = (long long)vq.forwarded; S.terminated_rays = (long long)vq.terminated;
+      S.traced_rays = S.dequeued_rays = (long long)vq.traced;
+      S.volume_samples = (long long)vq.samples;
+    } else if (F.peer) {
       S.forwarded_rays = (long long)t.n_spill + (long long)t.n_virtual;
       S.traced_rays = (long long)t.n_generated + (long long)t.n_hits * nsec + (long long)t.n_inbox;
       S.dequeued_rays = (long long)t.n_primary32 + (long long)t.n_hits * nsec + (long long)t.n_inbox;
@@ -2394,7 +2507,14 @@ static int frame_kind(int nparts, gxy_vis *const *parts) {
     for (int p = 0; p < nparts; p++)
       for (const GeomOp &g : parts[p]->geoms) fused = fused && g.kind != 2;
   if (const char *e = getenv("GXY_FUSED")) fused = fused && atoi(e) != 0;
-  if (!fused) return 0;
+  if (!fused) {
+    // one process per GPU, a Visualization with volumes: the list kernels with device-side lengths over the peer arenas
+    // (flight_enqueue_volume); GXY_VOLUME_FLIGHTS=0 / GXY_PEER=0: the synchronous NCCL list loop
+    if (parts[0]->ctx->comm && nparts == 1 && parts[0]->P.n_volvis >= 1 && parts[0]->samplers.empty() &&
+        !(getenv("GXY_PEER") && atoi(getenv("GXY_PEER")) == 0) && !(getenv("GXY_VOLUME_FLIGHTS") && atoi(getenv("GXY_VOLUME_FLIGHTS")) == 0))
+      return 3;
+    return 0;
+  }
   if (parts[0]->ctx->comm) {
     if (const char *e = getenv("GXY_PEER"))
       if (atoi(e) == 0) return 0;
@@ -2433,17 +2553,24 @@ int gxy_render_submit(int nparts, gxy_vis *const *parts, const gxy_camera *cam, 
   for (int s = 0; s < 2; s++)
     if (v->async_ready[s]) GXY_CUDA(cudaStreamWaitEvent(F.st, v->async_ready[s], 0));
   int kind = frame_kind(nparts, parts);
-  if (kind == 2) {
-    const unsigned long long cap = (unsigned long long)w * h * (unsigned long long)(1 + F.n_sec_per_hit);
-    GXY_CHECK(cap < (1ull << 31), "peer inbox too large (%llu records)", cap);
+  F.volume = false;
+  if (kind == 2 || kind == 3) {
+    unsigned long long cap = (unsigned long long)w * h * (unsigned long long)(1 + F.n_sec_per_hit);
+    if (kind == 3) {  // the lists hold the tile-ordered primaries (generation slots) or the secondaries + what the neighbours sent
+      const unsigned long long slots = (unsigned long long)((w + 15) / 16) * ((h + 7) / 8) * 128ull;
+      cap = std::max(slots, (unsigned long long)w * h) * (unsigned long long)(1 + F.n_sec_per_hit) + 1024ull;
+    }
+    GXY_CHECK(cap < (1ull << 31) - (1ull << 24), "peer inbox too large (%llu records)", cap);
     if (c->arena.disabled) F.arena.disabled = true;  // (decided once, by flight 0, on every rank alike)
     if (ensure_peer_arena(c, F.arena, (unsigned)(w * h), (unsigned)cap)) return 1;
     if (F.arena.disabled) { c->arena.disabled = true; kind = 0; }
+    F.v_cap = (int)cap;
   }
   if (kind == 1) {
     if (flight_submit_single(v, F, C, w, h, epsilon)) return 1;
-  } else if (kind == 2) {
+  } else if (kind == 2 || kind == 3) {
     F.peer = true;
+    F.volume = kind == 3;
     if (flight_submit_peer(v, F, C, w, h, epsilon)) return 1;
   } else {
     // synchronous schedules render here; the image is kept in the flight's own buffer until the wait

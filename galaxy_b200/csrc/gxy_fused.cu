@@ -756,6 +756,35 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
+// Flag barrier over all ranks (one warp): lane r publishes (work this rank leaves behind for a later wave, epoch) in rank r's arena and
+// waits for rank r's flag in its own.  Everything the kernels before this one wrote into peer arenas is complete (stream order) before
+// the flags go out.  Returns the sum of every rank's `sent` on every lane 0 (valid on lane 0).  All 32 lanes must call.
+__device__ __forceinline__ unsigned peer_barrier(const PeerTable &T, unsigned epoch, unsigned sent, unsigned long long timeout_ns,
+                                                 int *__restrict__ error_flag) {
+  const unsigned lane = threadIdx.x & 31u;
+  PeerCtrl *mine = peer_ctrl(T, T.rank);
+  sent = __shfl_sync(FULLMASK, sent, 0);
+  __threadfence_system();
+  __syncwarp();
+  unsigned theirs = 0u;
+  if ((int)lane < T.nranks) {
+    PeerCtrl *pc = peer_ctrl(T, (int)lane);
+    *reinterpret_cast<volatile unsigned *>(&pc->pending[epoch & 1u][T.rank]) = sent;
+    __threadfence_system();
+    st_release_sys(&pc->flags[T.rank], epoch);
+    const unsigned long long t0 = global_timer_ns();
+    bool ok = true;
+    while ((int)(ld_acquire_sys(&mine->flags[lane]) - epoch) < 0) {
+      if (global_timer_ns() - t0 > timeout_ns) { ok = false; break; }
+      __nanosleep(200);
+    }
+    if (!ok) *error_flag = 4;
+    theirs = *reinterpret_cast<volatile unsigned *>(&mine->pending[epoch & 1u][lane]);
+  }
+  for (int off = 16; off > 0; off >>= 1) theirs += __shfl_down_sync(FULLMASK, theirs, off);
+  return theirs;
+}
+
 // End of a wave on this rank (one warp): advance the queue bookkeeping, hand the consumed inbox back, then a
 // flag barrier over all ranks -- lane r publishes (rays sent this wave, epoch) in rank r's arena and waits for
 // rank r's flag in its own.  Everything the kernels before this one wrote into peer arenas is complete (stream
@@ -784,25 +813,7 @@ __global__ void __launch_bounds__(32)
       mine->inbox_count[parity_consumed] = 0u;
     }
   }
-  sent = __shfl_sync(FULLMASK, sent, 0);
-  __threadfence_system();
-  __syncwarp();
-  unsigned theirs = 0u;
-  if ((int)lane < T.nranks) {
-    PeerCtrl *pc = peer_ctrl(T, (int)lane);
-    *reinterpret_cast<volatile unsigned *>(&pc->pending[epoch & 1u][T.rank]) = sent;
-    __threadfence_system();
-    st_release_sys(&pc->flags[T.rank], epoch);
-    const unsigned long long t0 = global_timer_ns();
-    bool ok = true;
-    while ((int)(ld_acquire_sys(&mine->flags[lane]) - epoch) < 0) {
-      if (global_timer_ns() - t0 > timeout_ns) { ok = false; break; }
-      __nanosleep(200);
-    }
-    if (!ok) *error_flag = 4;
-    theirs = *reinterpret_cast<volatile unsigned *>(&mine->pending[epoch & 1u][lane]);
-  }
-  for (int off = 16; off > 0; off >>= 1) theirs += __shfl_down_sync(FULLMASK, theirs, off);
+  const unsigned theirs = peer_barrier(T, epoch, sent, timeout_ns, error_flag);
   if (lane == 0u) q->global_pending = theirs;
 }
 
@@ -825,6 +836,108 @@ __global__ void __launch_bounds__(256) fb_gather_kernel(const __grid_constant__ 
       if (r < T.nranks) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
     dst[i] = acc;
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Frames in flight for Visualizations with volumes (one process per GPU): the list kernels of gxy_kernels.cu run on two
+// device lists whose lengths never leave the device (VolQueues::cnt), rays that leave the brick travel as 64-byte inbox records --
+// they carry what a ray needs to go on in the next brick: origin, direction, t, tMax, the colour and opacity accumulated so far,
+// pixel, type -- and the flag barrier separates the waves, exactly as on the geometry path.
+__global__ void vol_wave_counts_kernel(VolQueues *__restrict__ q, int cur, int n_ao, int n_sh, int first) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int n = q->cnt[cur];
+  if (first) q->generated = (unsigned long long)n;
+  q->traced += (unsigned long long)n;
+  const long long nh = q->nhit;
+  q->ao += (unsigned long long)(nh * n_ao);
+  q->shadow += (unsigned long long)(nh * n_sh);
+  q->cnt[cur ^ 1] = (int)(nh * (n_ao + n_sh));  // the spawned rays open the next list; keepers and the inbox are appended behind them
+  q->away_wave = 0u;
+  q->kept_wave = 0u;
+}
+
+// Renderer::SendRays for one list (Renderer.cpp:620-634): every ray classified for another rank becomes a record in that rank's
+// inbox[parity]; a ray that stays (KEEP_HERE, or its own rank as destination) is appended to the next list
+__global__ void __launch_bounds__(256)
+    vol_forward_kernel(Rays R, int cap, Rays next, int next_cap, VolQueues *__restrict__ q, int cur, const __grid_constant__ PeerTable T, int parity,
+                       int *__restrict__ error_flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31u;
+  const int n = min(cap, q->cnt[cur]);
+  int cls = CLS_TERMINATED;
+  if (i < n) cls = R.classification[i];
+  if (cls == CLS_KEEP_HERE) cls = T.rank;
+  const bool away = cls >= 0 && cls != T.rank && cls < T.nranks;
+  const bool keep = cls == T.rank;
+  float3 org = f3(0.f, 0.f, 0.f), dir = f3(0.f, 0.f, 0.f);
+  float r = 0.f, g = 0.f, b = 0.f, o = 0.f, t = 0.f, tMax = 0.f;
+  int x = 0, y = 0, type = 0, term = 0;
+  if (away || keep) {
+    org = f3(R.ox[i], R.oy[i], R.oz[i]); dir = f3(R.dx[i], R.dy[i], R.dz[i]);
+    r = R.r[i]; g = R.g[i]; b = R.b[i]; o = R.o[i]; t = R.t[i]; tMax = R.tMax[i];
+    x = R.x[i]; y = R.y[i]; type = R.type[i]; term = R.term[i];
+  }
+  peer_push(T, parity, FULLMASK, lane, away, cls, org, dir, r, g, b, o, t, tMax, x, y, type, term, error_flag);
+  if (keep) {
+    const int pos = atomicAdd(&q->cnt[cur ^ 1], 1);
+    if (pos < next_cap) {
+      next.ox[pos] = org.x; next.oy[pos] = org.y; next.oz[pos] = org.z; next.dx[pos] = dir.x; next.dy[pos] = dir.y; next.dz[pos] = dir.z;
+      next.r[pos] = r; next.g[pos] = g; next.b[pos] = b; next.o[pos] = o; next.t[pos] = t; next.tMax[pos] = tMax;
+      next.x[pos] = x; next.y[pos] = y; next.type[pos] = type; next.term[pos] = term;
+    } else *error_flag = 3;
+  }
+  const unsigned ma = __ballot_sync(FULLMASK, away), mk = __ballot_sync(FULLMASK, keep);
+  if (lane == 0u) {
+    if (ma) atomicAdd(&q->away_wave, (unsigned)__popc(ma));
+    if (mk) atomicAdd(&q->kept_wave, (unsigned)__popc(mk));
+  }
+}
+
+// end of a wave: what this rank leaves for a later wave = the records it pushed to other ranks + the rays of its next list so far
+// (spawned AO/shadow rays and kept rays); barrier; the global sum is the termination test
+__global__ void __launch_bounds__(32)
+    vol_epilogue_kernel(const __grid_constant__ PeerTable T, VolQueues *__restrict__ q, int cur, unsigned epoch, unsigned long long timeout_ns,
+                        int *__restrict__ error_flag) {
+  const unsigned lane = threadIdx.x;
+  unsigned sent = 0u;
+  if (lane == 0u) {
+    sent = q->away_wave + (unsigned)max(q->cnt[cur ^ 1], 0);
+    q->forwarded += (unsigned long long)q->away_wave + (unsigned long long)q->kept_wave;
+  }
+  const unsigned theirs = peer_barrier(T, epoch, sent, timeout_ns, error_flag);
+  if (lane == 0u) q->global_pending = theirs;
+}
+
+// after the barrier: the records the other ranks wrote into inbox[parity] during this wave are appended to the next list
+__global__ void __launch_bounds__(256)
+    vol_unpack_kernel(const __grid_constant__ PeerTable T, int parity, Rays next, int next_cap, const VolQueues *__restrict__ q, int cur,
+                      int *__restrict__ error_flag) {
+  const float4 *__restrict__ inbox = peer_inbox(T, T.rank, parity);
+  const unsigned n_in = min(peer_ctrl(T, T.rank)->inbox_count[parity], T.inbox_cap);
+  const int base = q->cnt[cur ^ 1];
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += gridDim.x * blockDim.x) {
+    const long long pos = (long long)base + i;
+    if (pos >= next_cap) { *error_flag = 3; continue; }
+    const float4 a = inbox[4 * (size_t)i], b = inbox[4 * (size_t)i + 1], c = inbox[4 * (size_t)i + 2], d = inbox[4 * (size_t)i + 3];
+    next.ox[pos] = a.x; next.oy[pos] = a.y; next.oz[pos] = a.z; next.dx[pos] = a.w; next.dy[pos] = b.x; next.dz[pos] = b.y;
+    next.t[pos] = b.z; next.tMax[pos] = b.w;
+    next.r[pos] = c.x; next.g[pos] = c.y; next.b[pos] = c.z; next.o[pos] = c.w;
+    next.x[pos] = __float_as_int(d.x); next.y[pos] = __float_as_int(d.y); next.type[pos] = __float_as_int(d.z); next.term[pos] = __float_as_int(d.w);
+  }
+}
+// ... and the list's length and the inbox counter follow once every record is in place (next launch on the stream)
+__global__ void vol_unpack_commit_kernel(const __grid_constant__ PeerTable T, int parity, VolQueues *__restrict__ q, int cur, int next_cap) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  PeerCtrl *mine = peer_ctrl(T, T.rank);
+  const unsigned n_in = min(mine->inbox_count[parity], T.inbox_cap);
+  q->inbox += (unsigned long long)n_in;
+  const long long total = (long long)q->cnt[cur ^ 1] + n_in;
+  q->cnt[cur ^ 1] = (int)min(total, (long long)next_cap);
+  q->cnt[cur] = 0;
+  q->away_wave = 0u;  // (consumed by the wave's epilogue; the rendezvous at the end of a frame must not count them again)
+  q->kept_wave = 0u;
+  mine->inbox_count[parity] = 0u;
 }
 
 static int sm_count() {
@@ -997,6 +1110,31 @@ int launch_wave_epilogue(const PeerTable &T, FusedQueues *q, unsigned epoch, int
   unsigned long long timeout_ns = 30ull * 1000000000ull;
   if (const char *e = getenv("GXY_PEER_TIMEOUT_MS")) timeout_ns = (unsigned long long)atoll(e) * 1000000ull;
   wave_epilogue_kernel<<<1, 32, 0, st>>>(T, q, epoch, parity_consumed, hits_spawn ? 1 : 0, timeout_ns, error_flag);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_vol_wave_counts(VolQueues *q, int cur, int n_ao, int n_sh, bool first, cudaStream_t st) {
+  vol_wave_counts_kernel<<<1, 32, 0, st>>>(q, cur, n_ao, n_sh, first ? 1 : 0);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_vol_forward(Rays R, int cap, Rays next, int next_cap, VolQueues *q, int cur, const PeerTable &T, int parity, int *error_flag,
+                       cudaStream_t st) {
+  vol_forward_kernel<<<(cap + 255) / 256, 256, 0, st>>>(R, cap, next, next_cap, q, cur, T, parity, error_flag);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_vol_epilogue(const PeerTable &T, VolQueues *q, int cur, unsigned epoch, int *error_flag, cudaStream_t st) {
+  unsigned long long timeout_ns = 30ull * 1000000000ull;
+  if (const char *e = getenv("GXY_PEER_TIMEOUT_MS")) timeout_ns = (unsigned long long)atoll(e) * 1000000ull;
+  vol_epilogue_kernel<<<1, 32, 0, st>>>(T, q, cur, epoch, timeout_ns, error_flag);
+  GXY_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_vol_unpack(const PeerTable &T, int parity, Rays next, int next_cap, VolQueues *q, int cur, int *error_flag, cudaStream_t st) {
+  vol_unpack_kernel<<<(unsigned)sm_count() * 4u, 256, 0, st>>>(T, parity, next, next_cap, q, cur, error_flag);
+  vol_unpack_commit_kernel<<<1, 32, 0, st>>>(T, parity, q, cur, next_cap);
   GXY_CUDA(cudaGetLastError());
   return 0;
 }

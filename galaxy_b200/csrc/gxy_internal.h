@@ -7,18 +7,20 @@ namespace gxy {
 // ---- kernels (gxy_kernels.cu) ---------------------------------------------------------------
 // K1 TraceRays_TraceRays on n rays (TraceRays.ispc:326-623).  hit_ids may be NULL.
 // anyhit_secondary: occlusion-only traversal for non-PRIMARY rays (valid when no DVR integrates).
+// n_dev (here and below; may be NULL): the list's length on the device -- the launch is sized for n (the list's capacity) and every
+// kernel takes min(n, *n_dev); the waves of a frame in flight never bring a count to the host
 int launch_trace(const SceneParams &P, Rays R, int n, float global_epsilon, int *hit_ids, bool anyhit_secondary,
-                 unsigned long long *sample_counter, cudaStream_t st);
+                 unsigned long long *sample_counter, cudaStream_t st, const int *n_dev = nullptr);
 // offsets for the secondary list (TraceRays.cpp:89-117): per ray "1 if PRIMARY&&SURFACE" flags are
 // scanned; returns device pointers inside `scratch`.  n_hit is written to *d_nhit (device).
-int launch_hit_scan(Rays R, int n, int *d_hit_index /*n*/, int *d_block_sums, int *d_nhit, cudaStream_t st);
+int launch_hit_scan(Rays R, int n, int *d_hit_index /*n*/, int *d_block_sums, int *d_nhit, cudaStream_t st, const int *n_dev = nullptr);
 // ambientLighting + generateAORays + diffuseLighting + generateShadowRays (TraceRays.ispc:625-923)
 int launch_shade_spawn(const DevLights &L, Rays R, int n, const int *d_hit_index, const int *d_nhit, Rays out, float epsilon,
-                       cudaStream_t st);
+                       cudaStream_t st, int max_hits = 0);
 // Renderer::Classify + AssignDestinations (Renderer.cpp:304-454)
-int launch_classify(const SceneParams &P, Rays R, int n, cudaStream_t st);
+int launch_classify(const SceneParams &P, Rays R, int n, cudaStream_t st, const int *n_dev = nullptr);
 // HandleTerminatedRays + AddLocalPixels (Renderer.cpp:456-502, Rendering.cpp:125-153): fb += rgba
-int launch_accumulate(Rays R, int n, float *fb, int w, int h, unsigned long long *d_terminated, cudaStream_t st);
+int launch_accumulate(Rays R, int n, float *fb, int w, int h, unsigned long long *d_terminated, cudaStream_t st, const int *n_dev = nullptr);
 // counting-sort of rays with classification >= 0 into per-destination segments of `out`
 // (Renderer.cpp:561-618).  d_counts: nranks ints (device, zeroed by the call), d_offsets nranks+1.
 int launch_partition_by_destination(Rays R, int n, int nranks, int keep_rank, Rays out, int *d_counts, int *d_offsets, int *d_cursor,
@@ -144,6 +146,24 @@ int launch_wave_epilogue(const PeerTable &T, FusedQueues *q, unsigned epoch, int
                          cudaStream_t st);
 // sum of all partial framebuffers for this rank's slice of the image, written to the image owner (rank 0)
 int launch_fb_gather(const PeerTable &T, cudaStream_t st);
+
+// ---- frames in flight for Visualizations with volumes (one process per GPU): list kernels with device-side lengths + peer inboxes ----
+struct VolQueues {  // device memory, zeroed at the start of a frame
+  int cnt[2];                   // rays in the two device lists of the frame (the current one and the one being assembled)
+  int nhit;                     // PRIMARY && SURFACE rays of the current list (launch_hit_scan)
+  unsigned away_wave, kept_wave;  // this wave: records pushed to other ranks / rays appended to the own next list
+  unsigned global_pending;      // after a wave's barrier: work left on all ranks
+  unsigned long long generated, traced, ao, shadow, forwarded, terminated, samples, inbox;
+};
+// after the hit scan of list `cur`: statistics, and the next list opens with the nhit * (n_ao + n_sh) rays about to be spawned
+int launch_vol_wave_counts(VolQueues *q, int cur, int n_ao, int n_sh, bool first, cudaStream_t st);
+// classified list `cur` (capacity cap): rays for other ranks -> records in their inbox[parity]; rays that stay -> appended to `next`
+int launch_vol_forward(Rays R, int cap, Rays next, int next_cap, VolQueues *q, int cur, const PeerTable &T, int parity, int *error_flag,
+                       cudaStream_t st);
+// flag barrier of the wave; q->global_pending = work left anywhere
+int launch_vol_epilogue(const PeerTable &T, VolQueues *q, int cur, unsigned epoch, int *error_flag, cudaStream_t st);
+// after the barrier: the records of the own inbox[parity] are appended to `next`, its length is final, the inbox is handed back
+int launch_vol_unpack(const PeerTable &T, int parity, Rays next, int next_cap, VolQueues *q, int cur, int *error_flag, cudaStream_t st);
 
 // GXY_PROFILE=1: device timeline of a frame -- a named CUDA event after a launch; printed by the frame function
 void gxy_timeline_mark(const char *name, cudaStream_t st);

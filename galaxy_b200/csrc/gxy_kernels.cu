@@ -163,9 +163,12 @@ __device__ __forceinline__ void sample_volumes(const SceneParams &P, const VolK 
 template <int NV, bool HAS_GEOM, bool IDX32, bool CURVES = false>
 __global__ void __launch_bounds__(GXY_TRACE_THREADS, (NV <= 2 && !HAS_GEOM) ? GXY_MARCH_BLOCKS : 1)
     trace_kernel(const __grid_constant__ SceneParams P, Rays R, int n, float global_epsilon, int *__restrict__ hit_ids,
-                 int anyhit_secondary, unsigned long long *__restrict__ sample_counter) {
+                 int anyhit_secondary, unsigned long long *__restrict__ sample_counter, const int *__restrict__ n_dev) {
   __shared__ uint2 stack[HAS_GEOM ? GXY_STACK_SMEM * GXY_TRACE_THREADS : 1];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // n_dev != NULL: the list's length lives on the device (frames in flight: no host round trip between the waves of a frame);
+  // the launch is then sized for the list's capacity n
+  if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   // launch_trace instantiates NV = n_volvis for up to 3 volume operators; only the catch-all has fewer than NV
   const int nvv = (NV <= 3) ? NV : (NV < P.n_volvis ? NV : P.n_volvis);
@@ -612,7 +615,7 @@ static int launch_trace_geom(const SceneParams &P, Rays R, int n, int *hit_ids, 
 
 template <int NV>
 static int launch_trace_nv(const SceneParams &P, Rays R, int n, float eps, int *hit_ids, bool anyhit, unsigned long long *sc,
-                           cudaStream_t st) {
+                           cudaStream_t st, const int *n_dev) {
   const int blocks = (n + GXY_TRACE_THREADS - 1) / GXY_TRACE_THREADS;
   // 32-bit element indices in the sampler when every volume of the Visualization has fewer than 2^31 voxels
   bool idx32 = NV > 0;
@@ -622,30 +625,31 @@ static int launch_trace_nv(const SceneParams &P, Rays R, int n, float eps, int *
   }
   if (P.n_prims > 0 && P.n_curves > 0) {
     // Visualizations with PathLines: the per-lane traversal with the curve test; 64-bit sampler indices (one instantiation per NV)
-    trace_kernel<NV, true, false, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, anyhit ? 1 : 0, sc);
+    trace_kernel<NV, true, false, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, anyhit ? 1 : 0, sc, n_dev);
   } else if (P.n_prims > 0) {
-    if (idx32) trace_kernel<NV, true, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, anyhit ? 1 : 0, sc);
-    else trace_kernel<NV, true, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, anyhit ? 1 : 0, sc);
+    if (idx32) trace_kernel<NV, true, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, anyhit ? 1 : 0, sc, n_dev);
+    else trace_kernel<NV, true, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, anyhit ? 1 : 0, sc, n_dev);
   } else {
-    if (idx32) trace_kernel<NV, false, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, 0, sc);
-    else trace_kernel<NV, false, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, 0, sc);
+    if (idx32) trace_kernel<NV, false, true><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, 0, sc, n_dev);
+    else trace_kernel<NV, false, false><<<blocks, GXY_TRACE_THREADS, 0, st>>>(P, R, n, eps, hit_ids, 0, sc, n_dev);
   }
   GXY_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_trace(const SceneParams &P, Rays R, int n, float global_epsilon, int *hit_ids, bool anyhit_secondary,
-                 unsigned long long *sample_counter, cudaStream_t st) {
+                 unsigned long long *sample_counter, cudaStream_t st, const int *n_dev) {
   if (n <= 0) return 0;
   const char *pe = getenv("GXY_TRACE_PERSISTENT");
   const bool persistent = !(pe && atoi(pe) == 0);
-  if (P.n_volvis == 0 && P.n_prims > 0 && P.n_curves == 0 && persistent) return launch_trace_geom(P, R, n, hit_ids, anyhit_secondary, st);
+  // (the persistent geometry kernel pulls rays through a host-zeroed queue head and knows its list length on the host)
+  if (P.n_volvis == 0 && P.n_prims > 0 && P.n_curves == 0 && persistent && !n_dev) return launch_trace_geom(P, R, n, hit_ids, anyhit_secondary, st);
   switch (P.n_volvis) {
-    case 0: return launch_trace_nv<0>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st);
-    case 1: return launch_trace_nv<1>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st);
-    case 2: return launch_trace_nv<2>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st);
-    case 3: return launch_trace_nv<3>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st);
-    default: return launch_trace_nv<GXY_MAX_VOLUME_VIS>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st);
+    case 0: return launch_trace_nv<0>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st, n_dev);
+    case 1: return launch_trace_nv<1>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st, n_dev);
+    case 2: return launch_trace_nv<2>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st, n_dev);
+    case 3: return launch_trace_nv<3>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st, n_dev);
+    default: return launch_trace_nv<GXY_MAX_VOLUME_VIS>(P, R, n, global_epsilon, hit_ids, anyhit_secondary, sample_counter, st, n_dev);
   }
 }
 
@@ -733,7 +737,8 @@ __global__ void scan_block_sums_kernel(int *__restrict__ sums, int nblocks, int 
 __device__ __forceinline__ int hit_flag(const Rays &R, int i, int n) {
   return (i < n && R.type[i] == RAY_PRIMARY && (R.term[i] & RAY_SURFACE)) ? 1 : 0;
 }
-__global__ void __launch_bounds__(SCAN_THREADS) hit_count_kernel(Rays R, int n, int *__restrict__ block_sums) {
+__global__ void __launch_bounds__(SCAN_THREADS) hit_count_kernel(Rays R, int n, int *__restrict__ block_sums, const int *__restrict__ n_dev) {
+  if (n_dev) n = min(n, *n_dev);
   const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   int c = 0;
 #pragma unroll
@@ -743,7 +748,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) hit_count_kernel(Rays R, int n, 
   if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
 }
 __global__ void __launch_bounds__(SCAN_THREADS)
-    hit_index_kernel(Rays R, int n, const int *__restrict__ block_sums, int *__restrict__ hit_index, int *__restrict__ hit_list) {
+    hit_index_kernel(Rays R, int n, const int *__restrict__ block_sums, int *__restrict__ hit_index, int *__restrict__ hit_list,
+                     const int *__restrict__ n_dev) {
+  if (n_dev) n = min(n, *n_dev);
   const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   int f[SCAN_ITEMS], c = 0;
 #pragma unroll
@@ -757,12 +764,12 @@ __global__ void __launch_bounds__(SCAN_THREADS)
     }
 }
 
-int launch_hit_scan(Rays R, int n, int *d_hit_index, int *d_block_sums, int *d_nhit, cudaStream_t st) {
+int launch_hit_scan(Rays R, int n, int *d_hit_index, int *d_block_sums, int *d_nhit, cudaStream_t st, const int *n_dev) {
   // d_hit_index holds 2*n ints: [0,n) hit_index, [n,2n) hit_list
   const int nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
-  hit_count_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(R, n, d_block_sums);
+  hit_count_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(R, n, d_block_sums, n_dev);
   scan_block_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(d_block_sums, nblocks, d_nhit);
-  hit_index_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(R, n, d_block_sums, d_hit_index, d_hit_index + n);
+  hit_index_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(R, n, d_block_sums, d_hit_index, d_hit_index + n, n_dev);
   GXY_CUDA(cudaGetLastError());
   return 0;
 }
@@ -815,37 +822,42 @@ __global__ void __launch_bounds__(256)
 }
 
 int launch_shade_spawn(const DevLights &L, Rays R, int n, const int *d_hit_index, const int *d_nhit, Rays out, float epsilon,
-                       cudaStream_t st) {
-  // upper bounds for the grids (the exact hit count stays on the device)
+                       cudaStream_t st, int max_hits) {
+  // upper bounds for the grids (the exact hit count stays on the device); max_hits > 0: a tighter bound than the list's size
+  // (a list of capacity n never holds more PRIMARY rays than the image has pixels)
   if (n <= 0) return 0;
   if (ensure_ao_tables()) return 1;
   const int *hit_list = d_hit_index + n;
+  const int nh = max_hits > 0 && max_hits < n ? max_hits : n;
   if (L.n_ao > 0) {
-    const long long total = (long long)n * L.n_ao;
+    const long long total = (long long)nh * L.n_ao;
     const long long blocks = (total + 255) / 256;
     ao_spawn_kernel<<<(unsigned)blocks, 256, 0, st>>>(L, R, hit_list, d_nhit, out, epsilon);
   }
-  light_shadow_kernel<<<(n + 255) / 256, 256, 0, st>>>(L, R, hit_list, d_nhit, out, epsilon);
+  light_shadow_kernel<<<(nh + 255) / 256, 256, 0, st>>>(L, R, hit_list, d_nhit, out, epsilon);
   GXY_CUDA(cudaGetLastError());
   return 0;
 }
 
-__global__ void __launch_bounds__(256) classify_kernel(const __grid_constant__ SceneParams P, Rays R, int n) {
+__global__ void __launch_bounds__(256) classify_kernel(const __grid_constant__ SceneParams P, Rays R, int n, const int *__restrict__ n_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   R.classification[i] = classify_ray(P, R, i);
 }
 
-int launch_classify(const SceneParams &P, Rays R, int n, cudaStream_t st) {
+int launch_classify(const SceneParams &P, Rays R, int n, cudaStream_t st, const int *n_dev) {
   if (n <= 0) return 0;
-  classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(P, R, n);
+  classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(P, R, n, n_dev);
   GXY_CUDA(cudaGetLastError());
   return 0;
 }
 
 __global__ void __launch_bounds__(256)
-    accumulate_kernel(Rays R, int n, float *__restrict__ fb, int w, int h, unsigned long long *__restrict__ d_terminated) {
+    accumulate_kernel(Rays R, int n, float *__restrict__ fb, int w, int h, unsigned long long *__restrict__ d_terminated,
+                      const int *__restrict__ n_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   const bool term = i < n && R.classification[i] == CLS_TERMINATED;
   if (term) {
     const int x = R.x[i], y = R.y[i];
@@ -860,9 +872,9 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-int launch_accumulate(Rays R, int n, float *fb, int w, int h, unsigned long long *d_terminated, cudaStream_t st) {
+int launch_accumulate(Rays R, int n, float *fb, int w, int h, unsigned long long *d_terminated, cudaStream_t st, const int *n_dev) {
   if (n <= 0) return 0;
-  accumulate_kernel<<<(n + 255) / 256, 256, 0, st>>>(R, n, fb, w, h, d_terminated);
+  accumulate_kernel<<<(n + 255) / 256, 256, 0, st>>>(R, n, fb, w, h, d_terminated, n_dev);
   GXY_CUDA(cudaGetLastError());
   return 0;
 }
