@@ -1,4 +1,4 @@
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-GXY_PEER_TIMEOUT_MS=8000 timeout 600 $TR --master-port 29511 tools/mp_parity.py > gpurun_out/r2p_parity2.log 2>&1; echo "parity rc $?" >> gpurun_out/r2p_parity2.log
-GXY_VOLUME_FLIGHTS=1 GXY_PEER_TIMEOUT_MS=8000 timeout 600 $TR --master-port 29514 bench.py --gpus 2 --workload c3 --steps 16 --warmup 3 > gpurun_out/r2p_bench_c3_n2.json 2> gpurun_out/r2p_bench_c3_n2.err
-GXY_VOLUME_FLIGHTS=1 GXY_PEER_TIMEOUT_MS=8000 timeout 600 $TR --master-port 29515 bench.py --gpus 2 --workload c4 --steps 16 --warmup 3 > gpurun_out/r2p_bench_c4_n2.json 2> gpurun_out/r2p_bench_c4_n2.err
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2r_tests.log 2>&1; echo "tests rc $?" >> gpurun_out/r2r_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2r_smoke.log 2>&1; echo "smoke rc $?" >> gpurun_out/r2r_smoke.log
+timeout 400 python bench.py --workload c3 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2r_bench_c3.json 2> gpurun_out/r2r_bench_c3.err
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/r2r_bench.json 2> gpurun_out/r2r_bench.err
