@@ -286,8 +286,9 @@ int  gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *, const gxy
  * for gxy_frame_download_*.  Every slot owns its queues, framebuffer and (one process per GPU) peer arena: frames on
  * different slots overlap on the device, and a barrier a rank waits at in one frame costs latency, not throughput.
  * With a communicator attached the calls are collective: every rank submits and waits for the same slots in the same order.
- * Geometry-only Visualizations are enqueued without any host round trip; all others (volumes, PathLines, several partitions
- * in one process) render synchronously inside the submit call and hand their image over at the wait.
+ * Enqueued without any host round trip: geometry-only Visualizations (one GPU, or one process per GPU) and, with one process per
+ * GPU, Visualizations with volumes; everything else (volumes on one GPU, PathLines, several partitions in one process) renders
+ * synchronously inside the submit call and hands its image over at the wait.
  * gxy_render == submit + wait on slot 0. */
 int  gxy_render_submit(int nparts, gxy_vis *const *parts, const gxy_camera *, const gxy_lighting *, int w, int h,
                        float epsilon, int slot);
