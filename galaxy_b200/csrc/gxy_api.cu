@@ -2597,6 +2597,12 @@ int gxy_render_wait(int nparts, gxy_vis *const *parts, int slot, gxy_stats *stat
 
 int gxy_render_max_slots(void) { return GXY_MAX_FLIGHTS; }
 
+int gxy_debug_tile_rect(const gxy_camera *cam, int w, int h, const float lo[3], const float hi[3], int rect[4]) {
+  if (!cam || !lo || !hi || !rect || w <= 0 || h <= 0) return -1;
+  const DevCamera C = make_dev_camera(*cam, w, h);
+  return peer_tile_rect(C, lo, hi, w, h, rect) ? 1 : 0;
+}
+
 int gxy_render(int nparts, gxy_vis *const *parts, const gxy_camera *cam, const gxy_lighting *lights_in, int w, int h, float epsilon,
                gxy_stats *stats) {
   GXY_CHECK(nparts >= 1 && parts && cam && lights_in && w > 0 && h > 0, "gxy_render: bad arguments");

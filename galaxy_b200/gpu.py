@@ -133,6 +133,7 @@ def lib():
         L.gxy_render_submit.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(Camera), C.POINTER(Lighting), C.c_int, C.c_int, C.c_float, C.c_int]
         L.gxy_render_wait.argtypes = [C.c_int, C.POINTER(vp), C.c_int, C.POINTER(Stats)]
         L.gxy_context_mark.argtypes = [vp]
+        L.gxy_debug_tile_rect.argtypes = [C.POINTER(Camera), C.c_int, C.c_int, fp, fp, ip]
         L.gxy_frame_download_rgba32f.argtypes = [vp, fp]
         L.gxy_frame_download_rgba8.argtypes = [vp, C.POINTER(C.c_ubyte)]
         L.gxy_frame_download_rgba8_async.argtypes = [vp, C.POINTER(C.c_ubyte)]
@@ -517,6 +518,14 @@ def render_wait(parts, slot=0):
     st = Stats()
     check(lib().gxy_render_wait(len(parts), arr, slot, C.byref(st)))
     return st.as_dict()
+
+
+def debug_tile_rect(camera, w, h, lo, hi):
+    """(valid, (x0, y0, nx, ny)) in 8x4-pixel tiles: where a rank with partition box [lo, hi] generates primaries (host arithmetic)"""
+    cam = make_camera(camera)
+    lo, hi, rect = _f32(lo), _f32(hi), np.zeros(4, np.int32)
+    rc = lib().gxy_debug_tile_rect(C.byref(cam), w, h, _f(lo), _f(hi), _i(rect))
+    return rc, tuple(int(x) for x in rect)
 
 
 def max_slots():

@@ -294,6 +294,10 @@ int  gxy_render_submit(int nparts, gxy_vis *const *parts, const gxy_camera *, co
                        float epsilon, int slot);
 int  gxy_render_wait(int nparts, gxy_vis *const *parts, int slot, gxy_stats *stats);
 int  gxy_render_max_slots(void);
+/* Diagnostic (host arithmetic only, no device): the rectangle of 8x4-pixel tiles (x0, y0, nx, ny) over which a rank whose partition box
+ * is [lo, hi] generates primary rays on the multi-process frame path -- every pixel whose ray touches the box must lie inside it.
+ * Returns 1 (rect valid), 0 (a corner of the box is at or behind the eye plane: the whole image is scanned), -1 (bad arguments). */
+int  gxy_debug_tile_rect(const gxy_camera *, int w, int h, const float lo[3], const float hi[3], int rect[4]);
 /* D2H of the last frame: float RGBA (y up) ... */
 int  gxy_frame_download_rgba32f(gxy_vis *owner, float *fb);
 /* ... or RGBA8 rows top-down exactly as ColorImageWriter::Write does (ImageWriter.cpp:30-48) */
