@@ -991,7 +991,7 @@ static int check_error_flag(gxy_vis *v) {
   GXY_CUDA(cudaMemcpyAsync(&e, v->d_error, sizeof(int), cudaMemcpyDeviceToHost, v->ctx->stream));
   GXY_CUDA(cudaStreamSynchronize(v->ctx->stream));
   if (e != 0) GXY_CUDA(cudaMemsetAsync(v->d_error, 0, sizeof(int), v->ctx->stream));  // reported once
-  GXY_CHECK(e == 0, "device error flag %d (1: BVH traversal stack overflow, 3: ray list / inbox capacity, 4: peer barrier timeout, 6: TMA copy did not complete)", e);
+  GXY_CHECK(e == 0, "device error flag %d (1: BVH traversal stack overflow, 3: ray list / inbox capacity, 4: peer barrier timeout, 6: TMA copy did not complete, 7: translucent surface on the fused path)", e);
   return 0;
 }
 
@@ -1054,7 +1054,7 @@ struct LaneGuard {
     GXY_CUDA(cudaMemcpyAsync(&e, l->err.p, sizeof(int), cudaMemcpyDeviceToHost, l->st));
     GXY_CUDA(cudaStreamSynchronize(l->st));
     if (e != 0) GXY_CUDA(cudaMemsetAsync(l->err.p, 0, sizeof(int), l->st));  // reported once
-    GXY_CHECK(e == 0, "device error flag %d (1: BVH traversal stack overflow, 3: ray list / inbox capacity, 4: peer barrier timeout, 6: TMA copy did not complete)", e);
+    GXY_CHECK(e == 0, "device error flag %d (1: BVH traversal stack overflow, 3: ray list / inbox capacity, 4: peer barrier timeout, 6: TMA copy did not complete, 7: translucent surface on the fused path)", e);
     return 0;
   }
 };
@@ -1076,6 +1076,10 @@ static int trace_list_on_lane(gxy_vis *v, LaneGuard &G, const gxy_lighting *ligh
   GXY_CHECK(n_out < (1ll << 31), "secondary ray list too large (%lld)", n_out);
   const DevLights L = make_dev_lights(*lights);
   if (sec.reserve((size_t)std::max<long long>(n_out, 1), false, st)) return 1;
+  // the spawn kernels write the 16 columns generateAORays / the shadow-ray loop set (TraceRays.ispc:645-857); the others (normal,
+  // surface colour, sample, classification) are undefined in the reference's fresh RayList -- zero here, so that a list handed
+  // back to the caller is a function of its inputs alone and carries no stale device memory
+  if (n_out > 0) GXY_CUDA(cudaMemset2DAsync(sec.base, sec.cap * 4, 0, (size_t)n_out * 4, GXY_RAYLIST_COLUMNS, st));
   if (launch_shade_spawn(L, rays.v, n, l.hit_index.p, l.small.p, sec.v, epsilon, st)) return 1;
   *n_sec = n_out;
   (void)v;
@@ -2028,7 +2032,7 @@ static int flight_wait(gxy_vis *v, Flight &F, gxy_stats *stats) {
       }
       err = F.h_tail->error;
     }
-    GXY_CHECK(err == 0, "device error flag %d (1: BVH traversal stack overflow, 3: ray list / inbox capacity, 4: peer barrier timeout, 6: TMA copy did not complete)", err);
+    GXY_CHECK(err == 0, "device error flag %d (1: BVH traversal stack overflow, 3: ray list / inbox capacity, 4: peer barrier timeout, 6: TMA copy did not complete, 7: translucent surface on the fused path)", err);
     gxy_stats &S = F.S;
     FusedQueues t = F.h_tail->q[0];
     if (F.volume) memset(&t, 0, sizeof t);
@@ -2115,10 +2119,32 @@ static int render_sync(int nparts, gxy_vis *const *parts, const gxy_camera *cam,
   memset(&S, 0, sizeof S);
   PhaseTimer PT;
 
-  cudaEvent_t ev0, ev1;
+  struct FrameEvents {  // destroyed on every return path
+    cudaEvent_t a = nullptr, b = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace;
+    ~FrameEvents()
+    {
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+      for (auto &e : trace) {
+        if (e.first) cudaEventDestroy(e.first);
+        if (e.second) cudaEventDestroy(e.second);
+      }
+    }
+    int new_pair(cudaEvent_t *ta, cudaEvent_t *tb)  // owned from creation on
+    {
+      trace.push_back(std::make_pair((cudaEvent_t) nullptr, (cudaEvent_t) nullptr));
+      GXY_CUDA(cudaEventCreate(&trace.back().first));
+      GXY_CUDA(cudaEventCreate(&trace.back().second));
+      *ta = trace.back().first;
+      *tb = trace.back().second;
+      return 0;
+    }
+  } FE;
   if (use_device(ctx0)) return 1;
-  GXY_CUDA(cudaEventCreate(&ev0));
-  GXY_CUDA(cudaEventCreate(&ev1));
+  GXY_CUDA(cudaEventCreate(&FE.a));
+  GXY_CUDA(cudaEventCreate(&FE.b));
+  cudaEvent_t &ev0 = FE.a, &ev1 = FE.b;
   GXY_CUDA(cudaEventRecord(ev0, ctx0->stream));
 
   std::vector<int> n_cur(nparts, 0);
@@ -2131,7 +2157,7 @@ static int render_sync(int nparts, gxy_vis *const *parts, const gxy_camera *cam,
     for (int p = 0; p < nparts; p++)
       for (const GeomOp &g : parts[p]->geoms) fused = fused && g.kind != 2;
   if (const char *e = getenv("GXY_FUSED")) fused = fused && atoi(e) != 0;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_events;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &trace_events = FE.trace;
   for (int p = 0; p < nparts; p++) {
     gxy_vis *v = parts[p];
     if (use_device(v->ctx)) return 1;
@@ -2164,8 +2190,7 @@ static int render_sync(int nparts, gxy_vis *const *parts, const gxy_camera *cam,
       if (v->cur.reserve(can_spill[p] ? (size_t)npix : 64, false, st)) return 1;
       GXY_CUDA(cudaMemsetAsync(v->fq.p, 0, (size_t)n_bands * sizeof(FusedQueues), st));
       cudaEvent_t ta, tb;
-      GXY_CUDA(cudaEventCreate(&ta));
-      GXY_CUDA(cudaEventCreate(&tb));
+      if (FE.new_pair(&ta, &tb)) return 1;
       GXY_CUDA(cudaEventRecord(ta, st));
       {
         if (launch_fused_primary(v->P, C, L, w, h, v->fb.p, v->next.v, v->rawhits.p, (unsigned)qcap, v->hits.v, v->cur.v,
@@ -2176,7 +2201,6 @@ static int render_sync(int nparts, gxy_vis *const *parts, const gxy_camera *cam,
         S.waves++;
       }
       GXY_CUDA(cudaEventRecord(tb, st));
-      trace_events.push_back(std::make_pair(ta, tb));
     }
     PT.mark("launchP");
     // ---- secondary rays.  A partition without neighbours cannot spill: no host round trip at all.
@@ -2194,14 +2218,12 @@ static int render_sync(int nparts, gxy_vis *const *parts, const gxy_camera *cam,
         if (v->cur.reserve((size_t)(max_rays + fq[p].n_spill), true, st)) return 1;
       }
       cudaEvent_t ta, tb;
-      GXY_CUDA(cudaEventCreate(&ta));
-      GXY_CUDA(cudaEventCreate(&tb));
+      if (FE.new_pair(&ta, &tb)) return 1;
       GXY_CUDA(cudaEventRecord(ta, st));
       if (launch_fused_secondary(v->P, L, w, h, n_sec_per_hit, max_rays, v->fb.p, v->hits.v, v->cur.v, can_spill[p] ? (unsigned)v->cur.cap : 0u,
                                  reinterpret_cast<FusedQueues *>(v->fq.p), epsilon, !v->has_dvr, nullptr, 0, st))
         return 1;
       GXY_CUDA(cudaEventRecord(tb, st));
-      trace_events.push_back(std::make_pair(ta, tb));
       S.kernel_launches += 1;
       S.waves++;
     }
@@ -2263,8 +2285,7 @@ static int render_sync(int nparts, gxy_vis *const *parts, const gxy_camera *cam,
       if (use_device(v->ctx)) return 1;
       cudaStream_t st = v->ctx->stream;
       cudaEvent_t ta, tb;
-      GXY_CUDA(cudaEventCreate(&ta));
-      GXY_CUDA(cudaEventCreate(&tb));
+      if (FE.new_pair(&ta, &tb)) return 1;
       GXY_CUDA(cudaEventRecord(ta, st));
       // GXY_MARCH_TMA=1: the primaries (compact 16x8-pixel beams) of a one-volume scene go through the TMA-staged march
       const bool tma = wave == 0 && march_tma_on() && march_tma_eligible(v->P);
@@ -2274,7 +2295,6 @@ static int render_sync(int nparts, gxy_vis *const *parts, const gxy_camera *cam,
         if (launch_march_tma(v->P, v->cur.v, n, epsilon, axis, v->counters.p + 1, v->counters.p + 2, st)) return 1;
       } else if (launch_trace(v->P, v->cur.v, n, epsilon, nullptr, !v->has_dvr, v->counters.p + 1, st)) return 1;
       GXY_CUDA(cudaEventRecord(tb, st));
-      trace_events.push_back(std::make_pair(ta, tb));
       if (v->hit_index.reserve((size_t)2 * n) || v->block_sums.reserve((size_t)n / 1024 + 2)) return 1;
       if (launch_hit_scan(v->cur.v, n, v->hit_index.p, v->block_sums.p, v->small.p, st)) return 1;
       S.kernel_launches += 4;
@@ -2468,15 +2488,11 @@ static int render_sync(int nparts, gxy_vis *const *parts, const gxy_camera *cam,
   PT.report(rank0);
   if (PT.on) fprintf(stderr, "[gxy_render rank %d] waves=%lld traced=%lld forwarded=%lld\n", rank0, S.waves, S.traced_rays, S.forwarded_rays);
   cudaEventElapsedTime(&S.device_ms, ev0, ev1);
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
   for (auto &e : trace_events) {
     float ms = 0.f;
     cudaEventSynchronize(e.second);
     cudaEventElapsedTime(&ms, e.first, e.second);
     S.trace_ms += ms;
-    cudaEventDestroy(e.first);
-    cudaEventDestroy(e.second);
   }
   for (int p = 0; p < nparts; p++) {
     gxy_vis *v = parts[p];
@@ -2488,7 +2504,7 @@ static int render_sync(int nparts, gxy_vis *const *parts, const gxy_camera *cam,
     S.staged_samples += (long long)t.counters[2];
     S.nodes_visited += (long long)t.trav[0];
     S.prims_tested += (long long)t.trav[1];
-    GXY_CHECK(t.error == 0, "device error flag %d (1: BVH traversal stack overflow, 3: ray list / inbox capacity, 4: peer barrier timeout, 6: TMA copy did not complete)", t.error);
+    GXY_CHECK(t.error == 0, "device error flag %d (1: BVH traversal stack overflow, 3: ray list / inbox capacity, 4: peer barrier timeout, 6: TMA copy did not complete, 7: translucent surface on the fused path)", t.error);
   }
   if (stats) *stats = S;
   return 0;

@@ -484,6 +484,10 @@ __global__ void __launch_bounds__(256)
     if (cls == CLS_TERMINATED) {
       n_term++;
       atomicAdd(fb + ((size_t)hp.py * w + hp.px), make_float4(r, g, b, o));
+    } else if (cls == CLS_KEEP_HERE) {
+      // a translucent surface (opacity <= 0.999): the reference re-queues the primary behind the hit (Renderer.cpp:304-421); this
+      // path has no keeper list, and no shader here produces one today (shade_geometry_hit: opacity 1) -- refuse rather than lose it
+      *P.error_flag = 7;
     }
     hits.ox[hidx] = hp.ox; hits.oy[hidx] = hp.oy; hits.oz[hidx] = hp.oz;
     hits.dx[hidx] = hp.dx; hits.dy[hidx] = hp.dy; hits.dz[hidx] = hp.dz;

@@ -2,6 +2,7 @@
 // frame kernels (gxy_fused.cu): ray generation, box clipping, postIntersect shading, lighting and
 // secondary-ray construction, classification.  Every function restates the reference lines it cites.
 #pragma once
+#include <mutex>
 #include "gxy_traverse.cuh"
 
 #include <math.h>
@@ -128,7 +129,13 @@ static void halton_tables(float U[256], float V[256]) {
 }
 
 static int ensure_ao_tables() {
-  static bool done = false;
+  // __constant__ memory is per device: one upload for each device this process drives (a process may hold several contexts)
+  static std::mutex mu;
+  static bool done_on[64] = {};
+  int dev = 0;
+  GXY_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  bool &done = done_on[dev & 63];
   if (done) return 0;
   float U[256], V[256], x[256], y[256], z[256];
   halton_tables(U, V);

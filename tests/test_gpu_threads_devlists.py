@@ -24,6 +24,14 @@ def _scene(gpu, backend):
     return scenes.build_partitions(backend, vis, {"tris": tri, "parts": par}, 1)[0], vis
 
 
+def _diff(a, b):
+    """which columns of two (columns, n) arrays differ, in how many rays, and the first such ray"""
+    bad = a.view(np.int32) != b.view(np.int32)
+    cols = np.nonzero(bad.any(axis=1))[0]
+    rays = np.nonzero(bad.any(axis=0))[0]
+    return {"columns": cols.tolist(), "n_rays": int(rays.size), "first_ray": int(rays[0]) if rays.size else -1, "of": int(a.shape[1])}
+
+
 def test_five_threads_trace_on_one_visualization(gpu):
     """5 threads x 6 calls each, every thread its own RayList (different cameras and sizes): every result equals the result of the
     same call made alone (bit for bit: the trace is deterministic per list), nothing leaks between the lanes."""
@@ -51,10 +59,11 @@ def test_five_threads_trace_on_one_visualization(gpu):
                 g.classify(r, n)
                 ref = alone[k]
                 assert ns == ref[2], (k, ns, ref[2])
-                assert np.array_equal(r[:, :n].view(np.int32), ref[0][:, :n].view(np.int32)), k
-                assert np.array_equal(hits, ref[3]), k
+                assert np.array_equal(hits, ref[3]), (k, "hit ids", _diff(hits.T, ref[3].T))
+                assert np.array_equal(r[:, :n].view(np.int32), ref[0][:, :n].view(np.int32)), (k, "rays", _diff(r[:, :n], ref[0][:, :n]))
                 if ns:
-                    assert np.array_equal(sec[:, :ns].view(np.int32), ref[1][:, :ns].view(np.int32)), k
+                    assert np.array_equal(sec[:, :ns].view(np.int32), ref[1][:, :ns].view(np.int32)), (k, "secondaries",
+                                                                                                         _diff(sec[:, :ns], ref[1][:, :ns]))
         except Exception as e:  # noqa: BLE001
             errors.append((k, repr(e)))
 
