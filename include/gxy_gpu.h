@@ -16,6 +16,10 @@
  *  - host buffers passed in are copied to the device at create/commit time (the reference shares
  *    them, OSP_DATA_SHARED_BUFFER, OsprayVolume.cpp:36-37); the device owns its copy.
  *  - there is NO CPU fallback: if no CUDA device is usable every compute entry fails loudly.
+ *  - kernels report through a device error flag that the entry point reads before it returns ("device error flag N" in
+ *    gxy_last_error(); the flag is cleared once reported): 1 BVH traversal stack overflow, 3 ray list / inbox capacity
+ *    exceeded, 4 peer barrier timeout, 6 TMA copy did not complete, 7 translucent surface (opacity <= 0.999) on the
+ *    fused frame path, which has no keeper list (no shader produces one today).
  */
 #ifndef GXY_GPU_H
 #define GXY_GPU_H
@@ -197,7 +201,9 @@ void gxy_partition(int n, const int factors[3], const int grid[3], int *out);
  * _ambientLighting + _generateAORays + _diffuseLighting + _generateShadowRays
  * (TraceRays.ispc:326,625,735,763,859).  rays (host) are traced in place; *out receives the
  * SECONDARY list (NULL if no ray was spawned), library-owned.  lights must be resolved.
- * hit_ids (may be NULL): 2 ints per ray, nearest-hit (geomID, primID) or (-1,-1). */
+ * hit_ids (may be NULL): 2 ints per ray, nearest-hit (geomID, primID) or (-1,-1).
+ * Of the secondary list the 16 columns generateAORays / the shadow-ray loop set are defined (ox..dz r g b o t tMax x y type term);
+ * the reference leaves the other 9 uninitialised, here they are 0, so the list is a function of the call's inputs alone. */
 int  gxy_trace_raylist(gxy_vis *, const gxy_lighting *lights, gxy_raylist_view rays, float epsilon,
                        gxy_raylist **out, int *hit_ids);
 int  gxy_raylist_get_view(gxy_raylist *, gxy_raylist_view *view);
