@@ -598,7 +598,7 @@ def main():
             "rays_per_frame": int(rays_total), "traced_rays_per_frame": int(traced_total / args.steps),
             "dequeued_rays_per_frame": int(dequeued_total / args.steps), "wall_ms_per_step": t_wall / args.steps * 1e3,
             "frames_in_flight": depth, "frame_latency_ms": latency_ms,
-            "scene": {"triangles_this_rank": n_tris_local, "bvh_nodes": info["n_nodes"], "bvh_build_ms": info["build_ms"], "mesh_gen_s": t_gen,
+            "scene": {"triangles_this_rank": n_tris_local, "bvh_nodes": info["n_nodes"], "bvh_build_ms": info["build_ms"], "bvh_build_alloc_host_ms": info.get("alloc_host_ms"), "mesh_gen_s": t_gen,
                       "commit_s": t_commit}}
     if parity is not None:
         line["parity"] = parity

@@ -844,6 +844,12 @@ int gxy_vis_build_info(gxy_vis *v, long long *n_prims, long long *n_nodes, float
   if (build_ms) *build_ms = v->bvh.build_ms;
   return 0;
 }
+int gxy_vis_build_times(gxy_vis *v, float *build_ms, float *alloc_host_ms) {
+  GXY_CHECK(v, "NULL visualization");
+  if (build_ms) *build_ms = v->bvh.build_ms;
+  if (alloc_host_ms) *alloc_host_ms = v->bvh.alloc_host_ms;
+  return 0;
+}
 
 // ---- host helpers ------------------------------------------------------------------------------
 struct H3 { float x, y, z; };

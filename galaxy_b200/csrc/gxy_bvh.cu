@@ -13,6 +13,7 @@
 //      octant order; the internal children of a node get consecutive node ids (in slot order)
 //      and its leaf primitives consecutive record positions (compressed-wide-BVH addressing)
 //   5. primitive records (48 B: v0,e1,e2 | centre,radius + ids) written in node order
+#include <chrono>
 #include "gxy_internal.h"
 #include "gxy_curve.cuh"
 
@@ -393,11 +394,41 @@ __global__ void __launch_bounds__(256)
   out[dest_of[s]] = r;
 }
 
+// The build allocates and releases its multi-GB buffers one by one (peak memory stays near the result's size); the host time
+// the driver spends in those calls lies inside the build's event pair, so it is accounted for separately (BvhResult::alloc_host_ms).
+static thread_local double t_alloc_ms = 0.0;
+struct AllocClock {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  ~AllocClock() { t_alloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+template <typename T>
+static cudaError_t timed_malloc(T **p, size_t bytes) {
+  AllocClock c;
+  return cudaMalloc(p, bytes);
+}
+static void timed_free(void *p) {
+  AllocClock c;
+  cudaFree(p);
+}
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  int alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * (n ? n : 1)) == cudaSuccess ? 0 : 1; }
+  ~DevBuf() { if (p) timed_free(p); }
+  int alloc(size_t n) { return timed_malloc(&p, sizeof(T) * (n ? n : 1)) == cudaSuccess ? 0 : 1; }
+};
+
+// bump allocator over one device allocation (sizing pass with base == nullptr, then the real one)
+struct BuildArena {
+  char *base = nullptr;
+  size_t off = 0;
+  ~BuildArena() { if (base) timed_free(base); }
+  static size_t up(size_t b) { return (b + 255) & ~(size_t)255; }
+  template <typename T>
+  T *take(size_t count) {
+    T *q = reinterpret_cast<T *>(reinterpret_cast<uintptr_t>(base) + off);  // base == nullptr: the sizing pass
+    off += up(sizeof(T) * (count ? count : 1));
+    return q;
+  }
 };
 
 int build_bvh(const GeomBuildInput *geoms, int n_geoms, BvhResult *out, cudaStream_t st) {
@@ -414,17 +445,51 @@ int build_bvh(const GeomBuildInput *geoms, int n_geoms, BvhResult *out, cudaStre
   GXY_CUDA(cudaEventCreate(&e0));
   GXY_CUDA(cudaEventCreate(&e1));
   GXY_CUDA(cudaEventRecord(e0, st));
+  t_alloc_ms = 0.0;
   const int n = (int)N;
   const unsigned gridN = (unsigned)((N + 255) / 256);
 
-  DevBuf<float4> lo, hi, slo, shi, nlo, nhi;
-  DevBuf<unsigned> bounds, vals, vals2;
-  DevBuf<unsigned long long> keys, keys2, cnt;
-  DevBuf<int2> child, range;
-  DevBuf<int> parent_int, parent_leaf, flags, wide_bin, counter, err;
-  if (lo.alloc(N) || hi.alloc(N) || bounds.alloc(6) || keys.alloc(N) || keys2.alloc(N) || vals.alloc(N) || vals2.alloc(N)) {
-    gxy_set_error("BVH build: out of device memory"); return 1;
+  // One arena for all the scratch whose size follows from N alone (bump allocation, released once at the end): the driver's time for
+  // ~25 separate multi-GB cudaMalloc / cudaFree calls inside the build varied between 50 and 500 ms from run to run against ~40 ms
+  // of kernels (profiles/r02_m_bvh_build_probe_before.txt).  nlo/nhi (node boxes, first written by the refit) take the place of
+  // lo/hi (primitive boxes in input order, dead once gathered into sorted order).
+  size_t tmp_bytes = 0;
+  {
+    cub::DoubleBuffer<unsigned long long> qk(nullptr, nullptr);
+    cub::DoubleBuffer<unsigned> qv(nullptr, nullptr);
+    GXY_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, qk, qv, n, 0, 63, st));
   }
+  BuildArena arena;
+  float4 *lo_p = nullptr, *hi_p = nullptr, *slo_p = nullptr, *shi_p = nullptr;
+  unsigned *bounds_p = nullptr, *vals_p = nullptr, *vals2_p = nullptr, *dest_of_p = nullptr, *prim_counter_p = nullptr;
+  unsigned long long *keys_p = nullptr, *keys2_p = nullptr, *cnt_p = nullptr;
+  unsigned char *tmp_p = nullptr;
+  int2 *child_p = nullptr, *range_p = nullptr;
+  int *parent_int_p = nullptr, *parent_leaf_p = nullptr, *flags_p = nullptr, *counter_p = nullptr, *err_p = nullptr;
+  for (int pass = 0; pass < 2; pass++) {
+    arena.off = 0;
+    lo_p = arena.take<float4>(N); hi_p = arena.take<float4>(N);
+    slo_p = arena.take<float4>(N); shi_p = arena.take<float4>(N);
+    bounds_p = arena.take<unsigned>(6);
+    keys_p = arena.take<unsigned long long>(N); keys2_p = arena.take<unsigned long long>(N);
+    vals_p = arena.take<unsigned>(N); vals2_p = arena.take<unsigned>(N);
+    tmp_p = arena.take<unsigned char>(tmp_bytes);
+    dest_of_p = arena.take<unsigned>(N); prim_counter_p = arena.take<unsigned>(1);
+    child_p = arena.take<int2>(N); range_p = arena.take<int2>(N);
+    parent_int_p = arena.take<int>(N); parent_leaf_p = arena.take<int>(N); flags_p = arena.take<int>(N);
+    cnt_p = arena.take<unsigned long long>(1); counter_p = arena.take<int>(1); err_p = arena.take<int>(1);
+    if (pass == 0 && timed_malloc(&arena.base, arena.off) != cudaSuccess) {
+      cudaGetLastError();
+      gxy_set_error("BVH build: out of device memory (%zu bytes of scratch for %lld primitives)", arena.off, N);
+      return 1;
+    }
+  }
+  struct { float4 *p; } lo{lo_p}, hi{hi_p}, slo{slo_p}, shi{shi_p}, nlo{lo_p}, nhi{hi_p};
+  struct { unsigned *p; } bounds{bounds_p}, vals{vals_p}, vals2{vals2_p}, dest_of{dest_of_p}, prim_counter{prim_counter_p};
+  struct { unsigned long long *p; } keys{keys_p}, keys2{keys2_p}, cnt{cnt_p};
+  struct { int2 *p; } child{child_p}, range{range_p};
+  struct { int *p; } parent_int{parent_int_p}, parent_leaf{parent_leaf_p}, flags{flags_p}, counter{counter_p}, err{err_p};
+  DevBuf<int> wide_bin;
   const unsigned init_bounds[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
   GXY_CUDA(cudaMemcpyAsync(bounds.p, init_bounds, sizeof init_bounds, cudaMemcpyHostToDevice, st));
   prim_bounds_kernel<<<gridN, 256, 0, st>>>(B, N, lo.p, hi.p, bounds.p);
@@ -433,27 +498,17 @@ int build_bvh(const GeomBuildInput *geoms, int n_geoms, BvhResult *out, cudaStre
   {
     cub::DoubleBuffer<unsigned long long> dk(keys.p, keys2.p);
     cub::DoubleBuffer<unsigned> dv(vals.p, vals2.p);
-    size_t tmp_bytes = 0;
-    GXY_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, n, 0, 63, st));
-    DevBuf<unsigned char> tmp;
-    if (tmp.alloc(tmp_bytes)) { gxy_set_error("BVH build: out of device memory"); return 1; }
-    GXY_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, dk, dv, n, 0, 63, st));
+    GXY_CUDA(cub::DeviceRadixSort::SortPairs(tmp_p, tmp_bytes, dk, dv, n, 0, 63, st));
     GXY_CUDA(cudaStreamSynchronize(st));
     if (dk.Current() != keys.p) std::swap(keys.p, keys2.p);
     if (dv.Current() != vals.p) std::swap(vals.p, vals2.p);
   }
-  cudaFree(keys2.p); keys2.p = nullptr;
-  cudaFree(vals2.p); vals2.p = nullptr;
-  if (slo.alloc(N) || shi.alloc(N)) { gxy_set_error("BVH build: out of device memory"); return 1; }
   gather_boxes_kernel<<<gridN, 256, 0, st>>>(N, vals.p, lo.p, hi.p, slo.p, shi.p);
   GXY_CUDA(cudaStreamSynchronize(st));
-  cudaFree(lo.p); lo.p = nullptr;
-  cudaFree(hi.p); hi.p = nullptr;
 
   PrimRec *prims = nullptr;
-  GXY_CUDA(cudaMalloc(&prims, sizeof(PrimRec) * N));
-  DevBuf<unsigned> dest_of, prim_counter;  // sorted position -> record position (node order)
-  if (dest_of.alloc(N) || prim_counter.alloc(1)) { cudaFree(prims); gxy_set_error("BVH build: out of device memory"); return 1; }
+  GXY_CUDA(timed_malloc(&prims, sizeof(PrimRec) * N));
+  // dest_of: sorted position -> record position (node order)
   GXY_CUDA(cudaMemsetAsync(prim_counter.p, 0, sizeof(unsigned), st));
 
   WideNode *nodes = nullptr;
@@ -487,15 +542,11 @@ int build_bvh(const GeomBuildInput *geoms, int n_geoms, BvhResult *out, cudaStre
     const unsigned ident[LEAF_MAX] = {0u, 1u, 2u};
     GXY_CUDA(cudaMemcpyAsync(dest_of.p, ident, sizeof(unsigned) * n, cudaMemcpyHostToDevice, st));
     GXY_CUDA(cudaStreamSynchronize(st));
-    GXY_CUDA(cudaMalloc(&nodes, sizeof(WideNode)));
+    GXY_CUDA(timed_malloc(&nodes, sizeof(WideNode)));
     GXY_CUDA(cudaMemcpy(nodes, &nd, sizeof nd, cudaMemcpyHostToDevice));
     n_nodes = 1;
     depth = 1;
   } else {
-    if (child.alloc(n) || range.alloc(n) || parent_int.alloc(n) || parent_leaf.alloc(n) || flags.alloc(n) || nlo.alloc(n) || nhi.alloc(n) ||
-        cnt.alloc(1) || counter.alloc(1) || err.alloc(1)) {
-      gxy_set_error("BVH build: out of device memory"); return 1;
-    }
     karras_kernel<<<(n - 1 + 255) / 256, 256, 0, st>>>(n, keys.p, child.p, range.p, parent_int.p, parent_leaf.p);
     GXY_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int) * n, st));
     refit_kernel<<<gridN, 256, 0, st>>>(n, child.p, parent_int.p, parent_leaf.p, slo.p, shi.p, nlo.p, nhi.p, flags.p);
@@ -504,13 +555,9 @@ int build_bvh(const GeomBuildInput *geoms, int n_geoms, BvhResult *out, cudaStre
     unsigned long long h_cnt = 0;
     GXY_CUDA(cudaMemcpyAsync(&h_cnt, cnt.p, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
     GXY_CUDA(cudaStreamSynchronize(st));
-    cudaFree(keys.p); keys.p = nullptr;
-    cudaFree(parent_int.p); parent_int.p = nullptr;
-    cudaFree(parent_leaf.p); parent_leaf.p = nullptr;
-    cudaFree(flags.p); flags.p = nullptr;
     const int capacity = (int)h_cnt + 1;
     WideNode *tmp_nodes = nullptr;
-    GXY_CUDA(cudaMalloc(&tmp_nodes, sizeof(WideNode) * (size_t)capacity));
+    GXY_CUDA(timed_malloc(&tmp_nodes, sizeof(WideNode) * (size_t)capacity));
     if (wide_bin.alloc(capacity)) { gxy_set_error("BVH build: out of device memory"); return 1; }
     const int zero = 0, one = 1;
     GXY_CUDA(cudaMemcpyAsync(wide_bin.p, &zero, sizeof(int), cudaMemcpyHostToDevice, st));  // wide 0 <- binary root 0
@@ -532,12 +579,12 @@ int build_bvh(const GeomBuildInput *geoms, int n_geoms, BvhResult *out, cudaStre
     }
     int h_err = 0;
     GXY_CUDA(cudaMemcpy(&h_err, err.p, sizeof(int), cudaMemcpyDeviceToHost));
-    if (h_err) { cudaFree(tmp_nodes); cudaFree(prims); gxy_set_error("BVH build: wide-node capacity exceeded"); return 1; }
+    if (h_err) { timed_free(tmp_nodes); timed_free(prims); gxy_set_error("BVH build: wide-node capacity exceeded"); return 1; }
     n_nodes = end;
-    GXY_CUDA(cudaMalloc(&nodes, sizeof(WideNode) * (size_t)n_nodes));
+    GXY_CUDA(timed_malloc(&nodes, sizeof(WideNode) * (size_t)n_nodes));
     GXY_CUDA(cudaMemcpyAsync(nodes, tmp_nodes, sizeof(WideNode) * (size_t)n_nodes, cudaMemcpyDeviceToDevice, st));
     GXY_CUDA(cudaStreamSynchronize(st));
-    cudaFree(tmp_nodes);
+    timed_free(tmp_nodes);
   }
   emit_prims_kernel<<<gridN, 256, 0, st>>>(B, N, vals.p, dest_of.p, prims);
   GXY_CUDA(cudaGetLastError());
@@ -547,7 +594,7 @@ int build_bvh(const GeomBuildInput *geoms, int n_geoms, BvhResult *out, cudaStre
   cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  out->nodes = nodes; out->prims = prims; out->n_nodes = n_nodes; out->n_prims = N; out->max_depth = depth; out->build_ms = ms;
+  out->nodes = nodes; out->prims = prims; out->n_nodes = n_nodes; out->n_prims = N; out->max_depth = depth; out->build_ms = ms; out->alloc_host_ms = (float)t_alloc_ms;
   return 0;
 }
 

@@ -184,7 +184,8 @@ struct BvhResult {
   PrimRec *prims = nullptr;
   long long n_nodes = 0, n_prims = 0;
   int max_depth = 0;
-  float build_ms = 0.f;
+  float build_ms = 0.f;       // CUDA events around the whole build (kernels + the waits for the host between them)
+  float alloc_host_ms = 0.f;  // host time spent inside cudaMalloc / cudaFree of the build's buffers within that span
 };
 int build_bvh(const GeomBuildInput *geoms, int n_geoms, BvhResult *out, cudaStream_t st);
 

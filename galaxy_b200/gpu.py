@@ -113,6 +113,7 @@ def lib():
         L.gxy_vis_add_particles.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(TransferFunction)]
         L.gxy_vis_commit.argtypes = [vp]
         L.gxy_vis_build_info.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), fp]
+        L.gxy_vis_build_times.argtypes = [vp, fp, fp]
         L.gxy_resolve_lights.argtypes = [C.POINTER(Lighting), C.POINTER(Camera), C.POINTER(Lighting)]
         L.gxy_resample_transfer_function.argtypes = [C.c_int, fp, C.c_int, fp, C.POINTER(TransferFunction)]
         L.gxy_factor.argtypes = [C.c_int, ip]
@@ -341,7 +342,9 @@ class Scene:
     def build_info(self):
         a, b, ms = C.c_longlong(), C.c_longlong(), C.c_float()
         check(lib().gxy_vis_build_info(self.h, C.byref(a), C.byref(b), C.byref(ms)))
-        return dict(n_prims=a.value, n_nodes=b.value, build_ms=ms.value)
+        al = C.c_float()
+        check(lib().gxy_vis_build_times(self.h, None, C.byref(al)))
+        return dict(n_prims=a.value, n_nodes=b.value, build_ms=ms.value, alloc_host_ms=al.value)
 
     # -- per-list entry points (TraceRays::Trace etc.) ------------------------------------------
     def trace_raylist(self, lighting, rays, n, epsilon=0.001, want_hits=False):

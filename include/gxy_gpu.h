@@ -176,6 +176,10 @@ int  gxy_vis_add_pathlines(gxy_vis *, gxy_pathlines *, float radius0, float radi
 int  gxy_vis_commit(gxy_vis *);
 /* build statistics of the last commit: primitives, wide nodes, build milliseconds */
 int  gxy_vis_build_info(gxy_vis *, long long *n_prims, long long *n_nodes, float *build_ms);
+/* build_ms again (CUDA events around the whole build) and the part of that span the host spent inside cudaMalloc / cudaFree of the
+ * build's buffers: the build allocates and releases ~25 buffers of up to 4.8 GB one by one, and the driver's time for that varies
+ * from run to run (tens to hundreds of milliseconds) while the kernels' does not */
+int  gxy_vis_build_times(gxy_vis *, float *build_ms, float *alloc_host_ms);
 
 /* ---- host-side helpers that the reference keeps in C++ ------------------------------------ */
 /* Rendering::resolve_lights (src/renderer/Rendering.cpp:157-216) */
