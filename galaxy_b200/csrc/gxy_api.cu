@@ -1246,13 +1246,82 @@ static int reserve_samples(gxy_vis *v, unsigned long long need, cudaStream_t st)
 // Sampler over a frame (Sampler.cpp:52-133 on top of Renderer::local_render / processRays): per wave and partition
 //   sample-trace (+ sample points) -> Classify -> counting sort by destination, KEEP_HERE rays (the ones that left a sample)
 //   back into the partition's own next list, BOUNDARY rays to the neighbour; until no partition has rays left.
+// One exchange step of the list path across processes (one process per GPU): all-gather of the per-destination counts, then the
+// 24 ray columns of every non-empty (source, destination) pair as NCCL send/recv on the context's stream, and the received rays
+// plus the ones that stay (destination = this rank) appended to v->next at *n_next.  *global_pending = rays alive anywhere after it.
+static int nccl_exchange_rays(gxy_vis *v, int nranks, int me, const int *send_counts, const int *send_offsets, int *n_next, long long *global_pending,
+                              gxy_stats &S) {
+  cudaStream_t st = v->ctx->stream;
+  if (v->io_i.reserve((size_t)nranks * (nranks + 1))) return 1;
+  int *d_mine = v->io_i.p, *d_all = v->io_i.p + nranks;
+  GXY_CUDA(cudaMemcpyAsync(d_mine, send_counts, sizeof(int) * nranks, cudaMemcpyHostToDevice, st));
+  GXY_NCCL(g_nccl.AllGather(d_mine, d_all, nranks, ncclInt32, v->ctx->comm, st));
+  std::vector<int> all((size_t)nranks * nranks, 0);
+  GXY_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(int) * nranks * nranks, cudaMemcpyDeviceToHost, st));
+  GXY_CUDA(cudaStreamSynchronize(st));
+  std::vector<int> recv_from(nranks, 0);
+  long long pending = 0;
+  int n_recv = 0;
+  for (int r = 0; r < nranks; r++) {
+    for (int d = 0; d < nranks; d++) pending += all[(size_t)r * nranks + d];
+    recv_from[r] = all[(size_t)r * nranks + me];
+    if (r != me) n_recv += recv_from[r];
+  }
+  for (int d = 0; d < nranks; d++)
+    if (d != me) S.forwarded_rays += send_counts[d];
+  if (n_recv && v->recv.reserve((size_t)n_recv, false, st)) return 1;
+  bool any = false;
+  for (int r = 0; r < nranks; r++) any = any || (r != me && (recv_from[r] || send_counts[r]));
+  if (any) {
+    GXY_NCCL(g_nccl.GroupStart());
+    int roff = 0;
+    for (int r = 0; r < nranks; r++) {
+      if (r == me) continue;
+      if (send_counts[r])
+        for (int c = 0; c < 24; c++)
+          GXY_NCCL(g_nccl.Send(v->send.base + (size_t)c * v->send.cap + send_offsets[r], send_counts[r], ncclFloat32, r, v->ctx->comm, st));
+      if (recv_from[r])
+        for (int c = 0; c < 24; c++)
+          GXY_NCCL(g_nccl.Recv(v->recv.base + (size_t)c * v->recv.cap + roff, recv_from[r], ncclFloat32, r, v->ctx->comm, st));
+      roff += recv_from[r];
+    }
+    GXY_NCCL(g_nccl.GroupEnd());
+  }
+  const int total = n_recv + recv_from[me];
+  if (total) {
+    if (v->next.reserve((size_t)*n_next + total, true, st)) return 1;
+    if (recv_from[me]) {
+      if (launch_copy_rays(v->next.v, (size_t)*n_next, v->send.v, (size_t)send_offsets[me], recv_from[me], st)) return 1;
+      *n_next += recv_from[me];
+      S.kernel_launches += 1;
+    }
+    int roff = 0;
+    for (int r = 0; r < nranks; r++) {
+      if (r == me || !recv_from[r]) continue;
+      if (launch_copy_rays(v->next.v, (size_t)*n_next, v->recv.v, (size_t)roff, recv_from[r], st)) return 1;
+      *n_next += recv_from[r];
+      roff += recv_from[r];
+      S.kernel_launches += 1;
+    }
+  }
+  *global_pending = pending;
+  return 0;
+}
+
 int gxy_sample(int nparts, gxy_vis *const *parts, const gxy_camera *cam, int w, int h, gxy_stats *stats) {
   GXY_CHECK(nparts >= 1 && parts && cam && w > 0 && h > 0, "gxy_sample: bad arguments");
   for (int p = 0; p < nparts; p++) {
     if (check_vis(parts[p])) return 1;
     GXY_CHECK(!parts[p]->samplers.empty(), "gxy_sample: partition %d holds no sampler operator", p);
-    GXY_CHECK(parts[p]->ctx->comm == nullptr, "gxy_sample drives all partitions from one process (no communicator)");
   }
+  // one process per GPU (gxy_comm_init): this rank's partition is parts[0], rays that cross into a neighbour travel as NCCL
+  // send/recv pairs of their 24 columns, every rank takes part in every wave until no ray is left anywhere (Sampler.cpp:52-133
+  // runs on the Renderer's ray queues and message layer; src/sampler/Sampler.h)
+  const bool multi_proc = parts[0]->ctx->comm != nullptr;
+  GXY_CHECK(!multi_proc || nparts == 1, "gxy_sample: with a communicator every process passes its one partition");
+  for (int p = 0; p < nparts; p++) GXY_CHECK((parts[p]->ctx->comm != nullptr) == multi_proc, "gxy_sample: partitions with and without a communicator");
+  const int nd = multi_proc ? parts[0]->ctx->nranks : nparts;  // destinations of a forwarded ray
+  const int me = multi_proc ? parts[0]->ctx->rank : 0;
   const DevCamera C = make_dev_camera(*cam, w, h);
   const int npix = w * h;
   gxy_stats S;
@@ -1278,7 +1347,7 @@ int gxy_sample(int nparts, gxy_vis *const *parts, const gxy_camera *cam, int w, 
     if (use_device(v->ctx)) return 1;
     cudaStream_t st = v->ctx->stream;
     const int npix_pad = ((w + 15) / 16) * ((h + 7) / 8) * 128;
-    if (v->block_sums.reserve((size_t)std::max(npix_pad, 1 << 20) / 1024 + 2) || v->small.reserve(64 + 4 * (size_t)nparts)) return 1;
+    if (v->block_sums.reserve((size_t)std::max(npix_pad, 1 << 20) / 1024 + 2) || v->small.reserve(64 + 4 * (size_t)nd)) return 1;
     if (!v->d_sample_count) GXY_CUDA(cudaMalloc(&v->d_sample_count, 2 * sizeof(unsigned long long)));  // [0] samples [1] passes (loop mode)
     GXY_CUDA(cudaMemsetAsync(v->d_sample_count, 0, 2 * sizeof(unsigned long long), st));
     v->n_samples = 0;
@@ -1289,11 +1358,11 @@ int gxy_sample(int nparts, gxy_vis *const *parts, const gxy_camera *cam, int w, 
     GXY_CUDA(cudaStreamSynchronize(st));
     S.primary_rays += n_cur[p];
   }
-  std::vector<std::vector<int>> send_counts(nparts, std::vector<int>(nparts, 0)), send_offsets(nparts, std::vector<int>(nparts + 1, 0));
+  std::vector<std::vector<int>> send_counts(nparts, std::vector<int>(nd, 0)), send_offsets(nparts, std::vector<int>(nd + 1, 0));
   for (int wave = 0; wave < 1000000; wave++) {
     long long pending = 0;
     for (int p = 0; p < nparts; p++) pending += n_cur[p];
-    if (pending == 0) break;
+    if (pending == 0 && !multi_proc) break;  // (across processes the exchange below decides: a rank with nothing to trace may still receive)
     for (int p = 0; p < nparts; p++) {
       gxy_vis *v = parts[p];
       std::fill(send_counts[p].begin(), send_counts[p].end(), 0);
@@ -1330,10 +1399,10 @@ int gxy_sample(int nparts, gxy_vis *const *parts, const gxy_camera *cam, int w, 
       }
       if (launch_classify(v->P, v->cur.v, n, st)) return 1;
       if (v->send.reserve((size_t)n, false, st)) return 1;
-      int *d_counts = v->small.p + 8, *d_offsets = d_counts + nparts, *d_cursor = d_offsets + nparts + 1;
-      if (launch_partition_by_destination(v->cur.v, n, nparts, p, v->send.v, d_counts, d_offsets, d_cursor, st)) return 1;
-      GXY_CUDA(cudaMemcpyAsync(send_counts[p].data(), d_counts, sizeof(int) * nparts, cudaMemcpyDeviceToHost, st));
-      GXY_CUDA(cudaMemcpyAsync(send_offsets[p].data(), d_offsets, sizeof(int) * (nparts + 1), cudaMemcpyDeviceToHost, st));
+      int *d_counts = v->small.p + 8, *d_offsets = d_counts + nd, *d_cursor = d_offsets + nd + 1;
+      if (launch_partition_by_destination(v->cur.v, n, nd, multi_proc ? me : p, v->send.v, d_counts, d_offsets, d_cursor, st)) return 1;
+      GXY_CUDA(cudaMemcpyAsync(send_counts[p].data(), d_counts, sizeof(int) * nd, cudaMemcpyDeviceToHost, st));
+      GXY_CUDA(cudaMemcpyAsync(send_offsets[p].data(), d_offsets, sizeof(int) * (nd + 1), cudaMemcpyDeviceToHost, st));
       GXY_CUDA(cudaMemcpyAsync(&v->n_samples, v->d_sample_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
       S.kernel_launches += 5;
       S.traced_rays += n;
@@ -1345,6 +1414,15 @@ int gxy_sample(int nparts, gxy_vis *const *parts, const gxy_camera *cam, int w, 
       GXY_CUDA(cudaStreamSynchronize(parts[p]->ctx->stream));
     }
     std::vector<int> n_next(nparts, 0);
+    if (multi_proc) {
+      long long global_pending = 0;
+      if (nccl_exchange_rays(parts[0], nd, me, send_counts[0].data(), send_offsets[0].data(), &n_next[0], &global_pending, S)) return 1;
+      GXY_CUDA(cudaStreamSynchronize(parts[0]->ctx->stream));
+      std::swap(parts[0]->cur, parts[0]->next);
+      n_cur[0] = n_next[0];
+      if (global_pending == 0) break;
+      continue;
+    }
     for (int src = 0; src < nparts; src++)
       for (int dst = 0; dst < nparts; dst++) {
         const int cnt = send_counts[src][dst];

@@ -268,8 +268,10 @@ int  gxy_sample_raylist(gxy_vis *, gxy_raylist_view rays);
 /* Sampler over a frame of camera rays: Renderer::local_render with Sampler::Trace and Sampler::HandleTerminatedRays
  * (src/sampler/Sampler.cpp:52-133) on the device.  A ray leaves one sample per firing and continues behind it until it
  * reaches the partition's boundary, then moves to the neighbour.  Every partition keeps its samples on the device
- * (as every rank keeps its own Particles in the reference).  One process; stats: primary_rays, traced_rays,
- * forwarded_rays, waves, kernel_launches, device_ms. */
+ * (as every rank keeps its own Particles in the reference).  Either one process drives all partitions (nparts >= 1, no
+ * communicator), or one process per GPU (gxy_comm_init) passes its one partition: rays that cross into a neighbour then
+ * travel as NCCL send/recv pairs and every process must make the call (it is collective; the stats are this process's).
+ * stats: primary_rays, traced_rays, forwarded_rays, waves, kernel_launches, device_ms. */
 int  gxy_sample(int nparts, gxy_vis *const *parts, const gxy_camera *, int w, int h, gxy_stats *stats);
 /* the samples of one partition after gxy_sample: their number; their positions (3 floats each, order unspecified as in
  * the reference, where threads append under a lock); or as a Particles dataset (value 0, Sampler.cpp:83) without
