@@ -2,7 +2,8 @@
 """Throughput of the C5 frame with D frames in flight (gxy_render_submit / gxy_render_wait), the scene built once.
   python tools/flight_sweep.py [tess_div] [steps]                  (one GPU)
   torchrun --nproc-per-node N ... tools/flight_sweep.py [tess_div] (one process per GPU, peer arenas)
-Environment sweeps: FLIGHT_DEPTHS="1,2,4,8"  FLIGHT_ENVS="GXY_BANDS=4;GXY_BANDS=2;GXY_BANDS=1" """
+Environment sweeps: FLIGHT_DEPTHS="1,2,4,8"  FLIGHT_ENVS="GXY_BANDS=4;GXY_BANDS=2;GXY_BANDS=1"
+FLIGHT_TIMELINE=<file>: append one JSON line per (rank, frame) of the last repetition: begin / end of the frame on that rank's device. """
 import json
 import os
 import sys
@@ -94,6 +95,22 @@ for env in envs:
             if world > 1:
                 dist.all_reduce(pr)
             res.append((t[0].item() / steps, t[1].item() / steps, c[1].item() / world, c[0].item(), c[2].item(), [int(x) for x in pr.tolist()]))
+        tl_path = os.environ.get("FLIGHT_TIMELINE")
+        if tl_path:
+            # per-rank timeline of the last repetition: when each frame's first kernel started and its last one ended on this rank's
+            # device, relative to the mark all ranks set behind a barrier (so the origins agree to within the barrier's skew)
+            mine = [dict(frame=k, slot=k % depth, t_begin_ms=round(f["t_begin_ms"], 4), t_end_ms=round(f["t_end_ms"], 4),
+                         trace_ms=round(f["trace_ms"], 4), dequeued_rays=int(f["dequeued_rays"]), waves=int(f["waves"])) for k, f in enumerate(fr)]
+            allr = [None] * world
+            if world > 1:
+                dist.all_gather_object(allr, mine)
+            else:
+                allr = [mine]
+            if rank == 0:
+                with open(tl_path, "a") as fh:
+                    for r, rows in enumerate(allr):
+                        for row in rows:
+                            fh.write(json.dumps(dict(world=world, depth=depth, env=env, rank=r, **row)) + "\n")
         if rank == 0:
             best = min(res)
             print(json.dumps({"world": world, "env": env, "depth": depth, "ms_per_frame_device": round(best[0], 4), "ms_per_frame_wall": round(best[1], 4),
