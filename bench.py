@@ -4,8 +4,10 @@ on the synthetic 100 M-triangle scene (BASELINE.json configs[4], SURVEY 8d "C5")
 node, one process per GPU.
 
   python bench.py --gpus 1 --steps K --warmup W                (our arm, CUDA through the C ABI)
-  python bench.py --impl reference ...                         (CPU arm: the oracle port of the
-                                                                reference's algorithm on host cores)
+  python bench.py --impl reference ...                         (CPU arm on the host cores: the reference's own Embree 3.6.1 from
+                                                                oracle/_ref doing every nearest-hit query of the full scene inside
+                                                                the oracle's restatement of the ISPC glue; the scalar oracle port
+                                                                only if that library is absent)
   torchrun ... bench.py --gpus N ...                           (N>1: spatial partitions + NCCL)
 
 A step is one frame: generation -> trace waves -> shading/secondary rays -> classify -> ray
